@@ -1,0 +1,212 @@
+/*
+ * pagk.h -- C-ABI of the B200-native pixel-aware gyro-aided KLT hot path.
+ *
+ * This is the drop-in boundary for the path
+ *     GyroAidedTracker::TrackFeatures()            (reference src/gyro_aided_tracker.cpp:344-426)
+ *       -> IntegrateGyroMeasurements / SetRcl       (:511-587)
+ *       -> GyroPredictFeatures                      (:118-256)
+ *       -> PatchMatch::OpticalFlowMultiLevel        (reference src/patch_match.cpp:79-142)
+ *            CreatePyramids (:61-76), the per-feature Gauss-Newton loop (:167-367),
+ *            DistortPoints (:409-416), SetMatcher (:370-388)
+ *       -> threshold filter                         (src/gyro_aided_tracker.cpp:289-336)
+ *
+ * The reference has no FFI layer: callers construct a C++ GyroAidedTracker over cv::Mat /
+ * std::vector references (include/gyro_aided_tracker.h:109-126), call TrackFeatures() (:134) and
+ * read public result vectors (:173-259).  This header restates exactly those inputs and outputs as
+ * plain pointers and sizes.  include/pagk_tracker.hpp re-creates the two C++ classes on top of it.
+ *
+ * Everything here is POD; no C++ types, no exceptions cross the boundary.  All entry points return
+ * PAGK_OK (0) or a negative pagk_status.  There is NO CPU fallback behind this ABI: every compute
+ * entry point fails with PAGK_ERR_NO_DEVICE when no CUDA device is usable.
+ */
+#ifndef PAGK_H_
+#define PAGK_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PAGK_VERSION 100
+
+typedef enum pagk_status {
+  PAGK_OK = 0,
+  PAGK_ERR_INVALID = -1,     /* bad argument (null pointer, size out of the handle's limits, ...) */
+  PAGK_ERR_UNSUPPORTED = -2, /* eType 0 (cv::calcOpticalFlowPyrLK baseline), unknown eType, inverse mode */
+  PAGK_ERR_NO_DEVICE = -3,   /* no CUDA device / driver: the product path never falls back to the CPU */
+  PAGK_ERR_CUDA = -4,        /* a CUDA runtime call failed; see pagk_last_error() */
+  PAGK_ERR_NOMEM = -5
+} pagk_status;
+
+/* GyroAidedTracker::eType, reference include/gyro_aided_tracker.h:55-63 */
+enum {
+  PAGK_OPENCV_OPTICAL_FLOW_PYR_LK = 0, /* not provided: returns PAGK_ERR_UNSUPPORTED */
+  PAGK_GYRO_PREDICT = 1,
+  PAGK_GYRO_PREDICT_WITH_OPTICAL_FLOW_REFINED = 2,
+  PAGK_GYRO_PREDICT_WITH_OPTICAL_FLOW_REFINED_CONSIDER_ILLUMINATION = 3,
+  PAGK_GYRO_PREDICT_WITH_OPTICAL_FLOW_REFINED_CONSIDER_ILLUMINATION_DEFORMATION = 4, /* default */
+  PAGK_IMAGE_ONLY_OPTICAL_FLOW_CONSIDER_ILLUMINATION = 5,
+  PAGK_GYRO_PREDICT_WITH_OPTICAL_FLOW_REFINED_CONSIDER_ILLUMINATION_DEFORMATION_REGULAR = 6
+};
+
+/* GyroAidedTracker::ePredictMethod, reference include/gyro_aided_tracker.h:65-68 */
+enum { PAGK_PIXEL_AWARE_PREDICTION = 1, PAGK_SINGLE_HOMOGRAPHY = 2 };
+
+/* Capacity of one handle.  One handle lives on one device; handles on different devices are
+ * independent (multi-GPU = one handle per device, streams sharded by the caller). */
+typedef struct pagk_config {
+  int device;         /* CUDA ordinal */
+  int max_width;      /* largest image, pixels */
+  int max_height;
+  int max_keys;       /* keypoints per frame pair */
+  int max_pairs;      /* frame pairs per pagk_track_batch call */
+  int max_imu;        /* gyro samples per pair */
+  int max_levels;     /* pyramid levels (reference hard-codes 3, src/gyro_aided_tracker.cpp:277) */
+  int max_half_patch; /* reference default 5 (include/gyro_aided_tracker.h:115) */
+} pagk_config;
+
+/* Algorithm parameters.  Defaults (pagk_default_params) are the reference's hard-coded values:
+ * iterations 10 / pyramids 3 / inverse false (src/gyro_aided_tracker.cpp:276-278),
+ * lambda 1, alpha 0.5, max_distance 25 (src/patch_match.cpp:48-50), half_patch 5. */
+typedef struct pagk_params {
+  int e_type;         /* PAGK_* eType */
+  int predict_method; /* PAGK_PIXEL_AWARE_PREDICTION | PAGK_SINGLE_HOMOGRAPHY */
+  int half_patch;     /* 0 means 5, as in GyroAidedTracker::Initialize (:61) */
+  int iterations;
+  int pyramids;
+  int inverse;        /* must be 0: the reference marks the inverse path "not support yet" (src/patch_match.cpp:220) */
+  int calc_ncc;       /* PatchMatch bCalculateNCC_ (include/patch_match.h:49); the tracker never enables it */
+  float lambda;
+  float alpha;
+  int max_distance;
+} pagk_params;
+
+/* Inputs of one frame pair = what the GyroAidedTracker ctor binds (src/gyro_aided_tracker.cpp:30-49). */
+typedef struct pagk_pair_in {
+  const uint8_t *img_ref;   /* mImgGrayRef: CV_8UC1, height rows of `pitch` bytes */
+  const uint8_t *img_cur;   /* mImgGrayCur */
+  int width, height, pitch; /* all pairs of one batch must share width and height */
+  int n_keys;               /* mN = mvKeysRef.size() */
+  const float *keys_ref_un; /* mvKeysRefUn[i].pt, [n_keys][2] */
+  const float *keys_ref;    /* mvKeysRef[i].pt, [n_keys][2]; read only by eType 5 (:266); may be NULL otherwise */
+  int n_imu;                /* mvImuFromLastFrame.size() */
+  const double *imu_t;      /* IMU::Point::t, [n_imu] */
+  const float *imu_w;       /* IMU::Point::w, [n_imu][3] */
+  double t_ref, t_cur;      /* mTimeStampRef, mTimeStamp */
+  float bias_g[3];          /* mBias */
+  float K[9];               /* mK row-major 3x3 */
+  float dist[5];            /* mDistCoef k1 k2 p1 p2 k3 */
+  int n_dist;               /* mDistCoef.total(): k3 is read only when 5 (:70) */
+  float Rbc[9];             /* imuCalib.Tbc(0:3,0:3) row-major */
+  const float *normalize_table; /* mNormalizeTable, CV_32FC2 height x width, or NULL (drivers pass cv::Mat()) */
+  const float *Rcl_override;    /* NULL, or a 3x3 row-major rotation: SetRcl() instead of gyro integration */
+} pagk_pair_in;
+
+/* Outputs of one frame pair = the public result members of GyroAidedTracker
+ * (include/gyro_aided_tracker.h:173-259).  Every pointer is caller-allocated for n_keys entries and
+ * may be NULL when the caller does not want that vector. */
+typedef struct pagk_pair_out {
+  float *pt_predict_un;      /* mvPtPredictUn              [N][2] */
+  float *pt_predict;         /* mvPtPredict                [N][2] */
+  uint8_t *status;           /* mvStatus                   [N]    */
+  float *pt_gyro_predict_un; /* mvPtGyroPredictUn          [N][2] */
+  float *pt_gyro_predict;    /* mvPtGyroPredict            [N][2] */
+  float *flows_predict_un;   /* mvFlowsPredictUn           [N][2] */
+  float *affine;             /* mvAffineDeformationMatrix  [N][4] row-major 2x2; all-zero where the cv::Mat is empty */
+  float *corner_flows;       /* mvvFlowsPredictCorners     [N][4][2] */
+  float *pt_corners_un;      /* mvvPtPredictCornersUn      [N][4][2] */
+  float *pt_corners;         /* mvvPtPredictCorners        [N][4][2] */
+  float *pm_pt_un;           /* mvPtPredictAfterPatchMatchedUn [N][2] */
+  float *pm_pt;              /* mvPtPredictAfterPatchMatched   [N][2] */
+  uint8_t *pm_status;        /* mvStatusAfterPatchMatched  [N] */
+  double *pixel_error;       /* mvPixelErrorsOfPatchMatched [N] */
+  double *distance;          /* mvDistanceBetweenPredictedAndPatchMatched [N] */
+  float *ncc;                /* mvNccAfterPatchMatched     [N] */
+  int32_t *iters;            /* not in the reference: Gauss-Newton passes executed per feature, all levels */
+  float Rcl[9];              /* mRcl */
+  float KRKinv[9];           /* mKRKinv */
+  int n_predict;             /* return value of TrackFeatures() */
+  int64_t n_iterations;      /* sum of iters[] (the throughput unit: feature x iteration) */
+  float t_gyro_predict;      /* mTimeCostGyroPredict,            seconds (device time of the batch / n_pairs) */
+  float t_opt_flow;          /* mTimeCostOptFlow */
+  float t_filter;            /* mTimeCostOptFlowResultFilterOut */
+} pagk_pair_out;
+
+/* Explicit inputs of PatchMatch (include/patch_match.h:44-49): what it reads from the tracker. */
+typedef struct pagk_patch_match_in {
+  const uint8_t *img_ref, *img_cur;
+  int width, height, pitch;
+  int n_keys;
+  const float *keys_ref_un;   /* mpMatcher->mvKeysRefUn[i].pt */
+  const float *pt_predict_un; /* mpMatcher->mvPtPredictUn */
+  const uint8_t *status;      /* mpMatcher->mvStatus at construction (mvGyroPredictStatus) */
+  const float *affine;        /* mpMatcher->mvAffineDeformationMatrix [N][4] */
+  float K[9];
+  float dist[5];
+  int n_dist;
+  int half_patch, iterations, pyramids;
+  int has_gyro_predict_initial, inverse, consider_illumination, consider_affine_deformation,
+      regularization_penalty, calc_ncc;
+  float lambda, alpha;
+  int max_distance;
+} pagk_patch_match_in;
+
+typedef struct pagk_handle pagk_handle;
+
+void pagk_default_params(pagk_params *p);
+int pagk_version(void);
+const char *pagk_last_error(void);
+int pagk_device_count(void);
+
+int pagk_create(const pagk_config *cfg, pagk_handle **out);
+void pagk_destroy(pagk_handle *h);
+
+/* == GyroAidedTracker(...).TrackFeatures() for n_pairs independent frame pairs.
+ * Host buffers in, host buffers out; H2D/D2H copies are inside the call (pinned memory is used
+ * as-is, pageable memory goes through the driver's staging).  out[p].n_predict is -1 and the call
+ * returns PAGK_ERR_UNSUPPORTED for an unsupported eType, as TrackFeatures() returns -1 (:415-418). */
+int pagk_track_batch(pagk_handle *h, const pagk_params *prm, int n_pairs, const pagk_pair_in *in,
+                     pagk_pair_out *out);
+
+/* The same work split so that inputs can stay resident in HBM between runs:
+ *   pagk_upload_batch   H2D of images / keypoints / per-pair constants (gyro integrated on the host)
+ *   pagk_run_resident   the kernels only (pyramid, predict, patch match, filter), asynchronous on
+ *                       the handle's stream; may be called repeatedly on the same resident inputs
+ *   pagk_download_batch D2H of the result vectors (synchronises) */
+int pagk_upload_batch(pagk_handle *h, const pagk_params *prm, int n_pairs, const pagk_pair_in *in);
+int pagk_run_resident(pagk_handle *h);
+int pagk_download_batch(pagk_handle *h, int n_pairs, pagk_pair_out *out);
+int pagk_synchronize(pagk_handle *h);
+/* device time of the last pagk_run_resident, milliseconds (CUDA events on the handle's stream) */
+int pagk_last_run_ms(pagk_handle *h, float *total_ms, float *pyramid_ms, float *predict_ms,
+                     float *lk_ms, float *filter_ms);
+/* the cudaStream_t of the handle, as void* (for callers that time with their own events) */
+void *pagk_stream(pagk_handle *h);
+/* kernels launched by this handle since creation */
+int64_t pagk_launch_count(pagk_handle *h);
+
+/* == PatchMatch::CreatePyramids (src/patch_match.cpp:61-76) on the resident images.
+ * pagk_get_pyramid_level copies level `level` of image `which` (0 = ref, 1 = cur) of pair `pair`
+ * back to the host as a continuous cols x rows buffer. */
+int pagk_build_pyramids(pagk_handle *h, int n_images, const uint8_t *const *imgs, int width, int height,
+                        int pitch, int levels);
+int pagk_pyramid_level_size(int width, int height, int level, int *cols, int *rows);
+int pagk_get_pyramid_level(pagk_handle *h, int image, int level, uint8_t *dst, size_t dst_bytes);
+
+/* == IntegrateGyroMeasurements + SetRcl (src/gyro_aided_tracker.cpp:511-587). Host arithmetic
+ * (about ten 3x3 products per pair; uses libm sinf/cosf exactly like the reference). */
+int pagk_integrate_gyro(const pagk_pair_in *in, float Rcl[9], float KRKinv[9]);
+
+/* == GyroPredictFeatures (src/gyro_aided_tracker.cpp:118-185) for one pair, given Rcl. */
+int pagk_gyro_predict(pagk_handle *h, const pagk_params *prm, const pagk_pair_in *in, pagk_pair_out *out);
+
+/* == PatchMatch(...).OpticalFlowMultiLevel() (src/patch_match.cpp:79-142) for one pair with explicit
+ * inputs; fills pm_pt_un, pm_pt, pm_status, pixel_error, distance, ncc, iters of `out`. */
+int pagk_patch_match(pagk_handle *h, const pagk_patch_match_in *in, pagk_pair_out *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PAGK_H_ */

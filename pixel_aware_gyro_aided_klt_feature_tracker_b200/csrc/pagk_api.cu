@@ -1,0 +1,592 @@
+// pagk_api.cu -- the C-ABI of include/pagk.h: handle, HBM layout, copies, kernel sequencing.
+//
+// HBM layout of one handle (all allocated once in pagk_create, sized by pagk_config):
+//   images   [2 * max_pairs] slots; a slot holds every pyramid level of one image, each level
+//            continuous (step == cols) + one guard row + 1 byte, level bases 256-byte aligned.
+//            Slot 2p is the reference image of pair p, slot 2p+1 the current image.
+//   keys     float2 [max_pairs][max_keys] x 2 (undistorted, raw)
+//   consts   PagkPairConst [max_pairs]   (KRK^-1, r31..r33, intrinsics, distortion, n_keys)
+//   results  structure of arrays [max_pairs][max_keys] (PagkOutPtrs), PagkPairResult [max_pairs]
+// Host side: one pinned staging block mirrors keys+consts (upload) and one mirrors the results
+// (download) so that a batch moves with a handful of large copies.
+#include "../../include/pagk.h"
+#include "pagk_host_math.h"
+#include "pagk_kernels.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, const char *a = "", const char *b = "") {
+  snprintf(g_err, sizeof(g_err), fmt, a, b);
+  return code;
+}
+
+#define CU(call)                                                                       \
+  do {                                                                                 \
+    cudaError_t e__ = (call);                                                          \
+    if (e__ != cudaSuccess) return fail(PAGK_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__)); \
+  } while (0)
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+bool make_geom(int width, int height, int levels, PagkGeom *g) {
+  if (levels < 1 || levels > PAGK_MAX_LEVELS || width < 1 || height < 1) return false;
+  g->levels = levels; g->width = width; g->height = height;
+  size_t off = 0;
+  int c = width, r = height;
+  for (int l = 0; l < levels; ++l) {
+    if (c < 1 || r < 1) return false;
+    g->lv[l].cols = c; g->lv[l].rows = r; g->lv[l].offset = (unsigned int)off;
+    off += align_up((size_t)(r + 1) * c + 1, 256);
+    c = (int)(c * 0.5); r = (int)(r * 0.5);  // cv::Size(cols * 0.5, rows * 0.5), reference src/patch_match.cpp:69
+  }
+  for (int l = levels; l < PAGK_MAX_LEVELS; ++l) g->lv[l] = PagkLevelGeom{0, 0, 0};
+  g->slot_bytes = off;
+  return true;
+}
+
+enum OutKind {
+  O_PT_PREDICT_UN, O_PT_PREDICT, O_PT_GYRO_UN, O_PT_GYRO, O_FLOWS, O_AFFINE, O_CFLOWS, O_CORNERS_UN, O_CORNERS,
+  O_PM_UN, O_PM, O_STATUS, O_PM_STATUS, O_GYRO_STATUS, O_PIX_ERR, O_DIST, O_NCC, O_ITERS, O_COUNT
+};
+const size_t kOutElt[O_COUNT] = {8, 8, 8, 8, 8, 16, 32, 32, 32, 8, 8, 1, 1, 1, 8, 8, 4, 4};
+
+}  // namespace
+
+struct pagk_handle {
+  pagk_config cfg;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t slot_capacity = 0;
+  unsigned char *d_images = nullptr;
+  float2 *d_keys_un = nullptr, *d_keys = nullptr;
+  PagkPairConst *d_pc = nullptr;
+  PagkPairResult *d_res = nullptr;
+  unsigned char *d_out = nullptr;
+  size_t out_off[O_COUNT];
+  size_t out_bytes = 0;
+  float *d_ntab = nullptr;
+  size_t ntab_stride = 0;  // floats per pair
+  // pinned staging
+  unsigned char *h_in = nullptr;   // keys_un | keys | consts
+  size_t h_in_keys_un = 0, h_in_keys = 0, h_in_pc = 0, h_in_bytes = 0;
+  unsigned char *h_out = nullptr;  // mirror of d_out
+  PagkPairResult *h_res = nullptr;
+  // state of the resident batch
+  PagkGeom geom;
+  PagkMode mode;
+  int n_pairs = 0, n_max = 0, e_type = 0;
+  bool resident = false, ran = false;
+  std::vector<PagkPairConst> pcs;
+  std::vector<float> rcl, krk;  // [n_pairs][9]
+  long long launches = 0;
+  float ms[5] = {0, 0, 0, 0, 0};
+
+  PagkOutPtrs outs() const {
+    PagkOutPtrs o;
+    o.pt_predict_un = (float2 *)(d_out + out_off[O_PT_PREDICT_UN]); o.pt_predict = (float2 *)(d_out + out_off[O_PT_PREDICT]);
+    o.pt_gyro_un = (float2 *)(d_out + out_off[O_PT_GYRO_UN]); o.pt_gyro = (float2 *)(d_out + out_off[O_PT_GYRO]);
+    o.flows = (float2 *)(d_out + out_off[O_FLOWS]); o.affine = (float4 *)(d_out + out_off[O_AFFINE]);
+    o.cflows = (float2 *)(d_out + out_off[O_CFLOWS]); o.corners_un = (float2 *)(d_out + out_off[O_CORNERS_UN]);
+    o.corners = (float2 *)(d_out + out_off[O_CORNERS]); o.pm_un = (float2 *)(d_out + out_off[O_PM_UN]);
+    o.pm = (float2 *)(d_out + out_off[O_PM]); o.status = d_out + out_off[O_STATUS];
+    o.pm_status = d_out + out_off[O_PM_STATUS]; o.gyro_status = d_out + out_off[O_GYRO_STATUS];
+    o.pix_err = (double *)(d_out + out_off[O_PIX_ERR]); o.dist = (double *)(d_out + out_off[O_DIST]);
+    o.ncc = (float *)(d_out + out_off[O_NCC]); o.iters = (int *)(d_out + out_off[O_ITERS]);
+    return o;
+  }
+};
+
+namespace {
+
+int mode_from_etype(int e_type, PagkMode *m) {
+  switch (e_type) {  // reference src/gyro_aided_tracker.cpp:384-414
+    case PAGK_IMAGE_ONLY_OPTICAL_FLOW_CONSIDER_ILLUMINATION: m->gyro_init = 0; m->illum = 1; m->affine = 1; m->regular = 0; return 0;
+    case PAGK_GYRO_PREDICT_WITH_OPTICAL_FLOW_REFINED: m->gyro_init = 1; m->illum = 0; m->affine = 0; m->regular = 0; return 0;
+    case PAGK_GYRO_PREDICT_WITH_OPTICAL_FLOW_REFINED_CONSIDER_ILLUMINATION: m->gyro_init = 1; m->illum = 1; m->affine = 0; m->regular = 0; return 0;
+    case PAGK_GYRO_PREDICT_WITH_OPTICAL_FLOW_REFINED_CONSIDER_ILLUMINATION_DEFORMATION: m->gyro_init = 1; m->illum = 1; m->affine = 1; m->regular = 0; return 0;
+    case PAGK_GYRO_PREDICT_WITH_OPTICAL_FLOW_REFINED_CONSIDER_ILLUMINATION_DEFORMATION_REGULAR: m->gyro_init = 1; m->illum = 1; m->affine = 1; m->regular = 1; return 0;
+    case PAGK_GYRO_PREDICT: m->gyro_init = 1; m->illum = 0; m->affine = 0; m->regular = 0; return 0;
+    default: return -1;
+  }
+}
+
+void fill_mode_common(PagkMode *m, int half, int iterations, int levels, int calc_ncc, int predict_method, float lambda,
+                      float alpha, int max_distance) {
+  m->half = half; m->iterations = iterations; m->levels = levels; m->calc_ncc = calc_ncc;
+  m->predict_method = predict_method; m->lambda = lambda; m->alpha = alpha;
+  // PatchMatch ctor, reference src/patch_match.cpp:51,57
+  m->inv_log_max_dist = (float)(1.0 / (double)logf(alpha * (float)max_distance + 1.0f));
+  m->win_size_inv = (double)(1.0f / (2.0f * half + 1.0f) / (2.0f * half + 1.0f));
+  m->bb_inv = pagk_host::bbt_inverse_diag(half);
+}
+
+// GyroAidedTracker::Initialize caches (:64-70) + IntegrateGyroMeasurements/SetRcl
+void pair_const(const pagk_pair_in &in, PagkPairConst *pc, float Rcl[9], float KRK[9]) {
+  using namespace pagk_host;
+  const Mat3 K = from_array(in.K);
+  Mat3 R;
+  if (in.Rcl_override) R = from_array(in.Rcl_override);
+  else R = integrate(in.n_imu, in.imu_t, in.imu_w, in.t_ref, in.t_cur, in.bias_g, from_array(in.Rbc));
+  const Mat3 M = krkinv(K, R);
+  std::memcpy(Rcl, R.v, 9 * sizeof(float));
+  std::memcpy(KRK, M.v, 9 * sizeof(float));
+  std::memcpy(pc->M, M.v, 9 * sizeof(float));
+  pc->r31 = R.v[2][0]; pc->r32 = R.v[2][1]; pc->r33 = R.v[2][2];
+  pc->fx = in.K[0]; pc->fy = in.K[4]; pc->cx = in.K[2]; pc->cy = in.K[5];
+  pc->fx_inv = (float)(1.0 / pc->fx); pc->fy_inv = (float)(1.0 / pc->fy);
+  pc->k1 = in.dist[0]; pc->k2 = in.dist[1]; pc->p1 = in.dist[2]; pc->p2 = in.dist[3];
+  pc->k3 = (in.n_dist == 5) ? in.dist[4] : 0.0f;
+  pc->n_keys = in.n_keys;
+  pc->has_table = in.normalize_table ? 1 : 0;
+}
+
+int upload_images(pagk_handle *h, int n_pairs, const uint8_t *const *refs, const uint8_t *const *curs, int width,
+                  int height, const int *pitches) {
+  const PagkGeom &g = h->geom;
+  const size_t img_bytes = (size_t)width * height;
+  bool contiguous = true;
+  for (int p = 0; p < n_pairs && contiguous; ++p) {
+    if (pitches[p] != width) contiguous = false;
+    if (curs[p] != refs[p] + img_bytes) contiguous = false;
+    if (p + 1 < n_pairs && refs[p + 1] != curs[p] + img_bytes) contiguous = false;
+  }
+  if (contiguous && n_pairs > 0) {  // [n_pairs][2][H][W] in one strided copy
+    CU(cudaMemcpy2DAsync(h->d_images + g.lv[0].offset, g.slot_bytes, refs[0], img_bytes, img_bytes, (size_t)2 * n_pairs,
+                         cudaMemcpyHostToDevice, h->stream));
+    return PAGK_OK;
+  }
+  for (int p = 0; p < n_pairs; ++p) {
+    CU(cudaMemcpy2DAsync(h->d_images + (size_t)(2 * p) * g.slot_bytes + g.lv[0].offset, width, refs[p], pitches[p], width,
+                         height, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpy2DAsync(h->d_images + (size_t)(2 * p + 1) * g.slot_bytes + g.lv[0].offset, width, curs[p], pitches[p],
+                         width, height, cudaMemcpyHostToDevice, h->stream));
+  }
+  return PAGK_OK;
+}
+
+int check_batch(pagk_handle *h, int n_pairs, int width, int height, int levels, int half) {
+  if (!h) return fail(PAGK_ERR_INVALID, "null handle");
+  if (n_pairs < 0 || n_pairs > h->cfg.max_pairs) return fail(PAGK_ERR_INVALID, "n_pairs exceeds pagk_config.max_pairs");
+  if (levels < 1 || levels > h->cfg.max_levels) return fail(PAGK_ERR_INVALID, "pyramids exceeds pagk_config.max_levels");
+  if (half < 1 || half > h->cfg.max_half_patch) return fail(PAGK_ERR_INVALID, "half_patch exceeds pagk_config.max_half_patch");
+  PagkGeom g;
+  if (!make_geom(width, height, levels, &g)) return fail(PAGK_ERR_INVALID, "image too small for the requested pyramid");
+  if (g.slot_bytes > h->slot_capacity) return fail(PAGK_ERR_INVALID, "image exceeds pagk_config.max_width/max_height");
+  if (pagk_lk_smem_per_warp(half) > 227 * 1024) return fail(PAGK_ERR_INVALID, "half_patch too large for shared memory");
+  h->geom = g;
+  return PAGK_OK;
+}
+
+template <class T>
+void scatter(const pagk_handle *h, OutKind k, int n_pairs, const std::vector<int> &nk, T *const *dst) {
+  for (int p = 0; p < n_pairs; ++p)
+    if (dst[p]) std::memcpy(dst[p], h->h_out + h->out_off[k] + (size_t)p * h->cfg.max_keys * kOutElt[k], (size_t)nk[p] * kOutElt[k]);
+}
+
+}  // namespace
+
+extern "C" {
+
+void pagk_default_params(pagk_params *p) {
+  if (!p) return;
+  p->e_type = PAGK_GYRO_PREDICT_WITH_OPTICAL_FLOW_REFINED_CONSIDER_ILLUMINATION_DEFORMATION;
+  p->predict_method = PAGK_PIXEL_AWARE_PREDICTION;
+  p->half_patch = 5; p->iterations = 10; p->pyramids = 3; p->inverse = 0; p->calc_ncc = 0;
+  p->lambda = 1.0f; p->alpha = 0.5f; p->max_distance = 25;
+}
+
+int pagk_version(void) { return PAGK_VERSION; }
+const char *pagk_last_error(void) { return g_err; }
+
+int pagk_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int pagk_create(const pagk_config *cfg, pagk_handle **out) {
+  if (!cfg || !out) return fail(PAGK_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (cfg->max_width < 1 || cfg->max_height < 1 || cfg->max_keys < 1 || cfg->max_pairs < 1 || cfg->max_levels < 1 ||
+      cfg->max_levels > PAGK_MAX_LEVELS || cfg->max_half_patch < 1)
+    return fail(PAGK_ERR_INVALID, "bad pagk_config");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(PAGK_ERR_NO_DEVICE, "no CUDA device: the pagk hot path has no CPU fallback");
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(PAGK_ERR_INVALID, "pagk_config.device out of range");
+  CU(cudaSetDevice(cfg->device));
+  pagk_handle *h = new (std::nothrow) pagk_handle();
+  if (!h) return fail(PAGK_ERR_NOMEM, "out of host memory");
+  h->cfg = *cfg;
+  PagkGeom g;
+  // capacity: the requested number of levels on the largest image, every level present
+  int lv = cfg->max_levels;
+  while (lv > 1 && !make_geom(cfg->max_width, cfg->max_height, lv, &g)) --lv;
+  make_geom(cfg->max_width, cfg->max_height, lv, &g);
+  h->slot_capacity = g.slot_bytes + 256 * (size_t)cfg->max_levels;
+  const size_t NK = (size_t)cfg->max_pairs * cfg->max_keys;
+  size_t off = 0;
+  for (int k = 0; k < O_COUNT; ++k) { h->out_off[k] = off; off += align_up(NK * kOutElt[k], 256); }
+  h->out_bytes = off;
+  h->h_in_keys_un = 0;
+  h->h_in_keys = align_up(NK * sizeof(float2), 256);
+  h->h_in_pc = h->h_in_keys + align_up(NK * sizeof(float2), 256);
+  h->h_in_bytes = h->h_in_pc + align_up((size_t)cfg->max_pairs * sizeof(PagkPairConst), 256);
+  cudaError_t e = cudaSuccess;
+  auto ok = [&](cudaError_t r) { if (e == cudaSuccess && r != cudaSuccess) e = r; return r == cudaSuccess; };
+  ok(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 6; ++i) ok(cudaEventCreate(&h->ev[i]));
+  ok(cudaMalloc(&h->d_images, h->slot_capacity * 2 * (size_t)cfg->max_pairs));
+  ok(cudaMalloc(&h->d_keys_un, NK * sizeof(float2)));
+  ok(cudaMalloc(&h->d_keys, NK * sizeof(float2)));
+  ok(cudaMalloc(&h->d_pc, (size_t)cfg->max_pairs * sizeof(PagkPairConst)));
+  ok(cudaMalloc(&h->d_res, (size_t)cfg->max_pairs * sizeof(PagkPairResult)));
+  ok(cudaMalloc(&h->d_out, h->out_bytes));
+  ok(cudaMallocHost(&h->h_in, h->h_in_bytes));
+  ok(cudaMallocHost(&h->h_out, h->out_bytes));
+  ok(cudaMallocHost(&h->h_res, (size_t)cfg->max_pairs * sizeof(PagkPairResult)));
+  if (e == cudaSuccess) ok(cudaMemsetAsync(h->d_out, 0, h->out_bytes, h->stream));
+  if (e == cudaSuccess) ok(cudaStreamSynchronize(h->stream));
+  if (e != cudaSuccess) {
+    const int code = (e == cudaErrorMemoryAllocation) ? PAGK_ERR_NOMEM : PAGK_ERR_CUDA;
+    fail(code, "pagk_create: %s", cudaGetErrorString(e));
+    pagk_destroy(h);
+    return code;
+  }
+  *out = h;
+  return PAGK_OK;
+}
+
+void pagk_destroy(pagk_handle *h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  cudaFree(h->d_images); cudaFree(h->d_keys_un); cudaFree(h->d_keys); cudaFree(h->d_pc); cudaFree(h->d_res);
+  cudaFree(h->d_out); cudaFree(h->d_ntab);
+  cudaFreeHost(h->h_in); cudaFreeHost(h->h_out); cudaFreeHost(h->h_res);
+  for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  cudaGetLastError();
+  delete h;
+}
+
+int pagk_upload_batch(pagk_handle *h, const pagk_params *prm, int n_pairs, const pagk_pair_in *in) {
+  if (!h || !prm || (n_pairs > 0 && !in)) return fail(PAGK_ERR_INVALID, "null argument");
+  h->resident = false; h->ran = false;
+  PagkMode m;
+  std::memset(&m, 0, sizeof(m));
+  if (prm->e_type == PAGK_OPENCV_OPTICAL_FLOW_PYR_LK)
+    return fail(PAGK_ERR_UNSUPPORTED, "eType 0 (cv::calcOpticalFlowPyrLK comparison baseline) is not part of the hot path");
+  if (mode_from_etype(prm->e_type, &m) != 0) return fail(PAGK_ERR_UNSUPPORTED, "Unsupport type!!! return -1;");
+  if (prm->inverse) return fail(PAGK_ERR_UNSUPPORTED, "inverse mode is \"not support yet\" in the reference (src/patch_match.cpp:220)");
+  if (prm->predict_method != PAGK_PIXEL_AWARE_PREDICTION && prm->predict_method != PAGK_SINGLE_HOMOGRAPHY)
+    return fail(PAGK_ERR_INVALID, "bad predict_method");
+  const int half = prm->half_patch == 0 ? 5 : prm->half_patch;  // Initialize(), :61
+  if (n_pairs == 0) { h->n_pairs = 0; h->resident = true; return PAGK_OK; }
+  const int W = in[0].width, H = in[0].height;
+  int rc = check_batch(h, n_pairs, W, H, prm->pyramids, half);
+  if (rc != PAGK_OK) return rc;
+  if (prm->iterations < 0) return fail(PAGK_ERR_INVALID, "iterations < 0");
+  fill_mode_common(&m, half, prm->iterations, prm->pyramids, prm->calc_ncc, prm->predict_method, prm->lambda, prm->alpha,
+                   prm->max_distance);
+  CU(cudaSetDevice(h->cfg.device));
+  h->pcs.assign(n_pairs, PagkPairConst());
+  h->rcl.assign((size_t)n_pairs * 9, 0.f); h->krk.assign((size_t)n_pairs * 9, 0.f);
+  int n_max = 0;
+  bool any_table = false;
+  std::vector<const uint8_t *> refs(n_pairs), curs(n_pairs);
+  std::vector<int> pitches(n_pairs);
+  CU(cudaStreamSynchronize(h->stream));  // the pinned staging block may still feed an earlier copy
+  float2 *s_un = (float2 *)(h->h_in + h->h_in_keys_un), *s_k = (float2 *)(h->h_in + h->h_in_keys);
+  for (int p = 0; p < n_pairs; ++p) {
+    const pagk_pair_in &q = in[p];
+    if (q.width != W || q.height != H) return fail(PAGK_ERR_INVALID, "all pairs of a batch must share width and height");
+    if (!q.img_ref || !q.img_cur || q.pitch < W) return fail(PAGK_ERR_INVALID, "bad image pointer or pitch");
+    if (q.n_keys < 0 || q.n_keys > h->cfg.max_keys) return fail(PAGK_ERR_INVALID, "n_keys exceeds pagk_config.max_keys");
+    if (q.n_keys > 0 && !q.keys_ref_un) return fail(PAGK_ERR_INVALID, "keys_ref_un is null");
+    if (!m.gyro_init && q.n_keys > 0 && !q.keys_ref) return fail(PAGK_ERR_INVALID, "eType 5 reads keys_ref");
+    if (!q.Rcl_override && (q.n_imu < 0 || (q.n_imu > 0 && (!q.imu_t || !q.imu_w)))) return fail(PAGK_ERR_INVALID, "bad imu arrays");
+    pair_const(q, &h->pcs[p], &h->rcl[(size_t)p * 9], &h->krk[(size_t)p * 9]);
+    n_max = q.n_keys > n_max ? q.n_keys : n_max;
+    any_table |= (q.normalize_table != nullptr);
+    refs[p] = q.img_ref; curs[p] = q.img_cur; pitches[p] = q.pitch;
+    std::memcpy(s_un + (size_t)p * h->cfg.max_keys, q.keys_ref_un, (size_t)q.n_keys * sizeof(float2));
+    if (q.keys_ref) std::memcpy(s_k + (size_t)p * h->cfg.max_keys, q.keys_ref, (size_t)q.n_keys * sizeof(float2));
+  }
+  std::memcpy(h->h_in + h->h_in_pc, h->pcs.data(), (size_t)n_pairs * sizeof(PagkPairConst));
+  const size_t key_bytes = (size_t)n_pairs * h->cfg.max_keys * sizeof(float2);
+  CU(cudaMemcpyAsync(h->d_keys_un, s_un, key_bytes, cudaMemcpyHostToDevice, h->stream));
+  if (!m.gyro_init) CU(cudaMemcpyAsync(h->d_keys, s_k, key_bytes, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->d_pc, h->h_in + h->h_in_pc, (size_t)n_pairs * sizeof(PagkPairConst), cudaMemcpyHostToDevice, h->stream));
+  if (any_table) {
+    const size_t per = (size_t)W * H * 2;
+    if (!h->d_ntab || h->ntab_stride < per) {
+      cudaFree(h->d_ntab); h->d_ntab = nullptr;
+      h->ntab_stride = (size_t)h->cfg.max_width * h->cfg.max_height * 2;
+      CU(cudaMalloc(&h->d_ntab, h->ntab_stride * sizeof(float) * h->cfg.max_pairs));
+    }
+    for (int p = 0; p < n_pairs; ++p)
+      if (in[p].normalize_table)
+        CU(cudaMemcpyAsync(h->d_ntab + (size_t)p * h->ntab_stride, in[p].normalize_table, per * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  }
+  rc = upload_images(h, n_pairs, refs.data(), curs.data(), W, H, pitches.data());
+  if (rc != PAGK_OK) return rc;
+  h->mode = m; h->n_pairs = n_pairs; h->n_max = n_max; h->e_type = prm->e_type;
+  h->resident = true;
+  return PAGK_OK;
+}
+
+int pagk_run_resident(pagk_handle *h) {
+  if (!h) return fail(PAGK_ERR_INVALID, "null handle");
+  if (!h->resident) return fail(PAGK_ERR_INVALID, "pagk_run_resident: no resident batch (call pagk_upload_batch)");
+  if (h->n_pairs == 0) { h->ran = true; return PAGK_OK; }
+  CU(cudaSetDevice(h->cfg.device));
+  const PagkOutPtrs o = h->outs();
+  cudaStream_t st = h->stream;
+  const bool lk = (h->e_type != PAGK_GYRO_PREDICT);
+  CU(cudaEventRecord(h->ev[0], st));
+  if (lk) CU((cudaError_t)pagk_launch_pyramids(h->d_images, h->geom, 2 * h->n_pairs, st, &h->launches));
+  CU(cudaEventRecord(h->ev[1], st));
+  CU((cudaError_t)pagk_launch_predict(h->d_pc, h->d_keys_un, h->d_keys, o, h->mode, h->cfg.max_keys, h->n_max, h->n_pairs,
+                                      h->geom.width, h->geom.height, h->d_ntab, h->ntab_stride, st, &h->launches));
+  CU(cudaEventRecord(h->ev[2], st));
+  if (lk) CU((cudaError_t)pagk_launch_lk(h->d_images, h->geom, h->d_pc, h->d_keys_un, o, h->mode, h->cfg.max_keys, h->n_max,
+                                         h->n_pairs, st, &h->launches));
+  CU(cudaEventRecord(h->ev[3], st));
+  if (lk) CU((cudaError_t)pagk_launch_epilogue(h->d_pc, o, h->mode, h->cfg.max_keys, h->n_pairs, h->d_res, 1, st, &h->launches));
+  else {
+    // eType 1 never constructs a PatchMatch: its six result vectors stay empty in the reference
+    const size_t NK = (size_t)h->n_pairs * h->cfg.max_keys;
+    for (int k : {O_PM_UN, O_PM, O_PM_STATUS, O_PIX_ERR, O_DIST, O_NCC, O_ITERS})
+      CU(cudaMemsetAsync(h->d_out + h->out_off[k], 0, NK * kOutElt[k], st));
+    CU((cudaError_t)pagk_launch_count_status(h->d_pc, o, h->cfg.max_keys, h->n_pairs, h->d_res, st, &h->launches));
+  }
+  CU(cudaEventRecord(h->ev[4], st));
+  h->ran = true;
+  return PAGK_OK;
+}
+
+int pagk_synchronize(pagk_handle *h) {
+  if (!h) return fail(PAGK_ERR_INVALID, "null handle");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaStreamSynchronize(h->stream));
+  return PAGK_OK;
+}
+
+int pagk_last_run_ms(pagk_handle *h, float *total_ms, float *pyramid_ms, float *predict_ms, float *lk_ms, float *filter_ms) {
+  if (!h || !h->ran) return fail(PAGK_ERR_INVALID, "no run to time");
+  if (h->n_pairs == 0) { if (total_ms) *total_ms = 0; return PAGK_OK; }
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaEventSynchronize(h->ev[4]));
+  float t[5];
+  CU(cudaEventElapsedTime(&t[0], h->ev[0], h->ev[4]));
+  for (int i = 0; i < 4; ++i) CU(cudaEventElapsedTime(&t[i + 1], h->ev[i], h->ev[i + 1]));
+  if (total_ms) *total_ms = t[0];
+  if (pyramid_ms) *pyramid_ms = t[1];
+  if (predict_ms) *predict_ms = t[2];
+  if (lk_ms) *lk_ms = t[3];
+  if (filter_ms) *filter_ms = t[4];
+  return PAGK_OK;
+}
+
+void *pagk_stream(pagk_handle *h) { return h ? (void *)h->stream : nullptr; }
+int64_t pagk_launch_count(pagk_handle *h) { return h ? h->launches : 0; }
+
+int pagk_download_batch(pagk_handle *h, int n_pairs, pagk_pair_out *out) {
+  if (!h || (n_pairs > 0 && !out)) return fail(PAGK_ERR_INVALID, "null argument");
+  if (!h->ran || n_pairs != h->n_pairs) return fail(PAGK_ERR_INVALID, "pagk_download_batch: no finished run of that size");
+  if (n_pairs == 0) return PAGK_OK;
+  CU(cudaSetDevice(h->cfg.device));
+  std::vector<int> nk(n_pairs);
+  for (int p = 0; p < n_pairs; ++p) nk[p] = h->pcs[p].n_keys;
+  // which result vectors does the caller want, and can they be copied straight into its memory?
+  struct Want { OutKind k; size_t field_off; };
+  static const Want wants[] = {
+      {O_PT_PREDICT_UN, offsetof(pagk_pair_out, pt_predict_un)}, {O_PT_PREDICT, offsetof(pagk_pair_out, pt_predict)},
+      {O_STATUS, offsetof(pagk_pair_out, status)}, {O_PT_GYRO_UN, offsetof(pagk_pair_out, pt_gyro_predict_un)},
+      {O_PT_GYRO, offsetof(pagk_pair_out, pt_gyro_predict)}, {O_FLOWS, offsetof(pagk_pair_out, flows_predict_un)},
+      {O_AFFINE, offsetof(pagk_pair_out, affine)}, {O_CFLOWS, offsetof(pagk_pair_out, corner_flows)},
+      {O_CORNERS_UN, offsetof(pagk_pair_out, pt_corners_un)}, {O_CORNERS, offsetof(pagk_pair_out, pt_corners)},
+      {O_PM_UN, offsetof(pagk_pair_out, pm_pt_un)}, {O_PM, offsetof(pagk_pair_out, pm_pt)},
+      {O_PM_STATUS, offsetof(pagk_pair_out, pm_status)}, {O_PIX_ERR, offsetof(pagk_pair_out, pixel_error)},
+      {O_DIST, offsetof(pagk_pair_out, distance)}, {O_NCC, offsetof(pagk_pair_out, ncc)}, {O_ITERS, offsetof(pagk_pair_out, iters)}};
+  const int NW = (int)(sizeof(wants) / sizeof(wants[0]));
+  std::vector<char> staged(NW, 0);
+  auto field = [&](int p, size_t off) { return *reinterpret_cast<unsigned char *const *>(reinterpret_cast<const char *>(&out[p]) + off); };
+  for (int w = 0; w < NW; ++w) {
+    const size_t elt = kOutElt[wants[w].k];
+    bool any = false, direct = true;
+    for (int p = 0; p < n_pairs; ++p) {
+      unsigned char *d = field(p, wants[w].field_off);
+      if (d) any = true;
+      if (!d || nk[p] != h->cfg.max_keys || d != field(0, wants[w].field_off) + (size_t)p * h->cfg.max_keys * elt) direct = false;
+    }
+    if (!any) continue;
+    const size_t bytes = (size_t)n_pairs * h->cfg.max_keys * elt;
+    if (direct) {
+      CU(cudaMemcpyAsync(field(0, wants[w].field_off), h->d_out + h->out_off[wants[w].k], bytes, cudaMemcpyDeviceToHost, h->stream));
+    } else {
+      CU(cudaMemcpyAsync(h->h_out + h->out_off[wants[w].k], h->d_out + h->out_off[wants[w].k], bytes, cudaMemcpyDeviceToHost, h->stream));
+      staged[w] = 1;
+    }
+  }
+  CU(cudaMemcpyAsync(h->h_res, h->d_res, (size_t)n_pairs * sizeof(PagkPairResult), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  for (int w = 0; w < NW; ++w) {
+    if (!staged[w]) continue;
+    const size_t elt = kOutElt[wants[w].k];
+    for (int p = 0; p < n_pairs; ++p) {
+      unsigned char *d = field(p, wants[w].field_off);
+      if (d) std::memcpy(d, h->h_out + h->out_off[wants[w].k] + (size_t)p * h->cfg.max_keys * elt, (size_t)nk[p] * elt);
+    }
+  }
+  float t[5] = {0, 0, 0, 0, 0};
+  pagk_last_run_ms(h, &t[0], &t[1], &t[2], &t[3], &t[4]);
+  for (int p = 0; p < n_pairs; ++p) {
+    std::memcpy(out[p].Rcl, &h->rcl[(size_t)p * 9], 9 * sizeof(float));
+    std::memcpy(out[p].KRKinv, &h->krk[(size_t)p * 9], 9 * sizeof(float));
+    out[p].n_predict = h->h_res[p].n_predict;
+    out[p].n_iterations = h->h_res[p].n_iterations;
+    // per-pair share of the batch's device time, seconds (the reference records wall time per tracker)
+    out[p].t_gyro_predict = t[2] * 1e-3f / n_pairs;
+    out[p].t_opt_flow = (t[1] + t[3]) * 1e-3f / n_pairs;
+    out[p].t_filter = t[4] * 1e-3f / n_pairs;
+  }
+  return PAGK_OK;
+}
+
+int pagk_track_batch(pagk_handle *h, const pagk_params *prm, int n_pairs, const pagk_pair_in *in, pagk_pair_out *out) {
+  int rc = pagk_upload_batch(h, prm, n_pairs, in);
+  if (rc != PAGK_OK) {
+    if (rc == PAGK_ERR_UNSUPPORTED && out)
+      for (int p = 0; p < n_pairs; ++p) out[p].n_predict = -1;  // TrackFeatures() returns -1 (:415-418)
+    return rc;
+  }
+  rc = pagk_run_resident(h);
+  if (rc != PAGK_OK) return rc;
+  return pagk_download_batch(h, n_pairs, out);
+}
+
+int pagk_pyramid_level_size(int width, int height, int level, int *cols, int *rows) {
+  PagkGeom g;
+  if (level < 0 || level >= PAGK_MAX_LEVELS || !make_geom(width, height, level + 1, &g)) return fail(PAGK_ERR_INVALID, "bad level");
+  if (cols) *cols = g.lv[level].cols;
+  if (rows) *rows = g.lv[level].rows;
+  return PAGK_OK;
+}
+
+int pagk_build_pyramids(pagk_handle *h, int n_images, const uint8_t *const *imgs, int width, int height, int pitch, int levels) {
+  if (!h || !imgs) return fail(PAGK_ERR_INVALID, "null argument");
+  if (n_images < 1 || n_images > 2 * h->cfg.max_pairs) return fail(PAGK_ERR_INVALID, "n_images exceeds 2 * max_pairs");
+  int rc = check_batch(h, 1, width, height, levels, 1);
+  if (rc != PAGK_OK) return rc;
+  CU(cudaSetDevice(h->cfg.device));
+  h->resident = false; h->ran = false;
+  for (int i = 0; i < n_images; ++i) {
+    if (!imgs[i] || pitch < width) return fail(PAGK_ERR_INVALID, "bad image pointer or pitch");
+    CU(cudaMemcpy2DAsync(h->d_images + (size_t)i * h->geom.slot_bytes + h->geom.lv[0].offset, width, imgs[i], pitch, width,
+                         height, cudaMemcpyHostToDevice, h->stream));
+  }
+  CU((cudaError_t)pagk_launch_pyramids(h->d_images, h->geom, n_images, h->stream, &h->launches));
+  CU(cudaStreamSynchronize(h->stream));
+  return PAGK_OK;
+}
+
+int pagk_get_pyramid_level(pagk_handle *h, int image, int level, uint8_t *dst, size_t dst_bytes) {
+  if (!h || !dst) return fail(PAGK_ERR_INVALID, "null argument");
+  if (image < 0 || image >= 2 * h->cfg.max_pairs || level < 0 || level >= h->geom.levels) return fail(PAGK_ERR_INVALID, "bad image or level");
+  const PagkLevelGeom &L = h->geom.lv[level];
+  const size_t bytes = (size_t)L.cols * L.rows;
+  if (dst_bytes < bytes) return fail(PAGK_ERR_INVALID, "destination too small");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaMemcpyAsync(dst, h->d_images + (size_t)image * h->geom.slot_bytes + L.offset, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return PAGK_OK;
+}
+
+int pagk_integrate_gyro(const pagk_pair_in *in, float Rcl[9], float KRKinv[9]) {
+  if (!in || !Rcl || !KRKinv) return fail(PAGK_ERR_INVALID, "null argument");
+  PagkPairConst pc;
+  pair_const(*in, &pc, Rcl, KRKinv);
+  return PAGK_OK;
+}
+
+int pagk_gyro_predict(pagk_handle *h, const pagk_params *prm, const pagk_pair_in *in, pagk_pair_out *out) {
+  if (!h || !prm || !in || !out) return fail(PAGK_ERR_INVALID, "null argument");
+  pagk_params p = *prm;
+  p.e_type = PAGK_GYRO_PREDICT;
+  if (p.pyramids < 1) p.pyramids = 1;
+  return pagk_track_batch(h, &p, 1, in, out);
+}
+
+int pagk_patch_match(pagk_handle *h, const pagk_patch_match_in *in, pagk_pair_out *out) {
+  if (!h || !in || !out) return fail(PAGK_ERR_INVALID, "null argument");
+  if (in->inverse) return fail(PAGK_ERR_UNSUPPORTED, "inverse mode is \"not support yet\" in the reference (src/patch_match.cpp:220)");
+  if (!in->img_ref || !in->img_cur || in->pitch < in->width) return fail(PAGK_ERR_INVALID, "bad image pointer or pitch");
+  if (in->n_keys < 0 || in->n_keys > h->cfg.max_keys) return fail(PAGK_ERR_INVALID, "n_keys exceeds pagk_config.max_keys");
+  if (in->n_keys > 0 && (!in->keys_ref_un || !in->pt_predict_un || !in->status || (in->consider_affine_deformation && !in->affine)))
+    return fail(PAGK_ERR_INVALID, "null input vector");
+  int rc = check_batch(h, 1, in->width, in->height, in->pyramids, in->half_patch);
+  if (rc != PAGK_OK) return rc;
+  CU(cudaSetDevice(h->cfg.device));
+  h->resident = false; h->ran = false;
+  PagkMode m;
+  std::memset(&m, 0, sizeof(m));
+  m.gyro_init = in->has_gyro_predict_initial ? 1 : 0; m.illum = in->consider_illumination ? 1 : 0;
+  m.affine = in->consider_affine_deformation ? 1 : 0; m.regular = in->regularization_penalty ? 1 : 0;
+  fill_mode_common(&m, in->half_patch, in->iterations, in->pyramids, in->calc_ncc, PAGK_PIXEL_AWARE_PREDICTION, in->lambda,
+                   in->alpha, in->max_distance);
+  pagk_pair_in pin;
+  std::memset(&pin, 0, sizeof(pin));
+  std::memcpy(pin.K, in->K, sizeof(pin.K)); std::memcpy(pin.dist, in->dist, sizeof(pin.dist));
+  pin.n_dist = in->n_dist; pin.n_keys = in->n_keys;
+  const float eye[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  pin.Rcl_override = eye;
+  h->pcs.assign(1, PagkPairConst());
+  h->rcl.assign(9, 0.f); h->krk.assign(9, 0.f);
+  pair_const(pin, &h->pcs[0], h->rcl.data(), h->krk.data());
+  const size_t n = (size_t)in->n_keys;
+  const PagkOutPtrs o = h->outs();
+  cudaStream_t st = h->stream;
+  CU(cudaMemcpyAsync(h->d_pc, h->pcs.data(), sizeof(PagkPairConst), cudaMemcpyHostToDevice, st));
+  if (n) {
+    CU(cudaMemcpyAsync(h->d_keys_un, in->keys_ref_un, n * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(o.pt_predict_un, in->pt_predict_un, n * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(o.gyro_status, in->status, n, cudaMemcpyHostToDevice, st));
+    if (in->affine) CU(cudaMemcpyAsync(o.affine, in->affine, n * 16, cudaMemcpyHostToDevice, st));
+  }
+  const uint8_t *r = in->img_ref, *c = in->img_cur;
+  rc = upload_images(h, 1, &r, &c, in->width, in->height, &in->pitch);
+  if (rc != PAGK_OK) return rc;
+  CU(cudaStreamSynchronize(st));  // the caller's (pageable) inputs may go away after this call
+  h->mode = m; h->n_pairs = 1; h->n_max = in->n_keys; h->e_type = PAGK_GYRO_PREDICT_WITH_OPTICAL_FLOW_REFINED;
+  CU(cudaEventRecord(h->ev[0], st));
+  CU((cudaError_t)pagk_launch_pyramids(h->d_images, h->geom, 2, st, &h->launches));
+  CU(cudaEventRecord(h->ev[1], st));
+  CU(cudaEventRecord(h->ev[2], st));
+  CU((cudaError_t)pagk_launch_lk(h->d_images, h->geom, h->d_pc, h->d_keys_un, o, m, h->cfg.max_keys, in->n_keys, 1, st, &h->launches));
+  CU(cudaEventRecord(h->ev[3], st));
+  CU((cudaError_t)pagk_launch_epilogue(h->d_pc, o, m, h->cfg.max_keys, 1, h->d_res, 0, st, &h->launches));
+  CU(cudaEventRecord(h->ev[4], st));
+  h->ran = true;
+  pagk_pair_out tmp = *out;  // only the PatchMatch outputs (SetMatcher, src/patch_match.cpp:370-388)
+  tmp.pt_predict_un = nullptr; tmp.pt_predict = nullptr; tmp.status = nullptr; tmp.pt_gyro_predict_un = nullptr;
+  tmp.pt_gyro_predict = nullptr; tmp.flows_predict_un = nullptr; tmp.affine = nullptr; tmp.corner_flows = nullptr;
+  tmp.pt_corners_un = nullptr; tmp.pt_corners = nullptr;
+  rc = pagk_download_batch(h, 1, &tmp);
+  out->n_predict = tmp.n_predict; out->n_iterations = tmp.n_iterations;
+  out->t_gyro_predict = tmp.t_gyro_predict; out->t_opt_flow = tmp.t_opt_flow; out->t_filter = tmp.t_filter;
+  return rc;
+}
+
+}  // extern "C"

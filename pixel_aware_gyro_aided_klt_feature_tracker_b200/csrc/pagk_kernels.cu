@@ -1,0 +1,555 @@
+// pagk_kernels.cu -- the sm_100a kernels of the pixel-aware gyro-aided KLT hot path.
+//
+//   K1  pagk_pyramid_fused_kernel / pagk_pyramid_general_kernel
+//         PatchMatch::CreatePyramids               reference src/patch_match.cpp:61-76
+//   K2  pagk_gyro_predict_kernel
+//         GyroAidedTracker::GyroPredictFeatures    reference src/gyro_aided_tracker.cpp:118-256
+//   K3  pagk_lk_kernel (generic, any patch size)
+//         PatchMatch::OpticalFlowMultiLevel + OpticalFlowConsideringIlluminationChange_onePixel
+//                                                  reference src/patch_match.cpp:79-142, 167-367
+//   K4  pagk_epilogue_kernel
+//         DistortPoints / SetMatcher               reference src/patch_match.cpp:370-388, 409-416
+//         threshold filter                         reference src/gyro_aided_tracker.cpp:289-336
+//
+// Compiled with --fmad=false (see pagk_device.cuh for the arithmetic contract).
+#include "pagk_device.cuh"
+#include "pagk_kernels.h"
+
+#include <math_constants.h>
+
+// =================================================================================================
+// K1: image pyramid.  cv::resize(INTER_LINEAR) to exactly half size is OpenCV's 2x2 INTER_AREA fast
+// path: dst = (a + b + c + d + 2) >> 2 (verified against cv2).  One CTA owns a
+// 128 x 64 tile of level 0 and produces that tile of every further level of the exact-2x chain from
+// shared memory, so level 0 is read from HBM once and nothing is re-read.  16-byte loads, 8-byte
+// stores.  The CTA that owns the last row of a level also writes that level's guard row.
+// =================================================================================================
+#define PYR_TW 128
+#define PYR_TH 64
+
+__device__ __forceinline__ unsigned int pagk_avg4x8(unsigned int r0, unsigned int r1) {
+  // r0, r1: four horizontally adjacent pixels of two rows -> two output pixels in the low 16 bits
+  const unsigned int a = (r0 & 0xffu) + ((r0 >> 8) & 0xffu) + (r1 & 0xffu) + ((r1 >> 8) & 0xffu) + 2u;
+  const unsigned int b = ((r0 >> 16) & 0xffu) + (r0 >> 24) + ((r1 >> 16) & 0xffu) + (r1 >> 24) + 2u;
+  return (a >> 2) | ((b >> 2) << 8);
+}
+
+__global__ void __launch_bounds__(256) pagk_pyramid_fused_kernel(unsigned char *__restrict__ images, PagkGeom g,
+                                                               int n_fused /* last level produced here */) {
+  __shared__ __align__(16) unsigned char sbuf[2][(PYR_TW / 2) * (PYR_TH / 2)];
+  unsigned char *img = images + (size_t)blockIdx.z * g.slot_bytes;
+  const int t = threadIdx.x;
+  const int cols0 = g.lv[0].cols, rows0 = g.lv[0].rows;
+  unsigned char *l0 = img + g.lv[0].offset;
+  const int tx0 = blockIdx.x * PYR_TW, ty0 = blockIdx.y * PYR_TH;
+
+  // ---- level 0 -> level 1 (or only the guard row of level 0 when there is a single level)
+  {
+    const int tx = t & 7, ty = t >> 3;  // 8 threads x 16 px per row pair, 32 row pairs
+    const int x0 = tx0 + tx * 16, y0 = ty0 + ty * 2;
+    const bool vec = ((cols0 & 15) == 0);
+    unsigned int a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
+    const bool in0 = (x0 < cols0) && (y0 < rows0), in1 = (x0 < cols0) && (y0 + 1 < rows0);
+    if (vec) {
+      if (in0) { const uint4 v = *reinterpret_cast<const uint4 *>(l0 + (size_t)y0 * cols0 + x0); a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w; }
+      if (in1) { const uint4 v = *reinterpret_cast<const uint4 *>(l0 + (size_t)(y0 + 1) * cols0 + x0); b[0] = v.x; b[1] = v.y; b[2] = v.z; b[3] = v.w; }
+    } else {
+      for (int k = 0; k < 16; ++k) {
+        if (in0 && x0 + k < cols0) a[k >> 2] |= (unsigned int)l0[(size_t)y0 * cols0 + x0 + k] << (8 * (k & 3));
+        if (in1 && x0 + k < cols0) b[k >> 2] |= (unsigned int)l0[(size_t)(y0 + 1) * cols0 + x0 + k] << (8 * (k & 3));
+      }
+    }
+    // guard row of level 0 = copy of row rows0-1 (+ one byte)
+    if (in0 && (y0 == rows0 - 1 || y0 + 1 == rows0 - 1)) {
+      const unsigned int *src = (y0 == rows0 - 1) ? a : b;
+      unsigned char *gr = l0 + (size_t)rows0 * cols0 + x0;
+      if (vec) {
+        *reinterpret_cast<uint4 *>(gr) = make_uint4(src[0], src[1], src[2], src[3]);
+      } else {
+        for (int k = 0; k < 16 && x0 + k < cols0; ++k) gr[k] = (unsigned char)(src[k >> 2] >> (8 * (k & 3)));
+      }
+      if (x0 == 0) l0[(size_t)(rows0 + 1) * cols0] = (unsigned char)(src[0] & 0xffu);
+    }
+    if (n_fused >= 1) {
+      const int cols1 = g.lv[1].cols, rows1 = g.lv[1].rows;
+      unsigned char *l1 = img + g.lv[1].offset;
+      uint2 o;
+      o.x = pagk_avg4x8(a[0], b[0]) | (pagk_avg4x8(a[1], b[1]) << 16);
+      o.y = pagk_avg4x8(a[2], b[2]) | (pagk_avg4x8(a[3], b[3]) << 16);
+      *reinterpret_cast<uint2 *>(&sbuf[0][ty * (PYR_TW / 2) + tx * 8]) = o;
+      const int x1 = x0 >> 1, y1 = y0 >> 1;
+      if (y1 < rows1 && x1 < cols1) {
+        unsigned char *dst = l1 + (size_t)y1 * cols1 + x1;
+        if (vec && x1 + 8 <= cols1) {
+          *reinterpret_cast<uint2 *>(dst) = o;
+          if (y1 == rows1 - 1) *reinterpret_cast<uint2 *>(dst + cols1) = o;
+        } else {
+          for (int k = 0; k < 8 && x1 + k < cols1; ++k) {
+            const unsigned char v = (unsigned char)((k < 4 ? o.x : o.y) >> (8 * (k & 3)));
+            dst[k] = v;
+            if (y1 == rows1 - 1) dst[cols1 + k] = v;
+          }
+        }
+        if (y1 == rows1 - 1 && x1 == 0) l1[(size_t)(rows1 + 1) * cols1] = (unsigned char)(o.x & 0xffu);
+      }
+    }
+  }
+  // ---- level l-1 (shared memory) -> level l, l = 2 .. n_fused
+  int tw = PYR_TW / 2, th = PYR_TH / 2, cur = 0;
+  for (int l = 2; l <= n_fused; ++l) {
+    __syncthreads();
+    const int ow = tw >> 1, oh = th >> 1;
+    if (ow == 0 || oh == 0) break;  // host never asks for more than the tile can give
+    const int colsl = g.lv[l].cols, rowsl = g.lv[l].rows;
+    unsigned char *ll = img + g.lv[l].offset;
+    const unsigned char *s = sbuf[cur];
+    unsigned char *d = sbuf[cur ^ 1];
+    const int ox0 = tx0 >> l, oy0 = ty0 >> l;
+    for (int p = t; p < ow * oh; p += 256) {
+      const int ox = p % ow, oy = p / ow;
+      const unsigned char *q = s + (2 * oy) * tw + 2 * ox;
+      const unsigned char v = (unsigned char)((q[0] + q[1] + q[tw] + q[tw + 1] + 2) >> 2);
+      d[oy * ow + ox] = v;
+      const int gx = ox0 + ox, gy = oy0 + oy;
+      if (gx < colsl && gy < rowsl) {
+        ll[(size_t)gy * colsl + gx] = v;
+        if (gy == rowsl - 1) {
+          ll[(size_t)rowsl * colsl + gx] = v;
+          if (gx == 0) ll[(size_t)(rowsl + 1) * colsl] = v;
+        }
+      }
+    }
+    tw = ow; th = oh; cur ^= 1;
+  }
+}
+
+// General half-size cv::resize(INTER_LINEAR) for levels whose source has an odd dimension: the
+// 11-bit fixed-point bilinear of OpenCV.  One thread per output pixel.
+__global__ void __launch_bounds__(256) pagk_pyramid_general_kernel(unsigned char *__restrict__ images, PagkGeom g,
+                                                                 int level) {
+  unsigned char *img = images + (size_t)blockIdx.z * g.slot_bytes;
+  const int scols = g.lv[level - 1].cols, srows = g.lv[level - 1].rows;
+  const int dcols = g.lv[level].cols, drows = g.lv[level].rows;
+  const unsigned char *src = img + g.lv[level - 1].offset;
+  unsigned char *dst = img + g.lv[level].offset;
+  const int dx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int dy = blockIdx.y;
+  if (dx >= dcols || dy >= drows) return;
+  unsigned char v;
+  if (scols == 2 * dcols && srows == 2 * drows) {
+    const unsigned char *r0 = src + (size_t)(2 * dy) * scols + 2 * dx;
+    v = (unsigned char)((r0[0] + r0[1] + r0[scols] + r0[scols + 1] + 2) >> 2);
+  } else {
+    const double sx = (double)scols / dcols, sy = (double)srows / drows;
+    float fx = (float)((dx + 0.5) * sx - 0.5);
+    int ix = (int)floorf(fx);
+    fx -= (float)ix;
+    if (ix < 0) { ix = 0; fx = 0.f; }
+    if (ix >= scols - 1) { ix = scols - 1; fx = 0.f; }
+    const int a0 = __float2int_rn((1.f - fx) * 2048.f), a1 = __float2int_rn(fx * 2048.f);
+    float fy = (float)((dy + 0.5) * sy - 0.5);
+    int iy = (int)floorf(fy);
+    fy -= (float)iy;
+    const int y0 = min(max(iy, 0), srows - 1), y1 = min(max(iy + 1, 0), srows - 1);
+    const int b0 = __float2int_rn((1.f - fy) * 2048.f), b1 = __float2int_rn(fy * 2048.f);
+    const int ix1 = min(ix + 1, scols - 1);
+    const unsigned char *r0 = src + (size_t)y0 * scols, *r1 = src + (size_t)y1 * scols;
+    const int t0 = r0[ix] * a0 + r0[ix1] * a1;
+    const int t1 = r1[ix] * a0 + r1[ix1] * a1;
+    const int o = (((b0 * (t0 >> 4)) >> 16) + ((b1 * (t1 >> 4)) >> 16) + 2) >> 2;
+    v = (unsigned char)min(max(o, 0), 255);
+  }
+  dst[(size_t)dy * dcols + dx] = v;
+  if (dy == drows - 1) {
+    dst[(size_t)drows * dcols + dx] = v;
+    if (dx == 0) dst[(size_t)(drows + 1) * dcols] = v;
+  }
+}
+
+// =================================================================================================
+// K2: pixel-aware gyro prediction, one thread per feature.
+// =================================================================================================
+__device__ __forceinline__ void pagk_predict_one(const PagkPairConst &c, int method, const float *__restrict__ ntab,
+                                                 int width, float2 ref, float2 &pun, float2 &pd) {
+  float xn, yn;
+  if (ntab) {
+    const size_t o = ((size_t)((int)ref.y) * width + (int)ref.x) * 2;
+    xn = ntab[o]; yn = ntab[o + 1];
+  } else {
+    xn = (ref.x - c.cx) * c.fx_inv;
+    yn = (ref.y - c.cy) * c.fy_inv;
+  }
+  float lambda = 1.0f;
+  if (method == 1) {
+    const float den = (c.r31 * xn + c.r32 * yn) + c.r33;
+    lambda = (float)(1.0 / (double)den);
+  }
+  pun.x = ((c.M[0] * ref.x + c.M[1] * ref.y) + c.M[2]) * lambda;
+  pun.y = ((c.M[3] * ref.x + c.M[4] * ref.y) + c.M[5]) * lambda;
+  pd = pagk_distort(c, pun);
+}
+
+__global__ void __launch_bounds__(128) pagk_gyro_predict_kernel(const PagkPairConst *__restrict__ pcs,
+                                                              const float2 *__restrict__ keys_un,
+                                                              const float2 *__restrict__ keys, PagkOutPtrs out,
+                                                              PagkMode mode, int max_keys, int width, int height,
+                                                              const float *__restrict__ ntab_all,
+                                                              unsigned long long ntab_stride) {
+  const int pair = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const PagkPairConst &c = pcs[pair];
+  if (i >= c.n_keys) return;
+  const size_t o = (size_t)pair * max_keys + i;
+  const float2 ref = keys_un[o];
+  float2 z = make_float2(0.f, 0.f);
+  float2 pun = z, pd = z, fl = z, cf[4] = {z, z, z, z}, cu[4] = {z, z, z, z}, cd[4] = {z, z, z, z};
+  float4 A = make_float4(0.f, 0.f, 0.f, 0.f);
+  unsigned char st = 0;
+  if (!mode.gyro_init) {  // eType 5, reference src/gyro_aided_tracker.cpp:264-270
+    pun = ref; pd = keys[o]; st = 1;
+    A = make_float4(1.f, 0.f, 0.f, 1.f);
+    out.pt_gyro_un[o] = z; out.pt_gyro[o] = z;
+  } else {
+    const float *ntab = c.has_table ? ntab_all + (size_t)pair * ntab_stride : nullptr;
+    float2 p, d;
+    pagk_predict_one(c, mode.predict_method, ntab, width, ref, p, d);
+    const float W = (float)width, H = (float)height;
+    const bool ok = !(p.x < 0.f || p.x >= W || p.y < 0.f || p.y >= H) && !(d.x < 0.f || d.x >= W || d.y < 0.f || d.y >= H);
+    if (ok) {
+      pun = p; pd = d; st = 1;
+      fl = make_float2(p.x - ref.x, p.y - ref.y);
+      const float hf = (float)mode.half;
+      const float bx[4] = {-hf, hf, -hf, hf}, by[4] = {-hf, -hf, hf, hf};
+      double s00 = 0, s01 = 0, s10 = 0, s11 = 0;
+      double q00[4], q01[4], q10[4], q11[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        pagk_predict_one(c, mode.predict_method, ntab, width, make_float2(ref.x + bx[j], ref.y + by[j]), cu[j], cd[j]);
+        cf[j] = make_float2(cu[j].x - p.x, cu[j].y - p.y);
+        q00[j] = (double)cf[j].x * (double)bx[j]; q01[j] = (double)cf[j].x * (double)by[j];
+        q10[j] = (double)cf[j].y * (double)bx[j]; q11[j] = (double)cf[j].y * (double)by[j];
+      }
+      // C * B^T with OpenCV's double accumulation: s0 = q0, then s0 += (q1 + q2) + q3
+      s00 = q00[0] + ((q00[1] + q00[2]) + q00[3]); s01 = q01[0] + ((q01[1] + q01[2]) + q01[3]);
+      s10 = q10[0] + ((q10[1] + q10[2]) + q10[3]); s11 = q11[0] + ((q11[1] + q11[2]) + q11[3]);
+      const float S00 = (float)s00, S01 = (float)s01, S10 = (float)s10, S11 = (float)s11;
+      // times (B B^T)^-1 = [[bb, -0],[-0, bb]] as a float 2x2 small gemm
+      const float bb = mode.bb_inv, nz = -0.0f;
+      A.x = S00 * bb + S01 * nz; A.y = S00 * nz + S01 * bb;
+      A.z = S10 * bb + S11 * nz; A.w = S10 * nz + S11 * bb;
+    }
+    out.pt_gyro_un[o] = pun; out.pt_gyro[o] = pd;
+  }
+  out.pt_predict_un[o] = pun; out.pt_predict[o] = pd;
+  out.status[o] = st; out.gyro_status[o] = st;
+  out.flows[o] = fl; out.affine[o] = A;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { out.cflows[o * 4 + j] = cf[j]; out.corners_un[o * 4 + j] = cu[j]; out.corners[o * 4 + j] = cd[j]; }
+}
+
+// =================================================================================================
+// K3 (generic): coarse-to-fine forward-additive Lucas-Kanade with gain/bias and affine pre-warp.
+// One warp per feature, all pyramid levels inside the kernel (features are independent across
+// levels; the reference's per-level parallel_for is only a CPU scheduling choice).
+//   phase A  lanes = patch pixels: bilinear samples, residual e and gradient (Ix, Iy) -> shared memory
+//   phase B  lanes = accumulators: the 10 unique entries of H and 4 of b are summed in DOUBLE in the
+//            reference's pixel order (a structurally singular H makes the result order-sensitive,
+//            SURVEY.md F3); the float cost chain runs beside them
+//   solve    every lane runs the 4x4 LLT redundantly (no broadcast needed)
+// Shared memory per warp: NP * 56 + 128 bytes.
+// =================================================================================================
+__device__ __forceinline__ const unsigned char *pagk_level_ptr(const unsigned char *images, const PagkGeom &g,
+                                                               int pair, int which, int level) {
+  return images + (size_t)(pair * 2 + which) * g.slot_bytes + g.lv[level].offset;
+}
+
+__global__ void pagk_lk_kernel(const unsigned char *__restrict__ images, PagkGeom g,
+                               const PagkPairConst *__restrict__ pcs, const float2 *__restrict__ keys_un,
+                               PagkOutPtrs out, PagkMode mode, int max_keys, int warps_per_cta) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int pair = blockIdx.y;
+  const int i = blockIdx.x * warps_per_cta + wib;
+  if (i >= pcs[pair].n_keys) return;
+  const size_t o = (size_t)pair * max_keys + i;
+  const int h = mode.half, P = 2 * h + 1, NP = P * P;
+  const size_t per_warp = (size_t)NP * 56 + 128;
+  unsigned char *base = smem_raw + per_warp * wib;
+  double *sJ = reinterpret_cast<double *>(base);                  // [NP][5]: Ix, Iy, c, 1, -e
+  double *sRed = reinterpret_cast<double *>(base + (size_t)NP * 40);  // [16]
+  float *sE2 = reinterpret_cast<float *>(base + (size_t)NP * 40 + 128);
+  float *sWx = sE2 + NP, *sWy = sWx + NP, *sT = sWy + NP;
+
+  const float2 pt1 = keys_un[o];
+  float2 pt2 = mode.gyro_init ? out.pt_predict_un[o] : pt1;
+  const unsigned char gst = out.gyro_status[o];
+  int n_iter = 0;
+  bool succ = false;
+  float lastCost = 0.f;
+  if (gst) {
+    const float4 A = out.affine[o];
+    // accumulator role of this lane: acc += J[ia] * J[ib]; column 4 holds -e, so that the b lanes
+    // compute b_r += J_r * (-e), the same value as the reference's b += -J * e (negation is exact)
+    const int ia_tab[14] = {0, 0, 0, 0, 1, 1, 1, 2, 2, 3, 0, 1, 2, 3};
+    const int ib_tab[14] = {0, 1, 2, 3, 1, 2, 3, 2, 3, 3, 4, 4, 4, 4};
+    const int role = lane < 14 ? lane : 0;
+    const int ia = ia_tab[role], ib = ib_tab[role];
+    for (int p = lane; p < NP; p += 32) {
+      const int y = p / P - h, x = p % P - h;
+      float wx = (float)x, wy = (float)y;
+      if (mode.affine) {
+        wx = A.x * (float)x + A.y * (float)y;
+        wy = A.z * (float)x + A.w * (float)y;
+      }
+      sWx[p] = wx; sWy[p] = wy;
+    }
+    for (int level = mode.levels - 1; level >= 0; --level) {
+      const unsigned char *I1 = pagk_level_ptr(images, g, pair, 0, level);
+      const unsigned char *I2 = pagk_level_ptr(images, g, pair, 1, level);
+      const int cols = g.lv[level].cols, rows = g.lv[level].rows;
+      const float scale = 1.0f / (float)(1 << level);
+      const float ptx = pt1.x * scale, pty = pt1.y * scale;
+      float nx, ny;
+      if (level == mode.levels - 1) { nx = pt2.x * scale; ny = pt2.y * scale; }
+      else { nx = pt2.x * 2.0f; ny = pt2.y * 2.0f; }
+      float dx = nx - ptx, dy = ny - pty;
+      float dg = 0.f, db = 0.f, cost = 0.f;
+      lastCost = 0.f;
+      succ = true;
+      const float cval = -pagk_sample(I1, cols, rows, ptx, pty);
+      for (int p = lane; p < NP; p += 32) {
+        const int y = p / P - h, x = p % P - h;
+        sT[p] = pagk_sample(I1, cols, rows, ptx + (float)x, pty + (float)y);
+        sJ[p * 5 + 2] = (double)cval;
+        sJ[p * 5 + 3] = 1.0;
+      }
+      for (int iter = 0; iter < mode.iterations; ++iter) {
+        ++n_iter;
+        const float bx = ptx + dx, by = pty + dy;
+        const float gain = 1.0f + dg;
+        for (int p = lane; p < NP; p += 32) {
+          const float sx = bx + sWx[p], sy = by + sWy[p];
+          const float e = (pagk_sample(I2, cols, rows, sx, sy) + db) - gain * sT[p];
+          const float gx = pagk_sample(I2, cols, rows, sx + 1.0f, sy) - pagk_sample(I2, cols, rows, sx - 1.0f, sy);
+          const float gy = pagk_sample(I2, cols, rows, sx, sy + 1.0f) - pagk_sample(I2, cols, rows, sx, sy - 1.0f);
+          sJ[p * 5 + 0] = 0.5 * (double)gx;  // (float)(0.5 * (double)diff) is an exact halving
+          sJ[p * 5 + 1] = 0.5 * (double)gy;
+          sJ[p * 5 + 4] = -(double)e;
+          sE2[p] = e * e;
+        }
+        __syncwarp();
+        double acc = 0.0;
+        cost = 0.f;
+#pragma unroll 4
+        for (int p = 0; p < NP; ++p) {
+          acc = fma(sJ[p * 5 + ia], sJ[p * 5 + ib], acc);
+          cost = cost + sE2[p];
+        }
+        if (lane < 14) sRed[lane] = acc;
+        __syncwarp();
+        double h00 = sRed[0], h10 = sRed[1], h20 = sRed[2], h30 = sRed[3], h11 = sRed[4], h21 = sRed[5], h31 = sRed[6],
+               h22 = sRed[7], h32 = sRed[8], h33 = sRed[9], b0 = sRed[10], b1 = sRed[11], b2 = sRed[12], b3 = sRed[13];
+        __syncwarp();
+        if (mode.regular) {  // reference src/patch_match.cpp:302-314
+          const double d = (double)sqrtf(dx * dx + dy * dy);
+          const float li = mode.lambda * mode.inv_log_max_dist;
+          const double ad1 = (double)mode.alpha * d + 1.0;
+          const double e_pen = (double)li * log(ad1);
+          const double jx = ((double)(li * mode.alpha) / ad1) * ((double)dx / d);
+          const double jy = ((double)(li * mode.alpha) / ad1) * ((double)dy / d);
+          h00 += jx * jx; h10 += jy * jx; h11 += jy * jy;
+          h20 += 0.0 * jx; h21 += 0.0 * jy; h30 += 0.0 * jx; h31 += 0.0 * jy;
+          b0 += jx * e_pen; b1 += jy * e_pen; b2 += 0.0 * e_pen; b3 += 0.0 * e_pen;
+          cost = (float)((double)cost + e_pen * e_pen);
+        }
+        double u0, u1, u2, u3;
+        pagk_llt_solve4(h00, h10, h11, h20, h21, h22, h30, h31, h32, h33, b0, b1, b2, b3, u0, u1, u2, u3);
+        if (isnan(u0)) { succ = false; break; }
+        if (iter > 0 && cost > lastCost) break;
+        dx = (float)((double)dx + u0);
+        dy = (float)((double)dy + u1);
+        if (mode.illum) { dg = (float)((double)dg + u2); db = (float)((double)db + u3); }
+        lastCost = cost;
+        succ = true;
+        const double nrm = sqrt((u0 * u0 + u2 * u2) + (u1 * u1 + u3 * u3));
+        if (nrm < 1e-2) break;
+      }
+      pt2.x = ptx + dx; pt2.y = pty + dy;
+    }
+  }
+  if (lane == 0) {
+    out.pm_un[o] = pt2;
+    out.pm_status[o] = (gst && succ) ? 1 : 0;
+    out.pix_err[o] = gst ? sqrt((double)lastCost * mode.win_size_inv) : 0.0;
+    out.ncc[o] = gst ? 1.0f : 0.0f;
+    out.iters[o] = n_iter;
+  }
+}
+
+// =================================================================================================
+// K4: DistortPoints + SetMatcher + the threshold filter.  One CTA per frame pair.  The mean pixel
+// error is a double sum in feature-index order (src/gyro_aided_tracker.cpp:294-305): thread 0 adds
+// chunk after chunk from shared memory so that the rounding sequence is the reference's.
+// =================================================================================================
+#define EPI_THREADS 256
+#define EPI_CHUNK 2048
+
+__global__ void __launch_bounds__(EPI_THREADS) pagk_epilogue_kernel(const PagkPairConst *__restrict__ pcs,
+                                                                  PagkOutPtrs out, PagkMode mode, int max_keys,
+                                                                  PagkPairResult *__restrict__ res, int do_filter) {
+  __shared__ double s_err[EPI_CHUNK];
+  __shared__ unsigned char s_ok[EPI_CHUNK];
+  __shared__ double s_th[2];
+  __shared__ int s_cnt;
+  __shared__ unsigned long long s_it;
+  const int pair = blockIdx.x, t = threadIdx.x;
+  const PagkPairConst &c = pcs[pair];
+  const int N = c.n_keys;
+  const size_t o0 = (size_t)pair * max_keys;
+  if (t == 0) { s_cnt = 0; s_it = 0ull; }
+  // distort + drift distance (src/patch_match.cpp:378-387, 409-416)
+  for (int i = t; i < N; i += EPI_THREADS) {
+    const float2 p = out.pm_un[o0 + i];
+    out.pm[o0 + i] = (c.k1 == 0.0f) ? p : pagk_distort(c, p);
+    const float2 base = out.pt_predict_un[o0 + i];  // still the gyro prediction here (mvPtPredictUn, :384)
+    const float ddx = base.x - p.x, ddy = base.y - p.y;
+    out.dist[o0 + i] = (double)sqrtf(ddx * ddx + ddy * ddy);
+  }
+  double sum = 0.0;
+  int cnt = 0;
+  for (int c0 = 0; c0 < N; c0 += EPI_CHUNK) {
+    __syncthreads();
+    for (int i = t; i < EPI_CHUNK && c0 + i < N; i += EPI_THREADS) {
+      s_err[i] = out.pix_err[o0 + c0 + i];
+      s_ok[i] = out.pm_status[o0 + c0 + i];
+    }
+    __syncthreads();
+    if (t == 0) {
+      const int m = min(EPI_CHUNK, N - c0);
+      for (int i = 0; i < m; ++i)
+        if (s_ok[i]) { sum += s_err[i]; ++cnt; }
+    }
+  }
+  if (t == 0) {
+    const double avg = sum / (double)cnt;  // cnt == 0 -> NaN -> threshold falls back to half (:305-308)
+    const double hp = (double)mode.half;
+    s_th[0] = (4.0 * avg > hp) ? 4.0 * avg : hp;
+    s_th[1] = hp * 4.0;
+    res[pair].avg_pixel_error = avg;
+    res[pair].cnt_pm_ok = cnt;
+  }
+  __syncthreads();
+  const double thPix = s_th[0], thDist = s_th[1];
+  int my_cnt = 0;
+  unsigned long long my_it = 0;
+  for (int i = t; i < N; i += EPI_THREADS) {
+    my_it += (unsigned long long)out.iters[o0 + i];
+    if (!do_filter) continue;
+    const bool keep = out.pm_status[o0 + i] && out.pix_err[o0 + i] < thPix && out.dist[o0 + i] < thDist;
+    if (keep) {
+      out.pt_predict[o0 + i] = out.pm[o0 + i];
+      out.pt_predict_un[o0 + i] = out.pm_un[o0 + i];
+      out.status[o0 + i] = 1;
+      ++my_cnt;
+    } else {
+      out.status[o0 + i] = 0;
+    }
+  }
+  atomicAdd(&s_cnt, my_cnt);
+  atomicAdd(&s_it, my_it);
+  __syncthreads();
+  if (t == 0) { res[pair].n_predict = s_cnt; res[pair].n_iterations = (long long)s_it; }
+}
+
+// counts the gyro-predicted features of a pair (eType 1: TrackFeatures returns GyroPredictFeatures())
+__global__ void __launch_bounds__(256) pagk_count_status_kernel(const PagkPairConst *__restrict__ pcs, PagkOutPtrs out,
+                                                              int max_keys, PagkPairResult *__restrict__ res) {
+  __shared__ int s_cnt;
+  const int pair = blockIdx.x;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  int c = 0;
+  for (int i = threadIdx.x; i < pcs[pair].n_keys; i += blockDim.x) c += out.status[(size_t)pair * max_keys + i] ? 1 : 0;
+  atomicAdd(&s_cnt, c);
+  __syncthreads();
+  if (threadIdx.x == 0) { res[pair].n_predict = s_cnt; res[pair].n_iterations = 0; res[pair].cnt_pm_ok = 0; res[pair].avg_pixel_error = 0.0; }
+}
+
+// =================================================================================================
+// launch wrappers (host)
+// =================================================================================================
+int pagk_pyramid_fused_max_level() {
+  int l = 1, tw = PYR_TW / 2, th = PYR_TH / 2;
+  while ((tw >> 1) > 0 && (th >> 1) > 0) { tw >>= 1; th >>= 1; ++l; }
+  return l;
+}
+
+int pagk_launch_pyramids(unsigned char *images, const PagkGeom &g, int n_images, cudaStream_t st, long long *launches) {
+  // levels 1..n_fused form the exact-2x chain and come out of the fused kernel
+  int n_fused = 0;
+  for (int l = 1; l < g.levels; ++l) {
+    if (g.lv[l - 1].cols == 2 * g.lv[l].cols && g.lv[l - 1].rows == 2 * g.lv[l].rows && l <= pagk_pyramid_fused_max_level()) n_fused = l;
+    else break;
+  }
+  dim3 grid((g.lv[0].cols + PYR_TW - 1) / PYR_TW, (g.lv[0].rows + PYR_TH - 1) / PYR_TH, n_images);
+  pagk_pyramid_fused_kernel<<<grid, 256, 0, st>>>(images, g, n_fused);
+  ++*launches;
+  for (int l = n_fused + 1; l < g.levels; ++l) {
+    dim3 gg((g.lv[l].cols + 255) / 256, g.lv[l].rows, n_images);
+    pagk_pyramid_general_kernel<<<gg, 256, 0, st>>>(images, g, l);
+    ++*launches;
+  }
+  return (int)cudaGetLastError();
+}
+
+int pagk_launch_predict(const PagkPairConst *pcs, const float2 *keys_un, const float2 *keys, const PagkOutPtrs &out,
+                        const PagkMode &mode, int max_keys, int n_max, int n_pairs, int width, int height,
+                        const float *ntab, unsigned long long ntab_stride, cudaStream_t st, long long *launches) {
+  if (n_max <= 0 || n_pairs <= 0) return 0;
+  dim3 grid((n_max + 127) / 128, n_pairs);
+  pagk_gyro_predict_kernel<<<grid, 128, 0, st>>>(pcs, keys_un, keys, out, mode, max_keys, width, height, ntab, ntab_stride);
+  ++*launches;
+  return (int)cudaGetLastError();
+}
+
+size_t pagk_lk_smem_per_warp(int half) {
+  const size_t NP = (size_t)(2 * half + 1) * (2 * half + 1);
+  return NP * 56 + 128;
+}
+
+int pagk_launch_lk(const unsigned char *images, const PagkGeom &g, const PagkPairConst *pcs, const float2 *keys_un,
+                   const PagkOutPtrs &out, const PagkMode &mode, int max_keys, int n_max, int n_pairs, cudaStream_t st,
+                   long long *launches) {
+  if (n_max <= 0 || n_pairs <= 0) return 0;
+  const size_t pw = pagk_lk_smem_per_warp(mode.half);
+  int wpc = 8;
+  while (wpc > 1 && pw * wpc > 200 * 1024) wpc >>= 1;
+  const size_t smem = pw * wpc;
+  if (smem > 227 * 1024) return (int)cudaErrorInvalidValue;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(pagk_lk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = smem;
+  }
+  dim3 grid((n_max + wpc - 1) / wpc, n_pairs);
+  pagk_lk_kernel<<<grid, wpc * 32, smem, st>>>(images, g, pcs, keys_un, out, mode, max_keys, wpc);
+  ++*launches;
+  return (int)cudaGetLastError();
+}
+
+int pagk_launch_epilogue(const PagkPairConst *pcs, const PagkOutPtrs &out, const PagkMode &mode, int max_keys,
+                         int n_pairs, PagkPairResult *res, int do_filter, cudaStream_t st, long long *launches) {
+  if (n_pairs <= 0) return 0;
+  pagk_epilogue_kernel<<<n_pairs, EPI_THREADS, 0, st>>>(pcs, out, mode, max_keys, res, do_filter);
+  ++*launches;
+  return (int)cudaGetLastError();
+}
+
+int pagk_launch_count_status(const PagkPairConst *pcs, const PagkOutPtrs &out, int max_keys, int n_pairs,
+                             PagkPairResult *res, cudaStream_t st, long long *launches) {
+  if (n_pairs <= 0) return 0;
+  pagk_count_status_kernel<<<n_pairs, 256, 0, st>>>(pcs, out, max_keys, res);
+  ++*launches;
+  return (int)cudaGetLastError();
+}

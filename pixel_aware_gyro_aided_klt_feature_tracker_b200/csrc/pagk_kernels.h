@@ -1,0 +1,17 @@
+// pagk_kernels.h -- host-side launch wrappers of the kernels in pagk_kernels.cu
+#pragma once
+#include "pagk_device.cuh"
+
+int pagk_pyramid_fused_max_level();
+int pagk_launch_pyramids(unsigned char *images, const PagkGeom &g, int n_images, cudaStream_t st, long long *launches);
+int pagk_launch_predict(const PagkPairConst *pcs, const float2 *keys_un, const float2 *keys, const PagkOutPtrs &out,
+                        const PagkMode &mode, int max_keys, int n_max, int n_pairs, int width, int height,
+                        const float *ntab, unsigned long long ntab_stride, cudaStream_t st, long long *launches);
+size_t pagk_lk_smem_per_warp(int half);
+int pagk_launch_lk(const unsigned char *images, const PagkGeom &g, const PagkPairConst *pcs, const float2 *keys_un,
+                   const PagkOutPtrs &out, const PagkMode &mode, int max_keys, int n_max, int n_pairs, cudaStream_t st,
+                   long long *launches);
+int pagk_launch_epilogue(const PagkPairConst *pcs, const PagkOutPtrs &out, const PagkMode &mode, int max_keys,
+                         int n_pairs, PagkPairResult *res, int do_filter, cudaStream_t st, long long *launches);
+int pagk_launch_count_status(const PagkPairConst *pcs, const PagkOutPtrs &out, int max_keys, int n_pairs,
+                             PagkPairResult *res, cudaStream_t st, long long *launches);
