@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the pixel-aware gyro-aided KLT hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # the CUDA path (this repo)
+    python bench.py --impl reference --gpus N --steps K ...   # the CPU reference arm (oracle port)
+
+A "step" is one pass of the hot path (pyramids, gyro prediction, coarse-to-fine patch alignment,
+filter) over one batch of BASELINE.json config B: 64 frame pairs of 752x480 with 1024 features
+each, 4 pyramid levels, 11x11 patches, eType 4 (illumination + affine deformation).  One JSON line
+is printed by rank 0.  Under torchrun every rank owns one GPU and its own batches (independent
+streams, no collective on the data path: "weak" scaling).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from pixel_aware_gyro_aided_klt_feature_tracker_b200 import capi, synth  # noqa: E402
+
+METRIC = "tracked features/sec at 752x480, 1024 feats, 4 levels; px error vs CPU ref"
+# algorithmic work of one feature-iteration at an 11x11 patch
+FP32_FLOP_PER_FEATURE_ITER = {5: 8.5e3, 10: 30.9e3}
+HBM_BYTES_PER_FEATURE_ITER = 120.0
+N_ROTATE = 3  # resident batches per GPU; 3 x 61 MB of pyramids > 126 MB L2
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """polls NVML (SM clock, throttle reasons) while the timed region runs"""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            self.nv, self.err = None, repr(e)
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def result(self):
+        self.stop_flag = True
+        self.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "no NVML samples"}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def pinned(shape, dtype):
+    """page-locked host array (torch is only the allocator here)"""
+    import torch
+    t = torch.empty(tuple(shape), dtype=getattr(torch, np.dtype(dtype).name), pin_memory=torch.cuda.is_available())
+    return t.numpy()
+
+
+def make_batches(cfg_name: str, n_pairs: int, n_batches: int, seed0: int, use_pinned: bool):
+    """n_batches host batches; images/keypoints of a batch live in one contiguous (pinned) block"""
+    from concurrent.futures import ThreadPoolExecutor
+    cfg = {k: v for k, v in synth.CONFIGS[cfg_name].items() if k != "pairs"}
+    H, W, N = cfg["height"], cfg["width"], cfg["n_keys"]
+    alloc = pinned if use_pinned else (lambda s, d: np.empty(s, d))
+    batches = []
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        for b in range(n_batches):
+            imgs = alloc((n_pairs, 2, H, W), np.uint8)
+            keys = alloc((n_pairs, N, 2), np.float32)
+            raw = list(ex.map(lambda i: synth.make_pair(seed0 + b * n_pairs + i, **cfg), range(n_pairs)))
+            pairs = []
+            for i, p in enumerate(raw):
+                imgs[i, 0], imgs[i, 1], keys[i] = p.img_ref, p.img_cur, p.keys_ref_un
+                q = capi.PairInputs(imgs[i, 0], imgs[i, 1], keys[i], p.imu_t, p.imu_w, p.t_ref, p.t_cur, p.K, p.Rbc,
+                                    dist=p.dist, n_dist=p.n_dist)
+                pairs.append(q)
+            batches.append(dict(pairs=pairs, imgs=imgs, keys=keys))
+    return batches, cfg
+
+
+class OutBlock:
+    """result vectors of a batch in contiguous pinned blocks (what SetBackToFrame copies out,
+    reference src/gyro_aided_tracker.cpp:97-111, plus the patch-match status/error)"""
+    FIELDS = [("pt_predict_un", np.float32, (2,)), ("pt_predict", np.float32, (2,)), ("status", np.uint8, ()),
+              ("pt_gyro_predict_un", np.float32, (2,)), ("ncc", np.float32, ()), ("corner_flows", np.float32, (4, 2))]
+
+    def __init__(self, n_pairs, n_keys, use_pinned=True, all_fields=False):
+        alloc = pinned if use_pinned else (lambda s, d: np.zeros(s, d))
+        self.outs = [capi.PairOutputs.__new__(capi.PairOutputs) for _ in range(n_pairs)]
+        fields = capi._OUT_SPEC if all_fields else self.FIELDS
+        self.blocks = {}
+        for o in self.outs:
+            o.n_keys, o.struct = n_keys, capi.PagkPairOut()
+        for name, dt, tail in fields:
+            blk = alloc((n_pairs, n_keys) + tuple(tail), dt)
+            blk[...] = 0
+            self.blocks[name] = blk
+            for i, o in enumerate(self.outs):
+                setattr(o, name, blk[i])
+                setattr(o.struct, name, capi._ptr(blk[i], capi._PTR_OF[dt]))
+        self.nbytes = sum(b.nbytes for b in self.blocks.values())
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (the oracle port: the reference
+    itself needs OpenCV/Eigen/glog and cannot be built here), all host threads, same config."""
+    if rank != 0:
+        return
+    from oracle import oracle
+    oracle.build()
+    cores = os.cpu_count() or 1
+    sample_pairs = args.ref_pairs
+    batches, cfg = make_batches(args.config, sample_pairs, 1, 1000 * (ord(args.config) - 64), False)
+    pairs = batches[0]["pairs"]
+    prm = capi.default_params(pyramids=cfg["pyramids"], half_patch=cfg["half_patch"])
+    for _ in range(max(1, args.warmup // 3)):
+        oracle.track_batch(pairs[:2], prm, cores)
+    t0 = time.perf_counter()
+    iters = 0
+    for _ in range(args.steps):
+        rc, outs = oracle.track_batch(pairs, prm, cores)
+        iters += sum(o.n_iterations for o in outs)
+    dt = time.perf_counter() - t0
+    feats = args.steps * sample_pairs * cfg["n_keys"]
+    v = feats / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "features/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.config, cfg, sample_pairs), "sample": True},
+            "feature_iterations_per_sec": iters / dt,
+            "cpu_baseline": {"value": v, "unit": "features/s", "cores": cores, "kind": "port",
+                             "sample": f"{sample_pairs} frame pairs per step x {args.steps} steps, {cores} std::threads over features"},
+            "e2e": {"value": v, "unit": "features/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(name, cfg, n_pairs):
+    return (f"config {name}: {cfg['width']}x{cfg['height']}, {cfg['n_keys']} features/pair, {cfg['pyramids']} levels, "
+            f"{2 * cfg['half_patch'] + 1}x{2 * cfg['half_patch'] + 1} patch, eType 4, {n_pairs} frame pairs/step")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="pagk", choices=["pagk", "reference"])
+    ap.add_argument("--config", default="B", choices=list(synth.CONFIGS))
+    ap.add_argument("--pairs", type=int, default=None, help="frame pairs per step (default: the config's batch, 64 for B)")
+    ap.add_argument("--ref-pairs", type=int, default=8, help="frame pairs per step of the CPU reference arm")
+    ap.add_argument("--e2e-steps", type=int, default=None)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity leg")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from pixel_aware_gyro_aided_klt_feature_tracker_b200 import tracker
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the pagk hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    cfgd = synth.CONFIGS[args.config]
+    n_pairs = args.pairs or min(cfgd["pairs"], 64)
+    t_gen = time.time()
+    batches, cfg = make_batches(args.config, n_pairs, N_ROTATE, 1000 * (ord(args.config) - 64) + 100000 * rank, True)
+    log(f"[rank {rank}] generated {N_ROTATE} x {n_pairs} synthetic pairs in {time.time() - t_gen:.1f}s")
+    N, half = cfg["n_keys"], cfg["half_patch"]
+    prm = capi.default_params(pyramids=cfg["pyramids"], half_patch=half)
+    ctxs = [tracker.Context(device=local_rank, max_width=cfg["width"], max_height=cfg["height"], max_keys=N,
+                            max_pairs=n_pairs, max_levels=cfg["pyramids"], max_half_patch=half) for _ in range(N_ROTATE)]
+    feats_per_step = n_pairs * N
+
+    # ---- resident leg: inputs already in HBM, kernels only -------------------------------------
+    for c, b in zip(ctxs, batches):
+        c.upload(b["pairs"], prm)
+    for k in range(max(3, args.warmup)):
+        ctxs[k % N_ROTATE].run()
+    for c in ctxs:
+        c.synchronize()
+    outs0 = OutBlock(n_pairs, N, all_fields=True)
+    ctxs[0].run()
+    ctxs[0].download(outs0.outs)
+    iters_per_step = [None] * N_ROTATE
+    for k, c in enumerate(ctxs):
+        ob = OutBlock(n_pairs, N)
+        c.run()
+        c.download(ob.outs)
+        iters_per_step[k] = sum(o.n_iterations for o in ob.outs)
+    launches0 = sum(c.launch_count() for c in ctxs)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    lk_ms, tot_ms = [], []
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        ctxs[k % N_ROTATE].run()
+    for c in ctxs:
+        c.synchronize()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    clocks = sampler.result()
+    launches = sum(c.launch_count() for c in ctxs) - launches0
+    # per-kernel device time: CUDA events recorded by the handle around each kernel (last step of each handle)
+    for c in ctxs[:min(N_ROTATE, args.steps)]:
+        ms = c.last_run_ms()
+        lk_ms.append(ms["lk"]); tot_ms.append(ms["total"])
+    stage_ms = ctxs[0].last_run_ms()
+    tmax = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dt_max = float(tmax.item())
+    total_iters = sum(iters_per_step[k % N_ROTATE] for k in range(args.steps))
+    it_t = torch.tensor([float(total_iters)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(it_t, op=dist.ReduceOp.SUM)
+    value = world * args.steps * feats_per_step / dt_max
+    fi_per_s = float(it_t.item()) / dt_max
+
+    # ---- end-to-end leg: host (pinned) buffers in, host buffers out, through pagk_track_batch -------
+    e2e_steps = args.e2e_steps or max(3, min(args.steps, 30))
+    oblocks = [OutBlock(n_pairs, N) for _ in range(N_ROTATE)]
+    for k in range(3):
+        ctxs[k % N_ROTATE].track_batch(batches[k % N_ROTATE]["pairs"], prm, oblocks[k % N_ROTATE].outs)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        ctxs[k % N_ROTATE].track_batch(batches[k % N_ROTATE]["pairs"], prm, oblocks[k % N_ROTATE].outs)
+    torch.cuda.synchronize()
+    dte = time.perf_counter() - t0
+    te = torch.tensor([dte], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * e2e_steps * feats_per_step / float(te.item())
+    b0 = batches[0]
+    h2d = int(b0["imgs"].nbytes + b0["keys"].nbytes + n_pairs * 96)
+    d2h = int(oblocks[0].nbytes + n_pairs * 24)
+
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (the LK patch-alignment kernel) ------------------------------
+    peaks, peaks_kind = measured_peaks()
+    lk_avg_ms = float(np.mean(lk_ms))
+    it_launch = float(np.mean([iters_per_step[k] for k in range(len(lk_ms))]))
+    fp32_peak = 148 * 128 * 2 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12  # TFLOP/s with FMA, nominal lanes x clock
+    ach = it_launch * FP32_FLOP_PER_FEATURE_ITER.get(half, 70.0 * (2 * half + 1) ** 2) / (lk_avg_ms * 1e-3) / 1e12
+    hbm_ach = it_launch * HBM_BYTES_PER_FEATURE_ITER / (lk_avg_ms * 1e-3) / 1e9
+    roofline = {"bound": "fp32", "kernel": "pagk_lk_kernel", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
+                "frac": ach / fp32_peak, "frac_of_non_fma_peak": ach / (fp32_peak / 2), "traffic": None,
+                "peak_source": f"148 SM x 128 lanes x 2 x {peaks.get('sm_max_mhz', 1965.0):.0f} MHz ({peaks_kind} sm_max_mhz); "
+                               "FMA contraction is forbidden by bit-parity, so half of it is the reachable ceiling",
+                "kernel_ms": lk_avg_ms, "feature_iterations_per_launch": it_launch,
+                "hbm": {"achieved": hbm_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / peaks["hbm_gbs"],
+                        "peak_source": peaks_kind}}
+
+    # ---- CPU baseline + parity on the first batch (rank 0, bounded sample) ------------------------------
+    cpu_baseline, parity = None, None
+    if not args.no_cpu:
+        from oracle import oracle
+        from tests import helpers
+        oracle.build()
+        cores = os.cpu_count() or 1
+        sample = batches[0]["pairs"][:min(n_pairs, 32)]
+        oracle.track_batch(sample[:2], prm, cores)
+        t0 = time.perf_counter()
+        rc, cpu = oracle.track_batch(sample, prm, cores)
+        dtc = time.perf_counter() - t0
+        cpu_iters = sum(o.n_iterations for o in cpu)
+        cpu_baseline = {"value": len(sample) * N / dtc, "unit": "features/s", "cores": cores, "kind": "port",
+                        "feature_iterations_per_sec": cpu_iters / dtc,
+                        "sample": f"first {len(sample)} frame pairs of the timed workload, {cores} std::threads over features"}
+        worst, same, tot, bit = 0.0, 0, 0, True
+        for g, c in zip(outs0.outs, cpu):
+            rep = helpers.compare(g, c)
+            bit &= all(v.get("bit_mismatch", 0) == 0 for v in rep.values() if isinstance(v, dict) and "bit_mismatch" in v)
+            ok = (c.status == 1) & (g.status == 1)
+            if ok.any():
+                worst = max(worst, float(np.hypot(*(g.pt_predict_un[ok] - c.pt_predict_un[ok]).T).max()))
+            same += int((g.status == c.status).sum()); tot += c.status.size
+        parity = {"max_px_error_vs_cpu_ref": worst, "status_equal_frac": same / max(1, tot), "bit_exact_all_outputs": bool(bit),
+                  "pairs_checked": len(sample), "iterations_equal": bool(sum(g.n_iterations for g in outs0.outs[:len(sample)]) == cpu_iters)}
+
+    line = {"metric": METRIC, "value": value, "unit": "features/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": 1e3 * dt_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.config, cfg, n_pairs),
+                       "l2": f"{N_ROTATE} rotating resident batches per GPU ({(N_ROTATE * 2 * n_pairs * cfg['width'] * cfg['height'] * 4 // 3) >> 20} MiB of pyramids) > 126 MB L2",
+                       "timing": "wall clock around K back-to-back steps, barrier + device synchronize on both sides, max over ranks; per-kernel ms from CUDA events on the launching stream"},
+            "feature_iterations_per_sec": fi_per_s,
+            "stage_ms": stage_ms, "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "features/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "api": "pagk_track_batch (pinned host buffers in and out)"},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity}
+    print(json.dumps(line), flush=True)
+    for c in ctxs:
+        c.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

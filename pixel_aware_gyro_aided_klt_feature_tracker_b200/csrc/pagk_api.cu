@@ -74,6 +74,9 @@ struct pagk_handle {
   size_t out_bytes = 0;
   float *d_ntab = nullptr;
   size_t ntab_stride = 0;  // floats per pair
+  int *d_work = nullptr;   // work counter of the persistent LK kernel
+  int n_sms = 0;
+  int force_generic = 0;   // PAGK_LK_KERNEL=generic: use the any-patch-size kernel (tests compare both)
   // pinned staging
   unsigned char *h_in = nullptr;   // keys_un | keys | consts
   size_t h_in_keys_un = 0, h_in_keys = 0, h_in_pc = 0, h_in_bytes = 0;
@@ -185,6 +188,14 @@ int check_batch(pagk_handle *h, int n_pairs, int width, int height, int levels, 
   return PAGK_OK;
 }
 
+int launch_lk(pagk_handle *h, const PagkOutPtrs &o, const PagkMode &m, int n_max, int n_pairs) {
+  if (!h->force_generic && pagk_lk_slots_supported(m))
+    return pagk_launch_lk_slots(h->d_images, h->geom, h->d_pc, h->d_keys_un, o, m, h->cfg.max_keys, n_max, n_pairs, h->d_work,
+                                h->n_sms, h->stream, &h->launches);
+  return pagk_launch_lk(h->d_images, h->geom, h->d_pc, h->d_keys_un, o, m, h->cfg.max_keys, n_max, n_pairs, h->stream,
+                        &h->launches);
+}
+
 template <class T>
 void scatter(const pagk_handle *h, OutKind k, int n_pairs, const std::vector<int> &nk, T *const *dst) {
   for (int p = 0; p < n_pairs; ++p)
@@ -252,6 +263,12 @@ int pagk_create(const pagk_config *cfg, pagk_handle **out) {
   ok(cudaMalloc(&h->d_pc, (size_t)cfg->max_pairs * sizeof(PagkPairConst)));
   ok(cudaMalloc(&h->d_res, (size_t)cfg->max_pairs * sizeof(PagkPairResult)));
   ok(cudaMalloc(&h->d_out, h->out_bytes));
+  ok(cudaMalloc(&h->d_work, 256));
+  ok(cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, cfg->device));
+  {
+    const char *k = getenv("PAGK_LK_KERNEL");
+    h->force_generic = (k && std::strcmp(k, "generic") == 0) ? 1 : 0;
+  }
   ok(cudaMallocHost(&h->h_in, h->h_in_bytes));
   ok(cudaMallocHost(&h->h_out, h->out_bytes));
   ok(cudaMallocHost(&h->h_res, (size_t)cfg->max_pairs * sizeof(PagkPairResult)));
@@ -272,7 +289,7 @@ void pagk_destroy(pagk_handle *h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   cudaFree(h->d_images); cudaFree(h->d_keys_un); cudaFree(h->d_keys); cudaFree(h->d_pc); cudaFree(h->d_res);
-  cudaFree(h->d_out); cudaFree(h->d_ntab);
+  cudaFree(h->d_out); cudaFree(h->d_ntab); cudaFree(h->d_work);
   cudaFreeHost(h->h_in); cudaFreeHost(h->h_out); cudaFreeHost(h->h_res);
   for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -360,8 +377,7 @@ int pagk_run_resident(pagk_handle *h) {
   CU((cudaError_t)pagk_launch_predict(h->d_pc, h->d_keys_un, h->d_keys, o, h->mode, h->cfg.max_keys, h->n_max, h->n_pairs,
                                       h->geom.width, h->geom.height, h->d_ntab, h->ntab_stride, st, &h->launches));
   CU(cudaEventRecord(h->ev[2], st));
-  if (lk) CU((cudaError_t)pagk_launch_lk(h->d_images, h->geom, h->d_pc, h->d_keys_un, o, h->mode, h->cfg.max_keys, h->n_max,
-                                         h->n_pairs, st, &h->launches));
+  if (lk) CU((cudaError_t)launch_lk(h, o, h->mode, h->n_max, h->n_pairs));
   CU(cudaEventRecord(h->ev[3], st));
   if (lk) CU((cudaError_t)pagk_launch_epilogue(h->d_pc, o, h->mode, h->cfg.max_keys, h->n_pairs, h->d_res, 1, st, &h->launches));
   else {
@@ -574,7 +590,7 @@ int pagk_patch_match(pagk_handle *h, const pagk_patch_match_in *in, pagk_pair_ou
   CU((cudaError_t)pagk_launch_pyramids(h->d_images, h->geom, 2, st, &h->launches));
   CU(cudaEventRecord(h->ev[1], st));
   CU(cudaEventRecord(h->ev[2], st));
-  CU((cudaError_t)pagk_launch_lk(h->d_images, h->geom, h->d_pc, h->d_keys_un, o, m, h->cfg.max_keys, in->n_keys, 1, st, &h->launches));
+  CU((cudaError_t)launch_lk(h, o, m, in->n_keys, 1));
   CU(cudaEventRecord(h->ev[3], st));
   CU((cudaError_t)pagk_launch_epilogue(h->d_pc, o, m, h->cfg.max_keys, 1, h->d_res, 0, st, &h->launches));
   CU(cudaEventRecord(h->ev[4], st));

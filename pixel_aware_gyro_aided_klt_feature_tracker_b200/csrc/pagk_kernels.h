@@ -15,3 +15,10 @@ int pagk_launch_epilogue(const PagkPairConst *pcs, const PagkOutPtrs &out, const
                          int n_pairs, PagkPairResult *res, int do_filter, cudaStream_t st, long long *launches);
 int pagk_launch_count_status(const PagkPairConst *pcs, const PagkOutPtrs &out, int max_keys, int n_pairs,
                              PagkPairResult *res, cudaStream_t st, long long *launches);
+
+// production patch-alignment kernel (pagk_lk_slots.cu): persistent CTAs, 32 feature slots each
+size_t pagk_lk_slots_smem();
+bool pagk_lk_slots_supported(const PagkMode &mode);
+int pagk_launch_lk_slots(const unsigned char *images, const PagkGeom &g, const PagkPairConst *pcs, const float2 *keys_un,
+                         const PagkOutPtrs &out, const PagkMode &mode, int max_keys, int n_max, int n_pairs,
+                         int *work_counter, int n_sms, cudaStream_t st, long long *launches);

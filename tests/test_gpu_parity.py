@@ -56,3 +56,27 @@ def test_track_config_B_pair(gpu_ctx, oracle):
     for g, c in zip(gpu, cpu):
         helpers.assert_north_star(g, c)
         helpers.assert_bit_exact(g, c)
+
+
+def test_generic_kernel_still_bit_exact(cuda_lib, oracle, monkeypatch):
+    """the any-patch-size kernel (PAGK_LK_KERNEL=generic) stays a second implementation to compare against"""
+    from pixel_aware_gyro_aided_klt_feature_tracker_b200 import tracker
+    monkeypatch.setenv("PAGK_LK_KERNEL", "generic")
+    pairs = [synth.make_pair(7100 + i, width=320, height=240, n_keys=200, pyramids=3, border=20) for i in range(2)]
+    prm = capi.default_params(pyramids=3)
+    with tracker.Context(max_width=320, max_height=240, max_keys=200, max_pairs=2, max_levels=3) as ctx:
+        gpu = ctx.track_batch(pairs, prm)
+    rc, cpu = oracle.track_batch(pairs, prm, 4)
+    for g, c in zip(gpu, cpu):
+        helpers.assert_bit_exact(g, c)
+
+
+def test_border_features_bit_exact(gpu_ctx, oracle):
+    """keypoints right up to the image border: clamped taps, guard row, gyro border rejections"""
+    p = synth.make_pair(7200, width=320, height=240, n_keys=600, pyramids=3, border=0, sigma_w=2.0)
+    prm = capi.default_params(pyramids=3)
+    gpu = gpu_ctx.track_batch([p], prm)[0]
+    rc, cpu = oracle.track(p, prm, 4)
+    assert (cpu.status == 0).any() and (cpu.status == 1).any()
+    helpers.assert_north_star(gpu, cpu)
+    helpers.assert_bit_exact(gpu, cpu)
