@@ -8,16 +8,22 @@
 //   B  14 sums over those pixels that MUST be taken in the reference's pixel order in double
 //      (H is structurally singular, SURVEY.md F3: any other order changes the solve), then a 4x4
 //      LLT and the convergence logic -- serial per feature, independent across features.
-// A persistent CTA therefore owns SLOTS = 32 features ("slots") at once:
-//   phase A  each of the 8 warps takes 4 slots; its 32 lanes are the pixels of one slot at a time.
+// One persistent CTA per SM owns SLOTS = 64 features ("slots") in two groups of 32 and runs a
+// two-stage software pipeline: in every stage the warps do phase A on one group while phase B runs
+// on the other group, then the groups swap (one __syncthreads per stage).
+//   phase A  a warp takes one slot at a time from a shared cursor; its 32 lanes are the pixels.
 //            The current-image window of a slot is staged once per level in shared memory as
 //            float (no u8 conversions or 64-bit addressing in the loop); the template value T of
-//            each pixel is kept beside the pixel's (Ix, Iy, e) record, so one float4 per pixel
+//            each pixel is kept beside the pixel's (Ix, Iy, -e) record, so one float4 per pixel
 //            is the whole A->B hand-over.
-//   phase B  one warp, lane = slot: 12 dependent DFMA chains per lane walk the slot's 121 records
-//            in order (LDS.128 per step, conflict-free slot stride), then every lane solves its own
-//            4x4 system, applies the update and advances its slot's state machine (next iteration,
-//            next level, or fetch the next feature from a global counter).
+//   phase B  lane = slot of the group, full lane occupancy (the float->double conversions run on
+//            the 16-lane conversion pipe, so they must not be replicated).  Warp 0 walks the slot's
+//            121 records in order with the eight H chains, warp 1 with the four b chains and the
+//            float cost chain (LDS.128 per step, conflict-free slot stride); warp 0 then solves the
+//            4x4 system of every slot, applies the update and advances the slot's state machine
+//            (next iteration, next level, or the next feature).  Warp 1 meanwhile tops up a queue
+//            of prefetched feature descriptors from the global work counter, so fetching never
+//            sits on the solver's critical path.  Both join phase A when they are done.
 // Slots refill independently, so lanes never wait for the slowest feature of a group.
 //
 // Bit-exactness of the window path.  The reference samples at (sx, sy), (sx+-1, sy), (sx, sy+-1) with
@@ -37,58 +43,112 @@ constexpr int HALF = 5;
 constexpr int P = 2 * HALF + 1;
 constexpr int NP = P * P;                 // 121
 constexpr int PASSES = (NP + 31) / 32;    // 4
-constexpr int SLOTS = 32;
-constexpr int WARPS = 8;
+constexpr int SLOTS = 64;
+constexpr int HSLOTS = SLOTS / 2;         // one group = 32 slots = the lanes of a B warp
+constexpr int WARPS = 16;
 constexpr int THREADS = WARPS * 32;
-constexpr int SLOTS_PER_WARP = SLOTS / WARPS;
 constexpr int WIN_W = 21;                 // window width == row stride (21: rows of a pass land in distinct banks)
-constexpr int WIN_H = 18;
+constexpr int WIN_H = 17;
 constexpr int REC_STRIDE = NP;            // float4 records per slot; 484 words = 4 mod 32 -> LDS.128 conflict-free over slots
+constexpr int QCAP = 64;                  // prefetched feature descriptors
 
 struct SlotShared {
-  float4 rec[SLOTS][REC_STRIDE];          // (Ix, Iy, e, T) per pixel
+  float4 rec[SLOTS][REC_STRIDE];          // (Ix, Iy, -e, T) per pixel
   float win[SLOTS][WIN_W * WIN_H];
-  // slot state, written by the B lane (and the window origin / cval by the A warp)
+  double exch[HSLOTS][4];                 // b0..b3 of warp 1, handed to the solver
+  float exch_cost[HSLOTS];
+  // slot state, written by the solver lane (and the window origin / cval by the A warp)
   int feat[SLOTS];                        // pair * max_keys + i, or -1
   int pair[SLOTS];
   int level[SLOTS];
   int needs_setup[SLOTS];
+  int rec_valid[SLOTS];
   int win_x0[SLOTS], win_y0[SLOTS], win_valid[SLOTS];
   float ptx[SLOTS], pty[SLOTS], dx[SLOTS], dy[SLOTS], dg[SLOTS], db[SLOTS], cval[SLOTS];
   float a00[SLOTS], a01[SLOTS], a10[SLOTS], a11[SLOTS];
   float wxmin[SLOTS], wxmax[SLOTS], wymin[SLOTS], wymax[SLOTS];
-  int any_active;
+  // solver-only state (kept here because a B lane serves one slot of each group)
+  float pt1x[SLOTS], pt1y[SLOTS], lastCost[SLOTS];
+  int iter[SLOTS], n_iter[SLOTS], succ[SLOTS];
+  // queue of prefetched trackable features (ring; producer = warp 1, consumer = warp 0)
+  int q_feat[QCAP], q_pair[QCAP];
+  float q_pt1x[QCAP], q_pt1y[QCAP], q_pt2x[QCAP], q_pt2y[QCAP], q_a00[QCAP], q_a01[QCAP], q_a10[QCAP], q_a11[QCAP];
+  int q_head, q_tail;                     // monotonically increasing; index = value % QCAP
+  int lv_cols[PAGK_MAX_LEVELS], lv_rows[PAGK_MAX_LEVELS];
+  unsigned int lv_off[PAGK_MAX_LEVELS];
+  int a_cursor[2];                        // double-buffered by stage parity
+  int cons_more[2], prod_more[2];         // "keep going" votes of the consumer and the producer
 };
 
-__device__ __forceinline__ const unsigned char *level_ptr(const unsigned char *images, const PagkGeom &g, int pair,
-                                                          int which, int level) {
-  return images + (size_t)(pair * 2 + which) * g.slot_bytes + g.lv[level].offset;
+// Stage the WIN_W x WIN_H window with origin (x0, y0) of a level into shared memory as float; lane j < WIN_W
+// owns column j.  Coordinates are clamped into [0, cols] x [0, rows] (the level plus its wrap column and
+// guard row), so every load is in bounds and unconditional: the 17 loads of a lane are issued back to back.
+// Elements whose true position lies outside that range hold an arbitrary in-bounds pixel; callers never
+// read them.
+__device__ __forceinline__ void stage_window(float *__restrict__ win, const unsigned char *__restrict__ img, int cols,
+                                             int rows, int x0, int y0, int lane) {
+  if (lane < WIN_W) {
+    const int gx = min(max(x0 + lane, 0), cols);
+    unsigned char v[WIN_H];
+#pragma unroll
+    for (int i = 0; i < WIN_H; ++i) {
+      const int gy = min(max(y0 + i, 0), rows);
+      v[i] = __ldg(img + gy * cols + gx);
+    }
+#pragma unroll
+    for (int i = 0; i < WIN_H; ++i) win[i * WIN_W + lane] = (float)v[i];
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
-// phase A for one slot (whole warp)
+// phase A for one slot (whole warp).  xf/yf: this lane's pixel offsets of the four passes.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void phase_a_slot(SlotShared &S, int s, int lane, const unsigned char *__restrict__ images,
-                                             const PagkGeom &g, const PagkMode &mode) {
+__device__ __forceinline__ void phase_a_slot(SlotShared &S, int s, int lane, const float (&xf)[PASSES],
+                                             const float (&yf)[PASSES], const unsigned char *__restrict__ images,
+                                             unsigned long long slot_bytes, const PagkMode &mode) {
   const int level = S.level[s], pair = S.pair[s];
-  const unsigned char *I1 = level_ptr(images, g, pair, 0, level);
-  const unsigned char *I2 = level_ptr(images, g, pair, 1, level);
-  const int cols = g.lv[level].cols, rows = g.lv[level].rows;
+  const int cols = S.lv_cols[level], rows = S.lv_rows[level];
+  const unsigned char *I1 = images + (size_t)(pair * 2) * slot_bytes + S.lv_off[level];
+  const unsigned char *I2 = I1 + slot_bytes;
   const float ptx = S.ptx[s], pty = S.pty[s];
   float4 *rec = S.rec[s];
   float *win = S.win[s];
+  const float hf = (float)HALF;
 
-  if (S.needs_setup[s]) {  // new level: template values and c = -I1(pt)
+  if (S.needs_setup[s]) {  // new level: template values T = I1(pt + (x, y)) and c = -I1(pt)
+    const float txlo = ptx + (-hf), txhi = ptx + hf, tylo = pty + (-hf), tyhi = pty + hf;
+    float c;
+    if (txlo >= 0.0f && txhi < (float)cols && tylo >= 0.0f && tyhi < (float)rows) {
+      // no clamp fires anywhere in the template: sample from a staged window of the reference level
+      const int x0 = (int)txlo, y0 = (int)tylo;
+      __syncwarp();  // taps reach floor(hi) + 1 <= x0 + 12: inside the 21 x 17 window
+      stage_window(win, I1, cols, rows, x0, y0, lane);
+      __syncwarp();
 #pragma unroll
-    for (int k = 0; k < PASSES; ++k) {
-      const int p = lane + 32 * k;
-      if (p < NP) {
-        const int y = p / P - HALF, x = p % P - HALF;
-        rec[p].w = pagk_sample(I1, cols, rows, ptx + (float)x, pty + (float)y);
+      for (int k = 0; k < PASSES; ++k) {
+        const int p = lane + 32 * k;
+        if (p < NP) {
+          const float cx = ptx + xf[k], cy = pty + yf[k];
+          const float fx = floorf(cx), fy = floorf(cy);
+          const float xx = cx - fx, yy = cy - fy, a = 1.0f - xx, b = 1.0f - yy;
+          const float *q = win + ((int)fy - y0) * WIN_W + ((int)fx - x0);
+          rec[p].w = b * (a * q[0] + xx * q[1]) + yy * (a * q[WIN_W] + xx * q[WIN_W + 1]);
+        }
       }
+      {
+        const float fx = floorf(ptx), fy = floorf(pty);
+        const float xx = ptx - fx, yy = pty - fy, a = 1.0f - xx, b = 1.0f - yy;
+        const float *q = win + ((int)fy - y0) * WIN_W + ((int)fx - x0);
+        c = -(b * (a * q[0] + xx * q[1]) + yy * (a * q[WIN_W] + xx * q[WIN_W + 1]));
+      }
+    } else {
+#pragma unroll 1
+      for (int k = 0; k < PASSES; ++k) {
+        const int p = lane + 32 * k;
+        if (p < NP) rec[p].w = pagk_sample(I1, cols, rows, ptx + xf[k], pty + yf[k]);
+      }
+      c = -pagk_sample(I1, cols, rows, ptx, pty);
     }
-    const float c = -pagk_sample(I1, cols, rows, ptx, pty);
-    __syncwarp();
     if (lane == 0) { S.cval[s] = c; S.needs_setup[s] = 0; S.win_valid[s] = 0; }
     __syncwarp();
   }
@@ -102,8 +162,8 @@ __device__ __forceinline__ void phase_a_slot(SlotShared &S, int s, int lane, con
   bool use_window = (x2min >= 0.0f) && (x1max < (float)cols) && (y2min >= 0.0f) && (y1max < (float)rows);
   int wx0 = 0, wy0 = 0;
   if (use_window) {
-    const int ixlo = (int)floorf(x2min), ixhi = (int)floorf(x1max) + 1;
-    const int iylo = (int)floorf(y2min), iyhi = (int)floorf(y1max) + 1;
+    const int ixlo = (int)x2min, ixhi = (int)x1max + 1;  // non-negative: truncation == floor
+    const int iylo = (int)y2min, iyhi = (int)y1max + 1;
     const int needw = ixhi - ixlo + 1, needh = iyhi - iylo + 1;
     if (needw > WIN_W || needh > WIN_H) {
       use_window = false;
@@ -114,13 +174,7 @@ __device__ __forceinline__ void phase_a_slot(SlotShared &S, int s, int lane, con
         wx0 = ixlo - (WIN_W - needw) / 2;
         wy0 = iylo - (WIN_H - needh) / 2;
         __syncwarp();
-        for (int idx = lane; idx < WIN_W * WIN_H; idx += 32) {
-          const int j = idx % WIN_W, i = idx / WIN_W;
-          const int gx = wx0 + j, gy = wy0 + i;
-          float v = 0.0f;
-          if (gx >= 0 && gx <= cols && gy >= 0 && gy <= rows) v = (float)__ldg(I2 + (size_t)gy * cols + gx);
-          win[idx] = v;
-        }
+        stage_window(win, I2, cols, rows, wx0, wy0, lane);
         if (lane == 0) { S.win_x0[s] = wx0; S.win_y0[s] = wy0; S.win_valid[s] = 1; }
         __syncwarp();
       }
@@ -133,9 +187,8 @@ __device__ __forceinline__ void phase_a_slot(SlotShared &S, int s, int lane, con
     for (int k = 0; k < PASSES; ++k) {
       const int p = lane + 32 * k;
       if (p < NP) {
-        const float xf = (float)(p % P - HALF), yf = (float)(p / P - HALF);
-        float wx = xf, wy = yf;
-        if (mode.affine) { wx = a00 * xf + a01 * yf; wy = a10 * xf + a11 * yf; }
+        float wx = xf[k], wy = yf[k];
+        if (mode.affine) { wx = a00 * xf[k] + a01 * yf[k]; wy = a10 * xf[k] + a11 * yf[k]; }
         const float sx = bx + wx, sy = by + wy;
         const float fx = floorf(sx), fy = floorf(sy);
         const float xx = sx - fx, yy = sy - fy;
@@ -159,7 +212,7 @@ __device__ __forceinline__ void phase_a_slot(SlotShared &S, int s, int lane, con
         const float vy1 = b1 * H1 + yy1 * H2, vy2 = b * Hm + yy * H0;
         const float T = rec[p].w;
         const float e = (v0 + db) - gain * T;
-        rec[p] = make_float4(0.5f * (vx1 - vx2), 0.5f * (vy1 - vy2), e, T);
+        rec[p] = make_float4(0.5f * (vx1 - vx2), 0.5f * (vy1 - vy2), -e, T);
       }
     }
     bad = __any_sync(0xffffffffu, bad);
@@ -169,188 +222,269 @@ __device__ __forceinline__ void phase_a_slot(SlotShared &S, int s, int lane, con
     for (int k = 0; k < PASSES; ++k) {
       const int p = lane + 32 * k;
       if (p < NP) {
-        const float xf = (float)(p % P - HALF), yf = (float)(p / P - HALF);
-        float wx = xf, wy = yf;
-        if (mode.affine) { wx = a00 * xf + a01 * yf; wy = a10 * xf + a11 * yf; }
+        float wx = xf[k], wy = yf[k];
+        if (mode.affine) { wx = a00 * xf[k] + a01 * yf[k]; wy = a10 * xf[k] + a11 * yf[k]; }
         const float sx = bx + wx, sy = by + wy;
         const float T = rec[p].w;
         const float e = (pagk_sample(I2, cols, rows, sx, sy) + db) - gain * T;
         const float gx = pagk_sample(I2, cols, rows, sx + 1.0f, sy) - pagk_sample(I2, cols, rows, sx - 1.0f, sy);
         const float gy = pagk_sample(I2, cols, rows, sx, sy + 1.0f) - pagk_sample(I2, cols, rows, sx, sy - 1.0f);
-        rec[p] = make_float4(0.5f * gx, 0.5f * gy, e, T);
+        rec[p] = make_float4(0.5f * gx, 0.5f * gy, -e, T);
       }
     }
   }
+  if (lane == 0) S.rec_valid[s] = 1;
 }
 
-// per-lane (= per-slot) state of the B warp that is not needed by phase A
-struct LaneState {
-  float pt1x, pt1y;      // mvKeysRefUn[i].pt
-  float cost, lastCost;
-  int iter;              // iteration index inside the level
-  int n_iter;            // passes over all levels (output)
-  bool succ;
-};
+__device__ __forceinline__ void named_barrier_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 }  // namespace
 
-__global__ void __launch_bounds__(THREADS, 2)
+__global__ void __launch_bounds__(THREADS, 1)
 pagk_lk_slots_kernel(const unsigned char *__restrict__ images, PagkGeom g, const PagkPairConst *__restrict__ pcs,
                      const float2 *__restrict__ keys_un, PagkOutPtrs out, PagkMode mode, int max_keys, int n_max,
                      int n_pairs, int *__restrict__ work_counter) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SlotShared &S = *reinterpret_cast<SlotShared *>(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int b_warp = blockIdx.x % WARPS;  // spread the FP64-heavy warp of co-resident CTAs over the SM sub-partitions
   const int total_work = n_pairs * n_max;
   const int top = mode.levels - 1;
+  const unsigned long long slot_bytes = g.slot_bytes;
 
-  LaneState L;
-  L.pt1x = L.pt1y = 0.f; L.cost = L.lastCost = 0.f; L.iter = 0; L.n_iter = 0; L.succ = true;
-  bool exhausted = false;
-  if (warp == b_warp) { S.feat[lane] = -1; S.needs_setup[lane] = 0; S.win_valid[lane] = 0; }
+  float xf[PASSES], yf[PASSES];
+#pragma unroll
+  for (int k = 0; k < PASSES; ++k) {
+    const int p = lane + 32 * k;
+    xf[k] = (float)(p % P - HALF);
+    yf[k] = (float)(p / P - HALF);
+  }
 
-  // fetch features for every empty slot of this CTA (B warp only, lane = slot)
-  auto refill = [&]() {
-    while (true) {
-      const bool want = (S.feat[lane] < 0) && !exhausted;
-      const unsigned m = __ballot_sync(0xffffffffu, want);
-      if (m == 0u) break;
-      int base = 0;
-      if (lane == 0) base = atomicAdd(work_counter, __popc(m));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (want) {
-        const int wi = base + __popc(m & ((1u << lane) - 1u));
-        if (wi >= total_work) {
-          exhausted = true;
-        } else {
-          const int pair = wi / n_max, i = wi % n_max;
-          if (i < pcs[pair].n_keys) {
-            const size_t o = (size_t)pair * max_keys + i;
-            const float2 pt1 = keys_un[o];
-            const float2 pt2 = mode.gyro_init ? out.pt_predict_un[o] : pt1;
-            if (!out.gyro_status[o]) {  // skipped by the reference (src/patch_match.cpp:173): defaults only
-              out.pm_un[o] = pt2; out.pm_status[o] = 0; out.pix_err[o] = 0.0; out.ncc[o] = 0.f; out.iters[o] = 0;
-            } else {
-              const float4 A = out.affine[o];
-              const float scale = 1.0f / (float)(1 << top);
-              const float ptx = pt1.x * scale, pty = pt1.y * scale;
-              S.feat[lane] = (int)o; S.pair[lane] = pair; S.level[lane] = top; S.needs_setup[lane] = 1;
-              S.ptx[lane] = ptx; S.pty[lane] = pty;
-              S.dx[lane] = pt2.x * scale - ptx; S.dy[lane] = pt2.y * scale - pty;
-              S.dg[lane] = 0.f; S.db[lane] = 0.f;
-              S.a00[lane] = A.x; S.a01[lane] = A.y; S.a10[lane] = A.z; S.a11[lane] = A.w;
-              const float hf = (float)HALF;
-              float x0 = -hf, x1 = hf, y0 = -hf, y1 = hf;
-              if (mode.affine) {  // the warp offsets at the four patch corners, exactly as phase A computes them
-                const float c0x = A.x * -hf + A.y * -hf, c1x = A.x * hf + A.y * -hf, c2x = A.x * -hf + A.y * hf, c3x = A.x * hf + A.y * hf;
-                const float c0y = A.z * -hf + A.w * -hf, c1y = A.z * hf + A.w * -hf, c2y = A.z * -hf + A.w * hf, c3y = A.z * hf + A.w * hf;
-                x0 = fminf(fminf(c0x, c1x), fminf(c2x, c3x)); x1 = fmaxf(fmaxf(c0x, c1x), fmaxf(c2x, c3x));
-                y0 = fminf(fminf(c0y, c1y), fminf(c2y, c3y)); y1 = fmaxf(fmaxf(c0y, c1y), fmaxf(c2y, c3y));
-              }
-              S.wxmin[lane] = x0; S.wxmax[lane] = x1; S.wymin[lane] = y0; S.wymax[lane] = y1;
-              L.pt1x = pt1.x; L.pt1y = pt1.y; L.cost = 0.f; L.lastCost = 0.f; L.iter = 0; L.n_iter = 0; L.succ = true;
-            }
-          }
-        }
-      }
-    }
-  };
-
-  if (warp == b_warp) {
-    refill();
-    const unsigned act = __ballot_sync(0xffffffffu, S.feat[lane] >= 0);
-    if (lane == 0) S.any_active = (act != 0u);
+  bool exhausted = false;  // producer (warp 1) only
+  if (warp == 0) {
+    for (int s = lane; s < SLOTS; s += 32) { S.feat[s] = -1; S.needs_setup[s] = 0; S.win_valid[s] = 0; S.rec_valid[s] = 0; }
+    if (lane < PAGK_MAX_LEVELS) { S.lv_cols[lane] = g.lv[lane].cols; S.lv_rows[lane] = g.lv[lane].rows; S.lv_off[lane] = g.lv[lane].offset; }
+    if (lane == 0) { S.a_cursor[0] = 0; S.a_cursor[1] = 0; S.q_head = 0; S.q_tail = 0; }
   }
   __syncthreads();
 
-  while (S.any_active) {
-    // ------------------------------ phase A: all warps, SLOTS_PER_WARP slots each ------------------------------
-#pragma unroll 1
-    for (int q = 0; q < SLOTS_PER_WARP; ++q) {
-      const int s = warp + q * WARPS;
-      if (S.feat[s] >= 0) phase_a_slot(S, s, lane, images, g, mode);
-    }
-    __syncthreads();
-    // ------------------------------ phase B: one warp, lane = slot ------------------------------
-    if (warp == b_warp) {
-      const int s = lane;
-      const bool active = S.feat[s] >= 0;
-      double h00 = 0, h10 = 0, h11 = 0, h20 = 0, h21 = 0, h22 = 0, h30 = 0, h31 = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0;
-      float cost = 0.f;
-      const double c = (double)S.cval[s];
-      const float4 *rec = S.rec[s];
-#pragma unroll 2
-      for (int p = 0; p < NP; ++p) {
-        const float4 r = rec[p];
-        const double ix = (double)r.x, iy = (double)r.y, me = -(double)r.z;
-        h00 = fma(ix, ix, h00); h10 = fma(iy, ix, h10); h11 = fma(iy, iy, h11);
-        h20 = fma(c, ix, h20); h21 = fma(c, iy, h21); h22 = fma(c, c, h22);
-        h30 = h30 + ix; h31 = h31 + iy;
-        b0 = fma(ix, me, b0); b1 = fma(iy, me, b1); b2 = fma(c, me, b2); b3 = b3 + me;
-        cost = cost + r.z * r.z;
-      }
-      if (active) {
-        double h32 = c * (double)NP, h33 = (double)NP;  // sum of c and of 1 over the patch: exact in double
-        float dx = S.dx[s], dy = S.dy[s], dg = S.dg[s], db = S.db[s];
-        if (mode.regular) {  // reference src/patch_match.cpp:302-314
-          const double d = (double)sqrtf(dx * dx + dy * dy);
-          const float li = mode.lambda * mode.inv_log_max_dist;
-          const double ad1 = (double)mode.alpha * d + 1.0;
-          const double e_pen = (double)li * log(ad1);
-          const double jx = ((double)(li * mode.alpha) / ad1) * ((double)dx / d);
-          const double jy = ((double)(li * mode.alpha) / ad1) * ((double)dy / d);
-          h00 += jx * jx; h10 += jy * jx; h11 += jy * jy;
-          h20 += 0.0 * jx; h21 += 0.0 * jy; h30 += 0.0 * jx; h31 += 0.0 * jy;
-          b0 += jx * e_pen; b1 += jy * e_pen; b2 += 0.0 * e_pen; b3 += 0.0 * e_pen;
-          cost = (float)((double)cost + e_pen * e_pen);
-        }
-        double u0, u1, u2, u3;
-        pagk_llt_solve4(h00, h10, h11, h20, h21, h22, h30, h31, h32, h33, b0, b1, b2, b3, u0, u1, u2, u3);
-        ++L.n_iter;
-        bool level_done = false;
-        if (isnan(u0)) {
-          L.succ = false; level_done = true;
-        } else if (L.iter > 0 && cost > L.lastCost) {
-          level_done = true;
-        } else {
-          dx = (float)((double)dx + u0);
-          dy = (float)((double)dy + u1);
-          if (mode.illum) { dg = (float)((double)dg + u2); db = (float)((double)db + u3); }
-          L.lastCost = cost;
-          L.succ = true;
-          ++L.iter;
-          const double nrm = sqrt((u0 * u0 + u2 * u2) + (u1 * u1 + u3 * u3));
-          if (nrm < 1e-2 || L.iter >= mode.iterations) level_done = true;
-        }
-        if (!level_done) {
-          S.dx[s] = dx; S.dy[s] = dy; S.dg[s] = dg; S.db[s] = db;
-        } else {
-          const float p2x = S.ptx[s] + dx, p2y = S.pty[s] + dy;  // mvPtPyr2Un[i] = pt + (dx, dy)
-          const int level = S.level[s];
-          if (level == 0) {
-            const size_t o = (size_t)S.feat[s];
-            out.pm_un[o] = make_float2(p2x, p2y);
-            out.pm_status[o] = L.succ ? 1 : 0;
-            out.pix_err[o] = sqrt((double)L.lastCost * mode.win_size_inv);
-            out.ncc[o] = 1.0f;
-            out.iters[o] = L.n_iter;
-            S.feat[s] = -1;
+  // producer (warp 1): top the queue up to QCAP entries counted from `head`; features the reference
+  // skips (gyro status 0, src/patch_match.cpp:173) get their default outputs here and are not queued
+  auto produce = [&](int head, int tail) -> int {
+    int t = tail;
+    while (!exhausted && (t - head) + 32 <= QCAP) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(work_counter, 32);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (base >= total_work) { exhausted = true; break; }
+      const int wi = base + lane;
+      bool ok = false;
+      int pair = 0;
+      size_t o = 0;
+      float2 pt1 = make_float2(0.f, 0.f), pt2 = pt1;
+      float4 A = make_float4(1.f, 0.f, 0.f, 1.f);
+      if (wi < total_work) {
+        pair = wi / n_max;
+        const int i = wi % n_max;
+        if (i < pcs[pair].n_keys) {
+          o = (size_t)pair * max_keys + i;
+          pt1 = keys_un[o];
+          pt2 = mode.gyro_init ? out.pt_predict_un[o] : pt1;
+          if (!out.gyro_status[o]) {
+            out.pm_un[o] = pt2; out.pm_status[o] = 0; out.pix_err[o] = 0.0; out.ncc[o] = 0.f; out.iters[o] = 0;
           } else {
-            const int nl = level - 1;
-            const float scale = 1.0f / (float)(1 << nl);
-            const float ptx = L.pt1x * scale, pty = L.pt1y * scale;
-            S.level[s] = nl; S.needs_setup[s] = 1;
-            S.ptx[s] = ptx; S.pty[s] = pty;
-            S.dx[s] = p2x * 2.0f - ptx; S.dy[s] = p2y * 2.0f - pty;
-            S.dg[s] = 0.f; S.db[s] = 0.f;
-            L.iter = 0; L.lastCost = 0.f; L.succ = true;
+            A = out.affine[o];
+            ok = true;
           }
         }
       }
-      refill();
-      const unsigned act = __ballot_sync(0xffffffffu, S.feat[lane] >= 0);
-      if (lane == 0) S.any_active = (act != 0u);
+      const unsigned m = __ballot_sync(0xffffffffu, ok);
+      if (ok) {
+        const int q = (t + __popc(m & ((1u << lane) - 1u))) % QCAP;
+        S.q_feat[q] = (int)o; S.q_pair[q] = pair;
+        S.q_pt1x[q] = pt1.x; S.q_pt1y[q] = pt1.y; S.q_pt2x[q] = pt2.x; S.q_pt2y[q] = pt2.y;
+        S.q_a00[q] = A.x; S.q_a01[q] = A.y; S.q_a10[q] = A.z; S.q_a11[q] = A.w;
+      }
+      t += __popc(m);
+    }
+    return t;
+  };
+
+  // consumer (warp 0): give every empty slot of group `grp` a queued feature; returns the new head
+  auto consume = [&](int grp, int head, int tail) -> int {
+    const int s = grp * HSLOTS + lane;
+    const bool want = S.feat[s] < 0;
+    const unsigned m = __ballot_sync(0xffffffffu, want);
+    const int rank = __popc(m & ((1u << lane) - 1u));
+    if (want && head + rank < tail) {
+      const int q = (head + rank) % QCAP;
+      const float pt1x = S.q_pt1x[q], pt1y = S.q_pt1y[q], pt2x = S.q_pt2x[q], pt2y = S.q_pt2y[q];
+      const float a00 = S.q_a00[q], a01 = S.q_a01[q], a10 = S.q_a10[q], a11 = S.q_a11[q];
+      const float scale = 1.0f / (float)(1 << top);
+      const float ptx = pt1x * scale, pty = pt1y * scale;
+      S.feat[s] = S.q_feat[q]; S.pair[s] = S.q_pair[q]; S.level[s] = top; S.needs_setup[s] = 1; S.rec_valid[s] = 0;
+      S.ptx[s] = ptx; S.pty[s] = pty;
+      S.dx[s] = pt2x * scale - ptx; S.dy[s] = pt2y * scale - pty;
+      S.dg[s] = 0.f; S.db[s] = 0.f;
+      S.a00[s] = a00; S.a01[s] = a01; S.a10[s] = a10; S.a11[s] = a11;
+      const float hf = (float)HALF;
+      float x0 = -hf, x1 = hf, y0 = -hf, y1 = hf;
+      if (mode.affine) {  // the warp offsets at the four patch corners, exactly as phase A computes them
+        const float c0x = a00 * -hf + a01 * -hf, c1x = a00 * hf + a01 * -hf, c2x = a00 * -hf + a01 * hf, c3x = a00 * hf + a01 * hf;
+        const float c0y = a10 * -hf + a11 * -hf, c1y = a10 * hf + a11 * -hf, c2y = a10 * -hf + a11 * hf, c3y = a10 * hf + a11 * hf;
+        x0 = fminf(fminf(c0x, c1x), fminf(c2x, c3x)); x1 = fmaxf(fmaxf(c0x, c1x), fmaxf(c2x, c3x));
+        y0 = fminf(fminf(c0y, c1y), fminf(c2y, c3y)); y1 = fmaxf(fmaxf(c0y, c1y), fmaxf(c2y, c3y));
+      }
+      S.wxmin[s] = x0; S.wxmax[s] = x1; S.wymin[s] = y0; S.wymax[s] = y1;
+      S.pt1x[s] = pt1x; S.pt1y[s] = pt1y; S.lastCost[s] = 0.f; S.iter[s] = 0; S.n_iter[s] = 0; S.succ[s] = 1;
+    }
+    const int taken = min(__popc(m), tail - head);
+    return head + taken;
+  };
+
+  // prologue: fill the queue, then both groups
+  if (warp == 1) {
+    const int t = produce(0, 0);
+    if (lane == 0) S.q_tail = t;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    int head = consume(0, 0, S.q_tail);
+    __syncwarp();
+    head = consume(1, head, S.q_tail);
+    if (lane == 0) S.q_head = head;
+    const unsigned act = __ballot_sync(0xffffffffu, S.feat[lane] >= 0 || S.feat[HSLOTS + lane] >= 0);
+    if (lane == 0) { S.cons_more[0] = (act != 0u); S.prod_more[0] = 1; }
+  }
+  __syncthreads();
+
+  // stage t: phase A on group (t & 1), phase B on the other group.  Cursors and votes are
+  // double-buffered by stage parity so that one barrier per stage is enough.
+  for (int t = 0; S.cons_more[t & 1] | S.prod_more[t & 1]; ++t) {
+    const int hA = t & 1, hB = hA ^ 1;
+    if (threadIdx.x == 0) S.a_cursor[hB] = 0;  // the cursor of the next stage; nobody reads it during this one
+    if (warp < 2) {
+      // ------------------------------ phase B: lane = slot of group hB ------------------------------
+      const int s = hB * HSLOTS + lane;
+      const int q_head = S.q_head, q_tail = S.q_tail;  // stable since the barrier
+      const bool active = S.feat[s] >= 0 && S.rec_valid[s];
+      const bool any = __any_sync(0xffffffffu, active);
+      const double c = (double)S.cval[s];
+      const float4 *rec = S.rec[s];
+      if (warp == 1) {
+        // ---- b chains (b += -J * e; the record holds -e) and the float cost chain, then prefetch ----
+        double b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+        float cost = 0.f;
+        if (any) {
+#pragma unroll 4
+          for (int p = 0; p < NP; ++p) {
+            const float4 r = rec[p];
+            const double ix = (double)r.x, iy = (double)r.y, me = (double)r.z;
+            b0 = fma(ix, me, b0); b1 = fma(iy, me, b1); b2 = fma(c, me, b2); b3 = b3 + me;
+            cost = cost + r.z * r.z;
+          }
+        }
+        S.exch[lane][0] = b0; S.exch[lane][1] = b1; S.exch[lane][2] = b2; S.exch[lane][3] = b3;
+        S.exch_cost[lane] = cost;
+        named_barrier_sync(1, 64);
+        const int nt = produce(q_head, q_tail);
+        if (lane == 0) { S.q_tail = nt; S.prod_more[hB] = (nt > q_tail) || !exhausted; }
+      } else {
+        // ---- H chains, then the solve and the slot state machine ----
+        double h00 = 0, h10 = 0, h11 = 0, h20 = 0, h21 = 0, h22 = 0, h30 = 0, h31 = 0;
+        if (any) {
+#pragma unroll 4
+          for (int p = 0; p < NP; ++p) {
+            const float4 r = rec[p];
+            const double ix = (double)r.x, iy = (double)r.y;
+            h00 = fma(ix, ix, h00); h10 = fma(iy, ix, h10); h11 = fma(iy, iy, h11);
+            h20 = fma(c, ix, h20); h21 = fma(c, iy, h21); h22 = fma(c, c, h22);
+            h30 = h30 + ix; h31 = h31 + iy;
+          }
+        }
+        named_barrier_sync(1, 64);
+        if (active) {
+          double b0 = S.exch[lane][0], b1 = S.exch[lane][1], b2 = S.exch[lane][2], b3 = S.exch[lane][3];
+          float cost = S.exch_cost[lane];
+          const double h32 = c * (double)NP, h33 = (double)NP;  // sum of c and of 1 over the patch: exact in double
+          float dx = S.dx[s], dy = S.dy[s], dg = S.dg[s], db = S.db[s];
+          float lastCost = S.lastCost[s];
+          int iter = S.iter[s];
+          int succ = S.succ[s];
+          if (mode.regular) {  // reference src/patch_match.cpp:302-314
+            const double d = (double)sqrtf(dx * dx + dy * dy);
+            const float li = mode.lambda * mode.inv_log_max_dist;
+            const double ad1 = (double)mode.alpha * d + 1.0;
+            const double e_pen = (double)li * log(ad1);
+            const double jx = ((double)(li * mode.alpha) / ad1) * ((double)dx / d);
+            const double jy = ((double)(li * mode.alpha) / ad1) * ((double)dy / d);
+            h00 += jx * jx; h10 += jy * jx; h11 += jy * jy;
+            h20 += 0.0 * jx; h21 += 0.0 * jy; h30 += 0.0 * jx; h31 += 0.0 * jy;
+            b0 += jx * e_pen; b1 += jy * e_pen; b2 += 0.0 * e_pen; b3 += 0.0 * e_pen;
+            cost = (float)((double)cost + e_pen * e_pen);
+          }
+          double u0, u1, u2, u3;
+          pagk_llt_solve4(h00, h10, h11, h20, h21, h22, h30, h31, h32, h33, b0, b1, b2, b3, u0, u1, u2, u3);
+          const int n_iter = S.n_iter[s] + 1;
+          S.n_iter[s] = n_iter;
+          bool level_done = false;
+          if (isnan(u0)) {
+            succ = 0; level_done = true;
+          } else if (iter > 0 && cost > lastCost) {
+            level_done = true;
+          } else {
+            dx = (float)((double)dx + u0);
+            dy = (float)((double)dy + u1);
+            if (mode.illum) { dg = (float)((double)dg + u2); db = (float)((double)db + u3); }
+            lastCost = cost;
+            succ = 1;
+            ++iter;
+            const double nrm = sqrt((u0 * u0 + u2 * u2) + (u1 * u1 + u3 * u3));
+            if (nrm < 1e-2 || iter >= mode.iterations) level_done = true;
+          }
+          S.rec_valid[s] = 0;
+          if (!level_done) {
+            S.dx[s] = dx; S.dy[s] = dy; S.dg[s] = dg; S.db[s] = db;
+            S.lastCost[s] = lastCost; S.iter[s] = iter; S.succ[s] = succ;
+          } else {
+            const float p2x = S.ptx[s] + dx, p2y = S.pty[s] + dy;  // mvPtPyr2Un[i] = pt + (dx, dy)
+            const int level = S.level[s];
+            if (level == 0) {
+              const size_t o = (size_t)S.feat[s];
+              out.pm_un[o] = make_float2(p2x, p2y);
+              out.pm_status[o] = succ ? 1 : 0;
+              out.pix_err[o] = sqrt((double)lastCost * mode.win_size_inv);
+              out.ncc[o] = 1.0f;
+              out.iters[o] = n_iter;
+              S.feat[s] = -1;
+            } else {
+              const int nl = level - 1;
+              const float scale = 1.0f / (float)(1 << nl);
+              const float ptx = S.pt1x[s] * scale, pty = S.pt1y[s] * scale;
+              S.level[s] = nl; S.needs_setup[s] = 1;
+              S.ptx[s] = ptx; S.pty[s] = pty;
+              S.dx[s] = p2x * 2.0f - ptx; S.dy[s] = p2y * 2.0f - pty;
+              S.dg[s] = 0.f; S.db[s] = 0.f;
+              S.iter[s] = 0; S.lastCost[s] = 0.f; S.succ[s] = 1;
+            }
+          }
+        }
+        __syncwarp();
+        const int nh = consume(hB, q_head, q_tail);
+        if (lane == 0) S.q_head = nh;
+        const unsigned act = __ballot_sync(0xffffffffu, S.feat[lane] >= 0 || S.feat[HSLOTS + lane] >= 0);
+        if (lane == 0) S.cons_more[hB] = (act != 0u) || (q_tail - nh > 0);  // read at the top of stage t + 1
+      }
+    }
+    // ------------------------------ phase A on the other group (every warp, when free) ------------------------------
+    while (true) {
+      int k = 0;
+      if (lane == 0) k = atomicAdd(&S.a_cursor[hA], 1);
+      k = __shfl_sync(0xffffffffu, k, 0);
+      if (k >= HSLOTS) break;
+      const int s = hA * HSLOTS + k;
+      if (S.feat[s] >= 0) phase_a_slot(S, s, lane, xf, yf, images, slot_bytes, mode);
     }
     __syncthreads();
   }
@@ -377,7 +511,7 @@ int pagk_launch_lk_slots(const unsigned char *images, const PagkGeom &g, const P
   cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), st);
   if (e != cudaSuccess) return (int)e;
   const long long total = (long long)n_max * n_pairs;
-  long long ctas = 2LL * n_sms;  // persistent: two CTAs per SM
+  long long ctas = n_sms;  // persistent: one CTA per SM
   const long long needed = (total + SLOTS - 1) / SLOTS;
   if (ctas > needed) ctas = needed;
   pagk_lk_slots_kernel<<<(unsigned)ctas, THREADS, smem, st>>>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs,
