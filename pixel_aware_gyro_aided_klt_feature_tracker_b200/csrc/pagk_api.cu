@@ -76,6 +76,8 @@ struct pagk_handle {
   size_t ntab_stride = 0;  // floats per pair
   int *d_work = nullptr;   // work counter of the persistent LK kernel
   int n_sms = 0;
+  long long *d_dbg = nullptr;  // PAGK_LK_TIMELINE=<file>: clock64 timeline of CTA 0 of the LK kernel (developer aid)
+  const char *dbg_path = nullptr;
   int force_generic = 0;   // PAGK_LK_KERNEL=generic: use the any-patch-size kernel (tests compare both)
   // pinned staging
   unsigned char *h_in = nullptr;   // keys_un | keys | consts
@@ -189,9 +191,27 @@ int check_batch(pagk_handle *h, int n_pairs, int width, int height, int levels, 
 }
 
 int launch_lk(pagk_handle *h, const PagkOutPtrs &o, const PagkMode &m, int n_max, int n_pairs) {
-  if (!h->force_generic && pagk_lk_slots_supported(m))
-    return pagk_launch_lk_slots(h->d_images, h->geom, h->d_pc, h->d_keys_un, o, m, h->cfg.max_keys, n_max, n_pairs, h->d_work,
-                                h->n_sms, h->stream, &h->launches);
+  if (!h->force_generic && pagk_lk_slots_supported(m)) {
+    if (h->d_dbg) cudaMemsetAsync(h->d_dbg, 0, 512 * 16 * sizeof(long long), h->stream);
+    const int rc = pagk_launch_lk_slots(h->d_images, h->geom, h->d_pc, h->d_keys_un, o, m, h->cfg.max_keys, n_max, n_pairs,
+                                        h->d_work, h->n_sms, h->stream, &h->launches, h->d_dbg);
+    if (h->d_dbg && rc == 0) {
+      std::vector<long long> tl(512 * 16);
+      cudaMemcpyAsync(tl.data(), h->d_dbg, tl.size() * sizeof(long long), cudaMemcpyDeviceToHost, h->stream);
+      cudaStreamSynchronize(h->stream);
+      if (FILE *f = fopen(h->dbg_path, "w")) {
+        fprintf(f, "#");
+        for (int b = 0; b < 148; ++b) fprintf(f, " %lld:%lld", tl[6400 + 2 * b], tl[6400 + 2 * b + 1]);
+        fprintf(f, "\n");
+        for (int st = 0; st < 400; ++st) {
+          if (!tl[st * 16]) break;
+          for (int k = 0; k < 16; ++k) fprintf(f, "%lld%c", tl[st * 16 + k], k == 15 ? '\n' : ' ');
+        }
+        fclose(f);
+      }
+    }
+    return rc;
+  }
   return pagk_launch_lk(h->d_images, h->geom, h->d_pc, h->d_keys_un, o, m, h->cfg.max_keys, n_max, n_pairs, h->stream,
                         &h->launches);
 }
@@ -268,6 +288,8 @@ int pagk_create(const pagk_config *cfg, pagk_handle **out) {
   {
     const char *k = getenv("PAGK_LK_KERNEL");
     h->force_generic = (k && std::strcmp(k, "generic") == 0) ? 1 : 0;
+    h->dbg_path = getenv("PAGK_LK_TIMELINE");
+    if (h->dbg_path) { ok(cudaMalloc(&h->d_dbg, 512 * 16 * sizeof(long long))); }
   }
   ok(cudaMallocHost(&h->h_in, h->h_in_bytes));
   ok(cudaMallocHost(&h->h_out, h->out_bytes));
@@ -289,7 +311,7 @@ void pagk_destroy(pagk_handle *h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   cudaFree(h->d_images); cudaFree(h->d_keys_un); cudaFree(h->d_keys); cudaFree(h->d_pc); cudaFree(h->d_res);
-  cudaFree(h->d_out); cudaFree(h->d_ntab); cudaFree(h->d_work);
+  cudaFree(h->d_out); cudaFree(h->d_ntab); cudaFree(h->d_work); cudaFree(h->d_dbg);
   cudaFreeHost(h->h_in); cudaFreeHost(h->h_out); cudaFreeHost(h->h_res);
   for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   if (h->stream) cudaStreamDestroy(h->stream);

@@ -95,59 +95,77 @@ __device__ __forceinline__ float2 pagk_distort(const PagkPairConst &c, float2 p)
   return make_float2(c.fx * xd + c.cx, c.fy * yd + c.cy);
 }
 
+// IEEE double division / square root (kept as named wrappers: out-of-line versions were measured slower)
+__device__ __forceinline__ double pagk_ddiv(double a, double b) { return a / b; }
+__device__ __forceinline__ double pagk_dsqrt(double a) { return sqrt(a); }
+// PatchMatch::GetPixelValue out of line, for the rare per-sample paths of the production kernel
+static __device__ __noinline__ float pagk_sample_call(const unsigned char *__restrict__ img, int cols, int rows, float x, float y) {
+  return pagk_sample(img, cols, rows, x, y);
+}
+
 // Eigen::Matrix4d::llt().solve(b) as Eigen 3.3 evaluates it for a fixed 4x4 (see oracle/pagk_oracle.cpp
 // llt_solve4 for the derivation of the operation order).  Lower triangle of the symmetric H is passed
 // as h00,h10,h11,h20,h21,h22,h30,h31,h32,h33.  --fmad=false keeps every multiply and add separate.
-__device__ __forceinline__ void pagk_llt_solve4(double h00, double h10, double h11, double h20, double h21, double h22,
-                                                double h30, double h31, double h32, double h33, double b0, double b1,
-                                                double b2, double b3, double &x0, double &x1, double &x2, double &x3) {
-  // k = 0
+// Factorisation half: H = L L^T in place on the lower triangle (stops at the first pivot <= 0 like Eigen).
+__device__ __forceinline__ void pagk_llt_factor4(double &h00, double &h10, double &h11, double &h20, double &h21,
+                                                 double &h22, double &h30, double &h31, double &h32, double &h33) {
   bool go = true;
-  {
+  {  // k = 0
     double piv = h00;
     if (piv <= 0.0) go = false;
     if (go) {
-      piv = sqrt(piv);
+      piv = pagk_dsqrt(piv);
       h00 = piv;
-      h10 /= piv; h20 /= piv; h30 /= piv;
+      h10 = pagk_ddiv(h10, piv); h20 = pagk_ddiv(h20, piv); h30 = pagk_ddiv(h30, piv);
     }
   }
   if (go) {  // k = 1
     double piv = h11 - h10 * h10;
     if (piv <= 0.0) go = false;
     if (go) {
-      piv = sqrt(piv);
+      piv = pagk_dsqrt(piv);
       h11 = piv;
       const double t = -1.0 * h10;
       h21 += h20 * t; h31 += h30 * t;
-      h21 /= piv; h31 /= piv;
+      h21 = pagk_ddiv(h21, piv); h31 = pagk_ddiv(h31, piv);
     }
   }
   if (go) {  // k = 2
     double piv = h22 - (h20 * h20 + h21 * h21);
     if (piv <= 0.0) go = false;
     if (go) {
-      piv = sqrt(piv);
+      piv = pagk_dsqrt(piv);
       h22 = piv;
       const double t0 = -1.0 * h20, t1 = -1.0 * h21;
       h32 += h30 * t0;
       h32 += h31 * t1;
-      h32 /= piv;
+      h32 = pagk_ddiv(h32, piv);
     }
   }
   if (go) {  // k = 3
     double piv = h33 - ((h30 * h30 + h31 * h31) + h32 * h32);
-    if (!(piv <= 0.0)) h33 = sqrt(piv);  // a NaN pivot is not <= 0: Eigen goes on with sqrt(NaN)
+    if (!(piv <= 0.0)) h33 = pagk_dsqrt(piv);  // a NaN pivot is not <= 0: Eigen goes on with sqrt(NaN)
   }
-  // L y = b
-  double r0 = b0 / h00;
-  double r1 = (b1 - h10 * r0) / h11;
-  double r2 = (b2 - (h20 * r0 + h21 * r1)) / h22;
-  double r3 = (b3 - (h30 * r0 + (h31 * r1 + h32 * r2))) / h33;
-  // L^T x = y
-  r3 = r3 / h33;
-  r2 = (r2 - h32 * r3) / h22;
-  r1 = (r1 - (h21 * r2 + h31 * r3)) / h11;
-  r0 = (r0 - ((h10 * r1 + h20 * r2) + h30 * r3)) / h00;
+}
+
+// Substitution half: L y = b, then L^T x = y, in Eigen's fixed-size unroller order.
+__device__ __forceinline__ void pagk_llt_subst4(double h00, double h10, double h11, double h20, double h21, double h22,
+                                                double h30, double h31, double h32, double h33, double b0, double b1,
+                                                double b2, double b3, double &x0, double &x1, double &x2, double &x3) {
+  double r0 = pagk_ddiv(b0, h00);
+  double r1 = pagk_ddiv(b1 - h10 * r0, h11);
+  double r2 = pagk_ddiv(b2 - (h20 * r0 + h21 * r1), h22);
+  double r3 = pagk_ddiv(b3 - (h30 * r0 + (h31 * r1 + h32 * r2)), h33);
+  r3 = pagk_ddiv(r3, h33);
+  r2 = pagk_ddiv(r2 - h32 * r3, h22);
+  r1 = pagk_ddiv(r1 - (h21 * r2 + h31 * r3), h11);
+  r0 = pagk_ddiv(r0 - ((h10 * r1 + h20 * r2) + h30 * r3), h00);
   x0 = r0; x1 = r1; x2 = r2; x3 = r3;
+}
+
+__device__ __forceinline__ void pagk_llt_solve4(double h00, double h10, double h11, double h20, double h21, double h22,
+                                                double h30, double h31, double h32, double h33, double b0, double b1,
+                                                double b2, double b3, double &x0, double &x1, double &x2, double &x3) {
+  pagk_llt_factor4(h00, h10, h11, h20, h21, h22, h30, h31, h32, h33);
+  pagk_llt_subst4(h00, h10, h11, h20, h21, h22, h30, h31, h32, h33, b0, b1, b2, b3, x0, x1, x2, x3);
 }

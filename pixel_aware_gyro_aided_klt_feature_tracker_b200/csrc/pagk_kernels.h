@@ -21,4 +21,4 @@ size_t pagk_lk_slots_smem();
 bool pagk_lk_slots_supported(const PagkMode &mode);
 int pagk_launch_lk_slots(const unsigned char *images, const PagkGeom &g, const PagkPairConst *pcs, const float2 *keys_un,
                          const PagkOutPtrs &out, const PagkMode &mode, int max_keys, int n_max, int n_pairs,
-                         int *work_counter, int n_sms, cudaStream_t st, long long *launches);
+                         int *work_counter, int n_sms, cudaStream_t st, long long *launches, long long *dbg);
