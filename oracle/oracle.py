@@ -40,6 +40,8 @@ def load():
         lib.pagk_oracle_get_pixel_value.restype = C.c_float
         lib.pagk_oracle_llt_solve.argtypes = [_f64p, _f64p, _f64p]
         lib.pagk_oracle_llt_solve.restype = None
+        lib.pagk_oracle_affine_from_corners.argtypes = [_f32p, C.c_int, _f32p]
+        lib.pagk_oracle_affine_from_corners.restype = None
         lib.pagk_oracle_integrate_gyro.argtypes = [C.POINTER(capi.PagkPairIn), _f32p, _f32p]
         lib.pagk_oracle_gyro_predict.argtypes = [C.POINTER(capi.PagkParams), C.POINTER(capi.PagkPairIn),
                                                  C.POINTER(capi.PagkPairOut)]
@@ -88,6 +90,13 @@ def llt_solve(H: np.ndarray, b: np.ndarray) -> np.ndarray:
     x = np.zeros(4, np.float64)
     load().pagk_oracle_llt_solve(H.ctypes.data_as(_f64p), b.ctypes.data_as(_f64p), x.ctypes.data_as(_f64p))
     return x
+
+
+def affine_from_corners(cflows: np.ndarray, half: int) -> np.ndarray:
+    c = np.ascontiguousarray(cflows, np.float32).reshape(8)
+    A = np.zeros(4, np.float32)
+    load().pagk_oracle_affine_from_corners(c.ctypes.data_as(_f32p), half, A.ctypes.data_as(_f32p))
+    return A.reshape(2, 2)
 
 
 def integrate_gyro(pair: capi.PairInputs):

@@ -810,6 +810,19 @@ void pagk_oracle_llt_solve(const double *H16, const double *b4, double *x4) {
   llt_solve4(H, b4, x4);
 }
 
+// A = matC * B^T * (B*B^T)^-1 for given corner flows C[4][2] (test hook for the cv::Mat expression at
+// src/gyro_aided_tracker.cpp:166-167)
+void pagk_oracle_affine_from_corners(const float *cflows8, int half, float *A4) {
+  const float hf = (float)half;
+  const float corner[4][2] = {{-hf, -hf}, {hf, -hf}, {-hf, hf}, {hf, hf}};
+  float Bm[8], C[8], BBt[4], BBinv[4], S[4];
+  for (int j = 0; j < 4; ++j) { Bm[j] = corner[j][0]; Bm[4 + j] = corner[j][1]; C[j] = cflows8[2 * j]; C[4 + j] = cflows8[2 * j + 1]; }
+  small_gemm_dbl(Bm, 4, 1, Bm, 1, 4, BBt, 2, 2, 4);
+  small_inv2(BBt, BBinv);
+  small_gemm_dbl(C, 4, 1, Bm, 1, 4, S, 2, 2, 4);
+  small_gemm_nn(S, BBinv, A4, 2, 2, 2);
+}
+
 int pagk_oracle_integrate_gyro(const pagk_pair_in *in, float *Rcl, float *KRKinv) {
   integrate_gyro(*in, Rcl, KRKinv);
   return PAGK_OK;

@@ -1,0 +1,159 @@
+"""Generates tests/golden/*.npz.  Run HERE (needs cv2 4.x; the GPU box and the tests never run it).
+
+What is pinned against what (the reference ships no tests or golden vectors):
+  pyramid.npz   cv2.resize(INTER_LINEAR) chains  -> pins oracle resize_half() and the CUDA pyramid kernel
+  matexpr.npz   cv2.gemm / cv2.invert / cv2.scaleAdd / cv2.add chains that OpenCV's cv::MatExpr lowers
+                IntegrateGyroMeasurements, SetRcl and the affine-matrix expression to
+                (src/gyro_aided_tracker.cpp:166-167, 511-587)       -> pins oracle small_*() and integrate_gyro()
+  lk_frozen.npz outputs of the oracle itself on small seeded pairs, frozen so that any later edit of the
+                oracle's Gauss-Newton loop or LLT restatement is visible.  NOT a pin against the reference
+                (Eigen is not available): "parity unpinned" for that part.
+"""
+import ctypes
+import hashlib
+import os
+import sys
+
+import cv2
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from pixel_aware_gyro_aided_klt_feature_tracker_b200 import capi, synth  # noqa: E402
+from oracle import oracle  # noqa: E402
+
+f32 = np.float32
+libm = ctypes.CDLL("libm.so.6")
+libm.sinf.restype = libm.cosf.restype = ctypes.c_float
+libm.sinf.argtypes = libm.cosf.argtypes = [ctypes.c_float]
+
+
+def lcg_image(h, w, seed):
+    x = (np.arange(h * w, dtype=np.uint64) * np.uint64(6364136223846793005) + np.uint64(seed * 1442695040888963407 + 1))
+    x ^= x >> np.uint64(29)
+    x *= np.uint64(0xBF58476D1CE4E5B9)
+    return ((x >> np.uint64(40)) & np.uint64(0xFF)).astype(np.uint8).reshape(h, w)
+
+
+def make_pyramid():
+    out = {}
+    shapes = [(480, 752, 5), (480, 640, 4), (1080, 1920, 5), (2160, 3840, 5), (135, 240, 4), (77, 101, 4), (270, 135, 3),
+              (64, 64, 5), (67, 135, 3), (33, 50, 3)]
+    for (h, w, levels) in shapes:
+        img = lcg_image(h, w, 7)
+        cur = img
+        for l in range(1, levels):
+            dsz = (int(cur.shape[1] * 0.5), int(cur.shape[0] * 0.5))
+            if dsz[0] < 1 or dsz[1] < 1:
+                break
+            cur = cv2.resize(cur, dsz)   # default INTER_LINEAR, as src/patch_match.cpp:69
+            key = f"{h}x{w}_L{l}"
+            out["sha_" + key] = np.frombuffer(hashlib.sha256(cur.tobytes()).digest(), np.uint8)
+            out["shape_" + key] = np.array(cur.shape, np.int32)
+            if h * w <= 135 * 240:
+                out["img_" + key] = cur
+    np.savez_compressed(os.path.join(HERE, "pyramid.npz"), **out)
+    print("pyramid.npz", len(out))
+
+
+def integrate_cv2(imu_t, imu_w, t_ref, t_cur, bias, Rbc, K):
+    """IntegrateGyroMeasurements + SetRcl with cv2 primitives standing in for cv::MatExpr"""
+    I = np.eye(3, dtype=f32)
+    dR = I.copy()
+    n = len(imu_t) - 1
+    for i in range(n):
+        w0, w1 = imu_w[i].astype(f32), imu_w[i + 1].astype(f32)
+        if i == 0 and i < n - 1:
+            tab = f32(imu_t[i + 1] - imu_t[i]); tini = f32(imu_t[i] - t_ref); r = f32(tini / tab)
+            av = ((w0 + w1) - (w1 - w0) * r) * f32(0.5); tstep = f32(imu_t[i + 1] - t_ref)
+        elif i < n - 1:
+            av = (w0 + w1) * f32(0.5); tstep = f32(imu_t[i + 1] - imu_t[i])
+        elif i > 0 and i == n - 1:
+            tab = f32(imu_t[i + 1] - imu_t[i]); tend = f32(imu_t[i + 1] - t_cur); r = f32(tend / tab)
+            av = ((w0 + w1) - (w1 - w0) * r) * f32(0.5); tstep = f32(t_cur - imu_t[i])
+        else:
+            av = w0; tstep = f32(t_cur - t_ref)
+        x, y, z = [f32(float(f32(av[k] - bias[k])) * float(tstep)) for k in range(3)]
+        d2 = f32(f32(f32(x * x) + f32(y * y)) + f32(z * z))
+        d = f32(np.sqrt(d2))
+        W = np.array([[0, -z, y], [z, 0, -x], [-y, x, 0]], f32)
+        if float(d) < 1e-4:
+            dRi = cv2.add(I, W)
+        else:
+            a = float(libm.sinf(float(d))) * (1.0 / float(d))
+            b = float(f32(f32(1.0) - f32(libm.cosf(float(d))))) * (1.0 / float(d2))
+            dRi = cv2.add(cv2.scaleAdd(W, a, I), cv2.gemm(W, W, b, None, 0))
+        dR = cv2.gemm(dR, dRi, 1, None, 0)
+    M1 = cv2.gemm(Rbc, dR, 1, None, 0, flags=cv2.GEMM_1_T | cv2.GEMM_2_T)
+    Rcl = cv2.gemm(M1, Rbc, 1, None, 0)
+    return Rcl, krk_cv2(K, Rcl)
+
+
+def krk_cv2(K, Rcl):
+    return cv2.gemm(cv2.gemm(K, Rcl, 1, None, 0), cv2.invert(K)[1], 1, None, 0)
+
+
+def affine_cv2(cflows, half):
+    C = np.ascontiguousarray(cflows.reshape(4, 2).T)                      # matC 2x4
+    B = np.array([[-half, half, -half, half], [-half, -half, half, half]], f32)
+    S = cv2.gemm(C, B, 1, None, 0, flags=cv2.GEMM_2_T)
+    BBt = cv2.gemm(B, B, 1, None, 0, flags=cv2.GEMM_2_T)
+    return cv2.gemm(S, cv2.invert(BBt)[1], 1, None, 0)
+
+
+def make_matexpr():
+    rng = np.random.default_rng(20261018)
+    out = {"n": np.array(48)}
+    for i in range(48):
+        K = synth.EUROC_K.copy()
+        K[0, 0] += f32(rng.uniform(-40, 40)); K[1, 1] += f32(rng.uniform(-40, 40))
+        K[0, 2] += f32(rng.uniform(-20, 20)); K[1, 2] += f32(rng.uniform(-20, 20))
+        Rbc = synth.EUROC_RBC if i % 3 else np.eye(3, dtype=f32)
+        n_imu = [2, 3, 5, 12, 17][i % 5]
+        t_ref = 1403715000.0 + i
+        imu_t = t_ref - rng.uniform(0, 0.004) + np.arange(n_imu) * 0.005
+        t_cur = imu_t[-1] - rng.uniform(0, 0.004) if n_imu > 2 else imu_t[-1] + 0.001
+        scale = [1e-6, 0.05, 0.5, 3.0][i % 4]           # includes the d < 1e-4 branch
+        imu_w = (rng.normal(0, scale, (n_imu, 3))).astype(f32)
+        bias = rng.normal(0, 0.01, 3).astype(f32) if i % 2 else np.zeros(3, f32)
+        Rcl, KRK = integrate_cv2(imu_t, imu_w, t_ref, t_cur, bias, Rbc, K)
+        for k, v in dict(K=K, Rbc=Rbc, imu_t=imu_t, imu_w=imu_w, t_ref=np.array(t_ref), t_cur=np.array(t_cur), bias=bias,
+                         Rcl=Rcl, KRK=KRK).items():
+            out[f"g{i}_{k}"] = np.asarray(v)
+        half = [3, 5, 7, 10][i % 4]
+        cfl = (np.array([[-half, -half], [half, -half], [-half, half], [half, half]], f32) *
+               f32(1 + rng.normal(0, 0.05)) + rng.normal(0, 0.3, (4, 2)).astype(f32)).astype(f32)
+        out[f"a{i}_half"] = np.array(half); out[f"a{i}_cflows"] = cfl; out[f"a{i}_A"] = affine_cv2(cfl, half)
+    np.savez_compressed(os.path.join(HERE, "matexpr.npz"), **out)
+    print("matexpr.npz", len(out))
+
+
+def make_lk_frozen():
+    out = {}
+    cases = [dict(seed=9001, e_type=4, dist=None), dict(seed=9002, e_type=3, dist=None),
+             dict(seed=9003, e_type=4, dist=synth.EUROC_DIST), dict(seed=9004, e_type=2, dist=None),
+             dict(seed=9005, e_type=5, dist=None), dict(seed=9006, e_type=6, dist=None)]
+    out["n"] = np.array(len(cases))
+    for i, c in enumerate(cases):
+        p = synth.make_pair(c["seed"], width=160, height=120, n_keys=48, pyramids=3, border=12, margin=32,
+                            K=synth.scaled_euroc_K(160), dist=c["dist"], sigma_w=0.8)
+        prm = capi.default_params(e_type=c["e_type"], pyramids=3)
+        rc, o = oracle.track(p, prm, 1)
+        assert rc == 0
+        for k, v in dict(img_ref=p.img_ref, img_cur=p.img_cur, keys=p.keys_ref_un, imu_t=p.imu_t, imu_w=p.imu_w,
+                         t_ref=np.array(p.t_ref), t_cur=np.array(p.t_cur), K=p.K, Rbc=p.Rbc, dist=p.dist,
+                         n_dist=np.array(p.n_dist), e_type=np.array(c["e_type"])).items():
+            out[f"c{i}_in_{k}"] = np.asarray(v)
+        for k, v in o.arrays().items():
+            out[f"c{i}_out_{k}"] = v
+        out[f"c{i}_out_Rcl"] = o.Rcl; out[f"c{i}_out_KRKinv"] = o.KRKinv
+        out[f"c{i}_out_n_predict"] = np.array(o.n_predict); out[f"c{i}_out_n_iterations"] = np.array(o.n_iterations)
+        print("case", i, "eType", c["e_type"], "n_predict", o.n_predict, "iters", o.n_iterations)
+    np.savez_compressed(os.path.join(HERE, "lk_frozen.npz"), **out)
+
+
+if __name__ == "__main__":
+    make_pyramid()
+    make_matexpr()
+    make_lk_frozen()
