@@ -201,7 +201,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from pixel_aware_gyro_aided_klt_feature_tracker_b200 import tracker
+    from pixel_aware_gyro_aided_klt_feature_tracker_b200 import sharding, tracker
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the pagk hot path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
@@ -220,8 +220,12 @@ def main():
     log(f"[rank {rank}] generated {N_ROTATE} x {n_pairs} synthetic pairs in {time.time() - t_gen:.1f}s")
     N, half = cfg["n_keys"], cfg["half_patch"]
     prm = capi.default_params(pyramids=cfg["pyramids"], half_patch=half)
-    ctxs = [tracker.Context(device=local_rank, max_width=cfg["width"], max_height=cfg["height"], max_keys=N,
-                            max_pairs=n_pairs, max_levels=cfg["pyramids"], max_half_patch=half) for _ in range(N_ROTATE)]
+    def new_ctx():
+        return tracker.Context(device=local_rank, max_width=cfg["width"], max_height=cfg["height"], max_keys=N,
+                               max_pairs=n_pairs, max_levels=cfg["pyramids"], max_half_patch=half)
+    ctxs = [new_ctx() for _ in range(N_ROTATE)]
+    for c in ctxs[1:]:
+        c.share_stream(ctxs[0])      # one in-order stream: steps cannot overlap, CUDA events stay clean
     feats_per_step = n_pairs * N
 
     # ---- resident leg: inputs already in HBM, kernels only -------------------------------------
@@ -229,8 +233,7 @@ def main():
         c.upload(b["pairs"], prm)
     for k in range(max(3, args.warmup)):
         ctxs[k % N_ROTATE].run()
-    for c in ctxs:
-        c.synchronize()
+    ctxs[0].synchronize()
     outs0 = OutBlock(n_pairs, N, all_fields=True)
     ctxs[0].run()
     ctxs[0].download(outs0.outs)
@@ -241,50 +244,60 @@ def main():
         c.download(ob.outs)
         iters_per_step[k] = sum(o.n_iterations for o in ob.outs)
     launches0 = sum(c.launch_count() for c in ctxs)
+    for c in ctxs:
+        c.timing_reset()
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
-    lk_ms, tot_ms = [], []
     t0 = time.perf_counter()
     for k in range(args.steps):
         ctxs[k % N_ROTATE].run()
-    for c in ctxs:
-        c.synchronize()
+    ctxs[0].synchronize()
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     clocks = sampler.result()
     launches = sum(c.launch_count() for c in ctxs) - launches0
-    # per-kernel device time: CUDA events recorded by the handle around each kernel (last step of each handle)
-    for c in ctxs[:min(N_ROTATE, args.steps)]:
-        ms = c.last_run_ms()
-        lk_ms.append(ms["lk"]); tot_ms.append(ms["total"])
+    # device time of the dominant kernel: CUDA events around every LK launch of the timed region
+    lk_n, lk_sum, lk_iters = 0, 0.0, 0.0
+    for k, c in enumerate(ctxs):
+        n_r, ms_sum = c.timing_read()
+        lk_n += n_r; lk_sum += ms_sum; lk_iters += n_r * iters_per_step[k]
     stage_ms = ctxs[0].last_run_ms()
-    tmax = torch.tensor([dt], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    dt_max = float(tmax.item())
+    dt_max = sharding.reduce_time_max(dt)
     total_iters = sum(iters_per_step[k % N_ROTATE] for k in range(args.steps))
-    it_t = torch.tensor([float(total_iters)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(it_t, op=dist.ReduceOp.SUM)
+    (all_iters,) = sharding.reduce_counts(total_iters)
     value = world * args.steps * feats_per_step / dt_max
-    fi_per_s = float(it_t.item()) / dt_max
+    fi_per_s = all_iters / dt_max
 
-    # ---- end-to-end leg: host (pinned) buffers in, host buffers out, through pagk_track_batch -------
+    # ---- end-to-end leg: pinned host buffers in, pinned host buffers out, through the public C-ABI -------
+    # pagk_submit_batch / pagk_wait_batch on three handles with their own streams: the upload of batch k+1
+    # overlaps the kernels of batch k.  Every step copies its images, keypoints and gyro data host->device
+    # and its result vectors device->host inside the timed region.
     e2e_steps = args.e2e_steps or max(3, min(args.steps, 30))
+    ectx = [new_ctx() for _ in range(N_ROTATE)]
     oblocks = [OutBlock(n_pairs, N) for _ in range(N_ROTATE)]
-    for k in range(3):
-        ctxs[k % N_ROTATE].track_batch(batches[k % N_ROTATE]["pairs"], prm, oblocks[k % N_ROTATE].outs)
+    ins = [capi.make_in_array(b["pairs"]) for b in batches]
+    oarrs = [capi.make_out_array(ob.outs) for ob in oblocks]
+
+    def e2e_loop(steps):
+        inflight = [False] * N_ROTATE
+        for k in range(steps):
+            j = k % N_ROTATE
+            if inflight[j]:
+                ectx[j].wait()
+            ectx[j].submit_prepared(prm, ins[j], oarrs[j], n_pairs)
+            inflight[j] = True
+        for j in range(N_ROTATE):
+            if inflight[j]:
+                ectx[j].wait()
+    e2e_loop(3)
     barrier()
     t0 = time.perf_counter()
-    for k in range(e2e_steps):
-        ctxs[k % N_ROTATE].track_batch(batches[k % N_ROTATE]["pairs"], prm, oblocks[k % N_ROTATE].outs)
+    e2e_loop(e2e_steps)
     torch.cuda.synchronize()
-    dte = time.perf_counter() - t0
-    te = torch.tensor([dte], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * e2e_steps * feats_per_step / float(te.item())
+    dte = sharding.reduce_time_max(time.perf_counter() - t0)
+    e2e_value = world * e2e_steps * feats_per_step / dte
+    e2e_ok = int(oarrs[0][0].n_predict) > 0
     b0 = batches[0]
     h2d = int(b0["imgs"].nbytes + b0["keys"].nbytes + n_pairs * 96)
     d2h = int(oblocks[0].nbytes + n_pairs * 24)
@@ -298,8 +311,8 @@ def main():
 
     # ---- roofline of the dominant kernel (the LK patch-alignment kernel) ------------------------------
     peaks, peaks_kind = measured_peaks()
-    lk_avg_ms = float(np.mean(lk_ms))
-    it_launch = float(np.mean([iters_per_step[k] for k in range(len(lk_ms))]))
+    lk_avg_ms = lk_sum / max(1, lk_n)
+    it_launch = lk_iters / max(1, lk_n)
     fp32_peak = 148 * 128 * 2 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12  # TFLOP/s with FMA, nominal lanes x clock
     ach = it_launch * FP32_FLOP_PER_FEATURE_ITER.get(half, 70.0 * (2 * half + 1) ** 2) / (lk_avg_ms * 1e-3) / 1e12
     hbm_ach = it_launch * HBM_BYTES_PER_FEATURE_ITER / (lk_avg_ms * 1e-3) / 1e9
@@ -307,7 +320,8 @@ def main():
                 "frac": ach / fp32_peak, "frac_of_non_fma_peak": ach / (fp32_peak / 2), "traffic": None,
                 "peak_source": f"148 SM x 128 lanes x 2 x {peaks.get('sm_max_mhz', 1965.0):.0f} MHz ({peaks_kind} sm_max_mhz); "
                                "FMA contraction is forbidden by bit-parity, so half of it is the reachable ceiling",
-                "kernel_ms": lk_avg_ms, "feature_iterations_per_launch": it_launch,
+                "kernel_ms": lk_avg_ms, "kernel_launches_timed": lk_n, "feature_iterations_per_launch": it_launch,
+                "kernel_feature_iterations_per_sec": it_launch / (lk_avg_ms * 1e-3),
                 "hbm": {"achieved": hbm_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / peaks["hbm_gbs"],
                         "peak_source": peaks_kind}}
 
@@ -343,14 +357,15 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
             "config": {"workload": workload_name(args.config, cfg, n_pairs),
                        "l2": f"{N_ROTATE} rotating resident batches per GPU ({(N_ROTATE * 2 * n_pairs * cfg['width'] * cfg['height'] * 4 // 3) >> 20} MiB of pyramids) > 126 MB L2",
-                       "timing": "wall clock around K back-to-back steps, barrier + device synchronize on both sides, max over ranks; per-kernel ms from CUDA events on the launching stream"},
+                       "timing": "wall clock around K back-to-back steps on one in-order stream, barrier + device synchronize on both sides, max over ranks; kernel ms from CUDA events around every LK launch of the timed region"},
             "feature_iterations_per_sec": fi_per_s,
             "stage_ms": stage_ms, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "features/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "pagk_track_batch (pinned host buffers in and out)"},
+                    "steps": e2e_steps, "results_ok": bool(e2e_ok),
+                    "api": "pagk_submit_batch/pagk_wait_batch over 3 handles (pinned host buffers in and out)"},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity}
     print(json.dumps(line), flush=True)
-    for c in ctxs:
+    for c in (ctxs + ectx)[::-1]:   # borrowers of a shared stream before its owner
         c.close()
     if world > 1:
         dist.destroy_process_group()

@@ -170,6 +170,14 @@ void pagk_destroy(pagk_handle *h);
 int pagk_track_batch(pagk_handle *h, const pagk_params *prm, int n_pairs, const pagk_pair_in *in,
                      pagk_pair_out *out);
 
+/* Asynchronous form of pagk_track_batch: pagk_submit_batch enqueues the copies and kernels of one batch on
+ * the handle's stream and returns; pagk_wait_batch blocks until the results are in `out`.  A caller that
+ * rotates over two or three handles overlaps the upload of the next batch with the kernels of the
+ * current one.  `in`, `out` and every buffer they point to must stay valid until pagk_wait_batch. */
+int pagk_submit_batch(pagk_handle *h, const pagk_params *prm, int n_pairs, const pagk_pair_in *in,
+                      pagk_pair_out *out);
+int pagk_wait_batch(pagk_handle *h);
+
 /* The same work split so that inputs can stay resident in HBM between runs:
  *   pagk_upload_batch   H2D of images / keypoints / per-pair constants (gyro integrated on the host)
  *   pagk_run_resident   the kernels only (pyramid, predict, patch match, filter), asynchronous on
@@ -184,6 +192,12 @@ int pagk_last_run_ms(pagk_handle *h, float *total_ms, float *pyramid_ms, float *
                      float *lk_ms, float *filter_ms);
 /* the cudaStream_t of the handle, as void* (for callers that time with their own events) */
 void *pagk_stream(pagk_handle *h);
+/* make `h` issue its work on the stream of `other` (several resident batches, one in-order stream) */
+int pagk_share_stream(pagk_handle *h, pagk_handle *other);
+/* CUDA-event timing of the patch-alignment kernel over many runs: reset, run any number of times
+ * (up to 1024 are recorded), then read the count and the summed device milliseconds (synchronises). */
+int pagk_timing_reset(pagk_handle *h);
+int pagk_timing_read(pagk_handle *h, int *n_runs, float *lk_ms_sum);
 /* kernels launched by this handle since creation */
 int64_t pagk_launch_count(pagk_handle *h);
 

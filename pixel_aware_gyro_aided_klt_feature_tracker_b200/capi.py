@@ -88,12 +88,17 @@ SYMBOLS = {
     "pagk_create": (C.c_int, [C.POINTER(PagkConfig), C.POINTER(_H)]),
     "pagk_destroy": (None, [_H]),
     "pagk_track_batch": (C.c_int, [_H, C.POINTER(PagkParams), C.c_int, C.POINTER(PagkPairIn), C.POINTER(PagkPairOut)]),
+    "pagk_submit_batch": (C.c_int, [_H, C.POINTER(PagkParams), C.c_int, C.POINTER(PagkPairIn), C.POINTER(PagkPairOut)]),
+    "pagk_wait_batch": (C.c_int, [_H]),
     "pagk_upload_batch": (C.c_int, [_H, C.POINTER(PagkParams), C.c_int, C.POINTER(PagkPairIn)]),
     "pagk_run_resident": (C.c_int, [_H]),
     "pagk_download_batch": (C.c_int, [_H, C.c_int, C.POINTER(PagkPairOut)]),
     "pagk_synchronize": (C.c_int, [_H]),
     "pagk_last_run_ms": (C.c_int, [_H] + [_f32p] * 5),
     "pagk_stream": (C.c_void_p, [_H]),
+    "pagk_share_stream": (C.c_int, [_H, _H]),
+    "pagk_timing_reset": (C.c_int, [_H]),
+    "pagk_timing_read": (C.c_int, [_H, C.POINTER(C.c_int), _f32p]),
     "pagk_launch_count": (C.c_int64, [_H]),
     "pagk_build_pyramids": (C.c_int, [_H, C.c_int, C.POINTER(_u8p), C.c_int, C.c_int, C.c_int, C.c_int]),
     "pagk_pyramid_level_size": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),

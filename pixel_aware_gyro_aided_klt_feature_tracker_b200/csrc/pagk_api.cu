@@ -63,6 +63,9 @@ const size_t kOutElt[O_COUNT] = {8, 8, 8, 8, 8, 16, 32, 32, 32, 8, 8, 1, 1, 1, 8
 struct pagk_handle {
   pagk_config cfg;
   cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  std::vector<cudaEvent_t> tev;  // start/end event pairs around the LK kernel, pagk_timing_*
+  int tev_used = -1;             // -1: timing off
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t slot_capacity = 0;
   unsigned char *d_images = nullptr;
@@ -93,6 +96,10 @@ struct pagk_handle {
   std::vector<float> rcl, krk;  // [n_pairs][9]
   long long launches = 0;
   float ms[5] = {0, 0, 0, 0, 0};
+  // a download that has been enqueued but not finished (pagk_submit_batch / pagk_wait_batch)
+  pagk_pair_out *pending_out = nullptr;
+  int pending_n = 0;
+  std::vector<char> pending_staged;
 
   PagkOutPtrs outs() const {
     PagkOutPtrs o;
@@ -309,12 +316,15 @@ int pagk_create(const pagk_config *cfg, pagk_handle **out) {
 void pagk_destroy(pagk_handle *h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
-  if (h->stream) cudaStreamSynchronize(h->stream);
+  // a borrowed stream (pagk_share_stream) may already be gone with its owner: synchronise the device instead
+  if (h->stream && h->own_stream) cudaStreamSynchronize(h->stream);
+  else cudaDeviceSynchronize();
   cudaFree(h->d_images); cudaFree(h->d_keys_un); cudaFree(h->d_keys); cudaFree(h->d_pc); cudaFree(h->d_res);
   cudaFree(h->d_out); cudaFree(h->d_ntab); cudaFree(h->d_work); cudaFree(h->d_dbg);
   cudaFreeHost(h->h_in); cudaFreeHost(h->h_out); cudaFreeHost(h->h_res);
   for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
-  if (h->stream) cudaStreamDestroy(h->stream);
+  for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
+  if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
   cudaGetLastError();
   delete h;
 }
@@ -399,7 +409,13 @@ int pagk_run_resident(pagk_handle *h) {
   CU((cudaError_t)pagk_launch_predict(h->d_pc, h->d_keys_un, h->d_keys, o, h->mode, h->cfg.max_keys, h->n_max, h->n_pairs,
                                       h->geom.width, h->geom.height, h->d_ntab, h->ntab_stride, st, &h->launches));
   CU(cudaEventRecord(h->ev[2], st));
+  const bool timed = lk && h->tev_used >= 0 && h->tev_used < 1024;
+  if (timed) {
+    while ((int)h->tev.size() < 2 * (h->tev_used + 1)) { cudaEvent_t e; CU(cudaEventCreate(&e)); h->tev.push_back(e); }
+    CU(cudaEventRecord(h->tev[2 * h->tev_used], st));
+  }
   if (lk) CU((cudaError_t)launch_lk(h, o, h->mode, h->n_max, h->n_pairs));
+  if (timed) { CU(cudaEventRecord(h->tev[2 * h->tev_used + 1], st)); ++h->tev_used; }
   CU(cudaEventRecord(h->ev[3], st));
   if (lk) CU((cudaError_t)pagk_launch_epilogue(h->d_pc, o, h->mode, h->cfg.max_keys, h->n_pairs, h->d_res, 1, st, &h->launches));
   else {
@@ -438,54 +454,102 @@ int pagk_last_run_ms(pagk_handle *h, float *total_ms, float *pyramid_ms, float *
 }
 
 void *pagk_stream(pagk_handle *h) { return h ? (void *)h->stream : nullptr; }
+
+int pagk_share_stream(pagk_handle *h, pagk_handle *other) {
+  if (!h || !other || h->cfg.device != other->cfg.device) return fail(PAGK_ERR_INVALID, "pagk_share_stream: handles must live on one device");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaStreamSynchronize(h->stream));
+  if (h->own_stream && h->stream != other->stream) cudaStreamDestroy(h->stream);
+  h->stream = other->stream;
+  h->own_stream = false;
+  return PAGK_OK;
+}
+
+int pagk_timing_reset(pagk_handle *h) {
+  if (!h) return fail(PAGK_ERR_INVALID, "null handle");
+  h->tev_used = 0;
+  return PAGK_OK;
+}
+
+int pagk_timing_read(pagk_handle *h, int *n_runs, float *lk_ms_sum) {
+  if (!h || !n_runs || !lk_ms_sum) return fail(PAGK_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaStreamSynchronize(h->stream));
+  float sum = 0.f;
+  const int n = h->tev_used < 0 ? 0 : h->tev_used;
+  for (int i = 0; i < n; ++i) {
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, h->tev[2 * i], h->tev[2 * i + 1]));
+    sum += ms;
+  }
+  *n_runs = n; *lk_ms_sum = sum;
+  return PAGK_OK;
+}
 int64_t pagk_launch_count(pagk_handle *h) { return h ? h->launches : 0; }
 
-int pagk_download_batch(pagk_handle *h, int n_pairs, pagk_pair_out *out) {
+}  // extern "C"
+
+namespace {
+struct Want { OutKind k; size_t field_off; };
+const Want kWants[] = {
+    {O_PT_PREDICT_UN, offsetof(pagk_pair_out, pt_predict_un)}, {O_PT_PREDICT, offsetof(pagk_pair_out, pt_predict)},
+    {O_STATUS, offsetof(pagk_pair_out, status)}, {O_PT_GYRO_UN, offsetof(pagk_pair_out, pt_gyro_predict_un)},
+    {O_PT_GYRO, offsetof(pagk_pair_out, pt_gyro_predict)}, {O_FLOWS, offsetof(pagk_pair_out, flows_predict_un)},
+    {O_AFFINE, offsetof(pagk_pair_out, affine)}, {O_CFLOWS, offsetof(pagk_pair_out, corner_flows)},
+    {O_CORNERS_UN, offsetof(pagk_pair_out, pt_corners_un)}, {O_CORNERS, offsetof(pagk_pair_out, pt_corners)},
+    {O_PM_UN, offsetof(pagk_pair_out, pm_pt_un)}, {O_PM, offsetof(pagk_pair_out, pm_pt)},
+    {O_PM_STATUS, offsetof(pagk_pair_out, pm_status)}, {O_PIX_ERR, offsetof(pagk_pair_out, pixel_error)},
+    {O_DIST, offsetof(pagk_pair_out, distance)}, {O_NCC, offsetof(pagk_pair_out, ncc)}, {O_ITERS, offsetof(pagk_pair_out, iters)}};
+const int kNumWants = (int)(sizeof(kWants) / sizeof(kWants[0]));
+inline unsigned char *out_field(pagk_pair_out *out, int p, size_t off) {
+  return *reinterpret_cast<unsigned char *const *>(reinterpret_cast<const char *>(&out[p]) + off);
+}
+
+// enqueue the device-to-host copies of the requested result vectors (no synchronisation)
+int download_enqueue(pagk_handle *h, int n_pairs, pagk_pair_out *out) {
   if (!h || (n_pairs > 0 && !out)) return fail(PAGK_ERR_INVALID, "null argument");
   if (!h->ran || n_pairs != h->n_pairs) return fail(PAGK_ERR_INVALID, "pagk_download_batch: no finished run of that size");
+  h->pending_out = out; h->pending_n = n_pairs;
+  h->pending_staged.assign(kNumWants, 0);
   if (n_pairs == 0) return PAGK_OK;
   CU(cudaSetDevice(h->cfg.device));
-  std::vector<int> nk(n_pairs);
-  for (int p = 0; p < n_pairs; ++p) nk[p] = h->pcs[p].n_keys;
-  // which result vectors does the caller want, and can they be copied straight into its memory?
-  struct Want { OutKind k; size_t field_off; };
-  static const Want wants[] = {
-      {O_PT_PREDICT_UN, offsetof(pagk_pair_out, pt_predict_un)}, {O_PT_PREDICT, offsetof(pagk_pair_out, pt_predict)},
-      {O_STATUS, offsetof(pagk_pair_out, status)}, {O_PT_GYRO_UN, offsetof(pagk_pair_out, pt_gyro_predict_un)},
-      {O_PT_GYRO, offsetof(pagk_pair_out, pt_gyro_predict)}, {O_FLOWS, offsetof(pagk_pair_out, flows_predict_un)},
-      {O_AFFINE, offsetof(pagk_pair_out, affine)}, {O_CFLOWS, offsetof(pagk_pair_out, corner_flows)},
-      {O_CORNERS_UN, offsetof(pagk_pair_out, pt_corners_un)}, {O_CORNERS, offsetof(pagk_pair_out, pt_corners)},
-      {O_PM_UN, offsetof(pagk_pair_out, pm_pt_un)}, {O_PM, offsetof(pagk_pair_out, pm_pt)},
-      {O_PM_STATUS, offsetof(pagk_pair_out, pm_status)}, {O_PIX_ERR, offsetof(pagk_pair_out, pixel_error)},
-      {O_DIST, offsetof(pagk_pair_out, distance)}, {O_NCC, offsetof(pagk_pair_out, ncc)}, {O_ITERS, offsetof(pagk_pair_out, iters)}};
-  const int NW = (int)(sizeof(wants) / sizeof(wants[0]));
-  std::vector<char> staged(NW, 0);
-  auto field = [&](int p, size_t off) { return *reinterpret_cast<unsigned char *const *>(reinterpret_cast<const char *>(&out[p]) + off); };
-  for (int w = 0; w < NW; ++w) {
-    const size_t elt = kOutElt[wants[w].k];
+  for (int w = 0; w < kNumWants; ++w) {
+    const size_t elt = kOutElt[kWants[w].k];
     bool any = false, direct = true;
+    unsigned char *first = out_field(out, 0, kWants[w].field_off);
     for (int p = 0; p < n_pairs; ++p) {
-      unsigned char *d = field(p, wants[w].field_off);
+      unsigned char *d = out_field(out, p, kWants[w].field_off);
       if (d) any = true;
-      if (!d || nk[p] != h->cfg.max_keys || d != field(0, wants[w].field_off) + (size_t)p * h->cfg.max_keys * elt) direct = false;
+      // contiguous [n_pairs][max_keys] caller block: copy straight into it
+      if (!d || h->pcs[p].n_keys != h->cfg.max_keys || d != first + (size_t)p * h->cfg.max_keys * elt) direct = false;
     }
     if (!any) continue;
     const size_t bytes = (size_t)n_pairs * h->cfg.max_keys * elt;
     if (direct) {
-      CU(cudaMemcpyAsync(field(0, wants[w].field_off), h->d_out + h->out_off[wants[w].k], bytes, cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaMemcpyAsync(first, h->d_out + h->out_off[kWants[w].k], bytes, cudaMemcpyDeviceToHost, h->stream));
     } else {
-      CU(cudaMemcpyAsync(h->h_out + h->out_off[wants[w].k], h->d_out + h->out_off[wants[w].k], bytes, cudaMemcpyDeviceToHost, h->stream));
-      staged[w] = 1;
+      CU(cudaMemcpyAsync(h->h_out + h->out_off[kWants[w].k], h->d_out + h->out_off[kWants[w].k], bytes, cudaMemcpyDeviceToHost, h->stream));
+      h->pending_staged[w] = 1;
     }
   }
   CU(cudaMemcpyAsync(h->h_res, h->d_res, (size_t)n_pairs * sizeof(PagkPairResult), cudaMemcpyDeviceToHost, h->stream));
+  return PAGK_OK;
+}
+
+// wait for the copies, scatter the staged vectors, fill the scalar results
+int download_finish(pagk_handle *h) {
+  pagk_pair_out *out = h->pending_out;
+  const int n_pairs = h->pending_n;
+  h->pending_out = nullptr; h->pending_n = 0;
+  if (!out || n_pairs == 0) return PAGK_OK;
+  CU(cudaSetDevice(h->cfg.device));
   CU(cudaStreamSynchronize(h->stream));
-  for (int w = 0; w < NW; ++w) {
-    if (!staged[w]) continue;
-    const size_t elt = kOutElt[wants[w].k];
+  for (int w = 0; w < kNumWants; ++w) {
+    if (!h->pending_staged[w]) continue;
+    const size_t elt = kOutElt[kWants[w].k];
     for (int p = 0; p < n_pairs; ++p) {
-      unsigned char *d = field(p, wants[w].field_off);
-      if (d) std::memcpy(d, h->h_out + h->out_off[wants[w].k] + (size_t)p * h->cfg.max_keys * elt, (size_t)nk[p] * elt);
+      unsigned char *d = out_field(out, p, kWants[w].field_off);
+      if (d) std::memcpy(d, h->h_out + h->out_off[kWants[w].k] + (size_t)p * h->cfg.max_keys * elt, (size_t)h->pcs[p].n_keys * elt);
     }
   }
   float t[5] = {0, 0, 0, 0, 0};
@@ -502,8 +566,17 @@ int pagk_download_batch(pagk_handle *h, int n_pairs, pagk_pair_out *out) {
   }
   return PAGK_OK;
 }
+}  // namespace
 
-int pagk_track_batch(pagk_handle *h, const pagk_params *prm, int n_pairs, const pagk_pair_in *in, pagk_pair_out *out) {
+extern "C" {
+
+int pagk_download_batch(pagk_handle *h, int n_pairs, pagk_pair_out *out) {
+  const int rc = download_enqueue(h, n_pairs, out);
+  if (rc != PAGK_OK) return rc;
+  return download_finish(h);
+}
+
+int pagk_submit_batch(pagk_handle *h, const pagk_params *prm, int n_pairs, const pagk_pair_in *in, pagk_pair_out *out) {
   int rc = pagk_upload_batch(h, prm, n_pairs, in);
   if (rc != PAGK_OK) {
     if (rc == PAGK_ERR_UNSUPPORTED && out)
@@ -512,7 +585,18 @@ int pagk_track_batch(pagk_handle *h, const pagk_params *prm, int n_pairs, const 
   }
   rc = pagk_run_resident(h);
   if (rc != PAGK_OK) return rc;
-  return pagk_download_batch(h, n_pairs, out);
+  return download_enqueue(h, n_pairs, out);
+}
+
+int pagk_wait_batch(pagk_handle *h) {
+  if (!h) return fail(PAGK_ERR_INVALID, "null handle");
+  return download_finish(h);
+}
+
+int pagk_track_batch(pagk_handle *h, const pagk_params *prm, int n_pairs, const pagk_pair_in *in, pagk_pair_out *out) {
+  const int rc = pagk_submit_batch(h, prm, n_pairs, in, out);
+  if (rc != PAGK_OK) return rc;
+  return pagk_wait_batch(h);
 }
 
 int pagk_pyramid_level_size(int width, int height, int level, int *cols, int *rows) {

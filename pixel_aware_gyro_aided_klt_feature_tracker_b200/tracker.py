@@ -62,6 +62,13 @@ class Context:
         _check(self.lib, rc)
         return outs
 
+    def submit_prepared(self, params, ins, oarr, n):
+        """asynchronous pagk_track_batch on prebuilt ctypes arrays (kept alive by the caller until wait())"""
+        _check(self.lib, self.lib.pagk_submit_batch(self.handle, C.byref(params), n, ins, oarr))
+
+    def wait(self):
+        _check(self.lib, self.lib.pagk_wait_batch(self.handle))
+
     def upload(self, pairs, params):
         self._ins = capi.make_in_array(pairs)  # keep alive
         self._pairs = pairs
@@ -84,6 +91,17 @@ class Context:
         v = [C.c_float() for _ in range(5)]
         _check(self.lib, self.lib.pagk_last_run_ms(self.handle, *[C.byref(x) for x in v]))
         return dict(zip(("total", "pyramid", "predict", "lk", "filter"), [x.value for x in v]))
+
+    def share_stream(self, other: "Context"):
+        _check(self.lib, self.lib.pagk_share_stream(self.handle, other.handle))
+
+    def timing_reset(self):
+        _check(self.lib, self.lib.pagk_timing_reset(self.handle))
+
+    def timing_read(self):
+        n, ms = C.c_int(), C.c_float()
+        _check(self.lib, self.lib.pagk_timing_read(self.handle, C.byref(n), C.byref(ms)))
+        return n.value, ms.value
 
     def launch_count(self) -> int:
         return int(self.lib.pagk_launch_count(self.handle))
