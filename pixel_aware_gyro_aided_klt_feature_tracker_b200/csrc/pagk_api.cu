@@ -81,7 +81,8 @@ struct pagk_handle {
   int n_sms = 0;
   long long *d_dbg = nullptr;  // PAGK_LK_TIMELINE=<file>: clock64 timeline of CTA 0 of the LK kernel (developer aid)
   const char *dbg_path = nullptr;
-  int force_generic = 0;   // PAGK_LK_KERNEL=generic: use the any-patch-size kernel (tests compare both)
+  int lk_kernel = 0;       // PAGK_LK_KERNEL=slots|generic: use the previous pipelined kernel / the any-patch-size
+                           // kernel instead of the lane-per-feature one (tests compare them)
   // pinned staging
   unsigned char *h_in = nullptr;   // keys_un | keys | consts
   size_t h_in_keys_un = 0, h_in_keys = 0, h_in_pc = 0, h_in_bytes = 0;
@@ -198,7 +199,26 @@ int check_batch(pagk_handle *h, int n_pairs, int width, int height, int levels, 
 }
 
 int launch_lk(pagk_handle *h, const PagkOutPtrs &o, const PagkMode &m, int n_max, int n_pairs) {
-  if (!h->force_generic && pagk_lk_slots_supported(m)) {
+  if (h->lk_kernel == 0 && pagk_lk_lanes_supported(m)) {
+    // PAGK_LK_TIMELINE=<file> with a -DPAGK_LANES_PROF build: per-warp phase cycles (developer aid)
+    if (h->d_dbg) cudaMemsetAsync(h->d_dbg, 0, 2048 * 8 * sizeof(long long), h->stream);
+    const int rc = pagk_launch_lk_lanes(h->d_images, h->geom, h->d_pc, h->d_keys_un, o, m, h->cfg.max_keys, n_max, n_pairs,
+                                        h->d_work, h->n_sms, h->stream, &h->launches, h->d_dbg);
+    if (h->d_dbg && rc == 0) {
+      std::vector<long long> tl(2048 * 8);
+      cudaMemcpyAsync(tl.data(), h->d_dbg, tl.size() * sizeof(long long), cudaMemcpyDeviceToHost, h->stream);
+      cudaStreamSynchronize(h->stream);
+      if (FILE *f = fopen(h->dbg_path, "w")) {
+        for (size_t w = 0; w < tl.size() / 8; ++w) {
+          if (!tl[w * 8 + 6]) continue;
+          for (int k = 0; k < 8; ++k) fprintf(f, "%lld%c", tl[w * 8 + k], k == 7 ? '\n' : ' ');
+        }
+        fclose(f);
+      }
+    }
+    return rc;
+  }
+  if (h->lk_kernel != 2 && pagk_lk_slots_supported(m)) {
     if (h->d_dbg) cudaMemsetAsync(h->d_dbg, 0, 512 * 16 * sizeof(long long), h->stream);
     const int rc = pagk_launch_lk_slots(h->d_images, h->geom, h->d_pc, h->d_keys_un, o, m, h->cfg.max_keys, n_max, n_pairs,
                                         h->d_work, h->n_sms, h->stream, &h->launches, h->d_dbg);
@@ -294,9 +314,9 @@ int pagk_create(const pagk_config *cfg, pagk_handle **out) {
   ok(cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, cfg->device));
   {
     const char *k = getenv("PAGK_LK_KERNEL");
-    h->force_generic = (k && std::strcmp(k, "generic") == 0) ? 1 : 0;
+    h->lk_kernel = (k && std::strcmp(k, "generic") == 0) ? 2 : (k && std::strcmp(k, "slots") == 0) ? 1 : 0;
     h->dbg_path = getenv("PAGK_LK_TIMELINE");
-    if (h->dbg_path) { ok(cudaMalloc(&h->d_dbg, 512 * 16 * sizeof(long long))); }
+    if (h->dbg_path) { ok(cudaMalloc(&h->d_dbg, 2048 * 8 * sizeof(long long))); }
   }
   ok(cudaMallocHost(&h->h_in, h->h_in_bytes));
   ok(cudaMallocHost(&h->h_out, h->out_bytes));

@@ -22,3 +22,9 @@ bool pagk_lk_slots_supported(const PagkMode &mode);
 int pagk_launch_lk_slots(const unsigned char *images, const PagkGeom &g, const PagkPairConst *pcs, const float2 *keys_un,
                          const PagkOutPtrs &out, const PagkMode &mode, int max_keys, int n_max, int n_pairs,
                          int *work_counter, int n_sms, cudaStream_t st, long long *launches, long long *dbg);
+
+// production patch-alignment kernel (pagk_lk_lanes.cu): persistent CTAs, one lane per feature
+bool pagk_lk_lanes_supported(const PagkMode &mode);
+int pagk_launch_lk_lanes(const unsigned char *images, const PagkGeom &g, const PagkPairConst *pcs, const float2 *keys_un,
+                         const PagkOutPtrs &out, const PagkMode &mode, int max_keys, int n_max, int n_pairs,
+                         int *work_counter, int n_sms, cudaStream_t st, long long *launches, long long *prof);

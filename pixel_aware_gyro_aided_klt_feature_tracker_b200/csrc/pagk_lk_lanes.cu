@@ -1,0 +1,613 @@
+// pagk_lk_lanes.cu -- K3, the production patch-alignment kernel: one LANE per feature.
+//
+// Reference: PatchMatch::OpticalFlowMultiLevel + OpticalFlowConsideringIlluminationChange_onePixel,
+// src/patch_match.cpp:79-142 and :167-367 (forward-additive Gauss-Newton on (dx, dy, dg, db)).
+//
+// Why this shape.  The 4x4 normal matrix of the reference is structurally singular, so the
+// 14 sums of one Gauss-Newton pass must be taken in double, in the reference's pixel order: a serial chain
+// of P*P steps per feature.  Independent features are the only parallelism that keeps that order, so a
+// lane owns a feature ("slot") for its whole life -- all pyramid levels, all iterations -- and walks the
+// patch pixel by pixel: five bilinear samples of the current image (FP32, no FMA contraction), residual and
+// gradient, then straight into the lane's twelve FP64 accumulators and the float cost.  Nothing is handed
+// over between threads, there is no barrier and no role: every warp of the CTA is an independent worker
+// with 32 slots, and a lane refills itself from the global work counter when its feature is finished.
+// (The previous design computed the samples pixel-parallel and handed float4 records to two accumulation
+// warps through shared memory; its stage time was bound by those two warps' serial work, it issued about
+// 1000 warp instructions per feature-iteration and was at 50 % of the shared-memory bandwidth.  This one
+// issues about 500 and reads each window tap once.)
+//
+// Shared memory per slot: the (P+10) x (P+6) window of the current level as u8 (what the loop samples) and
+// the P*P template values T = I1(pt + (x, y)) as float.  8 warps x 32 slots x 848 B = 212 KiB for 11 x 11.
+// u8 -> float is  (0x4B000000 | b) - 2^23  (LOP3 + FADD): exact, and off the 4-lane conversion pipe that
+// the three float -> double conversions per pixel need.
+//
+// Per round a warp does, with warp-uniform control flow:
+//   refill   idle lanes take the next features from the global counter
+//   setup    (cooperative, lanes = pixels) for every lane that starts a level: stage the template window,
+//            compute T and c = -I1(pt)
+//   window   (cooperative) restage the current-image window of every lane whose sample box left it
+//   pass     lane = slot: P*P pixels, samples + ordered sums            <- the hot loop
+//   slow     lanes whose samples may clamp at the border, whose box does not fit the window, or that hit
+//            the one rounding case the shared-weight sampling does not cover, redo the pass sample by
+//            sample straight from the level (PatchMatch::GetPixelValue semantics, any coordinates)
+//   solve    lane = slot: 4x4 LLT in Eigen's operation order, update, exits, next level / next feature
+//
+// Bit-exactness of the window path is argued above the pass loop.
+#include "pagk_device.cuh"
+#include "pagk_kernels.h"
+
+namespace {
+
+constexpr int LANES_WARPS = 8;
+// a warp with at most this many live lanes runs them one by one through the cooperative pass (lanes = pixels,
+// then lanes = accumulators: about 2.2 k warp instructions per slot) instead of a lockstep pass (17 k)
+#ifndef PAGK_LANES_SPARSE
+#define PAGK_LANES_SPARSE 7
+#endif
+// pixels of a patch row unrolled in the pass loop.  The whole row (11) gives the scheduler the most to overlap but
+// is a 25 KB loop body, and with the warps of an SM in different phases the instruction cache then misses
+// (ncu: stalled_no_instruction 1.5 per issue, icc hit rate 72 %).
+#ifndef PAGK_LANES_UNROLL
+#define PAGK_LANES_UNROLL 2
+#endif
+#define PAGK_PRAGMA_(x) _Pragma(#x)
+#define PAGK_UNROLL(n) PAGK_PRAGMA_(unroll n)
+
+template <int HALF>
+struct LanesCfg {
+  static constexpr int P = 2 * HALF + 1;
+  static constexpr int NP = P * P;
+  static constexpr int WIN_W = P + 10;
+  static constexpr int WIN_H = P + 6;
+  // bytes per slot window, a whole and ODD number of 32-bit words: lane-private windows then start in
+  // distinct banks (NP is odd as well, so the same holds for the T rows)
+  static constexpr int WIN_WORDS = ((WIN_W * WIN_H + 3) / 4) | 1;
+  static constexpr int WIN_BYTES = WIN_WORDS * 4;
+  static constexpr int SLOT_BYTES = WIN_BYTES + NP * 4;
+  // per-warp scratch of the cooperative pass: NP records (Ix, Iy, -e) and the two constants c and 1
+  static constexpr int SCRATCH_FLOATS = NP * 3 + 4;
+  static constexpr int WARP_BYTES = 32 * SLOT_BYTES + SCRATCH_FLOATS * 4;
+  static constexpr int WARPS = (227 * 1024) / WARP_BYTES < LANES_WARPS ? (227 * 1024) / WARP_BYTES : LANES_WARPS;
+  static_assert(WIN_W <= 32, "one lane per window column");
+  static_assert(WARPS >= 1, "patch too large for the lane kernel");
+};
+
+// floor(x) as float for 0 <= x < 2^22 without the conversion pipe: x + 2^23 rounds to an integer,
+// subtracting 2^23 back is exact, one compare fixes the round-up case.
+__device__ __forceinline__ float floor_nn(float x) {
+  const float t = x + 8388608.0f;
+  float r = t - 8388608.0f;
+  if (r > x) r -= 1.0f;
+  return r;
+}
+__device__ __forceinline__ float floor_nn(float x, int &i) {
+  const float t = x + 8388608.0f;
+  float r = t - 8388608.0f;
+  i = __float_as_int(t) - 0x4B000000;
+  if (r > x) { r -= 1.0f; i -= 1; }
+  return r;
+}
+// exact u8 -> float on the ALU + FP32 pipes
+__device__ __forceinline__ float u8f(unsigned int b) { return __uint_as_float(0x4B000000u | b) - 8388608.0f; }
+
+// Stage the WIN_W x WIN_H window with origin (x0, y0) of a level into shared memory (u8, row pitch WIN_W);
+// lane j < WIN_W owns column j.  Coordinates are clamped into [0, cols] x [0, rows] -- the level plus its
+// wrap column and guard row -- so every load is in bounds and unconditional.  Elements whose true position
+// lies outside that range hold an arbitrary in-bounds pixel; the callers never read them.
+// Split in two so that the loads of two windows can be in flight together.
+template <int WIN_W, int WIN_H>
+__device__ __forceinline__ void load_window(unsigned char (&v)[WIN_H], const unsigned char *__restrict__ img, int cols,
+                                            int rows, int x0, int y0, int lane) {
+  if (lane < WIN_W) {
+    const int gx = min(max(x0 + lane, 0), cols);
+#pragma unroll
+    for (int i = 0; i < WIN_H; ++i) {
+      const int gy = min(max(y0 + i, 0), rows);
+      v[i] = __ldg(img + gy * cols + gx);
+    }
+  }
+}
+template <int WIN_W, int WIN_H>
+__device__ __forceinline__ void store_window(unsigned char *__restrict__ win, const unsigned char (&v)[WIN_H], int lane) {
+  if (lane < WIN_W) {
+#pragma unroll
+    for (int i = 0; i < WIN_H; ++i) win[i * WIN_W + lane] = v[i];
+  }
+}
+// PatchMatch::GetPixelValue (reference src/patch_match.cpp:391-406) with the four taps taken from a staged
+// window with origin (wx0, wy0): the same clamps, the same expression tree.
+template <int WIN_W>
+__device__ __forceinline__ float window_sample(const unsigned char *__restrict__ win, int wx0, int wy0, float fcols,
+                                               float fcm1, float frows, float frm1, float x, float y) {
+  if (x < 0.f) x = 0.f;
+  if (y < 0.f) y = 0.f;
+  if (x >= fcols) x = fcm1;
+  if (y >= frows) y = frm1;
+  int ix, iy;
+  const float fx = floor_nn(x, ix), fy = floor_nn(y, iy);
+  const float xx = x - fx, yy = y - fy, wa = 1.0f - xx, wb = 1.0f - yy;
+  const unsigned char *q = win + (iy - wy0) * WIN_W + (ix - wx0);
+  return wb * (wa * u8f(q[0]) + xx * u8f(q[1])) + yy * (wa * u8f(q[WIN_W]) + xx * u8f(q[WIN_W + 1]));
+}
+
+// developer aid (-DPAGK_LANES_PROF): per-warp cycles of every phase, rounds and active lane-rounds -> prof[warp_global][8]
+#ifdef PAGK_LANES_PROF
+#define PROF_DECL long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long pt = clock64();
+#define PROF(i) do { const long long now_ = clock64(); pf[i] += now_ - pt; pt = now_; } while (0)
+#define PROF_ADD(i, v) pf[i] += (v)
+#define PROF_FLUSH() do { if (prof && lane == 0) for (int i_ = 0; i_ < 8; ++i_) prof[(size_t)(blockIdx.x * (blockDim.x >> 5) + warp) * 8 + i_] = pf[i_]; } while (0)
+#else
+#define PROF_DECL
+#define PROF(i)
+#define PROF_ADD(i, v)
+#define PROF_FLUSH()
+#endif
+
+struct Sums {
+  double h00, h10, h11, h20, h21, h22, h30, h31, b0, b1, b2, b3;
+  float cost;
+};
+
+}  // namespace
+
+template <int HALF, bool AFFINE>
+__global__ void __launch_bounds__(LanesCfg<HALF>::WARPS * 32, 1)
+pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const PagkPairConst *__restrict__ pcs,
+                     const float2 *__restrict__ keys_un, PagkOutPtrs out, PagkMode mode, int max_keys, int n_max,
+                     int n_pairs, int *__restrict__ work_counter, long long *__restrict__ prof) {
+  using C = LanesCfg<HALF>;
+  constexpr int P = C::P, NP = C::NP, WIN_W = C::WIN_W, WIN_H = C::WIN_H;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char *wwin = smem_raw + (size_t)warp * C::WARP_BYTES;               // [32][WIN_BYTES]
+  float *wT = reinterpret_cast<float *>(wwin + 32 * C::WIN_BYTES);             // [32][NP]
+  float *scratch = wT + 32 * NP;                                               // [NP][3] records, c, 1
+  const unsigned char *mywin = wwin + lane * C::WIN_BYTES;
+  const float *myT = wT + lane * NP;
+  const int total_work = n_pairs * n_max;
+  const int top = mode.levels - 1;
+  const unsigned long long slot_bytes = g.slot_bytes;
+  const float hf = (float)HALF;
+  constexpr unsigned FULL = 0xffffffffu;
+  // level geometry, indexed by each lane's own level
+  __shared__ int s_cols[PAGK_MAX_LEVELS], s_rows[PAGK_MAX_LEVELS];
+  __shared__ unsigned int s_off[PAGK_MAX_LEVELS];
+  if (threadIdx.x < PAGK_MAX_LEVELS) {
+    s_cols[threadIdx.x] = g.lv[threadIdx.x].cols; s_rows[threadIdx.x] = g.lv[threadIdx.x].rows; s_off[threadIdx.x] = g.lv[threadIdx.x].offset;
+  }
+  __syncthreads();
+
+  // accumulator role of this lane in the cooperative pass: acc += A * B with A in {Ix, Iy, c, 1} and B in
+  // {Ix, Iy, -e, c}; lanes 0..11 = h00 h10 h11 h20 h21 h22 h30 h31 b0 b1 b2 b3.  An operand is a float in the
+  // scratch: a record field (stride 3) or one of the two constants behind the records (stride 0).
+  const int role = lane < 12 ? lane : 0;
+  const int selA = (int)((0x431044333110ull >> (4 * role)) & 0xfull);  // 0 Ix, 1 Iy, 3 c, 4 one
+  const int selB = (int)((0x222210310100ull >> (4 * role)) & 0xfull);  // 0 Ix, 1 Iy, 2 -e, 3 c
+  const int offA = selA < 3 ? selA : NP * 3 + (selA - 3), strideA = selA < 3 ? 3 : 0;
+  const int offB = selB < 3 ? selB : NP * 3 + (selB - 3), strideB = selB < 3 ? 3 : 0;
+
+  // ---- slot state (registers of the owning lane) ----
+  int feat = -1, pair = 0, level = 0, iter = 0, n_iter = 0, succ = 1;
+  float pt1x = 0.f, pt1y = 0.f, ptx = 0.f, pty = 0.f, dx = 0.f, dy = 0.f, dg = 0.f, db = 0.f, lastCost = 0.f, cval = 0.f;
+  float a00 = 1.f, a01 = 0.f, a10 = 0.f, a11 = 1.f;
+  float wxmin = -hf, wxmax = hf, wymin = -hf, wymax = hf;
+  int win_x0 = 0, win_y0 = 0;
+  bool needs_setup = false, win_valid = false;
+  bool exhausted = false;  // warp-uniform
+  PROF_DECL
+
+  while (true) {
+    // ------------------------------------------------------------------ refill
+    while (!exhausted) {
+      const bool want = feat < 0;
+      const unsigned m = __ballot_sync(FULL, want);
+      if (m == 0u) break;
+      const int cnt = __popc(m);
+      int base = 0;
+      if (lane == 0) base = atomicAdd(work_counter, cnt);
+      base = __shfl_sync(FULL, base, 0);
+      if (base + cnt >= total_work) exhausted = true;
+      if (want) {
+        const int wi = base + __popc(m & ((1u << lane) - 1u));
+        if (wi < total_work) {
+          const int pr = wi / n_max, i = wi - pr * n_max;
+          if (i < pcs[pr].n_keys) {
+            const size_t o = (size_t)pr * max_keys + i;
+            const float2 p1 = keys_un[o];
+            const float2 p2 = mode.gyro_init ? out.pt_predict_un[o] : p1;
+            if (!out.gyro_status[o]) {  // the reference skips these (src/patch_match.cpp:173): default outputs
+              out.pm_un[o] = p2; out.pm_status[o] = 0; out.pix_err[o] = 0.0; out.ncc[o] = 0.f; out.iters[o] = 0;
+            } else {
+              const float4 A = out.affine[o];
+              const float scale = 1.0f / (float)(1 << top);
+              feat = (int)o; pair = pr; level = top; needs_setup = true; win_valid = false;
+              pt1x = p1.x; pt1y = p1.y;
+              ptx = p1.x * scale; pty = p1.y * scale;
+              dx = p2.x * scale - ptx; dy = p2.y * scale - pty;
+              dg = 0.f; db = 0.f; lastCost = 0.f; iter = 0; n_iter = 0; succ = 1;
+              a00 = A.x; a01 = A.y; a10 = A.z; a11 = A.w;
+              wxmin = -hf; wxmax = hf; wymin = -hf; wymax = hf;
+              if (AFFINE) {  // warp offsets at the four patch corners, exactly as the pass computes them
+                const float c0x = a00 * -hf + a01 * -hf, c1x = a00 * hf + a01 * -hf, c2x = a00 * -hf + a01 * hf, c3x = a00 * hf + a01 * hf;
+                const float c0y = a10 * -hf + a11 * -hf, c1y = a10 * hf + a11 * -hf, c2y = a10 * -hf + a11 * hf, c3y = a10 * hf + a11 * hf;
+                wxmin = fminf(fminf(c0x, c1x), fminf(c2x, c3x)); wxmax = fmaxf(fmaxf(c0x, c1x), fmaxf(c2x, c3x));
+                wymin = fminf(fminf(c0y, c1y), fminf(c2y, c3y)); wymax = fmaxf(fmaxf(c0y, c1y), fmaxf(c2y, c3y));
+              }
+            }
+          }
+        }
+      }
+    }
+    const bool active = feat >= 0;
+    const unsigned m_active = __ballot_sync(FULL, active);
+    if (m_active == 0u) break;
+    PROF(0); PROF_ADD(6, 1); PROF_ADD(7, __popc(m_active));
+
+    const int cols = s_cols[level], rows = s_rows[level];
+    const unsigned char *I1 = images + (size_t)(pair * 2) * slot_bytes + s_off[level];
+    const unsigned char *I2 = I1 + slot_bytes;
+    const float fcols = (float)cols, frows = (float)rows, fcm1 = (float)(cols - 1), frm1 = (float)(rows - 1);
+
+    // ------------------------------------------------------------------ sample box of this pass (lane = slot)
+    // Extreme sample coordinates over the patch: the warp offsets are monotone in x and in y, so their extremes
+    // sit at the corners; the +-1 of the gradient samples and every rounding are monotone too.  `inside`: no
+    // clamp of GetPixelValue can fire for any sample.  The box of the CLAMPED coordinates is what a window has to
+    // hold (stage_window keeps the wrap column and the guard row), so border slots are windowable as well.
+    const float bx = ptx + dx, by = pty + dy;
+    bool windowable = false, fast = false, restage = false;
+    int nx0 = 0, ny0 = 0;
+    {
+      const float x2min = (bx + wxmin) - 1.0f, x1max = (bx + wxmax) + 1.0f;
+      const float y2min = (by + wymin) - 1.0f, y1max = (by + wymax) + 1.0f;
+      const bool inside = (x2min >= 0.0f) && (x1max < fcols) && (y2min >= 0.0f) && (y1max < frows);
+      const bool sane = fabsf(x2min) < 1.0e6f && fabsf(x1max) < 1.0e6f && fabsf(y2min) < 1.0e6f && fabsf(y1max) < 1.0e6f;  // false for NaN
+      if (active && sane) {
+        const int ixlo = (int)fminf(fmaxf(x2min, 0.0f), fcm1), ixhi = (int)fminf(fmaxf(x1max, 0.0f), fcm1) + 1;
+        const int iylo = (int)fminf(fmaxf(y2min, 0.0f), frm1), iyhi = (int)fminf(fmaxf(y1max, 0.0f), frm1) + 1;
+        const int needw = ixhi - ixlo + 1, needh = iyhi - iylo + 1;
+        if (needw <= WIN_W && needh <= WIN_H) {
+          windowable = true;
+          fast = inside;
+          const bool ok = win_valid && !needs_setup && ixlo >= win_x0 && ixhi <= win_x0 + WIN_W - 1 && iylo >= win_y0 && iyhi <= win_y0 + WIN_H - 1;
+          if (!ok) {  // (re)stage, centred on the needed box
+            restage = true;
+            nx0 = ixlo - (WIN_W - needw) / 2;
+            ny0 = iylo - (WIN_H - needh) / 2;
+          }
+        }
+      }
+    }
+
+    // ------------------------------------------------------------------ setup of a level (cooperative)
+    {
+      unsigned m = __ballot_sync(FULL, active && needs_setup);
+      while (m) {
+        const int s = __ffs(m) - 1;
+        m &= m - 1;
+        const float sptx = __shfl_sync(FULL, ptx, s), spty = __shfl_sync(FULL, pty, s);
+        const int scols = __shfl_sync(FULL, cols, s), srows = __shfl_sync(FULL, rows, s);
+        const unsigned char *img1 = reinterpret_cast<const unsigned char *>(__shfl_sync(FULL, (unsigned long long)I1, s));
+        const int rs = __shfl_sync(FULL, (int)restage, s), rx0 = __shfl_sync(FULL, nx0, s), ry0 = __shfl_sync(FULL, ny0, s);
+        unsigned char *win = wwin + s * C::WIN_BYTES;
+        float *T = wT + s * NP;
+        const float txlo = sptx + (-hf), txhi = sptx + hf, tylo = spty + (-hf), tyhi = spty + hf;
+        const bool tin = txlo >= 0.0f && txhi < (float)scols && tylo >= 0.0f && tyhi < (float)srows;
+        const int x0 = (int)txlo, y0 = (int)tylo;
+        unsigned char v1[WIN_H], v2[WIN_H];
+        // both windows' loads in flight together: one global round trip per level instead of two
+        if (tin) load_window<WIN_W, WIN_H>(v1, img1, scols, srows, x0, y0, lane);
+        if (rs) load_window<WIN_W, WIN_H>(v2, img1 + slot_bytes, scols, srows, rx0, ry0, lane);
+        float c;
+        if (tin) {
+          // no clamp fires anywhere in the template: sample from a staged window of the reference level
+          // (taps reach floor(hi) + 1 <= x0 + P + 1: inside the window)
+          __syncwarp();
+          store_window<WIN_W, WIN_H>(win, v1, lane);
+          __syncwarp();
+#pragma unroll
+          for (int k = 0; k < (NP + 31) / 32; ++k) {
+            const int p = lane + 32 * k;
+            if (p < NP) {
+              const int py = p / P, px = p - py * P;
+              const float cx = sptx + (float)(px - HALF), cy = spty + (float)(py - HALF);
+              int ix, iy;
+              const float fx = floor_nn(cx, ix), fy = floor_nn(cy, iy);
+              const float xx = cx - fx, yy = cy - fy, wa = 1.0f - xx, wb = 1.0f - yy;
+              const unsigned char *q = win + (iy - y0) * WIN_W + (ix - x0);
+              T[p] = wb * (wa * u8f(q[0]) + xx * u8f(q[1])) + yy * (wa * u8f(q[WIN_W]) + xx * u8f(q[WIN_W + 1]));
+            }
+          }
+          {
+            int ix, iy;
+            const float fx = floor_nn(sptx, ix), fy = floor_nn(spty, iy);
+            const float xx = sptx - fx, yy = spty - fy, wa = 1.0f - xx, wb = 1.0f - yy;
+            const unsigned char *q = win + (iy - y0) * WIN_W + (ix - x0);
+            c = -(wb * (wa * u8f(q[0]) + xx * u8f(q[1])) + yy * (wa * u8f(q[WIN_W]) + xx * u8f(q[WIN_W + 1])));
+          }
+        } else {
+#pragma unroll 1
+          for (int p = lane; p < NP; p += 32) {
+            const int py = p / P, px = p - py * P;
+            T[p] = pagk_sample_call(img1, scols, srows, sptx + (float)(px - HALF), spty + (float)(py - HALF));
+          }
+          c = -pagk_sample_call(img1, scols, srows, sptx, spty);
+        }
+        __syncwarp();
+        if (rs) store_window<WIN_W, WIN_H>(win, v2, lane);
+        if (lane == s) {
+          cval = c; needs_setup = false; win_valid = false;
+          if (rs) { win_x0 = nx0; win_y0 = ny0; win_valid = true; restage = false; }
+        }
+        __syncwarp();
+      }
+    }
+    PROF(1);
+    // ------------------------------------------------------------------ window of the current level (cooperative)
+    {
+      unsigned m = __ballot_sync(FULL, restage);
+      while (m) {
+        const int s = __ffs(m) - 1;
+        m &= m - 1;
+        const int x0 = __shfl_sync(FULL, nx0, s), y0 = __shfl_sync(FULL, ny0, s);
+        const int scols = __shfl_sync(FULL, cols, s), srows = __shfl_sync(FULL, rows, s);
+        const unsigned char *img2 = reinterpret_cast<const unsigned char *>(__shfl_sync(FULL, (unsigned long long)I2, s));
+        unsigned char v[WIN_H];
+        load_window<WIN_W, WIN_H>(v, img2, scols, srows, x0, y0, lane);
+        __syncwarp();
+        store_window<WIN_W, WIN_H>(wwin + s * C::WIN_BYTES, v, lane);
+      }
+      if (restage) { win_x0 = nx0; win_y0 = ny0; win_valid = true; }
+      __syncwarp();
+    }
+    PROF(2);
+
+    Sums S;
+    S.h00 = S.h10 = S.h11 = S.h20 = S.h21 = S.h22 = S.h30 = S.h31 = S.b0 = S.b1 = S.b2 = S.b3 = 0.0;
+    S.cost = 0.f;
+    const double c = (double)cval;
+    const float gain = 1.0f + dg;
+    const bool sparse = __popc(m_active) <= PAGK_LANES_SPARSE;
+    bool coop = active && (sparse || !fast);
+
+    // ------------------------------------------------------------------ the pass: lane = slot
+    // Bit-exactness of the window path.  The reference samples at (sx, sy), (sx+-1, sy), (sx, sy+-1), each
+    // through GetPixelValue (src/patch_match.cpp:391-406).  With no clamp firing (`fast`):
+    //   sx - 1 is exact (same or finer binade), so that sample has floor(sx) - 1 and the weights of sx;
+    //   X1 = fl(sx + 1) lies in [fx + 1, fx + 2]; X1 - (fx + 1) is exact (Sterbenz) and equals the reference's
+    //   X1 - floor(X1) unless X1 == fx + 2, where it is exactly 1 -- flagged `bad`, the slot then redoes the
+    //   pass through the cooperative path, which evaluates every sample on its own.
+    // Horizontal interpolations are shared between samples only where the reference would evaluate the
+    // identical expression.
+    if (!sparse) {
+      bool bad = false;
+      // lanes without a fast slot walk a harmless patch in the middle of their window
+      const float pbx = fast ? bx : (float)(HALF + 5) + 0.5f, pby = fast ? by : (float)(HALF + 3) + 0.5f;
+      const float q00 = fast ? a00 : 1.0f, q01 = fast ? a01 : 0.0f, q10 = fast ? a10 : 0.0f, q11 = fast ? a11 : 1.0f;
+      const float org = fast ? (float)(win_y0 * WIN_W + win_x0) : 0.0f;
+#pragma unroll 1
+      for (int yi = 0; yi < P; ++yi) {
+        const float yf = (float)(yi - HALF);
+        const float r01 = q01 * yf, r11 = q11 * yf;
+        const float *Trow = myT + yi * P;
+        PAGK_UNROLL(PAGK_LANES_UNROLL)
+        for (int xi = 0; xi < P; ++xi) {
+          const float xf = (float)(xi - HALF);
+          float wx = xf, wy = yf;
+          if (AFFINE) { wx = q00 * xf + r01; wy = q10 * xf + r11; }
+          const float sx = pbx + wx, sy = pby + wy;
+          const float fx = floor_nn(sx), fy = floor_nn(sy);
+          const float xx = sx - fx, yy = sy - fy;
+          const float wa = 1.0f - xx, wb = 1.0f - yy;
+          const float X1 = sx + 1.0f, Y1 = sy + 1.0f;
+          const float xx1 = X1 - (fx + 1.0f), yy1 = Y1 - (fy + 1.0f);
+          const float wa1 = 1.0f - xx1, wb1 = 1.0f - yy1;
+          bad |= (xx1 >= 1.0f) | (yy1 >= 1.0f);
+          // element index fy * WIN_W + fx - org, formed exactly in float and read off the mantissa
+          const float ti = __fmaf_rn(fy, (float)WIN_W, (fx - org) + 8388608.0f);
+          const unsigned char *w = mywin + (__float_as_int(ti) - 0x4B000000);
+          const float m0 = u8f(w[-WIN_W]), m1 = u8f(w[-WIN_W + 1]);
+          const float c_1 = u8f(w[-1]), c0 = u8f(w[0]), c1 = u8f(w[1]), c2 = u8f(w[2]);
+          const float d_1 = u8f(w[WIN_W - 1]), d0 = u8f(w[WIN_W]), d1 = u8f(w[WIN_W + 1]), d2 = u8f(w[WIN_W + 2]);
+          const float n0 = u8f(w[2 * WIN_W]), n1 = u8f(w[2 * WIN_W + 1]);
+          const float Hm = wa * m0 + xx * m1;
+          const float H0 = wa * c0 + xx * c1, H0p = wa1 * c1 + xx1 * c2, H0m = wa * c_1 + xx * c0;
+          const float H1 = wa * d0 + xx * d1, H1p = wa1 * d1 + xx1 * d2, H1m = wa * d_1 + xx * d0;
+          const float H2 = wa * n0 + xx * n1;
+          const float v0 = wb * H0 + yy * H1;
+          const float vx1 = wb * H0p + yy * H1p, vx2 = wb * H0m + yy * H1m;
+          const float vy1 = wb1 * H1 + yy1 * H2, vy2 = wb * Hm + yy * H0;
+          const float e = (v0 + db) - gain * Trow[xi];
+          const float gxf = 0.5f * (vx1 - vx2), gyf = 0.5f * (vy1 - vy2), mf = -e;
+          // J = (Ix, Iy, c, 1) as double; b += -J * e; H += J * J^T; cost += e * e (float), reference :264-299.
+          // Each product of two float-valued doubles is exact, so DFMA rounds like the separate mul + add.
+          const double x = (double)gxf, y = (double)gyf, mm = (double)mf;
+          S.h00 = fma(x, x, S.h00); S.h10 = fma(y, x, S.h10); S.h11 = fma(y, y, S.h11);
+          S.h20 = fma(c, x, S.h20); S.h21 = fma(c, y, S.h21); S.h22 = fma(c, c, S.h22);
+          S.h30 = S.h30 + x; S.h31 = S.h31 + y;
+          S.b0 = fma(x, mm, S.b0); S.b1 = fma(y, mm, S.b1); S.b2 = fma(c, mm, S.b2); S.b3 = S.b3 + mm;
+          S.cost = S.cost + mf * mf;
+        }
+      }
+      coop |= active && fast && bad;
+    }
+    PROF(3);
+
+    // ------------------------------------------------------------------ the cooperative pass, one slot at a time
+    // For slots whose samples may clamp at the image border, slots that hit the rounding case above, slots whose
+    // box does not fit the window (sampled straight from the level) and every live slot of a sparse warp.
+    // Lanes = pixels: each of the five samples through GetPixelValue on its own -> records; then lanes =
+    // accumulators: the twelve double sums and the float cost walk the records in pixel order.
+    {
+      unsigned m = __ballot_sync(FULL, coop);
+      while (m) {
+        const int s = __ffs(m) - 1;
+        m &= m - 1;
+        const float sbx = __shfl_sync(FULL, bx, s), sby = __shfl_sync(FULL, by, s);
+        const float s00 = __shfl_sync(FULL, a00, s), s01 = __shfl_sync(FULL, a01, s), s10 = __shfl_sync(FULL, a10, s), s11 = __shfl_sync(FULL, a11, s);
+        const float sdb = __shfl_sync(FULL, db, s), sgain = __shfl_sync(FULL, gain, s), scv = __shfl_sync(FULL, cval, s);
+        const int scols = __shfl_sync(FULL, cols, s), srows = __shfl_sync(FULL, rows, s);
+        const int swx0 = __shfl_sync(FULL, win_x0, s), swy0 = __shfl_sync(FULL, win_y0, s);
+        const int swin = __shfl_sync(FULL, (int)windowable, s);
+        const unsigned char *img2 = reinterpret_cast<const unsigned char *>(__shfl_sync(FULL, (unsigned long long)I2, s));
+        const unsigned char *win = wwin + s * C::WIN_BYTES;
+        const float *T = wT + s * NP;
+        const float gc = (float)scols, gr = (float)srows, gc1 = (float)(scols - 1), gr1 = (float)(srows - 1);
+        __syncwarp();
+#pragma unroll 1
+        for (int p = lane; p < NP; p += 32) {
+          const int py = p / P, px = p - py * P;
+          const float xf = (float)(px - HALF), yf = (float)(py - HALF);
+          float wx = xf, wy = yf;
+          if (AFFINE) { wx = s00 * xf + s01 * yf; wy = s10 * xf + s11 * yf; }
+          const float sx = sbx + wx, sy = sby + wy;
+          float v0, vx1, vx2, vy1, vy2;
+          if (swin) {
+            v0 = window_sample<WIN_W>(win, swx0, swy0, gc, gc1, gr, gr1, sx, sy);
+            vx1 = window_sample<WIN_W>(win, swx0, swy0, gc, gc1, gr, gr1, sx + 1.0f, sy);
+            vx2 = window_sample<WIN_W>(win, swx0, swy0, gc, gc1, gr, gr1, sx - 1.0f, sy);
+            vy1 = window_sample<WIN_W>(win, swx0, swy0, gc, gc1, gr, gr1, sx, sy + 1.0f);
+            vy2 = window_sample<WIN_W>(win, swx0, swy0, gc, gc1, gr, gr1, sx, sy - 1.0f);
+          } else {
+            v0 = pagk_sample_call(img2, scols, srows, sx, sy);
+            vx1 = pagk_sample_call(img2, scols, srows, sx + 1.0f, sy);
+            vx2 = pagk_sample_call(img2, scols, srows, sx - 1.0f, sy);
+            vy1 = pagk_sample_call(img2, scols, srows, sx, sy + 1.0f);
+            vy2 = pagk_sample_call(img2, scols, srows, sx, sy - 1.0f);
+          }
+          const float e = (v0 + sdb) - sgain * T[p];
+          scratch[3 * p] = 0.5f * (vx1 - vx2);
+          scratch[3 * p + 1] = 0.5f * (vy1 - vy2);
+          scratch[3 * p + 2] = -e;
+        }
+        if (lane == 0) { scratch[NP * 3] = scv; scratch[NP * 3 + 1] = 1.0f; }
+        __syncwarp();
+        double acc = 0.0;
+        float cacc = 0.f;
+        {
+          const float *pa = scratch + offA, *pb = scratch + offB, *pm = scratch + 2;
+#pragma unroll 4
+          for (int p = 0; p < NP; ++p) {
+            const float fa = *pa, fb = *pb, fm = *pm;
+            pa += strideA; pb += strideB; pm += 3;
+            acc = fma((double)fa, (double)fb, acc);
+            cacc = cacc + fm * fm;
+          }
+        }
+        const double t0 = __shfl_sync(FULL, acc, 0), t1 = __shfl_sync(FULL, acc, 1), t2 = __shfl_sync(FULL, acc, 2),
+                     t3 = __shfl_sync(FULL, acc, 3), t4 = __shfl_sync(FULL, acc, 4), t5 = __shfl_sync(FULL, acc, 5),
+                     t6 = __shfl_sync(FULL, acc, 6), t7 = __shfl_sync(FULL, acc, 7), t8 = __shfl_sync(FULL, acc, 8),
+                     t9 = __shfl_sync(FULL, acc, 9), t10 = __shfl_sync(FULL, acc, 10), t11 = __shfl_sync(FULL, acc, 11);
+        if (lane == s) {
+          S.h00 = t0; S.h10 = t1; S.h11 = t2; S.h20 = t3; S.h21 = t4; S.h22 = t5; S.h30 = t6; S.h31 = t7;
+          S.b0 = t8; S.b1 = t9; S.b2 = t10; S.b3 = t11; S.cost = cacc;
+        }
+      }
+      __syncwarp();
+    }
+    PROF(4);
+
+    // ------------------------------------------------------------------ solve, update, exits (lane = slot)
+    if (active) {
+      double h00 = S.h00, h10 = S.h10, h11 = S.h11, h20 = S.h20, h21 = S.h21, h22 = S.h22, h30 = S.h30, h31 = S.h31;
+      double h32 = c * (double)NP, h33 = (double)NP;  // sum of c and of 1 over the patch: exact in double
+      double b0 = S.b0, b1 = S.b1, b2 = S.b2, b3 = S.b3;
+      float cost = S.cost;
+      if (mode.regular) {  // reference src/patch_match.cpp:302-314
+        const double d = (double)sqrtf(dx * dx + dy * dy);
+        const float li = mode.lambda * mode.inv_log_max_dist;
+        const double ad1 = (double)mode.alpha * d + 1.0;
+        const double e_pen = (double)li * log(ad1);
+        const double jx = ((double)(li * mode.alpha) / ad1) * ((double)dx / d);
+        const double jy = ((double)(li * mode.alpha) / ad1) * ((double)dy / d);
+        h00 += jx * jx; h10 += jy * jx; h11 += jy * jy;
+        h20 += 0.0 * jx; h21 += 0.0 * jy; h30 += 0.0 * jx; h31 += 0.0 * jy;
+        b0 += jx * e_pen; b1 += jy * e_pen; b2 += 0.0 * e_pen; b3 += 0.0 * e_pen;
+        cost = (float)((double)cost + e_pen * e_pen);
+      }
+      double u0, u1, u2, u3;
+      pagk_llt_solve4(h00, h10, h11, h20, h21, h22, h30, h31, h32, h33, b0, b1, b2, b3, u0, u1, u2, u3);
+      ++n_iter;
+      bool level_done = false;
+      if (isnan(u0)) {
+        succ = 0; level_done = true;
+      } else if (iter > 0 && cost > lastCost) {
+        level_done = true;
+      } else {
+        dx = (float)((double)dx + u0);
+        dy = (float)((double)dy + u1);
+        if (mode.illum) { dg = (float)((double)dg + u2); db = (float)((double)db + u3); }
+        lastCost = cost;
+        succ = 1;
+        ++iter;
+        const double nrm = sqrt((u0 * u0 + u2 * u2) + (u1 * u1 + u3 * u3));
+        if (nrm < 1e-2 || iter >= mode.iterations) level_done = true;
+      }
+      if (level_done) {
+        const float p2x = ptx + dx, p2y = pty + dy;  // mvPtPyr2Un[i] = pt + (dx, dy)
+        if (level == 0) {
+          const size_t o = (size_t)feat;
+          out.pm_un[o] = make_float2(p2x, p2y);
+          out.pm_status[o] = succ ? 1 : 0;
+          out.pix_err[o] = sqrt((double)lastCost * mode.win_size_inv);
+          out.ncc[o] = 1.0f;
+          out.iters[o] = n_iter;
+          feat = -1;
+        } else {
+          --level;
+          const float scale = 1.0f / (float)(1 << level);
+          ptx = pt1x * scale; pty = pt1y * scale;
+          dx = p2x * 2.0f - ptx; dy = p2y * 2.0f - pty;
+          dg = 0.f; db = 0.f; iter = 0; lastCost = 0.f; succ = 1;
+          needs_setup = true; win_valid = false;
+        }
+      }
+    }
+    __syncwarp();
+    PROF(5);
+  }
+  PROF_FLUSH();
+}
+
+// -------------------------------------------------------------------------------------------------
+bool pagk_lk_lanes_supported(const PagkMode &mode) {
+  return (mode.half == 5 || mode.half == 10) && mode.iterations >= 1 && !mode.calc_ncc;
+}
+
+template <int HALF, bool AFFINE>
+static int launch_lanes(const unsigned char *images, const PagkGeom &g, const PagkPairConst *pcs, const float2 *keys_un,
+                        const PagkOutPtrs &out, const PagkMode &mode, int max_keys, int n_max, int n_pairs,
+                        int *work_counter, int n_sms, cudaStream_t st, long long *prof) {
+  using C = LanesCfg<HALF>;
+  const size_t smem = (size_t)C::WARPS * C::WARP_BYTES;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(pagk_lk_lanes_kernel<HALF, AFFINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  const long long total = (long long)n_max * n_pairs;
+  long long ctas = n_sms;  // persistent: one CTA per SM
+  const long long needed = (total + C::WARPS * 32 - 1) / (C::WARPS * 32);
+  if (ctas > needed) ctas = needed;
+  pagk_lk_lanes_kernel<HALF, AFFINE><<<(unsigned)ctas, C::WARPS * 32, smem, st>>>(images, g, pcs, keys_un, out, mode, max_keys,
+                                                                                  n_max, n_pairs, work_counter, prof);
+  return (int)cudaGetLastError();
+}
+
+int pagk_launch_lk_lanes(const unsigned char *images, const PagkGeom &g, const PagkPairConst *pcs, const float2 *keys_un,
+                         const PagkOutPtrs &out, const PagkMode &mode, int max_keys, int n_max, int n_pairs,
+                         int *work_counter, int n_sms, cudaStream_t st, long long *launches, long long *prof) {
+  if (n_max <= 0 || n_pairs <= 0) return 0;
+  cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), st);
+  if (e != cudaSuccess) return (int)e;
+  int rc;
+  if (mode.half == 5) {
+    rc = mode.affine ? launch_lanes<5, true>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, n_sms, st, prof)
+                     : launch_lanes<5, false>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, n_sms, st, prof);
+  } else {
+    rc = mode.affine ? launch_lanes<10, true>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, n_sms, st, prof)
+                     : launch_lanes<10, false>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, n_sms, st, prof);
+  }
+  ++*launches;
+  return rc;
+}

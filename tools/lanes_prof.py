@@ -1,0 +1,28 @@
+"""Phase profile of the lane-per-feature LK kernel (needs a build with PAGK_NVCC_EXTRA=-DPAGK_LANES_PROF)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.makedirs("gpurun_out", exist_ok=True)
+os.environ["PAGK_LK_TIMELINE"] = "gpurun_out/lanes_prof.txt"
+import numpy as np
+from pixel_aware_gyro_aided_klt_feature_tracker_b200 import capi, synth, tracker
+if len(sys.argv) > 1:
+    capi._lib = capi.load(sys.argv[1])
+cfg = {k: v for k, v in synth.CONFIGS["B"].items() if k != "pairs"}
+pairs = [synth.make_pair(2000 + i, **cfg) for i in range(64)]
+prm = capi.default_params(pyramids=4)
+with tracker.Context(max_keys=1024, max_pairs=64, max_levels=4) as ctx:
+    ctx.upload(pairs, prm)
+    for _ in range(3):
+        ctx.run(); ctx.synchronize()
+        print("run ms", ctx.last_run_ms())
+    outs = [capi.PairOutputs(p.n_keys) for p in pairs]
+    ctx.download(outs)
+it = np.concatenate([o.iters for o in outs])
+print("features", it.size, "iterations: mean %.2f p50 %d p90 %d p99 %d max %d" % (it.mean(), np.percentile(it, 50), np.percentile(it, 90), np.percentile(it, 99), it.max()))
+t = np.loadtxt("gpurun_out/lanes_prof.txt")
+names = ["refill", "setup", "window", "pass", "coop", "solve", "rounds", "lane-rounds"]
+tot = t[:, :6].sum(axis=1)
+print("warps", len(t), "cycles/warp: min %d mean %d max %d" % (tot.min(), tot.mean(), tot.max()))
+for i, n in enumerate(names):
+    print(f"{n:12s} mean {t[:, i].mean():10.0f}  min {t[:, i].min():10.0f} max {t[:, i].max():10.0f}" + (f"  share {100 * t[:, i].sum() / tot.sum():5.1f}%" if i < 6 else ""))
+print("lane occupancy %.3f ; cycles per round %.0f ; pass cycles per round %.0f" % (t[:, 7].sum() / (32 * t[:, 6].sum()), tot.sum() / t[:, 6].sum(), t[:, 3].sum() / t[:, 6].sum()))

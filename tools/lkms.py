@@ -17,4 +17,4 @@ for lib in libs:
         outs = [capi.PairOutputs(p.n_keys) for p in pairs]
         ctx.download(outs)
         it = sum(o.n_iterations for o in outs)
-        print(f"{os.path.basename(lib):28s} lk ms min {min(ms[2:]):.3f} med {np.median(ms[2:]):.3f}  -> {it / min(ms[2:]) / 1e6:.1f} M feature-iter/s (kernel only)")
+        print(f"{os.path.basename(lib):28s} lk ms min {min(ms[2:]):.3f} med {np.median(ms[2:]):.3f}  -> {it / min(ms[2:]) / 1e3:.1f} M feature-iter/s (kernel only)")

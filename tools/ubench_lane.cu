@@ -1,0 +1,131 @@
+// ubench_lane.cu -- de-risk "lane = feature slot" for the whole Gauss-Newton pass: every lane samples its own
+// window (shared memory, lane-private) and runs its own ordered FP64 chains.  Measures cycles per 121-pixel
+// pass per warp for W warps per SM, with fp32 or fp16 windows.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 --fmad=false -o ubench_lane ubench_lane.cu
+#include <cstdio>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+constexpr int WIN_W = 21, WIN_H = 17, NP = 121;
+template <typename WT> struct Lay;
+template <> struct Lay<float> { static constexpr int WIN_BYTES = 1428 + 0; };   // 357 words: odd
+template <> struct Lay<__half> { static constexpr int WIN_BYTES = 716; };       // 179 words: odd
+template <> struct Lay<unsigned char> { static constexpr int WIN_BYTES = 364; }; // 91 words: odd
+struct U8M { unsigned char v; };
+template <> struct Lay<U8M> { static constexpr int WIN_BYTES = 364; };
+
+__device__ __forceinline__ float ld(const float *p) { return *p; }
+__device__ __forceinline__ float ld(const __half *p) { return __half2float(*p); }
+__device__ __forceinline__ float ld(const unsigned char *p) { return (float)(int)*p; }
+__device__ __forceinline__ float ld(const U8M *p) { return __uint_as_float(0x4B000000u | (unsigned int)p->v) - 8388608.0f; }
+
+__device__ __forceinline__ float floor_nn(float x) {
+  const float t = x + 8388608.0f;
+  float r = t - 8388608.0f;
+  if (r > x) r -= 1.0f;
+  return r;
+}
+
+template <typename WT, int UNROLL_X>
+__global__ void __launch_bounds__(256, 1) k(float *out, long long *cycles, int rounds, int warps, int desync) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int WB = Lay<WT>::WIN_BYTES, SLOT = WB + 484;
+  unsigned char *wbase = smem + (size_t)warp * 32 * SLOT;
+  WT *win = reinterpret_cast<WT *>(wbase + lane * WB);
+  float *T = reinterpret_cast<float *>(wbase + 32 * WB + lane * 484);
+  unsigned int rng = 1234567u + threadIdx.x * 7919u + blockIdx.x * 104729u;
+  auto rnd = [&]() { rng = rng * 1664525u + 1013904223u; return (rng >> 8) * (1.0f / 16777216.0f); };
+  for (int i = 0; i < WIN_W * WIN_H; ++i) { const float v = (float)(int)(rnd() * 255.0f); if constexpr (sizeof(WT) == 1) reinterpret_cast<unsigned char *>(win)[i] = (unsigned char)v; else win[i] = (WT)v; }
+  for (int i = 0; i < NP; ++i) T[i] = rnd() * 255.0f;
+  // slot state: patch centre inside the window at (10 + frac, 8 + frac), near-identity affine
+  const float wx0 = 100.0f + (float)(int)(rnd() * 300.0f), wy0 = 80.0f + (float)(int)(rnd() * 200.0f);
+  float bx = wx0 + 10.0f + rnd(), by = wy0 + 8.0f + rnd();
+  const float a00 = 1.0f + 0.02f * (rnd() - 0.5f), a01 = 0.04f * (rnd() - 0.5f), a10 = 0.04f * (rnd() - 0.5f), a11 = 1.0f + 0.02f * (rnd() - 0.5f);
+  const float db = rnd(), gain = 1.0f + 0.01f * rnd();
+  const double c = -(double)(rnd() * 255.0f);
+  // float index magic: t = fy * 21 + (fx + 2^23 - origin) -> bits(t) - 0x4B000000 = element index
+  const float org = wy0 * (float)WIN_W + wx0;
+  __syncthreads();
+  double h00 = 0, h10 = 0, h11 = 0, h20 = 0, h21 = 0, h22 = 0, h30 = 0, h31 = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+  float cost = 0.f;
+  bool bad = false;
+  if (desync) { const long long tw = clock64() + (long long)warp * 3777 + 500; while (clock64() < tw) {} }
+  const long long t0 = clock64();
+  for (int r = 0; r < rounds; ++r) {
+#pragma unroll 1
+    for (int yi = 0; yi < 11; ++yi) {
+      const float yf = (float)(yi - 5);
+      const float r01 = a01 * yf, r11 = a11 * yf;
+#pragma unroll UNROLL_X
+      for (int xi = 0; xi < 11; ++xi) {
+        const float xf = (float)(xi - 5);
+        const float wx = a00 * xf + r01, wy = a10 * xf + r11;
+        const float sx = bx + wx, sy = by + wy;
+        const float fx = floor_nn(sx), fy = floor_nn(sy);
+        const float xx = sx - fx, yy = sy - fy;
+        const float wa = 1.0f - xx, wb = 1.0f - yy;
+        const float X1 = sx + 1.0f, Y1 = sy + 1.0f;
+        const float xx1 = X1 - (fx + 1.0f), yy1 = Y1 - (fy + 1.0f);
+        const float wa1 = 1.0f - xx1, wb1 = 1.0f - yy1;
+        bad |= (xx1 >= 1.0f) | (yy1 >= 1.0f);
+        const float ti = __fmaf_rn(fy, (float)WIN_W, (fx - org) + 8388608.0f);
+        const int idx = __float_as_int(ti) - 0x4B000000;
+        const WT *w = win + idx;
+        const float m0 = ld(w - WIN_W), m1 = ld(w - WIN_W + 1);
+        const float c_1 = ld(w - 1), c0 = ld(w), c1 = ld(w + 1), c2 = ld(w + 2);
+        const float d_1 = ld(w + WIN_W - 1), d0 = ld(w + WIN_W), d1 = ld(w + WIN_W + 1), d2 = ld(w + WIN_W + 2);
+        const float n0 = ld(w + 2 * WIN_W), n1 = ld(w + 2 * WIN_W + 1);
+        const float Hm = wa * m0 + xx * m1;
+        const float H0 = wa * c0 + xx * c1, H0p = wa1 * c1 + xx1 * c2, H0m = wa * c_1 + xx * c0;
+        const float H1 = wa * d0 + xx * d1, H1p = wa1 * d1 + xx1 * d2, H1m = wa * d_1 + xx * d0;
+        const float H2 = wa * n0 + xx * n1;
+        const float v0 = wb * H0 + yy * H1;
+        const float vx1 = wb * H0p + yy * H1p, vx2 = wb * H0m + yy * H1m;
+        const float vy1 = wb1 * H1 + yy1 * H2, vy2 = wb * Hm + yy * H0;
+        const float Tv = T[yi * 11 + xi];
+        const float e = (v0 + db) - gain * Tv;
+        const float gx = 0.5f * (vx1 - vx2), gy = 0.5f * (vy1 - vy2), mf = -e;
+        const double x = (double)gx, y = (double)gy, m = (double)mf;
+        h00 = fma(x, x, h00); h10 = fma(y, x, h10); h11 = fma(y, y, h11);
+        h20 = fma(c, x, h20); h21 = fma(c, y, h21); h22 = fma(c, c, h22);
+        h30 = h30 + x; h31 = h31 + y;
+        b0 = fma(x, m, b0); b1 = fma(y, m, b1); b2 = fma(c, m, b2); b3 = b3 + m;
+        cost = cost + mf * mf;
+      }
+    }
+    bx += 0.001f; by -= 0.001f;
+  }
+  const long long t1 = clock64();
+  out[blockIdx.x * blockDim.x + threadIdx.x] = (float)(h00 + h10 + h11 + h20 + h21 + h22 + h30 + h31 + b0 + b1 + b2 + b3) + cost + (bad ? 1.f : 0.f);
+  if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = t1 - t0;
+}
+
+template <typename WT, int U>
+void run(const char *name, int warps, int desync = 0) {
+  float *out; long long *cyc, h;
+  cudaMalloc(&out, 148 * 256 * 4); cudaMalloc(&cyc, 8);
+  const int rounds = 40;
+  const size_t smem = (size_t)warps * 32 * (Lay<WT>::WIN_BYTES + 484);
+  if (smem > 227 * 1024) { printf("%-10s unroll %2d warps %d: smem %zu too large\n", name, U, warps, smem); return; }
+  cudaFuncSetAttribute(k<WT, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  k<WT, U><<<148, warps * 32, smem>>>(out, cyc, rounds, warps, desync);
+  cudaEventRecord(e0);
+  k<WT, U><<<148, warps * 32, smem>>>(out, cyc, rounds, warps, desync);
+  cudaEventRecord(e1);
+  cudaError_t err = cudaDeviceSynchronize();
+  float ms; cudaEventElapsedTime(&ms, e0, e1);
+  cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+  const double cyc_round = (double)h / rounds;
+  printf("%-6s desync %d unroll %2d warps/SM %d (smem %6zu): %8.0f cycles/pass/warp = %6.1f cyc/pixel ; SM rate %.4f slot-passes/cycle -> %.2f G slot-passes/s @1.965GHz x148 (%.3f ms) %s\n",
+         name, desync, U, warps, smem, cyc_round, cyc_round / NP, warps * 32 / cyc_round, warps * 32 / cyc_round * 1.965 * 148, ms, err == cudaSuccess ? "" : cudaGetErrorString(err));
+  cudaFree(out); cudaFree(cyc);
+}
+
+int main() {
+  run<U8M, 11>("u8m", 8, 0); run<U8M, 11>("u8m", 8, 1);
+  run<U8M, 4>("u8m", 8, 1); run<U8M, 2>("u8m", 8, 1); run<U8M, 1>("u8m", 8, 1); run<U8M, 3>("u8m", 8, 1);
+  run<U8M, 2>("u8m", 8, 0); run<U8M, 4>("u8m", 8, 0);
+  return 0;
+}
