@@ -112,7 +112,8 @@ LIB_NAME = "libpagk_cuda.so"
 
 
 def lib_path() -> str:
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", LIB_NAME)
+    """the in-tree library; PAGK_LIB=<path> selects another build of the same ABI (kernel A/B runs)"""
+    return os.environ.get("PAGK_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", LIB_NAME)
 
 
 _lib = None

@@ -38,7 +38,13 @@
 
 namespace {
 
-constexpr int LANES_WARPS = 8;
+// warps per CTA and CTAs per SM: 8 warps (two per scheduler) fill the shared memory of an SM; as several small
+// CTAs they leave the SM one by one when the work runs out, and the next launch's CTAs move in
+#ifndef PAGK_LANES_WARPS
+#define PAGK_LANES_WARPS 8
+#endif
+constexpr int LANES_WARPS_SM = 8;
+constexpr int LANES_WARPS = PAGK_LANES_WARPS;
 // a warp with at most this many live lanes runs them one by one through the cooperative pass (lanes = pixels,
 // then lanes = accumulators: about 2.2 k warp instructions per slot) instead of a lockstep pass (17 k)
 #ifndef PAGK_LANES_SPARSE
@@ -67,7 +73,9 @@ struct LanesCfg {
   // per-warp scratch of the cooperative pass: NP records (Ix, Iy, -e) and the two constants c and 1
   static constexpr int SCRATCH_FLOATS = NP * 3 + 4;
   static constexpr int WARP_BYTES = 32 * SLOT_BYTES + SCRATCH_FLOATS * 4;
-  static constexpr int WARPS = (227 * 1024) / WARP_BYTES < LANES_WARPS ? (227 * 1024) / WARP_BYTES : LANES_WARPS;
+  static constexpr int WARPS_SM = (227 * 1024) / WARP_BYTES < LANES_WARPS_SM ? (227 * 1024) / WARP_BYTES : LANES_WARPS_SM;
+  static constexpr int WARPS = WARPS_SM < LANES_WARPS ? WARPS_SM : LANES_WARPS;
+  static constexpr int CTAS_SM = WARPS_SM / WARPS;
   static_assert(WIN_W <= 32, "one lane per window column");
   static_assert(WARPS >= 1, "patch too large for the lane kernel");
 };
@@ -151,7 +159,7 @@ struct Sums {
 }  // namespace
 
 template <int HALF, bool AFFINE>
-__global__ void __launch_bounds__(LanesCfg<HALF>::WARPS * 32, 1)
+__global__ void __launch_bounds__(LanesCfg<HALF>::WARPS * 32, LanesCfg<HALF>::CTAS_SM)
 pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const PagkPairConst *__restrict__ pcs,
                      const float2 *__restrict__ keys_un, PagkOutPtrs out, PagkMode mode, int max_keys, int n_max,
                      int n_pairs, int *__restrict__ work_counter, long long *__restrict__ prof) {
@@ -379,11 +387,13 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
     // Horizontal interpolations are shared between samples only where the reference would evaluate the
     // identical expression.
     if (!sparse) {
-      bool bad = false;
+      float badv = 0.0f;
       // lanes without a fast slot walk a harmless patch in the middle of their window
       const float pbx = fast ? bx : (float)(HALF + 5) + 0.5f, pby = fast ? by : (float)(HALF + 3) + 0.5f;
       const float q00 = fast ? a00 : 1.0f, q01 = fast ? a01 : 0.0f, q10 = fast ? a10 : 0.0f, q11 = fast ? a11 : 1.0f;
-      const float org = fast ? (float)(win_y0 * WIN_W + win_x0) : 0.0f;
+      // window element index from the mantissas of ty = 2^23 + floor(sy) and tx = 2^23 + floor(sx):
+      // bits(ty) * WIN_W + bits(tx) - kk, with kk = (WIN_W + 1) * bits(2^23) + origin (mod 2^32)
+      const unsigned int kk = (unsigned int)(WIN_W + 1) * 0x4B000000u + (unsigned int)(fast ? win_y0 * WIN_W + win_x0 : 0);
 #pragma unroll 1
       for (int yi = 0; yi < P; ++yi) {
         const float yf = (float)(yi - HALF);
@@ -395,16 +405,16 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
           float wx = xf, wy = yf;
           if (AFFINE) { wx = q00 * xf + r01; wy = q10 * xf + r11; }
           const float sx = pbx + wx, sy = pby + wy;
-          const float fx = floor_nn(sx), fy = floor_nn(sy);
+          // floor for 0 <= x < 2^22: x + 2^23 rounded DOWN is 2^23 + floor(x) exactly; taking 2^23 off is exact
+          const float tx = __fadd_rd(sx, 8388608.0f), ty = __fadd_rd(sy, 8388608.0f);
+          const float fx = tx - 8388608.0f, fy = ty - 8388608.0f;
           const float xx = sx - fx, yy = sy - fy;
           const float wa = 1.0f - xx, wb = 1.0f - yy;
           const float X1 = sx + 1.0f, Y1 = sy + 1.0f;
           const float xx1 = X1 - (fx + 1.0f), yy1 = Y1 - (fy + 1.0f);
           const float wa1 = 1.0f - xx1, wb1 = 1.0f - yy1;
-          bad |= (xx1 >= 1.0f) | (yy1 >= 1.0f);
-          // element index fy * WIN_W + fx - org, formed exactly in float and read off the mantissa
-          const float ti = __fmaf_rn(fy, (float)WIN_W, (fx - org) + 8388608.0f);
-          const unsigned char *w = mywin + (__float_as_int(ti) - 0x4B000000);
+          badv = fmaxf(badv, fmaxf(xx1, yy1));
+          const unsigned char *w = mywin + (int)((unsigned int)__float_as_int(ty) * (unsigned int)WIN_W + (unsigned int)__float_as_int(tx) - kk);
           const float m0 = u8f(w[-WIN_W]), m1 = u8f(w[-WIN_W + 1]);
           const float c_1 = u8f(w[-1]), c0 = u8f(w[0]), c1 = u8f(w[1]), c2 = u8f(w[2]);
           const float d_1 = u8f(w[WIN_W - 1]), d0 = u8f(w[WIN_W]), d1 = u8f(w[WIN_W + 1]), d2 = u8f(w[WIN_W + 2]);
@@ -428,7 +438,7 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
           S.cost = S.cost + mf * mf;
         }
       }
-      coop |= active && fast && bad;
+      coop |= active && fast && (badv >= 1.0f);
     }
     PROF(3);
 
@@ -586,7 +596,7 @@ static int launch_lanes(const unsigned char *images, const PagkGeom &g, const Pa
     configured = true;
   }
   const long long total = (long long)n_max * n_pairs;
-  long long ctas = n_sms;  // persistent: one CTA per SM
+  long long ctas = (long long)n_sms * C::CTAS_SM;  // persistent: the SMs are filled once
   const long long needed = (total + C::WARPS * 32 - 1) / (C::WARPS * 32);
   if (ctas > needed) ctas = needed;
   pagk_lk_lanes_kernel<HALF, AFFINE><<<(unsigned)ctas, C::WARPS * 32, smem, st>>>(images, g, pcs, keys_un, out, mode, max_keys,

@@ -26,7 +26,7 @@ __device__ __forceinline__ float floor_nn(float x) {
   return r;
 }
 
-template <typename WT, int UNROLL_X>
+template <typename WT, int UNROLL_X, bool FUSE = false>
 __global__ void __launch_bounds__(256, 1) k(float *out, long long *cycles, int rounds, int warps, int desync) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -72,6 +72,23 @@ __global__ void __launch_bounds__(256, 1) k(float *out, long long *cycles, int r
         const float ti = __fmaf_rn(fy, (float)WIN_W, (fx - org) + 8388608.0f);
         const int idx = __float_as_int(ti) - 0x4B000000;
         const WT *w = win + idx;
+        float v0, vx1, vx2, vy1, vy2;
+        if constexpr (FUSE) {
+          auto B = [](const WT *p) { return __uint_as_float(0x4B000000u | (unsigned int)*reinterpret_cast<const unsigned char *>(p)); };
+          const float m0 = B(w - WIN_W), m1 = B(w - WIN_W + 1);
+          const float c_1 = B(w - 1), c0 = B(w), c1 = B(w + 1), c2 = B(w + 2);
+          const float d_1 = B(w + WIN_W - 1), d0 = B(w + WIN_W), d1 = B(w + WIN_W + 1), d2 = B(w + WIN_W + 2);
+          const float n0 = B(w + 2 * WIN_W), n1 = B(w + 2 * WIN_W + 1);
+          const float na = wa * -8388608.0f, nx = xx * -8388608.0f, na1 = wa1 * -8388608.0f, nx1 = xx1 * -8388608.0f;
+#define PR(wt, nw, tap) __fmaf_rn(wt, tap, nw)
+          const float Hm = PR(wa, na, m0) + PR(xx, nx, m1);
+          const float H0 = PR(wa, na, c0) + PR(xx, nx, c1), H0p = PR(wa1, na1, c1) + PR(xx1, nx1, c2), H0m = PR(wa, na, c_1) + PR(xx, nx, c0);
+          const float H1 = PR(wa, na, d0) + PR(xx, nx, d1), H1p = PR(wa1, na1, d1) + PR(xx1, nx1, d2), H1m = PR(wa, na, d_1) + PR(xx, nx, d0);
+          const float H2 = PR(wa, na, n0) + PR(xx, nx, n1);
+          v0 = wb * H0 + yy * H1;
+          vx1 = wb * H0p + yy * H1p; vx2 = wb * H0m + yy * H1m;
+          vy1 = wb1 * H1 + yy1 * H2; vy2 = wb * Hm + yy * H0;
+        } else {
         const float m0 = ld(w - WIN_W), m1 = ld(w - WIN_W + 1);
         const float c_1 = ld(w - 1), c0 = ld(w), c1 = ld(w + 1), c2 = ld(w + 2);
         const float d_1 = ld(w + WIN_W - 1), d0 = ld(w + WIN_W), d1 = ld(w + WIN_W + 1), d2 = ld(w + WIN_W + 2);
@@ -80,9 +97,10 @@ __global__ void __launch_bounds__(256, 1) k(float *out, long long *cycles, int r
         const float H0 = wa * c0 + xx * c1, H0p = wa1 * c1 + xx1 * c2, H0m = wa * c_1 + xx * c0;
         const float H1 = wa * d0 + xx * d1, H1p = wa1 * d1 + xx1 * d2, H1m = wa * d_1 + xx * d0;
         const float H2 = wa * n0 + xx * n1;
-        const float v0 = wb * H0 + yy * H1;
-        const float vx1 = wb * H0p + yy * H1p, vx2 = wb * H0m + yy * H1m;
-        const float vy1 = wb1 * H1 + yy1 * H2, vy2 = wb * Hm + yy * H0;
+        v0 = wb * H0 + yy * H1;
+        vx1 = wb * H0p + yy * H1p; vx2 = wb * H0m + yy * H1m;
+        vy1 = wb1 * H1 + yy1 * H2; vy2 = wb * Hm + yy * H0;
+        }
         const float Tv = T[yi * 11 + xi];
         const float e = (v0 + db) - gain * Tv;
         const float gx = 0.5f * (vx1 - vx2), gy = 0.5f * (vy1 - vy2), mf = -e;
@@ -101,18 +119,18 @@ __global__ void __launch_bounds__(256, 1) k(float *out, long long *cycles, int r
   if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = t1 - t0;
 }
 
-template <typename WT, int U>
+template <typename WT, int U, bool FUSE = false>
 void run(const char *name, int warps, int desync = 0) {
   float *out; long long *cyc, h;
   cudaMalloc(&out, 148 * 256 * 4); cudaMalloc(&cyc, 8);
   const int rounds = 40;
   const size_t smem = (size_t)warps * 32 * (Lay<WT>::WIN_BYTES + 484);
   if (smem > 227 * 1024) { printf("%-10s unroll %2d warps %d: smem %zu too large\n", name, U, warps, smem); return; }
-  cudaFuncSetAttribute(k<WT, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(k<WT, U, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-  k<WT, U><<<148, warps * 32, smem>>>(out, cyc, rounds, warps, desync);
+  k<WT, U, FUSE><<<148, warps * 32, smem>>>(out, cyc, rounds, warps, desync);
   cudaEventRecord(e0);
-  k<WT, U><<<148, warps * 32, smem>>>(out, cyc, rounds, warps, desync);
+  k<WT, U, FUSE><<<148, warps * 32, smem>>>(out, cyc, rounds, warps, desync);
   cudaEventRecord(e1);
   cudaError_t err = cudaDeviceSynchronize();
   float ms; cudaEventElapsedTime(&ms, e0, e1);
@@ -124,8 +142,8 @@ void run(const char *name, int warps, int desync = 0) {
 }
 
 int main() {
-  run<U8M, 11>("u8m", 8, 0); run<U8M, 11>("u8m", 8, 1);
-  run<U8M, 4>("u8m", 8, 1); run<U8M, 2>("u8m", 8, 1); run<U8M, 1>("u8m", 8, 1); run<U8M, 3>("u8m", 8, 1);
-  run<U8M, 2>("u8m", 8, 0); run<U8M, 4>("u8m", 8, 0);
+  run<U8M, 2>("u8m", 8, 1); run<U8M, 2, true>("u8m-fuse", 8, 1);
+  run<U8M, 11>("u8m", 8, 1); run<U8M, 11, true>("u8m-fuse", 8, 1);
+  run<U8M, 2>("u8m", 4, 1); run<U8M, 2, true>("u8m-fuse", 4, 1);
   return 0;
 }
