@@ -198,7 +198,7 @@ int check_batch(pagk_handle *h, int n_pairs, int width, int height, int levels, 
   return PAGK_OK;
 }
 
-int launch_lk(pagk_handle *h, const PagkOutPtrs &o, const PagkMode &m, int n_max, int n_pairs) {
+int launch_lk_kernel(pagk_handle *h, const PagkOutPtrs &o, const PagkMode &m, int n_max, int n_pairs) {
   if (h->lk_kernel == 0 && pagk_lk_lanes_supported(m)) {
     // PAGK_LK_TIMELINE=<file> with a -DPAGK_LANES_PROF build: per-warp phase cycles (developer aid)
     if (h->d_dbg) cudaMemsetAsync(h->d_dbg, 0, 2048 * 8 * sizeof(long long), h->stream);
@@ -241,6 +241,14 @@ int launch_lk(pagk_handle *h, const PagkOutPtrs &o, const PagkMode &m, int n_max
   }
   return pagk_launch_lk(h->d_images, h->geom, h->d_pc, h->d_keys_un, o, m, h->cfg.max_keys, n_max, n_pairs, h->stream,
                         &h->launches);
+}
+
+// patch alignment, then PatchMatch::NCC when the caller asked for it (bCalculateNCC_)
+int launch_lk(pagk_handle *h, const PagkOutPtrs &o, const PagkMode &m, int n_max, int n_pairs) {
+  const int rc = launch_lk_kernel(h, o, m, n_max, n_pairs);
+  if (rc != 0 || !m.calc_ncc) return rc;
+  return pagk_launch_ncc(h->d_images, h->geom, h->d_pc, h->d_keys_un, o, m, h->cfg.max_keys, n_max, n_pairs, h->stream,
+                         &h->launches);
 }
 
 template <class T>

@@ -387,6 +387,51 @@ __global__ void pagk_lk_kernel(const unsigned char *__restrict__ images, PagkGeo
 }
 
 // =================================================================================================
+// PatchMatch::NCC (reference src/patch_match.cpp:433-469), run when bCalculateNCC_ is set (off by default,
+// include/patch_match.h:49).  The reference evaluates it after every level with the level-0 images and keeps the
+// last value (:356-366), i.e. the one taken at the final level-0 position.  Zero-mean NCC over the P x P samples in
+// x-outer / y-inner order with sequential float sums: one thread per feature walks them in that order (the second
+// pass recomputes the samples instead of storing them; the values are identical).
+// =================================================================================================
+__global__ void __launch_bounds__(128) pagk_ncc_kernel(const unsigned char *__restrict__ images, PagkGeom g,
+                                                     const PagkPairConst *__restrict__ pcs,
+                                                     const float2 *__restrict__ keys_un, PagkOutPtrs out, PagkMode mode,
+                                                     int max_keys) {
+  const int pair = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pcs[pair].n_keys) return;
+  const size_t o = (size_t)pair * max_keys + i;
+  if (!out.gyro_status[o]) return;  // skipped at :173, mvNcc stays 0
+  const unsigned char *I1 = pagk_level_ptr(images, g, pair, 0, 0), *I2 = pagk_level_ptr(images, g, pair, 1, 0);
+  const int cols = g.lv[0].cols, rows = g.lv[0].rows, h = mode.half;
+  const float2 pr = keys_un[o], pc = out.pm_un[o];
+  const float4 A = out.affine[o];
+  float mean_ref = 0.f, mean_cur = 0.f;
+  for (int x = -h; x <= h; ++x)
+    for (int y = -h; y <= h; ++y) {
+      float wx = (float)x, wy = (float)y;
+      if (mode.affine) { wx = A.x * (float)x + A.y * (float)y; wy = A.z * (float)x + A.w * (float)y; }
+      mean_ref += pagk_sample(I1, cols, rows, pr.x + (float)x, pr.y + (float)y);
+      mean_cur += pagk_sample(I2, cols, rows, pc.x + wx, pc.y + wy);
+    }
+  const float n = (float)((2 * h + 1) * (2 * h + 1));
+  mean_ref /= n;
+  mean_cur /= n;
+  float num = 0.f, d1 = 0.f, d2 = 0.f;
+  for (int x = -h; x <= h; ++x)
+    for (int y = -h; y <= h; ++y) {
+      float wx = (float)x, wy = (float)y;
+      if (mode.affine) { wx = A.x * (float)x + A.y * (float)y; wy = A.z * (float)x + A.w * (float)y; }
+      const float a = pagk_sample(I1, cols, rows, pr.x + (float)x, pr.y + (float)y) - mean_ref;
+      const float b = pagk_sample(I2, cols, rows, pc.x + wx, pc.y + wy) - mean_cur;
+      num += a * b;
+      d1 += a * a;
+      d2 += b * b;
+    }
+  out.ncc[o] = (float)((double)num / sqrt((double)(d1 * d2) + 1e-10));
+}
+
+// =================================================================================================
 // K4: DistortPoints + SetMatcher + the threshold filter.  One CTA per frame pair.  The mean pixel
 // error is a double sum in feature-index order (src/gyro_aided_tracker.cpp:294-305): thread 0 adds
 // chunk after chunk from shared memory so that the rounding sequence is the reference's.
@@ -534,6 +579,16 @@ int pagk_launch_lk(const unsigned char *images, const PagkGeom &g, const PagkPai
   }
   dim3 grid((n_max + wpc - 1) / wpc, n_pairs);
   pagk_lk_kernel<<<grid, wpc * 32, smem, st>>>(images, g, pcs, keys_un, out, mode, max_keys, wpc);
+  ++*launches;
+  return (int)cudaGetLastError();
+}
+
+int pagk_launch_ncc(const unsigned char *images, const PagkGeom &g, const PagkPairConst *pcs, const float2 *keys_un,
+                    const PagkOutPtrs &out, const PagkMode &mode, int max_keys, int n_max, int n_pairs, cudaStream_t st,
+                    long long *launches) {
+  if (n_max <= 0 || n_pairs <= 0) return 0;
+  dim3 grid((n_max + 127) / 128, n_pairs);
+  pagk_ncc_kernel<<<grid, 128, 0, st>>>(images, g, pcs, keys_un, out, mode, max_keys);
   ++*launches;
   return (int)cudaGetLastError();
 }

@@ -580,7 +580,7 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
 
 // -------------------------------------------------------------------------------------------------
 bool pagk_lk_lanes_supported(const PagkMode &mode) {
-  return (mode.half == 5 || mode.half == 10) && mode.iterations >= 1 && !mode.calc_ncc;
+  return (mode.half == 5 || mode.half == 10) && mode.iterations >= 1;
 }
 
 template <int HALF, bool AFFINE>

@@ -581,7 +581,7 @@ pagk_lk_slots_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
 size_t pagk_lk_slots_smem() { return sizeof(SlotShared); }
 
 bool pagk_lk_slots_supported(const PagkMode &mode) {
-  return mode.half == HALF && mode.iterations >= 1 && !mode.calc_ncc;
+  return mode.half == HALF && mode.iterations >= 1;
 }
 
 int pagk_launch_lk_slots(const unsigned char *images, const PagkGeom &g, const PagkPairConst *pcs, const float2 *keys_un,
