@@ -31,6 +31,9 @@ METRIC = "tracked features/sec at 752x480, 1024 feats, 4 levels; px error vs CPU
 # algorithmic work of one feature-iteration at an 11x11 patch
 FP32_FLOP_PER_FEATURE_ITER = {5: 8.5e3, 10: 30.9e3}
 HBM_BYTES_PER_FEATURE_ITER = 120.0
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the LK kernel on this workload, from the committed
+# `ncu --set full` capture (profiles/r01_ncu_summary.md): 49.55 MB + 1.59 MB
+LK_DRAM_TRAFFIC_BYTES_PER_LAUNCH = {("B", 64): 51.14e6}
 N_ROTATE = 3  # resident batches per GPU; 3 x 61 MB of pyramids > 126 MB L2
 
 
@@ -316,8 +319,11 @@ def main():
     fp32_peak = 148 * 128 * 2 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12  # TFLOP/s with FMA, nominal lanes x clock
     ach = it_launch * FP32_FLOP_PER_FEATURE_ITER.get(half, 70.0 * (2 * half + 1) ** 2) / (lk_avg_ms * 1e-3) / 1e12
     hbm_ach = it_launch * HBM_BYTES_PER_FEATURE_ITER / (lk_avg_ms * 1e-3) / 1e9
-    roofline = {"bound": "fp32", "kernel": "pagk_lk_kernel", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
-                "frac": ach / fp32_peak, "frac_of_non_fma_peak": ach / (fp32_peak / 2), "traffic": None,
+    roofline = {"bound": "fp32", "kernel": "pagk_lk_lanes_kernel", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
+                "frac": ach / fp32_peak, "frac_of_non_fma_peak": ach / (fp32_peak / 2),
+                "traffic": LK_DRAM_TRAFFIC_BYTES_PER_LAUNCH.get((args.config, n_pairs)),
+                "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                "algorithmic_flop_per_feature_iteration": FP32_FLOP_PER_FEATURE_ITER.get(half, 70.0 * (2 * half + 1) ** 2),
                 "peak_source": f"148 SM x 128 lanes x 2 x {peaks.get('sm_max_mhz', 1965.0):.0f} MHz ({peaks_kind} sm_max_mhz); "
                                "FMA contraction is forbidden by bit-parity, so half of it is the reachable ceiling",
                 "kernel_ms": lk_avg_ms, "kernel_launches_timed": lk_n, "feature_iterations_per_launch": it_launch,

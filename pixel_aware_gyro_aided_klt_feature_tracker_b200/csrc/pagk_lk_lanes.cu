@@ -108,11 +108,34 @@ __device__ __forceinline__ void load_window(unsigned char (&v)[WIN_H], const uns
                                             int rows, int x0, int y0, int lane) {
   if (lane < WIN_W) {
     const int gx = min(max(x0 + lane, 0), cols);
+    if (y0 >= 0 && y0 + WIN_H - 1 <= rows) {  // warp-uniform: no row clamps, one pointer walks down the column
+      const unsigned char *q = img + y0 * cols + gx;
 #pragma unroll
-    for (int i = 0; i < WIN_H; ++i) {
-      const int gy = min(max(y0 + i, 0), rows);
-      v[i] = __ldg(img + gy * cols + gx);
+      for (int i = 0; i < WIN_H; ++i) { v[i] = __ldg(q); q += cols; }
+    } else {
+#pragma unroll
+      for (int i = 0; i < WIN_H; ++i) {
+        const int gy = min(max(y0 + i, 0), rows);
+        v[i] = __ldg(img + gy * cols + gx);
+      }
     }
+  }
+}
+// the (P+2) x (P+2) taps of a template that lies inside the level: no clamps at all
+template <int TW>
+__device__ __forceinline__ void load_template(unsigned char (&v)[TW], const unsigned char *__restrict__ img, int cols, int x0,
+                                              int y0, int lane) {
+  if (lane < TW) {
+    const unsigned char *q = img + y0 * cols + x0 + lane;
+#pragma unroll
+    for (int i = 0; i < TW; ++i) { v[i] = __ldg(q); q += cols; }
+  }
+}
+template <int WIN_W, int TW>
+__device__ __forceinline__ void store_template(unsigned char *__restrict__ win, const unsigned char (&v)[TW], int lane) {
+  if (lane < TW) {
+#pragma unroll
+    for (int i = 0; i < TW; ++i) win[i * WIN_W + lane] = v[i];
   }
 }
 template <int WIN_W, int WIN_H>
@@ -193,6 +216,14 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
   const int selB = (int)((0x222210310100ull >> (4 * role)) & 0xfull);  // 0 Ix, 1 Iy, 2 -e, 3 c
   const int offA = selA < 3 ? selA : NP * 3 + (selA - 3), strideA = selA < 3 ? 3 : 0;
   const int offB = selB < 3 ? selB : NP * 3 + (selB - 3), strideB = selB < 3 ? 3 : 0;
+
+  // pixel offsets of this lane in the cooperative (lanes = pixels) template pass
+  float tpx[(NP + 31) / 32], tpy[(NP + 31) / 32];
+#pragma unroll
+  for (int k = 0; k < (NP + 31) / 32; ++k) {
+    const int p = lane + 32 * k, py = p / P;
+    tpx[k] = (float)(p - py * P - HALF); tpy[k] = (float)(py - HALF);
+  }
 
   // ---- slot state (registers of the owning lane) ----
   int feat = -1, pair = 0, level = 0, iter = 0, n_iter = 0, succ = 1;
@@ -301,27 +332,27 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
         const float txlo = sptx + (-hf), txhi = sptx + hf, tylo = spty + (-hf), tyhi = spty + hf;
         const bool tin = txlo >= 0.0f && txhi < (float)scols && tylo >= 0.0f && tyhi < (float)srows;
         const int x0 = (int)txlo, y0 = (int)tylo;
-        unsigned char v1[WIN_H], v2[WIN_H];
+        unsigned char v1[P + 2], v2[WIN_H];
         // both windows' loads in flight together: one global round trip per level instead of two
-        if (tin) load_window<WIN_W, WIN_H>(v1, img1, scols, srows, x0, y0, lane);
+        if (tin) load_template<P + 2>(v1, img1, scols, x0, y0, lane);
         if (rs) load_window<WIN_W, WIN_H>(v2, img1 + slot_bytes, scols, srows, rx0, ry0, lane);
         float c;
         if (tin) {
           // no clamp fires anywhere in the template: sample from a staged window of the reference level
           // (taps reach floor(hi) + 1 <= x0 + P + 1: inside the window)
           __syncwarp();
-          store_window<WIN_W, WIN_H>(win, v1, lane);
+          store_template<WIN_W, P + 2>(win, v1, lane);
           __syncwarp();
+          // window element index from the mantissas of 2^23 + floor(.), as in the pass
+          const unsigned int kt = (unsigned int)(WIN_W + 1) * 0x4B000000u + (unsigned int)(y0 * WIN_W + x0);
 #pragma unroll
           for (int k = 0; k < (NP + 31) / 32; ++k) {
             const int p = lane + 32 * k;
             if (p < NP) {
-              const int py = p / P, px = p - py * P;
-              const float cx = sptx + (float)(px - HALF), cy = spty + (float)(py - HALF);
-              int ix, iy;
-              const float fx = floor_nn(cx, ix), fy = floor_nn(cy, iy);
-              const float xx = cx - fx, yy = cy - fy, wa = 1.0f - xx, wb = 1.0f - yy;
-              const unsigned char *q = win + (iy - y0) * WIN_W + (ix - x0);
+              const float cx = sptx + tpx[k], cy = spty + tpy[k];
+              const float tx = __fadd_rd(cx, 8388608.0f), ty = __fadd_rd(cy, 8388608.0f);
+              const float xx = cx - (tx - 8388608.0f), yy = cy - (ty - 8388608.0f), wa = 1.0f - xx, wb = 1.0f - yy;
+              const unsigned char *q = win + (int)((unsigned int)__float_as_int(ty) * (unsigned int)WIN_W + (unsigned int)__float_as_int(tx) - kt);
               T[p] = wb * (wa * u8f(q[0]) + xx * u8f(q[1])) + yy * (wa * u8f(q[WIN_W]) + xx * u8f(q[WIN_W + 1]));
             }
           }

@@ -137,6 +137,20 @@ def test_distortion_and_single_homography(gpu_ctx, oracle):
         helpers.assert_bit_exact(g, c)
 
 
+@pytest.mark.parametrize("e_type", [3, 4])
+def test_ncc_enabled_bit_exact(gpu_ctx, oracle, e_type):
+    """bCalculateNCC_ = true (include/patch_match.h:49): PatchMatch::NCC, src/patch_match.cpp:433-469, with and
+    without the affine warp; the tracker itself never switches it on, so this is the only place it runs"""
+    pairs = [synth.make_pair(7600 + i, width=320, height=240, n_keys=200, pyramids=3, border=6) for i in range(2)]
+    prm = capi.default_params(pyramids=3, e_type=e_type, calc_ncc=1)
+    gpu = gpu_ctx.track_batch(pairs, prm)
+    for g, p in zip(gpu, pairs):
+        c = oracle.track(p, prm, 2)[1]
+        helpers.assert_bit_exact(g, c)
+        ok = c.pm_status == 1
+        assert ok.any() and np.all(np.abs(g.ncc[ok]) <= 1.0 + 1e-6) and np.median(g.ncc[ok]) > 0.8
+
+
 def test_stage_api_gyro_predict_and_patch_match(gpu_ctx, oracle):
     """the finer-grained entry points mirror GyroPredictFeatures and PatchMatch(...).OpticalFlowMultiLevel()"""
     p = synth.make_pair(7600, width=320, height=240, n_keys=180, pyramids=3, border=20)
