@@ -48,7 +48,7 @@ constexpr int LANES_WARPS = PAGK_LANES_WARPS;
 // a warp with at most this many live lanes runs them one by one through the cooperative pass (lanes = pixels,
 // then lanes = accumulators: about 2.2 k warp instructions per slot) instead of a lockstep pass (17 k)
 #ifndef PAGK_LANES_SPARSE
-#define PAGK_LANES_SPARSE 7
+#define PAGK_LANES_SPARSE 5
 #endif
 // pixels of a patch row unrolled in the pass loop.  The whole row (11) gives the scheduler the most to overlap but
 // is a 25 KB loop body, and with the warps of an SM in different phases the instruction cache then misses
@@ -185,7 +185,7 @@ template <int HALF, bool AFFINE>
 __global__ void __launch_bounds__(LanesCfg<HALF>::WARPS * 32, LanesCfg<HALF>::CTAS_SM)
 pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const PagkPairConst *__restrict__ pcs,
                      const float2 *__restrict__ keys_un, PagkOutPtrs out, PagkMode mode, int max_keys, int n_max,
-                     int n_pairs, int *__restrict__ work_counter, long long *__restrict__ prof) {
+                     int n_pairs, int *__restrict__ work_counter, int lane_cap, long long *__restrict__ prof) {
   using C = LanesCfg<HALF>;
   constexpr int P = C::P, NP = C::NP, WIN_W = C::WIN_W, WIN_H = C::WIN_H;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -238,7 +238,7 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
   while (true) {
     // ------------------------------------------------------------------ refill
     while (!exhausted) {
-      const bool want = feat < 0;
+      const bool want = feat < 0 && lane < lane_cap;
       const unsigned m = __ballot_sync(FULL, want);
       if (m == 0u) break;
       const int cnt = __popc(m);
@@ -628,10 +628,15 @@ static int launch_lanes(const unsigned char *images, const PagkGeom &g, const Pa
   }
   const long long total = (long long)n_max * n_pairs;
   long long ctas = (long long)n_sms * C::CTAS_SM;  // persistent: the SMs are filled once
-  const long long needed = (total + C::WARPS * 32 - 1) / (C::WARPS * 32);
-  if (ctas > needed) ctas = needed;
+  // A small batch is spread over all warps (lane_cap features per warp at a time) instead of filling a few: a warp
+  // with a handful of live lanes runs them through the cooperative pass, several times faster per iteration
+  // than a lockstep pass, which is what the latency of a single frame pair is made of.
+  const long long warps = ctas * C::WARPS;
+  int lane_cap = (int)((total + warps - 1) / warps);
+  if (lane_cap > 32) lane_cap = 32;
+  if (lane_cap < 1) lane_cap = 1;
   pagk_lk_lanes_kernel<HALF, AFFINE><<<(unsigned)ctas, C::WARPS * 32, smem, st>>>(images, g, pcs, keys_un, out, mode, max_keys,
-                                                                                  n_max, n_pairs, work_counter, prof);
+                                                                                  n_max, n_pairs, work_counter, lane_cap, prof);
   return (int)cudaGetLastError();
 }
 
