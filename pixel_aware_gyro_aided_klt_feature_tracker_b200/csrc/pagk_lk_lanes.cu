@@ -70,9 +70,12 @@ struct LanesCfg {
   static constexpr int WIN_WORDS = ((WIN_W * WIN_H + 3) / 4) | 1;
   static constexpr int WIN_BYTES = WIN_WORDS * 4;
   static constexpr int SLOT_BYTES = WIN_BYTES + NP * 4;
+  // slots per warp: all 32 lanes when eight warps' worth fits the SM; a 21 x 21 patch needs 2.6 KB per slot, and four
+  // warps (one per scheduler) of 20 slots then beat two warps of 32
+  static constexpr int SLOTS = HALF <= 5 ? 32 : 20;
   // per-warp scratch of the cooperative pass: NP records (Ix, Iy, -e) and the two constants c and 1
   static constexpr int SCRATCH_FLOATS = NP * 3 + 4;
-  static constexpr int WARP_BYTES = 32 * SLOT_BYTES + SCRATCH_FLOATS * 4;
+  static constexpr int WARP_BYTES = SLOTS * SLOT_BYTES + SCRATCH_FLOATS * 4;
   static constexpr int WARPS_SM = (227 * 1024) / WARP_BYTES < LANES_WARPS_SM ? (227 * 1024) / WARP_BYTES : LANES_WARPS_SM;
   static constexpr int WARPS = WARPS_SM < LANES_WARPS ? WARPS_SM : LANES_WARPS;
   static constexpr int CTAS_SM = WARPS_SM / WARPS;
@@ -190,11 +193,13 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
   constexpr int P = C::P, NP = C::NP, WIN_W = C::WIN_W, WIN_H = C::WIN_H;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned char *wwin = smem_raw + (size_t)warp * C::WARP_BYTES;               // [32][WIN_BYTES]
-  float *wT = reinterpret_cast<float *>(wwin + 32 * C::WIN_BYTES);             // [32][NP]
-  float *scratch = wT + 32 * NP;                                               // [NP][3] records, c, 1
-  const unsigned char *mywin = wwin + lane * C::WIN_BYTES;
-  const float *myT = wT + lane * NP;
+  unsigned char *wwin = smem_raw + (size_t)warp * C::WARP_BYTES;               // [SLOTS][WIN_BYTES]
+  float *wT = reinterpret_cast<float *>(wwin + C::SLOTS * C::WIN_BYTES);       // [SLOTS][NP]
+  float *scratch = wT + C::SLOTS * NP;                                         // [NP][3] records, c, 1
+  // lanes beyond SLOTS never own a feature; in the lockstep pass they read (harmlessly) the last slot's memory
+  const int myslot = lane < C::SLOTS ? lane : C::SLOTS - 1;
+  const unsigned char *mywin = wwin + myslot * C::WIN_BYTES;
+  const float *myT = wT + myslot * NP;
   const int total_work = n_pairs * n_max;
   const int top = mode.levels - 1;
   const unsigned long long slot_bytes = g.slot_bytes;
@@ -633,7 +638,7 @@ static int launch_lanes(const unsigned char *images, const PagkGeom &g, const Pa
   // than a lockstep pass, which is what the latency of a single frame pair is made of.
   const long long warps = ctas * C::WARPS;
   int lane_cap = (int)((total + warps - 1) / warps);
-  if (lane_cap > 32) lane_cap = 32;
+  if (lane_cap > C::SLOTS) lane_cap = C::SLOTS;
   if (lane_cap < 1) lane_cap = 1;
   pagk_lk_lanes_kernel<HALF, AFFINE><<<(unsigned)ctas, C::WARPS * 32, smem, st>>>(images, g, pcs, keys_un, out, mode, max_keys,
                                                                                   n_max, n_pairs, work_counter, lane_cap, prof);
