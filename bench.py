@@ -41,6 +41,27 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Everything any library prints on fd 1 (NCCL's version banner, ...) goes to stderr; the JSON line alone is
+    written to the real stdout by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -174,7 +195,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": v, "unit": "features/s", "cores": cores, "kind": "port",
                              "sample": f"{sample_pairs} frame pairs per step x {args.steps} steps, {cores} std::threads over features"},
             "e2e": {"value": v, "unit": "features/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_name(name, cfg, n_pairs):
@@ -195,6 +216,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity leg")
     args = ap.parse_args()
 
+    claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -370,7 +392,7 @@ def main():
                     "steps": e2e_steps, "results_ok": bool(e2e_ok),
                     "api": "pagk_submit_batch/pagk_wait_batch over 3 handles (pinned host buffers in and out)"},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity}
-    print(json.dumps(line), flush=True)
+    emit(line)
     for c in (ctxs + ectx)[::-1]:   # borrowers of a shared stream before its owner
         c.close()
     if world > 1:

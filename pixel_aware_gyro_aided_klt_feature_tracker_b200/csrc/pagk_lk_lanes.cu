@@ -85,12 +85,6 @@ struct LanesCfg {
 
 // floor(x) as float for 0 <= x < 2^22 without the conversion pipe: x + 2^23 rounds to an integer,
 // subtracting 2^23 back is exact, one compare fixes the round-up case.
-__device__ __forceinline__ float floor_nn(float x) {
-  const float t = x + 8388608.0f;
-  float r = t - 8388608.0f;
-  if (r > x) r -= 1.0f;
-  return r;
-}
 __device__ __forceinline__ float floor_nn(float x, int &i) {
   const float t = x + 8388608.0f;
   float r = t - 8388608.0f;
@@ -98,6 +92,11 @@ __device__ __forceinline__ float floor_nn(float x, int &i) {
   if (r > x) { r -= 1.0f; i -= 1; }
   return r;
 }
+#ifdef PAGK_LANES_CHECK
+#define CHECK_IDX0(i, lo, hi) do { if ((i) < (lo) || (i) > (hi)) __trap(); } while (0)
+#else
+#define CHECK_IDX0(i, lo, hi)
+#endif
 // exact u8 -> float on the ALU + FP32 pipes
 __device__ __forceinline__ float u8f(unsigned int b) { return __uint_as_float(0x4B000000u | b) - 8388608.0f; }
 
@@ -160,6 +159,7 @@ __device__ __forceinline__ float window_sample(const unsigned char *__restrict__
   int ix, iy;
   const float fx = floor_nn(x, ix), fy = floor_nn(y, iy);
   const float xx = x - fx, yy = y - fy, wa = 1.0f - xx, wb = 1.0f - yy;
+  CHECK_IDX0((iy - wy0) * WIN_W + (ix - wx0), 0, WIN_W * (WIN_W - 4) - WIN_W - 2);  // WIN_H = WIN_W - 4
   const unsigned char *q = win + (iy - wy0) * WIN_W + (ix - wx0);
   return wb * (wa * u8f(q[0]) + xx * u8f(q[1])) + yy * (wa * u8f(q[WIN_W]) + xx * u8f(q[WIN_W + 1]));
 }
@@ -175,6 +175,13 @@ __device__ __forceinline__ float window_sample(const unsigned char *__restrict__
 #define PROF(i)
 #define PROF_ADD(i, v)
 #define PROF_FLUSH()
+#endif
+
+// developer aid (-DPAGK_LANES_CHECK): trap on a window index outside the staged window (compute-sanitizer stand-in)
+#ifdef PAGK_LANES_CHECK
+#define CHECK_IDX(i, lo, hi) do { if ((i) < (lo) || (i) > (hi)) __trap(); } while (0)
+#else
+#define CHECK_IDX(i, lo, hi)
 #endif
 
 struct Sums {
@@ -357,7 +364,9 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
               const float cx = sptx + tpx[k], cy = spty + tpy[k];
               const float tx = __fadd_rd(cx, 8388608.0f), ty = __fadd_rd(cy, 8388608.0f);
               const float xx = cx - (tx - 8388608.0f), yy = cy - (ty - 8388608.0f), wa = 1.0f - xx, wb = 1.0f - yy;
-              const unsigned char *q = win + (int)((unsigned int)__float_as_int(ty) * (unsigned int)WIN_W + (unsigned int)__float_as_int(tx) - kt);
+              const int qidx = (int)((unsigned int)__float_as_int(ty) * (unsigned int)WIN_W + (unsigned int)__float_as_int(tx) - kt);
+              CHECK_IDX(qidx, 0, WIN_W * (P + 2) - WIN_W - 2);
+              const unsigned char *q = win + qidx;
               T[p] = wb * (wa * u8f(q[0]) + xx * u8f(q[1])) + yy * (wa * u8f(q[WIN_W]) + xx * u8f(q[WIN_W + 1]));
             }
           }
@@ -450,7 +459,9 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
           const float xx1 = X1 - (fx + 1.0f), yy1 = Y1 - (fy + 1.0f);
           const float wa1 = 1.0f - xx1, wb1 = 1.0f - yy1;
           badv = fmaxf(badv, fmaxf(xx1, yy1));
-          const unsigned char *w = mywin + (int)((unsigned int)__float_as_int(ty) * (unsigned int)WIN_W + (unsigned int)__float_as_int(tx) - kk);
+          const int widx = (int)((unsigned int)__float_as_int(ty) * (unsigned int)WIN_W + (unsigned int)__float_as_int(tx) - kk);
+          CHECK_IDX(widx, WIN_W + 1, WIN_W * WIN_H - 2 * WIN_W - 2);
+          const unsigned char *w = mywin + widx;
           const float m0 = u8f(w[-WIN_W]), m1 = u8f(w[-WIN_W + 1]);
           const float c_1 = u8f(w[-1]), c0 = u8f(w[0]), c1 = u8f(w[1]), c2 = u8f(w[2]);
           const float d_1 = u8f(w[WIN_W - 1]), d0 = u8f(w[WIN_W]), d1 = u8f(w[WIN_W + 1]), d2 = u8f(w[WIN_W + 2]);
