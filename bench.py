@@ -35,6 +35,7 @@ HBM_BYTES_PER_FEATURE_ITER = 120.0
 # `ncu --set full` capture (profiles/r01_ncu_summary.md): 49.55 MB + 1.59 MB
 LK_DRAM_TRAFFIC_BYTES_PER_LAUNCH = {("B", 64): 51.14e6}
 N_ROTATE = 3  # resident batches per GPU; 3 x 61 MB of pyramids > 126 MB L2
+E2E_DEPTH = 5  # handles (streams) the end-to-end leg rotates over: uploads, kernels and downloads of 5 batches in flight
 
 
 def log(*a):
@@ -295,34 +296,38 @@ def main():
     fi_per_s = all_iters / dt_max
 
     # ---- end-to-end leg: pinned host buffers in, pinned host buffers out, through the public C-ABI -------
-    # pagk_submit_batch / pagk_wait_batch on three handles with their own streams: the upload of batch k+1
-    # overlaps the kernels of batch k.  Every step copies its images, keypoints and gyro data host->device
+    # pagk_submit_batch / pagk_wait_batch on E2E_DEPTH handles with their own streams: the uploads of the next
+    # batches overlap the kernels of the current one.  Every step copies its images, keypoints and gyro data host->device
     # and its result vectors device->host inside the timed region.
     e2e_steps = args.e2e_steps or max(3, min(args.steps, 30))
-    ectx = [new_ctx() for _ in range(N_ROTATE)]
-    oblocks = [OutBlock(n_pairs, N) for _ in range(N_ROTATE)]
-    ins = [capi.make_in_array(b["pairs"]) for b in batches]
+    ectx = [new_ctx() for _ in range(E2E_DEPTH)]
+    oblocks = [OutBlock(n_pairs, N) for _ in range(E2E_DEPTH)]
+    ins = [capi.make_in_array(batches[j % N_ROTATE]["pairs"]) for j in range(E2E_DEPTH)]
     oarrs = [capi.make_out_array(ob.outs) for ob in oblocks]
 
     def e2e_loop(steps):
-        inflight = [False] * N_ROTATE
+        inflight = [False] * E2E_DEPTH
         for k in range(steps):
-            j = k % N_ROTATE
+            j = k % E2E_DEPTH
             if inflight[j]:
                 ectx[j].wait()
             ectx[j].submit_prepared(prm, ins[j], oarrs[j], n_pairs)
             inflight[j] = True
-        for j in range(N_ROTATE):
+        for j in range(E2E_DEPTH):
             if inflight[j]:
                 ectx[j].wait()
-    e2e_loop(3)
+    e2e_loop(E2E_DEPTH + 2)
     barrier()
     t0 = time.perf_counter()
     e2e_loop(e2e_steps)
     torch.cuda.synchronize()
     dte = sharding.reduce_time_max(time.perf_counter() - t0)
     e2e_value = world * e2e_steps * feats_per_step / dte
-    e2e_ok = int(oarrs[0][0].n_predict) > 0
+    # the end-to-end results of batch 0 must be the resident leg's results of the same batch, bit for bit
+    e2e_ok = int(oarrs[0][0].n_predict) > 0 and all(
+        np.array_equal(oblocks[0].outs[i].status, outs0.outs[i].status) and
+        np.array_equal(oblocks[0].outs[i].pt_predict_un.view(np.uint32), outs0.outs[i].pt_predict_un.view(np.uint32))
+        for i in range(n_pairs))
     b0 = batches[0]
     h2d = int(b0["imgs"].nbytes + b0["keys"].nbytes + n_pairs * 96)
     d2h = int(oblocks[0].nbytes + n_pairs * 24)
@@ -390,7 +395,7 @@ def main():
             "stage_ms": stage_ms, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "features/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "results_ok": bool(e2e_ok),
-                    "api": "pagk_submit_batch/pagk_wait_batch over 3 handles (pinned host buffers in and out)"},
+                    "api": f"pagk_submit_batch/pagk_wait_batch over {E2E_DEPTH} handles (pinned host buffers in and out)"},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity}
     emit(line)
     for c in (ctxs + ectx)[::-1]:   # borrowers of a shared stream before its owner

@@ -470,9 +470,15 @@ __global__ void __launch_bounds__(EPI_THREADS) pagk_epilogue_kernel(const PagkPa
     }
     __syncthreads();
     if (t == 0) {
+      // one thread, index order (the rounding sequence is the reference's).  Branch-free so that the loads run
+      // ahead of the dependent adds: a feature that is not ok contributes +0.0, which leaves a sum >= +0 unchanged
       const int m = min(EPI_CHUNK, N - c0);
-      for (int i = 0; i < m; ++i)
-        if (s_ok[i]) { sum += s_err[i]; ++cnt; }
+#pragma unroll 8
+      for (int i = 0; i < m; ++i) {
+        const bool ok = s_ok[i] != 0;
+        sum += ok ? s_err[i] : 0.0;
+        cnt += ok ? 1 : 0;
+      }
     }
   }
   if (t == 0) {
