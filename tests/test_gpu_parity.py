@@ -82,6 +82,58 @@ def test_border_features_bit_exact(gpu_ctx, oracle):
     helpers.assert_bit_exact(gpu, cpu)
 
 
+def _check(gpu_ctx, oracle, pairs, prm, threads=4):
+    gpu = gpu_ctx.track_batch(pairs, prm)
+    rc, cpu = oracle.track_batch(pairs, prm, threads)
+    assert rc == 0
+    for g, c in zip(gpu, cpu):
+        helpers.assert_north_star(g, c)
+        helpers.assert_bit_exact(g, c)
+    return gpu, cpu
+
+
+def test_flat_and_saturated_regions(gpu_ctx, oracle):
+    """constant patches: the normal matrix is exactly singular, the LLT stops at pivot 0 and the update is NaN
+    (reference src/patch_match.cpp:319-326) -> status 0, on both sides, feature for feature"""
+    pairs = [synth.make_pair(7700 + i, width=320, height=240, n_keys=300, pyramids=3, border=12) for i in range(2)]
+    for p in pairs:
+        for img in (p.img_ref, p.img_cur):
+            img[:, :110] = 128
+            img[:80, 200:] = 255
+            img[170:, 200:] = 0
+    gpu, cpu = _check(gpu_ctx, oracle, pairs, capi.default_params(pyramids=3))
+    assert any((c.pm_status == 0).any() for c in cpu) and any((c.pm_status == 1).any() for c in cpu)
+
+
+@pytest.mark.parametrize("shape,levels", [((243, 331), 3), ((201, 177), 2), ((480, 640), 5)])
+def test_odd_sizes_and_deep_pyramids(gpu_ctx, oracle, shape, levels):
+    """odd level sizes go through OpenCV's fixed-point bilinear resize and the byte-wise window staging; five
+    levels on 640 x 480 put the coarsest patches against the image border"""
+    h, w = shape
+    pairs = [synth.make_pair(7800 + i, width=w, height=h, n_keys=250, pyramids=levels, border=14) for i in range(2)]
+    _check(gpu_ctx, oracle, pairs, capi.default_params(pyramids=levels))
+
+
+def test_large_rotation_boxes_that_do_not_fit_the_window(gpu_ctx, oracle):
+    """0.3 rad between the frames: strongly sheared patches whose sample box exceeds the staged window are sampled
+    straight from the level by the cooperative pass; predictions that leave the image keep status 0"""
+    pairs = [synth.make_pair(7900 + i, width=400, height=300, n_keys=300, pyramids=3, border=40, sigma_w=6.0) for i in range(3)]
+    _check(gpu_ctx, oracle, pairs, capi.default_params(pyramids=3))
+
+
+@pytest.mark.parametrize("levels,iterations", [(1, 1), (1, 10), (3, 1), (2, 30)])
+def test_level_and_iteration_limits(gpu_ctx, oracle, levels, iterations):
+    pairs = [synth.make_pair(8000, width=320, height=240, n_keys=200, pyramids=max(levels, 2), border=20)]
+    _check(gpu_ctx, oracle, pairs, capi.default_params(pyramids=levels, iterations=iterations))
+
+
+@pytest.mark.parametrize("n_pairs,n_keys", [(8, 20), (1, 1), (3, 700), (8, 1500)])
+def test_batch_shapes_around_the_lane_cap(gpu_ctx, oracle, n_pairs, n_keys):
+    """few features spread one per warp (cooperative pass only), many features fill every lane (lockstep pass)"""
+    pairs = [synth.make_pair(8100 + i, width=320, height=240, n_keys=n_keys, pyramids=3, border=16) for i in range(n_pairs)]
+    _check(gpu_ctx, oracle, pairs, capi.default_params(pyramids=3), threads=8)
+
+
 def test_frozen_golden_cases_on_gpu(gpu_ctx):
     """the committed golden fixtures (oracle outputs frozen in tests/golden/lk_frozen.npz) against the CUDA path"""
     import os
