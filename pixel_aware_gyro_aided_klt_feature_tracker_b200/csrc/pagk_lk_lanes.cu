@@ -50,11 +50,11 @@ constexpr int LANES_WARPS = PAGK_LANES_WARPS;
 #ifndef PAGK_LANES_SPARSE
 #define PAGK_LANES_SPARSE 5
 #endif
-// pixels of a patch row unrolled in the pass loop.  The whole row (11) gives the scheduler the most to overlap but
-// is a 25 KB loop body, and with the warps of an SM in different phases the instruction cache then misses
-// (ncu: stalled_no_instruction 1.5 per issue, icc hit rate 72 %).
+// pixels unrolled in the pass loop.  A whole patch row (11) gives the scheduler the most to overlap but is a 25 KB
+// loop body, and with the warps of an SM in different phases the instruction cache then misses (ncu:
+// stalled_no_instruction 1.5 per issue, icc hit rate 72 %); 2 to 3 pixels measure best.
 #ifndef PAGK_LANES_UNROLL
-#define PAGK_LANES_UNROLL 2
+#define PAGK_LANES_UNROLL 3
 #endif
 #define PAGK_PRAGMA_(x) _Pragma(#x)
 #define PAGK_UNROLL(n) PAGK_PRAGMA_(unroll n)
@@ -439,16 +439,20 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
       // window element index from the mantissas of ty = 2^23 + floor(sy) and tx = 2^23 + floor(sx):
       // bits(ty) * WIN_W + bits(tx) - kk, with kk = (WIN_W + 1) * bits(2^23) + origin (mod 2^32)
       const unsigned int kk = (unsigned int)(WIN_W + 1) * 0x4B000000u + (unsigned int)(fast ? win_y0 * WIN_W + win_x0 : 0);
-#pragma unroll 1
-      for (int yi = 0; yi < P; ++yi) {
-        const float yf = (float)(yi - HALF);
-        const float r01 = q01 * yf, r11 = q11 * yf;
-        const float *Trow = myT + yi * P;
-        PAGK_UNROLL(PAGK_LANES_UNROLL)
-        for (int xi = 0; xi < P; ++xi) {
-          const float xf = (float)(xi - HALF);
+      // one flat loop over the P * P pixels (row-major, the reference's order): a single peeled pixel per pass
+      // instead of one per row, and the scheduler always has PAGK_LANES_UNROLL pixels to interleave
+      float xf = -(float)HALF, yf = -(float)HALF;
+      PAGK_UNROLL(PAGK_LANES_UNROLL)
+      for (int p = 0; p < NP; ++p) {
+        {
           float wx = xf, wy = yf;
-          if (AFFINE) { wx = q00 * xf + r01; wy = q10 * xf + r11; }
+          if (AFFINE) { wx = q00 * xf + q01 * yf; wy = q10 * xf + q11 * yf; }
+          {
+            const bool wrap = xf >= (float)HALF;  // next pixel: x + 1, or the start of the next row
+            const float nxf = xf + 1.0f;
+            yf = wrap ? yf + 1.0f : yf;
+            xf = wrap ? -(float)HALF : nxf;
+          }
           const float sx = pbx + wx, sy = pby + wy;
           // floor for 0 <= x < 2^22: x + 2^23 rounded DOWN is 2^23 + floor(x) exactly; taking 2^23 off is exact
           const float tx = __fadd_rd(sx, 8388608.0f), ty = __fadd_rd(sy, 8388608.0f);
@@ -473,7 +477,7 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
           const float v0 = wb * H0 + yy * H1;
           const float vx1 = wb * H0p + yy * H1p, vx2 = wb * H0m + yy * H1m;
           const float vy1 = wb1 * H1 + yy1 * H2, vy2 = wb * Hm + yy * H0;
-          const float e = (v0 + db) - gain * Trow[xi];
+          const float e = (v0 + db) - gain * myT[p];
           const float gxf = 0.5f * (vx1 - vx2), gyf = 0.5f * (vy1 - vy2), mf = -e;
           // J = (Ix, Iy, c, 1) as double; b += -J * e; H += J * J^T; cost += e * e (float), reference :264-299.
           // Each product of two float-valued doubles is exact, so DFMA rounds like the separate mul + add.
