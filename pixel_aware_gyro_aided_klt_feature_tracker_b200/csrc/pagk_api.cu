@@ -77,7 +77,8 @@ struct pagk_handle {
   size_t out_bytes = 0;
   float *d_ntab = nullptr;
   size_t ntab_stride = 0;  // floats per pair
-  int *d_work = nullptr;   // work counter of the persistent LK kernel
+  int *d_work = nullptr;   // work counters of the persistent LK kernels ([0]: slots kernel, [16..17]: lanes kernel)
+  int lk_parity = 0;       // which of the two lanes-kernel counters the next launch uses
   int n_sms = 0;
   long long *d_dbg = nullptr;  // PAGK_LK_TIMELINE=<file>: clock64 timeline of CTA 0 of the LK kernel (developer aid)
   const char *dbg_path = nullptr;
@@ -203,7 +204,8 @@ int launch_lk_kernel(pagk_handle *h, const PagkOutPtrs &o, const PagkMode &m, in
     // PAGK_LK_TIMELINE=<file> with a -DPAGK_LANES_PROF build: per-warp phase cycles (developer aid)
     if (h->d_dbg) cudaMemsetAsync(h->d_dbg, 0, 2048 * 8 * sizeof(long long), h->stream);
     const int rc = pagk_launch_lk_lanes(h->d_images, h->geom, h->d_pc, h->d_keys_un, o, m, h->cfg.max_keys, n_max, n_pairs,
-                                        h->d_work, h->n_sms, h->stream, &h->launches, h->d_dbg);
+                                        h->d_work + 16, h->lk_parity, h->n_sms, h->stream, &h->launches, h->d_dbg);
+    if (rc == 0 && n_max > 0 && n_pairs > 0) h->lk_parity ^= 1;
     if (h->d_dbg && rc == 0) {
       std::vector<long long> tl(2048 * 8);
       cudaMemcpyAsync(tl.data(), h->d_dbg, tl.size() * sizeof(long long), cudaMemcpyDeviceToHost, h->stream);
@@ -319,6 +321,7 @@ int pagk_create(const pagk_config *cfg, pagk_handle **out) {
   ok(cudaMalloc(&h->d_res, (size_t)cfg->max_pairs * sizeof(PagkPairResult)));
   ok(cudaMalloc(&h->d_out, h->out_bytes));
   ok(cudaMalloc(&h->d_work, 256));
+  if (e == cudaSuccess) ok(cudaMemset(h->d_work, 0, 256));
   ok(cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, cfg->device));
   {
     const char *k = getenv("PAGK_LK_KERNEL");

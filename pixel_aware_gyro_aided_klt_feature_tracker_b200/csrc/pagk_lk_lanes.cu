@@ -195,7 +195,8 @@ template <int HALF, bool AFFINE>
 __global__ void __launch_bounds__(LanesCfg<HALF>::WARPS * 32, LanesCfg<HALF>::CTAS_SM)
 pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const PagkPairConst *__restrict__ pcs,
                      const float2 *__restrict__ keys_un, PagkOutPtrs out, PagkMode mode, int max_keys, int n_max,
-                     int n_pairs, int *__restrict__ work_counter, int lane_cap, long long *__restrict__ prof) {
+                     int n_pairs, int *__restrict__ work_counter, int *__restrict__ next_counter, int lane_cap,
+                     long long *__restrict__ prof) {
   using C = LanesCfg<HALF>;
   constexpr int P = C::P, NP = C::NP, WIN_W = C::WIN_W, WIN_H = C::WIN_H;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -215,6 +216,8 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
   // level geometry, indexed by each lane's own level
   __shared__ int s_cols[PAGK_MAX_LEVELS], s_rows[PAGK_MAX_LEVELS];
   __shared__ unsigned int s_off[PAGK_MAX_LEVELS];
+  // the two work counters of a handle alternate between launches: this launch zeroes the one the next launch uses
+  if (blockIdx.x == 0 && threadIdx.x == 0) *next_counter = 0;
   if (threadIdx.x < PAGK_MAX_LEVELS) {
     s_cols[threadIdx.x] = g.lv[threadIdx.x].cols; s_rows[threadIdx.x] = g.lv[threadIdx.x].rows; s_off[threadIdx.x] = g.lv[threadIdx.x].offset;
   }
@@ -348,7 +351,6 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
         // both windows' loads in flight together: one global round trip per level instead of two
         if (tin) load_template<P + 2>(v1, img1, scols, x0, y0, lane);
         if (rs) load_window<WIN_W, WIN_H>(v2, img1 + slot_bytes, scols, srows, rx0, ry0, lane);
-        float c;
         if (tin) {
           // no clamp fires anywhere in the template: sample from a staged window of the reference level
           // (taps reach floor(hi) + 1 <= x0 + P + 1: inside the window)
@@ -370,25 +372,18 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
               T[p] = wb * (wa * u8f(q[0]) + xx * u8f(q[1])) + yy * (wa * u8f(q[WIN_W]) + xx * u8f(q[WIN_W + 1]));
             }
           }
-          {
-            int ix, iy;
-            const float fx = floor_nn(sptx, ix), fy = floor_nn(spty, iy);
-            const float xx = sptx - fx, yy = spty - fy, wa = 1.0f - xx, wb = 1.0f - yy;
-            const unsigned char *q = win + (iy - y0) * WIN_W + (ix - x0);
-            c = -(wb * (wa * u8f(q[0]) + xx * u8f(q[1])) + yy * (wa * u8f(q[WIN_W]) + xx * u8f(q[WIN_W + 1])));
-          }
         } else {
 #pragma unroll 1
           for (int p = lane; p < NP; p += 32) {
             const int py = p / P, px = p - py * P;
             T[p] = pagk_sample_call(img1, scols, srows, sptx + (float)(px - HALF), spty + (float)(py - HALF));
           }
-          c = -pagk_sample_call(img1, scols, srows, sptx, spty);
         }
         __syncwarp();
         if (rs) store_window<WIN_W, WIN_H>(win, v2, lane);
         if (lane == s) {
-          cval = c; needs_setup = false; win_valid = false;
+          // de_dg = -I1(pt) (src/patch_match.cpp:263) is minus the template value of the centre pixel: pt + (0, 0)
+          cval = -T[NP / 2]; needs_setup = false; win_valid = false;
           if (rs) { win_x0 = nx0; win_y0 = ny0; win_valid = true; restage = false; }
         }
         __syncwarp();
@@ -637,7 +632,7 @@ bool pagk_lk_lanes_supported(const PagkMode &mode) {
 template <int HALF, bool AFFINE>
 static int launch_lanes(const unsigned char *images, const PagkGeom &g, const PagkPairConst *pcs, const float2 *keys_un,
                         const PagkOutPtrs &out, const PagkMode &mode, int max_keys, int n_max, int n_pairs,
-                        int *work_counter, int n_sms, cudaStream_t st, long long *prof) {
+                        int *work_counter, int *next_counter, int n_sms, cudaStream_t st, long long *prof) {
   using C = LanesCfg<HALF>;
   const size_t smem = (size_t)C::WARPS * C::WARP_BYTES;
   static bool configured = false;
@@ -656,23 +651,23 @@ static int launch_lanes(const unsigned char *images, const PagkGeom &g, const Pa
   if (lane_cap > C::SLOTS) lane_cap = C::SLOTS;
   if (lane_cap < 1) lane_cap = 1;
   pagk_lk_lanes_kernel<HALF, AFFINE><<<(unsigned)ctas, C::WARPS * 32, smem, st>>>(images, g, pcs, keys_un, out, mode, max_keys,
-                                                                                  n_max, n_pairs, work_counter, lane_cap, prof);
+                                                                                  n_max, n_pairs, work_counter, next_counter, lane_cap, prof);
   return (int)cudaGetLastError();
 }
 
 int pagk_launch_lk_lanes(const unsigned char *images, const PagkGeom &g, const PagkPairConst *pcs, const float2 *keys_un,
                          const PagkOutPtrs &out, const PagkMode &mode, int max_keys, int n_max, int n_pairs,
-                         int *work_counter, int n_sms, cudaStream_t st, long long *launches, long long *prof) {
+                         int *work_counters, int parity, int n_sms, cudaStream_t st, long long *launches, long long *prof) {
   if (n_max <= 0 || n_pairs <= 0) return 0;
-  cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), st);
-  if (e != cudaSuccess) return (int)e;
+  // work_counters[0..1]: both zero when the handle is created; launch n uses [n & 1] and zeroes the other one
+  int *work_counter = work_counters + (parity & 1), *next_counter = work_counters + ((parity + 1) & 1);
   int rc;
   if (mode.half == 5) {
-    rc = mode.affine ? launch_lanes<5, true>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, n_sms, st, prof)
-                     : launch_lanes<5, false>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, n_sms, st, prof);
+    rc = mode.affine ? launch_lanes<5, true>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, next_counter, n_sms, st, prof)
+                     : launch_lanes<5, false>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, next_counter, n_sms, st, prof);
   } else {
-    rc = mode.affine ? launch_lanes<10, true>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, n_sms, st, prof)
-                     : launch_lanes<10, false>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, n_sms, st, prof);
+    rc = mode.affine ? launch_lanes<10, true>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, next_counter, n_sms, st, prof)
+                     : launch_lanes<10, false>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, next_counter, n_sms, st, prof);
   }
   ++*launches;
   return rc;
