@@ -58,10 +58,12 @@ def test_track_config_B_pair(gpu_ctx, oracle):
         helpers.assert_bit_exact(g, c)
 
 
-def test_generic_kernel_still_bit_exact(cuda_lib, oracle, monkeypatch):
-    """the any-patch-size kernel (PAGK_LK_KERNEL=generic) stays a second implementation to compare against"""
+@pytest.mark.parametrize("kernel", ["generic", "slots"])
+def test_other_lk_kernels_still_bit_exact(cuda_lib, oracle, monkeypatch, kernel):
+    """the any-patch-size kernel and the previous pipelined kernel (PAGK_LK_KERNEL=generic|slots) stay second and
+    third implementations of the same arithmetic to compare the production kernel against"""
     from pixel_aware_gyro_aided_klt_feature_tracker_b200 import tracker
-    monkeypatch.setenv("PAGK_LK_KERNEL", "generic")
+    monkeypatch.setenv("PAGK_LK_KERNEL", kernel)
     pairs = [synth.make_pair(7100 + i, width=320, height=240, n_keys=200, pyramids=3, border=20) for i in range(2)]
     prm = capi.default_params(pyramids=3)
     with tracker.Context(max_width=320, max_height=240, max_keys=200, max_pairs=2, max_levels=3) as ctx:
@@ -132,6 +134,13 @@ def test_batch_shapes_around_the_lane_cap(gpu_ctx, oracle, n_pairs, n_keys):
     """few features spread one per warp (cooperative pass only), many features fill every lane (lockstep pass)"""
     pairs = [synth.make_pair(8100 + i, width=320, height=240, n_keys=n_keys, pyramids=3, border=16) for i in range(n_pairs)]
     _check(gpu_ctx, oracle, pairs, capi.default_params(pyramids=3), threads=8)
+
+
+@pytest.mark.parametrize("half", [3, 7])
+def test_patch_sizes_served_by_the_generic_kernel(gpu_ctx, oracle, half):
+    """7 x 7 and 15 x 15 patches: no lane-kernel instantiation, the any-size kernel runs"""
+    pairs = [synth.make_pair(8200 + half, width=320, height=240, n_keys=150, pyramids=3, border=24, half_patch=half)]
+    _check(gpu_ctx, oracle, pairs, capi.default_params(pyramids=3, half_patch=half))
 
 
 def test_frozen_golden_cases_on_gpu(gpu_ctx):
