@@ -15,16 +15,24 @@
 //   src/patch_match.cpp:370-416,433-469 SetMatcher, GetPixelValue, DistortPoints, NCC
 //   src/utils.cpp:49-76                 DistortVecPoints
 //
-// The reference itself cannot be compiled in this image: it needs OpenCV (>= 3.4), Eigen3 and glog,
-// none of which are installed and there is no network.  Their arithmetic is restated here:
-//   * cv::resize INTER_LINEAR u8        -> resize_half()      PINNED bit-exact against cv2 4.13 fixtures
+// The reference cannot be built as shipped in this image: it needs OpenCV (>= 3.4), Eigen3 and glog, none of which
+// are installed, and there is no network.  Two things stand in for it:
+//   (1) this file, a restatement that travels to the GPU box in source form;
+//   (2) oracle/_ref/libpagk_ref.so (oracle/reference.py, oracle/ref_harness.cpp): the reference's OWN
+//       src/gyro_aided_tracker.cpp, src/patch_match.cpp and src/utils.cpp compiled unmodified, where they lie,
+//       against stand-in OpenCV / Eigen3 / glog headers (oracle/ref_shim/).  tests/test_reference_build.py holds this
+//       file bit-for-bit equal to it on every output (all eTypes, 1-5 levels, 7x7..21x21 patches, distortion,
+//       normalize table, border features, flat regions, empty inputs), and tests/golden/lk_frozen.npz freezes its
+//       outputs.  So the Gauss-Newton loop, the prediction, the filter and every implicit float/double promotion of
+//       the reference's C++ are PINNED against the reference's own code.
+// Third-party arithmetic, restated in both (1) and (2):
+//   * cv::resize INTER_LINEAR u8        -> pagk_cv_resize.h   PINNED bit-exact against cv2 4.13 fixtures
 //   * cv::Mat gemm / invert / scaleAdd  -> small_*()          PINNED bit-exact against cv2 4.13 fixtures
-//   * Eigen::Matrix4d::llt().solve()    -> llt_solve4()       PARITY UNPINNED: Eigen 3.3.4 (Ubuntu 18.04,
+//     (the stand-in cv::MatExpr of (2) is pinned against the same fixtures through the reference's own expressions)
+//   * Eigen::Matrix4d::llt().solve(), Vector4d::norm() -> llt_solve4()   PARITY UNPINNED: Eigen 3.3.4 (Ubuntu 18.04,
 //                                          README.md:21) restated from its published algorithm
 //                                          (llt_inplace<double,Lower>::unblocked, fixed-size triangular
 //                                          solver unrollers, SSE2 redux order).  No Eigen here to check.
-//   * the Gauss-Newton loop itself                            PARITY UNPINNED: the reference ships no tests,
-//                                          golden vectors or fixtures for it.
 //
 // Build: g++ -O2 -ffp-contract=off -fno-fast-math (x86-64 baseline: SSE2, no FMA), which is the
 // arithmetic of the reference's own -O3 build (CMakeLists.txt:10-11: no -march, no -ffast-math).
@@ -37,6 +45,7 @@
 // guard row).  Column overflow therefore wraps into the next row exactly as in a continuous cv::Mat.
 
 #include "../include/pagk.h"
+#include "pagk_cv_resize.h"
 
 #include <cmath>
 #include <cstdint>
@@ -74,48 +83,7 @@ void level_from_image(const uint8_t *img, int cols, int rows, int pitch, Level &
   finish_guard(L);
 }
 
-void resize_half(const uint8_t *src, int scols, int srows, int sstep, uint8_t *dst, int dcols, int drows) {
-  if (scols == 2 * dcols && srows == 2 * drows) {
-    for (int y = 0; y < drows; ++y) {
-      const uint8_t *r0 = src + (size_t)(2 * y) * sstep, *r1 = r0 + sstep;
-      uint8_t *d = dst + (size_t)y * dcols;
-      for (int x = 0; x < dcols; ++x)
-        d[x] = (uint8_t)((r0[2 * x] + r0[2 * x + 1] + r1[2 * x] + r1[2 * x + 1] + 2) >> 2);
-    }
-    return;
-  }
-  const double sx = (double)scols / dcols, sy = (double)srows / drows;
-  std::vector<int> xofs(dcols), a0(dcols), a1(dcols);
-  for (int dx = 0; dx < dcols; ++dx) {
-    float fx = (float)((dx + 0.5) * sx - 0.5);
-    int ix = (int)std::floor(fx);
-    fx -= ix;
-    if (ix < 0) { ix = 0; fx = 0.f; }
-    if (ix >= scols - 1) { ix = scols - 1; fx = 0.f; }
-    xofs[dx] = ix;
-    a0[dx] = (int)(short)std::lrint((1.f - fx) * 2048.f);
-    a1[dx] = (int)(short)std::lrint(fx * 2048.f);
-  }
-  std::vector<int> t0(dcols), t1(dcols);
-  for (int dy = 0; dy < drows; ++dy) {
-    float fy = (float)((dy + 0.5) * sy - 0.5);
-    int iy = (int)std::floor(fy);
-    fy -= iy;
-    const int y0 = std::min(std::max(iy, 0), srows - 1), y1 = std::min(std::max(iy + 1, 0), srows - 1);
-    const int b0 = (int)(short)std::lrint((1.f - fy) * 2048.f), b1 = (int)(short)std::lrint(fy * 2048.f);
-    const uint8_t *r0 = src + (size_t)y0 * sstep, *r1 = src + (size_t)y1 * sstep;
-    for (int dx = 0; dx < dcols; ++dx) {
-      const int ix = xofs[dx], ix1 = std::min(ix + 1, scols - 1);
-      t0[dx] = r0[ix] * a0[dx] + r0[ix1] * a1[dx];
-      t1[dx] = r1[ix] * a0[dx] + r1[ix1] * a1[dx];
-    }
-    uint8_t *d = dst + (size_t)dy * dcols;
-    for (int dx = 0; dx < dcols; ++dx) {
-      const int v = (((b0 * (t0[dx] >> 4)) >> 16) + ((b1 * (t1[dx] >> 4)) >> 16) + 2) >> 2;
-      d[dx] = (uint8_t)std::min(std::max(v, 0), 255);
-    }
-  }
-}
+using pagk_cv::resize_half;
 
 void build_pyramid(const uint8_t *img, int cols, int rows, int pitch, int levels, std::vector<Level> &pyr) {
   pyr.resize(levels);

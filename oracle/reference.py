@@ -1,0 +1,126 @@
+"""Build recipe and ctypes loader of oracle/_ref/libpagk_ref.so.  TEST INFRASTRUCTURE ONLY.
+
+libpagk_ref.so is the reference's OWN src/gyro_aided_tracker.cpp, src/patch_match.cpp and src/utils.cpp,
+compiled unmodified from /root/reference (where they lie; nothing is copied into this repository) against the
+stand-in OpenCV / Eigen3 / glog headers under oracle/ref_shim/ plus oracle/ref_harness.cpp.  What is real
+and what is restated is spelled out at the top of oracle/ref_shim/pagk_cv_shim.hpp.
+
+/root/reference exists only in the build container: `build()` compiles there; on the GPU box the prebuilt
+library travels with the snapshot (oracle/_ref/ is git-ignored, not gpurun-ignored) and `available()` says
+whether it is present.  Imported by tests/ and bench.py's CPU legs only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from pixel_aware_gyro_aided_klt_feature_tracker_b200 import capi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REFERENCE_ROOT = os.environ.get("PAGK_REFERENCE_ROOT", "/root/reference")
+OUT_DIR = os.path.join(_HERE, "_ref")
+LIB = os.path.join(OUT_DIR, "libpagk_ref.so")
+REF_SOURCES = ["src/gyro_aided_tracker.cpp", "src/patch_match.cpp", "src/utils.cpp"]
+# the reference's own flags (CMakeLists.txt:10-11, 17-20: -O3 -std=c++11, no -march, no -ffast-math)
+CXXFLAGS = ["-O3", "-std=c++11", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-pthread", "-w"]
+_f32p = C.POINTER(C.c_float)
+_f64p = C.POINTER(C.c_double)
+
+
+def sources_present() -> bool:
+    return all(os.path.exists(os.path.join(REFERENCE_ROOT, s)) for s in REF_SOURCES)
+
+
+def available() -> bool:
+    return os.path.exists(LIB)
+
+
+def _deps():
+    shim = os.path.join(_HERE, "ref_shim")
+    own = [os.path.join(_HERE, "ref_harness.cpp"), os.path.join(_HERE, "pagk_cv_resize.h"),
+           os.path.join(shim, "pagk_cv_shim.hpp"), os.path.join(shim, "pagk_eigen_shim.hpp"),
+           os.path.join(_HERE, "..", "include", "pagk.h")]
+    return own + [os.path.join(REFERENCE_ROOT, s) for s in REF_SOURCES]
+
+
+def build(force: bool = False) -> str | None:
+    """compile the reference sources where they lie; no-op (returns the prebuilt path or None) without them"""
+    if not sources_present():
+        return LIB if available() else None
+    if not force and available() and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in _deps()):
+        return LIB
+    os.makedirs(OUT_DIR, exist_ok=True)
+    shim = os.path.join(_HERE, "ref_shim")
+    cmd = ["g++"] + CXXFLAGS + ["-shared", "-I", shim, "-I", os.path.join(shim, "anchor"),
+                                "-I", os.path.join(REFERENCE_ROOT, "include"), "-I", _HERE, "-o", LIB,
+                                os.path.join(_HERE, "ref_harness.cpp")] + \
+          [os.path.join(REFERENCE_ROOT, s) for s in REF_SOURCES]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("reference build failed:\n" + r.stderr[-4000:])
+    return LIB
+
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not available():
+            build()
+        if not available():
+            raise RuntimeError("oracle/_ref/libpagk_ref.so is absent and /root/reference is not here to build it")
+        lib = C.CDLL(LIB)
+        lib.pagk_ref_track.argtypes = [C.POINTER(capi.PagkParams), C.POINTER(capi.PagkPairIn),
+                                       C.POINTER(capi.PagkPairOut), C.c_int]
+        lib.pagk_ref_track_batch.argtypes = [C.POINTER(capi.PagkParams), C.c_int, C.POINTER(capi.PagkPairIn),
+                                             C.POINTER(capi.PagkPairOut), C.c_int]
+        lib.pagk_ref_patch_match.argtypes = [C.POINTER(capi.PagkPatchMatchIn), C.POINTER(capi.PagkPairOut), C.c_int]
+        lib.pagk_ref_integrate_gyro.argtypes = [C.POINTER(capi.PagkPairIn), _f32p, _f32p]
+        lib.pagk_ref_inject_models.argtypes = [_f64p, _f64p]
+        lib.pagk_ref_inject_models.restype = None
+        _lib = lib
+    return _lib
+
+
+def last_path() -> int:
+    """0: the call went through GyroAidedTracker::TrackFeatures() itself; 1: composed from the public pieces"""
+    return int(load().pagk_ref_last_path())
+
+
+def integrate_gyro(pair: capi.PairInputs):
+    s = pair.as_struct()
+    R = np.zeros(9, np.float32)
+    M = np.zeros(9, np.float32)
+    load().pagk_ref_integrate_gyro(C.byref(s), R.ctypes.data_as(_f32p), M.ctypes.data_as(_f32p))
+    return R.reshape(3, 3), M.reshape(3, 3)
+
+
+def patch_match(pm_struct, n_keys: int, n_threads: int = 1):
+    out = capi.PairOutputs(n_keys)
+    rc = load().pagk_ref_patch_match(C.byref(pm_struct), C.byref(out.struct), n_threads)
+    return rc, out
+
+
+def track(pair: capi.PairInputs, params: capi.PagkParams, n_threads: int = 1):
+    s = pair.as_struct()
+    out = capi.PairOutputs(pair.n_keys)
+    rc = load().pagk_ref_track(C.byref(params), C.byref(s), C.byref(out.struct), n_threads)
+    return rc, out
+
+
+def track_batch(pairs, params: capi.PagkParams, n_threads: int = 1, outs=None):
+    ins = capi.make_in_array(pairs)
+    outs = outs or [capi.PairOutputs(p.n_keys) for p in pairs]
+    oarr = capi.make_out_array(outs)
+    rc = load().pagk_ref_track_batch(C.byref(params), len(pairs), ins, oarr, n_threads)
+    capi.sync_out_array(oarr, outs)
+    return rc, outs
+
+
+if __name__ == "__main__":
+    print(build(force=True))

@@ -5,9 +5,11 @@ What is pinned against what (the reference ships no tests 
   matexpr.npz   cv2.gemm / cv2.invert / cv2.scaleAdd / cv2.add chains that OpenCV's cv::MatExpr lowers
                 IntegrateGyroMeasurements, SetRcl and the affine-matrix expression to
                 (src/gyro_aided_tracker.cpp:166-167, 511-587)       -> pins oracle small_*() and integrate_gyro()
-  lk_frozen.npz outputs of the oracle itself on small seeded pairs, frozen so that any later edit of the
-                oracle's Gauss-Newton loop or LLT restatement is visible.  NOT a pin against the reference
-                (Eigen is not available): "parity unpinned" for that part.
+  lk_frozen.npz outputs of the reference build (oracle/_ref/libpagk_ref.so = the reference's own three sources
+                compiled against stand-in OpenCV/Eigen/glog headers, oracle/reference.py) on small seeded pairs
+                -> pins the restatement's Gauss-Newton loop, prediction, filter and control flow against the
+                reference's own code.  Eigen's LLT/norm arithmetic inside it is still a restatement (Eigen is not
+                available): "parity unpinned" for that one piece.
 """
 import ctypes
 import hashlib
@@ -130,26 +132,52 @@ def make_matexpr():
 
 
 def make_lk_frozen():
+    """outputs of the REFERENCE BUILD (oracle/_ref/libpagk_ref.so: the reference's own sources compiled against the
+    stand-in headers, oracle/reference.py) on small seeded pairs; the restatement must agree bit for bit before the
+    fixture is written.  `iters` (per-feature pass counts) is not observable from the reference and comes from the
+    restatement; its sum is checked against the reference build's count of H.llt() calls."""
+    from oracle import reference
+    from tests import helpers
+    reference.build(force=True)
     out = {}
     cases = [dict(seed=9001, e_type=4, dist=None), dict(seed=9002, e_type=3, dist=None),
              dict(seed=9003, e_type=4, dist=synth.EUROC_DIST), dict(seed=9004, e_type=2, dist=None),
-             dict(seed=9005, e_type=5, dist=None), dict(seed=9006, e_type=6, dist=None)]
+             dict(seed=9005, e_type=5, dist=None), dict(seed=9006, e_type=6, dist=None),
+             # TrackFeatures() hard-codes 3 levels / 10 iterations; these go through the composed path
+             dict(seed=9007, e_type=4, dist=None, pyramids=4), dict(seed=9008, e_type=4, dist=None, half_patch=10, pyramids=2),
+             dict(seed=9009, e_type=4, dist=None, border=0, sigma_w=3.0), dict(seed=9010, e_type=4, dist=None, flat=True)]
     out["n"] = np.array(len(cases))
     for i, c in enumerate(cases):
-        p = synth.make_pair(c["seed"], width=160, height=120, n_keys=48, pyramids=3, border=12, margin=32,
-                            K=synth.scaled_euroc_K(160), dist=c["dist"], sigma_w=0.8)
-        prm = capi.default_params(e_type=c["e_type"], pyramids=3)
-        rc, o = oracle.track(p, prm, 1)
+        pyr, half = c.get("pyramids", 3), c.get("half_patch", 5)
+        p = synth.make_pair(c["seed"], width=160, height=120, n_keys=48, pyramids=pyr, half_patch=half,
+                            border=c.get("border", 12 if half == 5 else 24), margin=32,
+                            K=synth.scaled_euroc_K(160), dist=c["dist"], sigma_w=c.get("sigma_w", 0.8))
+        if c.get("flat"):   # saturated / constant regions: singular normal matrix, NaN update, status 0
+            p.img_ref[:, :80] = 255
+            p.img_cur[:, :80] = 255
+            p.img_ref[60:, 80:] = 0
+            p.img_cur[60:, 80:] = 0
+        prm = capi.default_params(e_type=c["e_type"], pyramids=pyr, half_patch=half)
+        rc, o = reference.track(p, prm, 1)
         assert rc == 0
+        rc2, o2 = oracle.track(p, prm, 1)
+        assert rc2 == 0
+        rep = helpers.compare(o, o2)
+        bad = {k: v for k, v in rep.items() if isinstance(v, dict) and v.get("bit_mismatch", 0) and k != "iters"}
+        assert not bad and o.n_predict == o2.n_predict and o.n_iterations == o2.n_iterations, (i, bad)
+        assert rep["Rcl_bits"] == 0 and rep["KRKinv_bits"] == 0
         for k, v in dict(img_ref=p.img_ref, img_cur=p.img_cur, keys=p.keys_ref_un, imu_t=p.imu_t, imu_w=p.imu_w,
                          t_ref=np.array(p.t_ref), t_cur=np.array(p.t_cur), K=p.K, Rbc=p.Rbc, dist=p.dist,
-                         n_dist=np.array(p.n_dist), e_type=np.array(c["e_type"])).items():
+                         n_dist=np.array(p.n_dist), e_type=np.array(c["e_type"]), pyramids=np.array(pyr),
+                         half_patch=np.array(half)).items():
             out[f"c{i}_in_{k}"] = np.asarray(v)
         for k, v in o.arrays().items():
-            out[f"c{i}_out_{k}"] = v
+            out[f"c{i}_out_{k}"] = v if k != "iters" else o2.iters
         out[f"c{i}_out_Rcl"] = o.Rcl; out[f"c{i}_out_KRKinv"] = o.KRKinv
         out[f"c{i}_out_n_predict"] = np.array(o.n_predict); out[f"c{i}_out_n_iterations"] = np.array(o.n_iterations)
-        print("case", i, "eType", c["e_type"], "n_predict", o.n_predict, "iters", o.n_iterations)
+        out[f"c{i}_ref_path"] = np.array(reference.last_path())
+        print("case", i, "eType", c["e_type"], "n_predict", o.n_predict, "iters", o.n_iterations, "path", reference.last_path(),
+              "status0", int((o.status == 0).sum()), "nan", int(np.isnan(o.pixel_error).sum()))
     np.savez_compressed(os.path.join(HERE, "lk_frozen.npz"), **out)
 
 

@@ -144,7 +144,7 @@ def test_patch_sizes_served_by_the_generic_kernel(gpu_ctx, oracle, half):
 
 
 def test_frozen_golden_cases_on_gpu(gpu_ctx):
-    """the committed golden fixtures (oracle outputs frozen in tests/golden/lk_frozen.npz) against the CUDA path"""
+    """the committed golden fixtures (outputs of the reference build, tests/golden/lk_frozen.npz) against the CUDA path"""
     import os
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lk_frozen.npz"))
     for i in range(int(g["n"])):
@@ -152,7 +152,8 @@ def test_frozen_golden_cases_on_gpu(gpu_ctx):
         p = capi.PairInputs(g[f"c{i}_in_img_ref"], g[f"c{i}_in_img_cur"], g[f"c{i}_in_keys"], g[f"c{i}_in_imu_t"],
                             g[f"c{i}_in_imu_w"], float(g[f"c{i}_in_t_ref"]), float(g[f"c{i}_in_t_cur"]), g[f"c{i}_in_K"],
                             g[f"c{i}_in_Rbc"], dist=g[f"c{i}_in_dist"], n_dist=int(g[f"c{i}_in_n_dist"]))
-        o = gpu_ctx.track_batch([p], capi.default_params(e_type=e_type, pyramids=3))[0]
+        o = gpu_ctx.track_batch([p], capi.default_params(e_type=e_type, pyramids=int(g[f"c{i}_in_pyramids"]),
+                                                         half_patch=int(g[f"c{i}_in_half_patch"])))[0]
         for name, arr in o.arrays().items():
             ref = g[f"c{i}_out_{name}"]
             if e_type == 6 and arr.dtype.kind == "f":   # device log() vs glibc log(): last-bit differences allowed
@@ -163,6 +164,28 @@ def test_frozen_golden_cases_on_gpu(gpu_ctx):
             assert o.n_predict == int(g[f"c{i}_out_n_predict"]) and o.n_iterations == int(g[f"c{i}_out_n_iterations"])
         else:   # north-star tolerance for the mode with a transcendental in the loop
             assert (o.status == g[f"c{i}_out_status"]).mean() >= 0.999 or (o.status != g[f"c{i}_out_status"]).sum() <= 1
+
+
+@pytest.mark.parametrize("e_type,levels", [(4, 3), (2, 3), (3, 3), (5, 3), (4, 4)])
+def test_against_the_reference_build(gpu_ctx, e_type, levels):
+    """the CUDA path against oracle/_ref/libpagk_ref.so (the reference's own sources compiled in the build container
+    against stand-in third-party headers; the prebuilt library travels with the snapshot).  With 3 levels the call is
+    GyroAidedTracker::TrackFeatures() itself."""
+    from oracle import reference
+    if not reference.available():
+        pytest.skip("oracle/_ref/libpagk_ref.so was not built (no /root/reference in the build container)")
+    pairs = [synth.make_pair(7700 + 10 * e_type + i, width=320, height=240, n_keys=200, pyramids=levels, border=20)
+             for i in range(2)]
+    prm = capi.default_params(e_type=e_type, pyramids=levels)
+    gpu = gpu_ctx.track_batch(pairs, prm)
+    rc, ref = reference.track_batch(pairs, prm, 4)
+    assert rc == 0 and reference.last_path() == (0 if levels == 3 else 1)
+    fields = set(helpers.FLOAT_FIELDS) | {"status", "pm_status"}   # per-feature pass counts are not observable there
+    for g, c in zip(gpu, ref):
+        helpers.assert_north_star(g, c)
+        helpers.assert_bit_exact(g, c, fields=fields)
+        assert g.n_predict == c.n_predict and g.n_iterations == c.n_iterations
+        assert helpers.bits_equal(g.Rcl, c.Rcl).all() and helpers.bits_equal(g.KRKinv, c.KRKinv).all()
 
 
 def test_regularized_mode_within_tolerance(gpu_ctx, oracle):

@@ -69,13 +69,16 @@ def _frozen_case(g, i):
     p = capi.PairInputs(g[f"c{i}_in_img_ref"], g[f"c{i}_in_img_cur"], g[f"c{i}_in_keys"], g[f"c{i}_in_imu_t"],
                         g[f"c{i}_in_imu_w"], float(g[f"c{i}_in_t_ref"]), float(g[f"c{i}_in_t_cur"]), g[f"c{i}_in_K"],
                         g[f"c{i}_in_Rbc"], dist=g[f"c{i}_in_dist"], n_dist=int(g[f"c{i}_in_n_dist"]))
-    prm = capi.default_params(e_type=int(g[f"c{i}_in_e_type"]), pyramids=3)
+    prm = capi.default_params(e_type=int(g[f"c{i}_in_e_type"]), pyramids=int(g[f"c{i}_in_pyramids"]),
+                              half_patch=int(g[f"c{i}_in_half_patch"]))
     return p, prm
 
 
-@pytest.mark.parametrize("case", range(6))
+@pytest.mark.parametrize("case", range(10))
 def test_lk_frozen_outputs(oracle, case):
-    """the oracle's full path is frozen: an edit of its Gauss-Newton loop / LLT restatement shows up here"""
+    """the restatement against outputs of the reference build (the reference's own sources compiled against stand-in
+    third-party headers, tests/golden/make_golden.py): eTypes 2-6, distortion, 2/3/4 levels, 21x21 patches, features at
+    the image border, flat and saturated regions"""
     g = np.load(os.path.join(G, "lk_frozen.npz"))
     p, prm = _frozen_case(g, case)
     rc, o = oracle.track(p, prm, 1)
