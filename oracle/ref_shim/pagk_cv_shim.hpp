@@ -13,7 +13,7 @@
 //     scaleAdd, add, transpose) follow the rules measured bit-for-bit against cv2 4.13
 //     (tests/golden/matexpr.npz): see small_gemm below;
 //   * cv::resize (u8, INTER_LINEAR): bit-exact against cv2 4.13 (tests/golden/pyramid.npz);
-//   * cv::parallel_for_: a static split over std::thread (PAGK_REF_THREADS, default 1);
+//   * cv::parallel_for_: a static split over std::thread at multiples of 64 indices (see parallel_for_ below);
 //   * findHomography / findFundamentalMat / calcOpticalFlowPyrLK / BFMatcher / undistortPoints /
 //     initUndistortRectifyMap: declared so the sources compile; defined in oracle/ref_harness.cpp
 //     (the two RANSAC estimators return a model injected by the test, the others abort: they are
@@ -504,13 +504,19 @@ typedef const _OutputArray &OutputArray;
 void resize(const Mat &src, Mat &dst, Size dsize, double fx = 0, double fy = 0, int interpolation = INTER_LINEAR);
 
 inline int &shim_num_threads() { static int n = 1; return n; }
+// Static split over std::thread.  Stripe boundaries sit at multiples of 64 indices: PatchMatch::mvSuccess is a
+// std::vector<bool> (include/patch_match.h:94) that the parallel body writes per feature (src/patch_match.cpp:351), so two
+// stripes sharing a 64-bit word is a data race in the reference (a lost status bit now and then); word-aligned stripes
+// keep the reference build deterministic.
 template <typename F> inline void parallel_for_(const Range &range, F body) {
-  const int n = range.end - range.start, nt = std::max(1, std::min(shim_num_threads(), n));
+  const int n = range.end - range.start;
+  const int blocks = (n + 63) / 64, nt = std::max(1, std::min(shim_num_threads(), blocks));
   if (nt <= 1) { body(range); return; }
   std::vector<std::thread> th;
   for (int t = 0; t < nt; ++t) {
-    const int a = range.start + (int)((long long)n * t / nt), b = range.start + (int)((long long)n * (t + 1) / nt);
-    th.emplace_back([=, &body]() { body(Range(a, b)); });
+    const int a = range.start + std::min(n, 64 * (int)((long long)blocks * t / nt));
+    const int b = range.start + std::min(n, 64 * (int)((long long)blocks * (t + 1) / nt));
+    if (a < b) th.emplace_back([=, &body]() { body(Range(a, b)); });
   }
   for (auto &x : th) x.join();
 }

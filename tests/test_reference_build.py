@@ -144,3 +144,18 @@ def test_patch_match_entry(reference, oracle):
         fields = {"pm_pt_un", "pm_pt", "pm_status", "pixel_error", "distance", "ncc"}
         helpers.assert_bit_exact(ref, cpu, fields=fields)
         assert ref.n_iterations == cpu.n_iterations
+
+
+def test_reference_build_is_deterministic_under_threads(reference, oracle):
+    """PatchMatch::mvSuccess is a std::vector<bool> written from the parallel body (include/patch_match.h:94,
+    src/patch_match.cpp:351): stripes that share a word race.  The stand-in's parallel_for_ splits at multiples of 64, so
+    repeated many-thread runs must agree with the single-thread run on every status bit."""
+    pair = synth.make_pair(801, width=320, height=240, n_keys=333, pyramids=3, border=0, sigma_w=2.0)
+    pair.img_ref[:, :60] = 0
+    pair.img_cur[:, :60] = 0
+    prm = capi.default_params(pyramids=3)
+    one = reference.track(pair, prm, 1)[1]
+    for rep in range(20):
+        many = reference.track(pair, prm, 5 + rep % 4)[1]
+        assert np.array_equal(one.pm_status, many.pm_status) and np.array_equal(one.status, many.status), rep
+    _same(one, oracle.track(pair, prm, 3)[1])
