@@ -79,6 +79,8 @@ struct pagk_handle {
   size_t ntab_stride = 0;  // floats per pair
   int *d_work = nullptr;   // work counters of the persistent LK kernels ([0]: slots kernel, [16..17]: lanes kernel)
   int lk_parity = 0;       // which of the two lanes-kernel counters the next launch uses
+  int *d_progress = nullptr;  // lanes kernel, level-granular work items: per feature, epoch * 8 + levels finished
+  int lk_epoch = 0;           // launch number of the lanes kernel on this handle (values of earlier launches never match)
   int n_sms = 0;
   long long *d_dbg = nullptr;  // PAGK_LK_TIMELINE=<file>: clock64 timeline of CTA 0 of the LK kernel (developer aid)
   const char *dbg_path = nullptr;
@@ -204,7 +206,8 @@ int launch_lk_kernel(pagk_handle *h, const PagkOutPtrs &o, const PagkMode &m, in
     // PAGK_LK_TIMELINE=<file> with a -DPAGK_LANES_PROF build: per-warp phase cycles (developer aid)
     if (h->d_dbg) cudaMemsetAsync(h->d_dbg, 0, 2048 * 8 * sizeof(long long), h->stream);
     const int rc = pagk_launch_lk_lanes(h->d_images, h->geom, h->d_pc, h->d_keys_un, o, m, h->cfg.max_keys, n_max, n_pairs,
-                                        h->d_work + 16, h->lk_parity, h->n_sms, h->stream, &h->launches, h->d_dbg);
+                                        h->d_work + 16, h->lk_parity, h->d_progress, (++h->lk_epoch) & 0x0fffffff, h->n_sms,
+                                        h->stream, &h->launches, h->d_dbg);
     if (rc == 0 && n_max > 0 && n_pairs > 0) h->lk_parity ^= 1;
     if (h->d_dbg && rc == 0) {
       std::vector<long long> tl(2048 * 8);
@@ -322,6 +325,8 @@ int pagk_create(const pagk_config *cfg, pagk_handle **out) {
   ok(cudaMalloc(&h->d_out, h->out_bytes));
   ok(cudaMalloc(&h->d_work, 256));
   if (e == cudaSuccess) ok(cudaMemset(h->d_work, 0, 256));
+  ok(cudaMalloc(&h->d_progress, NK * sizeof(int)));
+  if (e == cudaSuccess) ok(cudaMemset(h->d_progress, 0, NK * sizeof(int)));
   ok(cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, cfg->device));
   {
     const char *k = getenv("PAGK_LK_KERNEL");
@@ -351,7 +356,7 @@ void pagk_destroy(pagk_handle *h) {
   if (h->stream && h->own_stream) cudaStreamSynchronize(h->stream);
   else cudaDeviceSynchronize();
   cudaFree(h->d_images); cudaFree(h->d_keys_un); cudaFree(h->d_keys); cudaFree(h->d_pc); cudaFree(h->d_res);
-  cudaFree(h->d_out); cudaFree(h->d_ntab); cudaFree(h->d_work); cudaFree(h->d_dbg);
+  cudaFree(h->d_out); cudaFree(h->d_ntab); cudaFree(h->d_work); cudaFree(h->d_progress); cudaFree(h->d_dbg);
   cudaFreeHost(h->h_in); cudaFreeHost(h->h_out); cudaFreeHost(h->h_res);
   for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   for (cudaEvent_t e : h->tev) cudaEventDestroy(e);

@@ -30,4 +30,5 @@ int pagk_launch_lk_slots(const unsigned char *images, const PagkGeom &g, const P
 bool pagk_lk_lanes_supported(const PagkMode &mode);
 int pagk_launch_lk_lanes(const unsigned char *images, const PagkGeom &g, const PagkPairConst *pcs, const float2 *keys_un,
                          const PagkOutPtrs &out, const PagkMode &mode, int max_keys, int n_max, int n_pairs,
-                         int *work_counters, int parity, int n_sms, cudaStream_t st, long long *launches, long long *prof);
+                         int *work_counters, int parity, int *progress, int epoch, int n_sms, cudaStream_t st,
+                         long long *launches, long long *prof);

@@ -33,6 +33,7 @@
 //   solve    lane = slot: 4x4 LLT in Eigen's operation order, update, exits, next level / next feature
 //
 // Bit-exactness of the window path is argued above the pass loop.
+#include <cstdlib>
 #include "pagk_device.cuh"
 #include "pagk_kernels.h"
 
@@ -196,7 +197,7 @@ __global__ void __launch_bounds__(LanesCfg<HALF>::WARPS * 32, LanesCfg<HALF>::CT
 pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const PagkPairConst *__restrict__ pcs,
                      const float2 *__restrict__ keys_un, PagkOutPtrs out, PagkMode mode, int max_keys, int n_max,
                      int n_pairs, int *__restrict__ work_counter, int *__restrict__ next_counter, int lane_cap,
-                     long long *__restrict__ prof) {
+                     int split, int *progress, int epoch_base, long long *__restrict__ prof) {
   using C = LanesCfg<HALF>;
   constexpr int P = C::P, NP = C::NP, WIN_W = C::WIN_W, WIN_H = C::WIN_H;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -210,6 +211,12 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
   const float *myT = wT + myslot * NP;
   const int total_work = n_pairs * n_max;
   const int top = mode.levels - 1;
+  // Work items.  split == 0: an item is a feature (all levels in one lane).  split != 0: an item is one LEVEL of a
+  // feature, queued level-major (every feature's coarsest level first).  All a level hands to the next one is
+  // mvPtPyr2Un[i] (src/patch_match.cpp:348; dg, db, cost restart per level), so the hand-over is out.pm_un[o] and the
+  // running pass count out.iters[o] through global memory plus progress[o] = epoch_base + levels finished.  The tail of
+  // a launch -- lanes idling while the last items finish -- is then one level long instead of one feature life long.
+  const int total_items = split ? total_work * mode.levels : total_work;
   const unsigned long long slot_bytes = g.slot_bytes;
   const float hf = (float)HALF;
   constexpr unsigned FULL = 0xffffffffu;
@@ -247,6 +254,8 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
   float wxmin = -hf, wxmax = hf, wymin = -hf, wymax = hf;
   int win_x0 = 0, win_y0 = 0;
   bool needs_setup = false, win_valid = false;
+  bool waiting = false;    // split mode: the item is claimed, the level above it is not finished yet
+  int item_lo = 0;         // last level of the claimed item
   bool exhausted = false;  // warp-uniform
   PROF_DECL
 
@@ -260,25 +269,36 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
       int base = 0;
       if (lane == 0) base = atomicAdd(work_counter, cnt);
       base = __shfl_sync(FULL, base, 0);
-      if (base + cnt >= total_work) exhausted = true;
+      if (base + cnt >= total_items) exhausted = true;
       if (want) {
         const int wi = base + __popc(m & ((1u << lane) - 1u));
-        if (wi < total_work) {
-          const int pr = wi / n_max, i = wi - pr * n_max;
+        if (wi < total_items) {
+          int idx = wi, lv = top, lo = 0;
+          if (split) { const int k = wi / total_work; idx = wi - k * total_work; lv = top - k; lo = lv; }
+          const int pr = idx / n_max, i = idx - pr * n_max;
           if (i < pcs[pr].n_keys) {
             const size_t o = (size_t)pr * max_keys + i;
-            const float2 p1 = keys_un[o];
-            const float2 p2 = mode.gyro_init ? out.pt_predict_un[o] : p1;
             if (!out.gyro_status[o]) {  // the reference skips these (src/patch_match.cpp:173): default outputs
-              out.pm_un[o] = p2; out.pm_status[o] = 0; out.pix_err[o] = 0.0; out.ncc[o] = 0.f; out.iters[o] = 0;
+              if (lv == top) {
+                const float2 p1 = keys_un[o];
+                out.pm_un[o] = mode.gyro_init ? out.pt_predict_un[o] : p1;
+                out.pm_status[o] = 0; out.pix_err[o] = 0.0; out.ncc[o] = 0.f; out.iters[o] = 0;
+              }
             } else {
+              const float2 p1 = keys_un[o];
               const float4 A = out.affine[o];
-              const float scale = 1.0f / (float)(1 << top);
-              feat = (int)o; pair = pr; level = top; needs_setup = true; win_valid = false;
+              const float scale = 1.0f / (float)(1 << lv);
+              feat = (int)o; pair = pr; level = lv; item_lo = lo; needs_setup = true; win_valid = false;
               pt1x = p1.x; pt1y = p1.y;
               ptx = p1.x * scale; pty = p1.y * scale;
-              dx = p2.x * scale - ptx; dy = p2.y * scale - pty;
-              dg = 0.f; db = 0.f; lastCost = 0.f; iter = 0; n_iter = 0; succ = 1;
+              if (lv == top) {
+                const float2 p2 = mode.gyro_init ? out.pt_predict_un[o] : p1;
+                dx = p2.x * scale - ptx; dy = p2.y * scale - pty;
+                n_iter = 0; waiting = false;
+              } else {
+                waiting = true;  // dx, dy, n_iter come from the level above (below)
+              }
+              dg = 0.f; db = 0.f; lastCost = 0.f; iter = 0; succ = 1;
               a00 = A.x; a01 = A.y; a10 = A.z; a11 = A.w;
               wxmin = -hf; wxmax = hf; wymin = -hf; wymax = hf;
               if (AFFINE) {  // warp offsets at the four patch corners, exactly as the pass computes them
@@ -292,7 +312,25 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
         }
       }
     }
-    const bool active = feat >= 0;
+    if (split) {
+      // a claimed level starts once the level above it has published its result.  The owner of that level is a
+      // running lane of this launch (items are claimed in queue order), so polling once per round cannot deadlock.
+      if (waiting) {
+        int v;
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(progress + feat) : "memory");
+        if (v == epoch_base + (top - level)) {
+          const float2 p2 = __ldcg(&out.pm_un[feat]);
+          n_iter = __ldcg(&out.iters[feat]);
+          dx = p2.x * 2.0f - ptx; dy = p2.y * 2.0f - pty;  // nextPt = mvPtPyr2Un[i] * 1.0f / mPyramidScale (:182)
+          waiting = false;
+        }
+      }
+      if (__ballot_sync(FULL, feat >= 0 && !waiting) == 0u && __ballot_sync(FULL, waiting) != 0u) {
+        __nanosleep(200);
+        continue;
+      }
+    }
+    const bool active = feat >= 0 && !waiting;
     const unsigned m_active = __ballot_sync(FULL, active);
     if (m_active == 0u) break;
     PROF(0); PROF_ADD(6, 1); PROF_ADD(7, __popc(m_active));
@@ -608,6 +646,13 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
           out.ncc[o] = 1.0f;
           out.iters[o] = n_iter;
           feat = -1;
+        } else if (level == item_lo) {  // split mode: publish this level's result, the lane is free
+          const size_t o = (size_t)feat;
+          __stcg(&out.pm_un[o], make_float2(p2x, p2y));
+          __stcg(&out.iters[o], n_iter);
+          __threadfence();
+          asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(progress + o), "r"(epoch_base + (top - level + 1)) : "memory");
+          feat = -1;
         } else {
           --level;
           const float scale = 1.0f / (float)(1 << level);
@@ -632,7 +677,8 @@ bool pagk_lk_lanes_supported(const PagkMode &mode) {
 template <int HALF, bool AFFINE>
 static int launch_lanes(const unsigned char *images, const PagkGeom &g, const PagkPairConst *pcs, const float2 *keys_un,
                         const PagkOutPtrs &out, const PagkMode &mode, int max_keys, int n_max, int n_pairs,
-                        int *work_counter, int *next_counter, int n_sms, cudaStream_t st, long long *prof) {
+                        int *work_counter, int *next_counter, int *progress, int epoch, int n_sms, cudaStream_t st,
+                        long long *prof) {
   using C = LanesCfg<HALF>;
   const size_t smem = (size_t)C::WARPS * C::WARP_BYTES;
   static bool configured = false;
@@ -650,24 +696,31 @@ static int launch_lanes(const unsigned char *images, const PagkGeom &g, const Pa
   int lane_cap = (int)((total + warps - 1) / warps);
   if (lane_cap > C::SLOTS) lane_cap = C::SLOTS;
   if (lane_cap < 1) lane_cap = 1;
+  // Level-granular work items when the batch is more than one wave of lanes (the tail of the launch is what they
+  // shorten); a batch that fits the lanes keeps a feature in its lane.  PAGK_LK_SPLIT=0|1 forces either.
+  static const int forced = [] { const char *e = getenv("PAGK_LK_SPLIT"); return e ? atoi(e) : -1; }();
+  int split = (progress != nullptr && mode.levels > 1 && total > warps * C::SLOTS) ? 1 : 0;
+  if (forced >= 0 && progress != nullptr && mode.levels > 1) split = forced ? 1 : 0;
   pagk_lk_lanes_kernel<HALF, AFFINE><<<(unsigned)ctas, C::WARPS * 32, smem, st>>>(images, g, pcs, keys_un, out, mode, max_keys,
-                                                                                  n_max, n_pairs, work_counter, next_counter, lane_cap, prof);
+                                                                                  n_max, n_pairs, work_counter, next_counter, lane_cap,
+                                                                                  split, progress, epoch * 8, prof);
   return (int)cudaGetLastError();
 }
 
 int pagk_launch_lk_lanes(const unsigned char *images, const PagkGeom &g, const PagkPairConst *pcs, const float2 *keys_un,
                          const PagkOutPtrs &out, const PagkMode &mode, int max_keys, int n_max, int n_pairs,
-                         int *work_counters, int parity, int n_sms, cudaStream_t st, long long *launches, long long *prof) {
+                         int *work_counters, int parity, int *progress, int epoch, int n_sms, cudaStream_t st,
+                         long long *launches, long long *prof) {
   if (n_max <= 0 || n_pairs <= 0) return 0;
   // work_counters[0..1]: both zero when the handle is created; launch n uses [n & 1] and zeroes the other one
   int *work_counter = work_counters + (parity & 1), *next_counter = work_counters + ((parity + 1) & 1);
   int rc;
   if (mode.half == 5) {
-    rc = mode.affine ? launch_lanes<5, true>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, next_counter, n_sms, st, prof)
-                     : launch_lanes<5, false>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, next_counter, n_sms, st, prof);
+    rc = mode.affine ? launch_lanes<5, true>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, next_counter, progress, epoch, n_sms, st, prof)
+                     : launch_lanes<5, false>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, next_counter, progress, epoch, n_sms, st, prof);
   } else {
-    rc = mode.affine ? launch_lanes<10, true>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, next_counter, n_sms, st, prof)
-                     : launch_lanes<10, false>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, next_counter, n_sms, st, prof);
+    rc = mode.affine ? launch_lanes<10, true>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, next_counter, progress, epoch, n_sms, st, prof)
+                     : launch_lanes<10, false>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, next_counter, progress, epoch, n_sms, st, prof);
   }
   ++*launches;
   return rc;
