@@ -124,23 +124,6 @@ __device__ __forceinline__ void load_window(unsigned char (&v)[WIN_H], const uns
     }
   }
 }
-// the (P+2) x (P+2) taps of a template that lies inside the level: no clamps at all
-template <int TW>
-__device__ __forceinline__ void load_template(unsigned char (&v)[TW], const unsigned char *__restrict__ img, int cols, int x0,
-                                              int y0, int lane) {
-  if (lane < TW) {
-    const unsigned char *q = img + y0 * cols + x0 + lane;
-#pragma unroll
-    for (int i = 0; i < TW; ++i) { v[i] = __ldg(q); q += cols; }
-  }
-}
-template <int WIN_W, int TW>
-__device__ __forceinline__ void store_template(unsigned char *__restrict__ win, const unsigned char (&v)[TW], int lane) {
-  if (lane < TW) {
-#pragma unroll
-    for (int i = 0; i < TW; ++i) win[i * WIN_W + lane] = v[i];
-  }
-}
 template <int WIN_W, int WIN_H>
 __device__ __forceinline__ void store_window(unsigned char *__restrict__ win, const unsigned char (&v)[WIN_H], int lane) {
   if (lane < WIN_W) {
@@ -170,9 +153,15 @@ __device__ __forceinline__ float window_sample(const unsigned char *__restrict__
 #define PROF_DECL long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long pt = clock64();
 #define PROF(i) do { const long long now_ = clock64(); pf[i] += now_ - pt; pt = now_; } while (0)
 #define PROF_ADD(i, v) pf[i] += (v)
+#ifdef PAGK_PROF_SETUP
+#define PROF_SUB(i) PROF(i)
+#else
+#define PROF_SUB(i)
+#endif
 #define PROF_FLUSH() do { if (prof && lane == 0) for (int i_ = 0; i_ < 8; ++i_) prof[(size_t)(blockIdx.x * (blockDim.x >> 5) + warp) * 8 + i_] = pf[i_]; } while (0)
 #else
 #define PROF_DECL
+#define PROF_SUB(i)
 #define PROF(i)
 #define PROF_ADD(i, v)
 #define PROF_FLUSH()
@@ -384,41 +373,51 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
         float *T = wT + s * NP;
         const float txlo = sptx + (-hf), txhi = sptx + hf, tylo = spty + (-hf), tyhi = spty + hf;
         const bool tin = txlo >= 0.0f && txhi < (float)scols && tylo >= 0.0f && tyhi < (float)srows;
-        const int x0 = (int)txlo, y0 = (int)tylo;
-        unsigned char v1[P + 2], v2[WIN_H];
-        // both windows' loads in flight together: one global round trip per level instead of two
-        if (tin) load_template<P + 2>(v1, img1, scols, x0, y0, lane);
-        if (rs) load_window<WIN_W, WIN_H>(v2, img1 + slot_bytes, scols, srows, rx0, ry0, lane);
+        unsigned char v2[WIN_H];
+        constexpr int TK = (NP + 31) / 32;
         if (tin) {
-          // no clamp fires anywhere in the template: sample from a staged window of the reference level
-          // (taps reach floor(hi) + 1 <= x0 + P + 1: inside the window)
-          __syncwarp();
-          store_template<WIN_W, P + 2>(win, v1, lane);
-          __syncwarp();
-          // window element index from the mantissas of 2^23 + floor(.), as in the pass
-          const unsigned int kt = (unsigned int)(WIN_W + 1) * 0x4B000000u + (unsigned int)(y0 * WIN_W + x0);
+          // No clamp fires anywhere in the template: lanes = pixels, the four taps of each pixel straight from the
+          // level (L1), all of them and the current-image window's loads in flight together -- one global round
+          // trip per level and no staging of the reference window.
+          unsigned char t00[TK], t10[TK], t01[TK], t11[TK];
+          float wxx[TK], wyy[TK];
 #pragma unroll
-          for (int k = 0; k < (NP + 31) / 32; ++k) {
+          for (int k = 0; k < TK; ++k) {
             const int p = lane + 32 * k;
+            const float cx = sptx + tpx[k], cy = spty + tpy[k];
+            // 2^23 + floor(.) by a round-down add, as in the pass
+            const float tx = __fadd_rd(cx, 8388608.0f), ty = __fadd_rd(cy, 8388608.0f);
+            wxx[k] = cx - (tx - 8388608.0f); wyy[k] = cy - (ty - 8388608.0f);
+            const int ix = __float_as_int(tx) - 0x4B000000, iy = __float_as_int(ty) - 0x4B000000;
+            t00[k] = t10[k] = t01[k] = t11[k] = 0;
             if (p < NP) {
-              const float cx = sptx + tpx[k], cy = spty + tpy[k];
-              const float tx = __fadd_rd(cx, 8388608.0f), ty = __fadd_rd(cy, 8388608.0f);
-              const float xx = cx - (tx - 8388608.0f), yy = cy - (ty - 8388608.0f), wa = 1.0f - xx, wb = 1.0f - yy;
-              const int qidx = (int)((unsigned int)__float_as_int(ty) * (unsigned int)WIN_W + (unsigned int)__float_as_int(tx) - kt);
-              CHECK_IDX(qidx, 0, WIN_W * (P + 2) - WIN_W - 2);
-              const unsigned char *q = win + qidx;
-              T[p] = wb * (wa * u8f(q[0]) + xx * u8f(q[1])) + yy * (wa * u8f(q[WIN_W]) + xx * u8f(q[WIN_W + 1]));
+              const unsigned char *q = img1 + iy * scols + ix;
+              t00[k] = __ldg(q); t10[k] = __ldg(q + 1); t01[k] = __ldg(q + scols); t11[k] = __ldg(q + scols + 1);
             }
           }
+          if (rs) load_window<WIN_W, WIN_H>(v2, img1 + slot_bytes, scols, srows, rx0, ry0, lane);
+          PROF_SUB(1);
+#ifdef PAGK_PROF_SETUP
+          { unsigned int sink = t00[0] + t11[TK - 2] + v2[0] + v2[WIN_H - 1]; asm volatile("" ::"r"(sink)); }
+          PROF_SUB(2);
+#endif
+#pragma unroll
+          for (int k = 0; k < TK; ++k) {
+            const int p = lane + 32 * k;
+            const float xx = wxx[k], yy = wyy[k], wa = 1.0f - xx, wb = 1.0f - yy;
+            if (p < NP) T[p] = wb * (wa * u8f(t00[k]) + xx * u8f(t10[k])) + yy * (wa * u8f(t01[k]) + xx * u8f(t11[k]));
+          }
         } else {
+          if (rs) load_window<WIN_W, WIN_H>(v2, img1 + slot_bytes, scols, srows, rx0, ry0, lane);
 #pragma unroll 1
           for (int p = lane; p < NP; p += 32) {
             const int py = p / P, px = p - py * P;
             T[p] = pagk_sample_call(img1, scols, srows, sptx + (float)(px - HALF), spty + (float)(py - HALF));
           }
         }
-        __syncwarp();
         if (rs) store_window<WIN_W, WIN_H>(win, v2, lane);
+        __syncwarp();
+        PROF_SUB(4);
         if (lane == s) {
           // de_dg = -I1(pt) (src/patch_match.cpp:263) is minus the template value of the centre pixel: pt + (0, 0)
           cval = -T[NP / 2]; needs_setup = false; win_valid = false;
@@ -445,7 +444,11 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
       if (restage) { win_x0 = nx0; win_y0 = ny0; win_valid = true; }
       __syncwarp();
     }
+#ifdef PAGK_PROF_SETUP
+    PROF(3);
+#else
     PROF(2);
+#endif
 
     Sums S;
     S.h00 = S.h10 = S.h11 = S.h20 = S.h21 = S.h22 = S.h30 = S.h31 = S.b0 = S.b1 = S.b2 = S.b3 = 0.0;
@@ -598,7 +601,11 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
       }
       __syncwarp();
     }
+#ifdef PAGK_PROF_SETUP
+    PROF(5);
+#else
     PROF(4);
+#endif
 
     // ------------------------------------------------------------------ solve, update, exits (lane = slot)
     if (active) {
