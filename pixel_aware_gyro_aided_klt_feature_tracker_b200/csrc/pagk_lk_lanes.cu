@@ -265,27 +265,41 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
           int idx = wi, lv = top, lo = 0;
           if (split) { const int k = wi / total_work; idx = wi - k * total_work; lv = top - k; lo = lv; }
           const int pr = idx / n_max, i = idx - pr * n_max;
-          if (i < pcs[pr].n_keys) {
-            const size_t o = (size_t)pr * max_keys + i;
-            if (!out.gyro_status[o]) {  // the reference skips these (src/patch_match.cpp:173): default outputs
+          // everything the claim needs, loaded in one go (o is inside the arrays for any i < n_max <= max_keys): one global
+          // round trip after the counter's instead of a chain of dependent ones
+          const size_t o = (size_t)pr * max_keys + i;
+          const int nk = pcs[pr].n_keys;
+          const unsigned char st = out.gyro_status[o];
+          const float2 p1 = keys_un[o];
+          const float4 A = out.affine[o];
+          float2 pp = p1;
+          int pv = 0;
+          if (lv == top) {
+            if (mode.gyro_init) pp = out.pt_predict_un[o];
+          } else {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(pv) : "l"(progress + o) : "memory");
+          }
+          if (i < nk) {
+            if (!st) {  // the reference skips these (src/patch_match.cpp:173): default outputs
               if (lv == top) {
-                const float2 p1 = keys_un[o];
-                out.pm_un[o] = mode.gyro_init ? out.pt_predict_un[o] : p1;
+                out.pm_un[o] = pp;
                 out.pm_status[o] = 0; out.pix_err[o] = 0.0; out.ncc[o] = 0.f; out.iters[o] = 0;
               }
             } else {
-              const float2 p1 = keys_un[o];
-              const float4 A = out.affine[o];
               const float scale = 1.0f / (float)(1 << lv);
               feat = (int)o; pair = pr; level = lv; item_lo = lo; needs_setup = true; win_valid = false;
               pt1x = p1.x; pt1y = p1.y;
               ptx = p1.x * scale; pty = p1.y * scale;
               if (lv == top) {
-                const float2 p2 = mode.gyro_init ? out.pt_predict_un[o] : p1;
-                dx = p2.x * scale - ptx; dy = p2.y * scale - pty;
+                dx = pp.x * scale - ptx; dy = pp.y * scale - pty;
                 n_iter = 0; waiting = false;
+              } else if (pv == epoch_base + (top - lv)) {  // the level above is already published (the usual case)
+                const float2 p2 = __ldcg(&out.pm_un[o]);
+                n_iter = __ldcg(&out.iters[o]);
+                dx = p2.x * 2.0f - ptx; dy = p2.y * 2.0f - pty;  // nextPt = mvPtPyr2Un[i] * 1.0f / mPyramidScale (:182)
+                waiting = false;
               } else {
-                waiting = true;  // dx, dy, n_iter come from the level above (below)
+                waiting = true;  // polled once per round below
               }
               dg = 0.f; db = 0.f; lastCost = 0.f; iter = 0; succ = 1;
               a00 = A.x; a01 = A.y; a10 = A.z; a11 = A.w;
