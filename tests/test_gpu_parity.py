@@ -309,3 +309,42 @@ def test_full_size_batch_properties(gpu_ctx, oracle):
     assert tot == sum(int(o.iters.sum()) for o in a) and tot > 8 * 1024 * 4
     ref = oracle.track(pairs[5], prm, 8)[1]
     helpers.assert_bit_exact(a[5], ref)
+
+
+def test_level_granular_work_items_on_a_batch_larger_than_the_lanes(cuda_lib, oracle):
+    """More features than the persistent kernel has lanes (148 SMs x 8 warps x 32): the launch queues one work item per
+    feature LEVEL, and a level's result reaches the next level's lane through global memory.  Every output of all 40
+    pairs bit-exact against the restatement, ragged key counts and skipped (status 0) features included."""
+    from pixel_aware_gyro_aided_klt_feature_tracker_b200 import tracker
+    cfg = {k: v for k, v in synth.CONFIGS["B"].items() if k != "pairs"}
+    pairs = [synth.make_pair(2300 + i, **cfg) for i in range(40)]
+    for p in pairs[::7]:                      # ragged: fewer keys than the batch maximum
+        p.keys_ref_un = np.ascontiguousarray(p.keys_ref_un[:700])
+        p.keys_ref = p.keys_ref_un
+    pairs[3].keys_ref_un[::5] = (-50.0, -50.0)   # predictions outside the image: gyro status 0, skipped at every level
+    prm = capi.default_params(pyramids=4)
+    with tracker.Context(max_width=752, max_height=480, max_keys=1024, max_pairs=40, max_levels=4) as ctx:
+        gpu = ctx.track_batch(pairs, prm)
+        again = ctx.track_batch(pairs, prm)   # the progress words of the first launch must not satisfy the second
+    rc, cpu = oracle.track_batch(pairs, prm, 8)
+    assert rc == 0
+    for g, a, c in zip(gpu, again, cpu):
+        helpers.assert_bit_exact(g, c)
+        helpers.assert_bit_exact(a, c)
+    assert (gpu[3].status[::5] == 0).all()
+
+
+def test_level_granular_work_items_forced_on_small_batches():
+    """PAGK_LK_SPLIT=1 forces level-granular items whatever the batch size (lanes then mostly WAIT for the level above):
+    the edge-case tests of this file rerun in a child process with it set."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, PAGK_LK_SPLIT="1")
+    sel = ("track_bit_exact_small or border_features or flat_and_saturated or odd_sizes or large_rotation or "
+           "level_and_iteration_limits or batch_shapes or ragged_and_empty or against_the_reference_build")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-x", "-q", "-k", sel],
+                       env=env, capture_output=True, text=True, timeout=900,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout
