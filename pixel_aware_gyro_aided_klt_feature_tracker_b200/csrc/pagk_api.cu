@@ -64,6 +64,8 @@ struct pagk_handle {
   pagk_config cfg;
   cudaStream_t stream = nullptr;
   bool own_stream = true;
+  cudaStream_t aux = nullptr;  // the gyro prediction runs here, beside the pyramid build (independent kernels)
+  cudaEvent_t ev_aux = nullptr;
   std::vector<cudaEvent_t> tev;  // start/end event pairs around the LK kernel, pagk_timing_*
   int tev_used = -1;             // -1: timing off
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -316,6 +318,8 @@ int pagk_create(const pagk_config *cfg, pagk_handle **out) {
   cudaError_t e = cudaSuccess;
   auto ok = [&](cudaError_t r) { if (e == cudaSuccess && r != cudaSuccess) e = r; return r == cudaSuccess; };
   ok(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  ok(cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking));
+  ok(cudaEventCreateWithFlags(&h->ev_aux, cudaEventDisableTiming));
   for (int i = 0; i < 6; ++i) ok(cudaEventCreate(&h->ev[i]));
   ok(cudaMalloc(&h->d_images, h->slot_capacity * 2 * (size_t)cfg->max_pairs));
   ok(cudaMalloc(&h->d_keys_un, NK * sizeof(float2)));
@@ -360,6 +364,8 @@ void pagk_destroy(pagk_handle *h) {
   cudaFreeHost(h->h_in); cudaFreeHost(h->h_out); cudaFreeHost(h->h_res);
   for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
+  if (h->aux) { cudaStreamSynchronize(h->aux); cudaStreamDestroy(h->aux); }
+  if (h->ev_aux) cudaEventDestroy(h->ev_aux);
   if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
   cudaGetLastError();
   delete h;
@@ -440,10 +446,22 @@ int pagk_run_resident(pagk_handle *h) {
   cudaStream_t st = h->stream;
   const bool lk = (h->e_type != PAGK_GYRO_PREDICT);
   CU(cudaEventRecord(h->ev[0], st));
-  if (lk) CU((cudaError_t)pagk_launch_pyramids(h->d_images, h->geom, 2 * h->n_pairs, st, &h->launches));
-  CU(cudaEventRecord(h->ev[1], st));
-  CU((cudaError_t)pagk_launch_predict(h->d_pc, h->d_keys_un, h->d_keys, o, h->mode, h->cfg.max_keys, h->n_max, h->n_pairs,
-                                      h->geom.width, h->geom.height, h->d_ntab, h->ntab_stride, st, &h->launches));
+  if (lk) {
+    // K2 (prediction) and K1 (pyramids) are independent: K2 runs on the handle's second stream beside K1 and joins
+    // before K3.  Stage clocks: ev[0]..ev[1] = the pyramid build with the prediction beside it, ev[1]..ev[2] = what
+    // is left of the prediction after the pyramids are done.
+    CU(cudaStreamWaitEvent(h->aux, h->ev[0], 0));
+    CU((cudaError_t)pagk_launch_predict(h->d_pc, h->d_keys_un, h->d_keys, o, h->mode, h->cfg.max_keys, h->n_max, h->n_pairs,
+                                        h->geom.width, h->geom.height, h->d_ntab, h->ntab_stride, h->aux, &h->launches));
+    CU(cudaEventRecord(h->ev_aux, h->aux));
+    CU((cudaError_t)pagk_launch_pyramids(h->d_images, h->geom, 2 * h->n_pairs, st, &h->launches));
+    CU(cudaEventRecord(h->ev[1], st));
+    CU(cudaStreamWaitEvent(st, h->ev_aux, 0));
+  } else {
+    CU(cudaEventRecord(h->ev[1], st));
+    CU((cudaError_t)pagk_launch_predict(h->d_pc, h->d_keys_un, h->d_keys, o, h->mode, h->cfg.max_keys, h->n_max, h->n_pairs,
+                                        h->geom.width, h->geom.height, h->d_ntab, h->ntab_stride, st, &h->launches));
+  }
   CU(cudaEventRecord(h->ev[2], st));
   const bool timed = lk && h->tev_used >= 0 && h->tev_used < 1024;
   if (timed) {
@@ -453,7 +471,7 @@ int pagk_run_resident(pagk_handle *h) {
   if (lk) CU((cudaError_t)launch_lk(h, o, h->mode, h->n_max, h->n_pairs));
   if (timed) { CU(cudaEventRecord(h->tev[2 * h->tev_used + 1], st)); ++h->tev_used; }
   CU(cudaEventRecord(h->ev[3], st));
-  if (lk) CU((cudaError_t)pagk_launch_epilogue(h->d_pc, o, h->mode, h->cfg.max_keys, h->n_pairs, h->d_res, 1, st, &h->launches));
+  if (lk) CU((cudaError_t)pagk_launch_epilogue(h->d_pc, o, h->mode, h->cfg.max_keys, h->n_max, h->n_pairs, h->d_res, 1, st, &h->launches));
   else {
     // eType 1 never constructs a PatchMatch: its six result vectors stay empty in the reference
     const size_t NK = (size_t)h->n_pairs * h->cfg.max_keys;
@@ -734,7 +752,7 @@ int pagk_patch_match(pagk_handle *h, const pagk_patch_match_in *in, pagk_pair_ou
   CU(cudaEventRecord(h->ev[2], st));
   CU((cudaError_t)launch_lk(h, o, m, in->n_keys, 1));
   CU(cudaEventRecord(h->ev[3], st));
-  CU((cudaError_t)pagk_launch_epilogue(h->d_pc, o, m, h->cfg.max_keys, 1, h->d_res, 0, st, &h->launches));
+  CU((cudaError_t)pagk_launch_epilogue(h->d_pc, o, m, h->cfg.max_keys, in->n_keys, 1, h->d_res, 0, st, &h->launches));
   CU(cudaEventRecord(h->ev[4], st));
   h->ran = true;
   pagk_pair_out tmp = *out;  // only the PatchMatch outputs (SetMatcher, src/patch_match.cpp:370-388)

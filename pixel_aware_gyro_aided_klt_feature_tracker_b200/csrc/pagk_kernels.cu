@@ -512,6 +512,79 @@ __global__ void __launch_bounds__(EPI_THREADS) pagk_epilogue_kernel(const PagkPa
   if (t == 0) { res[pair].n_predict = s_cnt; res[pair].n_iterations = (long long)s_it; }
 }
 
+// The same for pairs of at most EPI1_THREADS features (the usual case: BASELINE config B has 1024): one feature per
+// thread, every input read once and kept in registers across the three phases, so the kernel is one global round trip,
+// the ordered sum, and the stores -- the general kernel above walks its features in four dependent rounds per phase.
+#define EPI1_THREADS 1024
+
+__global__ void __launch_bounds__(EPI1_THREADS) pagk_epilogue1_kernel(const PagkPairConst *__restrict__ pcs, PagkOutPtrs out,
+                                                                   PagkMode mode, int max_keys,
+                                                                   PagkPairResult *__restrict__ res, int do_filter) {
+  __shared__ double s_err[EPI1_THREADS];
+  __shared__ double s_th[2];
+  __shared__ int s_cnt, s_ok_cnt;
+  __shared__ unsigned long long s_it;
+  const int pair = blockIdx.x, t = threadIdx.x;
+  const PagkPairConst &c = pcs[pair];
+  const int N = c.n_keys;
+  const size_t o = (size_t)pair * max_keys + t;
+  const bool mine = t < N;
+  if (t == 0) { s_cnt = 0; s_it = 0ull; }
+  float2 p = make_float2(0.f, 0.f), pd = p;
+  double err = 0.0, dist = 0.0;
+  unsigned char ok = 0;
+  int it = 0;
+  if (mine) {
+    p = out.pm_un[o];
+    const float2 base = out.pt_predict_un[o];  // still the gyro prediction here (mvPtPredictUn, src/patch_match.cpp:384)
+    err = out.pix_err[o];
+    ok = out.pm_status[o];
+    it = out.iters[o];
+    // distort + drift distance (src/patch_match.cpp:378-387, 409-416)
+    pd = (c.k1 == 0.0f) ? p : pagk_distort(c, p);
+    const float ddx = base.x - p.x, ddy = base.y - p.y;
+    dist = (double)sqrtf(ddx * ddx + ddy * ddy);
+    out.pm[o] = pd;
+    out.dist[o] = dist;
+  }
+  // a feature that is not ok contributes +0.0, which leaves a sum >= +0 unchanged
+  s_err[t] = (mine && ok) ? err : 0.0;
+  const int n_ok = __syncthreads_count(mine && ok);
+  if (t == 0) {
+    // one thread, index order: the rounding sequence is the reference's (src/gyro_aided_tracker.cpp:294-305)
+    double sum = 0.0;
+#pragma unroll 8
+    for (int i = 0; i < N; ++i) sum += s_err[i];
+    const double avg = sum / (double)n_ok;  // n_ok == 0 -> NaN -> threshold falls back to half (:305-308)
+    const double hp = (double)mode.half;
+    s_th[0] = (4.0 * avg > hp) ? 4.0 * avg : hp;
+    s_th[1] = hp * 4.0;
+    res[pair].avg_pixel_error = avg;
+    res[pair].cnt_pm_ok = n_ok;
+  }
+  __syncthreads();
+  bool keep = false;
+  if (mine && do_filter) {
+    keep = ok && err < s_th[0] && dist < s_th[1];
+    if (keep) {
+      out.pt_predict[o] = pd;
+      out.pt_predict_un[o] = p;
+    }
+    out.status[o] = keep ? 1 : 0;
+  }
+  // per-warp partial sums, then one shared atomic per warp
+  int kc = keep ? 1 : 0;
+  unsigned long long its = (unsigned long long)it;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    kc += __shfl_xor_sync(0xffffffffu, kc, d);
+    its += __shfl_xor_sync(0xffffffffu, its, d);
+  }
+  if ((t & 31) == 0) { atomicAdd(&s_cnt, kc); atomicAdd(&s_it, its); }
+  __syncthreads();
+  if (t == 0) { res[pair].n_predict = s_cnt; res[pair].n_iterations = (long long)s_it; }
+}
+
 // counts the gyro-predicted features of a pair (eType 1: TrackFeatures returns GyroPredictFeatures())
 __global__ void __launch_bounds__(256) pagk_count_status_kernel(const PagkPairConst *__restrict__ pcs, PagkOutPtrs out,
                                                               int max_keys, PagkPairResult *__restrict__ res) {
@@ -599,10 +672,11 @@ int pagk_launch_ncc(const unsigned char *images, const PagkGeom &g, const PagkPa
   return (int)cudaGetLastError();
 }
 
-int pagk_launch_epilogue(const PagkPairConst *pcs, const PagkOutPtrs &out, const PagkMode &mode, int max_keys,
+int pagk_launch_epilogue(const PagkPairConst *pcs, const PagkOutPtrs &out, const PagkMode &mode, int max_keys, int n_max,
                          int n_pairs, PagkPairResult *res, int do_filter, cudaStream_t st, long long *launches) {
   if (n_pairs <= 0) return 0;
-  pagk_epilogue_kernel<<<n_pairs, EPI_THREADS, 0, st>>>(pcs, out, mode, max_keys, res, do_filter);
+  if (n_max <= EPI1_THREADS) pagk_epilogue1_kernel<<<n_pairs, EPI1_THREADS, 0, st>>>(pcs, out, mode, max_keys, res, do_filter);
+  else pagk_epilogue_kernel<<<n_pairs, EPI_THREADS, 0, st>>>(pcs, out, mode, max_keys, res, do_filter);
   ++*launches;
   return (int)cudaGetLastError();
 }

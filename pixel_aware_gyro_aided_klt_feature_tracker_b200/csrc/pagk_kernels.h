@@ -14,7 +14,7 @@ int pagk_launch_lk(const unsigned char *images, const PagkGeom &g, const PagkPai
 int pagk_launch_ncc(const unsigned char *images, const PagkGeom &g, const PagkPairConst *pcs, const float2 *keys_un,
                     const PagkOutPtrs &out, const PagkMode &mode, int max_keys, int n_max, int n_pairs, cudaStream_t st,
                     long long *launches);
-int pagk_launch_epilogue(const PagkPairConst *pcs, const PagkOutPtrs &out, const PagkMode &mode, int max_keys,
+int pagk_launch_epilogue(const PagkPairConst *pcs, const PagkOutPtrs &out, const PagkMode &mode, int max_keys, int n_max,
                          int n_pairs, PagkPairResult *res, int do_filter, cudaStream_t st, long long *launches);
 int pagk_launch_count_status(const PagkPairConst *pcs, const PagkOutPtrs &out, int max_keys, int n_pairs,
                              PagkPairResult *res, cudaStream_t st, long long *launches);
