@@ -187,6 +187,12 @@ int pagk_upload_batch(pagk_handle *h, const pagk_params *prm, int n_pairs, const
 int pagk_run_resident(pagk_handle *h);
 int pagk_download_batch(pagk_handle *h, int n_pairs, pagk_pair_out *out);
 int pagk_synchronize(pagk_handle *h);
+/* Stage clocks.  By default a run records a CUDA event between its kernels so that pagk_last_run_ms and the
+ * t_gyro_predict / t_opt_flow / t_filter fields (mTimeCostGyroPredict, mTimeCostOptFlow,
+ * mTimeCostOptFlowResultFilterOut, include/gyro_aided_tracker.h:226-231) are per stage.  on = 0 drops those events --
+ * a throughput pipeline over several handles runs about 3 % faster without them -- and books the whole device time of
+ * the batch on the patch alignment (t_opt_flow); the other two read (almost) 0. */
+int pagk_set_stage_timing(pagk_handle *h, int on);
 /* device time of the last pagk_run_resident, milliseconds (CUDA events on the handle's stream) */
 int pagk_last_run_ms(pagk_handle *h, float *total_ms, float *pyramid_ms, float *predict_ms,
                      float *lk_ms, float *filter_ms);

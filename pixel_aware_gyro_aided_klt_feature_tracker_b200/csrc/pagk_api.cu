@@ -64,6 +64,7 @@ struct pagk_handle {
   pagk_config cfg;
   cudaStream_t stream = nullptr;
   bool own_stream = true;
+  int stage_timing = 1;        // CUDA events between the kernels of a run (pagk_set_stage_timing)
   cudaStream_t aux = nullptr;  // the gyro prediction runs here, beside the pyramid build (independent kernels)
   cudaEvent_t ev_aux = nullptr;
   std::vector<cudaEvent_t> tev;  // start/end event pairs around the LK kernel, pagk_timing_*
@@ -446,6 +447,9 @@ int pagk_run_resident(pagk_handle *h) {
   cudaStream_t st = h->stream;
   const bool lk = (h->e_type != PAGK_GYRO_PREDICT);
   CU(cudaEventRecord(h->ev[0], st));
+  // stage clocks off: no event sits between two kernels (the whole device time is booked on the patch alignment)
+  const bool stages = h->stage_timing != 0;
+  if (!stages) { CU(cudaEventRecord(h->ev[1], st)); CU(cudaEventRecord(h->ev[2], st)); }
   if (lk) {
     // K2 (prediction) and K1 (pyramids) are independent: K2 runs on the handle's second stream beside K1 and joins
     // before K3.  Stage clocks: ev[0]..ev[1] = the pyramid build with the prediction beside it, ev[1]..ev[2] = what
@@ -455,14 +459,14 @@ int pagk_run_resident(pagk_handle *h) {
                                         h->geom.width, h->geom.height, h->d_ntab, h->ntab_stride, h->aux, &h->launches));
     CU(cudaEventRecord(h->ev_aux, h->aux));
     CU((cudaError_t)pagk_launch_pyramids(h->d_images, h->geom, 2 * h->n_pairs, st, &h->launches));
-    CU(cudaEventRecord(h->ev[1], st));
+    if (stages) CU(cudaEventRecord(h->ev[1], st));
     CU(cudaStreamWaitEvent(st, h->ev_aux, 0));
   } else {
-    CU(cudaEventRecord(h->ev[1], st));
+    if (stages) CU(cudaEventRecord(h->ev[1], st));
     CU((cudaError_t)pagk_launch_predict(h->d_pc, h->d_keys_un, h->d_keys, o, h->mode, h->cfg.max_keys, h->n_max, h->n_pairs,
                                         h->geom.width, h->geom.height, h->d_ntab, h->ntab_stride, st, &h->launches));
   }
-  CU(cudaEventRecord(h->ev[2], st));
+  if (stages) CU(cudaEventRecord(h->ev[2], st));
   const bool timed = lk && h->tev_used >= 0 && h->tev_used < 1024;
   if (timed) {
     while ((int)h->tev.size() < 2 * (h->tev_used + 1)) { cudaEvent_t e; CU(cudaEventCreate(&e)); h->tev.push_back(e); }
@@ -470,7 +474,7 @@ int pagk_run_resident(pagk_handle *h) {
   }
   if (lk) CU((cudaError_t)launch_lk(h, o, h->mode, h->n_max, h->n_pairs));
   if (timed) { CU(cudaEventRecord(h->tev[2 * h->tev_used + 1], st)); ++h->tev_used; }
-  CU(cudaEventRecord(h->ev[3], st));
+  if (stages) CU(cudaEventRecord(h->ev[3], st));
   if (lk) CU((cudaError_t)pagk_launch_epilogue(h->d_pc, o, h->mode, h->cfg.max_keys, h->n_max, h->n_pairs, h->d_res, 1, st, &h->launches));
   else {
     // eType 1 never constructs a PatchMatch: its six result vectors stay empty in the reference
@@ -479,8 +483,15 @@ int pagk_run_resident(pagk_handle *h) {
       CU(cudaMemsetAsync(h->d_out + h->out_off[k], 0, NK * kOutElt[k], st));
     CU((cudaError_t)pagk_launch_count_status(h->d_pc, o, h->cfg.max_keys, h->n_pairs, h->d_res, st, &h->launches));
   }
+  if (!stages) CU(cudaEventRecord(h->ev[3], st));
   CU(cudaEventRecord(h->ev[4], st));
   h->ran = true;
+  return PAGK_OK;
+}
+
+int pagk_set_stage_timing(pagk_handle *h, int on) {
+  if (!h) return fail(PAGK_ERR_INVALID, "null handle");
+  h->stage_timing = on ? 1 : 0;
   return PAGK_OK;
 }
 

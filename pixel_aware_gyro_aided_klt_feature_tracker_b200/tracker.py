@@ -92,6 +92,10 @@ class Context:
         _check(self.lib, self.lib.pagk_last_run_ms(self.handle, *[C.byref(x) for x in v]))
         return dict(zip(("total", "pyramid", "predict", "lk", "filter"), [x.value for x in v]))
 
+    def set_stage_timing(self, on: bool):
+        """CUDA events between the kernels of a run (per-stage clocks); off for throughput pipelines"""
+        _check(self.lib, self.lib.pagk_set_stage_timing(self.handle, 1 if on else 0))
+
     def share_stream(self, other: "Context"):
         _check(self.lib, self.lib.pagk_share_stream(self.handle, other.handle))
 

@@ -348,3 +348,24 @@ def test_level_granular_work_items_forced_on_small_batches():
                        cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert " passed" in r.stdout and "failed" not in r.stdout
+
+
+def test_stage_timing_off_changes_only_the_clocks(gpu_ctx):
+    """pagk_set_stage_timing(h, 0): no CUDA event between the kernels of a run; results identical, the whole device time is
+    booked on the patch alignment"""
+    pairs = [synth.make_pair(8600 + i, width=320, height=240, n_keys=200, pyramids=3, border=20) for i in range(2)]
+    prm = capi.default_params(pyramids=3)
+    on = gpu_ctx.track_batch(pairs, prm)
+    t_on = gpu_ctx.last_run_ms()
+    gpu_ctx.set_stage_timing(False)
+    try:
+        off = gpu_ctx.track_batch(pairs, prm)
+        t_off = gpu_ctx.last_run_ms()
+    finally:
+        gpu_ctx.set_stage_timing(True)
+    for a, b in zip(on, off):
+        helpers.assert_bit_exact(a, b)
+    assert t_on["pyramid"] > 0 and t_on["lk"] > 0 and t_on["filter"] > 0
+    # back-to-back event records are a few microseconds apart
+    assert max(t_off["pyramid"], t_off["predict"], t_off["filter"]) < 0.02 and abs(t_off["lk"] - t_off["total"]) < 0.04
+    assert off[0].struct.t_gyro_predict < 2e-5 and off[0].struct.t_opt_flow > off[0].struct.t_gyro_predict
