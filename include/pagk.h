@@ -191,7 +191,7 @@ int pagk_synchronize(pagk_handle *h);
  * t_gyro_predict / t_opt_flow / t_filter fields (mTimeCostGyroPredict, mTimeCostOptFlow,
  * mTimeCostOptFlowResultFilterOut, include/gyro_aided_tracker.h:226-231) are per stage.  on = 0 drops those events --
  * a throughput pipeline over several handles runs about 3 % faster without them -- and books the whole device time of
- * the batch on the patch alignment (t_opt_flow); the other two read (almost) 0. */
+ * the batch on the patch alignment (t_opt_flow); the other two read 0. */
 int pagk_set_stage_timing(pagk_handle *h, int on);
 /* device time of the last pagk_run_resident, milliseconds (CUDA events on the handle's stream) */
 int pagk_last_run_ms(pagk_handle *h, float *total_ms, float *pyramid_ms, float *predict_ms,
@@ -225,6 +225,34 @@ int pagk_gyro_predict(pagk_handle *h, const pagk_params *prm, const pagk_pair_in
 /* == PatchMatch(...).OpticalFlowMultiLevel() (src/patch_match.cpp:79-142) for one pair with explicit
  * inputs; fills pm_pt_un, pm_pt, pm_status, pixel_error, distance, ncc, iters of `out`. */
 int pagk_patch_match(pagk_handle *h, const pagk_patch_match_in *in, pagk_pair_out *out);
+
+/* == GyroAidedTracker::GeometryValidation() without its two RANSAC estimators (src/gyro_aided_tracker.cpp:429-508,
+ * CheckHomography :589-678, CheckFundamental :680-768): the step both reference drivers run right after TrackFeatures().
+ * The caller supplies H21 / F21 -- what cv::findHomography(vPts1, vPts2, RANSAC, 3) and
+ * cv::findFundamentalMat(vPts1, vPts2, FM_RANSAC, 3., 0.99) returned for the status-1 correspondences -- and gets the
+ * symmetric-transfer / epipolar chi-square scoring, the model choice RH = SH / (SH + SF) > 0.45 and the outlier marking.
+ * (OpenCV's RANSAC draws from its own RNG; no from-scratch estimator can reproduce its models, so they stay with the caller.)
+ * keys_ref_un / pt_predict_un / status NULL: use the vectors of the handle's last run, resident on the device. */
+typedef struct pagk_geometry_in {
+  int n_keys;
+  const float *keys_ref_un;   /* mvKeysRefUn[i].pt  [n_keys][2] */
+  const float *pt_predict_un; /* mvPtPredictUn      [n_keys][2] */
+  const uint8_t *status;      /* mvStatus           [n_keys]    */
+  double H21[9];              /* row-major 3x3, CV_64F as cv::findHomography returns it */
+  double F21[9];
+  float sigma;                /* 1.0 in the reference (:447) */
+} pagk_geometry_in;
+
+typedef struct pagk_geometry_out {
+  uint8_t *status;   /* mvStatus after the call [n_keys]; may be NULL */
+  float score_H;     /* CheckHomography's score */
+  float score_F;     /* CheckFundamental's score */
+  int used_H;        /* 1: RH > 0.45, the homography's inliers were kept; 0: the fundamental matrix's */
+  int n_candidates;  /* vPts1.size(): features with status 1 before the call */
+  int n_inlier;      /* return value of GeometryValidation() (0 when n_candidates <= 8: nothing is validated) */
+} pagk_geometry_out;
+
+int pagk_geometry_validation(pagk_handle *h, int n_pairs, const pagk_geometry_in *in, pagk_geometry_out *out);
 
 #ifdef __cplusplus
 }

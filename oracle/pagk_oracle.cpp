@@ -749,6 +749,113 @@ int track_one(const pagk_params &prm, const pagk_pair_in &in, pagk_pair_out *out
   return PAGK_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// GeometryValidation without the two RANSAC estimators, src/gyro_aided_tracker.cpp:429-508, 589-768.
+// cv::Mat H12 = H21.inv() on a 3x3 CV_64F is OpenCV's closed form: adjugate times 1/det in double.
+// ---------------------------------------------------------------------------------------------
+void inv3_f64(const double *S, double *D) {
+  const double det = S[0] * (S[4] * S[8] - S[5] * S[7]) - S[1] * (S[3] * S[8] - S[5] * S[6]) + S[2] * (S[3] * S[7] - S[4] * S[6]);
+  if (det == 0.) { for (int i = 0; i < 9; ++i) D[i] = 0.; return; }
+  const double d = 1. / det;
+  double t[9];
+  t[0] = (S[4] * S[8] - S[5] * S[7]) * d; t[1] = (S[2] * S[7] - S[1] * S[8]) * d; t[2] = (S[1] * S[5] - S[2] * S[4]) * d;
+  t[3] = (S[5] * S[6] - S[3] * S[8]) * d; t[4] = (S[0] * S[8] - S[2] * S[6]) * d; t[5] = (S[2] * S[3] - S[0] * S[5]) * d;
+  t[6] = (S[3] * S[7] - S[4] * S[6]) * d; t[7] = (S[1] * S[6] - S[0] * S[7]) * d; t[8] = (S[0] * S[4] - S[1] * S[3]) * d;
+  memcpy(D, t, sizeof(t));
+}
+
+// CheckHomography, :589-678
+float check_homography(const double *H21, const std::vector<P2> &p1, const std::vector<P2> &p2, float sigma, std::vector<uint8_t> &inl) {
+  double H12[9];
+  inv3_f64(H21, H12);
+  const double h11 = H21[0], h12 = H21[1], h13 = H21[2], h21 = H21[3], h22 = H21[4], h23 = H21[5], h31 = H21[6], h32 = H21[7], h33 = H21[8];
+  const double h11inv = H12[0], h12inv = H12[1], h13inv = H12[2], h21inv = H12[3], h22inv = H12[4], h23inv = H12[5],
+               h31inv = H12[6], h32inv = H12[7], h33inv = H12[8];
+  const size_t N = p1.size();
+  inl.assign(N, 0);
+  float score = 0;
+  const float th = 5.99;
+  const float invSigmaSquare = 1.0 / (sigma * sigma);
+  for (size_t i = 0; i < N; i++) {
+    bool bIn = true;
+    const float u1 = p1[i].x, v1 = p1[i].y, u2 = p2[i].x, v2 = p2[i].y;
+    const float w1in2inv = 1.0 / (h31 * u1 + h32 * v1 + h33);
+    const float u1in2 = (h11 * u1 + h12 * v1 + h13) * w1in2inv;
+    const float v1in2 = (h21 * u1 + h22 * v1 + h23) * w1in2inv;
+    const float squareDist2 = (u2 - u1in2) * (u2 - u1in2) + (v2 - v1in2) * (v2 - v1in2);
+    const float chiSquare2 = squareDist2 * invSigmaSquare;
+    if (chiSquare2 > th) bIn = false; else score += th - chiSquare2;
+    const float w2in1inv = 1.0 / (h31inv * u2 + h32inv * v2 + h33inv);
+    const float u2in1 = (h11inv * u2 + h12inv * v2 + h13inv) * w2in1inv;
+    const float v2in1 = (h21inv * u2 + h22inv * v2 + h23inv) * w2in1inv;
+    const float squareDist1 = (u1 - u2in1) * (u1 - u2in1) + (v1 - v2in1) * (v1 - v2in1);
+    const float chiSquare1 = squareDist1 * invSigmaSquare;
+    if (chiSquare1 > th) bIn = false; else score += th - chiSquare1;
+    inl[i] = bIn ? 1 : 0;
+  }
+  return score;
+}
+
+// CheckFundamental, :680-768
+float check_fundamental(const double *F21, const std::vector<P2> &p1, const std::vector<P2> &p2, float sigma, std::vector<uint8_t> &inl) {
+  const double f11 = F21[0], f12 = F21[1], f13 = F21[2], f21 = F21[3], f22 = F21[4], f23 = F21[5], f31 = F21[6], f32 = F21[7], f33 = F21[8];
+  const size_t N = p1.size();
+  inl.assign(N, 0);
+  float score = 0;
+  const float th = 3.84;
+  const float thScore = 5.99;
+  const float invSigmaSquare = 1.0 / (sigma * sigma);
+  for (size_t i = 0; i < N; i++) {
+    bool bIn = true;
+    const float u1 = p1[i].x, v1 = p1[i].y, u2 = p2[i].x, v2 = p2[i].y;
+    const float a2 = f11 * u1 + f12 * v1 + f13;
+    const float b2 = f21 * u1 + f22 * v1 + f23;
+    const float c2 = f31 * u1 + f32 * v1 + f33;
+    const float num2 = a2 * u2 + b2 * v2 + c2;
+    const float squareDist2 = num2 * num2 / (a2 * a2 + b2 * b2);
+    const float chiSquare2 = squareDist2 * invSigmaSquare;
+    if (chiSquare2 > th) bIn = false; else score += thScore - chiSquare2;
+    const float a1 = u2 * f11 + v2 * f21 + f31;
+    const float b1 = u2 * f12 + v2 * f22 + f32;
+    const float c1 = u2 * f13 + v2 * f23 + f33;
+    const float num1 = a1 * u1 + b1 * v1 + c1;
+    const float squareDist1 = num1 * num1 / (a1 * a1 + b1 * b1);
+    const float chiSquare1 = squareDist1 * invSigmaSquare;
+    if (chiSquare1 > th) bIn = false; else score += thScore - chiSquare1;
+    inl[i] = bIn ? 1 : 0;
+  }
+  return score;
+}
+
+// GeometryValidation, :429-508
+void geometry_validation(const pagk_geometry_in &in, pagk_geometry_out *out) {
+  std::vector<P2> p1, p2;
+  std::vector<int> idx;
+  std::vector<uint8_t> st(in.status, in.status + in.n_keys);
+  for (int i = 0; i < in.n_keys; ++i)
+    if (st[i]) {
+      idx.push_back(i);
+      p1.push_back(P2{in.keys_ref_un[2 * i], in.keys_ref_un[2 * i + 1]});
+      p2.push_back(P2{in.pt_predict_un[2 * i], in.pt_predict_un[2 * i + 1]});
+    }
+  out->score_H = out->score_F = 0.f; out->used_H = 0; out->n_inlier = 0;
+  out->n_candidates = (int)p1.size();
+  if (p1.size() > 8) {
+    std::vector<uint8_t> inH, inF;
+    const float sH = check_homography(in.H21, p1, p2, in.sigma, inH);
+    const float sF = check_fundamental(in.F21, p1, p2, in.sigma, inF);
+    const float RH = sH / (sF + sH);
+    const bool useH = RH > 0.45;
+    const std::vector<uint8_t> &inl = useH ? inH : inF;
+    int cnt = 0;
+    for (size_t k = 0; k < idx.size(); ++k) {
+      if (!inl[k]) st[idx[k]] = 0; else cnt++;
+    }
+    out->score_H = sH; out->score_F = sF; out->used_H = useH ? 1 : 0; out->n_inlier = cnt;
+  }
+  if (out->status) memcpy(out->status, st.data(), (size_t)in.n_keys);
+}
+
 }  // namespace
 
 extern "C" {
@@ -814,6 +921,11 @@ int pagk_oracle_patch_match(const pagk_patch_match_in *in, pagk_pair_out *out, i
   const int rc = patch_match_run(*in, w, n_threads);
   if (rc != PAGK_OK) return rc;
   export_work(w, out);
+  return PAGK_OK;
+}
+
+int pagk_oracle_geometry_validation(int n_pairs, const pagk_geometry_in *in, pagk_geometry_out *out) {
+  for (int p = 0; p < n_pairs; ++p) geometry_validation(in[p], &out[p]);
   return PAGK_OK;
 }
 

@@ -298,6 +298,39 @@ int pagk_ref_integrate_gyro(const pagk_pair_in *in, float *Rcl, float *KRKinv) {
   return PAGK_OK;
 }
 
+// GyroAidedTracker::GeometryValidation() itself (src/gyro_aided_tracker.cpp:429-508) with cv::findHomography /
+// cv::findFundamentalMat standing in as "return the model the caller supplied".  Only mvStatus and the returned inlier
+// count are observable from outside; the two scores are locals of the reference.  GeometryValidation appends a line to
+// <saveFolderPath>/trackFeatures.txt and timeCost.txt on every call (:493, :502), hence the scratch folder.
+int pagk_ref_geometry_validation(int n_pairs, const pagk_geometry_in *in, pagk_geometry_out *out) {
+  static const uint8_t dummy[16] = {0};
+  for (int p = 0; p < n_pairs; ++p) {
+    const pagk_geometry_in &gi = in[p];
+    const float K[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, dist[5] = {0, 0, 0, 0, 0};
+    Scene s;
+    fill_scene(s, dummy, dummy, 2, 2, 2, gi.n_keys, gi.keys_ref_un, nullptr, K, dist, 4);
+    s.calib.Tbc = cv::Mat::eye(4, 4, CV_32F);
+    s.bias = cv::Point3f(0, 0, 0);
+    GyroAidedTracker t(s.ref, s.cur, s.calib, s.bias, s.table, GyroAidedTracker::GYRO_PREDICT_WITH_OPTICAL_FLOW_REFINED_CONSIDER_ILLUMINATION_DEFORMATION,
+                       GyroAidedTracker::PIXEL_AWARE_PREDICTION, "/tmp/pagk_ref_scratch/", 5);
+    for (int i = 0; i < gi.n_keys; ++i) {
+      t.mvPtPredictUn[i] = cv::Point2f(gi.pt_predict_un[2 * i], gi.pt_predict_un[2 * i + 1]);
+      t.mvStatus[i] = gi.status[i];
+    }
+    pagk_ref_inject_models(gi.H21, gi.F21);
+    int cand = 0;
+    for (int i = 0; i < gi.n_keys; ++i) cand += gi.status[i] ? 1 : 0;
+    // the reference's locals are sized from sigma = 1.0 (:447); any other value is not reachable through it
+    if (gi.sigma != 1.0f) return PAGK_ERR_UNSUPPORTED;
+    const int n_inlier = t.GeometryValidation();
+    out[p].score_H = out[p].score_F = 0.f; out[p].used_H = -1;
+    out[p].n_candidates = cand; out[p].n_inlier = n_inlier;
+    if (out[p].status) for (int i = 0; i < gi.n_keys; ++i) out[p].status[i] = t.mvStatus[i];
+  }
+  pagk_ref_inject_models(nullptr, nullptr);
+  return PAGK_OK;
+}
+
 // PatchMatch(&tracker, ...).OpticalFlowMultiLevel() on caller-given predictions, status and deformation matrices
 int pagk_ref_patch_match(const pagk_patch_match_in *in, pagk_pair_out *out, int n_threads) {
   cv::shim_num_threads() = n_threads > 0 ? n_threads : 1;

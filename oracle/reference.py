@@ -83,6 +83,7 @@ def load():
         lib.pagk_ref_integrate_gyro.argtypes = [C.POINTER(capi.PagkPairIn), _f32p, _f32p]
         lib.pagk_ref_inject_models.argtypes = [_f64p, _f64p]
         lib.pagk_ref_inject_models.restype = None
+        lib.pagk_ref_geometry_validation.argtypes = [C.c_int, C.POINTER(capi.PagkGeometryIn), C.POINTER(capi.PagkGeometryOut)]
         _lib = lib
     return _lib
 
@@ -104,6 +105,16 @@ def patch_match(pm_struct, n_keys: int, n_threads: int = 1):
     out = capi.PairOutputs(n_keys)
     rc = load().pagk_ref_patch_match(C.byref(pm_struct), C.byref(out.struct), n_threads)
     return rc, out
+
+
+def geometry_validation(cases):
+    """GyroAidedTracker::GeometryValidation() with caller-supplied models; returns (rc, [PagkGeometryOut]), status in case.out_status"""
+    ins = (capi.PagkGeometryIn * len(cases))()
+    outs = (capi.PagkGeometryOut * len(cases))()
+    for k, c in enumerate(cases):
+        ins[k], outs[k] = c.structs()
+    rc = load().pagk_ref_geometry_validation(len(cases), ins, outs)
+    return rc, list(outs)
 
 
 def track(pair: capi.PairInputs, params: capi.PagkParams, n_threads: int = 1):

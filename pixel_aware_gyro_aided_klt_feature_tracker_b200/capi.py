@@ -78,6 +78,43 @@ class PagkPatchMatchIn(C.Structure):
                 ("calc_ncc", C.c_int), ("lambda_", C.c_float), ("alpha", C.c_float), ("max_distance", C.c_int)]
 
 
+class PagkGeometryIn(C.Structure):
+    _fields_ = [("n_keys", C.c_int), ("keys_ref_un", _f32p), ("pt_predict_un", _f32p), ("status", _u8p),
+                ("H21", C.c_double * 9), ("F21", C.c_double * 9), ("sigma", C.c_float)]
+
+
+class PagkGeometryOut(C.Structure):
+    _fields_ = [("status", _u8p), ("score_H", C.c_float), ("score_F", C.c_float), ("used_H", C.c_int),
+                ("n_candidates", C.c_int), ("n_inlier", C.c_int)]
+
+
+class GeometryCase:
+    """One GeometryValidation() call in numpy form: correspondences, status, the two models; owns the output status."""
+
+    def __init__(self, keys_ref_un, pt_predict_un, status, H21, F21, sigma=1.0):
+        self.keys_ref_un = None if keys_ref_un is None else np.ascontiguousarray(keys_ref_un, np.float32).reshape(-1, 2)
+        self.pt_predict_un = None if pt_predict_un is None else np.ascontiguousarray(pt_predict_un, np.float32).reshape(-1, 2)
+        self.status = None if status is None else np.ascontiguousarray(status, np.uint8).reshape(-1)
+        self.H21 = np.ascontiguousarray(H21, np.float64).reshape(3, 3)
+        self.F21 = np.ascontiguousarray(F21, np.float64).reshape(3, 3)
+        self.sigma = float(sigma)
+        self.n_keys = 0 if self.status is None else self.status.size
+        self.out_status = np.zeros(max(self.n_keys, 1), np.uint8)
+
+    def structs(self, n_keys=None):
+        i, o = PagkGeometryIn(), PagkGeometryOut()
+        n = self.n_keys if n_keys is None else n_keys
+        if self.out_status.size < n:
+            self.out_status = np.zeros(n, np.uint8)
+        i.n_keys = n
+        i.keys_ref_un, i.pt_predict_un, i.status = _ptr(self.keys_ref_un, _f32p), _ptr(self.pt_predict_un, _f32p), _ptr(self.status, _u8p)
+        i.H21[:] = self.H21.reshape(-1).tolist()
+        i.F21[:] = self.F21.reshape(-1).tolist()
+        i.sigma = self.sigma
+        o.status = _ptr(self.out_status, _u8p)
+        return i, o
+
+
 #: every symbol include/pagk.h declares: name -> (restype, argtypes)
 _H = C.c_void_p
 SYMBOLS = {
@@ -107,6 +144,7 @@ SYMBOLS = {
     "pagk_integrate_gyro": (C.c_int, [C.POINTER(PagkPairIn), _f32p, _f32p]),
     "pagk_gyro_predict": (C.c_int, [_H, C.POINTER(PagkParams), C.POINTER(PagkPairIn), C.POINTER(PagkPairOut)]),
     "pagk_patch_match": (C.c_int, [_H, C.POINTER(PagkPatchMatchIn), C.POINTER(PagkPairOut)]),
+    "pagk_geometry_validation": (C.c_int, [_H, C.c_int, C.POINTER(PagkGeometryIn), C.POINTER(PagkGeometryOut)]),
 }
 
 LIB_NAME = "libpagk_cuda.so"

@@ -64,6 +64,7 @@ struct pagk_handle {
   pagk_config cfg;
   cudaStream_t stream = nullptr;
   bool own_stream = true;
+  bool ran_stages = true;      // whether the last run recorded them
   int stage_timing = 1;        // CUDA events between the kernels of a run (pagk_set_stage_timing)
   cudaStream_t aux = nullptr;  // the gyro prediction runs here, beside the pyramid build (independent kernels)
   cudaEvent_t ev_aux = nullptr;
@@ -82,6 +83,8 @@ struct pagk_handle {
   size_t ntab_stride = 0;  // floats per pair
   int *d_work = nullptr;   // work counters of the persistent LK kernels ([0]: slots kernel, [16..17]: lanes kernel)
   int lk_parity = 0;       // which of the two lanes-kernel counters the next launch uses
+  PagkGeoModel *d_geo = nullptr;    // pagk_geometry_validation: models in, results out (allocated on first use)
+  PagkGeoResult *d_geo_res = nullptr;
   int *d_progress = nullptr;  // lanes kernel, level-granular work items: per feature, epoch * 8 + levels finished
   int lk_epoch = 0;           // launch number of the lanes kernel on this handle (values of earlier launches never match)
   int n_sms = 0;
@@ -361,7 +364,7 @@ void pagk_destroy(pagk_handle *h) {
   if (h->stream && h->own_stream) cudaStreamSynchronize(h->stream);
   else cudaDeviceSynchronize();
   cudaFree(h->d_images); cudaFree(h->d_keys_un); cudaFree(h->d_keys); cudaFree(h->d_pc); cudaFree(h->d_res);
-  cudaFree(h->d_out); cudaFree(h->d_ntab); cudaFree(h->d_work); cudaFree(h->d_progress); cudaFree(h->d_dbg);
+  cudaFree(h->d_out); cudaFree(h->d_ntab); cudaFree(h->d_work); cudaFree(h->d_progress); cudaFree(h->d_geo); cudaFree(h->d_geo_res); cudaFree(h->d_dbg);
   cudaFreeHost(h->h_in); cudaFreeHost(h->h_out); cudaFreeHost(h->h_res);
   for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
@@ -449,7 +452,7 @@ int pagk_run_resident(pagk_handle *h) {
   CU(cudaEventRecord(h->ev[0], st));
   // stage clocks off: no event sits between two kernels (the whole device time is booked on the patch alignment)
   const bool stages = h->stage_timing != 0;
-  if (!stages) { CU(cudaEventRecord(h->ev[1], st)); CU(cudaEventRecord(h->ev[2], st)); }
+  h->ran_stages = stages;
   if (lk) {
     // K2 (prediction) and K1 (pyramids) are independent: K2 runs on the handle's second stream beside K1 and joins
     // before K3.  Stage clocks: ev[0]..ev[1] = the pyramid build with the prediction beside it, ev[1]..ev[2] = what
@@ -483,7 +486,6 @@ int pagk_run_resident(pagk_handle *h) {
       CU(cudaMemsetAsync(h->d_out + h->out_off[k], 0, NK * kOutElt[k], st));
     CU((cudaError_t)pagk_launch_count_status(h->d_pc, o, h->cfg.max_keys, h->n_pairs, h->d_res, st, &h->launches));
   }
-  if (!stages) CU(cudaEventRecord(h->ev[3], st));
   CU(cudaEventRecord(h->ev[4], st));
   h->ran = true;
   return PAGK_OK;
@@ -507,9 +509,10 @@ int pagk_last_run_ms(pagk_handle *h, float *total_ms, float *pyramid_ms, float *
   if (h->n_pairs == 0) { if (total_ms) *total_ms = 0; return PAGK_OK; }
   CU(cudaSetDevice(h->cfg.device));
   CU(cudaEventSynchronize(h->ev[4]));
-  float t[5];
+  float t[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
   CU(cudaEventElapsedTime(&t[0], h->ev[0], h->ev[4]));
-  for (int i = 0; i < 4; ++i) CU(cudaEventElapsedTime(&t[i + 1], h->ev[i], h->ev[i + 1]));
+  if (h->ran_stages) { for (int i = 0; i < 4; ++i) CU(cudaEventElapsedTime(&t[i + 1], h->ev[i], h->ev[i + 1])); }
+  else t[3] = t[0];  // no stage clocks: everything is booked on the patch alignment
   if (total_ms) *total_ms = t[0];
   if (pyramid_ms) *pyramid_ms = t[1];
   if (predict_ms) *predict_ms = t[2];
@@ -716,6 +719,52 @@ int pagk_gyro_predict(pagk_handle *h, const pagk_params *prm, const pagk_pair_in
   return pagk_track_batch(h, &p, 1, in, out);
 }
 
+int pagk_geometry_validation(pagk_handle *h, int n_pairs, const pagk_geometry_in *in, pagk_geometry_out *out) {
+  if (!h || !in || !out) return fail(PAGK_ERR_INVALID, "null argument");
+  if (n_pairs < 0 || n_pairs > h->cfg.max_pairs) return fail(PAGK_ERR_INVALID, "n_pairs exceeds pagk_config.max_pairs");
+  if (n_pairs == 0) return PAGK_OK;
+  CU(cudaSetDevice(h->cfg.device));
+  if (!h->d_geo) {
+    CU(cudaMalloc(&h->d_geo, (size_t)h->cfg.max_pairs * sizeof(PagkGeoModel)));
+    CU(cudaMalloc(&h->d_geo_res, (size_t)h->cfg.max_pairs * sizeof(PagkGeoResult)));
+  }
+  const PagkOutPtrs o = h->outs();
+  cudaStream_t st = h->stream;
+  std::vector<PagkGeoModel> models((size_t)n_pairs);
+  for (int p = 0; p < n_pairs; ++p) {
+    const pagk_geometry_in &g = in[p];
+    if (g.n_keys < 0 || g.n_keys > h->cfg.max_keys) return fail(PAGK_ERR_INVALID, "n_keys exceeds pagk_config.max_keys");
+    const bool given = g.keys_ref_un && g.pt_predict_un && g.status;
+    if (!given && (g.keys_ref_un || g.pt_predict_un || g.status))
+      return fail(PAGK_ERR_INVALID, "keys_ref_un, pt_predict_un and status: all three or none");
+    if (!given && !(h->ran && p < h->n_pairs)) return fail(PAGK_ERR_INVALID, "no resident run to validate");
+    PagkGeoModel &M = models[(size_t)p];
+    std::memcpy(M.H21, g.H21, sizeof(M.H21)); std::memcpy(M.F21, g.F21, sizeof(M.F21));
+    pagk_inv3_f64(g.H21, M.H12);  // cv::Mat H12 = H21.inv(), src/gyro_aided_tracker.cpp:597
+    M.sigma = g.sigma; M.n_keys = g.n_keys;
+    const size_t off = (size_t)p * h->cfg.max_keys, n = (size_t)g.n_keys;
+    if (given && n) {
+      CU(cudaMemcpyAsync(h->d_keys_un + off, g.keys_ref_un, n * sizeof(float2), cudaMemcpyHostToDevice, st));
+      CU(cudaMemcpyAsync(o.pt_predict_un + off, g.pt_predict_un, n * sizeof(float2), cudaMemcpyHostToDevice, st));
+      CU(cudaMemcpyAsync(o.status + off, g.status, n, cudaMemcpyHostToDevice, st));
+    }
+  }
+  CU(cudaMemcpyAsync(h->d_geo, models.data(), models.size() * sizeof(PagkGeoModel), cudaMemcpyHostToDevice, st));
+  CU((cudaError_t)pagk_launch_geometry(h->d_geo, h->d_keys_un, o.pt_predict_un, o.status, h->cfg.max_keys, n_pairs, h->d_geo_res,
+                                       st, &h->launches));
+  std::vector<PagkGeoResult> res((size_t)n_pairs);
+  CU(cudaMemcpyAsync(res.data(), h->d_geo_res, res.size() * sizeof(PagkGeoResult), cudaMemcpyDeviceToHost, st));
+  for (int p = 0; p < n_pairs; ++p)
+    if (out[p].status && in[p].n_keys)
+      CU(cudaMemcpyAsync(out[p].status, o.status + (size_t)p * h->cfg.max_keys, (size_t)in[p].n_keys, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  for (int p = 0; p < n_pairs; ++p) {
+    out[p].score_H = res[(size_t)p].score_H; out[p].score_F = res[(size_t)p].score_F; out[p].used_H = res[(size_t)p].used_H;
+    out[p].n_candidates = res[(size_t)p].n_candidates; out[p].n_inlier = res[(size_t)p].n_inlier;
+  }
+  return PAGK_OK;
+}
+
 int pagk_patch_match(pagk_handle *h, const pagk_patch_match_in *in, pagk_pair_out *out) {
   if (!h || !in || !out) return fail(PAGK_ERR_INVALID, "null argument");
   if (in->inverse) return fail(PAGK_ERR_UNSUPPORTED, "inverse mode is \"not support yet\" in the reference (src/patch_match.cpp:220)");
@@ -757,6 +806,7 @@ int pagk_patch_match(pagk_handle *h, const pagk_patch_match_in *in, pagk_pair_ou
   if (rc != PAGK_OK) return rc;
   CU(cudaStreamSynchronize(st));  // the caller's (pageable) inputs may go away after this call
   h->mode = m; h->n_pairs = 1; h->n_max = in->n_keys; h->e_type = PAGK_GYRO_PREDICT_WITH_OPTICAL_FLOW_REFINED;
+  h->ran_stages = true;
   CU(cudaEventRecord(h->ev[0], st));
   CU((cudaError_t)pagk_launch_pyramids(h->d_images, h->geom, 2, st, &h->launches));
   CU(cudaEventRecord(h->ev[1], st));

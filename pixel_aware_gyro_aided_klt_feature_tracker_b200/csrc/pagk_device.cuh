@@ -44,6 +44,17 @@ struct PagkPairResult {
   double avg_pixel_error;
 };
 
+// GeometryValidation (reference src/gyro_aided_tracker.cpp:429-508): the two models of one pair and what comes back
+struct PagkGeoModel {
+  double H21[9], H12[9], F21[9];
+  float sigma;
+  int n_keys;
+};
+struct PagkGeoResult {
+  float score_H, score_F;
+  int used_H, n_candidates, n_inlier, pad;
+};
+
 // Mode of one run (what TrackFeatures derives from eType, :384-414, plus the PatchMatch ctor args)
 struct PagkMode {
   int half, iterations, levels;

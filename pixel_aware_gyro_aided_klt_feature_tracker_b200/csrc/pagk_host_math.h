@@ -151,3 +151,16 @@ inline float bbt_inverse_diag(int half) {
 }
 
 }  // namespace pagk_host
+
+// cv::Mat::inv() of a 3x3 CV_64F (GeometryValidation's H12 = H21.inv(), reference src/gyro_aided_tracker.cpp:597):
+// OpenCV's closed form, adjugate times 1/det in double; an all-zero result for a singular matrix.
+inline void pagk_inv3_f64(const double *S, double *D) {
+  const double det = S[0] * (S[4] * S[8] - S[5] * S[7]) - S[1] * (S[3] * S[8] - S[5] * S[6]) + S[2] * (S[3] * S[7] - S[4] * S[6]);
+  if (det == 0.) { for (int i = 0; i < 9; ++i) D[i] = 0.; return; }
+  const double d = 1. / det;
+  double t[9];
+  t[0] = (S[4] * S[8] - S[5] * S[7]) * d; t[1] = (S[2] * S[7] - S[1] * S[8]) * d; t[2] = (S[1] * S[5] - S[2] * S[4]) * d;
+  t[3] = (S[5] * S[6] - S[3] * S[8]) * d; t[4] = (S[0] * S[8] - S[2] * S[6]) * d; t[5] = (S[2] * S[3] - S[0] * S[5]) * d;
+  t[6] = (S[3] * S[7] - S[4] * S[6]) * d; t[7] = (S[1] * S[6] - S[0] * S[7]) * d; t[8] = (S[0] * S[4] - S[1] * S[3]) * d;
+  for (int i = 0; i < 9; ++i) D[i] = t[i];
+}

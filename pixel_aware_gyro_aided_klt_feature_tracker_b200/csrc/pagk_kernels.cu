@@ -600,6 +600,122 @@ __global__ void __launch_bounds__(256) pagk_count_status_kernel(const PagkPairCo
 }
 
 // =================================================================================================
+// GeometryValidation without its two RANSAC estimators (reference src/gyro_aided_tracker.cpp:429-508): CheckHomography
+// (:589-678, symmetric transfer error) and CheckFundamental (:680-768, point-to-epipolar-line distance) on the status-1
+// correspondences, the model choice RH = SH / (SH + SF) > 0.45 and the outlier marking.  One CTA per pair.  The chi-square
+// terms are lane-parallel; each score is a float accumulated in correspondence order, two terms per correspondence, by one
+// thread (thread 0: homography, thread 32: fundamental matrix), chunk after chunk from shared memory.
+// While the scores are being summed status[i] carries the two inlier bits: 1 | inH << 1 | inF << 2.
+// =================================================================================================
+#define GEO_THREADS 1024
+
+__global__ void __launch_bounds__(GEO_THREADS) pagk_geometry_kernel(const PagkGeoModel *__restrict__ models,
+                                                                  const float2 *__restrict__ keys_un,
+                                                                  const float2 *__restrict__ pred_un,
+                                                                  unsigned char *__restrict__ status, int max_keys,
+                                                                  PagkGeoResult *__restrict__ res) {
+  __shared__ float s_chi[4][GEO_THREADS];
+  __shared__ unsigned char s_st[GEO_THREADS];
+  __shared__ float s_score[2];
+  __shared__ int s_use;
+  const int pair = blockIdx.x, t = threadIdx.x;
+  const PagkGeoModel &M = models[pair];
+  const int N = M.n_keys;
+  const size_t o0 = (size_t)pair * max_keys;
+  int cand = 0;
+  for (int c0 = 0; c0 < N; c0 += GEO_THREADS) cand += __syncthreads_count(c0 + t < N && status[o0 + c0 + t] != 0);
+  if (cand <= 8) {  // if (vPts1.size() > 8) ... : nothing is validated (:446)
+    if (t == 0) { PagkGeoResult r; r.score_H = 0.f; r.score_F = 0.f; r.used_H = 0; r.n_candidates = cand; r.n_inlier = 0; r.pad = 0; res[pair] = r; }
+    return;
+  }
+  const double h11 = M.H21[0], h12 = M.H21[1], h13 = M.H21[2], h21 = M.H21[3], h22 = M.H21[4], h23 = M.H21[5], h31 = M.H21[6],
+               h32 = M.H21[7], h33 = M.H21[8];
+  const double h11inv = M.H12[0], h12inv = M.H12[1], h13inv = M.H12[2], h21inv = M.H12[3], h22inv = M.H12[4], h23inv = M.H12[5],
+               h31inv = M.H12[6], h32inv = M.H12[7], h33inv = M.H12[8];
+  const double f11 = M.F21[0], f12 = M.F21[1], f13 = M.F21[2], f21 = M.F21[3], f22 = M.F21[4], f23 = M.F21[5], f31 = M.F21[6],
+               f32 = M.F21[7], f33 = M.F21[8];
+  const float thH = 5.99, thF = 3.84, thScore = 5.99;
+  const float invSigmaSquare = (float)(1.0 / (double)(M.sigma * M.sigma));
+  float sH = 0.f, sF = 0.f;
+  for (int c0 = 0; c0 < N; c0 += GEO_THREADS) {
+    const int i = c0 + t;
+    unsigned char st = 0;
+    if (i < N && status[o0 + i]) {
+      const float2 p1 = keys_un[o0 + i], p2 = pred_un[o0 + i];
+      const float u1 = p1.x, v1 = p1.y, u2 = p2.x, v2 = p2.y;
+      // CheckHomography (:631-664)
+      const float w1in2inv = (float)(1.0 / (h31 * (double)u1 + h32 * (double)v1 + h33));
+      const float u1in2 = (float)((h11 * (double)u1 + h12 * (double)v1 + h13) * (double)w1in2inv);
+      const float v1in2 = (float)((h21 * (double)u1 + h22 * (double)v1 + h23) * (double)w1in2inv);
+      const float chi2H = ((u2 - u1in2) * (u2 - u1in2) + (v2 - v1in2) * (v2 - v1in2)) * invSigmaSquare;
+      const float w2in1inv = (float)(1.0 / (h31inv * (double)u2 + h32inv * (double)v2 + h33inv));
+      const float u2in1 = (float)((h11inv * (double)u2 + h12inv * (double)v2 + h13inv) * (double)w2in1inv);
+      const float v2in1 = (float)((h21inv * (double)u2 + h22inv * (double)v2 + h23inv) * (double)w2in1inv);
+      const float chi1H = ((u1 - u2in1) * (u1 - u2in1) + (v1 - v2in1) * (v1 - v2in1)) * invSigmaSquare;
+      // CheckFundamental (:721-754)
+      const float a2 = (float)(f11 * (double)u1 + f12 * (double)v1 + f13);
+      const float b2 = (float)(f21 * (double)u1 + f22 * (double)v1 + f23);
+      const float c2 = (float)(f31 * (double)u1 + f32 * (double)v1 + f33);
+      const float num2 = a2 * u2 + b2 * v2 + c2;
+      const float chi2F = (num2 * num2 / (a2 * a2 + b2 * b2)) * invSigmaSquare;
+      const float a1 = (float)((double)u2 * f11 + (double)v2 * f21 + f31);
+      const float b1 = (float)((double)u2 * f12 + (double)v2 * f22 + f32);
+      const float c1 = (float)((double)u2 * f13 + (double)v2 * f23 + f33);
+      const float num1 = a1 * u1 + b1 * v1 + c1;
+      const float chi1F = (num1 * num1 / (a1 * a1 + b1 * b1)) * invSigmaSquare;
+      const bool inH = !(chi2H > thH) && !(chi1H > thH), inF = !(chi2F > thF) && !(chi1F > thF);
+      st = (unsigned char)(1 | (inH ? 2 : 0) | (inF ? 4 : 0));
+      s_chi[0][t] = chi2H; s_chi[1][t] = chi1H; s_chi[2][t] = chi2F; s_chi[3][t] = chi1F;
+      status[o0 + i] = st;
+    }
+    s_st[t] = st;
+    __syncthreads();
+    const int m = min(GEO_THREADS, N - c0);
+    if (t == 0) {
+      for (int j = 0; j < m; ++j)
+        if (s_st[j]) {
+          const float x2 = s_chi[0][j], x1 = s_chi[1][j];
+          if (!(x2 > thH)) sH += thH - x2;
+          if (!(x1 > thH)) sH += thH - x1;
+        }
+    } else if (t == 32) {
+      for (int j = 0; j < m; ++j)
+        if (s_st[j]) {
+          const float x2 = s_chi[2][j], x1 = s_chi[3][j];
+          if (!(x2 > thF)) sF += thScore - x2;
+          if (!(x1 > thF)) sF += thScore - x1;
+        }
+    }
+    __syncthreads();
+  }
+  if (t == 0) s_score[0] = sH;
+  if (t == 32) s_score[1] = sF;
+  __syncthreads();
+  if (t == 0) {
+    const float RH = s_score[0] / (s_score[1] + s_score[0]);  // :466
+    s_use = ((double)RH > 0.45) ? 1 : 0;
+  }
+  __syncthreads();
+  const int useH = s_use;
+  int inl = 0;
+  for (int c0 = 0; c0 < N; c0 += GEO_THREADS) {
+    const int i = c0 + t;
+    bool keep = false;
+    if (i < N) {
+      const unsigned char st = status[o0 + i];
+      keep = (st & 1) && (useH ? (st & 2) : (st & 4));
+      status[o0 + i] = keep ? 1 : 0;
+    }
+    inl += __syncthreads_count(keep);
+  }
+  if (t == 0) {
+    PagkGeoResult r;
+    r.score_H = s_score[0]; r.score_F = s_score[1]; r.used_H = useH; r.n_candidates = cand; r.n_inlier = inl; r.pad = 0;
+    res[pair] = r;
+  }
+}
+
+// =================================================================================================
 // launch wrappers (host)
 // =================================================================================================
 int pagk_pyramid_fused_max_level() {
@@ -677,6 +793,14 @@ int pagk_launch_epilogue(const PagkPairConst *pcs, const PagkOutPtrs &out, const
   if (n_pairs <= 0) return 0;
   if (n_max <= EPI1_THREADS) pagk_epilogue1_kernel<<<n_pairs, EPI1_THREADS, 0, st>>>(pcs, out, mode, max_keys, res, do_filter);
   else pagk_epilogue_kernel<<<n_pairs, EPI_THREADS, 0, st>>>(pcs, out, mode, max_keys, res, do_filter);
+  ++*launches;
+  return (int)cudaGetLastError();
+}
+
+int pagk_launch_geometry(const PagkGeoModel *models, const float2 *keys_un, const float2 *pred_un, unsigned char *status,
+                         int max_keys, int n_pairs, PagkGeoResult *res, cudaStream_t st, long long *launches) {
+  if (n_pairs <= 0) return 0;
+  pagk_geometry_kernel<<<n_pairs, GEO_THREADS, 0, st>>>(models, keys_un, pred_un, status, max_keys, res);
   ++*launches;
   return (int)cudaGetLastError();
 }

@@ -16,6 +16,9 @@ int pagk_launch_ncc(const unsigned char *images, const PagkGeom &g, const PagkPa
                     long long *launches);
 int pagk_launch_epilogue(const PagkPairConst *pcs, const PagkOutPtrs &out, const PagkMode &mode, int max_keys, int n_max,
                          int n_pairs, PagkPairResult *res, int do_filter, cudaStream_t st, long long *launches);
+// GeometryValidation minus its RANSAC estimators (reference src/gyro_aided_tracker.cpp:429-508, 589-768)
+int pagk_launch_geometry(const PagkGeoModel *models, const float2 *keys_un, const float2 *pred_un, unsigned char *status,
+                         int max_keys, int n_pairs, PagkGeoResult *res, cudaStream_t st, long long *launches);
 int pagk_launch_count_status(const PagkPairConst *pcs, const PagkOutPtrs &out, int max_keys, int n_pairs,
                              PagkPairResult *res, cudaStream_t st, long long *launches);
 

@@ -92,6 +92,16 @@ class Context:
         _check(self.lib, self.lib.pagk_last_run_ms(self.handle, *[C.byref(x) for x in v]))
         return dict(zip(("total", "pyramid", "predict", "lk", "filter"), [x.value for x in v]))
 
+    def geometry_validation(self, cases):
+        """GyroAidedTracker::GeometryValidation() without its RANSAC estimators (include/pagk.h): a list of capi.GeometryCase
+        (vectors None = the resident results of the last run); returns the PagkGeometryOut list, status in case.out_status"""
+        ins = (capi.PagkGeometryIn * len(cases))()
+        outs = (capi.PagkGeometryOut * len(cases))()
+        for k, c in enumerate(cases):
+            ins[k], outs[k] = c.structs(n_keys=c.n_keys if c.status is not None else getattr(c, "resident_n_keys", 0))
+        _check(self.lib, self.lib.pagk_geometry_validation(self.handle, len(cases), ins, outs))
+        return list(outs)
+
     def set_stage_timing(self, on: bool):
         """CUDA events between the kernels of a run (per-stage clocks); off for throughput pipelines"""
         _check(self.lib, self.lib.pagk_set_stage_timing(self.handle, 1 if on else 0))

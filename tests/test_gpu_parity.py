@@ -366,6 +366,5 @@ def test_stage_timing_off_changes_only_the_clocks(gpu_ctx):
     for a, b in zip(on, off):
         helpers.assert_bit_exact(a, b)
     assert t_on["pyramid"] > 0 and t_on["lk"] > 0 and t_on["filter"] > 0
-    # back-to-back event records are a few microseconds apart
-    assert max(t_off["pyramid"], t_off["predict"], t_off["filter"]) < 0.02 and abs(t_off["lk"] - t_off["total"]) < 0.04
-    assert off[0].struct.t_gyro_predict < 2e-5 and off[0].struct.t_opt_flow > off[0].struct.t_gyro_predict
+    assert t_off["pyramid"] == 0 and t_off["predict"] == 0 and t_off["filter"] == 0 and t_off["lk"] == t_off["total"] > 0
+    assert off[0].struct.t_gyro_predict == 0 and off[0].struct.t_opt_flow > 0
