@@ -170,6 +170,30 @@ class GyroAidedTracker {
     return out.n_predict;
   }
 
+  // int GeometryValidation(), reference :429-508.  The reference estimates H21 / F21 itself with cv::findHomography and
+  // cv::findFundamentalMat (OpenCV RANSAC); here the caller passes what those two calls returned for the status-1
+  // correspondences (mvKeysRefUn[i].pt -> mvPtPredictUn[i]) and the scoring, model choice and outlier marking run on the GPU.
+  int GeometryValidation(const double H21[9], const double F21[9], float sigma = 1.0f) {
+    pagk_geometry_in gi;
+    std::vector<float> k1((size_t)mN * 2), k2((size_t)mN * 2);
+    for (int i = 0; i < mN; ++i) {
+      k1[2 * (size_t)i] = mvKeysRefUn[(size_t)i].pt.x; k1[2 * (size_t)i + 1] = mvKeysRefUn[(size_t)i].pt.y;
+      k2[2 * (size_t)i] = mvPtPredictUn[(size_t)i].x; k2[2 * (size_t)i + 1] = mvPtPredictUn[(size_t)i].y;
+    }
+    gi.n_keys = mN; gi.keys_ref_un = k1.data(); gi.pt_predict_un = k2.data(); gi.status = mvStatus.data();
+    for (int i = 0; i < 9; ++i) { gi.H21[i] = H21[i]; gi.F21[i] = F21[i]; }
+    gi.sigma = sigma;
+    std::vector<uint8_t> st((size_t)mN);
+    pagk_geometry_out go;
+    go.status = st.data();
+    check(pagk_geometry_validation(dev_.handle(), 1, &gi, &go));
+    mvStatus = st;
+    mGeometryScoreH = go.score_H; mGeometryScoreF = go.score_F; mGeometryUsedH = go.used_H != 0;
+    return go.n_inlier;
+  }
+  float mGeometryScoreH = 0.f, mGeometryScoreF = 0.f;  // locals score_H / score_F of the reference (:448)
+  bool mGeometryUsedH = false;
+
   void SetBackToFrame(Frame &pFrame) const {  // reference :97-111
     pFrame.mvPtGyroPredictUn = mvPtGyroPredictUn;
     pFrame.mvPtPredict = mvPtPredict;
