@@ -85,7 +85,10 @@ typedef struct pagk_params {
 
 /* Inputs of one frame pair = what the GyroAidedTracker ctor binds (src/gyro_aided_tracker.cpp:30-49). */
 typedef struct pagk_pair_in {
-  const uint8_t *img_ref;   /* mImgGrayRef: CV_8UC1, height rows of `pitch` bytes */
+  const uint8_t *img_ref;   /* mImgGrayRef: CV_8UC1, height rows of `pitch` bytes.  NULL on EVERY pair of a batch = stream
+                             * continuation: the reference image of pair p is the current image of pair p of the previous
+                             * batch on this handle (same size, levels; its pyramid is still on the device), as in the
+                             * drivers' frame loop where curFrame becomes lastFrame.  Only img_cur crosses PCIe. */
   const uint8_t *img_cur;   /* mImgGrayCur */
   int width, height, pitch; /* all pairs of one batch must share width and height */
   int n_keys;               /* mN = mvKeysRef.size() */

@@ -202,9 +202,10 @@ class PairInputs:
 
     def __init__(self, img_ref, img_cur, keys_ref_un, imu_t, imu_w, t_ref, t_cur, K, Rbc, dist=(0, 0, 0, 0, 0),
                  n_dist=4, bias_g=(0, 0, 0), keys_ref=None, normalize_table=None, Rcl_override=None):
-        self.img_ref = np.ascontiguousarray(img_ref, dtype=np.uint8)
+        # img_ref None: stream continuation (the previous batch's current image of this pair index is the reference)
+        self.img_ref = None if img_ref is None else np.ascontiguousarray(img_ref, dtype=np.uint8)
         self.img_cur = np.ascontiguousarray(img_cur, dtype=np.uint8)
-        assert self.img_ref.shape == self.img_cur.shape and self.img_ref.ndim == 2
+        assert self.img_cur.ndim == 2 and (self.img_ref is None or self.img_ref.shape == self.img_cur.shape)
         self.keys_ref_un = np.ascontiguousarray(keys_ref_un, dtype=np.float32).reshape(-1, 2)
         self.keys_ref = (self.keys_ref_un if keys_ref is None
                          else np.ascontiguousarray(keys_ref, dtype=np.float32).reshape(-1, 2))
@@ -228,11 +229,11 @@ class PairInputs:
         return self.keys_ref_un.shape[0]
 
     def as_struct(self) -> PagkPairIn:
-        h, w = self.img_ref.shape
+        h, w = self.img_cur.shape
         s = PagkPairIn()
         s.img_ref = _ptr(self.img_ref, _u8p)
         s.img_cur = _ptr(self.img_cur, _u8p)
-        s.width, s.height, s.pitch = w, h, self.img_ref.strides[0]
+        s.width, s.height, s.pitch = w, h, self.img_cur.strides[0]
         s.n_keys = self.n_keys
         s.keys_ref_un = _ptr(self.keys_ref_un, _f32p)
         s.keys_ref = _ptr(self.keys_ref, _f32p)

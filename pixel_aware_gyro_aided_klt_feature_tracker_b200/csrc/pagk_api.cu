@@ -65,6 +65,8 @@ struct pagk_handle {
   cudaStream_t stream = nullptr;
   bool own_stream = true;
   bool ran_stages = true;      // whether the last run recorded them
+  int cur_pairs = 0;           // pairs whose CURRENT-image slot holds a finished pyramid (of geometry `geom`) from the last run
+  bool cont = false;           // the uploaded batch continues streams: its reference images are the previous current ones
   int stage_timing = 1;        // CUDA events between the kernels of a run (pagk_set_stage_timing)
   cudaStream_t aux = nullptr;  // the gyro prediction runs here, beside the pyramid build (independent kernels)
   cudaEvent_t ev_aux = nullptr;
@@ -191,6 +193,30 @@ int upload_images(pagk_handle *h, int n_pairs, const uint8_t *const *refs, const
     CU(cudaMemcpy2DAsync(h->d_images + (size_t)(2 * p + 1) * g.slot_bytes + g.lv[0].offset, width, curs[p], pitches[p],
                          width, height, cudaMemcpyHostToDevice, h->stream));
   }
+  return PAGK_OK;
+}
+
+// Stream continuation: the reference image of pair p is the current image of pair p of the previous batch, whose pyramid
+// is still on the device.  One device-to-device copy moves every current slot (all levels) into its reference slot; only
+// the new current images cross PCIe.
+int upload_images_continue(pagk_handle *h, int n_pairs, const uint8_t *const *curs, int width, int height, const int *pitches) {
+  const PagkGeom &g = h->geom;
+  const size_t img_bytes = (size_t)width * height;
+  CU(cudaMemcpy2DAsync(h->d_images, 2 * g.slot_bytes, h->d_images + g.slot_bytes, 2 * g.slot_bytes, g.slot_bytes, (size_t)n_pairs,
+                       cudaMemcpyDeviceToDevice, h->stream));
+  bool contiguous = true;
+  for (int p = 0; p < n_pairs && contiguous; ++p) {
+    if (pitches[p] != width) contiguous = false;
+    if (p + 1 < n_pairs && curs[p + 1] != curs[p] + img_bytes) contiguous = false;
+  }
+  if (contiguous && n_pairs > 0) {
+    CU(cudaMemcpy2DAsync(h->d_images + g.slot_bytes + g.lv[0].offset, 2 * g.slot_bytes, curs[0], img_bytes, img_bytes, (size_t)n_pairs,
+                         cudaMemcpyHostToDevice, h->stream));
+    return PAGK_OK;
+  }
+  for (int p = 0; p < n_pairs; ++p)
+    CU(cudaMemcpy2DAsync(h->d_images + (size_t)(2 * p + 1) * g.slot_bytes + g.lv[0].offset, width, curs[p], pitches[p], width,
+                         height, cudaMemcpyHostToDevice, h->stream));
   return PAGK_OK;
 }
 
@@ -389,8 +415,18 @@ int pagk_upload_batch(pagk_handle *h, const pagk_params *prm, int n_pairs, const
   const int half = prm->half_patch == 0 ? 5 : prm->half_patch;  // Initialize(), :61
   if (n_pairs == 0) { h->n_pairs = 0; h->resident = true; return PAGK_OK; }
   const int W = in[0].width, H = in[0].height;
+  // img_ref == NULL on every pair: the batch continues the streams of the previous batch of this handle
+  int n_null = 0;
+  for (int p = 0; p < n_pairs; ++p) n_null += in[p].img_ref ? 0 : 1;
+  const bool cont = n_null == n_pairs;
+  if (n_null != 0 && !cont) return fail(PAGK_ERR_INVALID, "img_ref: null on every pair of the batch (stream continuation) or on none");
+  const PagkGeom prev = h->geom;
   int rc = check_batch(h, n_pairs, W, H, prm->pyramids, half);
   if (rc != PAGK_OK) return rc;
+  if (cont && (h->cur_pairs < n_pairs || prev.width != h->geom.width || prev.height != h->geom.height || prev.levels != h->geom.levels)) {
+    h->cur_pairs = 0;
+    return fail(PAGK_ERR_INVALID, "stream continuation without a previous batch of the same geometry and at least as many pairs");
+  }
   if (prm->iterations < 0) return fail(PAGK_ERR_INVALID, "iterations < 0");
   fill_mode_common(&m, half, prm->iterations, prm->pyramids, prm->calc_ncc, prm->predict_method, prm->lambda, prm->alpha,
                    prm->max_distance);
@@ -406,7 +442,7 @@ int pagk_upload_batch(pagk_handle *h, const pagk_params *prm, int n_pairs, const
   for (int p = 0; p < n_pairs; ++p) {
     const pagk_pair_in &q = in[p];
     if (q.width != W || q.height != H) return fail(PAGK_ERR_INVALID, "all pairs of a batch must share width and height");
-    if (!q.img_ref || !q.img_cur || q.pitch < W) return fail(PAGK_ERR_INVALID, "bad image pointer or pitch");
+    if ((!cont && !q.img_ref) || !q.img_cur || q.pitch < W) return fail(PAGK_ERR_INVALID, "bad image pointer or pitch");
     if (q.n_keys < 0 || q.n_keys > h->cfg.max_keys) return fail(PAGK_ERR_INVALID, "n_keys exceeds pagk_config.max_keys");
     if (q.n_keys > 0 && !q.keys_ref_un) return fail(PAGK_ERR_INVALID, "keys_ref_un is null");
     if (!m.gyro_init && q.n_keys > 0 && !q.keys_ref) return fail(PAGK_ERR_INVALID, "eType 5 reads keys_ref");
@@ -434,8 +470,11 @@ int pagk_upload_batch(pagk_handle *h, const pagk_params *prm, int n_pairs, const
       if (in[p].normalize_table)
         CU(cudaMemcpyAsync(h->d_ntab + (size_t)p * h->ntab_stride, in[p].normalize_table, per * sizeof(float), cudaMemcpyHostToDevice, h->stream));
   }
-  rc = upload_images(h, n_pairs, refs.data(), curs.data(), W, H, pitches.data());
+  rc = cont ? upload_images_continue(h, n_pairs, curs.data(), W, H, pitches.data())
+            : upload_images(h, n_pairs, refs.data(), curs.data(), W, H, pitches.data());
   if (rc != PAGK_OK) return rc;
+  h->cont = cont;
+  if (!cont) h->cur_pairs = 0;  // until the run has rebuilt them
   h->mode = m; h->n_pairs = n_pairs; h->n_max = n_max; h->e_type = prm->e_type;
   h->resident = true;
   return PAGK_OK;
@@ -449,6 +488,7 @@ int pagk_run_resident(pagk_handle *h) {
   const PagkOutPtrs o = h->outs();
   cudaStream_t st = h->stream;
   const bool lk = (h->e_type != PAGK_GYRO_PREDICT);
+  if (!lk) h->cur_pairs = 0;  // no pyramids are built: nothing a later batch could continue from
   CU(cudaEventRecord(h->ev[0], st));
   // stage clocks off: no event sits between two kernels (the whole device time is booked on the patch alignment)
   const bool stages = h->stage_timing != 0;
@@ -461,7 +501,10 @@ int pagk_run_resident(pagk_handle *h) {
     CU((cudaError_t)pagk_launch_predict(h->d_pc, h->d_keys_un, h->d_keys, o, h->mode, h->cfg.max_keys, h->n_max, h->n_pairs,
                                         h->geom.width, h->geom.height, h->d_ntab, h->ntab_stride, h->aux, &h->launches));
     CU(cudaEventRecord(h->ev_aux, h->aux));
-    CU((cudaError_t)pagk_launch_pyramids(h->d_images, h->geom, 2 * h->n_pairs, st, &h->launches));
+    // a stream continuation already has the reference pyramids (copied from the previous current ones at upload)
+    if (h->cont) CU((cudaError_t)pagk_launch_pyramids(h->d_images + h->geom.slot_bytes, h->geom, h->n_pairs, 2, st, &h->launches));
+    else CU((cudaError_t)pagk_launch_pyramids(h->d_images, h->geom, 2 * h->n_pairs, 1, st, &h->launches));
+    h->cur_pairs = h->n_pairs;
     if (stages) CU(cudaEventRecord(h->ev[1], st));
     CU(cudaStreamWaitEvent(st, h->ev_aux, 0));
   } else {
@@ -687,7 +730,8 @@ int pagk_build_pyramids(pagk_handle *h, int n_images, const uint8_t *const *imgs
     CU(cudaMemcpy2DAsync(h->d_images + (size_t)i * h->geom.slot_bytes + h->geom.lv[0].offset, width, imgs[i], pitch, width,
                          height, cudaMemcpyHostToDevice, h->stream));
   }
-  CU((cudaError_t)pagk_launch_pyramids(h->d_images, h->geom, n_images, h->stream, &h->launches));
+  h->cur_pairs = 0;
+  CU((cudaError_t)pagk_launch_pyramids(h->d_images, h->geom, n_images, 1, h->stream, &h->launches));
   CU(cudaStreamSynchronize(h->stream));
   return PAGK_OK;
 }
@@ -808,7 +852,8 @@ int pagk_patch_match(pagk_handle *h, const pagk_patch_match_in *in, pagk_pair_ou
   h->mode = m; h->n_pairs = 1; h->n_max = in->n_keys; h->e_type = PAGK_GYRO_PREDICT_WITH_OPTICAL_FLOW_REFINED;
   h->ran_stages = true;
   CU(cudaEventRecord(h->ev[0], st));
-  CU((cudaError_t)pagk_launch_pyramids(h->d_images, h->geom, 2, st, &h->launches));
+  h->cur_pairs = 0;
+  CU((cudaError_t)pagk_launch_pyramids(h->d_images, h->geom, 2, 1, st, &h->launches));
   CU(cudaEventRecord(h->ev[1], st));
   CU(cudaEventRecord(h->ev[2], st));
   CU((cudaError_t)launch_lk(h, o, m, in->n_keys, 1));

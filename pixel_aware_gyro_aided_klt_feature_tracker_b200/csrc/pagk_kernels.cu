@@ -35,9 +35,10 @@ __device__ __forceinline__ unsigned int pagk_avg4x8(unsigned int r0, unsigned in
 }
 
 __global__ void __launch_bounds__(256) pagk_pyramid_fused_kernel(unsigned char *__restrict__ images, PagkGeom g,
-                                                               int n_fused /* last level produced here */) {
+                                                               int n_fused /* last level produced here */,
+                                                               int z_stride /* image z lives in slot z * z_stride */) {
   __shared__ __align__(16) unsigned char sbuf[2][(PYR_TW / 2) * (PYR_TH / 2)];
-  unsigned char *img = images + (size_t)blockIdx.z * g.slot_bytes;
+  unsigned char *img = images + (size_t)blockIdx.z * z_stride * g.slot_bytes;
   const int t = threadIdx.x;
   const int cols0 = g.lv[0].cols, rows0 = g.lv[0].rows;
   unsigned char *l0 = img + g.lv[0].offset;
@@ -126,8 +127,8 @@ __global__ void __launch_bounds__(256) pagk_pyramid_fused_kernel(unsigned char *
 // General half-size cv::resize(INTER_LINEAR) for levels whose source has an odd dimension: the
 // 11-bit fixed-point bilinear of OpenCV.  One thread per output pixel.
 __global__ void __launch_bounds__(256) pagk_pyramid_general_kernel(unsigned char *__restrict__ images, PagkGeom g,
-                                                                 int level) {
-  unsigned char *img = images + (size_t)blockIdx.z * g.slot_bytes;
+                                                                 int level, int z_stride) {
+  unsigned char *img = images + (size_t)blockIdx.z * z_stride * g.slot_bytes;
   const int scols = g.lv[level - 1].cols, srows = g.lv[level - 1].rows;
   const int dcols = g.lv[level].cols, drows = g.lv[level].rows;
   const unsigned char *src = img + g.lv[level - 1].offset;
@@ -724,7 +725,8 @@ int pagk_pyramid_fused_max_level() {
   return l;
 }
 
-int pagk_launch_pyramids(unsigned char *images, const PagkGeom &g, int n_images, cudaStream_t st, long long *launches) {
+int pagk_launch_pyramids(unsigned char *images, const PagkGeom &g, int n_images, int z_stride, cudaStream_t st,
+                         long long *launches) {
   // levels 1..n_fused form the exact-2x chain and come out of the fused kernel
   int n_fused = 0;
   for (int l = 1; l < g.levels; ++l) {
@@ -732,11 +734,11 @@ int pagk_launch_pyramids(unsigned char *images, const PagkGeom &g, int n_images,
     else break;
   }
   dim3 grid((g.lv[0].cols + PYR_TW - 1) / PYR_TW, (g.lv[0].rows + PYR_TH - 1) / PYR_TH, n_images);
-  pagk_pyramid_fused_kernel<<<grid, 256, 0, st>>>(images, g, n_fused);
+  pagk_pyramid_fused_kernel<<<grid, 256, 0, st>>>(images, g, n_fused, z_stride);
   ++*launches;
   for (int l = n_fused + 1; l < g.levels; ++l) {
     dim3 gg((g.lv[l].cols + 255) / 256, g.lv[l].rows, n_images);
-    pagk_pyramid_general_kernel<<<gg, 256, 0, st>>>(images, g, l);
+    pagk_pyramid_general_kernel<<<gg, 256, 0, st>>>(images, g, l, z_stride);
     ++*launches;
   }
   return (int)cudaGetLastError();

@@ -3,7 +3,9 @@
 #include "pagk_device.cuh"
 
 int pagk_pyramid_fused_max_level();
-int pagk_launch_pyramids(unsigned char *images, const PagkGeom &g, int n_images, cudaStream_t st, long long *launches);
+// image z of the launch lives in slot z * z_stride (1: every slot, 2: every other one, i.e. only the current images)
+int pagk_launch_pyramids(unsigned char *images, const PagkGeom &g, int n_images, int z_stride, cudaStream_t st,
+                         long long *launches);
 int pagk_launch_predict(const PagkPairConst *pcs, const float2 *keys_un, const float2 *keys, const PagkOutPtrs &out,
                         const PagkMode &mode, int max_keys, int n_max, int n_pairs, int width, int height,
                         const float *ntab, unsigned long long ntab_stride, cudaStream_t st, long long *launches);

@@ -150,6 +150,51 @@ def make_pair(seed: int, width: int = 752, height: int = 480, n_keys: int = 1024
     return PairInputs(ref, cur, keys, imu_t, imu_w.astype(np.float32), t_ref, t_cur, K, Rbc, dist=d, n_dist=d.size)
 
 
+def make_sequence(seed: int, n_frames: int, width: int = 752, height: int = 480, n_keys: int = 1024, half_patch: int = 5,
+                  pyramids: int = 4, fps: float = 20.0, sigma_w: float = 0.5, K=None, Rbc=None, imu_rate: float = 200.0,
+                  border: int | None = None, margin: int = 64, **_unused):
+    """One camera + IMU stream: frame 0 and n_frames - 1 consecutive pairs (frame t-1 -> frame t) of one rotating camera over
+    one texture.  Returns (frames, pairs): pairs[t-1] is the PairInputs of (frames[t-1], frames[t]) with fresh keypoints on
+    frames[t-1], as a driver that re-detects every frame would hand them over."""
+    rng = np.random.default_rng(seed)
+    K = scaled_euroc_K(width) if K is None else np.asarray(K, np.float32)
+    Rbc = EUROC_RBC if Rbc is None else np.asarray(Rbc, np.float32)
+    K64, Rbc64 = K.astype(np.float64), Rbc.astype(np.float64)
+    Kinv = np.linalg.inv(K64)
+    canvas = texture(rng, height, width, margin)
+    ys, xs = np.mgrid[0:height, 0:width].astype(np.float64)
+    dt = 1.0 / fps
+    if border is None:
+        border = 8 * (half_patch + 3) if pyramids >= 4 else 4 * (half_patch + 3)
+        border = min(border, min(width, height) // 4)
+    R_acc = np.eye(3)                       # camera rotation of frame t relative to frame 0: p_t ~ K R_acc K^-1 p_0
+    frames, pairs = [], []
+    t0 = 1403715000.0 + seed * 0.05
+    for t in range(n_frames):
+        Hl0 = np.linalg.inv(K64 @ R_acc @ Kinv)
+        den = Hl0[2, 0] * xs + Hl0[2, 1] * ys + Hl0[2, 2]
+        sx = (Hl0[0, 0] * xs + Hl0[0, 1] * ys + Hl0[0, 2]) / den + margin
+        sy = (Hl0[1, 0] * xs + Hl0[1, 1] * ys + Hl0[1, 2]) / den + margin
+        img = _bilinear(canvas, sx, sy) * rng.uniform(0.95, 1.05) + rng.uniform(-4.0, 4.0) + rng.normal(0.0, 1.0, (height, width))
+        frames.append(np.clip(np.rint(img), 0, 255).astype(np.uint8))
+        if t + 1 == n_frames:
+            break
+        w_body = rng.normal(0.0, sigma_w, 3)
+        Rcl = Rbc64.T @ so3_exp(w_body * dt).T @ Rbc64
+        t_ref, t_cur = t0 + t * dt, t0 + (t + 1) * dt
+        off = rng.uniform(0.0, 0.005)
+        imu_t = t_ref - off + np.arange(int(np.ceil(dt * imu_rate)) + 2) / imu_rate
+        while imu_t[-1] < t_cur:
+            imu_t = np.append(imu_t, imu_t[-1] + 1.0 / imu_rate)
+        imu_w = w_body[None, :] + rng.normal(0.0, 1.7e-4 * np.sqrt(imu_rate), (imu_t.size, 3))
+        keys = random_keypoints(rng, n_keys, width, height, border)
+        pairs.append(dict(keys=keys, imu_t=imu_t, imu_w=imu_w.astype(np.float32), t_ref=t_ref, t_cur=t_cur))
+        R_acc = Rcl @ R_acc
+    out = [PairInputs(frames[k], frames[k + 1], q["keys"], q["imu_t"], q["imu_w"], q["t_ref"], q["t_cur"], K, Rbc)
+           for k, q in enumerate(pairs)]
+    return frames, out
+
+
 def make_config_pairs(name: str, n_pairs: int | None = None, seed0: int | None = None, **override):
     cfg = dict(CONFIGS[name])
     cfg.update(override)

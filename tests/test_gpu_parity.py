@@ -368,3 +368,49 @@ def test_stage_timing_off_changes_only_the_clocks(gpu_ctx):
     assert t_on["pyramid"] > 0 and t_on["lk"] > 0 and t_on["filter"] > 0
     assert t_off["pyramid"] == 0 and t_off["predict"] == 0 and t_off["filter"] == 0 and t_off["lk"] == t_off["total"] > 0
     assert off[0].struct.t_gyro_predict == 0 and off[0].struct.t_opt_flow > 0
+
+
+def test_stream_continuation_reuses_the_previous_current_pyramid(gpu_ctx, oracle):
+    """img_ref = NULL on every pair: frame t is tracked against frame t-1 of the same stream, whose pyramid stays on the device
+    (only the new image is uploaded, only its pyramid is built).  Three streams, five frames: every step bit-exact against the
+    restatement run on the explicit pair, and against the pairwise call."""
+    import copy
+    seqs = [synth.make_sequence(8800 + s, 5, width=320, height=240, n_keys=200, pyramids=3, border=20) for s in range(3)]
+    prm = capi.default_params(pyramids=3)
+    for t in range(4):
+        pairs = [seq[1][t] for seq in seqs]
+        if t == 0:
+            got = gpu_ctx.track_batch(pairs, prm)                 # the first pair of a stream brings both images
+        else:
+            cont = []
+            for p in pairs:
+                q = copy.copy(p)
+                q.img_ref = None
+                cont.append(q)
+            got = gpu_ctx.track_batch(cont, prm)
+        rc, cpu = oracle.track_batch(pairs, prm, 4)
+        assert rc == 0
+        for g, c in zip(got, cpu):
+            helpers.assert_bit_exact(g, c)
+        gpu_ctx._pyr_wh = (320, 240)
+        for lvl in range(3):                                        # the pyramids on the device are those of this step's pair
+            assert np.array_equal(gpu_ctx.pyramid_level(0, lvl), oracle.pyramid_level(pairs[0].img_ref, lvl))
+            assert np.array_equal(gpu_ctx.pyramid_level(5, lvl), oracle.pyramid_level(pairs[2].img_cur, lvl))
+
+
+def test_stream_continuation_needs_a_previous_batch(cuda_lib):
+    from pixel_aware_gyro_aided_klt_feature_tracker_b200 import tracker
+    import copy
+    p = synth.make_pair(8900, width=160, height=120, n_keys=20, pyramids=3, border=12, margin=32)
+    q = copy.copy(p)
+    q.img_ref = None
+    prm = capi.default_params(pyramids=3)
+    with tracker.Context(max_width=160, max_height=120, max_keys=32, max_pairs=2, max_levels=3) as ctx:
+        with pytest.raises(tracker.PagkError):
+            ctx.track_batch([q], prm)                              # nothing to continue from
+        ctx.track_batch([p], prm)
+        ctx.track_batch([q], prm)                                  # fine now
+        with pytest.raises(tracker.PagkError):
+            ctx.track_batch([q, q], prm)                           # more streams than the previous batch had
+        with pytest.raises(tracker.PagkError):
+            ctx.track_batch([p, q], prm)                           # mixed
