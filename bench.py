@@ -211,6 +211,75 @@ def run_reference(args, rank, world):
     emit(line)
 
 
+def stream_leg(args, cfg, prm, n_streams, new_ctx, barrier, world):
+    """End to end over camera streams: every handle owns n_streams streams; a step uploads ONE new frame per stream (img_ref =
+    NULL: the previous current image and its pyramid are on the device), keypoints and gyro, and reads the results back."""
+    from concurrent.futures import ThreadPoolExecutor
+    import torch
+    steps = args.e2e_steps or max(3, min(args.steps, 30))
+    per_handle = -(-(steps + E2E_DEPTH + 2) // E2E_DEPTH)        # continuation steps each handle plays (warm-up included)
+    T = per_handle + 2
+    H, W, N = cfg["height"], cfg["width"], cfg["n_keys"]
+    n_distinct = min(n_streams, 8)                               # distinct synthetic streams; the others replay them
+    kw = {k: v for k, v in cfg.items() if k not in ("pairs",)}
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        seqs = list(ex.map(lambda i: synth.make_sequence(40000 + i, T, **kw), range(n_distinct)))
+    frames = pinned((T, n_streams, H, W), np.uint8)
+    keys = pinned((T - 1, n_streams, N, 2), np.float32)
+    for s_ in range(n_streams):
+        fr, prs = seqs[s_ % n_distinct]
+        for t in range(T):
+            frames[t, s_] = fr[t]
+        for t in range(T - 1):
+            keys[t, s_] = prs[t].keys_ref_un
+    def batch(t, cont):
+        prs = [seqs[s_ % n_distinct][1][t] for s_ in range(n_streams)]
+        return [capi.PairInputs(None if cont else frames[t, s_], frames[t + 1, s_], keys[t, s_], q.imu_t, q.imu_w, q.t_ref, q.t_cur,
+                                q.K, q.Rbc) for s_, q in enumerate(prs)]
+    ctxs = [new_ctx() for _ in range(E2E_DEPTH)]
+    oblocks = [OutBlock(n_streams, N) for _ in range(E2E_DEPTH)]
+    oarrs = [capi.make_out_array(ob.outs) for ob in oblocks]
+    for c in ctxs:
+        c.set_stage_timing(False)
+    keep = [batch(0, False)] + [batch(t, True) for t in range(1, T - 1)]
+    ins = [capi.make_in_array(b) for b in keep]
+    pos = [0] * E2E_DEPTH                                        # next frame pair of each handle's streams
+    inflight = [False] * E2E_DEPTH
+
+    def run_steps(k0, k1):
+        for k in range(k0, k1):
+            j = k % E2E_DEPTH
+            if inflight[j]:
+                ctxs[j].wait()
+            ctxs[j].submit_prepared(prm, ins[pos[j]], oarrs[j], n_streams)
+            pos[j] += 1
+            inflight[j] = True
+
+    def drain():
+        for j in range(E2E_DEPTH):
+            if inflight[j]:
+                ctxs[j].wait()
+                inflight[j] = False
+    warm = E2E_DEPTH + 2          # every handle has its first (two-image) batch behind it: all timed steps are continuations
+    run_steps(0, warm)
+    drain()
+    barrier()
+    t0 = time.perf_counter()
+    run_steps(warm, warm + steps)
+    drain()
+    torch.cuda.synchronize()
+    dte = sharding.reduce_time_max(time.perf_counter() - t0)
+    tracked = int(sum(int(o.n_predict) for o in oarrs[0][:n_streams]))
+    h2d = int(frames[0].nbytes + keys[0].nbytes + n_streams * 96)
+    res = {"value": world * steps * n_streams * N / dte, "unit": "features/s", "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": int(oblocks[0].nbytes + n_streams * 24), "steps": steps, "streams_per_step": n_streams,
+           "tracked_in_last_step_of_handle_0": tracked,
+           "api": f"pagk_submit_batch/pagk_wait_batch with img_ref = NULL (stream continuation) over {E2E_DEPTH} handles"}
+    for c in ctxs:
+        c.close()
+    return res
+
+
 def workload_name(name, cfg, n_pairs):
     return (f"config {name}: {cfg['width']}x{cfg['height']}, {cfg['n_keys']} features/pair, {cfg['pyramids']} levels, "
             f"{2 * cfg['half_patch'] + 1}x{2 * cfg['half_patch'] + 1} patch, eType 4, {n_pairs} frame pairs/step")
@@ -227,6 +296,9 @@ def main():
     ap.add_argument("--ref-pairs", type=int, default=8, help="frame pairs per step of the CPU reference arm")
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity leg")
+    ap.add_argument("--stream", action="store_true",
+                    help="extra leg `e2e_stream`: the same end-to-end pipeline over camera streams (BASELINE config D's unit): each "
+                         "step tracks frame t against frame t-1 of every stream, whose pyramid stayed on the device")
     args = ap.parse_args()
 
     claim_stdout()
@@ -353,6 +425,8 @@ def main():
     h2d = int(b0["imgs"].nbytes + b0["keys"].nbytes + n_pairs * 96)
     d2h = int(oblocks[0].nbytes + n_pairs * 24)
 
+    e2e_stream = stream_leg(args, cfg, prm, n_pairs, new_ctx, barrier, world) if args.stream else None
+
     if world > 1:
         dist.barrier()
     if rank != 0:
@@ -420,6 +494,8 @@ def main():
                     "steps": e2e_steps, "results_ok": bool(e2e_ok),
                     "api": f"pagk_submit_batch/pagk_wait_batch over {E2E_DEPTH} handles (pinned host buffers in and out, pagk_set_stage_timing off)"},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity}
+    if e2e_stream is not None:
+        line["e2e_stream"] = e2e_stream
     emit(line)
     for c in (ctxs + ectx)[::-1]:   # borrowers of a shared stream before its owner
         c.close()
