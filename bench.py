@@ -216,6 +216,7 @@ def stream_leg(args, cfg, prm, n_streams, new_ctx, barrier, world):
     NULL: the previous current image and its pyramid are on the device), keypoints and gyro, and reads the results back."""
     from concurrent.futures import ThreadPoolExecutor
     import torch
+    from pixel_aware_gyro_aided_klt_feature_tracker_b200 import sharding
     steps = args.e2e_steps or max(3, min(args.steps, 30))
     per_handle = -(-(steps + E2E_DEPTH + 2) // E2E_DEPTH)        # continuation steps each handle plays (warm-up included)
     T = per_handle + 2

@@ -237,8 +237,12 @@ int launch_lk_kernel(pagk_handle *h, const PagkOutPtrs &o, const PagkMode &m, in
   if (h->lk_kernel == 0 && pagk_lk_lanes_supported(m)) {
     // PAGK_LK_TIMELINE=<file> with a -DPAGK_LANES_PROF build: per-warp phase cycles (developer aid)
     if (h->d_dbg) cudaMemsetAsync(h->d_dbg, 0, 2048 * 8 * sizeof(long long), h->stream);
+    if (++h->lk_epoch >= 0x0fffffff) {  // the epoch is about to repeat: forget every progress word written so far
+      cudaMemsetAsync(h->d_progress, 0, (size_t)h->cfg.max_pairs * h->cfg.max_keys * sizeof(int), h->stream);
+      h->lk_epoch = 1;
+    }
     const int rc = pagk_launch_lk_lanes(h->d_images, h->geom, h->d_pc, h->d_keys_un, o, m, h->cfg.max_keys, n_max, n_pairs,
-                                        h->d_work + 16, h->lk_parity, h->d_progress, (++h->lk_epoch) & 0x0fffffff, h->n_sms,
+                                        h->d_work + 16, h->lk_parity, h->d_progress, h->lk_epoch, h->n_sms,
                                         h->stream, &h->launches, h->d_dbg);
     if (rc == 0 && n_max > 0 && n_pairs > 0) h->lk_parity ^= 1;
     if (h->d_dbg && rc == 0) {
@@ -474,7 +478,7 @@ int pagk_upload_batch(pagk_handle *h, const pagk_params *prm, int n_pairs, const
             : upload_images(h, n_pairs, refs.data(), curs.data(), W, H, pitches.data());
   if (rc != PAGK_OK) return rc;
   h->cont = cont;
-  if (!cont) h->cur_pairs = 0;  // until the run has rebuilt them
+  h->cur_pairs = 0;  // until the run has built the new current pyramids
   h->mode = m; h->n_pairs = n_pairs; h->n_max = n_max; h->e_type = prm->e_type;
   h->resident = true;
   return PAGK_OK;
