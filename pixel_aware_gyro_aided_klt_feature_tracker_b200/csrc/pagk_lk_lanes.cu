@@ -671,7 +671,7 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
           const size_t o = (size_t)feat;
           __stcg(&out.pm_un[o], make_float2(p2x, p2y));
           __stcg(&out.iters[o], n_iter);
-          __threadfence();
+          // release at gpu scope: the two stores above are visible to whoever acquires this word
           asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(progress + o), "r"(epoch_base + (top - level + 1)) : "memory");
           feat = -1;
         } else {
