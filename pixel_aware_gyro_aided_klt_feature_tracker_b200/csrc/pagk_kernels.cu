@@ -34,7 +34,41 @@ __device__ __forceinline__ unsigned int pagk_avg4x8(unsigned int r0, unsigned in
   return (a >> 2) | ((b >> 2) << 8);
 }
 
-__global__ void __launch_bounds__(256) pagk_pyramid_fused_kernel(unsigned char *__restrict__ images, PagkGeom g,
+// One more level of a tile: the TW x TH tile of level l-1 in shared memory `s` -> its (TW/2) x (TH/2) tile of level l,
+// to shared memory `d` and to the image; then recurses to level l+1.  All index arithmetic is shifts and masks.
+template <int TW, int TH>
+__device__ __forceinline__ void pagk_pyramid_tile_level(const unsigned char *s, unsigned char *d, unsigned char *img,
+                                                        const PagkGeom &g, int l, int n_fused, int tx0, int ty0, int t) {
+  constexpr int OW = TW / 2, OH = TH / 2;
+  if constexpr (OW >= 1 && OH >= 1) {
+    __syncthreads();
+    const int colsl = g.lv[l].cols, rowsl = g.lv[l].rows;
+    unsigned char *ll = img + g.lv[l].offset;
+    const int ox0 = tx0 >> l, oy0 = ty0 >> l;
+#pragma unroll
+    for (int p = t; p < OW * OH; p += 256) {
+      const int ox = p % OW, oy = p / OW;  // OW is a power of two: a mask and a shift
+      const unsigned char *q = s + (2 * oy) * TW + 2 * ox;
+      const unsigned int r0 = *reinterpret_cast<const unsigned short *>(q), r1 = *reinterpret_cast<const unsigned short *>(q + TW);
+      const unsigned char v = (unsigned char)(((r0 & 0xffu) + (r0 >> 8) + (r1 & 0xffu) + (r1 >> 8) + 2u) >> 2);
+      d[oy * OW + ox] = v;
+      const int gx = ox0 + ox, gy = oy0 + oy;
+      if (gx < colsl && gy < rowsl) {
+        ll[(size_t)gy * colsl + gx] = v;
+        if (gy == rowsl - 1) {
+          ll[(size_t)rowsl * colsl + gx] = v;
+          if (gx == 0) ll[(size_t)(rowsl + 1) * colsl] = v;
+        }
+      }
+    }
+    if (l < n_fused) pagk_pyramid_tile_level<OW, OH>(d, const_cast<unsigned char *>(s), img, g, l + 1, n_fused, tx0, ty0, t);
+  }
+}
+
+#ifndef PAGK_PYR_MIN_BLOCKS
+#define PAGK_PYR_MIN_BLOCKS 8
+#endif
+__global__ void __launch_bounds__(256, PAGK_PYR_MIN_BLOCKS) pagk_pyramid_fused_kernel(unsigned char *__restrict__ images, PagkGeom g,
                                                                int n_fused /* last level produced here */,
                                                                int z_stride /* image z lives in slot z * z_stride */) {
   __shared__ __align__(16) unsigned char sbuf[2][(PYR_TW / 2) * (PYR_TH / 2)];
@@ -95,33 +129,8 @@ __global__ void __launch_bounds__(256) pagk_pyramid_fused_kernel(unsigned char *
       }
     }
   }
-  // ---- level l-1 (shared memory) -> level l, l = 2 .. n_fused
-  int tw = PYR_TW / 2, th = PYR_TH / 2, cur = 0;
-  for (int l = 2; l <= n_fused; ++l) {
-    __syncthreads();
-    const int ow = tw >> 1, oh = th >> 1;
-    if (ow == 0 || oh == 0) break;  // host never asks for more than the tile can give
-    const int colsl = g.lv[l].cols, rowsl = g.lv[l].rows;
-    unsigned char *ll = img + g.lv[l].offset;
-    const unsigned char *s = sbuf[cur];
-    unsigned char *d = sbuf[cur ^ 1];
-    const int ox0 = tx0 >> l, oy0 = ty0 >> l;
-    for (int p = t; p < ow * oh; p += 256) {
-      const int ox = p % ow, oy = p / ow;
-      const unsigned char *q = s + (2 * oy) * tw + 2 * ox;
-      const unsigned char v = (unsigned char)((q[0] + q[1] + q[tw] + q[tw + 1] + 2) >> 2);
-      d[oy * ow + ox] = v;
-      const int gx = ox0 + ox, gy = oy0 + oy;
-      if (gx < colsl && gy < rowsl) {
-        ll[(size_t)gy * colsl + gx] = v;
-        if (gy == rowsl - 1) {
-          ll[(size_t)rowsl * colsl + gx] = v;
-          if (gx == 0) ll[(size_t)(rowsl + 1) * colsl] = v;
-        }
-      }
-    }
-    tw = ow; th = oh; cur ^= 1;
-  }
+  // ---- level l-1 (shared memory) -> level l, l = 2 .. n_fused: tile sizes are compile-time constants
+  if (n_fused >= 2) pagk_pyramid_tile_level<PYR_TW / 2, PYR_TH / 2>(sbuf[0], sbuf[1], img, g, 2, n_fused, tx0, ty0, t);
 }
 
 // General half-size cv::resize(INTER_LINEAR) for levels whose source has an odd dimension: the
