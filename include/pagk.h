@@ -257,6 +257,35 @@ typedef struct pagk_geometry_out {
 
 int pagk_geometry_validation(pagk_handle *h, int n_pairs, const pagk_geometry_in *in, pagk_geometry_out *out);
 
+/* == Frame::SetPredictKeyPointsAndMask() (src/frame.cpp:115-153): the step that turns the surviving predictions of one
+ * frame pair into the reference keypoints of the next one -- compaction in index order of mvKeys / mvKeysUn /
+ * mvKeysNormal / mvPtIndexInLastFrame, the flow velocity of the last frame's features in the normalised plane, and the
+ * occupancy mask (ones, with a 14 x 14 square zeroed around every survivor) that the detector top-up reads.
+ * pt_predict / pt_predict_un / status NULL: the vectors of the handle's last run (or last pagk_geometry_validation),
+ * resident on the device. */
+typedef struct pagk_carry_in {
+  int n_keys;                    /* mvStatus.size() */
+  const float *pt_predict;       /* mvPtPredict    [n_keys][2] */
+  const float *pt_predict_un;    /* mvPtPredictUn  [n_keys][2] */
+  const uint8_t *status;         /* mvStatus       [n_keys]    */
+  const float *keys_normal_last; /* mpLastFrame->mvKeysNormal[i].pt [n_keys][2] */
+  float fx, fy, cx, cy;          /* mfx, mfy, mcx, mcy (mfx_inv = 1.0 / mfx as the Frame constructor computes it) */
+  double t_cur, t_last;          /* mTimeStamp, mpLastFrame->mTimeStamp */
+  int width, height;             /* mpCameraParams->width / height = size of mMask */
+} pagk_carry_in;
+
+typedef struct pagk_carry_out {
+  int n_out;                 /* survivors = size of the four vectors below */
+  float *keys;               /* mvKeys[k].pt        [n_keys][2] capacity */
+  float *keys_un;            /* mvKeysUn[k].pt */
+  float *keys_normal;        /* mvKeysNormal[k].pt */
+  int32_t *index_in_last;    /* mvPtIndexInLastFrame[k] */
+  float *flow_velocity_last; /* mpLastFrame->mvFlowVelocityInNormalPlane[k] */
+  uint8_t *mask;             /* mMask, height x width, or NULL */
+} pagk_carry_out;
+
+int pagk_set_predict_keypoints_and_mask(pagk_handle *h, int n_pairs, const pagk_carry_in *in, pagk_carry_out *out);
+
 #ifdef __cplusplus
 }
 #endif

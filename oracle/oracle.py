@@ -51,6 +51,7 @@ def load():
         lib.pagk_oracle_track_batch.argtypes = [C.POINTER(capi.PagkParams), C.c_int, C.POINTER(capi.PagkPairIn),
                                                 C.POINTER(capi.PagkPairOut), C.c_int]
         lib.pagk_oracle_geometry_validation.argtypes = [C.c_int, C.POINTER(capi.PagkGeometryIn), C.POINTER(capi.PagkGeometryOut)]
+        lib.pagk_oracle_set_predict_keypoints_and_mask.argtypes = [C.c_int, C.POINTER(capi.PagkCarryIn), C.POINTER(capi.PagkCarryOut)]
         _lib = lib
     return _lib
 
@@ -130,6 +131,16 @@ def geometry_validation(cases):
         ins[k], outs[k] = c.structs()
     rc = load().pagk_oracle_geometry_validation(len(cases), ins, outs)
     return rc, list(outs)
+
+
+def set_predict_keypoints_and_mask(cases):
+    """Frame::SetPredictKeyPointsAndMask(); returns (rc, [n_out]); the vectors land in each case's arrays"""
+    ins = (capi.PagkCarryIn * len(cases))()
+    outs = (capi.PagkCarryOut * len(cases))()
+    for k, c in enumerate(cases):
+        ins[k], outs[k] = c.structs()
+    rc = load().pagk_oracle_set_predict_keypoints_and_mask(len(cases), ins, outs)
+    return rc, [int(o.n_out) for o in outs]
 
 
 def track(pair: capi.PairInputs, params: capi.PagkParams, n_threads: int = 1):

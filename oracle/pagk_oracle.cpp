@@ -856,6 +856,39 @@ void geometry_validation(const pagk_geometry_in &in, pagk_geometry_out *out) {
   if (out->status) memcpy(out->status, st.data(), (size_t)in.n_keys);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Frame::SetPredictKeyPointsAndMask, src/frame.cpp:115-153
+// ---------------------------------------------------------------------------------------------
+void set_predict_keypoints_and_mask(const pagk_carry_in &in, pagk_carry_out *out) {
+  const int half_path_size = 7;
+  const float mfx_inv = 1.0 / in.fx, mfy_inv = 1.0 / in.fy;  // Frame ctor, src/frame.cpp:71
+  if (out->mask) memset(out->mask, 1, (size_t)in.width * in.height);
+  int cnt = 0;
+  for (int i = 0; i < in.n_keys; ++i) {
+    if (!in.status[i]) continue;
+    const P2 pt_pred{in.pt_predict[2 * i], in.pt_predict[2 * i + 1]};
+    const P2 pt_pred_un{in.pt_predict_un[2 * i], in.pt_predict_un[2 * i + 1]};
+    P2 pt_pred_normal;
+    pt_pred_normal.x = (pt_pred_un.x - in.cx) * mfx_inv;
+    pt_pred_normal.y = (pt_pred_un.y - in.cy) * mfy_inv;
+    out->keys[2 * cnt] = pt_pred.x; out->keys[2 * cnt + 1] = pt_pred.y;
+    out->keys_un[2 * cnt] = pt_pred_un.x; out->keys_un[2 * cnt + 1] = pt_pred_un.y;
+    out->keys_normal[2 * cnt] = pt_pred_normal.x; out->keys_normal[2 * cnt + 1] = pt_pred_normal.y;
+    out->index_in_last[cnt] = i;
+    const float dnx = pt_pred_normal.x - in.keys_normal_last[2 * i], dny = pt_pred_normal.y - in.keys_normal_last[2 * i + 1];
+    const double dt = in.t_cur - in.t_last;
+    out->flow_velocity_last[2 * cnt] = (float)(dnx / dt);  // cv::Point2f / double: saturate_cast<float>(a.x / b)
+    out->flow_velocity_last[2 * cnt + 1] = (float)(dny / dt);
+    cnt++;
+    if (out->mask) {
+      const int _x = std::min(std::max(0, int(pt_pred_un.x) - half_path_size), in.width - 2 * half_path_size);
+      const int _y = std::min(std::max(0, int(pt_pred_un.y) - half_path_size), in.height - 2 * half_path_size);
+      for (int r = 0; r < 2 * half_path_size; ++r) memset(out->mask + (size_t)(_y + r) * in.width + _x, 0, 2 * half_path_size);
+    }
+  }
+  out->n_out = cnt;
+}
+
 }  // namespace
 
 extern "C" {
@@ -926,6 +959,11 @@ int pagk_oracle_patch_match(const pagk_patch_match_in *in, pagk_pair_out *out, i
 
 int pagk_oracle_geometry_validation(int n_pairs, const pagk_geometry_in *in, pagk_geometry_out *out) {
   for (int p = 0; p < n_pairs; ++p) geometry_validation(in[p], &out[p]);
+  return PAGK_OK;
+}
+
+int pagk_oracle_set_predict_keypoints_and_mask(int n_pairs, const pagk_carry_in *in, pagk_carry_out *out) {
+  for (int p = 0; p < n_pairs; ++p) set_predict_keypoints_and_mask(in[p], &out[p]);
   return PAGK_OK;
 }
 

@@ -1,6 +1,6 @@
 // ref_harness.cpp -- C entry points over the REFERENCE'S OWN hot-path sources.  TEST INFRASTRUCTURE ONLY.
 //
-// oracle/_ref/libpagk_ref.so = this file + /root/reference/src/{gyro_aided_tracker,patch_match,utils}.cpp compiled
+// oracle/_ref/libpagk_ref.so = this file + /root/reference/src/{gyro_aided_tracker,patch_match,utils,frame}.cpp compiled
 // unmodified, where they lie, against the stand-in headers in oracle/ref_shim/ (OpenCV, Eigen3 and glog are not
 // installed here).  See oracle/ref_shim/pagk_cv_shim.hpp for what is real and what is restated.  Only tests/ and
 // bench.py's CPU legs load it; it is the checker for oracle/pagk_oracle.cpp (the restatement that travels to the GPU
@@ -65,10 +65,8 @@ void initUndistortRectifyMap(const Mat &, const Mat &, const Mat &, const Mat &,
 Mat getOptimalNewCameraMatrix(const Mat &, const Mat &, Size, double, Size, void *) { shim_abort("getOptimalNewCameraMatrix"); }
 }  // namespace cv
 
-// Frame's constructors live in src/frame.cpp (ORB extraction, display: not on the path, not compiled).  The tracker
-// only reads public members of the two frames, so an empty Frame is all the harness needs.
-long unsigned int Frame::nNextId = 0;
-Frame::Frame() : mpLastFrame(nullptr), curFrameWithoutGeometryValid(nullptr), mpCameraParams(nullptr) {}
+// src/frame.cpp is compiled too (Frame::SetPredictKeyPointsAndMask lives there); the ORB extractor it can call is not.
+void ORB_SLAM2::ORBextractor::DetectFeatures(cv::InputArray, cv::InputArray, std::vector<cv::KeyPoint> &) { cv::shim_abort("ORBextractor::DetectFeatures"); }
 
 // ------------------------------------------------------------------------------------------------------------------
 namespace {
@@ -328,6 +326,44 @@ int pagk_ref_geometry_validation(int n_pairs, const pagk_geometry_in *in, pagk_g
     if (out[p].status) for (int i = 0; i < gi.n_keys; ++i) out[p].status[i] = t.mvStatus[i];
   }
   pagk_ref_inject_models(nullptr, nullptr);
+  return PAGK_OK;
+}
+
+// Frame::SetPredictKeyPointsAndMask() itself (src/frame.cpp:115-153) on a current and a last Frame filled from the arrays
+int pagk_ref_set_predict_keypoints_and_mask(int n_pairs, const pagk_carry_in *in, pagk_carry_out *out) {
+  for (int p = 0; p < n_pairs; ++p) {
+    const pagk_carry_in &ci = in[p];
+    CameraParams cam;
+    cam.width = ci.width; cam.height = ci.height;
+    Frame last, cur;
+    last.mTimeStamp = ci.t_last; cur.mTimeStamp = ci.t_cur;
+    cur.mpLastFrame = &last; cur.mpCameraParams = &cam; last.mpCameraParams = &cam;
+    cur.mfx = ci.fx; cur.mfy = ci.fy; cur.mcx = ci.cx; cur.mcy = ci.cy;
+    cur.mfx_inv = 1.0 / cur.mfx; cur.mfy_inv = 1.0 / cur.mfy;  // as Frame's constructor computes them (src/frame.cpp:71)
+    last.mvKeysNormal.resize(ci.n_keys);
+    last.mvFlowVelocityInNormalPlane.resize(ci.n_keys);
+    cur.mvStatus.resize(ci.n_keys); cur.mvPtPredict.resize(ci.n_keys); cur.mvPtPredictUn.resize(ci.n_keys);
+    for (int i = 0; i < ci.n_keys; ++i) {
+      last.mvKeysNormal[i].pt = cv::Point2f(ci.keys_normal_last[2 * i], ci.keys_normal_last[2 * i + 1]);
+      cur.mvStatus[i] = ci.status[i];
+      cur.mvPtPredict[i] = cv::Point2f(ci.pt_predict[2 * i], ci.pt_predict[2 * i + 1]);
+      cur.mvPtPredictUn[i] = cv::Point2f(ci.pt_predict_un[2 * i], ci.pt_predict_un[2 * i + 1]);
+    }
+    cur.mMask = cv::Mat::ones(ci.height, ci.width, CV_8UC1);  // what the constructor / Reset() leave (src/frame.cpp:89, 104)
+    cur.SetPredictKeyPointsAndMask();
+    pagk_carry_out &o = out[p];
+    o.n_out = (int)cur.mvKeysUn.size();
+    for (int k = 0; k < o.n_out; ++k) {
+      o.keys[2 * k] = cur.mvKeys[k].pt.x; o.keys[2 * k + 1] = cur.mvKeys[k].pt.y;
+      o.keys_un[2 * k] = cur.mvKeysUn[k].pt.x; o.keys_un[2 * k + 1] = cur.mvKeysUn[k].pt.y;
+      o.keys_normal[2 * k] = cur.mvKeysNormal[k].pt.x; o.keys_normal[2 * k + 1] = cur.mvKeysNormal[k].pt.y;
+      o.index_in_last[k] = cur.mvPtIndexInLastFrame[k];
+      o.flow_velocity_last[2 * k] = last.mvFlowVelocityInNormalPlane[k].x;
+      o.flow_velocity_last[2 * k + 1] = last.mvFlowVelocityInNormalPlane[k].y;
+    }
+    if (o.mask)
+      for (int y = 0; y < ci.height; ++y) std::memcpy(o.mask + (size_t)y * ci.width, cur.mMask.data + (size_t)y * cur.mMask.step, (size_t)ci.width);
+  }
   return PAGK_OK;
 }
 

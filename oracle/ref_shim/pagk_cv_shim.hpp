@@ -62,6 +62,8 @@ typedef unsigned char uchar;
 #define CV_64FC1 CV_MAKETYPE(CV_64F, 1)
 #define CV_FM_RANSAC 8
 #define CV_GRAY2BGR 8
+#define CV_RGB2GRAY 7
+#define CV_RGBA2GRAY 11
 
 namespace cv {
 
@@ -152,6 +154,13 @@ template <typename T> struct Size_ {
 };
 typedef Size_<int> Size;
 
+template <typename T> struct Rect_ {
+  T x, y, width, height;
+  Rect_() : x(0), y(0), width(0), height(0) {}
+  Rect_(T x_, T y_, T w, T h) : x(x_), y(y_), width(w), height(h) {}
+};
+typedef Rect_<int> Rect;
+
 struct Range {
   int start, end;
   Range() : start(0), end(0) {}
@@ -216,6 +225,7 @@ class Mat {
   // header over a vector of points: N x 1, two channels, no copy (cv::Mat(const std::vector<_Tp>&, copyData=false))
   explicit Mat(const std::vector<Point2f> &v)
       : rows((int)v.size()), cols(1), data((uchar *)v.data()), step(sizeof(Point2f)), type_(CV_32FC2) {}
+  Mat(int r, int c, int type, const struct Scalar &s);  // filled with s[0] (single channel use only)
   Mat(const MatExpr &e);
   Mat &operator=(const MatExpr &e);
 
@@ -256,6 +266,8 @@ class Mat {
     if (dst.rows != rows || dst.cols != cols || dst.type_ != type_ || !dst.data) dst.create(rows, cols, type_);
     for (int r = 0; r < rows; ++r) std::memcpy(dst.data + (size_t)r * dst.step, data + (size_t)r * step, (size_t)cols * elemSize());
   }
+  Mat operator()(const Rect &r) const { return rowRange(r.y, r.y + r.height).colRange(r.x, r.x + r.width); }
+  void copyTo(Mat &&dst) const { Mat d(dst); copyTo(d); }  // into a view (mMask(roi_rect), im_out.colRange(...))
   Mat rowRange(int a, int b) const { Mat m(*this); m.data = data + (size_t)a * step; m.rows = b - a; return m; }
   Mat colRange(int a, int b) const { Mat m(*this); m.data = data + (size_t)a * elemSize(); m.cols = b - a; return m; }
   Mat reshape(int cn, int new_rows = 0) const {
@@ -284,10 +296,22 @@ class Mat {
     return m;
   }
   static Mat zeros(int r, int c, int type) { return Mat(r, c, type); }  // create() value-initialises
+  static Mat ones(int r, int c, int type) {
+    Mat m(r, c, type);
+    if (m.depth() != CV_8U || m.channels() != 1) shim_abort("Mat::ones of this type");
+    for (int y = 0; y < r; ++y) std::memset(m.data + (size_t)y * m.step, 1, (size_t)c);
+    return m;
+  }
 
   std::shared_ptr<uchar> buf_;
   int type_;
 };
+
+inline Mat::Mat(int r, int c, int type, const Scalar &sc) : Mat() {
+  create(r, c, type);
+  if (depth() != CV_8U) shim_abort("Mat(rows, cols, type, Scalar) of this depth");
+  for (int y = 0; y < r; ++y) std::memset(data + (size_t)y * step, (int)sc.val[0], (size_t)c * elemSize());
+}
 
 template <typename T> struct MatCommaInitializer_ {
   Mat m;
@@ -529,6 +553,22 @@ void calcOpticalFlowPyrLK(const Mat &prev, const Mat &next, const std::vector<Po
 void undistortPoints(const Mat &src, Mat &dst, const Mat &K, const Mat &dist, const Mat &R, const Mat &P);
 void initUndistortRectifyMap(const Mat &K, const Mat &dist, const Mat &R, const Mat &newK, Size size, int type, Mat &m1, Mat &m2);
 Mat getOptimalNewCameraMatrix(const Mat &K, const Mat &dist, Size size, double alpha, Size newSize, void *roi = nullptr);
+
+// ---- not on the path: declared so that src/frame.cpp (Frame::SetPredictKeyPointsAndMask lives there) compiles ----
+enum { FONT_HERSHEY_PLAIN = 1, FONT_HERSHEY_DUPLEX = 2, LINE_AA = 16 };
+class Exception : public std::exception {
+ public:
+  std::string err;
+  const char *what() const noexcept override { return err.c_str(); }
+};
+inline void cvtColor(const Mat &, Mat &, int) { shim_abort("cvtColor"); }
+inline void goodFeaturesToTrack(const Mat &, std::vector<Point2f> &, int, double, double, const Mat &, int, bool, double) { shim_abort("goodFeaturesToTrack"); }
+inline void line(Mat &, Point, Point, const Scalar &, int = 1, int = 8, int = 0) { shim_abort("line"); }
+inline void circle(Mat &, Point, int, const Scalar &, int = 1, int = 8, int = 0) { shim_abort("circle"); }
+inline void putText(Mat &, const std::string &, Point, int, double, const Scalar &, int = 1, int = 8, bool = false) { shim_abort("putText"); }
+inline Size getTextSize(const std::string &, int, double, int, int *) { shim_abort("getTextSize"); }
+inline void imshow(const std::string &, const Mat &) { shim_abort("imshow"); }
+inline int waitKey(int = 0) { shim_abort("waitKey"); }
 
 struct BFMatcher {
   BFMatcher(int = NORM_L2, bool = false) {}

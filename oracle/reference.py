@@ -23,7 +23,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 REFERENCE_ROOT = os.environ.get("PAGK_REFERENCE_ROOT", "/root/reference")
 OUT_DIR = os.path.join(_HERE, "_ref")
 LIB = os.path.join(OUT_DIR, "libpagk_ref.so")
-REF_SOURCES = ["src/gyro_aided_tracker.cpp", "src/patch_match.cpp", "src/utils.cpp"]
+REF_SOURCES = ["src/gyro_aided_tracker.cpp", "src/patch_match.cpp", "src/utils.cpp", "src/frame.cpp"]
 # the reference's own flags (CMakeLists.txt:10-11, 17-20: -O3 -std=c++11, no -march, no -ffast-math)
 CXXFLAGS = ["-O3", "-std=c++11", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-pthread", "-w"]
 _f32p = C.POINTER(C.c_float)
@@ -84,6 +84,7 @@ def load():
         lib.pagk_ref_inject_models.argtypes = [_f64p, _f64p]
         lib.pagk_ref_inject_models.restype = None
         lib.pagk_ref_geometry_validation.argtypes = [C.c_int, C.POINTER(capi.PagkGeometryIn), C.POINTER(capi.PagkGeometryOut)]
+        lib.pagk_ref_set_predict_keypoints_and_mask.argtypes = [C.c_int, C.POINTER(capi.PagkCarryIn), C.POINTER(capi.PagkCarryOut)]
         _lib = lib
     return _lib
 
@@ -115,6 +116,16 @@ def geometry_validation(cases):
         ins[k], outs[k] = c.structs()
     rc = load().pagk_ref_geometry_validation(len(cases), ins, outs)
     return rc, list(outs)
+
+
+def set_predict_keypoints_and_mask(cases):
+    """Frame::SetPredictKeyPointsAndMask(); returns (rc, [n_out]); the vectors land in each case's arrays"""
+    ins = (capi.PagkCarryIn * len(cases))()
+    outs = (capi.PagkCarryOut * len(cases))()
+    for k, c in enumerate(cases):
+        ins[k], outs[k] = c.structs()
+    rc = load().pagk_ref_set_predict_keypoints_and_mask(len(cases), ins, outs)
+    return rc, [int(o.n_out) for o in outs]
 
 
 def track(pair: capi.PairInputs, params: capi.PagkParams, n_threads: int = 1):

@@ -115,6 +115,49 @@ class GeometryCase:
         return i, o
 
 
+class PagkCarryIn(C.Structure):
+    _fields_ = [("n_keys", C.c_int), ("pt_predict", _f32p), ("pt_predict_un", _f32p), ("status", _u8p),
+                ("keys_normal_last", _f32p), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+                ("t_cur", C.c_double), ("t_last", C.c_double), ("width", C.c_int), ("height", C.c_int)]
+
+
+class PagkCarryOut(C.Structure):
+    _fields_ = [("n_out", C.c_int), ("keys", _f32p), ("keys_un", _f32p), ("keys_normal", _f32p), ("index_in_last", _i32p),
+                ("flow_velocity_last", _f32p), ("mask", _u8p)]
+
+
+class CarryCase:
+    """One Frame::SetPredictKeyPointsAndMask() call in numpy form; owns the output arrays."""
+
+    def __init__(self, pt_predict, pt_predict_un, status, keys_normal_last, K, t_cur, t_last, width, height, n_keys=None,
+                 want_mask=True):
+        f = lambda a: None if a is None else np.ascontiguousarray(a, np.float32).reshape(-1, 2)
+        self.pt_predict, self.pt_predict_un = f(pt_predict), f(pt_predict_un)
+        self.status = None if status is None else np.ascontiguousarray(status, np.uint8).reshape(-1)
+        self.keys_normal_last = f(keys_normal_last)
+        self.n_keys = int(n_keys if n_keys is not None else self.keys_normal_last.shape[0])
+        K = np.asarray(K, np.float32).reshape(3, 3)
+        self.fx, self.fy, self.cx, self.cy = float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2])
+        self.t_cur, self.t_last, self.width, self.height = float(t_cur), float(t_last), int(width), int(height)
+        n = max(self.n_keys, 1)
+        self.keys, self.keys_un, self.keys_normal = (np.zeros((n, 2), np.float32) for _ in range(3))
+        self.flow_velocity_last = np.zeros((n, 2), np.float32)
+        self.index_in_last = np.full(n, -7, np.int32)
+        self.mask = np.zeros((height, width), np.uint8) if want_mask else None
+
+    def structs(self):
+        i, o = PagkCarryIn(), PagkCarryOut()
+        i.n_keys = self.n_keys
+        i.pt_predict, i.pt_predict_un, i.status = _ptr(self.pt_predict, _f32p), _ptr(self.pt_predict_un, _f32p), _ptr(self.status, _u8p)
+        i.keys_normal_last = _ptr(self.keys_normal_last, _f32p)
+        i.fx, i.fy, i.cx, i.cy = self.fx, self.fy, self.cx, self.cy
+        i.t_cur, i.t_last, i.width, i.height = self.t_cur, self.t_last, self.width, self.height
+        o.keys, o.keys_un, o.keys_normal = _ptr(self.keys, _f32p), _ptr(self.keys_un, _f32p), _ptr(self.keys_normal, _f32p)
+        o.index_in_last, o.flow_velocity_last = _ptr(self.index_in_last, _i32p), _ptr(self.flow_velocity_last, _f32p)
+        o.mask = _ptr(self.mask, _u8p)
+        return i, o
+
+
 #: every symbol include/pagk.h declares: name -> (restype, argtypes)
 _H = C.c_void_p
 SYMBOLS = {
@@ -145,6 +188,7 @@ SYMBOLS = {
     "pagk_gyro_predict": (C.c_int, [_H, C.POINTER(PagkParams), C.POINTER(PagkPairIn), C.POINTER(PagkPairOut)]),
     "pagk_patch_match": (C.c_int, [_H, C.POINTER(PagkPatchMatchIn), C.POINTER(PagkPairOut)]),
     "pagk_geometry_validation": (C.c_int, [_H, C.c_int, C.POINTER(PagkGeometryIn), C.POINTER(PagkGeometryOut)]),
+    "pagk_set_predict_keypoints_and_mask": (C.c_int, [_H, C.c_int, C.POINTER(PagkCarryIn), C.POINTER(PagkCarryOut)]),
 }
 
 LIB_NAME = "libpagk_cuda.so"

@@ -85,6 +85,10 @@ struct pagk_handle {
   size_t ntab_stride = 0;  // floats per pair
   int *d_work = nullptr;   // work counters of the persistent LK kernels ([0]: slots kernel, [16..17]: lanes kernel)
   int lk_parity = 0;       // which of the two lanes-kernel counters the next launch uses
+  // pagk_set_predict_keypoints_and_mask: one block, allocated on first use (consts, last normals, 5 result vectors, counts)
+  unsigned char *d_carry = nullptr;
+  unsigned char *d_mask = nullptr;
+  size_t mask_stride = 0;
   PagkGeoModel *d_geo = nullptr;    // pagk_geometry_validation: models in, results out (allocated on first use)
   PagkGeoResult *d_geo_res = nullptr;
   int *d_progress = nullptr;  // lanes kernel, level-granular work items: per feature, epoch * 8 + levels finished
@@ -394,7 +398,7 @@ void pagk_destroy(pagk_handle *h) {
   if (h->stream && h->own_stream) cudaStreamSynchronize(h->stream);
   else cudaDeviceSynchronize();
   cudaFree(h->d_images); cudaFree(h->d_keys_un); cudaFree(h->d_keys); cudaFree(h->d_pc); cudaFree(h->d_res);
-  cudaFree(h->d_out); cudaFree(h->d_ntab); cudaFree(h->d_work); cudaFree(h->d_progress); cudaFree(h->d_geo); cudaFree(h->d_geo_res); cudaFree(h->d_dbg);
+  cudaFree(h->d_out); cudaFree(h->d_ntab); cudaFree(h->d_work); cudaFree(h->d_progress); cudaFree(h->d_geo); cudaFree(h->d_geo_res); cudaFree(h->d_carry); cudaFree(h->d_mask); cudaFree(h->d_dbg);
   cudaFreeHost(h->h_in); cudaFreeHost(h->h_out); cudaFreeHost(h->h_res);
   for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
@@ -810,6 +814,78 @@ int pagk_geometry_validation(pagk_handle *h, int n_pairs, const pagk_geometry_in
     out[p].score_H = res[(size_t)p].score_H; out[p].score_F = res[(size_t)p].score_F; out[p].used_H = res[(size_t)p].used_H;
     out[p].n_candidates = res[(size_t)p].n_candidates; out[p].n_inlier = res[(size_t)p].n_inlier;
   }
+  return PAGK_OK;
+}
+
+int pagk_set_predict_keypoints_and_mask(pagk_handle *h, int n_pairs, const pagk_carry_in *in, pagk_carry_out *out) {
+  if (!h || !in || !out) return fail(PAGK_ERR_INVALID, "null argument");
+  if (n_pairs < 0 || n_pairs > h->cfg.max_pairs) return fail(PAGK_ERR_INVALID, "n_pairs exceeds pagk_config.max_pairs");
+  if (n_pairs == 0) return PAGK_OK;
+  CU(cudaSetDevice(h->cfg.device));
+  const size_t MP = (size_t)h->cfg.max_pairs, NK = MP * h->cfg.max_keys;
+  // layout of d_carry: consts | normal_last | keys | keys_un | keys_normal | flow_last | index_in_last | n_out
+  const size_t off_nl = align_up(MP * sizeof(PagkCarryConst), 256), off_k = off_nl + align_up(NK * 8, 256), off_ku = off_k + align_up(NK * 8, 256),
+               off_kn = off_ku + align_up(NK * 8, 256), off_fl = off_kn + align_up(NK * 8, 256), off_ix = off_fl + align_up(NK * 8, 256),
+               off_n = off_ix + align_up(NK * 4, 256), total = off_n + align_up(MP * 4, 256);
+  if (!h->d_carry) CU(cudaMalloc(&h->d_carry, total));
+  const PagkOutPtrs o = h->outs();
+  cudaStream_t st = h->stream;
+  std::vector<PagkCarryConst> cc((size_t)n_pairs);
+  bool any_mask = false;
+  int W = 0, H = 0;
+  for (int p = 0; p < n_pairs; ++p) {
+    const pagk_carry_in &g = in[p];
+    if (g.n_keys < 0 || g.n_keys > h->cfg.max_keys) return fail(PAGK_ERR_INVALID, "n_keys exceeds pagk_config.max_keys");
+    if (g.n_keys > 0 && (!g.keys_normal_last || !out[p].keys || !out[p].keys_un || !out[p].keys_normal || !out[p].index_in_last || !out[p].flow_velocity_last))
+      return fail(PAGK_ERR_INVALID, "null vector");
+    if (g.width < 14 || g.height < 14 || g.width > h->cfg.max_width || g.height > h->cfg.max_height) return fail(PAGK_ERR_INVALID, "bad mask size");
+    const bool given = g.pt_predict && g.pt_predict_un && g.status;
+    if (!given && (g.pt_predict || g.pt_predict_un || g.status)) return fail(PAGK_ERR_INVALID, "pt_predict, pt_predict_un and status: all three or none");
+    if (!given && !(h->ran && p < h->n_pairs)) return fail(PAGK_ERR_INVALID, "no resident run to carry over");
+    if (p == 0) { W = g.width; H = g.height; }
+    if (g.width != W || g.height != H) return fail(PAGK_ERR_INVALID, "all pairs of a call must share the mask size");
+    PagkCarryConst &c = cc[(size_t)p];
+    c.cx = g.cx; c.cy = g.cy;
+    c.fx_inv = (float)(1.0 / g.fx); c.fy_inv = (float)(1.0 / g.fy);  // Frame ctor, src/frame.cpp:71
+    c.dt = g.t_cur - g.t_last;
+    c.n_keys = g.n_keys; c.width = g.width; c.height = g.height; c.pad = 0;
+    any_mask |= out[p].mask != nullptr;
+    const size_t off = (size_t)p * h->cfg.max_keys, n = (size_t)g.n_keys;
+    if (n) CU(cudaMemcpyAsync(h->d_carry + off_nl + off * 8, g.keys_normal_last, n * 8, cudaMemcpyHostToDevice, st));
+    if (given && n) {
+      CU(cudaMemcpyAsync(o.pt_predict + off, g.pt_predict, n * 8, cudaMemcpyHostToDevice, st));
+      CU(cudaMemcpyAsync(o.pt_predict_un + off, g.pt_predict_un, n * 8, cudaMemcpyHostToDevice, st));
+      CU(cudaMemcpyAsync(o.status + off, g.status, n, cudaMemcpyHostToDevice, st));
+    }
+  }
+  if (any_mask) {
+    if (!h->d_mask) {
+      h->mask_stride = align_up((size_t)h->cfg.max_width * h->cfg.max_height, 256);
+      CU(cudaMalloc(&h->d_mask, h->mask_stride * MP));
+    }
+    CU(cudaMemsetAsync(h->d_mask, 1, h->mask_stride * (size_t)n_pairs, st));  // cv::Mat::ones
+  }
+  CU(cudaMemcpyAsync(h->d_carry, cc.data(), cc.size() * sizeof(PagkCarryConst), cudaMemcpyHostToDevice, st));
+  CU((cudaError_t)pagk_launch_carry((const PagkCarryConst *)h->d_carry, o.pt_predict, o.pt_predict_un, o.status,
+                                    (const float2 *)(h->d_carry + off_nl), h->cfg.max_keys, n_pairs, (float2 *)(h->d_carry + off_k),
+                                    (float2 *)(h->d_carry + off_ku), (float2 *)(h->d_carry + off_kn), (int *)(h->d_carry + off_ix),
+                                    (float2 *)(h->d_carry + off_fl), (int *)(h->d_carry + off_n), any_mask ? h->d_mask : nullptr,
+                                    h->mask_stride, st, &h->launches));
+  std::vector<int> n_out((size_t)n_pairs);
+  CU(cudaMemcpyAsync(n_out.data(), h->d_carry + off_n, n_out.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+  for (int p = 0; p < n_pairs; ++p) {
+    const size_t off = (size_t)p * h->cfg.max_keys, n = (size_t)in[p].n_keys;  // survivors <= n_keys: copy the capacity
+    if (n) {
+      CU(cudaMemcpyAsync(out[p].keys, h->d_carry + off_k + off * 8, n * 8, cudaMemcpyDeviceToHost, st));
+      CU(cudaMemcpyAsync(out[p].keys_un, h->d_carry + off_ku + off * 8, n * 8, cudaMemcpyDeviceToHost, st));
+      CU(cudaMemcpyAsync(out[p].keys_normal, h->d_carry + off_kn + off * 8, n * 8, cudaMemcpyDeviceToHost, st));
+      CU(cudaMemcpyAsync(out[p].flow_velocity_last, h->d_carry + off_fl + off * 8, n * 8, cudaMemcpyDeviceToHost, st));
+      CU(cudaMemcpyAsync(out[p].index_in_last, h->d_carry + off_ix + off * 4, n * 4, cudaMemcpyDeviceToHost, st));
+    }
+    if (out[p].mask) CU(cudaMemcpyAsync(out[p].mask, h->d_mask + (size_t)p * h->mask_stride, (size_t)W * H, cudaMemcpyDeviceToHost, st));
+  }
+  CU(cudaStreamSynchronize(st));
+  for (int p = 0; p < n_pairs; ++p) out[p].n_out = n_out[(size_t)p];
   return PAGK_OK;
 }
 

@@ -55,6 +55,13 @@ struct PagkGeoResult {
   int used_H, n_candidates, n_inlier, pad;
 };
 
+// Frame::SetPredictKeyPointsAndMask (reference src/frame.cpp:115-153): per pair constants and the survivor count
+struct PagkCarryConst {
+  float cx, cy, fx_inv, fy_inv;
+  double dt;  // mTimeStamp - mpLastFrame->mTimeStamp
+  int n_keys, width, height, pad;
+};
+
 // Mode of one run (what TrackFeatures derives from eType, :384-414, plus the PatchMatch ctor args)
 struct PagkMode {
   int half, iterations, levels;

@@ -726,6 +726,65 @@ __global__ void __launch_bounds__(GEO_THREADS) pagk_geometry_kernel(const PagkGe
 }
 
 // =================================================================================================
+// Frame::SetPredictKeyPointsAndMask (reference src/frame.cpp:115-153): the surviving predictions of a pair become the
+// reference keypoints of the next one.  One CTA per pair; survivors are compacted in index order (warp ballots + a scan of
+// the warp totals), each survivor zeroes its 14 x 14 square of the occupancy mask (the mask is set to ones beforehand;
+// overlapping squares all write zero).
+// =================================================================================================
+#define CARRY_THREADS 1024
+
+__global__ void __launch_bounds__(CARRY_THREADS) pagk_carry_kernel(const PagkCarryConst *__restrict__ ccs,
+                                                                const float2 *__restrict__ pt_predict,
+                                                                const float2 *__restrict__ pt_predict_un,
+                                                                const unsigned char *__restrict__ status,
+                                                                const float2 *__restrict__ normal_last, int max_keys,
+                                                                float2 *__restrict__ keys, float2 *__restrict__ keys_un,
+                                                                float2 *__restrict__ keys_normal, int *__restrict__ index_in_last,
+                                                                float2 *__restrict__ flow_last, int *__restrict__ n_out,
+                                                                unsigned char *__restrict__ mask, unsigned long long mask_stride) {
+  __shared__ int s_warp[CARRY_THREADS / 32];
+  __shared__ int s_base;
+  const int pair = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const PagkCarryConst c = ccs[pair];
+  const size_t o0 = (size_t)pair * max_keys;
+  unsigned char *m = mask ? mask + (size_t)pair * mask_stride : nullptr;
+  const int half_path_size = 7;
+  if (t == 0) s_base = 0;
+  __syncthreads();
+  for (int c0 = 0; c0 < c.n_keys; c0 += CARRY_THREADS) {
+    const int i = c0 + t;
+    const bool alive = i < c.n_keys && status[o0 + i] != 0;
+    const unsigned ballot = __ballot_sync(0xffffffffu, alive);
+    if (lane == 0) s_warp[warp] = __popc(ballot);
+    __syncthreads();
+    int before = s_base;
+    for (int w = 0; w < warp; ++w) before += s_warp[w];
+    if (alive) {
+      const int k = before + __popc(ballot & ((1u << lane) - 1u));
+      const float2 pd = pt_predict[o0 + i], pu = pt_predict_un[o0 + i], nl = normal_last[o0 + i];
+      const float2 pn = make_float2((pu.x - c.cx) * c.fx_inv, (pu.y - c.cy) * c.fy_inv);
+      keys[o0 + k] = pd; keys_un[o0 + k] = pu; keys_normal[o0 + k] = pn;
+      index_in_last[o0 + k] = i;
+      // dv = dpt_normal / (mTimeStamp - mpLastFrame->mTimeStamp): Point2f / double = float(double(x) / dt)
+      flow_last[o0 + k] = make_float2((float)((double)(pn.x - nl.x) / c.dt), (float)((double)(pn.y - nl.y) / c.dt));
+      if (m) {
+        const int x = min(max(0, (int)pu.x - half_path_size), c.width - 2 * half_path_size);
+        const int y = min(max(0, (int)pu.y - half_path_size), c.height - 2 * half_path_size);
+        for (int r = 0; r < 2 * half_path_size; ++r) {
+          unsigned char *row = m + (size_t)(y + r) * c.width + x;
+#pragma unroll
+          for (int q = 0; q < 2 * half_path_size; ++q) row[q] = 0;
+        }
+      }
+    }
+    __syncthreads();
+    if (t == 0) { int tot = 0; for (int w = 0; w < CARRY_THREADS / 32; ++w) tot += s_warp[w]; s_base += tot; }
+    __syncthreads();
+  }
+  if (t == 0) n_out[pair] = s_base;
+}
+
+// =================================================================================================
 // launch wrappers (host)
 // =================================================================================================
 int pagk_pyramid_fused_max_level() {
@@ -812,6 +871,17 @@ int pagk_launch_geometry(const PagkGeoModel *models, const float2 *keys_un, cons
                          int max_keys, int n_pairs, PagkGeoResult *res, cudaStream_t st, long long *launches) {
   if (n_pairs <= 0) return 0;
   pagk_geometry_kernel<<<n_pairs, GEO_THREADS, 0, st>>>(models, keys_un, pred_un, status, max_keys, res);
+  ++*launches;
+  return (int)cudaGetLastError();
+}
+
+int pagk_launch_carry(const PagkCarryConst *cc, const float2 *pt_predict, const float2 *pt_predict_un, const unsigned char *status,
+                      const float2 *normal_last, int max_keys, int n_pairs, float2 *keys, float2 *keys_un, float2 *keys_normal,
+                      int *index_in_last, float2 *flow_last, int *n_out, unsigned char *mask, unsigned long long mask_stride,
+                      cudaStream_t st, long long *launches) {
+  if (n_pairs <= 0) return 0;
+  pagk_carry_kernel<<<n_pairs, CARRY_THREADS, 0, st>>>(cc, pt_predict, pt_predict_un, status, normal_last, max_keys, keys, keys_un,
+                                                      keys_normal, index_in_last, flow_last, n_out, mask, mask_stride);
   ++*launches;
   return (int)cudaGetLastError();
 }

@@ -21,6 +21,11 @@ int pagk_launch_epilogue(const PagkPairConst *pcs, const PagkOutPtrs &out, const
 // GeometryValidation minus its RANSAC estimators (reference src/gyro_aided_tracker.cpp:429-508, 589-768)
 int pagk_launch_geometry(const PagkGeoModel *models, const float2 *keys_un, const float2 *pred_un, unsigned char *status,
                          int max_keys, int n_pairs, PagkGeoResult *res, cudaStream_t st, long long *launches);
+// Frame::SetPredictKeyPointsAndMask (reference src/frame.cpp:115-153); mask may be null
+int pagk_launch_carry(const PagkCarryConst *cc, const float2 *pt_predict, const float2 *pt_predict_un, const unsigned char *status,
+                      const float2 *normal_last, int max_keys, int n_pairs, float2 *keys, float2 *keys_un, float2 *keys_normal,
+                      int *index_in_last, float2 *flow_last, int *n_out, unsigned char *mask, unsigned long long mask_stride,
+                      cudaStream_t st, long long *launches);
 int pagk_launch_count_status(const PagkPairConst *pcs, const PagkOutPtrs &out, int max_keys, int n_pairs,
                              PagkPairResult *res, cudaStream_t st, long long *launches);
 

@@ -102,6 +102,16 @@ class Context:
         _check(self.lib, self.lib.pagk_geometry_validation(self.handle, len(cases), ins, outs))
         return list(outs)
 
+    def set_predict_keypoints_and_mask(self, cases):
+        """Frame::SetPredictKeyPointsAndMask() (include/pagk.h): a list of capi.CarryCase (prediction vectors None = the
+        resident results of the last run); returns the survivor counts, vectors and mask land in each case's arrays"""
+        ins = (capi.PagkCarryIn * len(cases))()
+        outs = (capi.PagkCarryOut * len(cases))()
+        for k, c in enumerate(cases):
+            ins[k], outs[k] = c.structs()
+        _check(self.lib, self.lib.pagk_set_predict_keypoints_and_mask(self.handle, len(cases), ins, outs))
+        return [int(o.n_out) for o in outs]
+
     def set_stage_timing(self, on: bool):
         """CUDA events between the kernels of a run (per-stage clocks); off for throughput pipelines"""
         _check(self.lib, self.lib.pagk_set_stage_timing(self.handle, 1 if on else 0))
