@@ -286,6 +286,15 @@ typedef struct pagk_carry_out {
 
 int pagk_set_predict_keypoints_and_mask(pagk_handle *h, int n_pairs, const pagk_carry_in *in, pagk_carry_out *out);
 
+/* == cv::FAST(image, keypoints, threshold, nonmaxSuppression, TYPE_9_16): the detector primitive under the keypoint top-up
+ * of the drivers (ORBextractor::ComputeKeyPointsOctTree calls it per 30-pixel cell, src/ORBextractor.cc:833-840).
+ * Keypoints come back in OpenCV's order (row-major), xy[k] = (x, y), response[k] = the corner score (0 without
+ * non-maximum suppression, as in OpenCV).  mask (height x width, e.g. the one pagk_set_predict_keypoints_and_mask
+ * returned) may be NULL; a keypoint on a zero mask byte is dropped, as ORBextractor::DetectFeatures does
+ * (src/ORBextractor.cc:1200-1203).  At most max_out keypoints are written; *n_out is the number found. */
+int pagk_fast_detect(pagk_handle *h, const uint8_t *img, int width, int height, int pitch, int threshold, int nonmax,
+                     const uint8_t *mask, int max_out, float *xy, float *response, int *n_out);
+
 #ifdef __cplusplus
 }
 #endif

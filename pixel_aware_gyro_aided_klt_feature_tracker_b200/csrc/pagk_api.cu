@@ -89,6 +89,9 @@ struct pagk_handle {
   unsigned char *d_carry = nullptr;
   unsigned char *d_mask = nullptr;
   size_t mask_stride = 0;
+  unsigned char *d_fast = nullptr;  // pagk_fast_detect: image | mask | score | keep | row counts | row offsets (first use)
+  unsigned char *d_fast_out = nullptr;
+  int fast_out_cap = 0;
   PagkGeoModel *d_geo = nullptr;    // pagk_geometry_validation: models in, results out (allocated on first use)
   PagkGeoResult *d_geo_res = nullptr;
   int *d_progress = nullptr;  // lanes kernel, level-granular work items: per feature, epoch * 8 + levels finished
@@ -398,7 +401,7 @@ void pagk_destroy(pagk_handle *h) {
   if (h->stream && h->own_stream) cudaStreamSynchronize(h->stream);
   else cudaDeviceSynchronize();
   cudaFree(h->d_images); cudaFree(h->d_keys_un); cudaFree(h->d_keys); cudaFree(h->d_pc); cudaFree(h->d_res);
-  cudaFree(h->d_out); cudaFree(h->d_ntab); cudaFree(h->d_work); cudaFree(h->d_progress); cudaFree(h->d_geo); cudaFree(h->d_geo_res); cudaFree(h->d_carry); cudaFree(h->d_mask); cudaFree(h->d_dbg);
+  cudaFree(h->d_out); cudaFree(h->d_ntab); cudaFree(h->d_work); cudaFree(h->d_progress); cudaFree(h->d_geo); cudaFree(h->d_geo_res); cudaFree(h->d_carry); cudaFree(h->d_mask); cudaFree(h->d_fast); cudaFree(h->d_fast_out); cudaFree(h->d_dbg);
   cudaFreeHost(h->h_in); cudaFreeHost(h->h_out); cudaFreeHost(h->h_res);
   for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
@@ -886,6 +889,42 @@ int pagk_set_predict_keypoints_and_mask(pagk_handle *h, int n_pairs, const pagk_
   }
   CU(cudaStreamSynchronize(st));
   for (int p = 0; p < n_pairs; ++p) out[p].n_out = n_out[(size_t)p];
+  return PAGK_OK;
+}
+
+int pagk_fast_detect(pagk_handle *h, const uint8_t *img, int width, int height, int pitch, int threshold, int nonmax,
+                     const uint8_t *mask, int max_out, float *xy, float *response, int *n_out) {
+  if (!h || !img || !n_out || max_out < 0 || (max_out > 0 && (!xy || !response))) return fail(PAGK_ERR_INVALID, "null argument");
+  if (width < 1 || height < 1 || pitch < width || width > h->cfg.max_width || height > h->cfg.max_height)
+    return fail(PAGK_ERR_INVALID, "image exceeds pagk_config.max_width/max_height");
+  CU(cudaSetDevice(h->cfg.device));
+  const size_t WH = align_up((size_t)h->cfg.max_width * h->cfg.max_height, 256), RW = align_up((size_t)(h->cfg.max_height + 1) * sizeof(int), 256);
+  // layout of d_fast: image | mask | score (u16) | keep | row counts | row offsets
+  const size_t off_mask = WH, off_score = 2 * WH, off_keep = 4 * WH, off_rc = 5 * WH, off_ro = off_rc + RW, total = off_ro + RW;
+  if (!h->d_fast) CU(cudaMalloc(&h->d_fast, total));
+  if (max_out > h->fast_out_cap) {
+    cudaFree(h->d_fast_out); h->d_fast_out = nullptr; h->fast_out_cap = 0;
+    CU(cudaMalloc(&h->d_fast_out, align_up((size_t)max_out * 8, 256) + align_up((size_t)max_out * 4, 256)));
+    h->fast_out_cap = max_out;
+  }
+  cudaStream_t st = h->stream;
+  CU(cudaMemcpy2DAsync(h->d_fast, (size_t)width, img, (size_t)pitch, (size_t)width, (size_t)height, cudaMemcpyHostToDevice, st));
+  if (mask) CU(cudaMemcpyAsync(h->d_fast + off_mask, mask, (size_t)width * height, cudaMemcpyHostToDevice, st));
+  float2 *d_xy = (float2 *)h->d_fast_out;
+  float *d_rs = (float *)(h->d_fast_out + align_up((size_t)h->fast_out_cap * 8, 256));
+  CU((cudaError_t)pagk_launch_fast(h->d_fast, width, height, threshold, nonmax ? 1 : 0, mask ? h->d_fast + off_mask : nullptr,
+                                   (unsigned short *)(h->d_fast + off_score), h->d_fast + off_keep, (int *)(h->d_fast + off_rc),
+                                   (int *)(h->d_fast + off_ro), max_out, d_xy, d_rs, st, &h->launches));
+  int total_found = 0;
+  CU(cudaMemcpyAsync(&total_found, h->d_fast + off_ro + (size_t)height * sizeof(int), sizeof(int), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  const int n = total_found < max_out ? total_found : max_out;
+  if (n > 0) {
+    CU(cudaMemcpyAsync(xy, d_xy, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(response, d_rs, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  *n_out = total_found;
   return PAGK_OK;
 }
 

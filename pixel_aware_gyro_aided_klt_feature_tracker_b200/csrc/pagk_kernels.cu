@@ -785,6 +785,139 @@ __global__ void __launch_bounds__(CARRY_THREADS) pagk_carry_kernel(const PagkCar
 }
 
 // =================================================================================================
+// cv::FAST(image, keypoints, threshold, nonmaxSuppression, TYPE_9_16) -- OpenCV modules/features2d/src/fast.cpp.
+// A pixel is a corner when nine contiguous pixels of the 16-pixel circle are all darker than v - t or all brighter than
+// v + t; its score is cornerScore<16> (the largest threshold for which it still is one); with non-maximum suppression a
+// corner is kept when its score is strictly greater than the scores of its eight neighbours.  Keypoints come out in
+// row-major order.  Four small kernels: scores (one thread per pixel), keep flags + per-row counts (one warp per row),
+// scan of the row counts (one block), ordered emit (one warp per row).  score image: (1 << 8 | score) for a corner, else 0.
+// =================================================================================================
+__constant__ int c_fast_dx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+__constant__ int c_fast_dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+
+__global__ void __launch_bounds__(256) pagk_fast_score_kernel(const unsigned char *__restrict__ img, int cols, int rows, int threshold,
+                                                            int nonmax, unsigned short *__restrict__ score) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= cols || y >= rows) return;
+  unsigned short out = 0;
+  if (x >= 3 && x < cols - 3 && y >= 3 && y < rows - 3) {
+    const unsigned char *ptr = img + (size_t)y * cols + x;
+    const int v = ptr[0];
+    int d[25];
+    unsigned dark = 0, bright = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int p = ptr[c_fast_dx[k] + c_fast_dy[k] * cols];
+      d[k] = v - p;
+      dark |= (p < v - threshold ? 1u : 0u) << k;
+      bright |= (p > v + threshold ? 1u : 0u) << k;
+    }
+#pragma unroll
+    for (int k = 16; k < 25; ++k) d[k] = d[k - 16];
+    // nine contiguous set bits on the circle: AND of the mask with its rotations by 1..8
+    auto arc9 = [](unsigned m) {
+      m |= m << 16;
+      unsigned a = m;
+#pragma unroll
+      for (int r = 1; r <= 8; ++r) a &= (m >> r);
+      return (a & 0xffffu) != 0u;
+    };
+    if (arc9(dark) || arc9(bright)) {
+      int sc = 0;
+      if (nonmax) {  // cornerScore<16>
+        int a0 = threshold;
+#pragma unroll
+        for (int k = 0; k < 16; k += 2) {
+          int a = min(d[k + 1], d[k + 2]);
+          a = min(a, d[k + 3]);
+          if (a <= a0) continue;
+          a = min(a, d[k + 4]); a = min(a, d[k + 5]); a = min(a, d[k + 6]); a = min(a, d[k + 7]); a = min(a, d[k + 8]);
+          a0 = max(a0, min(a, d[k]));
+          a0 = max(a0, min(a, d[k + 9]));
+        }
+        int b0 = -a0;
+#pragma unroll
+        for (int k = 0; k < 16; k += 2) {
+          int b = max(d[k + 1], d[k + 2]);
+          b = max(b, d[k + 3]); b = max(b, d[k + 4]); b = max(b, d[k + 5]);
+          if (b >= b0) continue;
+          b = max(b, d[k + 6]); b = max(b, d[k + 7]); b = max(b, d[k + 8]);
+          b0 = min(b0, max(b, d[k]));
+          b0 = min(b0, max(b, d[k + 9]));
+        }
+        sc = (-b0 - 1) & 0xff;  // curr[j] = (uchar)cornerScore(...)
+      }
+      out = (unsigned short)(0x100 | sc);
+    }
+  }
+  score[(size_t)y * cols + x] = out;
+}
+
+__device__ __forceinline__ bool pagk_fast_keep(const unsigned short *__restrict__ score, const unsigned char *__restrict__ mask, int cols,
+                                               int rows, int x, int y, int nonmax) {
+  if (x < 3 || x >= cols - 3 || y < 3 || y >= rows - 3) return false;
+  const unsigned short *s = score + (size_t)y * cols + x;
+  if (!(s[0] & 0x100)) return false;
+  if (nonmax) {
+    const int s0 = s[0] & 0xff;
+    const bool mx = s0 > (s[1] & 0xff) && s0 > (s[-1] & 0xff) && s0 > (s[-cols - 1] & 0xff) && s0 > (s[-cols] & 0xff) &&
+                    s0 > (s[-cols + 1] & 0xff) && s0 > (s[cols - 1] & 0xff) && s0 > (s[cols] & 0xff) && s0 > (s[cols + 1] & 0xff);
+    if (!mx) return false;
+  }
+  return !mask || mask[(size_t)y * cols + x] != 0;
+}
+
+// one warp per row: keep flags and the row's count
+__global__ void __launch_bounds__(256) pagk_fast_rows_kernel(const unsigned short *__restrict__ score, const unsigned char *__restrict__ mask,
+                                                           int cols, int rows, int nonmax, unsigned char *__restrict__ keep,
+                                                           int *__restrict__ row_count) {
+  const int y = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (y >= rows) return;
+  int cnt = 0;
+  for (int x0 = 0; x0 < cols; x0 += 32) {
+    const int x = x0 + lane;
+    const bool k = x < cols && pagk_fast_keep(score, mask, cols, rows, x, y, nonmax);
+    if (x < cols) keep[(size_t)y * cols + x] = k ? 1 : 0;
+    cnt += __popc(__ballot_sync(0xffffffffu, k));
+  }
+  if (lane == 0) row_count[y] = cnt;
+}
+
+// exclusive scan of the row counts by one block; row_offset[rows] = total
+__global__ void __launch_bounds__(1024) pagk_fast_scan_kernel(const int *__restrict__ row_count, int rows, int *__restrict__ row_offset) {
+  __shared__ int s_part[1024];
+  const int t = threadIdx.x, per = (rows + 1023) / 1024, b = t * per;
+  int sum = 0;
+  for (int i = b; i < min(b + per, rows); ++i) sum += row_count[i];
+  s_part[t] = sum;
+  __syncthreads();
+  if (t == 0) { int run = 0; for (int i = 0; i < 1024; ++i) { const int v = s_part[i]; s_part[i] = run; run += v; } row_offset[rows] = run; }
+  __syncthreads();
+  int run = s_part[t];
+  for (int i = b; i < min(b + per, rows); ++i) { row_offset[i] = run; run += row_count[i]; }
+}
+
+// one warp per row: keypoints of the row at row_offset[y] + rank within the row
+__global__ void __launch_bounds__(256) pagk_fast_emit_kernel(const unsigned short *__restrict__ score, const unsigned char *__restrict__ keep,
+                                                           const int *__restrict__ row_offset, int cols, int rows, int max_out,
+                                                           float2 *__restrict__ xy, float *__restrict__ response) {
+  const int y = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (y >= rows) return;
+  int base = row_offset[y];
+  if (row_offset[y + 1] == base) return;
+  for (int x0 = 0; x0 < cols; x0 += 32) {
+    const int x = x0 + lane;
+    const bool k = x < cols && keep[(size_t)y * cols + x] != 0;
+    const unsigned b = __ballot_sync(0xffffffffu, k);
+    if (k) {
+      const int pos = base + __popc(b & ((1u << lane) - 1u));
+      if (pos < max_out) { xy[pos] = make_float2((float)x, (float)y); response[pos] = (float)(score[(size_t)y * cols + x] & 0xff); }
+    }
+    base += __popc(b);
+  }
+}
+
+// =================================================================================================
 // launch wrappers (host)
 // =================================================================================================
 int pagk_pyramid_fused_max_level() {
@@ -883,6 +1016,20 @@ int pagk_launch_carry(const PagkCarryConst *cc, const float2 *pt_predict, const 
   pagk_carry_kernel<<<n_pairs, CARRY_THREADS, 0, st>>>(cc, pt_predict, pt_predict_un, status, normal_last, max_keys, keys, keys_un,
                                                       keys_normal, index_in_last, flow_last, n_out, mask, mask_stride);
   ++*launches;
+  return (int)cudaGetLastError();
+}
+
+int pagk_launch_fast(const unsigned char *img, int cols, int rows, int threshold, int nonmax, const unsigned char *mask,
+                     unsigned short *score, unsigned char *keep, int *row_count, int *row_offset, int max_out, float2 *xy,
+                     float *response, cudaStream_t st, long long *launches) {
+  if (cols <= 0 || rows <= 0) return 0;
+  threshold = threshold < 0 ? 0 : threshold > 255 ? 255 : threshold;
+  dim3 grid((cols + 31) / 32, (rows + 7) / 8);
+  pagk_fast_score_kernel<<<grid, 256, 0, st>>>(img, cols, rows, threshold, nonmax, score);
+  pagk_fast_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(score, mask, cols, rows, nonmax, keep, row_count);
+  pagk_fast_scan_kernel<<<1, 1024, 0, st>>>(row_count, rows, row_offset);
+  pagk_fast_emit_kernel<<<(rows + 7) / 8, 256, 0, st>>>(score, keep, row_offset, cols, rows, max_out, xy, response);
+  *launches += 4;
   return (int)cudaGetLastError();
 }
 

@@ -26,6 +26,10 @@ int pagk_launch_carry(const PagkCarryConst *cc, const float2 *pt_predict, const 
                       const float2 *normal_last, int max_keys, int n_pairs, float2 *keys, float2 *keys_un, float2 *keys_normal,
                       int *index_in_last, float2 *flow_last, int *n_out, unsigned char *mask, unsigned long long mask_stride,
                       cudaStream_t st, long long *launches);
+// cv::FAST TYPE_9_16 (OpenCV features2d fast.cpp): scores -> keep flags + row counts -> row offsets -> ordered emit
+int pagk_launch_fast(const unsigned char *img, int cols, int rows, int threshold, int nonmax, const unsigned char *mask,
+                     unsigned short *score, unsigned char *keep, int *row_count, int *row_offset, int max_out, float2 *xy,
+                     float *response, cudaStream_t st, long long *launches);
 int pagk_launch_count_status(const PagkPairConst *pcs, const PagkOutPtrs &out, int max_keys, int n_pairs,
                              PagkPairResult *res, cudaStream_t st, long long *launches);
 

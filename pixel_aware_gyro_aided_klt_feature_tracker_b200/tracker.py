@@ -112,6 +112,20 @@ class Context:
         _check(self.lib, self.lib.pagk_set_predict_keypoints_and_mask(self.handle, len(cases), ins, outs))
         return [int(o.n_out) for o in outs]
 
+    def fast_detect(self, img, threshold, nonmax=True, mask=None, max_out=200000):
+        """cv::FAST TYPE_9_16 (include/pagk.h); returns (xy [n][2], response [n]) in OpenCV's order"""
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape
+        xy, rs, n = np.zeros((max_out, 2), np.float32), np.zeros(max_out, np.float32), C.c_int(0)
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        u8 = C.POINTER(C.c_uint8)
+        f32 = C.POINTER(C.c_float)
+        _check(self.lib, self.lib.pagk_fast_detect(self.handle, img.ctypes.data_as(u8), w, h, img.strides[0], int(threshold),
+                                                   1 if nonmax else 0, None if m is None else m.ctypes.data_as(u8), max_out,
+                                                   xy.ctypes.data_as(f32), rs.ctypes.data_as(f32), C.byref(n)))
+        k = min(n.value, max_out)
+        return xy[:k].copy(), rs[:k].copy()
+
     def set_stage_timing(self, on: bool):
         """CUDA events between the kernels of a run (per-stage clocks); off for throughput pipelines"""
         _check(self.lib, self.lib.pagk_set_stage_timing(self.handle, 1 if on else 0))

@@ -5,6 +5,7 @@ What is pinned against what (the reference ships no tests 
   matexpr.npz   cv2.gemm / cv2.invert / cv2.scaleAdd / cv2.add chains that OpenCV's cv::MatExpr lowers
                 IntegrateGyroMeasurements, SetRcl and the affine-matrix expression to
                 (src/gyro_aided_tracker.cpp:166-167, 511-587)       -> pins oracle small_*() and integrate_gyro()
+  fast.npz      cv2.FastFeatureDetector (TYPE_9_16) keypoints and responses            -> pins oracle fast_detect()
   lk_frozen.npz outputs of the reference build (oracle/_ref/libpagk_ref.so = the reference's own three sources
                 compiled against stand-in OpenCV/Eigen/glog headers, oracle/reference.py) on small seeded pairs
                 -> pins the restatement's Gauss-Newton loop, prediction, filter and control flow against the
@@ -181,7 +182,33 @@ def make_lk_frozen():
     np.savez_compressed(os.path.join(HERE, "lk_frozen.npz"), **out)
 
 
+def make_fast():
+    """cv2.FastFeatureDetector (TYPE_9_16) keypoints: positions in OpenCV's order and responses -> pins oracle fast_detect()"""
+    rng = np.random.default_rng(77)
+    out, cases = {}, [(60, 80, 10, 1.2), (240, 320, 20, 2.0), (480, 752, 7, 2.0), (100, 101, 0, 0.0), (37, 50, 40, 0.8), (480, 640, 20, 1.5)]
+    out["n"] = np.array(len(cases))
+    for i, (h, w, th, sig) in enumerate(cases):
+        img = (rng.random((h, w)) * 255).astype(np.uint8)
+        if sig > 0:
+            img = cv2.normalize(cv2.GaussianBlur(img, (0, 0), sig), None, 0, 255, cv2.NORM_MINMAX)
+        out[f"f{i}_seed_shape_th"] = np.array([h, w, th], np.int32)
+        if h * w <= 240 * 320:
+            out[f"f{i}_img"] = img
+        out[f"f{i}_img_sha"] = np.frombuffer(hashlib.sha256(img.tobytes()).digest(), np.uint8)
+        for nm in (1, 0):
+            k = cv2.FastFeatureDetector_create(threshold=th, nonmaxSuppression=bool(nm), type=cv2.FAST_FEATURE_DETECTOR_TYPE_9_16).detect(img)
+            xy = np.array([p.pt for p in k], np.float32).reshape(-1, 2)
+            rs = np.array([p.response for p in k], np.float32)
+            out[f"f{i}_n{nm}"] = np.array(len(k))
+            out[f"f{i}_sha{nm}"] = np.frombuffer(hashlib.sha256(xy.tobytes() + rs.tobytes()).digest(), np.uint8)
+            if h * w <= 240 * 320 and nm:
+                out[f"f{i}_xy"] = xy; out[f"f{i}_rs"] = rs
+    np.savez_compressed(os.path.join(HERE, "fast.npz"), **out)
+    print("fast.npz", len(out))
+
+
 if __name__ == "__main__":
     make_pyramid()
     make_matexpr()
     make_lk_frozen()
+    make_fast()
