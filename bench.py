@@ -32,8 +32,8 @@ METRIC = "tracked features/sec at 752x480, 1024 feats, 4 levels; px error vs CPU
 FP32_FLOP_PER_FEATURE_ITER = {5: 8.5e3, 10: 30.9e3}
 HBM_BYTES_PER_FEATURE_ITER = 120.0
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the LK kernel on this workload, from the committed
-# `ncu --set full` capture (profiles/r01_ncu_summary.md): 48.94 MB + 2.00 MB
-LK_DRAM_TRAFFIC_BYTES_PER_LAUNCH = {("B", 64): 50.95e6}
+# `ncu --set full` capture (profiles/r01_ncu_summary.md): 48.91 MB + 2.80 MB
+LK_DRAM_TRAFFIC_BYTES_PER_LAUNCH = {("B", 64): 51.72e6}
 N_ROTATE = 3  # resident batches per GPU; 3 x 61 MB of pyramids > 126 MB L2
 E2E_DEPTH = 5  # handles (streams) the end-to-end leg rotates over: uploads, kernels and downloads of 5 batches in flight
 
