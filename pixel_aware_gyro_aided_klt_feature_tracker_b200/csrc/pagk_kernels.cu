@@ -532,7 +532,7 @@ __global__ void __launch_bounds__(EPI1_THREADS) pagk_epilogue1_kernel(const Pagk
                                                                    PagkPairResult *__restrict__ res, int do_filter) {
   __shared__ double s_err[EPI1_THREADS];
   __shared__ double s_th[2];
-  __shared__ int s_cnt, s_ok_cnt;
+  __shared__ int s_cnt;
   __shared__ unsigned long long s_it;
   const int pair = blockIdx.x, t = threadIdx.x;
   const PagkPairConst &c = pcs[pair];
