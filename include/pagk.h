@@ -295,6 +295,17 @@ int pagk_set_predict_keypoints_and_mask(pagk_handle *h, int n_pairs, const pagk_
 int pagk_fast_detect(pagk_handle *h, const uint8_t *img, int width, int height, int pitch, int threshold, int nonmax,
                      const uint8_t *mask, int max_out, float *xy, float *response, int *n_out);
 
+/* == The detection half of ORBextractor::DetectFeatures for one pyramid level (src/ORBextractor.cc:1148-1205 with
+ * ComputeKeyPointsOctTree :789-876), as Frame::DetectKeyPoints uses it to top keypoints up (src/frame.cpp:155-219): the
+ * image inside a 16-pixel border is cut into cells of about 30 pixels, every cell runs cv::FAST with non-maximum suppression
+ * at ini_th and, if that yields nothing, at min_th; keypoints on a zero mask byte are dropped (:1200-1203).  Keypoints come
+ * back cell by cell (cells row-major, row-major inside a cell).  NOT included: DistributeOctTree, which thins the set to
+ * nfeatures -- its node order is sorted with pointer values as tie-break (src/ORBextractor.cc:706-707), so its selection is
+ * not reproducible even between two runs of the reference; with nfeatures above the candidate count it keeps every keypoint,
+ * which is how the tests compare this call with the reference's own DetectFeatures. */
+int pagk_orb_cell_detect(pagk_handle *h, const uint8_t *img, int width, int height, int pitch, int ini_th, int min_th,
+                         const uint8_t *mask, int max_out, float *xy, float *response, int *n_out);
+
 #ifdef __cplusplus
 }
 #endif

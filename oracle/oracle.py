@@ -54,6 +54,8 @@ def load():
         lib.pagk_oracle_set_predict_keypoints_and_mask.argtypes = [C.c_int, C.POINTER(capi.PagkCarryIn), C.POINTER(capi.PagkCarryOut)]
         lib.pagk_oracle_fast_detect.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u8p, C.c_int, _f32p, _f32p,
                                                 C.POINTER(C.c_int)]
+        lib.pagk_oracle_orb_cell_detect.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u8p, C.c_int, _f32p, _f32p,
+                                                    C.POINTER(C.c_int)]
         _lib = lib
     return _lib
 
@@ -154,6 +156,19 @@ def fast_detect(img, threshold, nonmax=True, mask=None, max_out=200000):
     load().pagk_oracle_fast_detect(img.ctypes.data_as(_u8p), w, h, img.strides[0], threshold, 1 if nonmax else 0,
                                    None if m is None else m.ctypes.data_as(_u8p), max_out, xy.ctypes.data_as(_f32p),
                                    rs.ctypes.data_as(_f32p), C.byref(n))
+    k = min(n.value, max_out)
+    return xy[:k].copy(), rs[:k].copy()
+
+
+def orb_cell_detect(img, ini_th=20, min_th=7, mask=None, max_out=400000):
+    """per-cell FAST of ORBextractor::ComputeKeyPointsOctTree (one level) + the mask filter; (xy [n][2], response [n]), cell by cell"""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    xy, rs, n = np.zeros((max_out, 2), np.float32), np.zeros(max_out, np.float32), C.c_int(0)
+    m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+    load().pagk_oracle_orb_cell_detect(img.ctypes.data_as(_u8p), w, h, img.strides[0], ini_th, min_th,
+                                       None if m is None else m.ctypes.data_as(_u8p), max_out, xy.ctypes.data_as(_f32p),
+                                       rs.ctypes.data_as(_f32p), C.byref(n))
     k = min(n.value, max_out)
     return xy[:k].copy(), rs[:k].copy()
 

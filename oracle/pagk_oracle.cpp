@@ -46,6 +46,7 @@
 
 #include "../include/pagk.h"
 #include "pagk_cv_resize.h"
+#include "pagk_cv_fast.h"
 
 #include <cmath>
 #include <cstdint>
@@ -893,77 +894,48 @@ void set_predict_keypoints_and_mask(const pagk_carry_in &in, pagk_carry_out *out
 // cv::FAST, TYPE_9_16 (OpenCV modules/features2d/src/fast.cpp, FAST_t<16> and cornerScore<16>), restated from its
 // published algorithm.  PINNED bit-exact against cv2 4.13 (tests/golden/fast.npz): positions, order and responses.
 // ---------------------------------------------------------------------------------------------
-const int kFastDx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
-const int kFastDy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+using pagk_cv::fast_detect;
 
-int fast_corner_score(const uint8_t *ptr, const int *pixel, int threshold) {
-  const int K = 8, N = K * 3 + 1;
-  const int v = ptr[0];
-  short d[N];
-  for (int k = 0; k < N; k++) d[k] = (short)(v - ptr[pixel[k]]);
-  int a0 = threshold;
-  for (int k = 0; k < 16; k += 2) {
-    int a = std::min((int)d[k + 1], (int)d[k + 2]);
-    a = std::min(a, (int)d[k + 3]);
-    if (a <= a0) continue;
-    a = std::min(a, (int)d[k + 4]); a = std::min(a, (int)d[k + 5]); a = std::min(a, (int)d[k + 6]);
-    a = std::min(a, (int)d[k + 7]); a = std::min(a, (int)d[k + 8]);
-    a0 = std::max(a0, std::min(a, (int)d[k]));
-    a0 = std::max(a0, std::min(a, (int)d[k + 9]));
-  }
-  int b0 = -a0;
-  for (int k = 0; k < 16; k += 2) {
-    int b = std::max((int)d[k + 1], (int)d[k + 2]);
-    b = std::max(b, (int)d[k + 3]); b = std::max(b, (int)d[k + 4]); b = std::max(b, (int)d[k + 5]);
-    if (b >= b0) continue;
-    b = std::max(b, (int)d[k + 6]); b = std::max(b, (int)d[k + 7]); b = std::max(b, (int)d[k + 8]);
-    b0 = std::min(b0, std::max(b, (int)d[k]));
-    b0 = std::min(b0, std::max(b, (int)d[k + 9]));
-  }
-  return -b0 - 1;
-}
-
-int fast_detect(const uint8_t *img, int cols, int rows, int step, int threshold, bool nonmax, const uint8_t *mask, int max_out,
-                float *xy, float *response) {
-  const int K = 8, N = 25;
-  int pixel[25];
-  for (int k = 0; k < 16; ++k) pixel[k] = kFastDx[k] + kFastDy[k] * step;
-  for (int k = 16; k < 25; ++k) pixel[k] = pixel[k - 16];
-  threshold = std::min(std::max(threshold, 0), 255);
-  std::vector<uint8_t> score((size_t)rows * cols, 0), corner((size_t)rows * cols, 0);
-  for (int i = 3; i < rows - 3; ++i)
-    for (int j = 3; j < cols - 3; ++j) {
-      const uint8_t *ptr = img + (size_t)i * step + j;
-      const int v = ptr[0];
-      bool is = false;
-      {  // nine contiguous pixels of the circle darker than v - threshold ...
-        const int vt = v - threshold;
-        int count = 0;
-        for (int k = 0; k < N && !is; k++) { if (ptr[pixel[k]] < vt) { if (++count > K) is = true; } else count = 0; }
-      }
-      if (!is) {  // ... or brighter than v + threshold
-        const int vt = v + threshold;
-        int count = 0;
-        for (int k = 0; k < N && !is; k++) { if (ptr[pixel[k]] > vt) { if (++count > K) is = true; } else count = 0; }
-      }
-      if (is) {
-        corner[(size_t)i * cols + j] = 1;
-        if (nonmax) score[(size_t)i * cols + j] = (uint8_t)fast_corner_score(ptr, pixel, threshold);
-      }
-    }
+// ---------------------------------------------------------------------------------------------
+// ORBextractor::ComputeKeyPointsOctTree for one level, up to vToDistributeKeys (src/ORBextractor.cc:789-852), plus the
+// final mask filter of DetectFeatures (:1200-1203).  The cell arithmetic is the reference's (floats and all).
+// ---------------------------------------------------------------------------------------------
+int orb_cell_detect(const uint8_t *img, int cols, int rows, int step, int ini_th, int min_th, const uint8_t *mask, int max_out,
+                    float *xy, float *response) {
+  const int EDGE_THRESHOLD = 19;
+  const float W = 30;
+  const int minBorderX = EDGE_THRESHOLD - 3, minBorderY = minBorderX;
+  const int maxBorderX = cols - EDGE_THRESHOLD + 3, maxBorderY = rows - EDGE_THRESHOLD + 3;
+  const float width = (maxBorderX - minBorderX), height = (maxBorderY - minBorderY);
+  const int nCols = width / W, nRows = height / W;
+  if (nCols < 1 || nRows < 1) return 0;
+  const int wCell = ceil(width / nCols), hCell = ceil(height / nRows);
   int n = 0;
-  for (int i = 3; i < rows - 3; ++i)
-    for (int j = 3; j < cols - 3; ++j) {
-      if (!corner[(size_t)i * cols + j]) continue;
-      const uint8_t *sc = &score[(size_t)i * cols + j];
-      const int s0 = sc[0];
-      if (nonmax && !(s0 > sc[1] && s0 > sc[-1] && s0 > sc[-cols - 1] && s0 > sc[-cols] && s0 > sc[-cols + 1] && s0 > sc[cols - 1] &&
-                      s0 > sc[cols] && s0 > sc[cols + 1]))
-        continue;
-      if (mask && !mask[(size_t)i * cols + j]) continue;
-      if (n < max_out) { xy[2 * n] = (float)j; xy[2 * n + 1] = (float)i; response[n] = (float)s0; }
-      ++n;
+  std::vector<float> cxy, crs;
+  for (int i = 0; i < nRows; i++) {
+    const float iniY = minBorderY + i * hCell;
+    float maxY = iniY + hCell + 6;
+    if (iniY >= maxBorderY - 3) continue;
+    if (maxY > maxBorderY) maxY = maxBorderY;
+    for (int j = 0; j < nCols; j++) {
+      const float iniX = minBorderX + j * wCell;
+      float maxX = iniX + wCell + 6;
+      if (iniX >= maxBorderX - 6) continue;
+      if (maxX > maxBorderX) maxX = maxBorderX;
+      const int x0 = (int)iniX, y0 = (int)iniY, cw = (int)maxX - x0, ch = (int)maxY - y0;
+      const int cap = std::max(cw * ch, 1);
+      cxy.resize((size_t)2 * cap); crs.resize((size_t)cap);
+      const uint8_t *view = img + (size_t)y0 * step + x0;
+      int k = fast_detect(view, cw, ch, step, ini_th, true, nullptr, cap, cxy.data(), crs.data());
+      if (k == 0) k = fast_detect(view, cw, ch, step, min_th, true, nullptr, cap, cxy.data(), crs.data());
+      for (int q = 0; q < k; ++q) {
+        const float px = cxy[2 * q] + j * wCell + minBorderX, py = cxy[2 * q + 1] + i * hCell + minBorderY;
+        if (mask && !mask[(size_t)(int)py * cols + (int)px]) continue;
+        if (n < max_out) { xy[2 * n] = px; xy[2 * n + 1] = py; response[n] = crs[q]; }
+        ++n;
+      }
     }
+  }
   return n;
 }
 
@@ -1048,6 +1020,12 @@ int pagk_oracle_set_predict_keypoints_and_mask(int n_pairs, const pagk_carry_in 
 int pagk_oracle_fast_detect(const uint8_t *img, int width, int height, int pitch, int threshold, int nonmax, const uint8_t *mask,
                             int max_out, float *xy, float *response, int *n_out) {
   *n_out = fast_detect(img, width, height, pitch, threshold, nonmax != 0, mask, max_out, xy, response);
+  return PAGK_OK;
+}
+
+int pagk_oracle_orb_cell_detect(const uint8_t *img, int width, int height, int pitch, int ini_th, int min_th, const uint8_t *mask,
+                                int max_out, float *xy, float *response, int *n_out) {
+  *n_out = orb_cell_detect(img, width, height, pitch, ini_th, min_th, mask, max_out, xy, response);
   return PAGK_OK;
 }
 

@@ -1,6 +1,6 @@
 // ref_harness.cpp -- C entry points over the REFERENCE'S OWN hot-path sources.  TEST INFRASTRUCTURE ONLY.
 //
-// oracle/_ref/libpagk_ref.so = this file + /root/reference/src/{gyro_aided_tracker,patch_match,utils,frame}.cpp compiled
+// oracle/_ref/libpagk_ref.so = this file + /root/reference/src/{gyro_aided_tracker,patch_match,utils,frame}.cpp and src/ORBextractor.cc compiled
 // unmodified, where they lie, against the stand-in headers in oracle/ref_shim/ (OpenCV, Eigen3 and glog are not
 // installed here).  See oracle/ref_shim/pagk_cv_shim.hpp for what is real and what is restated.  Only tests/ and
 // bench.py's CPU legs load it; it is the checker for oracle/pagk_oracle.cpp (the restatement that travels to the GPU
@@ -19,6 +19,7 @@
 #include "gyro_aided_tracker.h"
 #include "patch_match.h"
 #include "pagk_cv_resize.h"
+#include "pagk_cv_fast.h"
 
 #include <atomic>
 
@@ -46,6 +47,28 @@ void resize(const Mat &src, Mat &dst, Size dsize, double, double, int interpolat
   finish_guard(out);
   dst = out;
 }
+void FAST(const Mat &image, std::vector<KeyPoint> &keypoints, int threshold, bool nonmaxSuppression) {
+  if (image.type() != CV_8UC1) shim_abort("FAST on this type");
+  const int cap = image.rows * image.cols;
+  std::vector<float> xy((size_t)2 * std::max(cap, 1)), rs((size_t)std::max(cap, 1));
+  const int n = pagk_cv::fast_detect(image.data, image.cols, image.rows, (int)image.step, threshold, nonmaxSuppression, nullptr, cap,
+                                     xy.data(), rs.data());
+  keypoints.clear();
+  for (int k = 0; k < n; ++k) keypoints.push_back(KeyPoint(xy[2 * k], xy[2 * k + 1], 7.f, -1, rs[k]));
+}
+void copyMakeBorder(const Mat &src, Mat &dst, int top, int bottom, int left, int right, int borderType) {
+  if ((borderType & ~BORDER_ISOLATED) != BORDER_REFLECT_101 || src.type() != CV_8UC1) shim_abort("copyMakeBorder of this kind");
+  const int R = src.rows + top + bottom, C = src.cols + left + right;
+  if (dst.rows != R || dst.cols != C || dst.type() != src.type() || !dst.data) dst.create(R, C, src.type());
+  auto refl = [](int p, int n) { if (n == 1) return 0; while (p < 0 || p >= n) p = p < 0 ? -p : 2 * (n - 1) - p; return p; };
+  // through a temporary: src may be a view of dst (ORBextractor::ComputePyramid, src/ORBextractor.cc:1222)
+  std::vector<uchar> tmp((size_t)R * C);
+  for (int r = 0; r < R; ++r) {
+    const uchar *srow = src.data + (size_t)refl(r - top, src.rows) * src.step;
+    for (int c = 0; c < C; ++c) tmp[(size_t)r * C + c] = srow[refl(c - left, src.cols)];
+  }
+  for (int r = 0; r < R; ++r) std::memcpy(dst.data + (size_t)r * dst.step, &tmp[(size_t)r * C], (size_t)C);
+}
 Mat findHomography(const std::vector<Point2f> &, const std::vector<Point2f> &, int, double, Mat &) {
   if (g_injected_H.empty()) shim_abort("findHomography (no model injected)");
   return g_injected_H.clone();
@@ -65,8 +88,8 @@ void initUndistortRectifyMap(const Mat &, const Mat &, const Mat &, const Mat &,
 Mat getOptimalNewCameraMatrix(const Mat &, const Mat &, Size, double, Size, void *) { shim_abort("getOptimalNewCameraMatrix"); }
 }  // namespace cv
 
-// src/frame.cpp is compiled too (Frame::SetPredictKeyPointsAndMask lives there); the ORB extractor it can call is not.
-void ORB_SLAM2::ORBextractor::DetectFeatures(cv::InputArray, cv::InputArray, std::vector<cv::KeyPoint> &) { cv::shim_abort("ORBextractor::DetectFeatures"); }
+// src/frame.cpp (Frame::SetPredictKeyPointsAndMask) and src/ORBextractor.cc (ORBextractor::DetectFeatures, the keypoint
+// top-up) are compiled too.
 
 // ------------------------------------------------------------------------------------------------------------------
 namespace {
@@ -364,6 +387,24 @@ int pagk_ref_set_predict_keypoints_and_mask(int n_pairs, const pagk_carry_in *in
     if (o.mask)
       for (int y = 0; y < ci.height; ++y) std::memcpy(o.mask + (size_t)y * ci.width, cur.mMask.data + (size_t)y * cur.mMask.step, (size_t)ci.width);
   }
+  return PAGK_OK;
+}
+
+// ORB_SLAM2::ORBextractor(nfeatures, 1.2f, 1, iniThFAST, minThFAST).DetectFeatures(image, mask, keypoints)
+// (src/ORBextractor.cc:1148-1205 with ComputeKeyPointsOctTree :789-876): the keypoint top-up of Frame::DetectKeyPoints
+// (src/frame.cpp:155-219).  With one level and nfeatures larger than the number of candidates, DistributeOctTree keeps every
+// keypoint (each ends in a node of its own), so the output is the set the per-cell FAST calls produced.
+int pagk_ref_orb_detect(const uint8_t *img, int width, int height, int pitch, const uint8_t *mask, int nfeatures, int ini_th, int min_th,
+                        int max_out, float *xy, float *response, int *n_out) {
+  cv::Mat image = image_mat(img, width, height, pitch);
+  cv::Mat m;
+  if (mask) { m = cv::Mat(height, width, CV_8UC1); std::memcpy(m.data, mask, (size_t)width * height); }
+  else m = cv::Mat::ones(height, width, CV_8UC1);
+  ORB_SLAM2::ORBextractor ex(nfeatures, 1.2f, 1, ini_th, min_th);
+  std::vector<cv::KeyPoint> keys;
+  ex.DetectFeatures(image, m, keys);
+  *n_out = (int)keys.size();
+  for (int k = 0; k < (int)keys.size() && k < max_out; ++k) { xy[2 * k] = keys[k].pt.x; xy[2 * k + 1] = keys[k].pt.y; response[k] = keys[k].response; }
   return PAGK_OK;
 }
 

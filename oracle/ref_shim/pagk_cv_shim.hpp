@@ -113,6 +113,8 @@ template <typename T> static inline Point_<T> &operator/=(Point_<T> &a, double b
 template <typename T> static inline Point_<T> operator/(const Point_<T> &a, int b) { Point_<T> t(a); t /= b; return t; }
 template <typename T> static inline Point_<T> operator/(const Point_<T> &a, float b) { Point_<T> t(a); t /= b; return t; }
 template <typename T> static inline Point_<T> operator/(const Point_<T> &a, double b) { Point_<T> t(a); t /= b; return t; }
+template <typename T> static inline Point_<T> &operator*=(Point_<T> &a, float b) { a.x = saturate_cast<T>(a.x * b); a.y = saturate_cast<T>(a.y * b); return a; }
+template <typename T> static inline Point_<T> &operator*=(Point_<T> &a, double b) { a.x = saturate_cast<T>(a.x * b); a.y = saturate_cast<T>(a.y * b); return a; }
 template <typename T> static inline Point_<T> &operator+=(Point_<T> &a, const Point_<T> &b) { a.x += b.x; a.y += b.y; return a; }
 template <typename T> static inline Point_<T> &operator-=(Point_<T> &a, const Point_<T> &b) { a.x -= b.x; a.y -= b.y; return a; }
 template <typename T> static inline bool operator==(const Point_<T> &a, const Point_<T> &b) { return a.x == b.x && a.y == b.y; }
@@ -243,9 +245,14 @@ class Mat {
   size_t elemSize() const { return elemSize1() * channels(); }
   bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
   size_t total() const { return (size_t)rows * cols; }
+  size_t step1() const { return step / elemSize1(); }
   bool isContinuous() const { return step == (size_t)cols * elemSize() || rows == 1; }
   Size size() const { return Size(cols, rows); }
 
+  template <typename T> T *ptr(int r = 0) { return (T *)(data + (size_t)r * step); }
+  template <typename T> const T *ptr(int r = 0) const { return (const T *)(data + (size_t)r * step); }
+  uchar *ptr(int r = 0) { return data + (size_t)r * step; }
+  const uchar *ptr(int r = 0) const { return data + (size_t)r * step; }
   template <typename T> T &at(int r, int c) { return *(T *)(data + (size_t)r * step + (size_t)c * sizeof(T)); }
   template <typename T> const T &at(int r, int c) const { return *(const T *)(data + (size_t)r * step + (size_t)c * sizeof(T)); }
   template <typename T> T &at(int i) { return const_cast<T &>(static_cast<const Mat *>(this)->at<T>(i)); }
@@ -519,8 +526,21 @@ inline MatExpr operator+(const MatExpr &a, const Mat &b) { return a + MatExpr(b)
 inline Mat &operator*=(Mat &a, const Mat &b) { a = shim::gemm(a, b, 1.0, 0); return a; }
 
 // ------------------------------------------------------------------------------------------ functions
-struct _InputArray { _InputArray(const Mat &) {} _InputArray() {} };
-struct _OutputArray { _OutputArray(Mat &) {} _OutputArray() {} };
+struct _InputArray {
+  const Mat *m;
+  _InputArray() : m(nullptr) {}
+  _InputArray(const Mat &m_) : m(&m_) {}
+  Mat getMat() const { return m ? *m : Mat(); }
+  bool empty() const { return !m || m->empty(); }
+};
+struct _OutputArray {
+  Mat *m;
+  _OutputArray() : m(nullptr) {}
+  _OutputArray(Mat &m_) : m(&m_) {}
+  void create(int r, int c, int type) const { if (m) m->create(r, c, type); }
+  Mat getMat() const { return m ? *m : Mat(); }
+  void release() const { if (m) *m = Mat(); }
+};
 typedef const _InputArray &InputArray;
 typedef const _OutputArray &OutputArray;
 
@@ -553,6 +573,29 @@ void calcOpticalFlowPyrLK(const Mat &prev, const Mat &next, const std::vector<Po
 void undistortPoints(const Mat &src, Mat &dst, const Mat &K, const Mat &dist, const Mat &R, const Mat &P);
 void initUndistortRectifyMap(const Mat &K, const Mat &dist, const Mat &R, const Mat &newK, Size size, int type, Mat &m1, Mat &m2);
 Mat getOptimalNewCameraMatrix(const Mat &K, const Mat &dist, Size size, double alpha, Size newSize, void *roi = nullptr);
+
+// ---- for src/ORBextractor.cc (the keypoint top-up; only DetectFeatures / ComputeKeyPointsOctTree are exercised) ----
+enum { BORDER_REFLECT_101 = 4, BORDER_ISOLATED = 16 };
+#ifndef CV_PI
+#define CV_PI 3.1415926535897932384626433832795
+#endif
+inline int cvFloor(double v) { const int i = (int)v; return i - (i > v); }
+inline int cvCeil(double v) { const int i = (int)v; return i + (i < v); }
+inline int cvRound(double v) { return (int)lrint(v); }
+inline int cvRound(float v) { return (int)lrintf(v); }
+inline int cvRound(int v) { return v; }
+inline float fastAtan2(float y, float x) {  // degrees in [0, 360); the keypoint angle is never read on the path
+  float a = std::atan2(y, x) * 57.29577951308232f;
+  return a < 0.f ? a + 360.f : a;
+}
+struct KeyPointsFilter {
+  static void retainBest(std::vector<KeyPoint> &, int) { shim_abort("KeyPointsFilter::retainBest"); }
+};
+inline void GaussianBlur(const Mat &, Mat &, Size, double, double = 0, int = BORDER_REFLECT_101) { shim_abort("GaussianBlur"); }
+// src into the centre of a (rows + top + bottom) x (cols + left + right) dst, borders mirrored without repeating the edge pixel
+void copyMakeBorder(const Mat &src, Mat &dst, int top, int bottom, int left, int right, int borderType);
+// cv::FAST, TYPE_9_16: oracle/pagk_cv_fast.h (bit-exact against cv2.FastFeatureDetector fixtures)
+void FAST(const Mat &image, std::vector<KeyPoint> &keypoints, int threshold, bool nonmaxSuppression = true);
 
 // ---- not on the path: declared so that src/frame.cpp (Frame::SetPredictKeyPointsAndMask lives there) compiles ----
 enum { FONT_HERSHEY_PLAIN = 1, FONT_HERSHEY_DUPLEX = 2, LINE_AA = 16 };

@@ -23,7 +23,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 REFERENCE_ROOT = os.environ.get("PAGK_REFERENCE_ROOT", "/root/reference")
 OUT_DIR = os.path.join(_HERE, "_ref")
 LIB = os.path.join(OUT_DIR, "libpagk_ref.so")
-REF_SOURCES = ["src/gyro_aided_tracker.cpp", "src/patch_match.cpp", "src/utils.cpp", "src/frame.cpp"]
+REF_SOURCES = ["src/gyro_aided_tracker.cpp", "src/patch_match.cpp", "src/utils.cpp", "src/frame.cpp", "src/ORBextractor.cc"]
 # the reference's own flags (CMakeLists.txt:10-11, 17-20: -O3 -std=c++11, no -march, no -ffast-math)
 CXXFLAGS = ["-O3", "-std=c++11", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-pthread", "-w"]
 _f32p = C.POINTER(C.c_float)
@@ -40,7 +40,7 @@ def available() -> bool:
 
 def _deps():
     shim = os.path.join(_HERE, "ref_shim")
-    own = [os.path.join(_HERE, "ref_harness.cpp"), os.path.join(_HERE, "pagk_cv_resize.h"),
+    own = [os.path.join(_HERE, "ref_harness.cpp"), os.path.join(_HERE, "pagk_cv_resize.h"), os.path.join(_HERE, "pagk_cv_fast.h"),
            os.path.join(shim, "pagk_cv_shim.hpp"), os.path.join(shim, "pagk_eigen_shim.hpp"),
            os.path.join(_HERE, "..", "include", "pagk.h")]
     return own + [os.path.join(REFERENCE_ROOT, s) for s in REF_SOURCES]
@@ -85,6 +85,8 @@ def load():
         lib.pagk_ref_inject_models.restype = None
         lib.pagk_ref_geometry_validation.argtypes = [C.c_int, C.POINTER(capi.PagkGeometryIn), C.POINTER(capi.PagkGeometryOut)]
         lib.pagk_ref_set_predict_keypoints_and_mask.argtypes = [C.c_int, C.POINTER(capi.PagkCarryIn), C.POINTER(capi.PagkCarryOut)]
+        lib.pagk_ref_orb_detect.argtypes = [C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int,
+                                            C.c_int, _f32p, _f32p, C.POINTER(C.c_int)]
         _lib = lib
     return _lib
 
@@ -126,6 +128,19 @@ def set_predict_keypoints_and_mask(cases):
         ins[k], outs[k] = c.structs()
     rc = load().pagk_ref_set_predict_keypoints_and_mask(len(cases), ins, outs)
     return rc, [int(o.n_out) for o in outs]
+
+
+def orb_detect(img, ini_th=20, min_th=7, nfeatures=1000000, mask=None, max_out=400000):
+    """ORBextractor(nfeatures, 1.2, 1, ini_th, min_th).DetectFeatures(img, mask): (xy [n][2], response [n]) in its output order"""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    u8 = C.POINTER(C.c_uint8)
+    xy, rs, n = np.zeros((max_out, 2), np.float32), np.zeros(max_out, np.float32), C.c_int(0)
+    m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+    load().pagk_ref_orb_detect(img.ctypes.data_as(u8), w, h, img.strides[0], None if m is None else m.ctypes.data_as(u8), nfeatures,
+                               ini_th, min_th, max_out, xy.ctypes.data_as(_f32p), rs.ctypes.data_as(_f32p), C.byref(n))
+    k = min(n.value, max_out)
+    return xy[:k].copy(), rs[:k].copy()
 
 
 def track(pair: capi.PairInputs, params: capi.PagkParams, n_threads: int = 1):

@@ -190,6 +190,8 @@ SYMBOLS = {
     "pagk_geometry_validation": (C.c_int, [_H, C.c_int, C.POINTER(PagkGeometryIn), C.POINTER(PagkGeometryOut)]),
     "pagk_fast_detect": (C.c_int, [_H, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u8p, C.c_int, _f32p, _f32p,
                                    C.POINTER(C.c_int)]),
+    "pagk_orb_cell_detect": (C.c_int, [_H, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u8p, C.c_int, _f32p, _f32p,
+                                       C.POINTER(C.c_int)]),
     "pagk_set_predict_keypoints_and_mask": (C.c_int, [_H, C.c_int, C.POINTER(PagkCarryIn), C.POINTER(PagkCarryOut)]),
 }
 

@@ -892,21 +892,77 @@ int pagk_set_predict_keypoints_and_mask(pagk_handle *h, int n_pairs, const pagk_
   return PAGK_OK;
 }
 
+// device block of the detector entry points: image | mask | score (u16) | keep | row or cell counts | their offsets
+static int fast_buffers(pagk_handle *h, size_t *off_mask, size_t *off_score, size_t *off_keep, size_t *off_rc, size_t *off_ro) {
+  const size_t WH = align_up((size_t)h->cfg.max_width * h->cfg.max_height, 256);
+  const size_t n_cells = (size_t)(h->cfg.max_width / 30 + 1) * (size_t)(h->cfg.max_height / 30 + 1);
+  const size_t n_int = std::max((size_t)h->cfg.max_height, n_cells) + 1;
+  const size_t RW = align_up(n_int * sizeof(int), 256);
+  *off_mask = WH; *off_score = 2 * WH; *off_keep = 4 * WH; *off_rc = 5 * WH; *off_ro = *off_rc + RW;
+  if (!h->d_fast) CU(cudaMalloc(&h->d_fast, *off_ro + RW));
+  return PAGK_OK;
+}
+
+static int fast_out_buffers(pagk_handle *h, int max_out) {
+  if (max_out > h->fast_out_cap) {
+    cudaFree(h->d_fast_out); h->d_fast_out = nullptr; h->fast_out_cap = 0;
+    CU(cudaMalloc(&h->d_fast_out, align_up((size_t)max_out * 8, 256) + align_up((size_t)max_out * 4, 256)));
+    h->fast_out_cap = max_out;
+  }
+  return PAGK_OK;
+}
+
+int pagk_orb_cell_detect(pagk_handle *h, const uint8_t *img, int width, int height, int pitch, int ini_th, int min_th,
+                         const uint8_t *mask, int max_out, float *xy, float *response, int *n_out) {
+  if (!h || !img || !n_out || max_out < 0 || (max_out > 0 && (!xy || !response))) return fail(PAGK_ERR_INVALID, "null argument");
+  if (width < 1 || height < 1 || pitch < width || width > h->cfg.max_width || height > h->cfg.max_height)
+    return fail(PAGK_ERR_INVALID, "image exceeds pagk_config.max_width/max_height");
+  *n_out = 0;
+  // the cell grid, with the reference's own float arithmetic (src/ORBextractor.cc:793-811)
+  const int EDGE_THRESHOLD = 19;
+  const float W = 30;
+  PagkCellGrid g;
+  g.min_x = EDGE_THRESHOLD - 3; g.min_y = g.min_x;
+  g.max_x = width - EDGE_THRESHOLD + 3; g.max_y = height - EDGE_THRESHOLD + 3;
+  const float fw = (float)(g.max_x - g.min_x), fh = (float)(g.max_y - g.min_y);
+  g.n_cols = (int)(fw / W); g.n_rows = (int)(fh / W);
+  if (g.n_cols < 1 || g.n_rows < 1) return PAGK_OK;
+  g.w_cell = (int)std::ceil(fw / g.n_cols); g.h_cell = (int)std::ceil(fh / g.n_rows);
+  CU(cudaSetDevice(h->cfg.device));
+  size_t off_mask, off_score, off_keep, off_rc, off_ro;
+  if (fast_buffers(h, &off_mask, &off_score, &off_keep, &off_rc, &off_ro) != PAGK_OK) return PAGK_ERR_CUDA;
+  if (fast_out_buffers(h, max_out) != PAGK_OK) return PAGK_ERR_CUDA;
+  cudaStream_t st = h->stream;
+  CU(cudaMemcpy2DAsync(h->d_fast, (size_t)width, img, (size_t)pitch, (size_t)width, (size_t)height, cudaMemcpyHostToDevice, st));
+  if (mask) CU(cudaMemcpyAsync(h->d_fast + off_mask, mask, (size_t)width * height, cudaMemcpyHostToDevice, st));
+  float2 *d_xy = (float2 *)h->d_fast_out;
+  float *d_rs = (float *)(h->d_fast_out + align_up((size_t)h->fast_out_cap * 8, 256));
+  const int n_cells = g.n_cols * g.n_rows;
+  CU((cudaError_t)pagk_launch_orb_cells(h->d_fast, width, height, ini_th, min_th, mask ? h->d_fast + off_mask : nullptr,
+                                        (unsigned short *)(h->d_fast + off_score), h->d_fast + off_keep, (int *)(h->d_fast + off_rc),
+                                        (int *)(h->d_fast + off_ro), g, max_out, d_xy, d_rs, st, &h->launches));
+  int total_found = 0;
+  CU(cudaMemcpyAsync(&total_found, h->d_fast + off_ro + (size_t)n_cells * sizeof(int), sizeof(int), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  const int n = total_found < max_out ? total_found : max_out;
+  if (n > 0) {
+    CU(cudaMemcpyAsync(xy, d_xy, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(response, d_rs, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  *n_out = total_found;
+  return PAGK_OK;
+}
+
 int pagk_fast_detect(pagk_handle *h, const uint8_t *img, int width, int height, int pitch, int threshold, int nonmax,
                      const uint8_t *mask, int max_out, float *xy, float *response, int *n_out) {
   if (!h || !img || !n_out || max_out < 0 || (max_out > 0 && (!xy || !response))) return fail(PAGK_ERR_INVALID, "null argument");
   if (width < 1 || height < 1 || pitch < width || width > h->cfg.max_width || height > h->cfg.max_height)
     return fail(PAGK_ERR_INVALID, "image exceeds pagk_config.max_width/max_height");
   CU(cudaSetDevice(h->cfg.device));
-  const size_t WH = align_up((size_t)h->cfg.max_width * h->cfg.max_height, 256), RW = align_up((size_t)(h->cfg.max_height + 1) * sizeof(int), 256);
-  // layout of d_fast: image | mask | score (u16) | keep | row counts | row offsets
-  const size_t off_mask = WH, off_score = 2 * WH, off_keep = 4 * WH, off_rc = 5 * WH, off_ro = off_rc + RW, total = off_ro + RW;
-  if (!h->d_fast) CU(cudaMalloc(&h->d_fast, total));
-  if (max_out > h->fast_out_cap) {
-    cudaFree(h->d_fast_out); h->d_fast_out = nullptr; h->fast_out_cap = 0;
-    CU(cudaMalloc(&h->d_fast_out, align_up((size_t)max_out * 8, 256) + align_up((size_t)max_out * 4, 256)));
-    h->fast_out_cap = max_out;
-  }
+  size_t off_mask, off_score, off_keep, off_rc, off_ro;
+  if (fast_buffers(h, &off_mask, &off_score, &off_keep, &off_rc, &off_ro) != PAGK_OK) return PAGK_ERR_CUDA;
+  if (fast_out_buffers(h, max_out) != PAGK_OK) return PAGK_ERR_CUDA;
   cudaStream_t st = h->stream;
   CU(cudaMemcpy2DAsync(h->d_fast, (size_t)width, img, (size_t)pitch, (size_t)width, (size_t)height, cudaMemcpyHostToDevice, st));
   if (mask) CU(cudaMemcpyAsync(h->d_fast + off_mask, mask, (size_t)width * height, cudaMemcpyHostToDevice, st));

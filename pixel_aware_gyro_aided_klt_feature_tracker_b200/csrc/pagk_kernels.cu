@@ -918,6 +918,101 @@ __global__ void __launch_bounds__(256) pagk_fast_emit_kernel(const unsigned shor
 }
 
 // =================================================================================================
+// The detection half of ORBextractor::ComputeKeyPointsOctTree for one level (reference src/ORBextractor.cc:789-852) plus the
+// mask filter of DetectFeatures (:1200-1203).  cv::FAST on a cell's sub-image sees the same 16-pixel circles as on the whole
+// image, a corner's score does not depend on the threshold it was found with, and it is a corner at threshold T exactly when
+// its score is >= T; so one score image at min_th serves both thresholds of every cell.  What is per cell is the non-maximum
+// suppression: neighbours outside the cell's interior (its sub-image minus FAST's 3-pixel border) or below the threshold
+// count as 0.  The interiors of the cells tile the image without overlap.  One warp per cell.
+// =================================================================================================
+__device__ __forceinline__ void pagk_cell_box(const PagkCellGrid &g, int ci, int cj, int &x0, int &y0, int &x1, int &y1, bool &live) {
+  const float iniY = (float)(g.min_y + ci * g.h_cell), iniX = (float)(g.min_x + cj * g.w_cell);
+  float maxY = iniY + (float)g.h_cell + 6.0f, maxX = iniX + (float)g.w_cell + 6.0f;
+  live = !(iniY >= (float)(g.max_y - 3)) && !(iniX >= (float)(g.max_x - 6));
+  if (maxY > (float)g.max_y) maxY = (float)g.max_y;
+  if (maxX > (float)g.max_x) maxX = (float)g.max_x;
+  // interior of the sub-image [ini, max): FAST skips a 3-pixel border
+  x0 = (int)iniX + 3; y0 = (int)iniY + 3; x1 = (int)maxX - 3; y1 = (int)maxY - 3;
+}
+
+__device__ __forceinline__ int pagk_cell_score(const unsigned short *__restrict__ score, int cols, int x, int y, int x0, int y0, int x1,
+                                               int y1, int th) {
+  if (x < x0 || x >= x1 || y < y0 || y >= y1) return 0;
+  const unsigned short s = score[(size_t)y * cols + x];
+  return ((s & 0x100) && (int)(s & 0xff) >= th) ? (int)(s & 0xff) : 0;
+}
+
+__device__ __forceinline__ bool pagk_cell_keep(const unsigned short *__restrict__ score, int cols, int x, int y, int x0, int y0, int x1,
+                                               int y1, int th) {
+  const unsigned short s = score[(size_t)y * cols + x];
+  if (!(s & 0x100) || (int)(s & 0xff) < th) return false;
+  const int s0 = s & 0xff;
+  return s0 > pagk_cell_score(score, cols, x + 1, y, x0, y0, x1, y1, th) && s0 > pagk_cell_score(score, cols, x - 1, y, x0, y0, x1, y1, th) &&
+         s0 > pagk_cell_score(score, cols, x - 1, y - 1, x0, y0, x1, y1, th) && s0 > pagk_cell_score(score, cols, x, y - 1, x0, y0, x1, y1, th) &&
+         s0 > pagk_cell_score(score, cols, x + 1, y - 1, x0, y0, x1, y1, th) && s0 > pagk_cell_score(score, cols, x - 1, y + 1, x0, y0, x1, y1, th) &&
+         s0 > pagk_cell_score(score, cols, x, y + 1, x0, y0, x1, y1, th) && s0 > pagk_cell_score(score, cols, x + 1, y + 1, x0, y0, x1, y1, th);
+}
+
+__global__ void __launch_bounds__(256) pagk_orb_cells_kernel(const unsigned short *__restrict__ score, const unsigned char *__restrict__ mask,
+                                                           int cols, PagkCellGrid g, int ini_th, int min_th,
+                                                           unsigned char *__restrict__ keep, int *__restrict__ cell_count) {
+  const int cell = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (cell >= g.n_cols * g.n_rows) return;
+  const int ci = cell / g.n_cols, cj = cell - ci * g.n_cols;
+  int x0, y0, x1, y1;
+  bool live;
+  pagk_cell_box(g, ci, cj, x0, y0, x1, y1, live);
+  const int w = x1 - x0, hgt = y1 - y0, npx = (live && w > 0 && hgt > 0) ? w * hgt : 0;
+  // does ini_th leave anything in this cell?
+  int n_ini = 0;
+  for (int p0 = 0; p0 < npx; p0 += 32) {
+    const int p = p0 + lane;
+    bool k = false;
+    if (p < npx) { const int y = y0 + p / w, x = x0 + p % w; k = pagk_cell_keep(score, cols, x, y, x0, y0, x1, y1, ini_th); }
+    n_ini += __popc(__ballot_sync(0xffffffffu, k));
+  }
+  const int th = n_ini > 0 ? ini_th : min_th;
+  int cnt = 0;
+  for (int p0 = 0; p0 < npx; p0 += 32) {
+    const int p = p0 + lane;
+    bool k = false;
+    if (p < npx) {
+      const int y = y0 + p / w, x = x0 + p % w;
+      k = pagk_cell_keep(score, cols, x, y, x0, y0, x1, y1, th) && (!mask || mask[(size_t)y * cols + x] != 0);
+      keep[(size_t)y * cols + x] = k ? 1 : 0;
+    }
+    cnt += __popc(__ballot_sync(0xffffffffu, k));
+  }
+  if (lane == 0) cell_count[cell] = cnt;
+}
+
+__global__ void __launch_bounds__(256) pagk_orb_emit_kernel(const unsigned short *__restrict__ score, const unsigned char *__restrict__ keep,
+                                                          const int *__restrict__ cell_offset, int cols, PagkCellGrid g, int max_out,
+                                                          float2 *__restrict__ xy, float *__restrict__ response) {
+  const int cell = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (cell >= g.n_cols * g.n_rows) return;
+  int base = cell_offset[cell];
+  if (cell_offset[cell + 1] == base) return;
+  const int ci = cell / g.n_cols, cj = cell - ci * g.n_cols;
+  int x0, y0, x1, y1;
+  bool live;
+  pagk_cell_box(g, ci, cj, x0, y0, x1, y1, live);
+  const int w = x1 - x0, npx = w * (y1 - y0);
+  for (int p0 = 0; p0 < npx; p0 += 32) {
+    const int p = p0 + lane;
+    bool k = false;
+    int x = 0, y = 0;
+    if (p < npx) { y = y0 + p / w; x = x0 + p % w; k = keep[(size_t)y * cols + x] != 0; }
+    const unsigned b = __ballot_sync(0xffffffffu, k);
+    if (k) {
+      const int pos = base + __popc(b & ((1u << lane) - 1u));
+      if (pos < max_out) { xy[pos] = make_float2((float)x, (float)y); response[pos] = (float)(score[(size_t)y * cols + x] & 0xff); }
+    }
+    base += __popc(b);
+  }
+}
+
+// =================================================================================================
 // launch wrappers (host)
 // =================================================================================================
 int pagk_pyramid_fused_max_level() {
@@ -1029,6 +1124,21 @@ int pagk_launch_fast(const unsigned char *img, int cols, int rows, int threshold
   pagk_fast_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(score, mask, cols, rows, nonmax, keep, row_count);
   pagk_fast_scan_kernel<<<1, 1024, 0, st>>>(row_count, rows, row_offset);
   pagk_fast_emit_kernel<<<(rows + 7) / 8, 256, 0, st>>>(score, keep, row_offset, cols, rows, max_out, xy, response);
+  *launches += 4;
+  return (int)cudaGetLastError();
+}
+
+int pagk_launch_orb_cells(const unsigned char *img, int cols, int rows, int ini_th, int min_th, const unsigned char *mask,
+                          unsigned short *score, unsigned char *keep, int *cell_count, int *cell_offset, PagkCellGrid grid,
+                          int max_out, float2 *xy, float *response, cudaStream_t st, long long *launches) {
+  const int n_cells = grid.n_cols * grid.n_rows;
+  if (cols <= 0 || rows <= 0 || n_cells <= 0) return 0;
+  const int t = min_th < 0 ? 0 : min_th > 255 ? 255 : min_th;
+  dim3 g((cols + 31) / 32, (rows + 7) / 8);
+  pagk_fast_score_kernel<<<g, 256, 0, st>>>(img, cols, rows, t, 1, score);
+  pagk_orb_cells_kernel<<<(n_cells + 7) / 8, 256, 0, st>>>(score, mask, cols, grid, ini_th, min_th, keep, cell_count);
+  pagk_fast_scan_kernel<<<1, 1024, 0, st>>>(cell_count, n_cells, cell_offset);
+  pagk_orb_emit_kernel<<<(n_cells + 7) / 8, 256, 0, st>>>(score, keep, cell_offset, cols, grid, max_out, xy, response);
   *launches += 4;
   return (int)cudaGetLastError();
 }

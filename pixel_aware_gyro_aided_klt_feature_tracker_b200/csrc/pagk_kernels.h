@@ -30,6 +30,12 @@ int pagk_launch_carry(const PagkCarryConst *cc, const float2 *pt_predict, const 
 int pagk_launch_fast(const unsigned char *img, int cols, int rows, int threshold, int nonmax, const unsigned char *mask,
                      unsigned short *score, unsigned char *keep, int *row_count, int *row_offset, int max_out, float2 *xy,
                      float *response, cudaStream_t st, long long *launches);
+// per-cell FAST of ORBextractor::ComputeKeyPointsOctTree (one level): scores at min_th, per-cell threshold choice + keep flags,
+// scan of the cell counts, ordered emit (cells row-major, row-major inside a cell)
+struct PagkCellGrid { int n_cols, n_rows, w_cell, h_cell, min_x, min_y, max_x, max_y; };
+int pagk_launch_orb_cells(const unsigned char *img, int cols, int rows, int ini_th, int min_th, const unsigned char *mask,
+                          unsigned short *score, unsigned char *keep, int *cell_count, int *cell_offset, PagkCellGrid grid,
+                          int max_out, float2 *xy, float *response, cudaStream_t st, long long *launches);
 int pagk_launch_count_status(const PagkPairConst *pcs, const PagkOutPtrs &out, int max_keys, int n_pairs,
                              PagkPairResult *res, cudaStream_t st, long long *launches);
 

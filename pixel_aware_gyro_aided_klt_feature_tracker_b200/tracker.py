@@ -126,6 +126,20 @@ class Context:
         k = min(n.value, max_out)
         return xy[:k].copy(), rs[:k].copy()
 
+    def orb_cell_detect(self, img, ini_th=20, min_th=7, mask=None, max_out=400000):
+        """the per-cell FAST detection of ORBextractor::DetectFeatures, one level (include/pagk.h)"""
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape
+        xy, rs, n = np.zeros((max_out, 2), np.float32), np.zeros(max_out, np.float32), C.c_int(0)
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        u8 = C.POINTER(C.c_uint8)
+        f32 = C.POINTER(C.c_float)
+        _check(self.lib, self.lib.pagk_orb_cell_detect(self.handle, img.ctypes.data_as(u8), w, h, img.strides[0], int(ini_th), int(min_th),
+                                                       None if m is None else m.ctypes.data_as(u8), max_out, xy.ctypes.data_as(f32),
+                                                       rs.ctypes.data_as(f32), C.byref(n)))
+        k = min(n.value, max_out)
+        return xy[:k].copy(), rs[:k].copy()
+
     def set_stage_timing(self, on: bool):
         """CUDA events between the kernels of a run (per-stage clocks); off for throughput pipelines"""
         _check(self.lib, self.lib.pagk_set_stage_timing(self.handle, 1 if on else 0))

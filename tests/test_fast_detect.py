@@ -87,3 +87,47 @@ def test_cuda_fast_bit_exact(gpu_ctx, oracle):
         assert np.array_equal(gxy, cxy) and np.array_equal(grs, crs)
         gxy, grs = gpu_ctx.fast_detect(img, th, True, max_out=7)
         assert np.array_equal(gxy, cxy[:0] if False else oracle.fast_detect(img, th, True, max_out=7)[0])
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# the per-cell detection of ORBextractor::DetectFeatures (one level)
+# ---------------------------------------------------------------------------------------------------------------------------
+def _cell_images():
+    rng = np.random.default_rng(3)
+    out = []
+    for (h, w, k, ini, mn) in [(240, 320, 3, 20, 7), (480, 752, 5, 20, 7), (480, 640, 7, 30, 5), (100, 131, 2, 20, 7), (77, 300, 6, 40, 10)]:
+        img = rng.random((h, w)).astype(np.float32)
+        for _ in range(k):                      # cheap blur without cv2
+            img = (img + np.roll(img, 1, 0) + np.roll(img, -1, 0) + np.roll(img, 1, 1) + np.roll(img, -1, 1)) / 5
+        img = ((img - img.min()) / (img.max() - img.min()) * 255).astype(np.uint8)
+        img[h // 2:, w // 2:] = img[h // 2:, w // 2:] // 8 + 100      # a low-contrast quadrant: its cells fall back to min_th
+        out.append((img, ini, mn, (rng.random((h, w)) < 0.8).astype(np.uint8)))
+    return out
+
+
+def _sorted(xy, rs):
+    o = np.lexsort((xy[:, 0], xy[:, 1]))
+    return xy[o], rs[o]
+
+
+def test_cell_detection_matches_the_reference_DetectFeatures(oracle):
+    """ORBextractor(nfeatures = 10^6, 1.2, 1, ini, min).DetectFeatures of the reference build (src/ORBextractor.cc compiled
+    unmodified; its cv::FAST is the cv2-pinned restatement): with nfeatures above the candidate count the octree keeps every
+    keypoint, so the reference's output set is what the per-cell FAST calls produced"""
+    from oracle import reference
+    if reference.build() is None:
+        pytest.skip("neither /root/reference nor a prebuilt oracle/_ref/libpagk_ref.so is here")
+    for img, ini, mn, mask in _cell_images():
+        for m in (None, mask):
+            ax, ar = _sorted(*reference.orb_detect(img, ini, mn, mask=m))
+            bx, br = _sorted(*oracle.orb_cell_detect(img, ini, mn, mask=m))
+            assert len(ax) > 20 and np.array_equal(ax, bx) and np.array_equal(ar, br), img.shape
+
+
+@pytest.mark.gpu
+def test_cuda_cell_detection_bit_exact(gpu_ctx, oracle):
+    for img, ini, mn, mask in _cell_images():
+        for m in (None, mask):
+            gxy, grs = gpu_ctx.orb_cell_detect(img, ini, mn, mask=m)
+            cxy, crs = oracle.orb_cell_detect(img, ini, mn, mask=m)
+            assert len(gxy) == len(cxy) and np.array_equal(gxy, cxy) and np.array_equal(grs, crs), img.shape   # same order too
