@@ -306,6 +306,14 @@ int pagk_fast_detect(pagk_handle *h, const uint8_t *img, int width, int height, 
 int pagk_orb_cell_detect(pagk_handle *h, const uint8_t *img, int width, int height, int pitch, int ini_th, int min_th,
                          const uint8_t *mask, int max_out, float *xy, float *response, int *n_out);
 
+/* == cv::remap(src, dst, map_x, map_y, cv::INTER_LINEAR) on CV_8UC1 with CV_32FC1 maps and the default constant (0) border:
+ * the rectification both drivers run on every frame before tracking (Examples/Demo/RealSenseD435i.cpp:202,
+ * Examples/ROS/.../feature_tracker.cpp:137; the maps come from cv::initUndistortRectifyMap, include/imu_types.h:63-65).
+ * OpenCV's fixed-point arithmetic: coordinates rounded to 1/32 pixel, 15-bit weights, (sum + 2^14) >> 15.  Maps and dst are
+ * dst_height x dst_width, contiguous. */
+int pagk_remap_linear(pagk_handle *h, const uint8_t *src, int width, int height, int pitch, const float *map_x,
+                      const float *map_y, int dst_width, int dst_height, uint8_t *dst);
+
 #ifdef __cplusplus
 }
 #endif

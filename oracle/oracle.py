@@ -56,6 +56,7 @@ def load():
                                                 C.POINTER(C.c_int)]
         lib.pagk_oracle_orb_cell_detect.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u8p, C.c_int, _f32p, _f32p,
                                                     C.POINTER(C.c_int)]
+        lib.pagk_oracle_remap_linear.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, _f32p, _f32p, C.c_int, C.c_int, _u8p]
         _lib = lib
     return _lib
 
@@ -171,6 +172,18 @@ def orb_cell_detect(img, ini_th=20, min_th=7, mask=None, max_out=400000):
                                        rs.ctypes.data_as(_f32p), C.byref(n))
     k = min(n.value, max_out)
     return xy[:k].copy(), rs[:k].copy()
+
+
+def remap_linear(img, map_x, map_y):
+    """cv::remap(img, map_x, map_y, INTER_LINEAR), constant 0 border"""
+    img = np.ascontiguousarray(img, np.uint8)
+    mx, my = np.ascontiguousarray(map_x, np.float32), np.ascontiguousarray(map_y, np.float32)
+    h, w = img.shape
+    dh, dw = mx.shape
+    out = np.zeros((dh, dw), np.uint8)
+    load().pagk_oracle_remap_linear(img.ctypes.data_as(_u8p), w, h, img.strides[0], mx.ctypes.data_as(_f32p), my.ctypes.data_as(_f32p),
+                                    dw, dh, out.ctypes.data_as(_u8p))
+    return out
 
 
 def track(pair: capi.PairInputs, params: capi.PagkParams, n_threads: int = 1):

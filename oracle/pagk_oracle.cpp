@@ -939,6 +939,25 @@ int orb_cell_detect(const uint8_t *img, int cols, int rows, int step, int ini_th
   return n;
 }
 
+// ---------------------------------------------------------------------------------------------
+// cv::remap, INTER_LINEAR, CV_8UC1, CV_32FC1 maps, BORDER_CONSTANT 0 (OpenCV modules/imgproc/src/imgwarp.cpp: remap ->
+// remapBilinear with the INTER_BITS = 5 coordinate grid and the INTER_REMAP_COEF_BITS = 15 weight table), restated from its
+// published algorithm.  PINNED bit-exact against cv2 4.13 (tests/golden/remap.npz).
+// ---------------------------------------------------------------------------------------------
+void remap_linear(const uint8_t *src, int cols, int rows, int step, const float *mx, const float *my, int dcols, int drows, uint8_t *dst) {
+  auto px = [&](int y, int x) -> int { return (x >= 0 && x < cols && y >= 0 && y < rows) ? src[(size_t)y * step + x] : 0; };
+  auto sat16 = [](int v) { return v < -32768 ? -32768 : v > 32767 ? 32767 : v; };
+  for (int y = 0; y < drows; ++y)
+    for (int x = 0; x < dcols; ++x) {
+      const size_t o = (size_t)y * dcols + x;
+      const int sx = (int)lrintf(mx[o] * 32.0f), sy = (int)lrintf(my[o] * 32.0f);  // cvRound(x * INTER_TAB_SIZE)
+      const int ix = sat16(sx >> 5), iy = sat16(sy >> 5), fx = sx & 31, fy = sy & 31;
+      const int w00 = (32 - fy) * (32 - fx) * 32, w01 = (32 - fy) * fx * 32, w10 = fy * (32 - fx) * 32, w11 = fy * fx * 32;
+      const int v = (px(iy, ix) * w00 + px(iy, ix + 1) * w01 + px(iy + 1, ix) * w10 + px(iy + 1, ix + 1) * w11 + (1 << 14)) >> 15;
+      dst[o] = (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v);
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -1026,6 +1045,12 @@ int pagk_oracle_fast_detect(const uint8_t *img, int width, int height, int pitch
 int pagk_oracle_orb_cell_detect(const uint8_t *img, int width, int height, int pitch, int ini_th, int min_th, const uint8_t *mask,
                                 int max_out, float *xy, float *response, int *n_out) {
   *n_out = orb_cell_detect(img, width, height, pitch, ini_th, min_th, mask, max_out, xy, response);
+  return PAGK_OK;
+}
+
+int pagk_oracle_remap_linear(const uint8_t *src, int width, int height, int pitch, const float *map_x, const float *map_y,
+                             int dst_width, int dst_height, uint8_t *dst) {
+  remap_linear(src, width, height, pitch, map_x, map_y, dst_width, dst_height, dst);
   return PAGK_OK;
 }
 

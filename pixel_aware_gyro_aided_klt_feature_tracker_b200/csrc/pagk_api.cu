@@ -89,6 +89,7 @@ struct pagk_handle {
   unsigned char *d_carry = nullptr;
   unsigned char *d_mask = nullptr;
   size_t mask_stride = 0;
+  unsigned char *d_remap = nullptr;  // pagk_remap_linear: source | map_x | map_y | destination (first use)
   unsigned char *d_fast = nullptr;  // pagk_fast_detect: image | mask | score | keep | row counts | row offsets (first use)
   unsigned char *d_fast_out = nullptr;
   int fast_out_cap = 0;
@@ -401,7 +402,7 @@ void pagk_destroy(pagk_handle *h) {
   if (h->stream && h->own_stream) cudaStreamSynchronize(h->stream);
   else cudaDeviceSynchronize();
   cudaFree(h->d_images); cudaFree(h->d_keys_un); cudaFree(h->d_keys); cudaFree(h->d_pc); cudaFree(h->d_res);
-  cudaFree(h->d_out); cudaFree(h->d_ntab); cudaFree(h->d_work); cudaFree(h->d_progress); cudaFree(h->d_geo); cudaFree(h->d_geo_res); cudaFree(h->d_carry); cudaFree(h->d_mask); cudaFree(h->d_fast); cudaFree(h->d_fast_out); cudaFree(h->d_dbg);
+  cudaFree(h->d_out); cudaFree(h->d_ntab); cudaFree(h->d_work); cudaFree(h->d_progress); cudaFree(h->d_geo); cudaFree(h->d_geo_res); cudaFree(h->d_carry); cudaFree(h->d_mask); cudaFree(h->d_fast); cudaFree(h->d_fast_out); cudaFree(h->d_remap); cudaFree(h->d_dbg);
   cudaFreeHost(h->h_in); cudaFreeHost(h->h_out); cudaFreeHost(h->h_res);
   for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
@@ -981,6 +982,28 @@ int pagk_fast_detect(pagk_handle *h, const uint8_t *img, int width, int height, 
     CU(cudaStreamSynchronize(st));
   }
   *n_out = total_found;
+  return PAGK_OK;
+}
+
+int pagk_remap_linear(pagk_handle *h, const uint8_t *src, int width, int height, int pitch, const float *map_x,
+                      const float *map_y, int dst_width, int dst_height, uint8_t *dst) {
+  if (!h || !src || !map_x || !map_y || !dst) return fail(PAGK_ERR_INVALID, "null argument");
+  if (width < 1 || height < 1 || pitch < width || width > h->cfg.max_width || height > h->cfg.max_height || dst_width < 1 ||
+      dst_height < 1 || dst_width > h->cfg.max_width || dst_height > h->cfg.max_height)
+    return fail(PAGK_ERR_INVALID, "image exceeds pagk_config.max_width/max_height");
+  CU(cudaSetDevice(h->cfg.device));
+  const size_t WH = align_up((size_t)h->cfg.max_width * h->cfg.max_height, 256);
+  if (!h->d_remap) CU(cudaMalloc(&h->d_remap, WH * 10));  // u8 source, two float maps, u8 destination
+  cudaStream_t st = h->stream;
+  const size_t n = (size_t)dst_width * dst_height;
+  float *d_mx = (float *)(h->d_remap + WH), *d_my = (float *)(h->d_remap + 5 * WH);
+  unsigned char *d_dst = h->d_remap + 9 * WH;
+  CU(cudaMemcpy2DAsync(h->d_remap, (size_t)width, src, (size_t)pitch, (size_t)width, (size_t)height, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_mx, map_x, n * sizeof(float), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_my, map_y, n * sizeof(float), cudaMemcpyHostToDevice, st));
+  CU((cudaError_t)pagk_launch_remap(h->d_remap, width, height, d_mx, d_my, dst_width, dst_height, d_dst, st, &h->launches));
+  CU(cudaMemcpyAsync(dst, d_dst, n, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
   return PAGK_OK;
 }
 

@@ -1013,6 +1013,26 @@ __global__ void __launch_bounds__(256) pagk_orb_emit_kernel(const unsigned short
 }
 
 // =================================================================================================
+// cv::remap(src, dst, map_x, map_y, INTER_LINEAR) for CV_8UC1 and CV_32FC1 maps with the default constant 0 border
+// (OpenCV modules/imgproc/src/imgwarp.cpp, remapBilinear): coordinates rounded to 1/32 pixel (cvRound = round half to even),
+// integer part saturated to short, 15-bit weights (32 - fy)(32 - fx) * 32 ..., (sum + 2^14) >> 15.  One thread per output pixel.
+// =================================================================================================
+__global__ void __launch_bounds__(256) pagk_remap_kernel(const unsigned char *__restrict__ src, int cols, int rows,
+                                                       const float *__restrict__ map_x, const float *__restrict__ map_y, int dcols,
+                                                       int drows, unsigned char *__restrict__ dst) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= dcols || y >= drows) return;
+  const size_t o = (size_t)y * dcols + x;
+  const int sx = __float2int_rn(map_x[o] * 32.0f), sy = __float2int_rn(map_y[o] * 32.0f);
+  const int ix = min(max(sx >> 5, -32768), 32767), iy = min(max(sy >> 5, -32768), 32767), fx = sx & 31, fy = sy & 31;
+  const bool x0 = ix >= 0 && ix < cols, x1 = ix + 1 >= 0 && ix + 1 < cols, y0 = iy >= 0 && iy < rows, y1 = iy + 1 >= 0 && iy + 1 < rows;
+  const unsigned char *p = src + (long long)iy * cols + ix;
+  const int p00 = (x0 && y0) ? p[0] : 0, p01 = (x1 && y0) ? p[1] : 0, p10 = (x0 && y1) ? p[cols] : 0, p11 = (x1 && y1) ? p[cols + 1] : 0;
+  const int v = (p00 * ((32 - fy) * (32 - fx) * 32) + p01 * ((32 - fy) * fx * 32) + p10 * (fy * (32 - fx) * 32) + p11 * (fy * fx * 32) + (1 << 14)) >> 15;
+  dst[o] = (unsigned char)min(max(v, 0), 255);
+}
+
+// =================================================================================================
 // launch wrappers (host)
 // =================================================================================================
 int pagk_pyramid_fused_max_level() {
@@ -1140,6 +1160,15 @@ int pagk_launch_orb_cells(const unsigned char *img, int cols, int rows, int ini_
   pagk_fast_scan_kernel<<<1, 1024, 0, st>>>(cell_count, n_cells, cell_offset);
   pagk_orb_emit_kernel<<<(n_cells + 7) / 8, 256, 0, st>>>(score, keep, cell_offset, cols, grid, max_out, xy, response);
   *launches += 4;
+  return (int)cudaGetLastError();
+}
+
+int pagk_launch_remap(const unsigned char *src, int cols, int rows, const float *map_x, const float *map_y, int dcols, int drows,
+                      unsigned char *dst, cudaStream_t st, long long *launches) {
+  if (dcols <= 0 || drows <= 0) return 0;
+  dim3 g((dcols + 31) / 32, (drows + 7) / 8);
+  pagk_remap_kernel<<<g, 256, 0, st>>>(src, cols, rows, map_x, map_y, dcols, drows, dst);
+  ++*launches;
   return (int)cudaGetLastError();
 }
 

@@ -36,6 +36,9 @@ struct PagkCellGrid { int n_cols, n_rows, w_cell, h_cell, min_x, min_y, max_x, m
 int pagk_launch_orb_cells(const unsigned char *img, int cols, int rows, int ini_th, int min_th, const unsigned char *mask,
                           unsigned short *score, unsigned char *keep, int *cell_count, int *cell_offset, PagkCellGrid grid,
                           int max_out, float2 *xy, float *response, cudaStream_t st, long long *launches);
+// cv::remap INTER_LINEAR, CV_8UC1, float maps, constant 0 border (OpenCV imgwarp.cpp remapBilinear)
+int pagk_launch_remap(const unsigned char *src, int cols, int rows, const float *map_x, const float *map_y, int dcols, int drows,
+                      unsigned char *dst, cudaStream_t st, long long *launches);
 int pagk_launch_count_status(const PagkPairConst *pcs, const PagkOutPtrs &out, int max_keys, int n_pairs,
                              PagkPairResult *res, cudaStream_t st, long long *launches);
 

@@ -140,6 +140,18 @@ class Context:
         k = min(n.value, max_out)
         return xy[:k].copy(), rs[:k].copy()
 
+    def remap_linear(self, img, map_x, map_y):
+        """cv::remap(img, map_x, map_y, INTER_LINEAR) with the constant 0 border (include/pagk.h)"""
+        img = np.ascontiguousarray(img, np.uint8)
+        mx, my = np.ascontiguousarray(map_x, np.float32), np.ascontiguousarray(map_y, np.float32)
+        h, w = img.shape
+        dh, dw = mx.shape
+        out = np.zeros((dh, dw), np.uint8)
+        u8, f32 = C.POINTER(C.c_uint8), C.POINTER(C.c_float)
+        _check(self.lib, self.lib.pagk_remap_linear(self.handle, img.ctypes.data_as(u8), w, h, img.strides[0], mx.ctypes.data_as(f32),
+                                                    my.ctypes.data_as(f32), dw, dh, out.ctypes.data_as(u8)))
+        return out
+
     def set_stage_timing(self, on: bool):
         """CUDA events between the kernels of a run (per-stage clocks); off for throughput pipelines"""
         _check(self.lib, self.lib.pagk_set_stage_timing(self.handle, 1 if on else 0))

@@ -5,6 +5,7 @@ What is pinned against what (the reference ships no tests 
   matexpr.npz   cv2.gemm / cv2.invert / cv2.scaleAdd / cv2.add chains that OpenCV's cv::MatExpr lowers
                 IntegrateGyroMeasurements, SetRcl and the affine-matrix expression to
                 (src/gyro_aided_tracker.cpp:166-167, 511-587)       -> pins oracle small_*() and integrate_gyro()
+  remap.npz     cv2.remap (INTER_LINEAR, u8, float maps, constant border)               -> pins oracle remap_linear()
   fast.npz      cv2.FastFeatureDetector (TYPE_9_16) keypoints and responses            -> pins oracle fast_detect()
   lk_frozen.npz outputs of the reference build (oracle/_ref/libpagk_ref.so = the reference's own three sources
                 compiled against stand-in OpenCV/Eigen/glog headers, oracle/reference.py) on small seeded pairs
@@ -207,8 +208,37 @@ def make_fast():
     print("fast.npz", len(out))
 
 
+def make_remap():
+    """cv2.remap(INTER_LINEAR) on u8 with float maps -> pins oracle remap_linear(): random maps with out-of-range, integer and tie
+    coordinates, and the rectification map of the EuRoC calibration (cv2.initUndistortRectifyMap, as include/imu_types.h:63-65)"""
+    rng = np.random.default_rng(99)
+    out = {}
+    H, W = 60, 80
+    img = (rng.random((H, W)) * 255).astype(np.uint8)
+    mx = rng.uniform(-5, W + 4, (48, 64)).astype(np.float32); my = rng.uniform(-5, H + 4, (48, 64)).astype(np.float32)
+    mx[::7, ::5] = np.round(mx[::7, ::5]); my[::3, ::11] = np.round(my[::3, ::11])
+    mx[1, :10] = [-1, -0.99, -1.01, W - 1, W - 1.01, W - 0.5, W, 1e6, -1e6, 40000.0]; my[1, :10] = 0
+    my[2, :6] = [-1, -0.99, H - 1, H - 1.01, H, 1e6]; mx[2, :6] = 3
+    mx[3, :] = (np.arange(64) + 1 / 64).astype(np.float32); my[3, :] = np.float32(7 + 3 / 64)     # ties of the 1/32 grid
+    out["s_img"], out["s_mx"], out["s_my"] = img, mx, my
+    out["s_out"] = cv2.remap(img, mx, my, cv2.INTER_LINEAR)
+    H, W = 480, 752
+    K = synth.EUROC_K.astype(np.float64); D = np.asarray(synth.EUROC_DIST, np.float64)
+    newK = cv2.getOptimalNewCameraMatrix(K, D, (W, H), 0, (W, H))[0]
+    M1, M2 = cv2.initUndistortRectifyMap(K, D, None, newK, (W, H), cv2.CV_32F)
+    big = lcg_image(H, W, 11)
+    res = cv2.remap(big, M1, M2, cv2.INTER_LINEAR)
+    out["r_M1"], out["r_M2"] = M1.astype(np.float16).astype(np.float32), M2.astype(np.float16).astype(np.float32)   # halves keep the fixture small
+    res = cv2.remap(big, out["r_M1"], out["r_M2"], cv2.INTER_LINEAR)
+    out["r_sha"] = np.frombuffer(hashlib.sha256(res.tobytes()).digest(), np.uint8)
+    out["r_M1"], out["r_M2"] = out["r_M1"].astype(np.float16), out["r_M2"].astype(np.float16)
+    np.savez_compressed(os.path.join(HERE, "remap.npz"), **out)
+    print("remap.npz", len(out))
+
+
 if __name__ == "__main__":
     make_pyramid()
     make_matexpr()
     make_lk_frozen()
     make_fast()
+    make_remap()
