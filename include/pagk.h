@@ -314,6 +314,12 @@ int pagk_orb_cell_detect(pagk_handle *h, const uint8_t *img, int width, int heig
 int pagk_remap_linear(pagk_handle *h, const uint8_t *src, int width, int height, int pitch, const float *map_x,
                       const float *map_y, int dst_width, int dst_height, uint8_t *dst);
 
+/* The same rectification inside the pipeline: once maps are set, every img_ref / img_cur a batch brings is taken as the
+ * DISTORTED image; it is uploaded as it is and remapped on the device straight into level 0 of its pyramid slot (nothing more
+ * crosses PCIe, the maps stay on the device).  The maps must have the size of the images.  map_x = map_y = NULL switches the
+ * rectification off again. */
+int pagk_set_rectify_maps(pagk_handle *h, const float *map_x, const float *map_y, int width, int height);
+
 #ifdef __cplusplus
 }
 #endif

@@ -89,6 +89,9 @@ struct pagk_handle {
   unsigned char *d_carry = nullptr;
   unsigned char *d_mask = nullptr;
   size_t mask_stride = 0;
+  float *d_maps = nullptr;          // pagk_set_rectify_maps: map_x | map_y of map_w x map_h; batches then bring distorted images
+  int map_w = 0, map_h = 0;
+  unsigned char *d_raw = nullptr;   // the distorted images of a batch, as uploaded (2 * max_pairs images)
   unsigned char *d_remap = nullptr;  // pagk_remap_linear: source | map_x | map_y | destination (first use)
   unsigned char *d_fast = nullptr;  // pagk_fast_detect: image | mask | score | keep | row counts | row offsets (first use)
   unsigned char *d_fast_out = nullptr;
@@ -180,8 +183,27 @@ void pair_const(const pagk_pair_in &in, PagkPairConst *pc, float Rcl[9], float K
   pc->has_table = in.normalize_table ? 1 : 0;
 }
 
+// with rectification maps set: the images go to the raw stack as they are and are remapped into level 0 of their slots
+int upload_images_rectify(pagk_handle *h, int n_pairs, const uint8_t *const *refs, const uint8_t *const *curs, int width, int height,
+                          const int *pitches) {
+  const PagkGeom &g = h->geom;
+  const size_t img_bytes = (size_t)width * height;
+  if (h->map_w != width || h->map_h != height) return fail(PAGK_ERR_INVALID, "rectification maps do not have the size of the images");
+  if (!h->d_raw) CU(cudaMalloc(&h->d_raw, (size_t)2 * h->cfg.max_pairs * h->cfg.max_width * h->cfg.max_height));
+  const bool cont = refs == nullptr;
+  const int per = cont ? 1 : 2;
+  for (int p = 0; p < n_pairs; ++p) {
+    if (!cont) CU(cudaMemcpy2DAsync(h->d_raw + (size_t)(2 * p) * img_bytes, width, refs[p], pitches[p], width, height, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpy2DAsync(h->d_raw + (size_t)(per * p + per - 1) * img_bytes, width, curs[p], pitches[p], width, height, cudaMemcpyHostToDevice, h->stream));
+  }
+  CU((cudaError_t)pagk_launch_remap_slots(h->d_raw, h->d_images, g, h->d_maps, h->d_maps + img_bytes, per * n_pairs, cont ? 2 : 1,
+                                          cont ? 1 : 0, h->stream, &h->launches));
+  return PAGK_OK;
+}
+
 int upload_images(pagk_handle *h, int n_pairs, const uint8_t *const *refs, const uint8_t *const *curs, int width,
                   int height, const int *pitches) {
+  if (h->d_maps) return upload_images_rectify(h, n_pairs, refs, curs, width, height, pitches);
   const PagkGeom &g = h->geom;
   const size_t img_bytes = (size_t)width * height;
   bool contiguous = true;
@@ -212,6 +234,7 @@ int upload_images_continue(pagk_handle *h, int n_pairs, const uint8_t *const *cu
   const size_t img_bytes = (size_t)width * height;
   CU(cudaMemcpy2DAsync(h->d_images, 2 * g.slot_bytes, h->d_images + g.slot_bytes, 2 * g.slot_bytes, g.slot_bytes, (size_t)n_pairs,
                        cudaMemcpyDeviceToDevice, h->stream));
+  if (h->d_maps) return upload_images_rectify(h, n_pairs, nullptr, curs, width, height, pitches);
   bool contiguous = true;
   for (int p = 0; p < n_pairs && contiguous; ++p) {
     if (pitches[p] != width) contiguous = false;
@@ -402,7 +425,7 @@ void pagk_destroy(pagk_handle *h) {
   if (h->stream && h->own_stream) cudaStreamSynchronize(h->stream);
   else cudaDeviceSynchronize();
   cudaFree(h->d_images); cudaFree(h->d_keys_un); cudaFree(h->d_keys); cudaFree(h->d_pc); cudaFree(h->d_res);
-  cudaFree(h->d_out); cudaFree(h->d_ntab); cudaFree(h->d_work); cudaFree(h->d_progress); cudaFree(h->d_geo); cudaFree(h->d_geo_res); cudaFree(h->d_carry); cudaFree(h->d_mask); cudaFree(h->d_fast); cudaFree(h->d_fast_out); cudaFree(h->d_remap); cudaFree(h->d_dbg);
+  cudaFree(h->d_out); cudaFree(h->d_ntab); cudaFree(h->d_work); cudaFree(h->d_progress); cudaFree(h->d_geo); cudaFree(h->d_geo_res); cudaFree(h->d_carry); cudaFree(h->d_mask); cudaFree(h->d_fast); cudaFree(h->d_fast_out); cudaFree(h->d_remap); cudaFree(h->d_maps); cudaFree(h->d_raw); cudaFree(h->d_dbg);
   cudaFreeHost(h->h_in); cudaFreeHost(h->h_out); cudaFreeHost(h->h_res);
   for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
@@ -982,6 +1005,23 @@ int pagk_fast_detect(pagk_handle *h, const uint8_t *img, int width, int height, 
     CU(cudaStreamSynchronize(st));
   }
   *n_out = total_found;
+  return PAGK_OK;
+}
+
+int pagk_set_rectify_maps(pagk_handle *h, const float *map_x, const float *map_y, int width, int height) {
+  if (!h) return fail(PAGK_ERR_INVALID, "null handle");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaStreamSynchronize(h->stream));
+  h->cur_pairs = 0;  // pyramids built so far belong to the other kind of image
+  if (!map_x && !map_y) { cudaFree(h->d_maps); h->d_maps = nullptr; h->map_w = h->map_h = 0; return PAGK_OK; }
+  if (!map_x || !map_y || width < 1 || height < 1 || width > h->cfg.max_width || height > h->cfg.max_height)
+    return fail(PAGK_ERR_INVALID, "bad rectification maps");
+  const size_t n = (size_t)width * height;
+  cudaFree(h->d_maps); h->d_maps = nullptr;
+  CU(cudaMalloc(&h->d_maps, 2 * n * sizeof(float)));
+  CU(cudaMemcpy(h->d_maps, map_x, n * sizeof(float), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->d_maps + n, map_y, n * sizeof(float), cudaMemcpyHostToDevice));
+  h->map_w = width; h->map_h = height;
   return PAGK_OK;
 }
 

@@ -39,6 +39,9 @@ int pagk_launch_orb_cells(const unsigned char *img, int cols, int rows, int ini_
 // cv::remap INTER_LINEAR, CV_8UC1, float maps, constant 0 border (OpenCV imgwarp.cpp remapBilinear)
 int pagk_launch_remap(const unsigned char *src, int cols, int rows, const float *map_x, const float *map_y, int dcols, int drows,
                       unsigned char *dst, cudaStream_t st, long long *launches);
+// the same, from a contiguous stack of raw images into level 0 of pyramid slots: image z -> slot z * z_stride + z_offset
+int pagk_launch_remap_slots(const unsigned char *raw, unsigned char *images, const PagkGeom &g, const float *map_x, const float *map_y,
+                            int n_images, int z_stride, int z_offset, cudaStream_t st, long long *launches);
 int pagk_launch_count_status(const PagkPairConst *pcs, const PagkOutPtrs &out, int max_keys, int n_pairs,
                              PagkPairResult *res, cudaStream_t st, long long *launches);
 

@@ -152,6 +152,15 @@ class Context:
                                                     my.ctypes.data_as(f32), dw, dh, out.ctypes.data_as(u8)))
         return out
 
+    def set_rectify_maps(self, map_x, map_y):
+        """batches then bring DISTORTED images, remapped on the device into their pyramid slots; (None, None) switches it off"""
+        if map_x is None:
+            _check(self.lib, self.lib.pagk_set_rectify_maps(self.handle, None, None, 0, 0))
+            return
+        mx, my = np.ascontiguousarray(map_x, np.float32), np.ascontiguousarray(map_y, np.float32)
+        f32 = C.POINTER(C.c_float)
+        _check(self.lib, self.lib.pagk_set_rectify_maps(self.handle, mx.ctypes.data_as(f32), my.ctypes.data_as(f32), mx.shape[1], mx.shape[0]))
+
     def set_stage_timing(self, on: bool):
         """CUDA events between the kernels of a run (per-stage clocks); off for throughput pipelines"""
         _check(self.lib, self.lib.pagk_set_stage_timing(self.handle, 1 if on else 0))

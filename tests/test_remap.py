@@ -37,3 +37,34 @@ def test_cuda_remap_bit_exact(gpu_ctx, oracle):
     mx = rng.uniform(-40, 380, (200, 301)).astype(np.float32)
     my = rng.uniform(-40, 290, (200, 301)).astype(np.float32)
     assert np.array_equal(gpu_ctx.remap_linear(img, mx, my), oracle.remap_linear(img, mx, my))
+
+
+@pytest.mark.gpu
+def test_rectification_inside_the_pipeline(gpu_ctx, oracle):
+    """pagk_set_rectify_maps: a batch brings distorted images, the device remaps them into the pyramid slots; results equal
+    tracking the cv::remap-ed images, for whole pairs and for stream continuation"""
+    import copy
+    from pixel_aware_gyro_aided_klt_feature_tracker_b200 import capi, synth
+    from tests import helpers
+    W, H = 320, 240
+    ys, xs = np.mgrid[0:H, 0:W].astype(np.float32)
+    mx = (xs + 1.5 * np.sin(ys / 37.0) + 0.25).astype(np.float32)          # a smooth, slightly shifting distortion
+    my = (ys + 1.2 * np.cos(xs / 41.0) - 0.4).astype(np.float32)
+    frames, pairs = synth.make_sequence(9500, 4, width=W, height=H, n_keys=150, pyramids=3, border=24)
+    rect = [oracle.remap_linear(f, mx, my) for f in frames]
+    prm = capi.default_params(pyramids=3)
+    gpu_ctx.set_rectify_maps(mx, my)
+    try:
+        for t, p in enumerate(pairs):
+            q = copy.copy(p)                        # distorted images in, continuation from the second pair on
+            q.img_ref = p.img_ref if t == 0 else None
+            got = gpu_ctx.track_batch([q], prm)[0]
+            e = copy.copy(p)
+            e.img_ref, e.img_cur = rect[t], rect[t + 1]
+            rc, want = oracle.track(e, prm, 2)
+            assert rc == 0
+            helpers.assert_bit_exact(got, want)
+    finally:
+        gpu_ctx.set_rectify_maps(None, None)
+    got = gpu_ctx.track_batch([pairs[0]], prm)[0]   # and off again
+    helpers.assert_bit_exact(got, oracle.track(pairs[0], prm, 2)[1])
