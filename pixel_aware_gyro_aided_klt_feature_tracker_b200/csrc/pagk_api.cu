@@ -86,6 +86,8 @@ struct pagk_handle {
   int *d_work = nullptr;   // work counters of the persistent LK kernels ([0]: slots kernel, [16..17]: lanes kernel)
   int lk_parity = 0;       // which of the two lanes-kernel counters the next launch uses
   // pagk_set_predict_keypoints_and_mask: one block, allocated on first use (consts, last normals, 5 result vectors, counts)
+  unsigned char *h_aux = nullptr;   // pinned staging of the entry points around the path (grown on demand)
+  size_t h_aux_bytes = 0;
   unsigned char *d_carry = nullptr;
   unsigned char *d_mask = nullptr;
   size_t mask_stride = 0;
@@ -425,7 +427,7 @@ void pagk_destroy(pagk_handle *h) {
   if (h->stream && h->own_stream) cudaStreamSynchronize(h->stream);
   else cudaDeviceSynchronize();
   cudaFree(h->d_images); cudaFree(h->d_keys_un); cudaFree(h->d_keys); cudaFree(h->d_pc); cudaFree(h->d_res);
-  cudaFree(h->d_out); cudaFree(h->d_ntab); cudaFree(h->d_work); cudaFree(h->d_progress); cudaFree(h->d_geo); cudaFree(h->d_geo_res); cudaFree(h->d_carry); cudaFree(h->d_mask); cudaFree(h->d_fast); cudaFree(h->d_fast_out); cudaFree(h->d_remap); cudaFree(h->d_maps); cudaFree(h->d_raw); cudaFree(h->d_dbg);
+  cudaFree(h->d_out); cudaFree(h->d_ntab); cudaFree(h->d_work); cudaFree(h->d_progress); cudaFree(h->d_geo); cudaFree(h->d_geo_res); cudaFree(h->d_carry); cudaFree(h->d_mask); cudaFreeHost(h->h_aux); cudaFree(h->d_fast); cudaFree(h->d_fast_out); cudaFree(h->d_remap); cudaFree(h->d_maps); cudaFree(h->d_raw); cudaFree(h->d_dbg);
   cudaFreeHost(h->h_in); cudaFreeHost(h->h_out); cudaFreeHost(h->h_res);
   for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
@@ -798,6 +800,14 @@ int pagk_gyro_predict(pagk_handle *h, const pagk_params *prm, const pagk_pair_in
   return pagk_track_batch(h, &p, 1, in, out);
 }
 
+static int aux_staging(pagk_handle *h, size_t bytes) {
+  if (bytes <= h->h_aux_bytes) return PAGK_OK;
+  cudaFreeHost(h->h_aux); h->h_aux = nullptr; h->h_aux_bytes = 0;
+  CU(cudaMallocHost(&h->h_aux, bytes));
+  h->h_aux_bytes = bytes;
+  return PAGK_OK;
+}
+
 int pagk_geometry_validation(pagk_handle *h, int n_pairs, const pagk_geometry_in *in, pagk_geometry_out *out) {
   if (!h || !in || !out) return fail(PAGK_ERR_INVALID, "null argument");
   if (n_pairs < 0 || n_pairs > h->cfg.max_pairs) return fail(PAGK_ERR_INVALID, "n_pairs exceeds pagk_config.max_pairs");
@@ -833,10 +843,13 @@ int pagk_geometry_validation(pagk_handle *h, int n_pairs, const pagk_geometry_in
                                        st, &h->launches));
   std::vector<PagkGeoResult> res((size_t)n_pairs);
   CU(cudaMemcpyAsync(res.data(), h->d_geo_res, res.size() * sizeof(PagkGeoResult), cudaMemcpyDeviceToHost, st));
-  for (int p = 0; p < n_pairs; ++p)
-    if (out[p].status && in[p].n_keys)
-      CU(cudaMemcpyAsync(out[p].status, o.status + (size_t)p * h->cfg.max_keys, (size_t)in[p].n_keys, cudaMemcpyDeviceToHost, st));
+  // one copy of the status rows into pinned memory, then per pair on the host
+  const size_t st_bytes = (size_t)n_pairs * h->cfg.max_keys;
+  if (aux_staging(h, st_bytes) != PAGK_OK) return PAGK_ERR_CUDA;
+  CU(cudaMemcpyAsync(h->h_aux, o.status, st_bytes, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
+  for (int p = 0; p < n_pairs; ++p)
+    if (out[p].status && in[p].n_keys) std::memcpy(out[p].status, h->h_aux + (size_t)p * h->cfg.max_keys, (size_t)in[p].n_keys);
   for (int p = 0; p < n_pairs; ++p) {
     out[p].score_H = res[(size_t)p].score_H; out[p].score_F = res[(size_t)p].score_F; out[p].used_H = res[(size_t)p].used_H;
     out[p].n_candidates = res[(size_t)p].n_candidates; out[p].n_inlier = res[(size_t)p].n_inlier;
@@ -858,6 +871,9 @@ int pagk_set_predict_keypoints_and_mask(pagk_handle *h, int n_pairs, const pagk_
   const PagkOutPtrs o = h->outs();
   cudaStream_t st = h->stream;
   std::vector<PagkCarryConst> cc((size_t)n_pairs);
+  const size_t rows8 = (size_t)n_pairs * h->cfg.max_keys * 8;  // bytes of n_pairs rows of a float2 vector
+  if (aux_staging(h, 5 * rows8) != PAGK_OK) return PAGK_ERR_CUDA;
+  CU(cudaStreamSynchronize(st));  // the staging block may still feed an earlier copy
   bool any_mask = false;
   int W = 0, H = 0;
   for (int p = 0; p < n_pairs; ++p) {
@@ -878,7 +894,7 @@ int pagk_set_predict_keypoints_and_mask(pagk_handle *h, int n_pairs, const pagk_
     c.n_keys = g.n_keys; c.width = g.width; c.height = g.height; c.pad = 0;
     any_mask |= out[p].mask != nullptr;
     const size_t off = (size_t)p * h->cfg.max_keys, n = (size_t)g.n_keys;
-    if (n) CU(cudaMemcpyAsync(h->d_carry + off_nl + off * 8, g.keys_normal_last, n * 8, cudaMemcpyHostToDevice, st));
+    if (n) std::memcpy(h->h_aux + off * 8, g.keys_normal_last, n * 8);  // one H2D copy below
     if (given && n) {
       CU(cudaMemcpyAsync(o.pt_predict + off, g.pt_predict, n * 8, cudaMemcpyHostToDevice, st));
       CU(cudaMemcpyAsync(o.pt_predict_un + off, g.pt_predict_un, n * 8, cudaMemcpyHostToDevice, st));
@@ -892,6 +908,7 @@ int pagk_set_predict_keypoints_and_mask(pagk_handle *h, int n_pairs, const pagk_
     }
     CU(cudaMemsetAsync(h->d_mask, 1, h->mask_stride * (size_t)n_pairs, st));  // cv::Mat::ones
   }
+  CU(cudaMemcpyAsync(h->d_carry + off_nl, h->h_aux, rows8, cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(h->d_carry, cc.data(), cc.size() * sizeof(PagkCarryConst), cudaMemcpyHostToDevice, st));
   CU((cudaError_t)pagk_launch_carry((const PagkCarryConst *)h->d_carry, o.pt_predict, o.pt_predict_un, o.status,
                                     (const float2 *)(h->d_carry + off_nl), h->cfg.max_keys, n_pairs, (float2 *)(h->d_carry + off_k),
@@ -900,18 +917,24 @@ int pagk_set_predict_keypoints_and_mask(pagk_handle *h, int n_pairs, const pagk_
                                     h->mask_stride, st, &h->launches));
   std::vector<int> n_out((size_t)n_pairs);
   CU(cudaMemcpyAsync(n_out.data(), h->d_carry + off_n, n_out.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+  // the five result vectors: one copy each into pinned memory (the normals staged above are consumed by then), per pair on the host
+  CU(cudaMemcpyAsync(h->h_aux, h->d_carry + off_k, rows8, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(h->h_aux + rows8, h->d_carry + off_ku, rows8, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(h->h_aux + 2 * rows8, h->d_carry + off_kn, rows8, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(h->h_aux + 3 * rows8, h->d_carry + off_fl, rows8, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(h->h_aux + 4 * rows8, h->d_carry + off_ix, rows8 / 2, cudaMemcpyDeviceToHost, st));
+  for (int p = 0; p < n_pairs; ++p)
+    if (out[p].mask) CU(cudaMemcpyAsync(out[p].mask, h->d_mask + (size_t)p * h->mask_stride, (size_t)W * H, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
   for (int p = 0; p < n_pairs; ++p) {
     const size_t off = (size_t)p * h->cfg.max_keys, n = (size_t)in[p].n_keys;  // survivors <= n_keys: copy the capacity
-    if (n) {
-      CU(cudaMemcpyAsync(out[p].keys, h->d_carry + off_k + off * 8, n * 8, cudaMemcpyDeviceToHost, st));
-      CU(cudaMemcpyAsync(out[p].keys_un, h->d_carry + off_ku + off * 8, n * 8, cudaMemcpyDeviceToHost, st));
-      CU(cudaMemcpyAsync(out[p].keys_normal, h->d_carry + off_kn + off * 8, n * 8, cudaMemcpyDeviceToHost, st));
-      CU(cudaMemcpyAsync(out[p].flow_velocity_last, h->d_carry + off_fl + off * 8, n * 8, cudaMemcpyDeviceToHost, st));
-      CU(cudaMemcpyAsync(out[p].index_in_last, h->d_carry + off_ix + off * 4, n * 4, cudaMemcpyDeviceToHost, st));
-    }
-    if (out[p].mask) CU(cudaMemcpyAsync(out[p].mask, h->d_mask + (size_t)p * h->mask_stride, (size_t)W * H, cudaMemcpyDeviceToHost, st));
+    if (!n) continue;
+    std::memcpy(out[p].keys, h->h_aux + off * 8, n * 8);
+    std::memcpy(out[p].keys_un, h->h_aux + rows8 + off * 8, n * 8);
+    std::memcpy(out[p].keys_normal, h->h_aux + 2 * rows8 + off * 8, n * 8);
+    std::memcpy(out[p].flow_velocity_last, h->h_aux + 3 * rows8 + off * 8, n * 8);
+    std::memcpy(out[p].index_in_last, h->h_aux + 4 * rows8 + off * 4, n * 4);
   }
-  CU(cudaStreamSynchronize(st));
   for (int p = 0; p < n_pairs; ++p) out[p].n_out = n_out[(size_t)p];
   return PAGK_OK;
 }

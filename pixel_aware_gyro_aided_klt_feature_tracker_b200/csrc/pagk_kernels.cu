@@ -1032,22 +1032,42 @@ __global__ void __launch_bounds__(256) pagk_remap_kernel(const unsigned char *__
   dst[o] = (unsigned char)min(max(v, 0), 255);
 }
 
+__device__ __forceinline__ unsigned int pagk_remap_px(const unsigned char *__restrict__ src, int cols, int rows, float mx, float my) {
+  const int sx = __float2int_rn(mx * 32.0f), sy = __float2int_rn(my * 32.0f);
+  const int ix = min(max(sx >> 5, -32768), 32767), iy = min(max(sy >> 5, -32768), 32767), fx = sx & 31, fy = sy & 31;
+  const bool x0 = ix >= 0 && ix < cols, x1 = ix + 1 >= 0 && ix + 1 < cols, y0 = iy >= 0 && iy < rows, y1 = iy + 1 >= 0 && iy + 1 < rows;
+  const unsigned char *p = src + (long long)iy * cols + ix;
+  const int p00 = (x0 && y0) ? __ldg(p) : 0, p01 = (x1 && y0) ? __ldg(p + 1) : 0, p10 = (x0 && y1) ? __ldg(p + cols) : 0,
+            p11 = (x1 && y1) ? __ldg(p + cols + 1) : 0;
+  const int v = (p00 * ((32 - fy) * (32 - fx) * 32) + p01 * ((32 - fy) * fx * 32) + p10 * (fy * (32 - fx) * 32) + p11 * (fy * fx * 32) + (1 << 14)) >> 15;
+  return (unsigned int)min(max(v, 0), 255);
+}
+
+// four output pixels per thread when the row length allows it: 16-byte map loads, one 4-byte store
 __global__ void __launch_bounds__(256) pagk_remap_slots_kernel(const unsigned char *__restrict__ raw, unsigned char *__restrict__ images,
                                                              PagkGeom g, const float *__restrict__ map_x, const float *__restrict__ map_y,
                                                              int z_stride, int z_offset) {
   const int cols = g.lv[0].cols, rows = g.lv[0].rows;
-  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
-  if (x >= cols || y >= rows) return;
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (y >= rows) return;
   const unsigned char *src = raw + (size_t)blockIdx.z * cols * rows;
   unsigned char *dst = images + (size_t)(blockIdx.z * z_stride + z_offset) * g.slot_bytes + g.lv[0].offset;
-  const size_t o = (size_t)y * cols + x;
-  const int sx = __float2int_rn(map_x[o] * 32.0f), sy = __float2int_rn(map_y[o] * 32.0f);
-  const int ix = min(max(sx >> 5, -32768), 32767), iy = min(max(sy >> 5, -32768), 32767), fx = sx & 31, fy = sy & 31;
-  const bool x0 = ix >= 0 && ix < cols, x1 = ix + 1 >= 0 && ix + 1 < cols, y0 = iy >= 0 && iy < rows, y1 = iy + 1 >= 0 && iy + 1 < rows;
-  const unsigned char *p = src + (long long)iy * cols + ix;
-  const int p00 = (x0 && y0) ? p[0] : 0, p01 = (x1 && y0) ? p[1] : 0, p10 = (x0 && y1) ? p[cols] : 0, p11 = (x1 && y1) ? p[cols + 1] : 0;
-  const int v = (p00 * ((32 - fy) * (32 - fx) * 32) + p01 * ((32 - fy) * fx * 32) + p10 * (fy * (32 - fx) * 32) + p11 * (fy * fx * 32) + (1 << 14)) >> 15;
-  dst[o] = (unsigned char)min(max(v, 0), 255);
+  if ((cols & 3) == 0) {
+    const int x = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4;
+    if (x >= cols) return;
+    const size_t o = (size_t)y * cols + x;
+    const float4 mx = *reinterpret_cast<const float4 *>(map_x + o), my = *reinterpret_cast<const float4 *>(map_y + o);
+    const unsigned int v = pagk_remap_px(src, cols, rows, mx.x, my.x) | (pagk_remap_px(src, cols, rows, mx.y, my.y) << 8) |
+                           (pagk_remap_px(src, cols, rows, mx.z, my.z) << 16) | (pagk_remap_px(src, cols, rows, mx.w, my.w) << 24);
+    *reinterpret_cast<unsigned int *>(dst + o) = v;
+  } else {
+    for (int k = 0; k < 4; ++k) {
+      const int x = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4 + k;
+      if (x >= cols) return;
+      const size_t o = (size_t)y * cols + x;
+      dst[o] = (unsigned char)pagk_remap_px(src, cols, rows, map_x[o], map_y[o]);
+    }
+  }
 }
 
 // =================================================================================================
@@ -1193,7 +1213,7 @@ int pagk_launch_remap(const unsigned char *src, int cols, int rows, const float 
 int pagk_launch_remap_slots(const unsigned char *raw, unsigned char *images, const PagkGeom &g, const float *map_x, const float *map_y,
                             int n_images, int z_stride, int z_offset, cudaStream_t st, long long *launches) {
   if (n_images <= 0) return 0;
-  dim3 grid((g.lv[0].cols + 31) / 32, (g.lv[0].rows + 7) / 8, n_images);
+  dim3 grid((g.lv[0].cols + 127) / 128, (g.lv[0].rows + 7) / 8, n_images);
   pagk_remap_slots_kernel<<<grid, 256, 0, st>>>(raw, images, g, map_x, map_y, z_stride, z_offset);
   ++*launches;
   return (int)cudaGetLastError();
