@@ -68,6 +68,11 @@ int main() {
     int ok = 0;
     for (int i = 0; i < N; ++i) ok += trk2.mvStatusAfterPatchMatched[i];
     std::printf("patch_match_ok %d\n", ok);
+    // GeometryValidation() with the models the caller's cv::findHomography / cv::findFundamentalMat would hand over: here the
+    // true motion of the synthetic pair (a shift by (2, 1)) and an arbitrary fundamental matrix
+    const double H21[9] = {1, 0, 2, 0, 1, 1, 0, 0, 1}, F21[9] = {0, -1e-3, 0.2, 1e-3, 0, -0.3, -0.2, 0.3, 0.01};
+    const int n_in = trk.GeometryValidation(H21, F21);
+    std::printf("geometry %d %d %.9g %.9g\n", n_in, (int)trk.mGeometryUsedH, trk.mGeometryScoreH, trk.mGeometryScoreF);
     trk.SetType(pagk::GyroAidedTracker::OPENCV_OPTICAL_FLOW_PYR_LK);
     std::printf("unsupported %d\n", trk.TrackFeatures());
   } catch (const pagk::Error &e) {

@@ -63,4 +63,11 @@ def test_shim_driver_matches_oracle(cuda_lib, oracle, tmp_path):
     ok = o.status.astype(bool)
     assert ok.sum() > 50 and np.abs((o.pt_predict_un - keys)[ok] - np.array([2.0, 1.0])).max() < 0.1
     assert lines[1 + N] == f"patch_match_ok {int(o.pm_status.sum())}"
-    assert lines[2 + N] == "unsupported -1"
+    # GeometryValidation() of the shim against the restatement on the same correspondences and models
+    gc = capi.GeometryCase(keys, o.pt_predict_un, o.status, [1, 0, 2, 0, 1, 1, 0, 0, 1], [0, -1e-3, 0.2, 1e-3, 0, -0.3, -0.2, 0.3, 0.01])
+    rc, (go,) = oracle.geometry_validation([gc])
+    geo = lines[2 + N].split()
+    assert geo[0] == "geometry" and int(geo[1]) == go.n_inlier and int(geo[2]) == go.used_H
+    assert np.float32(geo[3]) == np.float32(go.score_H) and np.float32(geo[4]) == np.float32(go.score_F)
+    assert go.used_H == 1 and go.n_inlier > 50
+    assert lines[3 + N] == "unsupported -1"
