@@ -466,9 +466,18 @@ def main():
         rc, cpu = oracle.track_batch(sample, prm, cores)
         dtc = time.perf_counter() - t0
         cpu_iters = sum(o.n_iterations for o in cpu)
+        # one thread on the first pairs of the same sample, and the three spans the reference times itself
+        # (mTimeCostGyroPredict, mTimeCostOptFlow, mTimeCostOptFlowResultFilterOut), mean per frame pair of the threaded run
+        one = sample[:min(len(sample), 4)]
+        t0 = time.perf_counter()
+        oracle.track_batch(one, prm, 1)
+        dt1 = time.perf_counter() - t0
+        spans = {k: 1e3 * float(np.mean([getattr(o.struct, k) for o in cpu])) for k in ("t_gyro_predict", "t_opt_flow", "t_filter")}
         cpu_baseline = {"value": len(sample) * N / dtc, "unit": "features/s", "cores": cores, "kind": kind,
                         "kind_note": kind_note, "feature_iterations_per_sec": cpu_iters / dtc,
-                        "sample": f"first {len(sample)} frame pairs of the timed workload, {cores} std::threads over features"}
+                        "sample": f"first {len(sample)} frame pairs of the timed workload, {cores} std::threads over features",
+                        "one_thread": {"value": len(one) * N / dt1, "unit": "features/s", "sample": f"first {len(one)} frame pairs"},
+                        "reference_spans_ms_per_pair": spans}
         worst, same, tot, bit = 0.0, 0, 0, True
         for g, c in zip(outs0.outs, cpu):
             rep = helpers.compare(g, c)

@@ -22,6 +22,7 @@
 #include "pagk_cv_fast.h"
 
 #include <atomic>
+#include <chrono>
 
 // ------------------------------------------------------------------------------------------------------------------
 // definitions for the stand-in headers
@@ -251,10 +252,13 @@ int track_one(const pagk_params &prm, const pagk_pair_in &in, pagk_pair_out *out
   t.mbHasGyroPredictInitial = gyro_init; t.mbConsiderIllumination = illum; t.mbConsiderAffineDeformation = affine;
   t.mbRegularizationPenalty = regular;
   const int half = t.mHalfPatchSize;
+  // the two spans TrackFeatures() would time itself (mTimeCostOptFlow, mTimeCostOptFlowResultFilterOut, seconds)
+  const auto tp0 = std::chrono::steady_clock::now();
   {
     PatchMatch pm(&t, half, prm.iterations, prm.pyramids, gyro_init, prm.inverse != 0, illum, affine, regular, prm.calc_ncc != 0);
     pm.OpticalFlowMultiLevel();
   }
+  const auto tp1 = std::chrono::steady_clock::now();
   // result filter, src/gyro_aided_tracker.cpp:289-336
   double sum = 0;
   int cnt = 0;
@@ -275,7 +279,10 @@ int track_one(const pagk_params &prm, const pagk_pair_in &in, pagk_pair_out *out
       t.mvStatus[i] = false;
     }
   }
+  const auto tp2 = std::chrono::steady_clock::now();
   export_tracker(t, N, out);
+  out->t_opt_flow = std::chrono::duration<float>(tp1 - tp0).count();
+  out->t_filter = std::chrono::duration<float>(tp2 - tp1).count();
   out->n_predict = n_predict;
   out->n_iterations = pagk_eigen_shim::g_llt_calls.load() - llt0;
   return PAGK_OK;
