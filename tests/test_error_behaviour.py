@@ -108,3 +108,33 @@ def test_the_handle_survives_its_errors(small_ctx, oracle, pair):
     empty.keys_ref = empty.keys_ref_un
     (g0,) = small_ctx.track_batch([empty], prm)                  # no keypoints is not an error (the reference returns 0)
     assert g0.n_predict == 0
+
+
+def test_non_finite_inputs_fail_per_feature(small_ctx, oracle, pair):
+    """Repeated IMU timestamps (tab = 0, src/gyro_aided_tracker.cpp:531-535) or a NaN gyro sample make Rcl NaN; the reference
+    (and the restatement, faithfully) then index images with int(NaN) and die with SIGSEGV.  The CUDA path answers with
+    status 0 for every feature it cannot place, touches no memory it does not own, and the handle stays usable."""
+    prm = capi.default_params(pyramids=3)
+    for case in ("dup01", "dup12", "nan_w"):
+        q = copy.copy(pair)
+        if case == "nan_w":
+            q.imu_w = pair.imu_w.copy(); q.imu_w[2, 1] = np.nan
+        else:
+            q.imu_t, q.imu_w = pair.imu_t[:3].copy(), pair.imu_w[:3].copy()
+            k = 1 if case == "dup01" else 2
+            q.imu_t[k] = q.imu_t[k - 1]
+        (g,) = small_ctx.track_batch([q], prm)
+        assert np.isnan(np.asarray(g.Rcl)).any(), case
+        assert g.n_predict == 0 and not g.status.any(), case
+    q = copy.copy(pair)
+    q.keys_ref_un = pair.keys_ref_un.copy()
+    q.keys_ref_un[3] = np.nan
+    q.keys_ref_un[5, 0] = np.inf
+    q.keys_ref = q.keys_ref_un
+    (g,) = small_ctx.track_batch([q], prm)
+    assert g.status[3] == 0 and g.status[5] == 0
+    rc, c = oracle.track(pair, prm, 1)                            # the finite features are tracked as if the others were not there
+    keep = np.ones(pair.n_keys, bool); keep[[3, 5]] = False
+    assert np.array_equal(g.pm_status[keep], c.pm_status[keep]) and np.array_equal(g.pm_pt_un[keep].view(np.uint32), c.pm_pt_un[keep].view(np.uint32))
+    (g,) = small_ctx.track_batch([pair], prm)
+    helpers.assert_bit_exact(g, c)

@@ -414,3 +414,18 @@ def test_stream_continuation_needs_a_previous_batch(cuda_lib):
             ctx.track_batch([q, q], prm)                           # more streams than the previous batch had
         with pytest.raises(tracker.PagkError):
             ctx.track_batch([p, q], prm)                           # mixed
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_imu", [0, 1, 2, 3])
+def test_short_imu_vectors(gpu_ctx, oracle, n_imu):
+    """no / one / two / three gyro samples (src/gyro_aided_tracker.cpp:521-562: size() - 1 intervals)"""
+    import copy
+    p = synth.make_pair(8100 + n_imu, width=320, height=240, n_keys=64, pyramids=3, border=24)
+    q = copy.copy(p)
+    q.imu_t, q.imu_w = p.imu_t[:n_imu].copy(), p.imu_w[:n_imu].copy()
+    prm = capi.default_params(pyramids=3)
+    (g,) = gpu_ctx.track_batch([q], prm)
+    rc, c = oracle.track(q, prm, 1)
+    assert rc == 0
+    helpers.assert_bit_exact(g, c)

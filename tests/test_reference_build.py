@@ -159,3 +159,22 @@ def test_reference_build_is_deterministic_under_threads(reference, oracle):
         many = reference.track(pair, prm, 5 + rep % 4)[1]
         assert np.array_equal(one.pm_status, many.pm_status) and np.array_equal(one.status, many.status), rep
     _same(one, oracle.track(pair, prm, 3)[1])
+
+
+@pytest.mark.parametrize("n_imu", [0, 1, 2, 3])
+def test_short_imu_vectors(reference, oracle, n_imu):
+    """`n = mvImuFromLastFrame.size() - 1` intervals (src/gyro_aided_tracker.cpp:524): no sample or one sample integrate
+    nothing (Rcl = Rbc^T Rbc), two use w[0] over the whole frame interval, three take the first- and last-interval branches"""
+    import copy
+    p = synth.make_pair(8100 + n_imu, width=320, height=240, n_keys=64, pyramids=3, border=24)
+    q = copy.copy(p)
+    q.imu_t, q.imu_w = p.imu_t[:n_imu].copy(), p.imu_w[:n_imu].copy()
+    prm = capi.default_params(pyramids=3)
+    rc, ref = reference.track(q, prm, 2)
+    assert rc == 0
+    rc, cpu = oracle.track(q, prm, 2)
+    assert rc == 0
+    _same(ref, cpu)
+    if n_imu < 2:
+        assert np.array_equal(np.asarray(cpu.Rcl, np.float32).reshape(3, 3), (q.Rbc.T.astype(np.float64) @ q.Rbc).astype(np.float32)) \
+            or np.allclose(np.asarray(cpu.Rcl).reshape(3, 3), np.eye(3), atol=1e-6)
