@@ -429,3 +429,25 @@ def test_short_imu_vectors(gpu_ctx, oracle, n_imu):
     rc, c = oracle.track(q, prm, 1)
     assert rc == 0
     helpers.assert_bit_exact(g, c)
+
+
+@pytest.mark.gpu
+def test_images_with_a_row_pitch(gpu_ctx, oracle):
+    """a cv::Mat that is a region of a larger one has step > cols (GetPixelValue indexes with img.step,
+    src/patch_match.cpp:397-403): pagk_pair_in.pitch carries it; the result is that of the packed image"""
+    import ctypes as C
+    p = synth.make_pair(8300, width=320, height=240, n_keys=100, pyramids=3, border=24)
+    prm = capi.default_params(pyramids=3)
+    rc, c = oracle.track(p, prm, 1)
+    assert rc == 0
+    pad = 40
+    big_ref = np.full((240, 320 + pad), 255, np.uint8); big_ref[:, :320] = p.img_ref
+    big_cur = np.full((240, 320 + pad), 7, np.uint8); big_cur[:, :320] = p.img_cur
+    ins = capi.make_in_array([p])
+    ins[0].img_ref, ins[0].img_cur = big_ref.ctypes.data_as(capi._u8p), big_cur.ctypes.data_as(capi._u8p)
+    ins[0].pitch = big_ref.strides[0]
+    out = capi.PairOutputs(p.n_keys)
+    oarr = capi.make_out_array([out])
+    assert gpu_ctx.lib.pagk_track_batch(gpu_ctx.handle, C.byref(prm), 1, ins, oarr) == capi.PAGK_OK
+    capi.sync_out_array(oarr, [out])
+    helpers.assert_bit_exact(out, c)
