@@ -10,6 +10,9 @@ CSRC = os.path.join(_HERE, "csrc")
 SOURCES = ["pagk_kernels.cu", "pagk_lk_slots.cu", "pagk_lk_lanes.cu", "pagk_api.cu"]
 HEADERS = ["pagk_device.cuh", "pagk_kernels.h", "pagk_host_math.h", os.path.join("..", "..", "include", "pagk.h")]
 OUT = os.path.join(CSRC, "libpagk_cuda.so")
+# the same library with the index traps of the LK lanes kernel compiled in (-DPAGK_LANES_CHECK): test infrastructure,
+# selected with PAGK_LIB=<this path>; compute-sanitizer is not available on the GPU pool
+OUT_CHECK = os.path.join(CSRC, "libpagk_cuda_check.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -26,28 +29,29 @@ def nvcc_path() -> str:
     return p
 
 
-def needs_build() -> bool:
-    if not os.path.exists(OUT):
+def needs_build(out: str = OUT) -> bool:
+    if not os.path.exists(out):
         return True
-    t = os.path.getmtime(OUT)
+    t = os.path.getmtime(out)
     deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
-        return OUT
-    extra = os.environ.get("PAGK_NVCC_EXTRA", "").split()
+def build(force: bool = False, verbose: bool = False, check: bool = False) -> str:
+    out = OUT_CHECK if check else OUT
+    if not force and not needs_build(out):
+        return out
+    extra = os.environ.get("PAGK_NVCC_EXTRA", "").split() + (["-DPAGK_LANES_CHECK"] if check else [])
     cmd = [nvcc_path()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
+          ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         print(r.stdout + r.stderr)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + r.stderr[-4000:])
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
     import sys
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, check="--check" in sys.argv))
