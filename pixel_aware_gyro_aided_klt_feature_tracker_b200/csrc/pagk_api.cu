@@ -1,9 +1,10 @@
 // pagk_api.cu -- the C-ABI of include/pagk.h: handle, HBM layout, copies, kernel sequencing.
 //
 // HBM layout of one handle (all allocated once in pagk_create, sized by pagk_config):
-//   images   [2 * max_pairs] slots; a slot holds every pyramid level of one image, each level
-//            continuous (step == cols) + one guard row + 1 byte, level bases 256-byte aligned.
-//            Slot 2p is the reference image of pair p, slot 2p+1 the current image.
+//   images   [2 * max_pairs] slots; a slot holds every pyramid level of one image, each level with a
+//            4-byte aligned row pitch, its wrap column and guard row (PagkLevelGeom), level bases
+//            256-byte aligned.  Slot 2p is the reference image of pair p, slot 2p+1 the current image.
+//   tmpl     [max_pairs * max_keys][levels] template records of the alignment kernel (pagk_lk_lanes.cu)
 //   keys     float2 [max_pairs][max_keys] x 2 (undistorted, raw)
 //   consts   PagkPairConst [max_pairs]   (KRK^-1, r31..r33, intrinsics, distortion, n_keys)
 //   results  structure of arrays [max_pairs][max_keys] (PagkOutPtrs), PagkPairResult [max_pairs]
@@ -13,6 +14,7 @@
 #include "pagk_host_math.h"
 #include "pagk_kernels.h"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -43,11 +45,14 @@ bool make_geom(int width, int height, int levels, PagkGeom *g) {
   int c = width, r = height;
   for (int l = 0; l < levels; ++l) {
     if (c < 1 || r < 1) return false;
-    g->lv[l].cols = c; g->lv[l].rows = r; g->lv[l].offset = (unsigned int)off;
-    off += align_up((size_t)(r + 1) * c + 1, 256);
+    // continuous when the rows are 4-byte aligned as they are, else padded with room for the explicit wrap column
+    const int pitch = (c % 4 == 0) ? c : (int)align_up((size_t)c + 1, 4);
+    g->lv[l].cols = c; g->lv[l].rows = r; g->lv[l].pitch = pitch; g->lv[l].offset = (unsigned int)off;
+    // rows + guard row, at least 32 rows, and 64 bytes: a staged window may overhang the image (its content is not used)
+    off += align_up((size_t)std::max(r + 1, 32) * pitch + 64, 256);
     c = (int)(c * 0.5); r = (int)(r * 0.5);  // cv::Size(cols * 0.5, rows * 0.5), reference src/patch_match.cpp:69
   }
-  for (int l = levels; l < PAGK_MAX_LEVELS; ++l) g->lv[l] = PagkLevelGeom{0, 0, 0};
+  for (int l = levels; l < PAGK_MAX_LEVELS; ++l) g->lv[l] = PagkLevelGeom{0, 0, 0, 0};
   g->slot_bytes = off;
   return true;
 }
@@ -83,7 +88,9 @@ struct pagk_handle {
   size_t out_bytes = 0;
   float *d_ntab = nullptr;
   size_t ntab_stride = 0;  // floats per pair
-  int *d_work = nullptr;   // work counters of the persistent LK kernels ([0]: slots kernel, [16..17]: lanes kernel)
+  int *d_work = nullptr;   // work counters of the persistent LK kernel ([16..17])
+  unsigned char *d_tmpl = nullptr;  // template records of the alignment kernel, [max_pairs * max_keys][max_levels]
+  size_t tmpl_rec = 0;              // bytes per record the buffer was sized for (0: patch size without a lanes kernel)
   int lk_parity = 0;       // which of the two lanes-kernel counters the next launch uses
   // pagk_set_predict_keypoints_and_mask: one block, allocated on first use (consts, last normals, 5 result vectors, counts)
   unsigned char *h_aux = nullptr;   // pinned staging of the entry points around the path (grown on demand)
@@ -105,8 +112,8 @@ struct pagk_handle {
   int n_sms = 0;
   long long *d_dbg = nullptr;  // PAGK_LK_TIMELINE=<file>: clock64 timeline of CTA 0 of the LK kernel (developer aid)
   const char *dbg_path = nullptr;
-  int lk_kernel = 0;       // PAGK_LK_KERNEL=slots|generic: use the previous pipelined kernel / the any-patch-size
-                           // kernel instead of the lane-per-feature one (tests compare them)
+  int lk_kernel = 0;       // PAGK_LK_KERNEL=generic: use the any-patch-size kernel instead of the lane-per-feature
+                           // one (tests compare them)
   // pinned staging
   unsigned char *h_in = nullptr;   // keys_un | keys | consts
   size_t h_in_keys_un = 0, h_in_keys = 0, h_in_pc = 0, h_in_bytes = 0;
@@ -208,7 +215,8 @@ int upload_images(pagk_handle *h, int n_pairs, const uint8_t *const *refs, const
   if (h->d_maps) return upload_images_rectify(h, n_pairs, refs, curs, width, height, pitches);
   const PagkGeom &g = h->geom;
   const size_t img_bytes = (size_t)width * height;
-  bool contiguous = true;
+  const size_t dp = (size_t)g.lv[0].pitch;
+  bool contiguous = dp == (size_t)width;  // level 0 is stored continuous on the device as well
   for (int p = 0; p < n_pairs && contiguous; ++p) {
     if (pitches[p] != width) contiguous = false;
     if (curs[p] != refs[p] + img_bytes) contiguous = false;
@@ -220,9 +228,9 @@ int upload_images(pagk_handle *h, int n_pairs, const uint8_t *const *refs, const
     return PAGK_OK;
   }
   for (int p = 0; p < n_pairs; ++p) {
-    CU(cudaMemcpy2DAsync(h->d_images + (size_t)(2 * p) * g.slot_bytes + g.lv[0].offset, width, refs[p], pitches[p], width,
+    CU(cudaMemcpy2DAsync(h->d_images + (size_t)(2 * p) * g.slot_bytes + g.lv[0].offset, dp, refs[p], pitches[p], width,
                          height, cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemcpy2DAsync(h->d_images + (size_t)(2 * p + 1) * g.slot_bytes + g.lv[0].offset, width, curs[p], pitches[p],
+    CU(cudaMemcpy2DAsync(h->d_images + (size_t)(2 * p + 1) * g.slot_bytes + g.lv[0].offset, dp, curs[p], pitches[p],
                          width, height, cudaMemcpyHostToDevice, h->stream));
   }
   return PAGK_OK;
@@ -237,7 +245,8 @@ int upload_images_continue(pagk_handle *h, int n_pairs, const uint8_t *const *cu
   CU(cudaMemcpy2DAsync(h->d_images, 2 * g.slot_bytes, h->d_images + g.slot_bytes, 2 * g.slot_bytes, g.slot_bytes, (size_t)n_pairs,
                        cudaMemcpyDeviceToDevice, h->stream));
   if (h->d_maps) return upload_images_rectify(h, n_pairs, nullptr, curs, width, height, pitches);
-  bool contiguous = true;
+  const size_t dp = (size_t)g.lv[0].pitch;
+  bool contiguous = dp == (size_t)width;
   for (int p = 0; p < n_pairs && contiguous; ++p) {
     if (pitches[p] != width) contiguous = false;
     if (p + 1 < n_pairs && curs[p + 1] != curs[p] + img_bytes) contiguous = false;
@@ -248,65 +257,47 @@ int upload_images_continue(pagk_handle *h, int n_pairs, const uint8_t *const *cu
     return PAGK_OK;
   }
   for (int p = 0; p < n_pairs; ++p)
-    CU(cudaMemcpy2DAsync(h->d_images + (size_t)(2 * p + 1) * g.slot_bytes + g.lv[0].offset, width, curs[p], pitches[p], width,
+    CU(cudaMemcpy2DAsync(h->d_images + (size_t)(2 * p + 1) * g.slot_bytes + g.lv[0].offset, dp, curs[p], pitches[p], width,
                          height, cudaMemcpyHostToDevice, h->stream));
   return PAGK_OK;
 }
 
-int check_batch(pagk_handle *h, int n_pairs, int width, int height, int levels, int half) {
+// Validates a batch against the handle's capacity and computes its geometry into *g.  The handle's own geometry
+// (h->geom: the layout of the pyramids that ARE on the device) only changes when the caller commits *g, i.e. when
+// images of that layout are on their way into the slots.
+int check_batch(pagk_handle *h, int n_pairs, int width, int height, int levels, int half, PagkGeom *g) {
   if (!h) return fail(PAGK_ERR_INVALID, "null handle");
   if (n_pairs < 0 || n_pairs > h->cfg.max_pairs) return fail(PAGK_ERR_INVALID, "n_pairs exceeds pagk_config.max_pairs");
   if (levels < 1 || levels > h->cfg.max_levels) return fail(PAGK_ERR_INVALID, "pyramids exceeds pagk_config.max_levels");
   if (half < 1 || half > h->cfg.max_half_patch) return fail(PAGK_ERR_INVALID, "half_patch exceeds pagk_config.max_half_patch");
-  PagkGeom g;
-  if (!make_geom(width, height, levels, &g)) return fail(PAGK_ERR_INVALID, "image too small for the requested pyramid");
-  if (g.slot_bytes > h->slot_capacity) return fail(PAGK_ERR_INVALID, "image exceeds pagk_config.max_width/max_height");
+  // buffers beside the image slots (normalize tables, raw images of the rectification) are sized by max_width * max_height
+  if (width > h->cfg.max_width || height > h->cfg.max_height) return fail(PAGK_ERR_INVALID, "image exceeds pagk_config.max_width/max_height");
+  if (!make_geom(width, height, levels, g)) return fail(PAGK_ERR_INVALID, "image too small for the requested pyramid");
+  if (g->slot_bytes > h->slot_capacity) return fail(PAGK_ERR_INVALID, "image exceeds pagk_config.max_width/max_height");
   if (pagk_lk_smem_per_warp(half) > 227 * 1024) return fail(PAGK_ERR_INVALID, "half_patch too large for shared memory");
-  h->geom = g;
   return PAGK_OK;
 }
 
 int launch_lk_kernel(pagk_handle *h, const PagkOutPtrs &o, const PagkMode &m, int n_max, int n_pairs) {
-  if (h->lk_kernel == 0 && pagk_lk_lanes_supported(m)) {
+  if (h->lk_kernel == 0 && pagk_lk_lanes_supported(m) && h->d_tmpl && pagk_lk_lanes_record_bytes(m.half) <= h->tmpl_rec) {
     // PAGK_LK_TIMELINE=<file> with a -DPAGK_LANES_PROF build: per-warp phase cycles (developer aid)
-    if (h->d_dbg) cudaMemsetAsync(h->d_dbg, 0, 2048 * 8 * sizeof(long long), h->stream);
+    if (h->d_dbg) CU(cudaMemsetAsync(h->d_dbg, 0, 2048 * 8 * sizeof(long long), h->stream));
     if (++h->lk_epoch >= 0x0fffffff) {  // the epoch is about to repeat: forget every progress word written so far
-      cudaMemsetAsync(h->d_progress, 0, (size_t)h->cfg.max_pairs * h->cfg.max_keys * sizeof(int), h->stream);
+      CU(cudaMemsetAsync(h->d_progress, 0, (size_t)h->cfg.max_pairs * h->cfg.max_keys * sizeof(int), h->stream));
       h->lk_epoch = 1;
     }
     const int rc = pagk_launch_lk_lanes(h->d_images, h->geom, h->d_pc, h->d_keys_un, o, m, h->cfg.max_keys, n_max, n_pairs,
-                                        h->d_work + 16, h->lk_parity, h->d_progress, h->lk_epoch, h->n_sms,
+                                        h->d_work + 16, h->lk_parity, h->d_progress, h->lk_epoch, h->n_sms, h->d_tmpl,
                                         h->stream, &h->launches, h->d_dbg);
     if (rc == 0 && n_max > 0 && n_pairs > 0) h->lk_parity ^= 1;
     if (h->d_dbg && rc == 0) {
       std::vector<long long> tl(2048 * 8);
-      cudaMemcpyAsync(tl.data(), h->d_dbg, tl.size() * sizeof(long long), cudaMemcpyDeviceToHost, h->stream);
-      cudaStreamSynchronize(h->stream);
+      CU(cudaMemcpyAsync(tl.data(), h->d_dbg, tl.size() * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
       if (FILE *f = fopen(h->dbg_path, "w")) {
         for (size_t w = 0; w < tl.size() / 8; ++w) {
           if (!tl[w * 8 + 6]) continue;
           for (int k = 0; k < 8; ++k) fprintf(f, "%lld%c", tl[w * 8 + k], k == 7 ? '\n' : ' ');
-        }
-        fclose(f);
-      }
-    }
-    return rc;
-  }
-  if (h->lk_kernel != 2 && pagk_lk_slots_supported(m)) {
-    if (h->d_dbg) cudaMemsetAsync(h->d_dbg, 0, 512 * 16 * sizeof(long long), h->stream);
-    const int rc = pagk_launch_lk_slots(h->d_images, h->geom, h->d_pc, h->d_keys_un, o, m, h->cfg.max_keys, n_max, n_pairs,
-                                        h->d_work, h->n_sms, h->stream, &h->launches, h->d_dbg);
-    if (h->d_dbg && rc == 0) {
-      std::vector<long long> tl(512 * 16);
-      cudaMemcpyAsync(tl.data(), h->d_dbg, tl.size() * sizeof(long long), cudaMemcpyDeviceToHost, h->stream);
-      cudaStreamSynchronize(h->stream);
-      if (FILE *f = fopen(h->dbg_path, "w")) {
-        fprintf(f, "#");
-        for (int b = 0; b < 148; ++b) fprintf(f, " %lld:%lld", tl[6400 + 2 * b], tl[6400 + 2 * b + 1]);
-        fprintf(f, "\n");
-        for (int st = 0; st < 400; ++st) {
-          if (!tl[st * 16]) break;
-          for (int k = 0; k < 16; ++k) fprintf(f, "%lld%c", tl[st * 16 + k], k == 15 ? '\n' : ' ');
         }
         fclose(f);
       }
@@ -358,6 +349,9 @@ int pagk_create(const pagk_config *cfg, pagk_handle **out) {
   if (cfg->max_width < 1 || cfg->max_height < 1 || cfg->max_keys < 1 || cfg->max_pairs < 1 || cfg->max_levels < 1 ||
       cfg->max_levels > PAGK_MAX_LEVELS || cfg->max_half_patch < 1)
     return fail(PAGK_ERR_INVALID, "bad pagk_config");
+  // the pair (and the image, 2 * pair) is a grid dimension of the per-pair kernels: 65535 at most
+  if (cfg->max_pairs > 32767) return fail(PAGK_ERR_INVALID, "pagk_config.max_pairs exceeds 32767");
+  if ((long long)cfg->max_pairs * cfg->max_keys > 0x3fffffffLL) return fail(PAGK_ERR_INVALID, "pagk_config: max_pairs * max_keys exceeds 2^30");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     cudaGetLastError();
@@ -399,9 +393,15 @@ int pagk_create(const pagk_config *cfg, pagk_handle **out) {
   ok(cudaMalloc(&h->d_progress, NK * sizeof(int)));
   if (e == cudaSuccess) ok(cudaMemset(h->d_progress, 0, NK * sizeof(int)));
   ok(cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, cfg->device));
+  // function attributes belong to the device: set them for this handle's device (no process-wide "done" flag)
+  ok((cudaError_t)pagk_configure_kernels());
+  ok((cudaError_t)pagk_lk_lanes_configure());
+  // template records of the alignment kernel for the largest patch this handle may be asked for (5 and 10 have a lanes kernel)
+  h->tmpl_rec = cfg->max_half_patch >= 10 ? pagk_lk_lanes_record_bytes(10) : cfg->max_half_patch >= 5 ? pagk_lk_lanes_record_bytes(5) : 0;
+  if (h->tmpl_rec) ok(cudaMalloc(&h->d_tmpl, NK * (size_t)cfg->max_levels * h->tmpl_rec));
   {
     const char *k = getenv("PAGK_LK_KERNEL");
-    h->lk_kernel = (k && std::strcmp(k, "generic") == 0) ? 2 : (k && std::strcmp(k, "slots") == 0) ? 1 : 0;
+    h->lk_kernel = (k && std::strcmp(k, "generic") == 0) ? 2 : 0;
     h->dbg_path = getenv("PAGK_LK_TIMELINE");
     if (h->dbg_path) { ok(cudaMalloc(&h->d_dbg, 2048 * 8 * sizeof(long long))); }
   }
@@ -427,7 +427,7 @@ void pagk_destroy(pagk_handle *h) {
   if (h->stream && h->own_stream) cudaStreamSynchronize(h->stream);
   else cudaDeviceSynchronize();
   cudaFree(h->d_images); cudaFree(h->d_keys_un); cudaFree(h->d_keys); cudaFree(h->d_pc); cudaFree(h->d_res);
-  cudaFree(h->d_out); cudaFree(h->d_ntab); cudaFree(h->d_work); cudaFree(h->d_progress); cudaFree(h->d_geo); cudaFree(h->d_geo_res); cudaFree(h->d_carry); cudaFree(h->d_mask); cudaFreeHost(h->h_aux); cudaFree(h->d_fast); cudaFree(h->d_fast_out); cudaFree(h->d_remap); cudaFree(h->d_maps); cudaFree(h->d_raw); cudaFree(h->d_dbg);
+  cudaFree(h->d_out); cudaFree(h->d_ntab); cudaFree(h->d_work); cudaFree(h->d_tmpl); cudaFree(h->d_progress); cudaFree(h->d_geo); cudaFree(h->d_geo_res); cudaFree(h->d_carry); cudaFree(h->d_mask); cudaFreeHost(h->h_aux); cudaFree(h->d_fast); cudaFree(h->d_fast_out); cudaFree(h->d_remap); cudaFree(h->d_maps); cudaFree(h->d_raw); cudaFree(h->d_dbg);
   cudaFreeHost(h->h_in); cudaFreeHost(h->h_out); cudaFreeHost(h->h_res);
   for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
@@ -457,10 +457,10 @@ int pagk_upload_batch(pagk_handle *h, const pagk_params *prm, int n_pairs, const
   for (int p = 0; p < n_pairs; ++p) n_null += in[p].img_ref ? 0 : 1;
   const bool cont = n_null == n_pairs;
   if (n_null != 0 && !cont) return fail(PAGK_ERR_INVALID, "img_ref: null on every pair of the batch (stream continuation) or on none");
-  const PagkGeom prev = h->geom;
-  int rc = check_batch(h, n_pairs, W, H, prm->pyramids, half);
+  PagkGeom geom;
+  int rc = check_batch(h, n_pairs, W, H, prm->pyramids, half, &geom);
   if (rc != PAGK_OK) return rc;
-  if (cont && (h->cur_pairs < n_pairs || prev.width != h->geom.width || prev.height != h->geom.height || prev.levels != h->geom.levels)) {
+  if (cont && (h->cur_pairs < n_pairs || geom.width != h->geom.width || geom.height != h->geom.height || geom.levels != h->geom.levels)) {
     h->cur_pairs = 0;
     return fail(PAGK_ERR_INVALID, "stream continuation without a previous batch of the same geometry and at least as many pairs");
   }
@@ -507,11 +507,14 @@ int pagk_upload_batch(pagk_handle *h, const pagk_params *prm, int n_pairs, const
       if (in[p].normalize_table)
         CU(cudaMemcpyAsync(h->d_ntab + (size_t)p * h->ntab_stride, in[p].normalize_table, per * sizeof(float), cudaMemcpyHostToDevice, h->stream));
   }
+  // from here on the slots change: the geometry is committed together with the images, and whatever pyramids a failed
+  // copy leaves behind are not continued from
+  h->geom = geom;
+  h->cur_pairs = 0;  // until the run has built the new current pyramids
   rc = cont ? upload_images_continue(h, n_pairs, curs.data(), W, H, pitches.data())
             : upload_images(h, n_pairs, refs.data(), curs.data(), W, H, pitches.data());
   if (rc != PAGK_OK) return rc;
   h->cont = cont;
-  h->cur_pairs = 0;  // until the run has built the new current pyramids
   h->mode = m; h->n_pairs = n_pairs; h->n_max = n_max; h->e_type = prm->e_type;
   h->resident = true;
   return PAGK_OK;
@@ -758,16 +761,18 @@ int pagk_pyramid_level_size(int width, int height, int level, int *cols, int *ro
 int pagk_build_pyramids(pagk_handle *h, int n_images, const uint8_t *const *imgs, int width, int height, int pitch, int levels) {
   if (!h || !imgs) return fail(PAGK_ERR_INVALID, "null argument");
   if (n_images < 1 || n_images > 2 * h->cfg.max_pairs) return fail(PAGK_ERR_INVALID, "n_images exceeds 2 * max_pairs");
-  int rc = check_batch(h, 1, width, height, levels, 1);
+  PagkGeom geom;
+  int rc = check_batch(h, 1, width, height, levels, 1, &geom);
   if (rc != PAGK_OK) return rc;
+  for (int i = 0; i < n_images; ++i)
+    if (!imgs[i] || pitch < width) return fail(PAGK_ERR_INVALID, "bad image pointer or pitch");
   CU(cudaSetDevice(h->cfg.device));
   h->resident = false; h->ran = false;
-  for (int i = 0; i < n_images; ++i) {
-    if (!imgs[i] || pitch < width) return fail(PAGK_ERR_INVALID, "bad image pointer or pitch");
-    CU(cudaMemcpy2DAsync(h->d_images + (size_t)i * h->geom.slot_bytes + h->geom.lv[0].offset, width, imgs[i], pitch, width,
-                         height, cudaMemcpyHostToDevice, h->stream));
-  }
+  h->geom = geom;
   h->cur_pairs = 0;
+  for (int i = 0; i < n_images; ++i)
+    CU(cudaMemcpy2DAsync(h->d_images + (size_t)i * h->geom.slot_bytes + h->geom.lv[0].offset, (size_t)h->geom.lv[0].pitch, imgs[i], pitch,
+                         width, height, cudaMemcpyHostToDevice, h->stream));
   CU((cudaError_t)pagk_launch_pyramids(h->d_images, h->geom, n_images, 1, h->stream, &h->launches));
   CU(cudaStreamSynchronize(h->stream));
   return PAGK_OK;
@@ -780,7 +785,8 @@ int pagk_get_pyramid_level(pagk_handle *h, int image, int level, uint8_t *dst, s
   const size_t bytes = (size_t)L.cols * L.rows;
   if (dst_bytes < bytes) return fail(PAGK_ERR_INVALID, "destination too small");
   CU(cudaSetDevice(h->cfg.device));
-  CU(cudaMemcpyAsync(dst, h->d_images + (size_t)image * h->geom.slot_bytes + L.offset, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpy2DAsync(dst, (size_t)L.cols, h->d_images + (size_t)image * h->geom.slot_bytes + L.offset, (size_t)L.pitch, (size_t)L.cols,
+                       (size_t)L.rows, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return PAGK_OK;
 }
@@ -1077,10 +1083,13 @@ int pagk_patch_match(pagk_handle *h, const pagk_patch_match_in *in, pagk_pair_ou
   if (in->n_keys < 0 || in->n_keys > h->cfg.max_keys) return fail(PAGK_ERR_INVALID, "n_keys exceeds pagk_config.max_keys");
   if (in->n_keys > 0 && (!in->keys_ref_un || !in->pt_predict_un || !in->status || (in->consider_affine_deformation && !in->affine)))
     return fail(PAGK_ERR_INVALID, "null input vector");
-  int rc = check_batch(h, 1, in->width, in->height, in->pyramids, in->half_patch);
+  PagkGeom geom;
+  int rc = check_batch(h, 1, in->width, in->height, in->pyramids, in->half_patch, &geom);
   if (rc != PAGK_OK) return rc;
   CU(cudaSetDevice(h->cfg.device));
   h->resident = false; h->ran = false;
+  h->geom = geom;
+  h->cur_pairs = 0;
   PagkMode m;
   std::memset(&m, 0, sizeof(m));
   m.gyro_init = in->has_gyro_predict_initial ? 1 : 0; m.illum = in->consider_illumination ? 1 : 0;

@@ -12,11 +12,18 @@
 
 #define PAGK_MAX_LEVELS 8
 
-// One pyramid level inside an image slot.  A level is stored continuous (step == cols) and is
-// followed by one guard row (a copy of the last row) plus one byte, so that the +1 / +step taps of
-// PatchMatch::GetPixelValue (reference src/patch_match.cpp:399-403) never leave the allocation.
+// One pyramid level inside an image slot.  The reference's levels are continuous cv::Mats (step == cols), and the
+// +1 / +step taps of PatchMatch::GetPixelValue (reference src/patch_match.cpp:399-403) read one column past the row
+// end (the first byte of the next row) and one row past the image.  Here a level has a row pitch that is a multiple
+// of four bytes (the 4-byte asynchronous copies that stage the alignment kernel's windows need aligned rows):
+//   pitch == cols (cols % 4 == 0)   the level is continuous, column `cols` of row y IS pixel (0, y + 1)
+//   pitch  > cols                   column `cols` of row y is an explicit WRAP byte holding pixel (0, min(y + 1, rows - 1))
+// and in both cases row `rows` is a guard row (a copy of row rows - 1, with its own wrap byte).  So the byte at
+// (x, y) for 0 <= x <= cols, 0 <= y <= rows is what a continuous cv::Mat followed by a copy of its last row yields.
+// Past that the allocation continues (at least 32 rows and 64 bytes of slack) so that a staged window may overhang.
 struct PagkLevelGeom {
   int cols, rows;
+  int pitch;            // row pitch in bytes, a multiple of 4, >= cols (+1 when it is not cols)
   unsigned int offset;  // bytes from the start of the image slot, 256-byte aligned
 };
 
@@ -85,18 +92,18 @@ struct PagkOutPtrs {
 };
 
 // PatchMatch::GetPixelValue, reference src/patch_match.cpp:391-406, on a continuous level.
-__device__ __forceinline__ float pagk_sample(const unsigned char *__restrict__ img, int cols, int rows, float x,
+__device__ __forceinline__ float pagk_sample(const unsigned char *__restrict__ img, int pitch, int cols, int rows, float x,
                                              float y) {
   if (x < 0.f) x = 0.f;
   if (y < 0.f) y = 0.f;
   if (x >= (float)cols) x = (float)(cols - 1);
   if (y >= (float)rows) y = (float)(rows - 1);
   const int ix = (int)x, iy = (int)y;
-  const unsigned char *d = img + (size_t)iy * cols + ix;
+  const unsigned char *d = img + (size_t)iy * pitch + ix;
   const float xx = x - floorf(x), yy = y - floorf(y);
   const float a = 1.0f - xx, b = 1.0f - yy;
   const float top = a * (float)__ldg(d) + xx * (float)__ldg(d + 1);
-  const float bot = a * (float)__ldg(d + cols) + xx * (float)__ldg(d + cols + 1);
+  const float bot = a * (float)__ldg(d + pitch) + xx * (float)__ldg(d + pitch + 1);
   return b * top + yy * bot;
 }
 
@@ -117,8 +124,8 @@ __device__ __forceinline__ float2 pagk_distort(const PagkPairConst &c, float2 p)
 __device__ __forceinline__ double pagk_ddiv(double a, double b) { return a / b; }
 __device__ __forceinline__ double pagk_dsqrt(double a) { return sqrt(a); }
 // PatchMatch::GetPixelValue out of line, for the rare per-sample paths of the production kernel
-static __device__ __noinline__ float pagk_sample_call(const unsigned char *__restrict__ img, int cols, int rows, float x, float y) {
-  return pagk_sample(img, cols, rows, x, y);
+static __device__ __noinline__ float pagk_sample_call(const unsigned char *__restrict__ img, int pitch, int cols, int rows, float x, float y) {
+  return pagk_sample(img, pitch, cols, rows, x, y);
 }
 
 // Eigen::Matrix4d::llt().solve(b) as Eigen 3.3 evaluates it for a fixed 4x4 (see oracle/pagk_oracle.cpp

@@ -27,6 +27,17 @@
 #define PYR_TW 128
 #define PYR_TH 64
 
+// Pixel (0, gy) = v has just been produced: write the wrap bytes that mirror it (pagk_device.cuh, PagkLevelGeom):
+// column `cols` of the row above, and for the last row its own wrap byte and the guard row's.  In a continuous
+// level (pitch == cols) the first two are the pixel itself and the guard row's first byte: same value, harmless.
+__device__ __forceinline__ void pagk_write_wrap(unsigned char *ll, int pitch, int cols, int rows, int gy, unsigned char v) {
+  if (gy >= 1 && pitch > cols) ll[(size_t)(gy - 1) * pitch + cols] = v;
+  if (gy == rows - 1) {
+    if (pitch > cols) ll[(size_t)gy * pitch + cols] = v;
+    ll[(size_t)rows * pitch + cols] = v;
+  }
+}
+
 __device__ __forceinline__ unsigned int pagk_avg4x8(unsigned int r0, unsigned int r1) {
   // r0, r1: four horizontally adjacent pixels of two rows -> two output pixels in the low 16 bits
   const unsigned int a = (r0 & 0xffu) + ((r0 >> 8) & 0xffu) + (r1 & 0xffu) + ((r1 >> 8) & 0xffu) + 2u;
@@ -42,7 +53,7 @@ __device__ __forceinline__ void pagk_pyramid_tile_level(const unsigned char *s, 
   constexpr int OW = TW / 2, OH = TH / 2;
   if constexpr (OW >= 1 && OH >= 1) {
     __syncthreads();
-    const int colsl = g.lv[l].cols, rowsl = g.lv[l].rows;
+    const int colsl = g.lv[l].cols, rowsl = g.lv[l].rows, pl = g.lv[l].pitch;
     unsigned char *ll = img + g.lv[l].offset;
     const int ox0 = tx0 >> l, oy0 = ty0 >> l;
 #pragma unroll
@@ -54,11 +65,9 @@ __device__ __forceinline__ void pagk_pyramid_tile_level(const unsigned char *s, 
       d[oy * OW + ox] = v;
       const int gx = ox0 + ox, gy = oy0 + oy;
       if (gx < colsl && gy < rowsl) {
-        ll[(size_t)gy * colsl + gx] = v;
-        if (gy == rowsl - 1) {
-          ll[(size_t)rowsl * colsl + gx] = v;
-          if (gx == 0) ll[(size_t)(rowsl + 1) * colsl] = v;
-        }
+        ll[(size_t)gy * pl + gx] = v;
+        if (gy == rowsl - 1) ll[(size_t)rowsl * pl + gx] = v;  // guard row
+        if (gx == 0) pagk_write_wrap(ll, pl, colsl, rowsl, gy, v);
       }
     }
     if (l < n_fused) pagk_pyramid_tile_level<OW, OH>(d, const_cast<unsigned char *>(s), img, g, l + 1, n_fused, tx0, ty0, t);
@@ -74,7 +83,7 @@ __global__ void __launch_bounds__(256, PAGK_PYR_MIN_BLOCKS) pagk_pyramid_fused_k
   __shared__ __align__(16) unsigned char sbuf[2][(PYR_TW / 2) * (PYR_TH / 2)];
   unsigned char *img = images + (size_t)blockIdx.z * z_stride * g.slot_bytes;
   const int t = threadIdx.x;
-  const int cols0 = g.lv[0].cols, rows0 = g.lv[0].rows;
+  const int cols0 = g.lv[0].cols, rows0 = g.lv[0].rows, p0 = g.lv[0].pitch;
   unsigned char *l0 = img + g.lv[0].offset;
   const int tx0 = blockIdx.x * PYR_TW, ty0 = blockIdx.y * PYR_TH;
 
@@ -82,31 +91,38 @@ __global__ void __launch_bounds__(256, PAGK_PYR_MIN_BLOCKS) pagk_pyramid_fused_k
   {
     const int tx = t & 7, ty = t >> 3;  // 8 threads x 16 px per row pair, 32 row pairs
     const int x0 = tx0 + tx * 16, y0 = ty0 + ty * 2;
-    const bool vec = ((cols0 & 15) == 0);
+    const bool vec = ((cols0 & 15) == 0);  // then p0 == cols0 and every further fused level is continuous as well
     unsigned int a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
     const bool in0 = (x0 < cols0) && (y0 < rows0), in1 = (x0 < cols0) && (y0 + 1 < rows0);
     if (vec) {
-      if (in0) { const uint4 v = *reinterpret_cast<const uint4 *>(l0 + (size_t)y0 * cols0 + x0); a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w; }
-      if (in1) { const uint4 v = *reinterpret_cast<const uint4 *>(l0 + (size_t)(y0 + 1) * cols0 + x0); b[0] = v.x; b[1] = v.y; b[2] = v.z; b[3] = v.w; }
+      if (in0) { const uint4 v = *reinterpret_cast<const uint4 *>(l0 + (size_t)y0 * p0 + x0); a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w; }
+      if (in1) { const uint4 v = *reinterpret_cast<const uint4 *>(l0 + (size_t)(y0 + 1) * p0 + x0); b[0] = v.x; b[1] = v.y; b[2] = v.z; b[3] = v.w; }
     } else {
       for (int k = 0; k < 16; ++k) {
-        if (in0 && x0 + k < cols0) a[k >> 2] |= (unsigned int)l0[(size_t)y0 * cols0 + x0 + k] << (8 * (k & 3));
-        if (in1 && x0 + k < cols0) b[k >> 2] |= (unsigned int)l0[(size_t)(y0 + 1) * cols0 + x0 + k] << (8 * (k & 3));
+        if (in0 && x0 + k < cols0) a[k >> 2] |= (unsigned int)l0[(size_t)y0 * p0 + x0 + k] << (8 * (k & 3));
+        if (in1 && x0 + k < cols0) b[k >> 2] |= (unsigned int)l0[(size_t)(y0 + 1) * p0 + x0 + k] << (8 * (k & 3));
       }
+    }
+    // explicit wrap bytes of a padded level 0 (the caller's image has a width that is not a multiple of 4)
+    if (p0 > cols0 && x0 == 0) {
+      if (in0 && y0 >= 1) l0[(size_t)(y0 - 1) * p0 + cols0] = (unsigned char)(a[0] & 0xffu);
+      if (in1) l0[(size_t)y0 * p0 + cols0] = (unsigned char)(b[0] & 0xffu);
+      if (in0 && y0 == rows0 - 1) l0[(size_t)y0 * p0 + cols0] = (unsigned char)(a[0] & 0xffu);
+      if (in1 && y0 + 1 == rows0 - 1) l0[(size_t)(y0 + 1) * p0 + cols0] = (unsigned char)(b[0] & 0xffu);
     }
     // guard row of level 0 = copy of row rows0-1 (+ one byte)
     if (in0 && (y0 == rows0 - 1 || y0 + 1 == rows0 - 1)) {
       const unsigned int *src = (y0 == rows0 - 1) ? a : b;
-      unsigned char *gr = l0 + (size_t)rows0 * cols0 + x0;
+      unsigned char *gr = l0 + (size_t)rows0 * p0 + x0;
       if (vec) {
         *reinterpret_cast<uint4 *>(gr) = make_uint4(src[0], src[1], src[2], src[3]);
       } else {
         for (int k = 0; k < 16 && x0 + k < cols0; ++k) gr[k] = (unsigned char)(src[k >> 2] >> (8 * (k & 3)));
       }
-      if (x0 == 0) l0[(size_t)(rows0 + 1) * cols0] = (unsigned char)(src[0] & 0xffu);
+      if (x0 == 0) l0[(size_t)rows0 * p0 + cols0] = (unsigned char)(src[0] & 0xffu);
     }
     if (n_fused >= 1) {
-      const int cols1 = g.lv[1].cols, rows1 = g.lv[1].rows;
+      const int cols1 = g.lv[1].cols, rows1 = g.lv[1].rows, p1 = g.lv[1].pitch;
       unsigned char *l1 = img + g.lv[1].offset;
       uint2 o;
       o.x = pagk_avg4x8(a[0], b[0]) | (pagk_avg4x8(a[1], b[1]) << 16);
@@ -114,18 +130,18 @@ __global__ void __launch_bounds__(256, PAGK_PYR_MIN_BLOCKS) pagk_pyramid_fused_k
       *reinterpret_cast<uint2 *>(&sbuf[0][ty * (PYR_TW / 2) + tx * 8]) = o;
       const int x1 = x0 >> 1, y1 = y0 >> 1;
       if (y1 < rows1 && x1 < cols1) {
-        unsigned char *dst = l1 + (size_t)y1 * cols1 + x1;
+        unsigned char *dst = l1 + (size_t)y1 * p1 + x1;
         if (vec && x1 + 8 <= cols1) {
           *reinterpret_cast<uint2 *>(dst) = o;
-          if (y1 == rows1 - 1) *reinterpret_cast<uint2 *>(dst + cols1) = o;
+          if (y1 == rows1 - 1) *reinterpret_cast<uint2 *>(dst + p1) = o;
         } else {
           for (int k = 0; k < 8 && x1 + k < cols1; ++k) {
             const unsigned char v = (unsigned char)((k < 4 ? o.x : o.y) >> (8 * (k & 3)));
             dst[k] = v;
-            if (y1 == rows1 - 1) dst[cols1 + k] = v;
+            if (y1 == rows1 - 1) dst[p1 + k] = v;
           }
         }
-        if (y1 == rows1 - 1 && x1 == 0) l1[(size_t)(rows1 + 1) * cols1] = (unsigned char)(o.x & 0xffu);
+        if (x1 == 0) pagk_write_wrap(l1, p1, cols1, rows1, y1, (unsigned char)(o.x & 0xffu));
       }
     }
   }
@@ -138,8 +154,8 @@ __global__ void __launch_bounds__(256, PAGK_PYR_MIN_BLOCKS) pagk_pyramid_fused_k
 __global__ void __launch_bounds__(256) pagk_pyramid_general_kernel(unsigned char *__restrict__ images, PagkGeom g,
                                                                  int level, int z_stride) {
   unsigned char *img = images + (size_t)blockIdx.z * z_stride * g.slot_bytes;
-  const int scols = g.lv[level - 1].cols, srows = g.lv[level - 1].rows;
-  const int dcols = g.lv[level].cols, drows = g.lv[level].rows;
+  const int scols = g.lv[level - 1].cols, srows = g.lv[level - 1].rows, sp = g.lv[level - 1].pitch;
+  const int dcols = g.lv[level].cols, drows = g.lv[level].rows, dp = g.lv[level].pitch;
   const unsigned char *src = img + g.lv[level - 1].offset;
   unsigned char *dst = img + g.lv[level].offset;
   const int dx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -147,8 +163,8 @@ __global__ void __launch_bounds__(256) pagk_pyramid_general_kernel(unsigned char
   if (dx >= dcols || dy >= drows) return;
   unsigned char v;
   if (scols == 2 * dcols && srows == 2 * drows) {
-    const unsigned char *r0 = src + (size_t)(2 * dy) * scols + 2 * dx;
-    v = (unsigned char)((r0[0] + r0[1] + r0[scols] + r0[scols + 1] + 2) >> 2);
+    const unsigned char *r0 = src + (size_t)(2 * dy) * sp + 2 * dx;
+    v = (unsigned char)((r0[0] + r0[1] + r0[sp] + r0[sp + 1] + 2) >> 2);
   } else {
     const double sx = (double)scols / dcols, sy = (double)srows / drows;
     float fx = (float)((dx + 0.5) * sx - 0.5);
@@ -163,17 +179,15 @@ __global__ void __launch_bounds__(256) pagk_pyramid_general_kernel(unsigned char
     const int y0 = min(max(iy, 0), srows - 1), y1 = min(max(iy + 1, 0), srows - 1);
     const int b0 = __float2int_rn((1.f - fy) * 2048.f), b1 = __float2int_rn(fy * 2048.f);
     const int ix1 = min(ix + 1, scols - 1);
-    const unsigned char *r0 = src + (size_t)y0 * scols, *r1 = src + (size_t)y1 * scols;
+    const unsigned char *r0 = src + (size_t)y0 * sp, *r1 = src + (size_t)y1 * sp;
     const int t0 = r0[ix] * a0 + r0[ix1] * a1;
     const int t1 = r1[ix] * a0 + r1[ix1] * a1;
     const int o = (((b0 * (t0 >> 4)) >> 16) + ((b1 * (t1 >> 4)) >> 16) + 2) >> 2;
     v = (unsigned char)min(max(o, 0), 255);
   }
-  dst[(size_t)dy * dcols + dx] = v;
-  if (dy == drows - 1) {
-    dst[(size_t)drows * dcols + dx] = v;
-    if (dx == 0) dst[(size_t)(drows + 1) * dcols] = v;
-  }
+  dst[(size_t)dy * dp + dx] = v;
+  if (dy == drows - 1) dst[(size_t)drows * dp + dx] = v;
+  if (dx == 0) pagk_write_wrap(dst, dp, dcols, drows, dy, v);
 }
 
 // =================================================================================================
@@ -316,7 +330,7 @@ __global__ void pagk_lk_kernel(const unsigned char *__restrict__ images, PagkGeo
     for (int level = mode.levels - 1; level >= 0; --level) {
       const unsigned char *I1 = pagk_level_ptr(images, g, pair, 0, level);
       const unsigned char *I2 = pagk_level_ptr(images, g, pair, 1, level);
-      const int cols = g.lv[level].cols, rows = g.lv[level].rows;
+      const int cols = g.lv[level].cols, rows = g.lv[level].rows, pitch = g.lv[level].pitch;
       const float scale = 1.0f / (float)(1 << level);
       const float ptx = pt1.x * scale, pty = pt1.y * scale;
       float nx, ny;
@@ -326,10 +340,10 @@ __global__ void pagk_lk_kernel(const unsigned char *__restrict__ images, PagkGeo
       float dg = 0.f, db = 0.f, cost = 0.f;
       lastCost = 0.f;
       succ = true;
-      const float cval = -pagk_sample(I1, cols, rows, ptx, pty);
+      const float cval = -pagk_sample(I1, pitch, cols, rows, ptx, pty);
       for (int p = lane; p < NP; p += 32) {
         const int y = p / P - h, x = p % P - h;
-        sT[p] = pagk_sample(I1, cols, rows, ptx + (float)x, pty + (float)y);
+        sT[p] = pagk_sample(I1, pitch, cols, rows, ptx + (float)x, pty + (float)y);
         sJ[p * 5 + 2] = (double)cval;
         sJ[p * 5 + 3] = 1.0;
       }
@@ -339,9 +353,9 @@ __global__ void pagk_lk_kernel(const unsigned char *__restrict__ images, PagkGeo
         const float gain = 1.0f + dg;
         for (int p = lane; p < NP; p += 32) {
           const float sx = bx + sWx[p], sy = by + sWy[p];
-          const float e = (pagk_sample(I2, cols, rows, sx, sy) + db) - gain * sT[p];
-          const float gx = pagk_sample(I2, cols, rows, sx + 1.0f, sy) - pagk_sample(I2, cols, rows, sx - 1.0f, sy);
-          const float gy = pagk_sample(I2, cols, rows, sx, sy + 1.0f) - pagk_sample(I2, cols, rows, sx, sy - 1.0f);
+          const float e = (pagk_sample(I2, pitch, cols, rows, sx, sy) + db) - gain * sT[p];
+          const float gx = pagk_sample(I2, pitch, cols, rows, sx + 1.0f, sy) - pagk_sample(I2, pitch, cols, rows, sx - 1.0f, sy);
+          const float gy = pagk_sample(I2, pitch, cols, rows, sx, sy + 1.0f) - pagk_sample(I2, pitch, cols, rows, sx, sy - 1.0f);
           sJ[p * 5 + 0] = 0.5 * (double)gx;  // (float)(0.5 * (double)diff) is an exact halving
           sJ[p * 5 + 1] = 0.5 * (double)gy;
           sJ[p * 5 + 4] = -(double)e;
@@ -413,7 +427,7 @@ __global__ void __launch_bounds__(128) pagk_ncc_kernel(const unsigned char *__re
   const size_t o = (size_t)pair * max_keys + i;
   if (!out.gyro_status[o]) return;  // skipped at :173, mvNcc stays 0
   const unsigned char *I1 = pagk_level_ptr(images, g, pair, 0, 0), *I2 = pagk_level_ptr(images, g, pair, 1, 0);
-  const int cols = g.lv[0].cols, rows = g.lv[0].rows, h = mode.half;
+  const int cols = g.lv[0].cols, rows = g.lv[0].rows, pitch = g.lv[0].pitch, h = mode.half;
   const float2 pr = keys_un[o], pc = out.pm_un[o];
   const float4 A = out.affine[o];
   float mean_ref = 0.f, mean_cur = 0.f;
@@ -421,8 +435,8 @@ __global__ void __launch_bounds__(128) pagk_ncc_kernel(const unsigned char *__re
     for (int y = -h; y <= h; ++y) {
       float wx = (float)x, wy = (float)y;
       if (mode.affine) { wx = A.x * (float)x + A.y * (float)y; wy = A.z * (float)x + A.w * (float)y; }
-      mean_ref += pagk_sample(I1, cols, rows, pr.x + (float)x, pr.y + (float)y);
-      mean_cur += pagk_sample(I2, cols, rows, pc.x + wx, pc.y + wy);
+      mean_ref += pagk_sample(I1, pitch, cols, rows, pr.x + (float)x, pr.y + (float)y);
+      mean_cur += pagk_sample(I2, pitch, cols, rows, pc.x + wx, pc.y + wy);
     }
   const float n = (float)((2 * h + 1) * (2 * h + 1));
   mean_ref /= n;
@@ -432,8 +446,8 @@ __global__ void __launch_bounds__(128) pagk_ncc_kernel(const unsigned char *__re
     for (int y = -h; y <= h; ++y) {
       float wx = (float)x, wy = (float)y;
       if (mode.affine) { wx = A.x * (float)x + A.y * (float)y; wy = A.z * (float)x + A.w * (float)y; }
-      const float a = pagk_sample(I1, cols, rows, pr.x + (float)x, pr.y + (float)y) - mean_ref;
-      const float b = pagk_sample(I2, cols, rows, pc.x + wx, pc.y + wy) - mean_cur;
+      const float a = pagk_sample(I1, pitch, cols, rows, pr.x + (float)x, pr.y + (float)y) - mean_ref;
+      const float b = pagk_sample(I2, pitch, cols, rows, pc.x + wx, pc.y + wy) - mean_cur;
       num += a * b;
       d1 += a * a;
       d2 += b * b;
@@ -1047,7 +1061,7 @@ __device__ __forceinline__ unsigned int pagk_remap_px(const unsigned char *__res
 __global__ void __launch_bounds__(256) pagk_remap_slots_kernel(const unsigned char *__restrict__ raw, unsigned char *__restrict__ images,
                                                              PagkGeom g, const float *__restrict__ map_x, const float *__restrict__ map_y,
                                                              int z_stride, int z_offset) {
-  const int cols = g.lv[0].cols, rows = g.lv[0].rows;
+  const int cols = g.lv[0].cols, rows = g.lv[0].rows, pitch = g.lv[0].pitch;  // the raw images and the maps are dense
   const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
   if (y >= rows) return;
   const unsigned char *src = raw + (size_t)blockIdx.z * cols * rows;
@@ -1059,13 +1073,13 @@ __global__ void __launch_bounds__(256) pagk_remap_slots_kernel(const unsigned ch
     const float4 mx = *reinterpret_cast<const float4 *>(map_x + o), my = *reinterpret_cast<const float4 *>(map_y + o);
     const unsigned int v = pagk_remap_px(src, cols, rows, mx.x, my.x) | (pagk_remap_px(src, cols, rows, mx.y, my.y) << 8) |
                            (pagk_remap_px(src, cols, rows, mx.z, my.z) << 16) | (pagk_remap_px(src, cols, rows, mx.w, my.w) << 24);
-    *reinterpret_cast<unsigned int *>(dst + o) = v;
+    *reinterpret_cast<unsigned int *>(dst + (size_t)y * pitch + x) = v;
   } else {
     for (int k = 0; k < 4; ++k) {
       const int x = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4 + k;
       if (x >= cols) return;
       const size_t o = (size_t)y * cols + x;
-      dst[o] = (unsigned char)pagk_remap_px(src, cols, rows, map_x[o], map_y[o]);
+      dst[(size_t)y * pitch + x] = (unsigned char)pagk_remap_px(src, cols, rows, map_x[o], map_y[o]);
     }
   }
 }
@@ -1108,6 +1122,11 @@ int pagk_launch_predict(const PagkPairConst *pcs, const float2 *keys_un, const f
   return (int)cudaGetLastError();
 }
 
+// per device, from pagk_create after cudaSetDevice (a function attribute belongs to the device it was set on)
+int pagk_configure_kernels() {
+  return (int)cudaFuncSetAttribute(pagk_lk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+
 size_t pagk_lk_smem_per_warp(int half) {
   const size_t NP = (size_t)(2 * half + 1) * (2 * half + 1);
   return NP * 56 + 128;
@@ -1122,12 +1141,6 @@ int pagk_launch_lk(const unsigned char *images, const PagkGeom &g, const PagkPai
   while (wpc > 1 && pw * wpc > 200 * 1024) wpc >>= 1;
   const size_t smem = pw * wpc;
   if (smem > 227 * 1024) return (int)cudaErrorInvalidValue;
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(pagk_lk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    configured = smem;
-  }
   dim3 grid((n_max + wpc - 1) / wpc, n_pairs);
   pagk_lk_kernel<<<grid, wpc * 32, smem, st>>>(images, g, pcs, keys_un, out, mode, max_keys, wpc);
   ++*launches;

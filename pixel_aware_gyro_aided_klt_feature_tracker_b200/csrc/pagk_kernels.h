@@ -45,16 +45,15 @@ int pagk_launch_remap_slots(const unsigned char *raw, unsigned char *images, con
 int pagk_launch_count_status(const PagkPairConst *pcs, const PagkOutPtrs &out, int max_keys, int n_pairs,
                              PagkPairResult *res, cudaStream_t st, long long *launches);
 
-// production patch-alignment kernel (pagk_lk_slots.cu): persistent CTAs, 32 feature slots each
-size_t pagk_lk_slots_smem();
-bool pagk_lk_slots_supported(const PagkMode &mode);
-int pagk_launch_lk_slots(const unsigned char *images, const PagkGeom &g, const PagkPairConst *pcs, const float2 *keys_un,
-                         const PagkOutPtrs &out, const PagkMode &mode, int max_keys, int n_max, int n_pairs,
-                         int *work_counter, int n_sms, cudaStream_t st, long long *launches, long long *dbg);
+// per device, from pagk_create after cudaSetDevice: dynamic shared memory opt-in of every kernel that needs it
+int pagk_configure_kernels();
+int pagk_lk_lanes_configure();
 
-// production patch-alignment kernel (pagk_lk_lanes.cu): persistent CTAs, one lane per feature
+// production patch-alignment kernels (pagk_lk_lanes.cu): template staging pass + persistent CTAs, one lane per feature.
+// tmpl: [max_pairs * max_keys][levels] template records of pagk_lk_lanes_record_bytes(half) bytes each.
 bool pagk_lk_lanes_supported(const PagkMode &mode);
+size_t pagk_lk_lanes_record_bytes(int half);
 int pagk_launch_lk_lanes(const unsigned char *images, const PagkGeom &g, const PagkPairConst *pcs, const float2 *keys_un,
                          const PagkOutPtrs &out, const PagkMode &mode, int max_keys, int n_max, int n_pairs,
-                         int *work_counters, int parity, int *progress, int epoch, int n_sms, cudaStream_t st,
-                         long long *launches, long long *prof);
+                         int *work_counters, int parity, int *progress, int epoch, int n_sms, unsigned char *tmpl,
+                         cudaStream_t st, long long *launches, long long *prof);

@@ -1,4 +1,5 @@
-// pagk_lk_lanes.cu -- K3, the production patch-alignment kernel: one LANE per feature.
+// pagk_lk_lanes.cu -- K3, the production patch-alignment kernels: a template staging pass (K3a) and the alignment
+// kernel proper (K3b, one LANE per feature) fed by the copy engines.
 //
 // Reference: PatchMatch::OpticalFlowMultiLevel + OpticalFlowConsideringIlluminationChange_onePixel,
 // src/patch_match.cpp:79-142 and :167-367 (forward-additive Gauss-Newton on (dx, dy, dg, db)).
@@ -6,31 +7,38 @@
 // Why this shape.  The 4x4 normal matrix of the reference is structurally singular, so the
 // 14 sums of one Gauss-Newton pass must be taken in double, in the reference's pixel order: a serial chain
 // of P*P steps per feature.  Independent features are the only parallelism that keeps that order, so a
-// lane owns a feature ("slot") for its whole life -- all pyramid levels, all iterations -- and walks the
-// patch pixel by pixel: five bilinear samples of the current image (FP32, no FMA contraction), residual and
-// gradient, then straight into the lane's twelve FP64 accumulators and the float cost.  Nothing is handed
-// over between threads, there is no barrier and no role: every warp of the CTA is an independent worker
-// with 32 slots, and a lane refills itself from the global work counter when its feature is finished.
-// (The previous design computed the samples pixel-parallel and handed float4 records to two accumulation
-// warps through shared memory; its stage time was bound by those two warps' serial work, it issued about
-// 1000 warp instructions per feature-iteration and was at 50 % of the shared-memory bandwidth.  This one
-// issues about 500 and reads each window tap once.)
+// lane owns a feature ("slot") for a whole pyramid level -- all its iterations -- and walks the patch pixel by
+// pixel: five bilinear samples of the current image (FP32, no FMA contraction), residual and gradient, then
+// straight into the lane's eleven FP64 accumulators and the float cost.  Nothing is handed over between threads
+// inside a level, there is no block barrier and no role: every warp of the CTA is an independent worker with 32
+// slots, and a lane refills itself from the global work counter when its level is finished.
 //
-// Shared memory per slot: the (P+10) x (P+6) window of the current level as u8 (what the loop samples) and
-// the P*P template values T = I1(pt + (x, y)) as float.  8 warps x 32 slots x 848 B = 212 KiB for 11 x 11.
-// u8 -> float is  (0x4B000000 | b) - 2^23  (LOP3 + FADD): exact, and off the 4-lane conversion pipe that
-// the three float -> double conversions per pixel need.
+// What a level needs before its first pass, and where it comes from:
+//   T[p] = I1(pt + (x, y)), the P*P template values, c = -I1(pt) and h22 = sum of c*c.  They depend on the
+//        reference keypoint and the level only -- not on the tracking result of the level above -- so K3a computes
+//        them for every (feature, level) of the batch up front, pixel-parallel at full occupancy, into one record
+//        per item in global memory.  K3b moves a record's T into the lane's slot with ONE bulk asynchronous copy
+//        (cp.async.bulk -> UBLKCP, completion on a per-warp mbarrier) issued by the lane itself, and the record's
+//        16-byte tail (last T value, c, h22) with one vector load.
+//   the WIN_W x WIN_H u8 window of the current image around the lane's sample box: 4-byte asynchronous copies
+//        (cp.async -> LDGSTS, lanes = window words) straight from the pyramid level, which is why a level's rows
+//        are 4-byte aligned (PagkLevelGeom::pitch).
+// All copies of a round -- every lane that starts a level, every window that moved -- are in flight together and
+// the warp waits for them once; no tap is staged through registers and no lane-serial setup code is left in the
+// alignment kernel (it was 31 % of a warp's time and a third of the kernel's code).
+//
+// Shared memory per slot: T_BULK bytes of template + the window (u8).  u8 -> float is (0x4B000000 | b) - 2^23
+// (LOP3 + FADD): exact, and off the 4-lane conversion pipe that the three float -> double conversions per pixel need.
 //
 // Per round a warp does, with warp-uniform control flow:
-//   refill   idle lanes take the next features from the global counter
-//   setup    (cooperative, lanes = pixels) for every lane that starts a level: stage the template window,
-//            compute T and c = -I1(pt)
-//   window   (cooperative) restage the current-image window of every lane whose sample box left it
+//   refill   idle lanes take the next items from the global counter
+//   issue    lanes that start a level: bulk copy of T + tail load; lanes whose sample box left the window (or that
+//            start a level): window copy; one wait for everything
 //   pass     lane = slot: P*P pixels, samples + ordered sums            <- the hot loop
 //   slow     lanes whose samples may clamp at the border, whose box does not fit the window, or that hit
 //            the one rounding case the shared-weight sampling does not cover, redo the pass sample by
-//            sample straight from the level (PatchMatch::GetPixelValue semantics, any coordinates)
-//   solve    lane = slot: 4x4 LLT in Eigen's operation order, update, exits, next level / next feature
+//            sample (PatchMatch::GetPixelValue semantics, any coordinates), lanes = pixels then lanes = accumulators
+//   solve    lane = slot: 4x4 LLT in Eigen's operation order, update, exits, next level / next item
 //
 // Bit-exactness of the window path is argued above the pass loop.
 #include <cstdlib>
@@ -39,48 +47,62 @@
 
 namespace {
 
-// warps per CTA and CTAs per SM: 8 warps (two per scheduler) fill the shared memory of an SM; as several small
-// CTAs they leave the SM one by one when the work runs out, and the next launch's CTAs move in
+// warps per CTA and CTAs per SM: 8 warps (two per scheduler) fill the shared memory of an SM
 #ifndef PAGK_LANES_WARPS
 #define PAGK_LANES_WARPS 8
 #endif
 constexpr int LANES_WARPS_SM = 8;
 constexpr int LANES_WARPS = PAGK_LANES_WARPS;
 // a warp with at most this many live lanes runs them one by one through the cooperative pass (lanes = pixels,
-// then lanes = accumulators: about 2.2 k warp instructions per slot) instead of a lockstep pass (17 k)
+// then lanes = accumulators: about 2.2 k warp instructions per slot) instead of a lockstep pass (16 k)
 #ifndef PAGK_LANES_SPARSE
 #define PAGK_LANES_SPARSE 5
 #endif
-// pixels unrolled in the pass loop.  A whole patch row (11) gives the scheduler the most to overlap but is a 25 KB
-// loop body, and with the warps of an SM in different phases the instruction cache then misses (ncu:
-// stalled_no_instruction 1.5 per issue, icc hit rate 72 %); 2 to 3 pixels measure best.
+// pixels per trip of the pass loop = floats per vector load of T (4: LDS.128, 2: LDS.64)
 #ifndef PAGK_LANES_UNROLL
-#define PAGK_LANES_UNROLL 3
+#define PAGK_LANES_UNROLL 4
 #endif
-#define PAGK_PRAGMA_(x) _Pragma(#x)
-#define PAGK_UNROLL(n) PAGK_PRAGMA_(unroll n)
 
 template <int HALF>
 struct LanesCfg {
   static constexpr int P = 2 * HALF + 1;
   static constexpr int NP = P * P;
-  static constexpr int WIN_W = P + 10;
+  // window of the current level: rows of WIN_W bytes copied as 4-byte words from a 4-byte aligned origin, so the
+  // usable width for an arbitrary box origin is WIN_W - 3
+  static constexpr int WIN_W = HALF <= 5 ? 24 : 36;
   static constexpr int WIN_H = P + 6;
-  // bytes per slot window, a whole and ODD number of 32-bit words: lane-private windows then start in
-  // distinct banks (NP is odd as well, so the same holds for the T rows)
-  static constexpr int WIN_WORDS = ((WIN_W * WIN_H + 3) / 4) | 1;
-  static constexpr int WIN_BYTES = WIN_WORDS * 4;
-  static constexpr int SLOT_BYTES = WIN_BYTES + NP * 4;
-  // slots per warp: all 32 lanes when eight warps' worth fits the SM; a 21 x 21 patch needs 2.6 KB per slot, and four
+  static constexpr int WPR = WIN_W / 4;  // words per window row
+  static constexpr int WIN_WORDS = WPR * WIN_H;
+  // bytes from one slot's window to the next: an ODD number of words, lane-private windows start in distinct banks
+  static constexpr int WIN_STRIDE = (WIN_WORDS | 1) * 4;
+  // a template record in global memory: T[0 .. NP-2] (T_BULK bytes, what the bulk copy moves: a multiple of 16),
+  // then T[NP-1], c = -T[NP/2], and h22 = the ordered double sum of c*c over the patch
+  static constexpr int T_BULK = (NP * 4) & ~15;
+  static constexpr int REC_BYTES = T_BULK + 16;
+  static_assert(NP * 4 - T_BULK == 4, "exactly the last template value stays out of the bulk copy");
+  // slots per warp: all 32 lanes when eight warps' worth fits the SM; a 21 x 21 patch needs 2.7 KB per slot, and four
   // warps (one per scheduler) of 20 slots then beat two warps of 32
   static constexpr int SLOTS = HALF <= 5 ? 32 : 20;
-  // per-warp scratch of the cooperative pass: NP records (Ix, Iy, -e) and the two constants c and 1
-  static constexpr int SCRATCH_FLOATS = NP * 3 + 4;
-  static constexpr int WARP_BYTES = SLOTS * SLOT_BYTES + SCRATCH_FLOATS * 4;
-  static constexpr int WARPS_SM = (227 * 1024) / WARP_BYTES < LANES_WARPS_SM ? (227 * 1024) / WARP_BYTES : LANES_WARPS_SM;
+  // T of slot s sits at t_off(s): 16-byte aligned for the bulk copy.  T_BULK / 16 is even, so plain s * T_BULK would
+  // put lanes s and s + 4 of a quarter warp into the same 16-byte bank group when every lane reads its own T with one
+  // 16-byte load; slots 4..7 of every group of eight are therefore moved up by 16 bytes (and the next group starts
+  // 16 bytes later): eight consecutive lanes then hit eight different bank groups.
+  __host__ __device__ static constexpr int t_off(int s) { return (s >> 3) * (8 * T_BULK + 16) + (s & 7) * T_BULK + 16 * ((s >> 2) & 1); }
+  static_assert((T_BULK / 16) % 8 == 6, "the bank-group argument above is for T_BULK = 480 and 1760");
+  static constexpr int T_WARP_BYTES = t_off(SLOTS - 1) + T_BULK;
+  static constexpr int WARP_BYTES = T_WARP_BYTES + SLOTS * WIN_STRIDE;
+  static_assert(WARP_BYTES % 16 == 0 && T_WARP_BYTES % 16 == 0, "bulk copies need 16-byte aligned destinations");
+  // per-warp scratch of the cooperative pass: 32 records (Ix, Iy, -e) -- one chunk of the patch -- and the two
+  // constants c and 1
+  static constexpr int SCRATCH_FLOATS = 32 * 3 + 4;
+  static constexpr int TAIL_BYTES = LANES_WARPS_SM * (SCRATCH_FLOATS * 4 + 8);  // + one mbarrier per warp
+  static constexpr int SMEM_MAX = 227 * 1024 - 256;  // the static shared arrays of the kernel
+  static constexpr int WARPS_FIT = (SMEM_MAX - TAIL_BYTES) / WARP_BYTES;
+  static constexpr int WARPS_SM = WARPS_FIT < LANES_WARPS_SM ? WARPS_FIT : LANES_WARPS_SM;
   static constexpr int WARPS = WARPS_SM < LANES_WARPS ? WARPS_SM : LANES_WARPS;
   static constexpr int CTAS_SM = WARPS_SM / WARPS;
-  static_assert(WIN_W <= 32, "one lane per window column");
+  static constexpr int SMEM_BYTES = WARPS * WARP_BYTES + TAIL_BYTES;
+  static_assert(WIN_W % 4 == 0 && WIN_W - 3 >= P + 4, "window narrower than a sample box");
   static_assert(WARPS >= 1, "patch too large for the lane kernel");
 };
 
@@ -93,47 +115,46 @@ __device__ __forceinline__ float floor_nn(float x, int &i) {
   if (r > x) { r -= 1.0f; i -= 1; }
   return r;
 }
+// developer aid (-DPAGK_LANES_CHECK): trap on a window index outside the staged window (compute-sanitizer stand-in)
 #ifdef PAGK_LANES_CHECK
-#define CHECK_IDX0(i, lo, hi) do { if ((i) < (lo) || (i) > (hi)) __trap(); } while (0)
+#define CHECK_IDX(i, lo, hi) do { if ((i) < (lo) || (i) > (hi)) __trap(); } while (0)
 #else
-#define CHECK_IDX0(i, lo, hi)
+#define CHECK_IDX(i, lo, hi)
 #endif
 // exact u8 -> float on the ALU + FP32 pipes
 __device__ __forceinline__ float u8f(unsigned int b) { return __uint_as_float(0x4B000000u | b) - 8388608.0f; }
 
-// Stage the WIN_W x WIN_H window with origin (x0, y0) of a level into shared memory (u8, row pitch WIN_W);
-// lane j < WIN_W owns column j.  Coordinates are clamped into [0, cols] x [0, rows] -- the level plus its
-// wrap column and guard row -- so every load is in bounds and unconditional.  Elements whose true position
-// lies outside that range hold an arbitrary in-bounds pixel; the callers never read them.
-// Split in two so that the loads of two windows can be in flight together.
-template <int WIN_W, int WIN_H>
-__device__ __forceinline__ void load_window(unsigned char (&v)[WIN_H], const unsigned char *__restrict__ img, int cols,
-                                            int rows, int x0, int y0, int lane) {
-  if (lane < WIN_W) {
-    const int gx = min(max(x0 + lane, 0), cols);
-    if (y0 >= 0 && y0 + WIN_H - 1 <= rows) {  // warp-uniform: no row clamps, one pointer walks down the column
-      const unsigned char *q = img + y0 * cols + gx;
-#pragma unroll
-      for (int i = 0; i < WIN_H; ++i) { v[i] = __ldg(q); q += cols; }
-    } else {
-#pragma unroll
-      for (int i = 0; i < WIN_H; ++i) {
-        const int gy = min(max(y0 + i, 0), rows);
-        v[i] = __ldg(img + gy * cols + gx);
-      }
-    }
-  }
+// ---- asynchronous copies and the mbarrier they complete on (PTX; SASS: LDGSTS, UBLKCP, SYNCS) ----
+__device__ __forceinline__ unsigned int smem_u32(const void *p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async4(unsigned int dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
-template <int WIN_W, int WIN_H>
-__device__ __forceinline__ void store_window(unsigned char *__restrict__ win, const unsigned char (&v)[WIN_H], int lane) {
-  if (lane < WIN_W) {
-#pragma unroll
-    for (int i = 0; i < WIN_H; ++i) win[i * WIN_W + lane] = v[i];
-  }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void mbar_init(unsigned int bar, unsigned int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(unsigned int bar, unsigned int bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned int bar, unsigned int parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(unsigned int dst, const void *src, unsigned int bytes, unsigned int bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar) : "memory");
+}
+
 // PatchMatch::GetPixelValue (reference src/patch_match.cpp:391-406) with the four taps taken from a staged
 // window with origin (wx0, wy0): the same clamps, the same expression tree.
-template <int WIN_W>
+template <int WIN_W, int WIN_H>
 __device__ __forceinline__ float window_sample(const unsigned char *__restrict__ win, int wx0, int wy0, float fcols,
                                                float fcm1, float frows, float frm1, float x, float y) {
   if (x < 0.f) x = 0.f;
@@ -143,7 +164,7 @@ __device__ __forceinline__ float window_sample(const unsigned char *__restrict__
   int ix, iy;
   const float fx = floor_nn(x, ix), fy = floor_nn(y, iy);
   const float xx = x - fx, yy = y - fy, wa = 1.0f - xx, wb = 1.0f - yy;
-  CHECK_IDX0((iy - wy0) * WIN_W + (ix - wx0), 0, WIN_W * (WIN_W - 4) - WIN_W - 2);  // WIN_H = WIN_W - 4
+  CHECK_IDX((iy - wy0) * WIN_W + (ix - wx0), 0, WIN_W * WIN_H - WIN_W - 2);
   const unsigned char *q = win + (iy - wy0) * WIN_W + (ix - wx0);
   return wb * (wa * u8f(q[0]) + xx * u8f(q[1])) + yy * (wa * u8f(q[WIN_W]) + xx * u8f(q[WIN_W + 1]));
 }
@@ -153,51 +174,143 @@ __device__ __forceinline__ float window_sample(const unsigned char *__restrict__
 #define PROF_DECL long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long pt = clock64();
 #define PROF(i) do { const long long now_ = clock64(); pf[i] += now_ - pt; pt = now_; } while (0)
 #define PROF_ADD(i, v) pf[i] += (v)
-#ifdef PAGK_PROF_SETUP
-#define PROF_SUB(i) PROF(i)
-#else
-#define PROF_SUB(i)
-#endif
 #define PROF_FLUSH() do { if (prof && lane == 0) for (int i_ = 0; i_ < 8; ++i_) prof[(size_t)(blockIdx.x * (blockDim.x >> 5) + warp) * 8 + i_] = pf[i_]; } while (0)
 #else
 #define PROF_DECL
-#define PROF_SUB(i)
 #define PROF(i)
 #define PROF_ADD(i, v)
 #define PROF_FLUSH()
 #endif
 
-// developer aid (-DPAGK_LANES_CHECK): trap on a window index outside the staged window (compute-sanitizer stand-in)
-#ifdef PAGK_LANES_CHECK
-#define CHECK_IDX(i, lo, hi) do { if ((i) < (lo) || (i) > (hi)) __trap(); } while (0)
-#else
-#define CHECK_IDX(i, lo, hi)
-#endif
-
 struct Sums {
-  double h00, h10, h11, h20, h21, h22, h30, h31, b0, b1, b2, b3;
+  double h00, h10, h11, h20, h21, h30, h31, b0, b1, b2, b3;
   float cost;
 };
 
 }  // namespace
 
+// =================================================================================================
+// K3a: the template records.  One warp per 32 consecutive (pair, feature, level) items: for each item lanes = pixels
+// compute T (the reference's GetPixelValue on the reference image, src/patch_match.cpp:253, :263) and store it,
+// then lane j of the warp runs item j's ordered sum of c*c (the h22 entry of the normal matrix, the same for every
+// iteration of the level: src/patch_match.cpp:296 with J[2] = c) and writes the record's tail.
+// =================================================================================================
+template <int HALF>
+__global__ void __launch_bounds__(256) pagk_lk_template_kernel(const unsigned char *__restrict__ images, PagkGeom g,
+                                                             const PagkPairConst *__restrict__ pcs,
+                                                             const float2 *__restrict__ keys_un, int levels, int max_keys,
+                                                             int n_max, int n_pairs, unsigned char *__restrict__ tmpl) {
+  using C = LanesCfg<HALF>;
+  constexpr int P = C::P, NP = C::NP, TK = (NP + 31) / 32;
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const long long wg = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long total = (long long)n_pairs * n_max * levels, base = wg * 32;
+  if (base >= total) return;
+  const float hf = (float)HALF;
+  float tpx[TK], tpy[TK];
+#pragma unroll
+  for (int k = 0; k < TK; ++k) {
+    const int p = lane + 32 * k, py = p / P;
+    tpx[k] = (float)(p - py * P - HALF); tpy[k] = (float)(py - HALF);
+  }
+  const int per_pair = n_max * levels;
+  float myc = 0.f, mylast = 0.f;
+  unsigned char *myrec = nullptr;
+#pragma unroll 1
+  for (int j = 0; j < 32; ++j) {
+    const long long idx = base + j;
+    if (idx >= total) break;
+    const int pr = (int)(idx / per_pair), rem = (int)(idx - (long long)pr * per_pair);
+    const int i = rem / levels, lv = rem - i * levels;
+    if (i >= pcs[pr].n_keys) continue;
+    const size_t o = (size_t)pr * max_keys + i;
+    const float2 p1 = keys_un[o];
+    const float scale = 1.0f / (float)(1 << lv);
+    const float ptx = p1.x * scale, pty = p1.y * scale;  // pt = mvKeysRefUn[i].pt * mvScales[level] (:177)
+    const int cols = g.lv[lv].cols, rows = g.lv[lv].rows, pitch = g.lv[lv].pitch;
+    const unsigned char *img1 = images + (size_t)(pr * 2) * g.slot_bytes + g.lv[lv].offset;
+    unsigned char *rec = tmpl + (o * (size_t)levels + lv) * C::REC_BYTES;
+    float *T = reinterpret_cast<float *>(rec);
+    const float txlo = ptx + (-hf), txhi = ptx + hf, tylo = pty + (-hf), tyhi = pty + hf;
+    const bool tin = txlo >= 0.0f && txhi < (float)cols && tylo >= 0.0f && tyhi < (float)rows;
+    float tv[TK];
+    if (tin) {
+      // no clamp of GetPixelValue fires anywhere in the template: the four taps of each pixel straight from the level,
+      // floor by a round-down add of 2^23 (exact for 0 <= x < 2^22), u8 -> float without the conversion pipe
+      unsigned char t00[TK], t10[TK], t01[TK], t11[TK];
+      float wxx[TK], wyy[TK];
+#pragma unroll
+      for (int k = 0; k < TK; ++k) {
+        const int p = lane + 32 * k;
+        const float cx = ptx + tpx[k], cy = pty + tpy[k];
+        const float tx = __fadd_rd(cx, 8388608.0f), ty = __fadd_rd(cy, 8388608.0f);
+        wxx[k] = cx - (tx - 8388608.0f); wyy[k] = cy - (ty - 8388608.0f);
+        const int ix = __float_as_int(tx) - 0x4B000000, iy = __float_as_int(ty) - 0x4B000000;
+        t00[k] = t10[k] = t01[k] = t11[k] = 0;
+        if (p < NP) {
+          const unsigned char *q = img1 + iy * pitch + ix;
+          t00[k] = __ldg(q); t10[k] = __ldg(q + 1); t01[k] = __ldg(q + pitch); t11[k] = __ldg(q + pitch + 1);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < TK; ++k) {
+        const float xx = wxx[k], yy = wyy[k], wa = 1.0f - xx, wb = 1.0f - yy;
+        tv[k] = wb * (wa * u8f(t00[k]) + xx * u8f(t10[k])) + yy * (wa * u8f(t01[k]) + xx * u8f(t11[k]));
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < TK; ++k) {
+        tv[k] = 0.f;
+        if (lane + 32 * k < NP) tv[k] = pagk_sample_call(img1, pitch, cols, rows, ptx + tpx[k], pty + tpy[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < TK; ++k) {
+      const int p = lane + 32 * k;
+      if (p < NP - 1) T[p] = tv[k];
+    }
+    // de_dg = -I1(pt) (src/patch_match.cpp:263) is minus the template value of the centre pixel: pt + (0, 0)
+    const float tc = __shfl_sync(FULL, tv[(NP / 2) / 32], (NP / 2) % 32);
+    const float tl = __shfl_sync(FULL, tv[(NP - 1) / 32], (NP - 1) % 32);
+    if (lane == j) { myc = -tc; mylast = tl; myrec = rec; }
+  }
+  if (myrec) {
+    const double c = (double)myc;
+    double h22 = 0.0;
+#pragma unroll 11
+    for (int p = 0; p < NP; ++p) h22 = fma(c, c, h22);  // c*c is exact in double: DFMA rounds like mul + add
+    float4 tail;
+    tail.x = mylast; tail.y = myc;
+    tail.z = __int_as_float(__double2loint(h22)); tail.w = __int_as_float(__double2hiint(h22));
+    *reinterpret_cast<float4 *>(myrec + C::T_BULK) = tail;
+  }
+}
+
+// =================================================================================================
+// K3b: the alignment kernel
+// =================================================================================================
 template <int HALF, bool AFFINE>
 __global__ void __launch_bounds__(LanesCfg<HALF>::WARPS * 32, LanesCfg<HALF>::CTAS_SM)
 pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const PagkPairConst *__restrict__ pcs,
                      const float2 *__restrict__ keys_un, PagkOutPtrs out, PagkMode mode, int max_keys, int n_max,
                      int n_pairs, int *__restrict__ work_counter, int *__restrict__ next_counter, int lane_cap,
-                     int split, int *progress, int epoch_base, long long *__restrict__ prof) {
+                     int split, int *progress, int epoch_base, const unsigned char *__restrict__ tmpl,
+                     long long *__restrict__ prof) {
   using C = LanesCfg<HALF>;
   constexpr int P = C::P, NP = C::NP, WIN_W = C::WIN_W, WIN_H = C::WIN_H;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned char *wwin = smem_raw + (size_t)warp * C::WARP_BYTES;               // [SLOTS][WIN_BYTES]
-  float *wT = reinterpret_cast<float *>(wwin + C::SLOTS * C::WIN_BYTES);       // [SLOTS][NP]
-  float *scratch = wT + C::SLOTS * NP;                                         // [NP][3] records, c, 1
+  unsigned char *wbase = smem_raw + (size_t)warp * C::WARP_BYTES;
+  unsigned char *wwin = wbase + C::T_WARP_BYTES;                                          // [SLOTS] windows, stride WIN_STRIDE
+  unsigned char *tail = smem_raw + (size_t)C::WARPS * C::WARP_BYTES;
+  float *scratch = reinterpret_cast<float *>(tail) + warp * C::SCRATCH_FLOATS;  // [32][3] records, c, 1
+  unsigned long long *mbars = reinterpret_cast<unsigned long long *>(tail + LANES_WARPS_SM * C::SCRATCH_FLOATS * 4);
+  const unsigned int mbar = smem_u32(mbars + warp);
   // lanes beyond SLOTS never own a feature; in the lockstep pass they read (harmlessly) the last slot's memory
   const int myslot = lane < C::SLOTS ? lane : C::SLOTS - 1;
-  const unsigned char *mywin = wwin + myslot * C::WIN_BYTES;
-  const float *myT = wT + myslot * NP;
+  const unsigned char *mywin = wwin + myslot * C::WIN_STRIDE;
+  const float *myT = reinterpret_cast<const float *>(wbase + C::t_off(myslot));
   const int total_work = n_pairs * n_max;
   const int top = mode.levels - 1;
   // Work items.  split == 0: an item is a feature (all levels in one lane).  split != 0: an item is one LEVEL of a
@@ -210,14 +323,20 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
   const float hf = (float)HALF;
   constexpr unsigned FULL = 0xffffffffu;
   // level geometry, indexed by each lane's own level
-  __shared__ int s_cols[PAGK_MAX_LEVELS], s_rows[PAGK_MAX_LEVELS];
+  __shared__ int s_cols[PAGK_MAX_LEVELS], s_rows[PAGK_MAX_LEVELS], s_pitch[PAGK_MAX_LEVELS];
   __shared__ unsigned int s_off[PAGK_MAX_LEVELS];
   // the two work counters of a handle alternate between launches: this launch zeroes the one the next launch uses
   if (blockIdx.x == 0 && threadIdx.x == 0) *next_counter = 0;
   if (threadIdx.x < PAGK_MAX_LEVELS) {
-    s_cols[threadIdx.x] = g.lv[threadIdx.x].cols; s_rows[threadIdx.x] = g.lv[threadIdx.x].rows; s_off[threadIdx.x] = g.lv[threadIdx.x].offset;
+    s_cols[threadIdx.x] = g.lv[threadIdx.x].cols; s_rows[threadIdx.x] = g.lv[threadIdx.x].rows;
+    s_pitch[threadIdx.x] = g.lv[threadIdx.x].pitch; s_off[threadIdx.x] = g.lv[threadIdx.x].offset;
+  }
+  if (lane == 0) {
+    mbar_init(mbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  unsigned int tphase = 0;  // parity of the warp's mbarrier phase the next wait looks at
 
   // accumulator role of this lane in the cooperative pass: acc += A * B with A in {Ix, Iy, c, 1} and B in
   // {Ix, Iy, -e, c}; lanes 0..11 = h00 h10 h11 h20 h21 h22 h30 h31 b0 b1 b2 b3.  An operand is a float in the
@@ -225,20 +344,14 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
   const int role = lane < 12 ? lane : 0;
   const int selA = (int)((0x431044333110ull >> (4 * role)) & 0xfull);  // 0 Ix, 1 Iy, 3 c, 4 one
   const int selB = (int)((0x222210310100ull >> (4 * role)) & 0xfull);  // 0 Ix, 1 Iy, 2 -e, 3 c
-  const int offA = selA < 3 ? selA : NP * 3 + (selA - 3), strideA = selA < 3 ? 3 : 0;
-  const int offB = selB < 3 ? selB : NP * 3 + (selB - 3), strideB = selB < 3 ? 3 : 0;
-
-  // pixel offsets of this lane in the cooperative (lanes = pixels) template pass
-  float tpx[(NP + 31) / 32], tpy[(NP + 31) / 32];
-#pragma unroll
-  for (int k = 0; k < (NP + 31) / 32; ++k) {
-    const int p = lane + 32 * k, py = p / P;
-    tpx[k] = (float)(p - py * P - HALF); tpy[k] = (float)(py - HALF);
-  }
+  const int offA = selA < 3 ? selA : 32 * 3 + (selA - 3), strideA = selA < 3 ? 3 : 0;
+  const int offB = selB < 3 ? selB : 32 * 3 + (selB - 3), strideB = selB < 3 ? 3 : 0;
 
   // ---- slot state (registers of the owning lane) ----
   int feat = -1, pair = 0, level = 0, iter = 0, n_iter = 0, succ = 1;
   float pt1x = 0.f, pt1y = 0.f, ptx = 0.f, pty = 0.f, dx = 0.f, dy = 0.f, dg = 0.f, db = 0.f, lastCost = 0.f, cval = 0.f;
+  float tlast = 0.f;   // T[NP - 1]
+  double h22v = 0.0;   // the level's sum of c*c
   float a00 = 1.f, a01 = 0.f, a10 = 0.f, a11 = 1.f;
   float wxmin = -hf, wxmax = hf, wymin = -hf, wymax = hf;
   int win_x0 = 0, win_y0 = 0;
@@ -315,6 +428,29 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
         }
       }
     }
+    // ------------------------------------------------------------------ template of a level that starts: one bulk copy
+    // (UBLKCP) per lane from its record, the record's tail by a vector load.  The template does not depend on the level
+    // above, so a lane that still waits for its hand-over issues it as well.
+    bool tpend = false;  // warp-uniform
+    {
+      const bool iss = feat >= 0 && needs_setup;
+      const unsigned mi = __ballot_sync(FULL, iss);
+      if (mi) {
+        // the slots' T areas were last read through the generic proxy; the copy engine writes them through the async one
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (lane == 0) mbar_expect_tx(mbar, (unsigned int)C::T_BULK * (unsigned int)__popc(mi));
+        __syncwarp();
+        if (iss) {
+          const unsigned char *rec = tmpl + ((size_t)feat * (size_t)mode.levels + (size_t)level) * C::REC_BYTES;
+          bulk_copy_g2s(smem_u32(myT), rec, C::T_BULK, mbar);
+          const float4 tl = __ldg(reinterpret_cast<const float4 *>(rec + C::T_BULK));
+          tlast = tl.x; cval = tl.y;
+          h22v = __hiloint2double(__float_as_int(tl.w), __float_as_int(tl.z));
+          needs_setup = false; win_valid = false;
+        }
+        tpend = true;
+      }
+    }
     if (split) {
       // a claimed level starts once the level above it has published its result.  The owner of that level is a
       // running lane of this launch (items are claimed in queue order), so polling once per round cannot deadlock.
@@ -328,26 +464,26 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
           waiting = false;
         }
       }
-      if (__ballot_sync(FULL, feat >= 0 && !waiting) == 0u && __ballot_sync(FULL, waiting) != 0u) {
-        __nanosleep(200);
-        continue;
-      }
     }
     const bool active = feat >= 0 && !waiting;
     const unsigned m_active = __ballot_sync(FULL, active);
-    if (m_active == 0u) break;
+    if (m_active == 0u) {
+      // nothing to run this round: finish the copies in flight (a waiting lane's template), then poll again or leave
+      if (tpend) { mbar_wait(mbar, tphase); tphase ^= 1u; }
+      if (__ballot_sync(FULL, waiting) != 0u) { __nanosleep(200); continue; }
+      break;
+    }
     PROF(0); PROF_ADD(6, 1); PROF_ADD(7, __popc(m_active));
 
-    const int cols = s_cols[level], rows = s_rows[level];
-    const unsigned char *I1 = images + (size_t)(pair * 2) * slot_bytes + s_off[level];
-    const unsigned char *I2 = I1 + slot_bytes;
+    const int cols = s_cols[level], rows = s_rows[level], pitch = s_pitch[level];
+    const unsigned char *I2 = images + (size_t)(pair * 2 + 1) * slot_bytes + s_off[level];
     const float fcols = (float)cols, frows = (float)rows, fcm1 = (float)(cols - 1), frm1 = (float)(rows - 1);
 
     // ------------------------------------------------------------------ sample box of this pass (lane = slot)
     // Extreme sample coordinates over the patch: the warp offsets are monotone in x and in y, so their extremes
     // sit at the corners; the +-1 of the gradient samples and every rounding are monotone too.  `inside`: no
     // clamp of GetPixelValue can fire for any sample.  The box of the CLAMPED coordinates is what a window has to
-    // hold (stage_window keeps the wrap column and the guard row), so border slots are windowable as well.
+    // hold (a level keeps its wrap column and its guard row), so border slots are windowable as well.
     const float bx = ptx + dx, by = pty + dy;
     bool windowable = false, fast = false, restage = false;
     int nx0 = 0, ny0 = 0;
@@ -360,112 +496,46 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
         const int ixlo = (int)fminf(fmaxf(x2min, 0.0f), fcm1), ixhi = (int)fminf(fmaxf(x1max, 0.0f), fcm1) + 1;
         const int iylo = (int)fminf(fmaxf(y2min, 0.0f), frm1), iyhi = (int)fminf(fmaxf(y1max, 0.0f), frm1) + 1;
         const int needw = ixhi - ixlo + 1, needh = iyhi - iylo + 1;
-        if (needw <= WIN_W && needh <= WIN_H) {
+        // the window's origin is a multiple of four columns: any box up to WIN_W - 3 wide fits
+        if (needw <= WIN_W - 3 && needh <= WIN_H) {
           windowable = true;
           fast = inside;
-          const bool ok = win_valid && !needs_setup && ixlo >= win_x0 && ixhi <= win_x0 + WIN_W - 1 && iylo >= win_y0 && iyhi <= win_y0 + WIN_H - 1;
-          if (!ok) {  // (re)stage, centred on the needed box
+          const bool ok = win_valid && ixlo >= win_x0 && ixhi <= win_x0 + WIN_W - 1 && iylo >= win_y0 && iyhi <= win_y0 + WIN_H - 1;
+          if (!ok) {  // (re)stage, centred on the needed box: 0 <= x0 <= ixlo, x0 + WIN_W - 1 >= ixhi, the same in y;
+                      // the rows of a level are followed by at least 32 - rows allocated rows and 64 bytes
             restage = true;
-            nx0 = ixlo - (WIN_W - needw) / 2;
-            ny0 = iylo - (WIN_H - needh) / 2;
+            nx0 = max((ixlo - (WIN_W - 3 - needw) / 2) & ~3, 0);
+            ny0 = max(min(iylo - (WIN_H - needh) / 2, rows + 1 - WIN_H), 0);
           }
         }
       }
     }
 
-    // ------------------------------------------------------------------ setup of a level (cooperative)
-    {
-      unsigned m = __ballot_sync(FULL, active && needs_setup);
-      while (m) {
-        const int s = __ffs(m) - 1;
-        m &= m - 1;
-        const float sptx = __shfl_sync(FULL, ptx, s), spty = __shfl_sync(FULL, pty, s);
-        const int scols = __shfl_sync(FULL, cols, s), srows = __shfl_sync(FULL, rows, s);
-        const unsigned char *img1 = reinterpret_cast<const unsigned char *>(__shfl_sync(FULL, (unsigned long long)I1, s));
-        const int rs = __shfl_sync(FULL, (int)restage, s), rx0 = __shfl_sync(FULL, nx0, s), ry0 = __shfl_sync(FULL, ny0, s);
-        unsigned char *win = wwin + s * C::WIN_BYTES;
-        float *T = wT + s * NP;
-        const float txlo = sptx + (-hf), txhi = sptx + hf, tylo = spty + (-hf), tyhi = spty + hf;
-        const bool tin = txlo >= 0.0f && txhi < (float)scols && tylo >= 0.0f && tyhi < (float)srows;
-        unsigned char v2[WIN_H];
-        constexpr int TK = (NP + 31) / 32;
-        if (tin) {
-          // No clamp fires anywhere in the template: lanes = pixels, the four taps of each pixel straight from the
-          // level (L1), all of them and the current-image window's loads in flight together -- one global round
-          // trip per level and no staging of the reference window.
-          unsigned char t00[TK], t10[TK], t01[TK], t11[TK];
-          float wxx[TK], wyy[TK];
-#pragma unroll
-          for (int k = 0; k < TK; ++k) {
-            const int p = lane + 32 * k;
-            const float cx = sptx + tpx[k], cy = spty + tpy[k];
-            // 2^23 + floor(.) by a round-down add, as in the pass
-            const float tx = __fadd_rd(cx, 8388608.0f), ty = __fadd_rd(cy, 8388608.0f);
-            wxx[k] = cx - (tx - 8388608.0f); wyy[k] = cy - (ty - 8388608.0f);
-            const int ix = __float_as_int(tx) - 0x4B000000, iy = __float_as_int(ty) - 0x4B000000;
-            t00[k] = t10[k] = t01[k] = t11[k] = 0;
-            if (p < NP) {
-              const unsigned char *q = img1 + iy * scols + ix;
-              t00[k] = __ldg(q); t10[k] = __ldg(q + 1); t01[k] = __ldg(q + scols); t11[k] = __ldg(q + scols + 1);
-            }
-          }
-          if (rs) load_window<WIN_W, WIN_H>(v2, img1 + slot_bytes, scols, srows, rx0, ry0, lane);
-          PROF_SUB(1);
-#ifdef PAGK_PROF_SETUP
-          { unsigned int sink = t00[0] + t11[TK - 2] + v2[0] + v2[WIN_H - 1]; asm volatile("" ::"r"(sink)); }
-          PROF_SUB(2);
-#endif
-#pragma unroll
-          for (int k = 0; k < TK; ++k) {
-            const int p = lane + 32 * k;
-            const float xx = wxx[k], yy = wyy[k], wa = 1.0f - xx, wb = 1.0f - yy;
-            if (p < NP) T[p] = wb * (wa * u8f(t00[k]) + xx * u8f(t10[k])) + yy * (wa * u8f(t01[k]) + xx * u8f(t11[k]));
-          }
-        } else {
-          if (rs) load_window<WIN_W, WIN_H>(v2, img1 + slot_bytes, scols, srows, rx0, ry0, lane);
-#pragma unroll 1
-          for (int p = lane; p < NP; p += 32) {
-            const int py = p / P, px = p - py * P;
-            T[p] = pagk_sample_call(img1, scols, srows, sptx + (float)(px - HALF), spty + (float)(py - HALF));
-          }
-        }
-        if (rs) store_window<WIN_W, WIN_H>(win, v2, lane);
-        __syncwarp();
-        PROF_SUB(4);
-        if (lane == s) {
-          // de_dg = -I1(pt) (src/patch_match.cpp:263) is minus the template value of the centre pixel: pt + (0, 0)
-          cval = -T[NP / 2]; needs_setup = false; win_valid = false;
-          if (rs) { win_x0 = nx0; win_y0 = ny0; win_valid = true; restage = false; }
-        }
-        __syncwarp();
-      }
-    }
-    PROF(1);
-    // ------------------------------------------------------------------ window of the current level (cooperative)
+    // ------------------------------------------------------------------ window of the current level: LDGSTS, lanes = words
     {
       unsigned m = __ballot_sync(FULL, restage);
       while (m) {
         const int s = __ffs(m) - 1;
         m &= m - 1;
-        const int x0 = __shfl_sync(FULL, nx0, s), y0 = __shfl_sync(FULL, ny0, s);
-        const int scols = __shfl_sync(FULL, cols, s), srows = __shfl_sync(FULL, rows, s);
-        const unsigned char *img2 = reinterpret_cast<const unsigned char *>(__shfl_sync(FULL, (unsigned long long)I2, s));
-        unsigned char v[WIN_H];
-        load_window<WIN_W, WIN_H>(v, img2, scols, srows, x0, y0, lane);
-        __syncwarp();
-        store_window<WIN_W, WIN_H>(wwin + s * C::WIN_BYTES, v, lane);
+        const int x0 = __shfl_sync(FULL, nx0, s), y0 = __shfl_sync(FULL, ny0, s), sp = __shfl_sync(FULL, pitch, s);
+        const unsigned char *src = reinterpret_cast<const unsigned char *>(__shfl_sync(FULL, (unsigned long long)I2, s)) + y0 * sp + x0;
+        const unsigned int dst = smem_u32(wwin + s * C::WIN_STRIDE);
+#pragma unroll
+        for (int k = 0; k < (C::WIN_WORDS + 31) / 32; ++k) {
+          const int e = lane + 32 * k, r = e / C::WPR, w = e - r * C::WPR;
+          if (e < C::WIN_WORDS) cp_async4(dst + 4u * (unsigned int)e, src + r * sp + 4 * w);
+        }
       }
       if (restage) { win_x0 = nx0; win_y0 = ny0; win_valid = true; }
-      __syncwarp();
     }
-#ifdef PAGK_PROF_SETUP
-    PROF(3);
-#else
-    PROF(2);
-#endif
+    // one wait for every copy of the round
+    cp_async_wait_all();
+    if (tpend) { mbar_wait(mbar, tphase); tphase ^= 1u; }
+    __syncwarp();
+    PROF(1);
 
     Sums S;
-    S.h00 = S.h10 = S.h11 = S.h20 = S.h21 = S.h22 = S.h30 = S.h31 = S.b0 = S.b1 = S.b2 = S.b3 = 0.0;
+    S.h00 = S.h10 = S.h11 = S.h20 = S.h21 = S.h30 = S.h31 = S.b0 = S.b1 = S.b2 = S.b3 = 0.0;
     S.cost = 0.f;
     const double c = (double)cval;
     const float gain = 1.0f + dg;
@@ -489,56 +559,67 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
       // window element index from the mantissas of ty = 2^23 + floor(sy) and tx = 2^23 + floor(sx):
       // bits(ty) * WIN_W + bits(tx) - kk, with kk = (WIN_W + 1) * bits(2^23) + origin (mod 2^32)
       const unsigned int kk = (unsigned int)(WIN_W + 1) * 0x4B000000u + (unsigned int)(fast ? win_y0 * WIN_W + win_x0 : 0);
-      // one flat loop over the P * P pixels (row-major, the reference's order): a single peeled pixel per pass
-      // instead of one per row, and the scheduler always has PAGK_LANES_UNROLL pixels to interleave
+      // one flat walk over the P * P pixels (row-major, the reference's order), PAGK_LANES_UNROLL pixels per trip with
+      // their template values in one vector load; the last pixel's template value is a register
       float xf = -(float)HALF, yf = -(float)HALF;
-      PAGK_UNROLL(PAGK_LANES_UNROLL)
-      for (int p = 0; p < NP; ++p) {
+      auto pixel = [&](const float tval) {
+        float wx = xf, wy = yf;
+        if (AFFINE) { wx = q00 * xf + q01 * yf; wy = q10 * xf + q11 * yf; }
         {
-          float wx = xf, wy = yf;
-          if (AFFINE) { wx = q00 * xf + q01 * yf; wy = q10 * xf + q11 * yf; }
-          {
-            const bool wrap = xf >= (float)HALF;  // next pixel: x + 1, or the start of the next row
-            const float nxf = xf + 1.0f;
-            yf = wrap ? yf + 1.0f : yf;
-            xf = wrap ? -(float)HALF : nxf;
-          }
-          const float sx = pbx + wx, sy = pby + wy;
-          // floor for 0 <= x < 2^22: x + 2^23 rounded DOWN is 2^23 + floor(x) exactly; taking 2^23 off is exact
-          const float tx = __fadd_rd(sx, 8388608.0f), ty = __fadd_rd(sy, 8388608.0f);
-          const float fx = tx - 8388608.0f, fy = ty - 8388608.0f;
-          const float xx = sx - fx, yy = sy - fy;
-          const float wa = 1.0f - xx, wb = 1.0f - yy;
-          const float X1 = sx + 1.0f, Y1 = sy + 1.0f;
-          const float xx1 = X1 - (fx + 1.0f), yy1 = Y1 - (fy + 1.0f);
-          const float wa1 = 1.0f - xx1, wb1 = 1.0f - yy1;
-          badv = fmaxf(badv, fmaxf(xx1, yy1));
-          const int widx = (int)((unsigned int)__float_as_int(ty) * (unsigned int)WIN_W + (unsigned int)__float_as_int(tx) - kk);
-          CHECK_IDX(widx, WIN_W + 1, WIN_W * WIN_H - 2 * WIN_W - 2);
-          const unsigned char *w = mywin + widx;
-          const float m0 = u8f(w[-WIN_W]), m1 = u8f(w[-WIN_W + 1]);
-          const float c_1 = u8f(w[-1]), c0 = u8f(w[0]), c1 = u8f(w[1]), c2 = u8f(w[2]);
-          const float d_1 = u8f(w[WIN_W - 1]), d0 = u8f(w[WIN_W]), d1 = u8f(w[WIN_W + 1]), d2 = u8f(w[WIN_W + 2]);
-          const float n0 = u8f(w[2 * WIN_W]), n1 = u8f(w[2 * WIN_W + 1]);
-          const float Hm = wa * m0 + xx * m1;
-          const float H0 = wa * c0 + xx * c1, H0p = wa1 * c1 + xx1 * c2, H0m = wa * c_1 + xx * c0;
-          const float H1 = wa * d0 + xx * d1, H1p = wa1 * d1 + xx1 * d2, H1m = wa * d_1 + xx * d0;
-          const float H2 = wa * n0 + xx * n1;
-          const float v0 = wb * H0 + yy * H1;
-          const float vx1 = wb * H0p + yy * H1p, vx2 = wb * H0m + yy * H1m;
-          const float vy1 = wb1 * H1 + yy1 * H2, vy2 = wb * Hm + yy * H0;
-          const float e = (v0 + db) - gain * myT[p];
-          const float gxf = 0.5f * (vx1 - vx2), gyf = 0.5f * (vy1 - vy2), mf = -e;
-          // J = (Ix, Iy, c, 1) as double; b += -J * e; H += J * J^T; cost += e * e (float), reference :264-299.
-          // Each product of two float-valued doubles is exact, so DFMA rounds like the separate mul + add.
-          const double x = (double)gxf, y = (double)gyf, mm = (double)mf;
-          S.h00 = fma(x, x, S.h00); S.h10 = fma(y, x, S.h10); S.h11 = fma(y, y, S.h11);
-          S.h20 = fma(c, x, S.h20); S.h21 = fma(c, y, S.h21); S.h22 = fma(c, c, S.h22);
-          S.h30 = S.h30 + x; S.h31 = S.h31 + y;
-          S.b0 = fma(x, mm, S.b0); S.b1 = fma(y, mm, S.b1); S.b2 = fma(c, mm, S.b2); S.b3 = S.b3 + mm;
-          S.cost = S.cost + mf * mf;
+          const bool wrap = xf >= (float)HALF;  // next pixel: x + 1, or the start of the next row
+          const float nxf = xf + 1.0f;
+          yf = wrap ? yf + 1.0f : yf;
+          xf = wrap ? -(float)HALF : nxf;
+        }
+        const float sx = pbx + wx, sy = pby + wy;
+        // floor for 0 <= x < 2^22: x + 2^23 rounded DOWN is 2^23 + floor(x) exactly; taking 2^23 off is exact
+        const float tx = __fadd_rd(sx, 8388608.0f), ty = __fadd_rd(sy, 8388608.0f);
+        const float fx = tx - 8388608.0f, fy = ty - 8388608.0f;
+        const float xx = sx - fx, yy = sy - fy;
+        const float wa = 1.0f - xx, wb = 1.0f - yy;
+        const float X1 = sx + 1.0f, Y1 = sy + 1.0f;
+        const float xx1 = X1 - (fx + 1.0f), yy1 = Y1 - (fy + 1.0f);
+        const float wa1 = 1.0f - xx1, wb1 = 1.0f - yy1;
+        badv = fmaxf(badv, fmaxf(xx1, yy1));
+        const int widx = (int)((unsigned int)__float_as_int(ty) * (unsigned int)WIN_W + (unsigned int)__float_as_int(tx) - kk);
+        CHECK_IDX(widx, WIN_W + 1, WIN_W * WIN_H - 2 * WIN_W - 3);
+        const unsigned char *w = mywin + widx;
+        const float m0 = u8f(w[-WIN_W]), m1 = u8f(w[-WIN_W + 1]);
+        const float c_1 = u8f(w[-1]), c0 = u8f(w[0]), c1 = u8f(w[1]), c2 = u8f(w[2]);
+        const float d_1 = u8f(w[WIN_W - 1]), d0 = u8f(w[WIN_W]), d1 = u8f(w[WIN_W + 1]), d2 = u8f(w[WIN_W + 2]);
+        const float n0 = u8f(w[2 * WIN_W]), n1 = u8f(w[2 * WIN_W + 1]);
+        const float Hm = wa * m0 + xx * m1;
+        const float H0 = wa * c0 + xx * c1, H0p = wa1 * c1 + xx1 * c2, H0m = wa * c_1 + xx * c0;
+        const float H1 = wa * d0 + xx * d1, H1p = wa1 * d1 + xx1 * d2, H1m = wa * d_1 + xx * d0;
+        const float H2 = wa * n0 + xx * n1;
+        const float v0 = wb * H0 + yy * H1;
+        const float vx1 = wb * H0p + yy * H1p, vx2 = wb * H0m + yy * H1m;
+        const float vy1 = wb1 * H1 + yy1 * H2, vy2 = wb * Hm + yy * H0;
+        const float e = (v0 + db) - gain * tval;
+        const float gxf = 0.5f * (vx1 - vx2), gyf = 0.5f * (vy1 - vy2), mf = -e;
+        // J = (Ix, Iy, c, 1) as double; b += -J * e; H += J * J^T; cost += e * e (float), reference :264-299.
+        // Each product of two float-valued doubles is exact, so DFMA rounds like the separate mul + add.
+        // (H[2][2] = sum of c*c does not depend on the samples: it comes with the template record.)
+        const double x = (double)gxf, y = (double)gyf, mm = (double)mf;
+        S.h00 = fma(x, x, S.h00); S.h10 = fma(y, x, S.h10); S.h11 = fma(y, y, S.h11);
+        S.h20 = fma(c, x, S.h20); S.h21 = fma(c, y, S.h21);
+        S.h30 = S.h30 + x; S.h31 = S.h31 + y;
+        S.b0 = fma(x, mm, S.b0); S.b1 = fma(y, mm, S.b1); S.b2 = fma(c, mm, S.b2); S.b3 = S.b3 + mm;
+        S.cost = S.cost + mf * mf;
+      };
+      constexpr int V = PAGK_LANES_UNROLL;
+      static_assert((NP - 1) % V == 0 && (V == 4 || V == 2), "vector width of the template loads");
+#pragma unroll 1
+      for (int j = 0; j < (NP - 1) / V; ++j) {
+        if (V == 4) {
+          const float4 t4 = reinterpret_cast<const float4 *>(myT)[j];
+          pixel(t4.x); pixel(t4.y); pixel(t4.z); pixel(t4.w);
+        } else {
+          const float2 t2 = reinterpret_cast<const float2 *>(myT)[j];
+          pixel(t2.x); pixel(t2.y);
         }
       }
+      pixel(tlast);
       coop |= active && fast && (badv >= 1.0f);
     }
     PROF(3);
@@ -556,74 +637,76 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
         const float sbx = __shfl_sync(FULL, bx, s), sby = __shfl_sync(FULL, by, s);
         const float s00 = __shfl_sync(FULL, a00, s), s01 = __shfl_sync(FULL, a01, s), s10 = __shfl_sync(FULL, a10, s), s11 = __shfl_sync(FULL, a11, s);
         const float sdb = __shfl_sync(FULL, db, s), sgain = __shfl_sync(FULL, gain, s), scv = __shfl_sync(FULL, cval, s);
-        const int scols = __shfl_sync(FULL, cols, s), srows = __shfl_sync(FULL, rows, s);
+        const float stl = __shfl_sync(FULL, tlast, s);
+        const int scols = __shfl_sync(FULL, cols, s), srows = __shfl_sync(FULL, rows, s), sp = __shfl_sync(FULL, pitch, s);
         const int swx0 = __shfl_sync(FULL, win_x0, s), swy0 = __shfl_sync(FULL, win_y0, s);
         const int swin = __shfl_sync(FULL, (int)windowable, s);
         const unsigned char *img2 = reinterpret_cast<const unsigned char *>(__shfl_sync(FULL, (unsigned long long)I2, s));
-        const unsigned char *win = wwin + s * C::WIN_BYTES;
-        const float *T = wT + s * NP;
+        const unsigned char *win = wwin + s * C::WIN_STRIDE;
+        const float *T = reinterpret_cast<const float *>(wbase + C::t_off(s));
         const float gc = (float)scols, gr = (float)srows, gc1 = (float)(scols - 1), gr1 = (float)(srows - 1);
-        __syncwarp();
-#pragma unroll 1
-        for (int p = lane; p < NP; p += 32) {
-          const int py = p / P, px = p - py * P;
-          const float xf = (float)(px - HALF), yf = (float)(py - HALF);
-          float wx = xf, wy = yf;
-          if (AFFINE) { wx = s00 * xf + s01 * yf; wy = s10 * xf + s11 * yf; }
-          const float sx = sbx + wx, sy = sby + wy;
-          float v0, vx1, vx2, vy1, vy2;
-          if (swin) {
-            v0 = window_sample<WIN_W>(win, swx0, swy0, gc, gc1, gr, gr1, sx, sy);
-            vx1 = window_sample<WIN_W>(win, swx0, swy0, gc, gc1, gr, gr1, sx + 1.0f, sy);
-            vx2 = window_sample<WIN_W>(win, swx0, swy0, gc, gc1, gr, gr1, sx - 1.0f, sy);
-            vy1 = window_sample<WIN_W>(win, swx0, swy0, gc, gc1, gr, gr1, sx, sy + 1.0f);
-            vy2 = window_sample<WIN_W>(win, swx0, swy0, gc, gc1, gr, gr1, sx, sy - 1.0f);
-          } else {
-            v0 = pagk_sample_call(img2, scols, srows, sx, sy);
-            vx1 = pagk_sample_call(img2, scols, srows, sx + 1.0f, sy);
-            vx2 = pagk_sample_call(img2, scols, srows, sx - 1.0f, sy);
-            vy1 = pagk_sample_call(img2, scols, srows, sx, sy + 1.0f);
-            vy2 = pagk_sample_call(img2, scols, srows, sx, sy - 1.0f);
-          }
-          const float e = (v0 + sdb) - sgain * T[p];
-          scratch[3 * p] = 0.5f * (vx1 - vx2);
-          scratch[3 * p + 1] = 0.5f * (vy1 - vy2);
-          scratch[3 * p + 2] = -e;
-        }
-        if (lane == 0) { scratch[NP * 3] = scv; scratch[NP * 3 + 1] = 1.0f; }
-        __syncwarp();
         double acc = 0.0;
         float cacc = 0.f;
-        {
+        __syncwarp();
+        if (lane == 0) { scratch[32 * 3] = scv; scratch[32 * 3 + 1] = 1.0f; }
+        // the patch in chunks of 32 pixels: records into the scratch, then every accumulator walks the chunk in order
+#pragma unroll 1
+        for (int p0 = 0; p0 < NP; p0 += 32) {
+          const int p = p0 + lane;
+          if (p < NP) {
+            const int py = p / P, px = p - py * P;
+            const float xf = (float)(px - HALF), yf = (float)(py - HALF);
+            float wx = xf, wy = yf;
+            if (AFFINE) { wx = s00 * xf + s01 * yf; wy = s10 * xf + s11 * yf; }
+            const float sx = sbx + wx, sy = sby + wy;
+            float v0, vx1, vx2, vy1, vy2;
+            if (swin) {
+              v0 = window_sample<WIN_W, WIN_H>(win, swx0, swy0, gc, gc1, gr, gr1, sx, sy);
+              vx1 = window_sample<WIN_W, WIN_H>(win, swx0, swy0, gc, gc1, gr, gr1, sx + 1.0f, sy);
+              vx2 = window_sample<WIN_W, WIN_H>(win, swx0, swy0, gc, gc1, gr, gr1, sx - 1.0f, sy);
+              vy1 = window_sample<WIN_W, WIN_H>(win, swx0, swy0, gc, gc1, gr, gr1, sx, sy + 1.0f);
+              vy2 = window_sample<WIN_W, WIN_H>(win, swx0, swy0, gc, gc1, gr, gr1, sx, sy - 1.0f);
+            } else {
+              v0 = pagk_sample_call(img2, sp, scols, srows, sx, sy);
+              vx1 = pagk_sample_call(img2, sp, scols, srows, sx + 1.0f, sy);
+              vx2 = pagk_sample_call(img2, sp, scols, srows, sx - 1.0f, sy);
+              vy1 = pagk_sample_call(img2, sp, scols, srows, sx, sy + 1.0f);
+              vy2 = pagk_sample_call(img2, sp, scols, srows, sx, sy - 1.0f);
+            }
+            const float tval = p < NP - 1 ? T[p] : stl;
+            const float e = (v0 + sdb) - sgain * tval;
+            scratch[3 * lane] = 0.5f * (vx1 - vx2);
+            scratch[3 * lane + 1] = 0.5f * (vy1 - vy2);
+            scratch[3 * lane + 2] = -e;
+          }
+          __syncwarp();
+          const int n = min(32, NP - p0);
           const float *pa = scratch + offA, *pb = scratch + offB, *pm = scratch + 2;
 #pragma unroll 4
-          for (int p = 0; p < NP; ++p) {
+          for (int q = 0; q < n; ++q) {
             const float fa = *pa, fb = *pb, fm = *pm;
             pa += strideA; pb += strideB; pm += 3;
             acc = fma((double)fa, (double)fb, acc);
             cacc = cacc + fm * fm;
           }
+          __syncwarp();
         }
         const double t0 = __shfl_sync(FULL, acc, 0), t1 = __shfl_sync(FULL, acc, 1), t2 = __shfl_sync(FULL, acc, 2),
-                     t3 = __shfl_sync(FULL, acc, 3), t4 = __shfl_sync(FULL, acc, 4), t5 = __shfl_sync(FULL, acc, 5),
-                     t6 = __shfl_sync(FULL, acc, 6), t7 = __shfl_sync(FULL, acc, 7), t8 = __shfl_sync(FULL, acc, 8),
-                     t9 = __shfl_sync(FULL, acc, 9), t10 = __shfl_sync(FULL, acc, 10), t11 = __shfl_sync(FULL, acc, 11);
+                     t3 = __shfl_sync(FULL, acc, 3), t4 = __shfl_sync(FULL, acc, 4), t6 = __shfl_sync(FULL, acc, 6),
+                     t7 = __shfl_sync(FULL, acc, 7), t8 = __shfl_sync(FULL, acc, 8), t9 = __shfl_sync(FULL, acc, 9),
+                     t10 = __shfl_sync(FULL, acc, 10), t11 = __shfl_sync(FULL, acc, 11);
         if (lane == s) {
-          S.h00 = t0; S.h10 = t1; S.h11 = t2; S.h20 = t3; S.h21 = t4; S.h22 = t5; S.h30 = t6; S.h31 = t7;
+          S.h00 = t0; S.h10 = t1; S.h11 = t2; S.h20 = t3; S.h21 = t4; S.h30 = t6; S.h31 = t7;
           S.b0 = t8; S.b1 = t9; S.b2 = t10; S.b3 = t11; S.cost = cacc;
         }
       }
       __syncwarp();
     }
-#ifdef PAGK_PROF_SETUP
-    PROF(5);
-#else
     PROF(4);
-#endif
 
     // ------------------------------------------------------------------ solve, update, exits (lane = slot)
     if (active) {
-      double h00 = S.h00, h10 = S.h10, h11 = S.h11, h20 = S.h20, h21 = S.h21, h22 = S.h22, h30 = S.h30, h31 = S.h31;
+      double h00 = S.h00, h10 = S.h10, h11 = S.h11, h20 = S.h20, h21 = S.h21, h22 = h22v, h30 = S.h30, h31 = S.h31;
       double h32 = c * (double)NP, h33 = (double)NP;  // sum of c and of 1 over the patch: exact in double
       double b0 = S.b0, b1 = S.b1, b2 = S.b2, b3 = S.b3;
       float cost = S.cost;
@@ -695,20 +778,38 @@ bool pagk_lk_lanes_supported(const PagkMode &mode) {
   return (mode.half == 5 || mode.half == 10) && mode.iterations >= 1;
 }
 
+size_t pagk_lk_lanes_record_bytes(int half) {
+  return half == 5 ? (size_t)LanesCfg<5>::REC_BYTES : half == 10 ? (size_t)LanesCfg<10>::REC_BYTES : 0;
+}
+
+template <int HALF, bool AFFINE>
+static cudaError_t configure_lanes() {
+  return cudaFuncSetAttribute(pagk_lk_lanes_kernel<HALF, AFFINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, LanesCfg<HALF>::SMEM_BYTES);
+}
+
+// per device, from pagk_create after cudaSetDevice (a function attribute belongs to the device it was set on)
+int pagk_lk_lanes_configure() {
+  cudaError_t e = configure_lanes<5, true>();
+  if (e == cudaSuccess) e = configure_lanes<5, false>();
+  if (e == cudaSuccess) e = configure_lanes<10, true>();
+  if (e == cudaSuccess) e = configure_lanes<10, false>();
+  return (int)e;
+}
+
 template <int HALF, bool AFFINE>
 static int launch_lanes(const unsigned char *images, const PagkGeom &g, const PagkPairConst *pcs, const float2 *keys_un,
                         const PagkOutPtrs &out, const PagkMode &mode, int max_keys, int n_max, int n_pairs,
-                        int *work_counter, int *next_counter, int *progress, int epoch, int n_sms, cudaStream_t st,
-                        long long *prof) {
+                        int *work_counter, int *next_counter, int *progress, int epoch, int n_sms, unsigned char *tmpl,
+                        cudaStream_t st, long long *prof) {
   using C = LanesCfg<HALF>;
-  const size_t smem = (size_t)C::WARPS * C::WARP_BYTES;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(pagk_lk_lanes_kernel<HALF, AFFINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
-  }
   const long long total = (long long)n_max * n_pairs;
+  {  // K3a: 8 warps per CTA, 32 items per warp
+    const long long items = total * mode.levels, groups = (items + 31) / 32;
+    pagk_lk_template_kernel<HALF><<<(unsigned)((groups + 7) / 8), 256, 0, st>>>(images, g, pcs, keys_un, mode.levels, max_keys, n_max,
+                                                                               n_pairs, tmpl);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+  }
   long long ctas = (long long)n_sms * C::CTAS_SM;  // persistent: the SMs are filled once
   // A small batch is spread over all warps (lane_cap features per warp at a time) instead of filling a few: a warp
   // with a handful of live lanes runs them through the cooperative pass, several times faster per iteration
@@ -722,27 +823,27 @@ static int launch_lanes(const unsigned char *images, const PagkGeom &g, const Pa
   static const int forced = [] { const char *e = getenv("PAGK_LK_SPLIT"); return e ? atoi(e) : -1; }();
   int split = (progress != nullptr && mode.levels > 1 && total > warps * C::SLOTS) ? 1 : 0;
   if (forced >= 0 && progress != nullptr && mode.levels > 1) split = forced ? 1 : 0;
-  pagk_lk_lanes_kernel<HALF, AFFINE><<<(unsigned)ctas, C::WARPS * 32, smem, st>>>(images, g, pcs, keys_un, out, mode, max_keys,
-                                                                                  n_max, n_pairs, work_counter, next_counter, lane_cap,
-                                                                                  split, progress, epoch * 8, prof);
+  pagk_lk_lanes_kernel<HALF, AFFINE><<<(unsigned)ctas, C::WARPS * 32, C::SMEM_BYTES, st>>>(
+      images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, next_counter, lane_cap, split, progress, epoch * 8,
+      tmpl, prof);
   return (int)cudaGetLastError();
 }
 
 int pagk_launch_lk_lanes(const unsigned char *images, const PagkGeom &g, const PagkPairConst *pcs, const float2 *keys_un,
                          const PagkOutPtrs &out, const PagkMode &mode, int max_keys, int n_max, int n_pairs,
-                         int *work_counters, int parity, int *progress, int epoch, int n_sms, cudaStream_t st,
-                         long long *launches, long long *prof) {
+                         int *work_counters, int parity, int *progress, int epoch, int n_sms, unsigned char *tmpl,
+                         cudaStream_t st, long long *launches, long long *prof) {
   if (n_max <= 0 || n_pairs <= 0) return 0;
   // work_counters[0..1]: both zero when the handle is created; launch n uses [n & 1] and zeroes the other one
   int *work_counter = work_counters + (parity & 1), *next_counter = work_counters + ((parity + 1) & 1);
   int rc;
   if (mode.half == 5) {
-    rc = mode.affine ? launch_lanes<5, true>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, next_counter, progress, epoch, n_sms, st, prof)
-                     : launch_lanes<5, false>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, next_counter, progress, epoch, n_sms, st, prof);
+    rc = mode.affine ? launch_lanes<5, true>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, next_counter, progress, epoch, n_sms, tmpl, st, prof)
+                     : launch_lanes<5, false>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, next_counter, progress, epoch, n_sms, tmpl, st, prof);
   } else {
-    rc = mode.affine ? launch_lanes<10, true>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, next_counter, progress, epoch, n_sms, st, prof)
-                     : launch_lanes<10, false>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, next_counter, progress, epoch, n_sms, st, prof);
+    rc = mode.affine ? launch_lanes<10, true>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, next_counter, progress, epoch, n_sms, tmpl, st, prof)
+                     : launch_lanes<10, false>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, next_counter, progress, epoch, n_sms, tmpl, st, prof);
   }
-  ++*launches;
+  *launches += 2;
   return rc;
 }
