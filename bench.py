@@ -374,13 +374,36 @@ def main():
     ctxs[0].synchronize()
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    clocks = sampler.result()
-    launches = sum(c.launch_count() for c in ctxs) - launches0
+    clocks_serial = sampler.result()
     # device time of the dominant kernel: CUDA events around every LK launch of the timed region
     lk_n, lk_sum, lk_iters = 0, 0.0, 0.0
     for k, c in enumerate(ctxs):
         n_r, ms_sum = c.timing_read()
         lk_n += n_r; lk_sum += ms_sum; lk_iters += n_r * iters_per_step[k]
+    dt_serial = sharding.reduce_time_max(dt)
+    # ---- pipelined resident leg: the same steps, every resident batch on its own handle AND stream, so the kernels of
+    # consecutive steps overlap (the tail of one step's alignment kernel runs beside the head of the next step)
+    pctx = [new_ctx() for _ in range(N_ROTATE)]
+    for c, b in zip(pctx, batches):
+        c.upload(b["pairs"], prm)
+        c.set_stage_timing(False)
+    for k in range(max(3, args.warmup) + N_ROTATE):
+        pctx[k % N_ROTATE].run()
+    for c in pctx:
+        c.synchronize()
+    launches0 = sum(c.launch_count() for c in pctx)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        pctx[k % N_ROTATE].run()
+    for c in pctx:
+        c.synchronize()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    clocks = sampler.result()
+    launches = sum(c.launch_count() for c in pctx) - launches0
     dt_max = sharding.reduce_time_max(dt)
     total_iters = sum(iters_per_step[k % N_ROTATE] for k in range(args.steps))
     (all_iters,) = sharding.reduce_counts(total_iters)
@@ -497,8 +520,11 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
             "config": {"workload": workload_name(args.config, cfg, n_pairs),
                        "l2": f"{N_ROTATE} rotating resident batches per GPU ({(N_ROTATE * 2 * n_pairs * cfg['width'] * cfg['height'] * 4 // 3) >> 20} MiB of pyramids) > 126 MB L2",
-                       "timing": "wall clock around K back-to-back steps on one in-order stream, barrier + device synchronize on both sides, max over ranks; kernel ms from CUDA events around every LK launch of the timed region; stage_ms from one untimed run with per-stage events on"},
+                       "timing": f"wall clock around K back-to-back steps over {N_ROTATE} resident batches, each on its own handle and stream (consecutive steps overlap on the device), barrier + device synchronize on both sides, max over ranks; `serial` repeats the K steps on one in-order stream, and the kernel ms of `roofline` are CUDA events around every LK launch of that serial leg; stage_ms from one untimed run with per-stage events on"},
             "feature_iterations_per_sec": fi_per_s,
+            "serial": {"ms_per_step": 1e3 * dt_serial / args.steps, "value": world * args.steps * feats_per_step / dt_serial,
+                       "unit": "features/s", "clocks": clocks_serial,
+                       "note": "the same steps on ONE in-order stream (no overlap between steps): the leg the kernel events of `roofline` and `stage_ms` come from"},
             "stage_ms": stage_ms, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "features/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "results_ok": bool(e2e_ok),
@@ -507,7 +533,7 @@ def main():
     if e2e_stream is not None:
         line["e2e_stream"] = e2e_stream
     emit(line)
-    for c in (ctxs + ectx)[::-1]:   # borrowers of a shared stream before its owner
+    for c in (ctxs + pctx + ectx)[::-1]:   # borrowers of a shared stream before its owner
         c.close()
     if world > 1:
         dist.destroy_process_group()

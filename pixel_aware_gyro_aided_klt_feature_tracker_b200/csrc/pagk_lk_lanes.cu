@@ -47,20 +47,26 @@
 
 namespace {
 
-// warps per CTA and CTAs per SM: 8 warps (two per scheduler) fill the shared memory of an SM
-#ifndef PAGK_LANES_WARPS
-#define PAGK_LANES_WARPS 8
-#endif
-constexpr int LANES_WARPS_SM = 8;
-constexpr int LANES_WARPS = PAGK_LANES_WARPS;
 // a warp with at most this many live lanes runs them one by one through the cooperative pass (lanes = pixels,
-// then lanes = accumulators: about 2.2 k warp instructions per slot) instead of a lockstep pass (16 k)
+// then lanes = accumulators: about 2.2 k warp instructions per slot) instead of a lockstep pass (15 k)
 #ifndef PAGK_LANES_SPARSE
 #define PAGK_LANES_SPARSE 5
 #endif
-// pixels per trip of the pass loop = floats per vector load of T (4: LDS.128, 2: LDS.64)
+// pixels per trip of the pass loop = floats per vector load of T (4: LDG.128, 2: LDG.64)
 #ifndef PAGK_LANES_UNROLL
 #define PAGK_LANES_UNROLL 4
+#endif
+// warps per SM for 11 x 11 patches.  Twelve (three per scheduler, what the register file allows) win on batches of 128
+// pairs and more (lane occupancy 0.92, 14 % faster per pair than eight); on config B's 64 pairs a launch is only 16
+// rounds deep for 56 k lanes, the tail and the level hand-overs leave 28 % of the lanes idle, and eight warps are faster.
+// Eight warps also leave a third of the registers to the small kernels of the neighbouring steps (other streams).
+#ifndef PAGK_LANES_WARPS5
+#define PAGK_LANES_WARPS5 8
+#endif
+// warps per CTA: the warps of an SM as several small CTAs leave the SM one by one when the work runs out, and the
+// CTAs of the next launch (another stream) move in
+#ifndef PAGK_LANES_CTA_WARPS
+#define PAGK_LANES_CTA_WARPS 4
 #endif
 
 template <int HALF>
@@ -75,35 +81,24 @@ struct LanesCfg {
   static constexpr int WIN_WORDS = WPR * WIN_H;
   // bytes from one slot's window to the next: an ODD number of words, lane-private windows start in distinct banks
   static constexpr int WIN_STRIDE = (WIN_WORDS | 1) * 4;
-  // a template record in global memory: T[0 .. NP-2] (T_BULK bytes, what the bulk copy moves: a multiple of 16),
-  // then T[NP-1], c = -T[NP/2], and h22 = the ordered double sum of c*c over the patch
+  // a template record in global memory: T[0 .. NP-2] (T_BULK bytes, a multiple of 16: the pass reads it with 16-byte
+  // loads), then T[NP-1], c = -T[NP/2], and h22 = the ordered double sum of c*c over the patch
   static constexpr int T_BULK = (NP * 4) & ~15;
   static constexpr int REC_BYTES = T_BULK + 16;
-  static_assert(NP * 4 - T_BULK == 4, "exactly the last template value stays out of the bulk copy");
-  // slots per warp: all 32 lanes when eight warps' worth fits the SM; a 21 x 21 patch needs 2.7 KB per slot, and four
-  // warps (one per scheduler) of 20 slots then beat two warps of 32
-  static constexpr int SLOTS = HALF <= 5 ? 32 : 20;
-  // T of slot s sits at t_off(s): 16-byte aligned for the bulk copy.  T_BULK / 16 is even, so plain s * T_BULK would
-  // put lanes s and s + 4 of a quarter warp into the same 16-byte bank group when every lane reads its own T with one
-  // 16-byte load; slots 4..7 of every group of eight are therefore moved up by 16 bytes (and the next group starts
-  // 16 bytes later): eight consecutive lanes then hit eight different bank groups.
-  __host__ __device__ static constexpr int t_off(int s) { return (s >> 3) * (8 * T_BULK + 16) + (s & 7) * T_BULK + 16 * ((s >> 2) & 1); }
-  static_assert((T_BULK / 16) % 8 == 6, "the bank-group argument above is for T_BULK = 480 and 1760");
-  static constexpr int T_WARP_BYTES = t_off(SLOTS - 1) + T_BULK;
-  static constexpr int WARP_BYTES = T_WARP_BYTES + SLOTS * WIN_STRIDE;
-  static_assert(WARP_BYTES % 16 == 0 && T_WARP_BYTES % 16 == 0, "bulk copies need 16-byte aligned destinations");
+  static_assert(NP * 4 - T_BULK == 4, "exactly the last template value sits in the record's tail");
+  // Shared memory holds the windows only (the template is streamed from its record), so the warps per SM are bound
+  // by the register file: 12 warps of 32 slots for 11 x 11; a 21 x 21 window is 972 bytes: 8 warps of 28 slots
+  static constexpr int SLOTS = HALF <= 5 ? 32 : 28;
+  static constexpr int WARPS_SM = HALF <= 5 ? PAGK_LANES_WARPS5 : 8;
+  static constexpr int WARPS = WARPS_SM % PAGK_LANES_CTA_WARPS == 0 ? PAGK_LANES_CTA_WARPS : WARPS_SM;  // per CTA
+  static constexpr int CTAS_SM = WARPS_SM / WARPS;
   // per-warp scratch of the cooperative pass: 32 records (Ix, Iy, -e) -- one chunk of the patch -- and the two
   // constants c and 1
   static constexpr int SCRATCH_FLOATS = 32 * 3 + 4;
-  static constexpr int TAIL_BYTES = LANES_WARPS_SM * (SCRATCH_FLOATS * 4 + 8);  // + one mbarrier per warp
-  static constexpr int SMEM_MAX = 227 * 1024 - 256;  // the static shared arrays of the kernel
-  static constexpr int WARPS_FIT = (SMEM_MAX - TAIL_BYTES) / WARP_BYTES;
-  static constexpr int WARPS_SM = WARPS_FIT < LANES_WARPS_SM ? WARPS_FIT : LANES_WARPS_SM;
-  static constexpr int WARPS = WARPS_SM < LANES_WARPS ? WARPS_SM : LANES_WARPS;
-  static constexpr int CTAS_SM = WARPS_SM / WARPS;
-  static constexpr int SMEM_BYTES = WARPS * WARP_BYTES + TAIL_BYTES;
+  static constexpr int WARP_BYTES = SLOTS * WIN_STRIDE + SCRATCH_FLOATS * 4;
+  static constexpr int SMEM_BYTES = WARPS * WARP_BYTES;
   static_assert(WIN_W % 4 == 0 && WIN_W - 3 >= P + 4, "window narrower than a sample box");
-  static_assert(WARPS >= 1, "patch too large for the lane kernel");
+  static_assert(CTAS_SM * (SMEM_BYTES + 1024 + 256) <= 228 * 1024, "windows do not fit the SM");
 };
 
 // floor(x) as float for 0 <= x < 2^22 without the conversion pipe: x + 2^23 rounds to an integer,
@@ -124,34 +119,12 @@ __device__ __forceinline__ float floor_nn(float x, int &i) {
 // exact u8 -> float on the ALU + FP32 pipes
 __device__ __forceinline__ float u8f(unsigned int b) { return __uint_as_float(0x4B000000u | b) - 8388608.0f; }
 
-// ---- asynchronous copies and the mbarrier they complete on (PTX; SASS: LDGSTS, UBLKCP, SYNCS) ----
+// ---- asynchronous copies (PTX cp.async; SASS: LDGSTS) ----
 __device__ __forceinline__ unsigned int smem_u32(const void *p) { return (unsigned int)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp_async4(unsigned int dst, const void *src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-__device__ __forceinline__ void mbar_init(unsigned int bar, unsigned int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned int bar, unsigned int bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned int bar, unsigned int parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_copy_g2s(unsigned int dst, const void *src, unsigned int bytes, unsigned int bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-               "r"(bytes), "r"(bar) : "memory");
-}
-
 // PatchMatch::GetPixelValue (reference src/patch_match.cpp:391-406) with the four taps taken from a staged
 // window with origin (wx0, wy0): the same clamps, the same expression tree.
 template <int WIN_W, int WIN_H>
@@ -182,6 +155,11 @@ __device__ __forceinline__ float window_sample(const unsigned char *__restrict__
 #define PROF_FLUSH()
 #endif
 
+// patch offsets (x, y) of pixel p in the reference's order (y outer, x inner, src/patch_match.cpp:233-246), read with
+// a warp-uniform index in the pass: one constant load instead of the compare/select that walks (x, y)
+__constant__ float2 c_pix5[121];
+__constant__ float2 c_pix10[441];
+
 struct Sums {
   double h00, h10, h11, h20, h21, h30, h31, b0, b1, b2, b3;
   float cost;
@@ -190,21 +168,38 @@ struct Sums {
 }  // namespace
 
 // =================================================================================================
-// K3a: the template records.  One warp per 32 consecutive (pair, feature, level) items: for each item lanes = pixels
-// compute T (the reference's GetPixelValue on the reference image, src/patch_match.cpp:253, :263) and store it,
-// then lane j of the warp runs item j's ordered sum of c*c (the h22 entry of the normal matrix, the same for every
-// iteration of the level: src/patch_match.cpp:296 with J[2] = c) and writes the record's tail.
+// K3a: the template records.  One warp per 32 consecutive (pair, feature, level) items.  Lane j decodes item j (one
+// coalesced load of the keypoints); the warp then stages the raw (P+2) x (P+2) tap block of the reference image of
+// G items at a time into shared memory with 4-byte asynchronous copies (lanes = words, the next group's copies in
+// flight while this group is computed), and for each item lanes = pixels compute T (the reference's GetPixelValue on
+// the reference image, src/patch_match.cpp:253, :263) from the staged taps and store it.  Lane j finally runs item j's
+// ordered sum of c*c (the h22 entry of the normal matrix, the same for every iteration of the level:
+// src/patch_match.cpp:296 with J[2] = c) and writes the record's tail.
 // =================================================================================================
+template <int HALF>
+struct TmplCfg {
+  static constexpr int P = 2 * HALF + 1;
+  // floor(fl(pt + x)) is floor(pt) + x, or one more when the sum is rounded up across a binade: taps span P + 2 columns
+  // and rows from floor(pt) - HALF; the staged rows start at the 4-byte aligned column below
+  static constexpr int ROWS = P + 2;
+  static constexpr int ROW_BYTES = (3 + P + 2 + 3) & ~3;
+  static constexpr int RWORDS = ROW_BYTES / 4;
+  static constexpr int WORDS = ROWS * RWORDS;
+  static constexpr int G = HALF <= 5 ? 8 : 4;  // items staged together, twice (double buffer): 26 / 40 KB per CTA
+};
+
 template <int HALF>
 __global__ void __launch_bounds__(256) pagk_lk_template_kernel(const unsigned char *__restrict__ images, PagkGeom g,
                                                              const PagkPairConst *__restrict__ pcs,
                                                              const float2 *__restrict__ keys_un, int levels, int max_keys,
                                                              int n_max, int n_pairs, unsigned char *__restrict__ tmpl) {
   using C = LanesCfg<HALF>;
-  constexpr int P = C::P, NP = C::NP, TK = (NP + 31) / 32;
+  using TC = TmplCfg<HALF>;
+  constexpr int P = C::P, NP = C::NP, TK = (NP + 31) / 32, G = TC::G, RB = TC::ROW_BYTES;
   constexpr unsigned FULL = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
-  const long long wg = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  __shared__ __align__(16) unsigned char s_raw[8][2][G][TC::WORDS * 4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long wg = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
   const long long total = (long long)n_pairs * n_max * levels, base = wg * 32;
   if (base >= total) return;
   const float hf = (float)HALF;
@@ -214,68 +209,110 @@ __global__ void __launch_bounds__(256) pagk_lk_template_kernel(const unsigned ch
     const int p = lane + 32 * k, py = p / P;
     tpx[k] = (float)(p - py * P - HALF); tpy[k] = (float)(py - HALF);
   }
-  const int per_pair = n_max * levels;
-  float myc = 0.f, mylast = 0.f;
-  unsigned char *myrec = nullptr;
+  // ---- lane j: item j
+  bool valid = false, tin = false;
+  float ptx = 0.f, pty = 0.f;
+  int cols = 1, rows = 1, pitch = 4, wx0 = 0, wy0 = 0;
+  const unsigned char *img1 = images;
+  unsigned char *rec = nullptr;
+  {
+    const long long idx = base + lane;
+    const int per_pair = n_max * levels;
+    if (idx < total) {
+      const int pr = (int)(idx / per_pair), rem = (int)(idx - (long long)pr * per_pair);
+      const int i = rem / levels, lv = rem - i * levels;
+      if (i < pcs[pr].n_keys) {
+        valid = true;
+        const size_t o = (size_t)pr * max_keys + i;
+        const float2 p1 = keys_un[o];
+        const float scale = 1.0f / (float)(1 << lv);
+        ptx = p1.x * scale; pty = p1.y * scale;  // pt = mvKeysRefUn[i].pt * mvScales[level] (:177)
+        cols = g.lv[lv].cols; rows = g.lv[lv].rows; pitch = g.lv[lv].pitch;
+        img1 = images + (size_t)(pr * 2) * g.slot_bytes + g.lv[lv].offset;
+        rec = tmpl + (o * (size_t)levels + lv) * C::REC_BYTES;
+        const float txlo = ptx + (-hf), txhi = ptx + hf, tylo = pty + (-hf), tyhi = pty + hf;
+        // no clamp of GetPixelValue fires anywhere in the template
+        tin = txlo >= 0.0f && txhi < (float)cols && tylo >= 0.0f && tyhi < (float)rows;
+        if (tin) { wx0 = (int)txlo & ~3; wy0 = (int)tylo; }  // pt - HALF is exact: floor(pt) - HALF
+      }
+    }
+  }
+  auto stage = [&](int gi) {  // the tap blocks of items gi * G .. gi * G + G - 1 -> buffer gi & 1
 #pragma unroll 1
-  for (int j = 0; j < 32; ++j) {
-    const long long idx = base + j;
-    if (idx >= total) break;
-    const int pr = (int)(idx / per_pair), rem = (int)(idx - (long long)pr * per_pair);
-    const int i = rem / levels, lv = rem - i * levels;
-    if (i >= pcs[pr].n_keys) continue;
-    const size_t o = (size_t)pr * max_keys + i;
-    const float2 p1 = keys_un[o];
-    const float scale = 1.0f / (float)(1 << lv);
-    const float ptx = p1.x * scale, pty = p1.y * scale;  // pt = mvKeysRefUn[i].pt * mvScales[level] (:177)
-    const int cols = g.lv[lv].cols, rows = g.lv[lv].rows, pitch = g.lv[lv].pitch;
-    const unsigned char *img1 = images + (size_t)(pr * 2) * g.slot_bytes + g.lv[lv].offset;
-    unsigned char *rec = tmpl + (o * (size_t)levels + lv) * C::REC_BYTES;
-    float *T = reinterpret_cast<float *>(rec);
-    const float txlo = ptx + (-hf), txhi = ptx + hf, tylo = pty + (-hf), tyhi = pty + hf;
-    const bool tin = txlo >= 0.0f && txhi < (float)cols && tylo >= 0.0f && tyhi < (float)rows;
-    float tv[TK];
-    if (tin) {
-      // no clamp of GetPixelValue fires anywhere in the template: the four taps of each pixel straight from the level,
-      // floor by a round-down add of 2^23 (exact for 0 <= x < 2^22), u8 -> float without the conversion pipe
-      unsigned char t00[TK], t10[TK], t01[TK], t11[TK];
-      float wxx[TK], wyy[TK];
+    for (int jj = 0; jj < G; ++jj) {
+      const int j = gi * G + jj;
+      const int go = __shfl_sync(FULL, (int)(valid && tin), j);
+      const int sp = __shfl_sync(FULL, pitch, j), sx0 = __shfl_sync(FULL, wx0, j), sy0 = __shfl_sync(FULL, wy0, j);
+      const int rmax = __shfl_sync(FULL, rows, j) - sy0;  // rows past the guard row are never sampled: copy the guard row again
+      const unsigned char *src = reinterpret_cast<const unsigned char *>(__shfl_sync(FULL, (unsigned long long)img1, j)) + sy0 * sp + sx0;
+      if (!go) continue;
+      const unsigned int dst = smem_u32(&s_raw[warp][gi & 1][jj][0]);
 #pragma unroll
-      for (int k = 0; k < TK; ++k) {
-        const int p = lane + 32 * k;
-        const float cx = ptx + tpx[k], cy = pty + tpy[k];
-        const float tx = __fadd_rd(cx, 8388608.0f), ty = __fadd_rd(cy, 8388608.0f);
-        wxx[k] = cx - (tx - 8388608.0f); wyy[k] = cy - (ty - 8388608.0f);
-        const int ix = __float_as_int(tx) - 0x4B000000, iy = __float_as_int(ty) - 0x4B000000;
-        t00[k] = t10[k] = t01[k] = t11[k] = 0;
-        if (p < NP) {
-          const unsigned char *q = img1 + iy * pitch + ix;
-          t00[k] = __ldg(q); t10[k] = __ldg(q + 1); t01[k] = __ldg(q + pitch); t11[k] = __ldg(q + pitch + 1);
+      for (int k = 0; k < (TC::WORDS + 31) / 32; ++k) {
+        const int e = lane + 32 * k, r = e / TC::RWORDS, w = e - r * TC::RWORDS;
+        if (e < TC::WORDS) cp_async4(dst + 4u * (unsigned int)e, src + min(r, rmax) * sp + 4 * w);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  float myc = 0.f, mylast = 0.f;
+  stage(0);
+#pragma unroll 1
+  for (int gi = 0; gi < 32 / G; ++gi) {
+    if (gi + 1 < 32 / G) {
+      stage(gi + 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int jj = 0; jj < G; ++jj) {
+      const int j = gi * G + jj;
+      if (!__shfl_sync(FULL, (int)valid, j)) continue;
+      const int stin = __shfl_sync(FULL, (int)tin, j);
+      const float sptx = __shfl_sync(FULL, ptx, j), spty = __shfl_sync(FULL, pty, j);
+      float *T = reinterpret_cast<float *>(__shfl_sync(FULL, (unsigned long long)rec, j));
+      float tv[TK];
+      if (stin) {
+        // floor by a round-down add of 2^23 (exact for 0 <= x < 2^22), u8 -> float without the conversion pipe
+        const int sx0 = __shfl_sync(FULL, wx0, j), sy0 = __shfl_sync(FULL, wy0, j);
+        const unsigned char *raw = &s_raw[warp][gi & 1][jj][0];
+#pragma unroll
+        for (int k = 0; k < TK; ++k) {
+          const float cx = sptx + tpx[k], cy = spty + tpy[k];
+          const float tx = __fadd_rd(cx, 8388608.0f), ty = __fadd_rd(cy, 8388608.0f);
+          const float xx = cx - (tx - 8388608.0f), yy = cy - (ty - 8388608.0f), wa = 1.0f - xx, wb = 1.0f - yy;
+          const int ix = __float_as_int(tx) - 0x4B000000, iy = __float_as_int(ty) - 0x4B000000;
+          tv[k] = 0.f;
+          if (lane + 32 * k < NP) {
+            CHECK_IDX((iy - sy0) * RB + (ix - sx0), 0, TC::WORDS * 4 - RB - 2);
+            const unsigned char *q = raw + (iy - sy0) * RB + (ix - sx0);
+            tv[k] = wb * (wa * u8f(q[0]) + xx * u8f(q[1])) + yy * (wa * u8f(q[RB]) + xx * u8f(q[RB + 1]));
+          }
+        }
+      } else {
+        const int scols = __shfl_sync(FULL, cols, j), srows = __shfl_sync(FULL, rows, j), sp = __shfl_sync(FULL, pitch, j);
+        const unsigned char *simg = reinterpret_cast<const unsigned char *>(__shfl_sync(FULL, (unsigned long long)img1, j));
+#pragma unroll
+        for (int k = 0; k < TK; ++k) {
+          tv[k] = 0.f;
+          if (lane + 32 * k < NP) tv[k] = pagk_sample_call(simg, sp, scols, srows, sptx + tpx[k], spty + tpy[k]);
         }
       }
 #pragma unroll
       for (int k = 0; k < TK; ++k) {
-        const float xx = wxx[k], yy = wyy[k], wa = 1.0f - xx, wb = 1.0f - yy;
-        tv[k] = wb * (wa * u8f(t00[k]) + xx * u8f(t10[k])) + yy * (wa * u8f(t01[k]) + xx * u8f(t11[k]));
+        const int p = lane + 32 * k;
+        if (p < NP - 1) T[p] = tv[k];
       }
-    } else {
-#pragma unroll
-      for (int k = 0; k < TK; ++k) {
-        tv[k] = 0.f;
-        if (lane + 32 * k < NP) tv[k] = pagk_sample_call(img1, pitch, cols, rows, ptx + tpx[k], pty + tpy[k]);
-      }
+      // de_dg = -I1(pt) (src/patch_match.cpp:263) is minus the template value of the centre pixel: pt + (0, 0)
+      const float tc = __shfl_sync(FULL, tv[(NP / 2) / 32], (NP / 2) % 32);
+      const float tl = __shfl_sync(FULL, tv[(NP - 1) / 32], (NP - 1) % 32);
+      if (lane == j) { myc = -tc; mylast = tl; }
     }
-#pragma unroll
-    for (int k = 0; k < TK; ++k) {
-      const int p = lane + 32 * k;
-      if (p < NP - 1) T[p] = tv[k];
-    }
-    // de_dg = -I1(pt) (src/patch_match.cpp:263) is minus the template value of the centre pixel: pt + (0, 0)
-    const float tc = __shfl_sync(FULL, tv[(NP / 2) / 32], (NP / 2) % 32);
-    const float tl = __shfl_sync(FULL, tv[(NP - 1) / 32], (NP - 1) % 32);
-    if (lane == j) { myc = -tc; mylast = tl; myrec = rec; }
+    __syncwarp();
   }
-  if (myrec) {
+  if (valid) {
     const double c = (double)myc;
     double h22 = 0.0;
 #pragma unroll 11
@@ -283,7 +320,7 @@ __global__ void __launch_bounds__(256) pagk_lk_template_kernel(const unsigned ch
     float4 tail;
     tail.x = mylast; tail.y = myc;
     tail.z = __int_as_float(__double2loint(h22)); tail.w = __int_as_float(__double2hiint(h22));
-    *reinterpret_cast<float4 *>(myrec + C::T_BULK) = tail;
+    *reinterpret_cast<float4 *>(rec + C::T_BULK) = tail;
   }
 }
 
@@ -301,16 +338,11 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
   constexpr int P = C::P, NP = C::NP, WIN_W = C::WIN_W, WIN_H = C::WIN_H;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned char *wbase = smem_raw + (size_t)warp * C::WARP_BYTES;
-  unsigned char *wwin = wbase + C::T_WARP_BYTES;                                          // [SLOTS] windows, stride WIN_STRIDE
-  unsigned char *tail = smem_raw + (size_t)C::WARPS * C::WARP_BYTES;
-  float *scratch = reinterpret_cast<float *>(tail) + warp * C::SCRATCH_FLOATS;  // [32][3] records, c, 1
-  unsigned long long *mbars = reinterpret_cast<unsigned long long *>(tail + LANES_WARPS_SM * C::SCRATCH_FLOATS * 4);
-  const unsigned int mbar = smem_u32(mbars + warp);
+  unsigned char *wwin = smem_raw + (size_t)warp * C::WARP_BYTES;                          // [SLOTS] windows, stride WIN_STRIDE
+  float *scratch = reinterpret_cast<float *>(wwin + C::SLOTS * C::WIN_STRIDE);            // [32][3] records, c, 1
   // lanes beyond SLOTS never own a feature; in the lockstep pass they read (harmlessly) the last slot's memory
   const int myslot = lane < C::SLOTS ? lane : C::SLOTS - 1;
   const unsigned char *mywin = wwin + myslot * C::WIN_STRIDE;
-  const float *myT = reinterpret_cast<const float *>(wbase + C::t_off(myslot));
   const int total_work = n_pairs * n_max;
   const int top = mode.levels - 1;
   // Work items.  split == 0: an item is a feature (all levels in one lane).  split != 0: an item is one LEVEL of a
@@ -331,12 +363,7 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
     s_cols[threadIdx.x] = g.lv[threadIdx.x].cols; s_rows[threadIdx.x] = g.lv[threadIdx.x].rows;
     s_pitch[threadIdx.x] = g.lv[threadIdx.x].pitch; s_off[threadIdx.x] = g.lv[threadIdx.x].offset;
   }
-  if (lane == 0) {
-    mbar_init(mbar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
   __syncthreads();
-  unsigned int tphase = 0;  // parity of the warp's mbarrier phase the next wait looks at
 
   // accumulator role of this lane in the cooperative pass: acc += A * B with A in {Ix, Iy, c, 1} and B in
   // {Ix, Iy, -e, c}; lanes 0..11 = h00 h10 h11 h20 h21 h22 h30 h31 b0 b1 b2 b3.  An operand is a float in the
@@ -350,6 +377,7 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
   // ---- slot state (registers of the owning lane) ----
   int feat = -1, pair = 0, level = 0, iter = 0, n_iter = 0, succ = 1;
   float pt1x = 0.f, pt1y = 0.f, ptx = 0.f, pty = 0.f, dx = 0.f, dy = 0.f, dg = 0.f, db = 0.f, lastCost = 0.f, cval = 0.f;
+  const float4 *Tg = reinterpret_cast<const float4 *>(tmpl);  // the level's template record (any valid record when idle)
   float tlast = 0.f;   // T[NP - 1]
   double h22v = 0.0;   // the level's sum of c*c
   float a00 = 1.f, a01 = 0.f, a10 = 0.f, a11 = 1.f;
@@ -428,28 +456,16 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
         }
       }
     }
-    // ------------------------------------------------------------------ template of a level that starts: one bulk copy
-    // (UBLKCP) per lane from its record, the record's tail by a vector load.  The template does not depend on the level
-    // above, so a lane that still waits for its hand-over issues it as well.
-    bool tpend = false;  // warp-uniform
-    {
-      const bool iss = feat >= 0 && needs_setup;
-      const unsigned mi = __ballot_sync(FULL, iss);
-      if (mi) {
-        // the slots' T areas were last read through the generic proxy; the copy engine writes them through the async one
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        if (lane == 0) mbar_expect_tx(mbar, (unsigned int)C::T_BULK * (unsigned int)__popc(mi));
-        __syncwarp();
-        if (iss) {
-          const unsigned char *rec = tmpl + ((size_t)feat * (size_t)mode.levels + (size_t)level) * C::REC_BYTES;
-          bulk_copy_g2s(smem_u32(myT), rec, C::T_BULK, mbar);
-          const float4 tl = __ldg(reinterpret_cast<const float4 *>(rec + C::T_BULK));
-          tlast = tl.x; cval = tl.y;
-          h22v = __hiloint2double(__float_as_int(tl.w), __float_as_int(tl.z));
-          needs_setup = false; win_valid = false;
-        }
-        tpend = true;
-      }
+    // ------------------------------------------------------------------ a level that starts: its template record
+    // (the pass streams T from it; c, h22 and the last T value come from the record's tail).  The template does not depend
+    // on the level above, so a lane that still waits for its hand-over does this as well.
+    if (feat >= 0 && needs_setup) {
+      const unsigned char *rec = tmpl + ((size_t)feat * (size_t)mode.levels + (size_t)level) * C::REC_BYTES;
+      Tg = reinterpret_cast<const float4 *>(rec);
+      const float4 tl = __ldg(reinterpret_cast<const float4 *>(rec + C::T_BULK));
+      tlast = tl.x; cval = tl.y;
+      h22v = __hiloint2double(__float_as_int(tl.w), __float_as_int(tl.z));
+      needs_setup = false; win_valid = false;
     }
     if (split) {
       // a claimed level starts once the level above it has published its result.  The owner of that level is a
@@ -468,12 +484,10 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
     const bool active = feat >= 0 && !waiting;
     const unsigned m_active = __ballot_sync(FULL, active);
     if (m_active == 0u) {
-      // nothing to run this round: finish the copies in flight (a waiting lane's template), then poll again or leave
-      if (tpend) { mbar_wait(mbar, tphase); tphase ^= 1u; }
-      if (__ballot_sync(FULL, waiting) != 0u) { __nanosleep(200); continue; }
+      if (__ballot_sync(FULL, waiting) != 0u) { __nanosleep(200); continue; }  // nothing to run this round: poll again
       break;
     }
-    PROF(0); PROF_ADD(6, 1); PROF_ADD(7, __popc(m_active));
+    PROF(0); PROF_ADD(6, 1); PROF_ADD(7, __popc(m_active)); PROF_ADD(2, __popc(__ballot_sync(FULL, waiting)));
 
     const int cols = s_cols[level], rows = s_rows[level], pitch = s_pitch[level];
     const unsigned char *I2 = images + (size_t)(pair * 2 + 1) * slot_bytes + s_off[level];
@@ -530,7 +544,6 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
     }
     // one wait for every copy of the round
     cp_async_wait_all();
-    if (tpend) { mbar_wait(mbar, tphase); tphase ^= 1u; }
     __syncwarp();
     PROF(1);
 
@@ -561,16 +574,12 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
       const unsigned int kk = (unsigned int)(WIN_W + 1) * 0x4B000000u + (unsigned int)(fast ? win_y0 * WIN_W + win_x0 : 0);
       // one flat walk over the P * P pixels (row-major, the reference's order), PAGK_LANES_UNROLL pixels per trip with
       // their template values in one vector load; the last pixel's template value is a register
-      float xf = -(float)HALF, yf = -(float)HALF;
-      auto pixel = [&](const float tval) {
+      const float2 *pix = HALF == 5 ? c_pix5 : c_pix10;
+      auto pixel = [&](const int p, const float tval) {
+        const float2 xy = pix[p];
+        const float xf = xy.x, yf = xy.y;
         float wx = xf, wy = yf;
         if (AFFINE) { wx = q00 * xf + q01 * yf; wy = q10 * xf + q11 * yf; }
-        {
-          const bool wrap = xf >= (float)HALF;  // next pixel: x + 1, or the start of the next row
-          const float nxf = xf + 1.0f;
-          yf = wrap ? yf + 1.0f : yf;
-          xf = wrap ? -(float)HALF : nxf;
-        }
         const float sx = pbx + wx, sy = pby + wy;
         // floor for 0 <= x < 2^22: x + 2^23 rounded DOWN is 2^23 + floor(x) exactly; taking 2^23 off is exact
         const float tx = __fadd_rd(sx, 8388608.0f), ty = __fadd_rd(sy, 8388608.0f);
@@ -596,7 +605,10 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
         const float vx1 = wb * H0p + yy * H1p, vx2 = wb * H0m + yy * H1m;
         const float vy1 = wb1 * H1 + yy1 * H2, vy2 = wb * Hm + yy * H0;
         const float e = (v0 + db) - gain * tval;
-        const float gxf = 0.5f * (vx1 - vx2), gyf = 0.5f * (vy1 - vy2), mf = -e;
+        // twice the gradient: Ix = 0.5 * gxf is an exact halving, and every sum below that contains Ix or Iy is the
+        // reference's sum times a power of two at every step (scaling by 2^k commutes with rounding; nothing here is
+        // near the subnormals), so the factors 0.5 and 0.25 are applied once, after the loop
+        const float gxf = vx1 - vx2, gyf = vy1 - vy2, mf = -e;
         // J = (Ix, Iy, c, 1) as double; b += -J * e; H += J * J^T; cost += e * e (float), reference :264-299.
         // Each product of two float-valued doubles is exact, so DFMA rounds like the separate mul + add.
         // (H[2][2] = sum of c*c does not depend on the samples: it comes with the template record.)
@@ -609,17 +621,28 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
       };
       constexpr int V = PAGK_LANES_UNROLL;
       static_assert((NP - 1) % V == 0 && (V == 4 || V == 2), "vector width of the template loads");
+      // T streams from the record (L1 / L2): the next trip's vector is loaded before this trip's pixels are computed
+      if (V == 4) {
+        float4 t4 = __ldg(Tg);
 #pragma unroll 1
-      for (int j = 0; j < (NP - 1) / V; ++j) {
-        if (V == 4) {
-          const float4 t4 = reinterpret_cast<const float4 *>(myT)[j];
-          pixel(t4.x); pixel(t4.y); pixel(t4.z); pixel(t4.w);
-        } else {
-          const float2 t2 = reinterpret_cast<const float2 *>(myT)[j];
-          pixel(t2.x); pixel(t2.y);
+        for (int j = 0; j < (NP - 1) / 4; ++j) {
+          const float4 nx = __ldg(Tg + min(j + 1, (NP - 1) / 4 - 1));
+          pixel(4 * j, t4.x); pixel(4 * j + 1, t4.y); pixel(4 * j + 2, t4.z); pixel(4 * j + 3, t4.w);
+          t4 = nx;
+        }
+      } else {
+        const float2 *Tg2 = reinterpret_cast<const float2 *>(Tg);
+        float2 t2 = __ldg(Tg2);
+#pragma unroll 1
+        for (int j = 0; j < (NP - 1) / 2; ++j) {
+          const float2 nx = __ldg(Tg2 + min(j + 1, (NP - 1) / 2 - 1));
+          pixel(2 * j, t2.x); pixel(2 * j + 1, t2.y);
+          t2 = nx;
         }
       }
-      pixel(tlast);
+      pixel(NP - 1, tlast);
+      S.h00 *= 0.25; S.h10 *= 0.25; S.h11 *= 0.25;
+      S.h20 *= 0.5; S.h21 *= 0.5; S.h30 *= 0.5; S.h31 *= 0.5; S.b0 *= 0.5; S.b1 *= 0.5;
       coop |= active && fast && (badv >= 1.0f);
     }
     PROF(3);
@@ -643,7 +666,7 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
         const int swin = __shfl_sync(FULL, (int)windowable, s);
         const unsigned char *img2 = reinterpret_cast<const unsigned char *>(__shfl_sync(FULL, (unsigned long long)I2, s));
         const unsigned char *win = wwin + s * C::WIN_STRIDE;
-        const float *T = reinterpret_cast<const float *>(wbase + C::t_off(s));
+        const float *T = reinterpret_cast<const float *>(__shfl_sync(FULL, (unsigned long long)Tg, s));
         const float gc = (float)scols, gr = (float)srows, gc1 = (float)(scols - 1), gr1 = (float)(srows - 1);
         double acc = 0.0;
         float cacc = 0.f;
@@ -673,7 +696,7 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
               vy1 = pagk_sample_call(img2, sp, scols, srows, sx, sy + 1.0f);
               vy2 = pagk_sample_call(img2, sp, scols, srows, sx, sy - 1.0f);
             }
-            const float tval = p < NP - 1 ? T[p] : stl;
+            const float tval = p < NP - 1 ? __ldg(T + p) : stl;
             const float e = (v0 + sdb) - sgain * tval;
             scratch[3 * lane] = 0.5f * (vx1 - vx2);
             scratch[3 * lane + 1] = 0.5f * (vy1 - vy2);
@@ -787,9 +810,19 @@ static cudaError_t configure_lanes() {
   return cudaFuncSetAttribute(pagk_lk_lanes_kernel<HALF, AFFINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, LanesCfg<HALF>::SMEM_BYTES);
 }
 
-// per device, from pagk_create after cudaSetDevice (a function attribute belongs to the device it was set on)
+template <int HALF>
+static cudaError_t upload_pix(const float2 *sym) {
+  constexpr int P = 2 * HALF + 1;
+  float2 h[P * P];
+  for (int p = 0; p < P * P; ++p) h[p] = make_float2((float)(p % P - HALF), (float)(p / P - HALF));
+  return cudaMemcpyToSymbol(*reinterpret_cast<const float2(*)[P * P]>(sym), h, sizeof(h));
+}
+
+// per device, from pagk_create after cudaSetDevice (function attributes and __constant__ data belong to the device)
 int pagk_lk_lanes_configure() {
-  cudaError_t e = configure_lanes<5, true>();
+  cudaError_t e = upload_pix<5>(c_pix5);
+  if (e == cudaSuccess) e = upload_pix<10>(c_pix10);
+  if (e == cudaSuccess) e = configure_lanes<5, true>();
   if (e == cudaSuccess) e = configure_lanes<5, false>();
   if (e == cudaSuccess) e = configure_lanes<10, true>();
   if (e == cudaSuccess) e = configure_lanes<10, false>();

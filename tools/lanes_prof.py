@@ -10,7 +10,9 @@ if len(sys.argv) > 1:
 cfg = {k: v for k, v in synth.CONFIGS["B"].items() if k != "pairs"}
 pairs = [synth.make_pair(2000 + i, **cfg) for i in range(64)]
 prm = capi.default_params(pyramids=4)
-with tracker.Context(max_keys=1024, max_pairs=64, max_levels=4) as ctx:
+NP = int(os.environ.get("PROF_PAIRS", "64"))
+pairs = (pairs * ((NP + 63) // 64))[:NP]
+with tracker.Context(max_keys=1024, max_pairs=NP, max_levels=4) as ctx:
     ctx.upload(pairs, prm)
     for _ in range(3):
         ctx.run(); ctx.synchronize()
@@ -20,9 +22,10 @@ with tracker.Context(max_keys=1024, max_pairs=64, max_levels=4) as ctx:
 it = np.concatenate([o.iters for o in outs])
 print("features", it.size, "iterations: mean %.2f p50 %d p90 %d p99 %d max %d" % (it.mean(), np.percentile(it, 50), np.percentile(it, 90), np.percentile(it, 99), it.max()))
 t = np.loadtxt("gpurun_out/lanes_prof.txt")
-names = ["refill", "setup", "window", "pass", "coop", "solve", "rounds", "lane-rounds"]
-tot = t[:, :6].sum(axis=1)
+names = ["refill", "setup", "waiting-lane-rounds", "pass", "coop", "solve", "rounds", "lane-rounds"]
+tot = t[:, [0, 1, 3, 4, 5]].sum(axis=1)
 print("warps", len(t), "cycles/warp: min %d mean %d max %d" % (tot.min(), tot.mean(), tot.max()))
 for i, n in enumerate(names):
-    print(f"{n:12s} mean {t[:, i].mean():10.0f}  min {t[:, i].min():10.0f} max {t[:, i].max():10.0f}" + (f"  share {100 * t[:, i].sum() / tot.sum():5.1f}%" if i < 6 else ""))
+    print(f"{n:12s} mean {t[:, i].mean():10.0f}  min {t[:, i].min():10.0f} max {t[:, i].max():10.0f}" + (f"  share {100 * t[:, i].sum() / tot.sum():5.1f}%" if i in (0, 1, 3, 4, 5) else ""))
+print("slots per warp-round: active %.2f waiting %.2f" % (t[:, 7].sum() / t[:, 6].sum(), t[:, 2].sum() / t[:, 6].sum()))
 print("lane occupancy %.3f ; cycles per round %.0f ; pass cycles per round %.0f" % (t[:, 7].sum() / (32 * t[:, 6].sum()), tot.sum() / t[:, 6].sum(), t[:, 3].sum() / t[:, 6].sum()))
