@@ -48,11 +48,18 @@ bool make_geom(int width, int height, int levels, PagkGeom *g) {
     // continuous when the rows are 4-byte aligned as they are, else padded with room for the explicit wrap column
     const int pitch = (c % 4 == 0) ? c : (int)align_up((size_t)c + 1, 4);
     g->lv[l].cols = c; g->lv[l].rows = r; g->lv[l].pitch = pitch; g->lv[l].offset = (unsigned int)off;
-    // rows + guard row, at least 32 rows, and 64 bytes: a staged window may overhang the image (its content is not used)
+    // rows + guard row, at least 32 rows, and 64 elements: a staged window may overhang the image (its content is not used)
     off += align_up((size_t)std::max(r + 1, 32) * pitch + 64, 256);
     c = (int)(c * 0.5); r = (int)(r * 0.5);  // cv::Size(cols * 0.5, rows * 0.5), reference src/patch_match.cpp:69
   }
-  for (int l = levels; l < PAGK_MAX_LEVELS; ++l) g->lv[l] = PagkLevelGeom{0, 0, 0, 0};
+  g->u8_bytes = off;
+  for (int l = 0; l < levels; ++l) {  // the same levels with 16-bit elements (bfloat16 pixels of the current images)
+    g->lv[l].offset16 = 0;
+    if (!pagk_lk_lanes_win16()) continue;  // only builds whose alignment kernel reads that plane have it
+    g->lv[l].offset16 = (unsigned int)off;
+    off += align_up(2 * ((size_t)std::max(g->lv[l].rows + 1, 32) * g->lv[l].pitch + 64), 256);
+  }
+  for (int l = levels; l < PAGK_MAX_LEVELS; ++l) g->lv[l] = PagkLevelGeom{0, 0, 0, 0, 0};
   g->slot_bytes = off;
   return true;
 }
@@ -242,7 +249,8 @@ int upload_images(pagk_handle *h, int n_pairs, const uint8_t *const *refs, const
 int upload_images_continue(pagk_handle *h, int n_pairs, const uint8_t *const *curs, int width, int height, const int *pitches) {
   const PagkGeom &g = h->geom;
   const size_t img_bytes = (size_t)width * height;
-  CU(cudaMemcpy2DAsync(h->d_images, 2 * g.slot_bytes, h->d_images + g.slot_bytes, 2 * g.slot_bytes, g.slot_bytes, (size_t)n_pairs,
+  // (the u8 levels only: a reference image's bfloat16 plane is not read)
+  CU(cudaMemcpy2DAsync(h->d_images, 2 * g.slot_bytes, h->d_images + g.slot_bytes, 2 * g.slot_bytes, g.u8_bytes, (size_t)n_pairs,
                        cudaMemcpyDeviceToDevice, h->stream));
   if (h->d_maps) return upload_images_rectify(h, n_pairs, nullptr, curs, width, height, pitches);
   const size_t dp = (size_t)g.lv[0].pitch;
@@ -367,7 +375,7 @@ int pagk_create(const pagk_config *cfg, pagk_handle **out) {
   int lv = cfg->max_levels;
   while (lv > 1 && !make_geom(cfg->max_width, cfg->max_height, lv, &g)) --lv;
   make_geom(cfg->max_width, cfg->max_height, lv, &g);
-  h->slot_capacity = g.slot_bytes + 256 * (size_t)cfg->max_levels;
+  h->slot_capacity = g.slot_bytes + 512 * (size_t)cfg->max_levels;
   const size_t NK = (size_t)cfg->max_pairs * cfg->max_keys;
   size_t off = 0;
   for (int k = 0; k < O_COUNT; ++k) { h->out_off[k] = off; off += align_up(NK * kOutElt[k], 256); }
@@ -542,8 +550,8 @@ int pagk_run_resident(pagk_handle *h) {
                                         h->geom.width, h->geom.height, h->d_ntab, h->ntab_stride, h->aux, &h->launches));
     CU(cudaEventRecord(h->ev_aux, h->aux));
     // a stream continuation already has the reference pyramids (copied from the previous current ones at upload)
-    if (h->cont) CU((cudaError_t)pagk_launch_pyramids(h->d_images + h->geom.slot_bytes, h->geom, h->n_pairs, 2, st, &h->launches));
-    else CU((cudaError_t)pagk_launch_pyramids(h->d_images, h->geom, 2 * h->n_pairs, 1, st, &h->launches));
+    if (h->cont) CU((cudaError_t)pagk_launch_pyramids(h->d_images + h->geom.slot_bytes, h->geom, h->n_pairs, 2, 1, st, &h->launches));
+    else CU((cudaError_t)pagk_launch_pyramids(h->d_images, h->geom, 2 * h->n_pairs, 1, 0, st, &h->launches));
     h->cur_pairs = h->n_pairs;
     if (stages) CU(cudaEventRecord(h->ev[1], st));
     CU(cudaStreamWaitEvent(st, h->ev_aux, 0));
@@ -773,7 +781,7 @@ int pagk_build_pyramids(pagk_handle *h, int n_images, const uint8_t *const *imgs
   for (int i = 0; i < n_images; ++i)
     CU(cudaMemcpy2DAsync(h->d_images + (size_t)i * h->geom.slot_bytes + h->geom.lv[0].offset, (size_t)h->geom.lv[0].pitch, imgs[i], pitch,
                          width, height, cudaMemcpyHostToDevice, h->stream));
-  CU((cudaError_t)pagk_launch_pyramids(h->d_images, h->geom, n_images, 1, h->stream, &h->launches));
+  CU((cudaError_t)pagk_launch_pyramids(h->d_images, h->geom, n_images, 1, 0, h->stream, &h->launches));
   CU(cudaStreamSynchronize(h->stream));
   return PAGK_OK;
 }
@@ -1123,7 +1131,7 @@ int pagk_patch_match(pagk_handle *h, const pagk_patch_match_in *in, pagk_pair_ou
   h->ran_stages = true;
   CU(cudaEventRecord(h->ev[0], st));
   h->cur_pairs = 0;
-  CU((cudaError_t)pagk_launch_pyramids(h->d_images, h->geom, 2, 1, st, &h->launches));
+  CU((cudaError_t)pagk_launch_pyramids(h->d_images, h->geom, 2, 1, 0, st, &h->launches));
   CU(cudaEventRecord(h->ev[1], st));
   CU(cudaEventRecord(h->ev[2], st));
   CU((cudaError_t)launch_lk(h, o, m, in->n_keys, 1));

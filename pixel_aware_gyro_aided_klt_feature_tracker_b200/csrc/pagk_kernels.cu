@@ -28,13 +28,22 @@
 #define PYR_TH 64
 
 // Pixel (0, gy) = v has just been produced: write the wrap bytes that mirror it (pagk_device.cuh, PagkLevelGeom):
-// column `cols` of the row above, and for the last row its own wrap byte and the guard row's.  In a continuous
-// level (pitch == cols) the first two are the pixel itself and the guard row's first byte: same value, harmless.
-__device__ __forceinline__ void pagk_write_wrap(unsigned char *ll, int pitch, int cols, int rows, int gy, unsigned char v) {
-  if (gy >= 1 && pitch > cols) ll[(size_t)(gy - 1) * pitch + cols] = v;
+// column `cols` of the row above when the level is padded, and for the last row its own wrap byte and the guard row's.
+// l16: the level's bfloat16 plane (null: not written).
+__device__ __forceinline__ void pagk_write_wrap(unsigned char *ll, unsigned short *l16, int pitch, int cols, int rows, int gy,
+                                                unsigned char v) {
+  const unsigned short v16 = pagk_bf16_of_u8(v);
+  if (gy >= 1 && pitch > cols) {
+    ll[(size_t)(gy - 1) * pitch + cols] = v;
+    if (l16) l16[(size_t)(gy - 1) * pitch + cols] = v16;
+  }
   if (gy == rows - 1) {
-    if (pitch > cols) ll[(size_t)gy * pitch + cols] = v;
+    if (pitch > cols) {
+      ll[(size_t)gy * pitch + cols] = v;
+      if (l16) l16[(size_t)gy * pitch + cols] = v16;
+    }
     ll[(size_t)rows * pitch + cols] = v;
+    if (l16) l16[(size_t)rows * pitch + cols] = v16;
   }
 }
 
@@ -49,12 +58,13 @@ __device__ __forceinline__ unsigned int pagk_avg4x8(unsigned int r0, unsigned in
 // to shared memory `d` and to the image; then recurses to level l+1.  All index arithmetic is shifts and masks.
 template <int TW, int TH>
 __device__ __forceinline__ void pagk_pyramid_tile_level(const unsigned char *s, unsigned char *d, unsigned char *img,
-                                                        const PagkGeom &g, int l, int n_fused, int tx0, int ty0, int t) {
+                                                        const PagkGeom &g, int l, int n_fused, int tx0, int ty0, int t, bool w16) {
   constexpr int OW = TW / 2, OH = TH / 2;
   if constexpr (OW >= 1 && OH >= 1) {
     __syncthreads();
     const int colsl = g.lv[l].cols, rowsl = g.lv[l].rows, pl = g.lv[l].pitch;
     unsigned char *ll = img + g.lv[l].offset;
+    unsigned short *l16 = w16 ? reinterpret_cast<unsigned short *>(img + g.lv[l].offset16) : nullptr;
     const int ox0 = tx0 >> l, oy0 = ty0 >> l;
 #pragma unroll
     for (int p = t; p < OW * OH; p += 256) {
@@ -67,24 +77,32 @@ __device__ __forceinline__ void pagk_pyramid_tile_level(const unsigned char *s, 
       if (gx < colsl && gy < rowsl) {
         ll[(size_t)gy * pl + gx] = v;
         if (gy == rowsl - 1) ll[(size_t)rowsl * pl + gx] = v;  // guard row
-        if (gx == 0) pagk_write_wrap(ll, pl, colsl, rowsl, gy, v);
+        if (l16) {
+          const unsigned short v16 = pagk_bf16_of_u8(v);
+          l16[(size_t)gy * pl + gx] = v16;
+          if (gy == rowsl - 1) l16[(size_t)rowsl * pl + gx] = v16;
+        }
+        if (gx == 0) pagk_write_wrap(ll, l16, pl, colsl, rowsl, gy, v);
       }
     }
-    if (l < n_fused) pagk_pyramid_tile_level<OW, OH>(d, const_cast<unsigned char *>(s), img, g, l + 1, n_fused, tx0, ty0, t);
+    if (l < n_fused) pagk_pyramid_tile_level<OW, OH>(d, const_cast<unsigned char *>(s), img, g, l + 1, n_fused, tx0, ty0, t, w16);
   }
 }
 
 #ifndef PAGK_PYR_MIN_BLOCKS
-#define PAGK_PYR_MIN_BLOCKS 8
+#define PAGK_PYR_MIN_BLOCKS 4
 #endif
 __global__ void __launch_bounds__(256, PAGK_PYR_MIN_BLOCKS) pagk_pyramid_fused_kernel(unsigned char *__restrict__ images, PagkGeom g,
                                                                int n_fused /* last level produced here */,
-                                                               int z_stride /* image z lives in slot z * z_stride */) {
+                                                               int z_stride /* image z lives in slot z * z_stride */,
+                                                               int cur_parity /* (z * z_stride + cur_parity) odd: a current image */) {
   __shared__ __align__(16) unsigned char sbuf[2][(PYR_TW / 2) * (PYR_TH / 2)];
   unsigned char *img = images + (size_t)blockIdx.z * z_stride * g.slot_bytes;
+  const bool w16 = g.lv[0].offset16 != 0 && ((blockIdx.z * z_stride + cur_parity) & 1) != 0;  // current images get their bfloat16 plane
   const int t = threadIdx.x;
   const int cols0 = g.lv[0].cols, rows0 = g.lv[0].rows, p0 = g.lv[0].pitch;
   unsigned char *l0 = img + g.lv[0].offset;
+  unsigned short *l0h = reinterpret_cast<unsigned short *>(img + g.lv[0].offset16);
   const int tx0 = blockIdx.x * PYR_TW, ty0 = blockIdx.y * PYR_TH;
 
   // ---- level 0 -> level 1 (or only the guard row of level 0 when there is a single level)
@@ -109,21 +127,58 @@ __global__ void __launch_bounds__(256, PAGK_PYR_MIN_BLOCKS) pagk_pyramid_fused_k
       if (in1) l0[(size_t)y0 * p0 + cols0] = (unsigned char)(b[0] & 0xffu);
       if (in0 && y0 == rows0 - 1) l0[(size_t)y0 * p0 + cols0] = (unsigned char)(a[0] & 0xffu);
       if (in1 && y0 + 1 == rows0 - 1) l0[(size_t)(y0 + 1) * p0 + cols0] = (unsigned char)(b[0] & 0xffu);
+      if (w16) {
+        if (in0 && y0 >= 1) l0h[(size_t)(y0 - 1) * p0 + cols0] = pagk_bf16_of_u8(a[0] & 0xffu);
+        if (in1) l0h[(size_t)y0 * p0 + cols0] = pagk_bf16_of_u8(b[0] & 0xffu);
+        if (in0 && y0 == rows0 - 1) l0h[(size_t)y0 * p0 + cols0] = pagk_bf16_of_u8(a[0] & 0xffu);
+        if (in1 && y0 + 1 == rows0 - 1) l0h[(size_t)(y0 + 1) * p0 + cols0] = pagk_bf16_of_u8(b[0] & 0xffu);
+      }
+    }
+    // the bfloat16 plane of level 0 itself
+    if (w16) {
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const unsigned int *src = r ? b : a;
+        if (!(r ? in1 : in0)) continue;
+        unsigned short *dst = l0h + (size_t)(y0 + r) * p0 + x0;
+        if (vec) {
+          const uint2 q0 = pagk_bf16x4_of_u8x4(src[0]), q1 = pagk_bf16x4_of_u8x4(src[1]), q2 = pagk_bf16x4_of_u8x4(src[2]),
+                      q3 = pagk_bf16x4_of_u8x4(src[3]);
+          reinterpret_cast<uint4 *>(dst)[0] = make_uint4(q0.x, q0.y, q1.x, q1.y);
+          reinterpret_cast<uint4 *>(dst)[1] = make_uint4(q2.x, q2.y, q3.x, q3.y);
+        } else {
+          for (int k = 0; k < 16 && x0 + k < cols0; ++k) dst[k] = pagk_bf16_of_u8((src[k >> 2] >> (8 * (k & 3))) & 0xffu);
+        }
+      }
     }
     // guard row of level 0 = copy of row rows0-1 (+ one byte)
     if (in0 && (y0 == rows0 - 1 || y0 + 1 == rows0 - 1)) {
       const unsigned int *src = (y0 == rows0 - 1) ? a : b;
       unsigned char *gr = l0 + (size_t)rows0 * p0 + x0;
+      unsigned short *grh = l0h + (size_t)rows0 * p0 + x0;
       if (vec) {
         *reinterpret_cast<uint4 *>(gr) = make_uint4(src[0], src[1], src[2], src[3]);
+        if (w16) {
+          const uint2 q0 = pagk_bf16x4_of_u8x4(src[0]), q1 = pagk_bf16x4_of_u8x4(src[1]), q2 = pagk_bf16x4_of_u8x4(src[2]),
+                      q3 = pagk_bf16x4_of_u8x4(src[3]);
+          reinterpret_cast<uint4 *>(grh)[0] = make_uint4(q0.x, q0.y, q1.x, q1.y);
+          reinterpret_cast<uint4 *>(grh)[1] = make_uint4(q2.x, q2.y, q3.x, q3.y);
+        }
       } else {
-        for (int k = 0; k < 16 && x0 + k < cols0; ++k) gr[k] = (unsigned char)(src[k >> 2] >> (8 * (k & 3)));
+        for (int k = 0; k < 16 && x0 + k < cols0; ++k) {
+          gr[k] = (unsigned char)(src[k >> 2] >> (8 * (k & 3)));
+          if (w16) grh[k] = pagk_bf16_of_u8((src[k >> 2] >> (8 * (k & 3))) & 0xffu);
+        }
       }
-      if (x0 == 0) l0[(size_t)rows0 * p0 + cols0] = (unsigned char)(src[0] & 0xffu);
+      if (x0 == 0) {
+        l0[(size_t)rows0 * p0 + cols0] = (unsigned char)(src[0] & 0xffu);
+        if (w16) l0h[(size_t)rows0 * p0 + cols0] = pagk_bf16_of_u8(src[0] & 0xffu);
+      }
     }
     if (n_fused >= 1) {
       const int cols1 = g.lv[1].cols, rows1 = g.lv[1].rows, p1 = g.lv[1].pitch;
       unsigned char *l1 = img + g.lv[1].offset;
+      unsigned short *l1h = w16 ? reinterpret_cast<unsigned short *>(img + g.lv[1].offset16) : nullptr;
       uint2 o;
       o.x = pagk_avg4x8(a[0], b[0]) | (pagk_avg4x8(a[1], b[1]) << 16);
       o.y = pagk_avg4x8(a[2], b[2]) | (pagk_avg4x8(a[3], b[3]) << 16);
@@ -134,30 +189,43 @@ __global__ void __launch_bounds__(256, PAGK_PYR_MIN_BLOCKS) pagk_pyramid_fused_k
         if (vec && x1 + 8 <= cols1) {
           *reinterpret_cast<uint2 *>(dst) = o;
           if (y1 == rows1 - 1) *reinterpret_cast<uint2 *>(dst + p1) = o;
+          if (l1h) {
+            const uint2 q0 = pagk_bf16x4_of_u8x4(o.x), q1 = pagk_bf16x4_of_u8x4(o.y);
+            const uint4 q = make_uint4(q0.x, q0.y, q1.x, q1.y);
+            *reinterpret_cast<uint4 *>(l1h + (size_t)y1 * p1 + x1) = q;
+            if (y1 == rows1 - 1) *reinterpret_cast<uint4 *>(l1h + (size_t)rows1 * p1 + x1) = q;
+          }
         } else {
           for (int k = 0; k < 8 && x1 + k < cols1; ++k) {
             const unsigned char v = (unsigned char)((k < 4 ? o.x : o.y) >> (8 * (k & 3)));
             dst[k] = v;
             if (y1 == rows1 - 1) dst[p1 + k] = v;
+            if (l1h) {
+              const unsigned short v16 = pagk_bf16_of_u8(v);
+              l1h[(size_t)y1 * p1 + x1 + k] = v16;
+              if (y1 == rows1 - 1) l1h[(size_t)rows1 * p1 + x1 + k] = v16;
+            }
           }
         }
-        if (x1 == 0) pagk_write_wrap(l1, p1, cols1, rows1, y1, (unsigned char)(o.x & 0xffu));
+        if (x1 == 0) pagk_write_wrap(l1, l1h, p1, cols1, rows1, y1, (unsigned char)(o.x & 0xffu));
       }
     }
   }
   // ---- level l-1 (shared memory) -> level l, l = 2 .. n_fused: tile sizes are compile-time constants
-  if (n_fused >= 2) pagk_pyramid_tile_level<PYR_TW / 2, PYR_TH / 2>(sbuf[0], sbuf[1], img, g, 2, n_fused, tx0, ty0, t);
+  if (n_fused >= 2) pagk_pyramid_tile_level<PYR_TW / 2, PYR_TH / 2>(sbuf[0], sbuf[1], img, g, 2, n_fused, tx0, ty0, t, w16);
 }
 
 // General half-size cv::resize(INTER_LINEAR) for levels whose source has an odd dimension: the
 // 11-bit fixed-point bilinear of OpenCV.  One thread per output pixel.
 __global__ void __launch_bounds__(256) pagk_pyramid_general_kernel(unsigned char *__restrict__ images, PagkGeom g,
-                                                                 int level, int z_stride) {
+                                                                 int level, int z_stride, int cur_parity) {
   unsigned char *img = images + (size_t)blockIdx.z * z_stride * g.slot_bytes;
+  const bool w16 = g.lv[0].offset16 != 0 && ((blockIdx.z * z_stride + cur_parity) & 1) != 0;
   const int scols = g.lv[level - 1].cols, srows = g.lv[level - 1].rows, sp = g.lv[level - 1].pitch;
   const int dcols = g.lv[level].cols, drows = g.lv[level].rows, dp = g.lv[level].pitch;
   const unsigned char *src = img + g.lv[level - 1].offset;
   unsigned char *dst = img + g.lv[level].offset;
+  unsigned short *d16 = w16 ? reinterpret_cast<unsigned short *>(img + g.lv[level].offset16) : nullptr;
   const int dx = blockIdx.x * blockDim.x + threadIdx.x;
   const int dy = blockIdx.y;
   if (dx >= dcols || dy >= drows) return;
@@ -187,7 +255,12 @@ __global__ void __launch_bounds__(256) pagk_pyramid_general_kernel(unsigned char
   }
   dst[(size_t)dy * dp + dx] = v;
   if (dy == drows - 1) dst[(size_t)drows * dp + dx] = v;
-  if (dx == 0) pagk_write_wrap(dst, dp, dcols, drows, dy, v);
+  if (d16) {
+    const unsigned short v16 = pagk_bf16_of_u8(v);
+    d16[(size_t)dy * dp + dx] = v16;
+    if (dy == drows - 1) d16[(size_t)drows * dp + dx] = v16;
+  }
+  if (dx == 0) pagk_write_wrap(dst, d16, dp, dcols, drows, dy, v);
 }
 
 // =================================================================================================
@@ -1093,7 +1166,7 @@ int pagk_pyramid_fused_max_level() {
   return l;
 }
 
-int pagk_launch_pyramids(unsigned char *images, const PagkGeom &g, int n_images, int z_stride, cudaStream_t st,
+int pagk_launch_pyramids(unsigned char *images, const PagkGeom &g, int n_images, int z_stride, int cur_parity, cudaStream_t st,
                          long long *launches) {
   // levels 1..n_fused form the exact-2x chain and come out of the fused kernel
   int n_fused = 0;
@@ -1102,11 +1175,11 @@ int pagk_launch_pyramids(unsigned char *images, const PagkGeom &g, int n_images,
     else break;
   }
   dim3 grid((g.lv[0].cols + PYR_TW - 1) / PYR_TW, (g.lv[0].rows + PYR_TH - 1) / PYR_TH, n_images);
-  pagk_pyramid_fused_kernel<<<grid, 256, 0, st>>>(images, g, n_fused, z_stride);
+  pagk_pyramid_fused_kernel<<<grid, 256, 0, st>>>(images, g, n_fused, z_stride, cur_parity);
   ++*launches;
   for (int l = n_fused + 1; l < g.levels; ++l) {
     dim3 gg((g.lv[l].cols + 255) / 256, g.lv[l].rows, n_images);
-    pagk_pyramid_general_kernel<<<gg, 256, 0, st>>>(images, g, l, z_stride);
+    pagk_pyramid_general_kernel<<<gg, 256, 0, st>>>(images, g, l, z_stride, cur_parity);
     ++*launches;
   }
   return (int)cudaGetLastError();

@@ -42,6 +42,7 @@
 //
 // Bit-exactness of the window path is argued above the pass loop.
 #include <cstdlib>
+#include <type_traits>
 #include "pagk_device.cuh"
 #include "pagk_kernels.h"
 
@@ -60,6 +61,9 @@ namespace {
 // pairs and more (lane occupancy 0.92, 14 % faster per pair than eight); on config B's 64 pairs a launch is only 16
 // rounds deep for 56 k lanes, the tail and the level hand-overs leave 28 % of the lanes idle, and eight warps are faster.
 // Eight warps also leave a third of the registers to the small kernels of the neighbouring steps (other streams).
+#ifndef PAGK_WIN16
+#define PAGK_WIN16 0
+#endif
 #ifndef PAGK_LANES_WARPS5
 #define PAGK_LANES_WARPS5 8
 #endif
@@ -73,11 +77,18 @@ template <int HALF>
 struct LanesCfg {
   static constexpr int P = 2 * HALF + 1;
   static constexpr int NP = P * P;
-  // window of the current level: rows of WIN_W bytes copied as 4-byte words from a 4-byte aligned origin, so the
-  // usable width for an arbitrary box origin is WIN_W - 3
-  static constexpr int WIN_W = HALF <= 5 ? 24 : 36;
+  // window of the current level: WIN_W x WIN_H elements, copied as 4-byte words from a 4-byte aligned origin: the
+  // origin is a multiple of ALIGN elements and the usable width for any box is WIN_W - (ALIGN - 1).  The elements are
+  // the level's bytes.  -DPAGK_WIN16=1 (11 x 11 patches): the bfloat16 pixels of a 16-bit plane that the pyramid kernel
+  // then writes beside every current image; a tap is one load and one shift instead of a load, an OR and a subtraction
+  // (115 instead of 126 instructions per pixel).  Measured on config B: the passes get 4 % shorter, the pyramid kernel
+  // 14 us longer and the windows twice as large (no room left for the neighbouring steps' kernels): not the default.
+  static constexpr bool W16 = PAGK_WIN16 != 0 && HALF <= 5;
+  static constexpr int ELT = W16 ? 2 : 1;
+  static constexpr int ALIGN = 4 / ELT;
+  static constexpr int WIN_W = HALF > 5 ? 36 : W16 ? 22 : 24;
   static constexpr int WIN_H = P + 6;
-  static constexpr int WPR = WIN_W / 4;  // words per window row
+  static constexpr int WPR = WIN_W * ELT / 4;  // words per window row
   static constexpr int WIN_WORDS = WPR * WIN_H;
   // bytes from one slot's window to the next: an ODD number of words, lane-private windows start in distinct banks
   static constexpr int WIN_STRIDE = (WIN_WORDS | 1) * 4;
@@ -97,7 +108,7 @@ struct LanesCfg {
   static constexpr int SCRATCH_FLOATS = 32 * 3 + 4;
   static constexpr int WARP_BYTES = SLOTS * WIN_STRIDE + SCRATCH_FLOATS * 4;
   static constexpr int SMEM_BYTES = WARPS * WARP_BYTES;
-  static_assert(WIN_W % 4 == 0 && WIN_W - 3 >= P + 4, "window narrower than a sample box");
+  static_assert((WIN_W * ELT) % 4 == 0 && WIN_W - (ALIGN - 1) >= P + 4, "window narrower than a sample box");
   static_assert(CTAS_SM * (SMEM_BYTES + 1024 + 256) <= 228 * 1024, "windows do not fit the SM");
 };
 
@@ -127,8 +138,12 @@ __device__ __forceinline__ void cp_async4(unsigned int dst, const void *src) {
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 // PatchMatch::GetPixelValue (reference src/patch_match.cpp:391-406) with the four taps taken from a staged
 // window with origin (wx0, wy0): the same clamps, the same expression tree.
-template <int WIN_W, int WIN_H>
-__device__ __forceinline__ float window_sample(const unsigned char *__restrict__ win, int wx0, int wy0, float fcols,
+// a window element as float: a byte through the 2^23 trick, a bfloat16 by moving it to the upper half
+__device__ __forceinline__ float elt_f(unsigned char b) { return u8f(b); }
+__device__ __forceinline__ float elt_f(unsigned short h) { return __uint_as_float((unsigned int)h << 16); }
+
+template <int WIN_W, int WIN_H, class E>
+__device__ __forceinline__ float window_sample(const E *__restrict__ win, int wx0, int wy0, float fcols,
                                                float fcm1, float frows, float frm1, float x, float y) {
   if (x < 0.f) x = 0.f;
   if (y < 0.f) y = 0.f;
@@ -138,8 +153,8 @@ __device__ __forceinline__ float window_sample(const unsigned char *__restrict__
   const float fx = floor_nn(x, ix), fy = floor_nn(y, iy);
   const float xx = x - fx, yy = y - fy, wa = 1.0f - xx, wb = 1.0f - yy;
   CHECK_IDX((iy - wy0) * WIN_W + (ix - wx0), 0, WIN_W * WIN_H - WIN_W - 2);
-  const unsigned char *q = win + (iy - wy0) * WIN_W + (ix - wx0);
-  return wb * (wa * u8f(q[0]) + xx * u8f(q[1])) + yy * (wa * u8f(q[WIN_W]) + xx * u8f(q[WIN_W + 1]));
+  const E *q = win + (iy - wy0) * WIN_W + (ix - wx0);
+  return wb * (wa * elt_f(q[0]) + xx * elt_f(q[1])) + yy * (wa * elt_f(q[WIN_W]) + xx * elt_f(q[WIN_W + 1]));
 }
 
 // developer aid (-DPAGK_LANES_PROF): per-warp cycles of every phase, rounds and active lane-rounds -> prof[warp_global][8]
@@ -336,13 +351,14 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
                      long long *__restrict__ prof) {
   using C = LanesCfg<HALF>;
   constexpr int P = C::P, NP = C::NP, WIN_W = C::WIN_W, WIN_H = C::WIN_H;
+  using E = typename std::conditional<C::W16, unsigned short, unsigned char>::type;  // window element
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned char *wwin = smem_raw + (size_t)warp * C::WARP_BYTES;                          // [SLOTS] windows, stride WIN_STRIDE
   float *scratch = reinterpret_cast<float *>(wwin + C::SLOTS * C::WIN_STRIDE);            // [32][3] records, c, 1
   // lanes beyond SLOTS never own a feature; in the lockstep pass they read (harmlessly) the last slot's memory
   const int myslot = lane < C::SLOTS ? lane : C::SLOTS - 1;
-  const unsigned char *mywin = wwin + myslot * C::WIN_STRIDE;
+  const E *mywin = reinterpret_cast<const E *>(wwin + myslot * C::WIN_STRIDE);
   const int total_work = n_pairs * n_max;
   const int top = mode.levels - 1;
   // Work items.  split == 0: an item is a feature (all levels in one lane).  split != 0: an item is one LEVEL of a
@@ -356,12 +372,13 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
   constexpr unsigned FULL = 0xffffffffu;
   // level geometry, indexed by each lane's own level
   __shared__ int s_cols[PAGK_MAX_LEVELS], s_rows[PAGK_MAX_LEVELS], s_pitch[PAGK_MAX_LEVELS];
-  __shared__ unsigned int s_off[PAGK_MAX_LEVELS];
+  __shared__ unsigned int s_off[PAGK_MAX_LEVELS], s_offw[PAGK_MAX_LEVELS];  // u8 level, level the windows come from
   // the two work counters of a handle alternate between launches: this launch zeroes the one the next launch uses
   if (blockIdx.x == 0 && threadIdx.x == 0) *next_counter = 0;
   if (threadIdx.x < PAGK_MAX_LEVELS) {
     s_cols[threadIdx.x] = g.lv[threadIdx.x].cols; s_rows[threadIdx.x] = g.lv[threadIdx.x].rows;
     s_pitch[threadIdx.x] = g.lv[threadIdx.x].pitch; s_off[threadIdx.x] = g.lv[threadIdx.x].offset;
+    s_offw[threadIdx.x] = C::W16 ? g.lv[threadIdx.x].offset16 : g.lv[threadIdx.x].offset;
   }
   __syncthreads();
 
@@ -490,7 +507,7 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
     PROF(0); PROF_ADD(6, 1); PROF_ADD(7, __popc(m_active)); PROF_ADD(2, __popc(__ballot_sync(FULL, waiting)));
 
     const int cols = s_cols[level], rows = s_rows[level], pitch = s_pitch[level];
-    const unsigned char *I2 = images + (size_t)(pair * 2 + 1) * slot_bytes + s_off[level];
+    const unsigned char *I2w = images + (size_t)(pair * 2 + 1) * slot_bytes + s_offw[level];  // the plane the windows come from
     const float fcols = (float)cols, frows = (float)rows, fcm1 = (float)(cols - 1), frm1 = (float)(rows - 1);
 
     // ------------------------------------------------------------------ sample box of this pass (lane = slot)
@@ -510,15 +527,15 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
         const int ixlo = (int)fminf(fmaxf(x2min, 0.0f), fcm1), ixhi = (int)fminf(fmaxf(x1max, 0.0f), fcm1) + 1;
         const int iylo = (int)fminf(fmaxf(y2min, 0.0f), frm1), iyhi = (int)fminf(fmaxf(y1max, 0.0f), frm1) + 1;
         const int needw = ixhi - ixlo + 1, needh = iyhi - iylo + 1;
-        // the window's origin is a multiple of four columns: any box up to WIN_W - 3 wide fits
-        if (needw <= WIN_W - 3 && needh <= WIN_H) {
+        // the window's origin is a multiple of ALIGN columns: any box up to WIN_W - (ALIGN - 1) wide fits
+        if (needw <= WIN_W - (C::ALIGN - 1) && needh <= WIN_H) {
           windowable = true;
           fast = inside;
           const bool ok = win_valid && ixlo >= win_x0 && ixhi <= win_x0 + WIN_W - 1 && iylo >= win_y0 && iyhi <= win_y0 + WIN_H - 1;
           if (!ok) {  // (re)stage, centred on the needed box: 0 <= x0 <= ixlo, x0 + WIN_W - 1 >= ixhi, the same in y;
                       // the rows of a level are followed by at least 32 - rows allocated rows and 64 bytes
             restage = true;
-            nx0 = max((ixlo - (WIN_W - 3 - needw) / 2) & ~3, 0);
+            nx0 = max((ixlo - (WIN_W - (C::ALIGN - 1) - needw) / 2) & ~(C::ALIGN - 1), 0);
             ny0 = max(min(iylo - (WIN_H - needh) / 2, rows + 1 - WIN_H), 0);
           }
         }
@@ -532,12 +549,12 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
         const int s = __ffs(m) - 1;
         m &= m - 1;
         const int x0 = __shfl_sync(FULL, nx0, s), y0 = __shfl_sync(FULL, ny0, s), sp = __shfl_sync(FULL, pitch, s);
-        const unsigned char *src = reinterpret_cast<const unsigned char *>(__shfl_sync(FULL, (unsigned long long)I2, s)) + y0 * sp + x0;
+        const unsigned char *src = reinterpret_cast<const unsigned char *>(__shfl_sync(FULL, (unsigned long long)I2w, s)) + (y0 * sp + x0) * C::ELT;
         const unsigned int dst = smem_u32(wwin + s * C::WIN_STRIDE);
 #pragma unroll
         for (int k = 0; k < (C::WIN_WORDS + 31) / 32; ++k) {
           const int e = lane + 32 * k, r = e / C::WPR, w = e - r * C::WPR;
-          if (e < C::WIN_WORDS) cp_async4(dst + 4u * (unsigned int)e, src + r * sp + 4 * w);
+          if (e < C::WIN_WORDS) cp_async4(dst + 4u * (unsigned int)e, src + r * (sp * C::ELT) + 4 * w);
         }
       }
       if (restage) { win_x0 = nx0; win_y0 = ny0; win_valid = true; }
@@ -592,11 +609,11 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
         badv = fmaxf(badv, fmaxf(xx1, yy1));
         const int widx = (int)((unsigned int)__float_as_int(ty) * (unsigned int)WIN_W + (unsigned int)__float_as_int(tx) - kk);
         CHECK_IDX(widx, WIN_W + 1, WIN_W * WIN_H - 2 * WIN_W - 3);
-        const unsigned char *w = mywin + widx;
-        const float m0 = u8f(w[-WIN_W]), m1 = u8f(w[-WIN_W + 1]);
-        const float c_1 = u8f(w[-1]), c0 = u8f(w[0]), c1 = u8f(w[1]), c2 = u8f(w[2]);
-        const float d_1 = u8f(w[WIN_W - 1]), d0 = u8f(w[WIN_W]), d1 = u8f(w[WIN_W + 1]), d2 = u8f(w[WIN_W + 2]);
-        const float n0 = u8f(w[2 * WIN_W]), n1 = u8f(w[2 * WIN_W + 1]);
+        const E *w = mywin + widx;
+        const float m0 = elt_f(w[-WIN_W]), m1 = elt_f(w[-WIN_W + 1]);
+        const float c_1 = elt_f(w[-1]), c0 = elt_f(w[0]), c1 = elt_f(w[1]), c2 = elt_f(w[2]);
+        const float d_1 = elt_f(w[WIN_W - 1]), d0 = elt_f(w[WIN_W]), d1 = elt_f(w[WIN_W + 1]), d2 = elt_f(w[WIN_W + 2]);
+        const float n0 = elt_f(w[2 * WIN_W]), n1 = elt_f(w[2 * WIN_W + 1]);
         const float Hm = wa * m0 + xx * m1;
         const float H0 = wa * c0 + xx * c1, H0p = wa1 * c1 + xx1 * c2, H0m = wa * c_1 + xx * c0;
         const float H1 = wa * d0 + xx * d1, H1p = wa1 * d1 + xx1 * d2, H1m = wa * d_1 + xx * d0;
@@ -664,8 +681,9 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
         const int scols = __shfl_sync(FULL, cols, s), srows = __shfl_sync(FULL, rows, s), sp = __shfl_sync(FULL, pitch, s);
         const int swx0 = __shfl_sync(FULL, win_x0, s), swy0 = __shfl_sync(FULL, win_y0, s);
         const int swin = __shfl_sync(FULL, (int)windowable, s);
-        const unsigned char *img2 = reinterpret_cast<const unsigned char *>(__shfl_sync(FULL, (unsigned long long)I2, s));
-        const unsigned char *win = wwin + s * C::WIN_STRIDE;
+        const int spair = __shfl_sync(FULL, pair, s), slevel = __shfl_sync(FULL, level, s);
+        const unsigned char *img2 = images + (size_t)(spair * 2 + 1) * slot_bytes + s_off[slevel];  // the u8 level
+        const E *win = reinterpret_cast<const E *>(wwin + s * C::WIN_STRIDE);
         const float *T = reinterpret_cast<const float *>(__shfl_sync(FULL, (unsigned long long)Tg, s));
         const float gc = (float)scols, gr = (float)srows, gc1 = (float)(scols - 1), gr1 = (float)(srows - 1);
         double acc = 0.0;
@@ -797,6 +815,9 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
 }
 
 // -------------------------------------------------------------------------------------------------
+// whether the alignment kernel stages its windows from the 16-bit plane of the current images (build option)
+bool pagk_lk_lanes_win16() { return PAGK_WIN16 != 0; }
+
 bool pagk_lk_lanes_supported(const PagkMode &mode) {
   return (mode.half == 5 || mode.half == 10) && mode.iterations >= 1;
 }

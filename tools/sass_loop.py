@@ -24,7 +24,7 @@ for f in funcs[1:]:
             if tgt < a and tgt in addr2i:
                 body = ins[addr2i[tgt]:i + 1]
                 nd = sum(1 for _, x in body if "DFMA" in x or "DADD" in x)
-                nl = sum(1 for _, x in body if "LDS.U8" in x)
+                nl = sum(1 for _, x in body if "LDS.U8" in x or "LDS.U16" in x)
                 if nd >= 10 and nl >= 12 and (best is None or len(body) < len(best[1])):
                     best = (nd, body)
     print(name, "total instr", len(ins), "bytes", len(ins) * 16)
