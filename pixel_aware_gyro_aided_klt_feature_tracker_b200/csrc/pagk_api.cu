@@ -45,8 +45,9 @@ bool make_geom(int width, int height, int levels, PagkGeom *g) {
   int c = width, r = height;
   for (int l = 0; l < levels; ++l) {
     if (c < 1 || r < 1) return false;
-    // continuous when the rows are 4-byte aligned as they are, else padded with room for the explicit wrap column
-    const int pitch = (c % 4 == 0) ? c : (int)align_up((size_t)c + 1, 4);
+    // rows are 16-byte aligned (TMA tensor maps need that of every stride): continuous when the width allows it, else
+    // padded with room for the explicit wrap column
+    const int pitch = (c % 16 == 0) ? c : (int)align_up((size_t)c + 1, 16);
     g->lv[l].cols = c; g->lv[l].rows = r; g->lv[l].pitch = pitch; g->lv[l].offset = (unsigned int)off;
     // rows + guard row, at least 32 rows, and 64 elements: a staged window may overhang the image (its content is not used)
     off += align_up((size_t)std::max(r + 1, 32) * pitch + 64, 256);
@@ -96,6 +97,9 @@ struct pagk_handle {
   float *d_ntab = nullptr;
   size_t ntab_stride = 0;  // floats per pair
   int *d_work = nullptr;   // work counters of the persistent LK kernel ([16..17])
+  PagkTmaLevels tmaps;              // tensor maps of the u8 levels for the template kernel's tile loads ...
+  PagkGeom tmaps_geom;              // ... of this geometry and patch size (rebuilt when either changes)
+  int tmaps_half = 0;
   unsigned char *d_tmpl = nullptr;  // template records of the alignment kernel, [max_pairs * max_keys][max_levels]
   size_t tmpl_rec = 0;              // bytes per record the buffer was sized for (0: patch size without a lanes kernel)
   int lk_parity = 0;       // which of the two lanes-kernel counters the next launch uses
@@ -286,8 +290,47 @@ int check_batch(pagk_handle *h, int n_pairs, int width, int height, int levels, 
   return PAGK_OK;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (libcuda is not linked)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+// One tensor map per level: x = the padded row (pitch bytes), y = the allocated rows, z = the image slot.  Boxes that
+// overhang the tensor are filled with zeros, so the kernels never clamp a tile's origin.
+int build_tmaps(pagk_handle *h, int half) {
+  if (h->tmaps_half == half && std::memcmp(&h->tmaps_geom, &h->geom, sizeof(PagkGeom)) == 0) return PAGK_OK;
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) return fail(PAGK_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  int bw = 0, bh = 0;
+  pagk_lk_lanes_tma_box(half, &bw, &bh);
+  std::memset(&h->tmaps, 0, sizeof(h->tmaps));
+  for (int l = 0; l < h->geom.levels; ++l) {
+    const PagkLevelGeom &L = h->geom.lv[l];
+    const cuuint64_t dims[3] = {(cuuint64_t)L.pitch, (cuuint64_t)std::max(L.rows + 1, 32), (cuuint64_t)(2 * h->cfg.max_pairs)};
+    const cuuint64_t strides[2] = {(cuuint64_t)L.pitch, (cuuint64_t)h->geom.slot_bytes};
+    const cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    const CUresult r = enc(&h->tmaps.lv[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, h->d_images + L.offset, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { h->tmaps_half = 0; return fail(PAGK_ERR_CUDA, "cuTensorMapEncodeTiled failed"); }
+  }
+  h->tmaps_geom = h->geom; h->tmaps_half = half;
+  return PAGK_OK;
+}
+
 int launch_lk_kernel(pagk_handle *h, const PagkOutPtrs &o, const PagkMode &m, int n_max, int n_pairs) {
   if (h->lk_kernel == 0 && pagk_lk_lanes_supported(m) && h->d_tmpl && pagk_lk_lanes_record_bytes(m.half) <= h->tmpl_rec) {
+    if (build_tmaps(h, m.half) != PAGK_OK) return (int)cudaErrorUnknown;
     // PAGK_LK_TIMELINE=<file> with a -DPAGK_LANES_PROF build: per-warp phase cycles (developer aid)
     if (h->d_dbg) CU(cudaMemsetAsync(h->d_dbg, 0, 2048 * 8 * sizeof(long long), h->stream));
     if (++h->lk_epoch >= 0x0fffffff) {  // the epoch is about to repeat: forget every progress word written so far
@@ -295,7 +338,7 @@ int launch_lk_kernel(pagk_handle *h, const PagkOutPtrs &o, const PagkMode &m, in
       h->lk_epoch = 1;
     }
     const int rc = pagk_launch_lk_lanes(h->d_images, h->geom, h->d_pc, h->d_keys_un, o, m, h->cfg.max_keys, n_max, n_pairs,
-                                        h->d_work + 16, h->lk_parity, h->d_progress, h->lk_epoch, h->n_sms, h->d_tmpl,
+                                        h->d_work + 16, h->lk_parity, h->d_progress, h->lk_epoch, h->n_sms, h->d_tmpl, &h->tmaps,
                                         h->stream, &h->launches, h->d_dbg);
     if (rc == 0 && n_max > 0 && n_pairs > 0) h->lk_parity ^= 1;
     if (h->d_dbg && rc == 0) {

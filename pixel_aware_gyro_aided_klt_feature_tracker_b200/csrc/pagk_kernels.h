@@ -1,6 +1,12 @@
 // pagk_kernels.h -- host-side launch wrappers of the kernels in pagk_kernels.cu
 #pragma once
+#include <cuda.h>  // CUtensorMap (the type only: the driver entry point is looked up at run time)
 #include "pagk_device.cuh"
+
+// one TMA tensor map per pyramid level: the level with its padding as (x, y), the image slot as z
+struct PagkTmaLevels {
+  CUtensorMap lv[PAGK_MAX_LEVELS];
+};
 
 int pagk_pyramid_fused_max_level();
 // image z of the launch lives in slot z * z_stride (1: every slot, 2: every other one, i.e. only the current images);
@@ -56,7 +62,8 @@ int pagk_lk_lanes_configure();
 bool pagk_lk_lanes_supported(const PagkMode &mode);
 bool pagk_lk_lanes_win16();
 size_t pagk_lk_lanes_record_bytes(int half);
+void pagk_lk_lanes_tma_box(int half, int *box_w, int *box_h);
 int pagk_launch_lk_lanes(const unsigned char *images, const PagkGeom &g, const PagkPairConst *pcs, const float2 *keys_un,
                          const PagkOutPtrs &out, const PagkMode &mode, int max_keys, int n_max, int n_pairs,
                          int *work_counters, int parity, int *progress, int epoch, int n_sms, unsigned char *tmpl,
-                         cudaStream_t st, long long *launches, long long *prof);
+                         const PagkTmaLevels *tmaps, cudaStream_t st, long long *launches, long long *prof);

@@ -136,6 +136,31 @@ __device__ __forceinline__ void cp_async4(unsigned int dst, const void *src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// ---- TMA tile loads (cp.async.bulk.tensor; SASS: UTMALDG) and the mbarrier they complete on (SYNCS) ----
+__device__ __forceinline__ void mbar_init(unsigned int bar, unsigned int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned int bar, unsigned int bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned int bar, unsigned int parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+// box of a 3-D tensor (x, y: a pyramid level with its padding; z: the image slot) -> shared memory, rows dense.
+// Coordinates may lie outside the tensor: those elements arrive as zeros (and are never sampled).
+__device__ __forceinline__ void tma_load_3d(unsigned int dst, const CUtensorMap *map, int x, int y, int z, unsigned int bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+               "l"(reinterpret_cast<unsigned long long>(map)), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
+}
+
 // PatchMatch::GetPixelValue (reference src/patch_match.cpp:391-406) with the four taps taken from a staged
 // window with origin (wx0, wy0): the same clamps, the same expression tree.
 // a window element as float: a byte through the 2^23 trick, a bfloat16 by moving it to the upper half
@@ -184,27 +209,31 @@ struct Sums {
 
 // =================================================================================================
 // K3a: the template records.  One warp per 32 consecutive (pair, feature, level) items.  Lane j decodes item j (one
-// coalesced load of the keypoints); the warp then stages the raw (P+2) x (P+2) tap block of the reference image of
-// G items at a time into shared memory with 4-byte asynchronous copies (lanes = words, the next group's copies in
-// flight while this group is computed), and for each item lanes = pixels compute T (the reference's GetPixelValue on
-// the reference image, src/patch_match.cpp:253, :263) from the staged taps and store it.  Lane j finally runs item j's
-// ordered sum of c*c (the h22 entry of the normal matrix, the same for every iteration of the level:
-// src/patch_match.cpp:296 with J[2] = c) and writes the record's tail.
+// coalesced load of the keypoints) and fetches the item's raw (P+2) x (P+2) tap block of the reference image with ONE
+// TMA tile load (UTMALDG: a box of the level's 3-D tensor at an arbitrary byte position, completion on the warp's
+// mbarrier); then for each item lanes = pixels compute T (the reference's GetPixelValue on the reference image,
+// src/patch_match.cpp:253, :263) from the staged taps and store it.  Lane j finally runs item j's ordered sum of c*c
+// (the h22 entry of the normal matrix, the same for every iteration of the level: src/patch_match.cpp:296 with
+// J[2] = c) and writes the record's tail.
 // =================================================================================================
 template <int HALF>
 struct TmplCfg {
   static constexpr int P = 2 * HALF + 1;
   // floor(fl(pt + x)) is floor(pt) + x, or one more when the sum is rounded up across a binade: taps span P + 2 columns
-  // and rows from floor(pt) - HALF; the staged rows start at the 4-byte aligned column below
+  // and rows from floor(pt) - HALF.  A TMA box starts at a 16-byte aligned byte of the row (a tile load whose innermost
+  // coordinate is not a multiple of 16 bytes faults: measured, tools/probes/tma_probe2.cu), so the box is the aligned
+  // ROW_BYTES around those columns x ROWS.
   static constexpr int ROWS = P + 2;
-  static constexpr int ROW_BYTES = (3 + P + 2 + 3) & ~3;
-  static constexpr int RWORDS = ROW_BYTES / 4;
-  static constexpr int WORDS = ROWS * RWORDS;
-  static constexpr int G = HALF <= 5 ? 8 : 4;  // items staged together, twice (double buffer): 26 / 40 KB per CTA
+  static constexpr int ROW_BYTES = (15 + P + 2 + 15) & ~15;
+  static constexpr int BOX_BYTES = ROWS * ROW_BYTES;
+  static constexpr int ITEM_BYTES = (BOX_BYTES + 127) & ~127;  // TMA destinations are 128-byte aligned
+  static constexpr int G = HALF <= 5 ? 16 : 8;                 // items fetched together: 8 / 9 KB per warp
+  static constexpr int WARPS = 4;
 };
 
 template <int HALF>
-__global__ void __launch_bounds__(256) pagk_lk_template_kernel(const unsigned char *__restrict__ images, PagkGeom g,
+__global__ void __launch_bounds__(TmplCfg<HALF>::WARPS * 32) pagk_lk_template_kernel(const unsigned char *__restrict__ images, PagkGeom g,
+                                                             const __grid_constant__ PagkTmaLevels maps,
                                                              const PagkPairConst *__restrict__ pcs,
                                                              const float2 *__restrict__ keys_un, int levels, int max_keys,
                                                              int n_max, int n_pairs, unsigned char *__restrict__ tmpl) {
@@ -212,22 +241,32 @@ __global__ void __launch_bounds__(256) pagk_lk_template_kernel(const unsigned ch
   using TC = TmplCfg<HALF>;
   constexpr int P = C::P, NP = C::NP, TK = (NP + 31) / 32, G = TC::G, RB = TC::ROW_BYTES;
   constexpr unsigned FULL = 0xffffffffu;
-  __shared__ __align__(16) unsigned char s_raw[8][2][G][TC::WORDS * 4];
+  __shared__ __align__(128) unsigned char s_raw[TC::WARPS][G][TC::ITEM_BYTES];
+  __shared__ __align__(8) unsigned long long s_bar[TC::WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long wg = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  const long long wg = (long long)blockIdx.x * TC::WARPS + warp;
   const long long total = (long long)n_pairs * n_max * levels, base = wg * 32;
   if (base >= total) return;
+  const unsigned int mbar = smem_u32(&s_bar[warp]);
+  if (lane == 0) {
+    mbar_init(mbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  unsigned int phase = 0;
   const float hf = (float)HALF;
   float tpx[TK], tpy[TK];
+  int toff[TK];  // tap offset of pixel p inside the staged block when nothing is rounded: py * RB + px
 #pragma unroll
   for (int k = 0; k < TK; ++k) {
-    const int p = lane + 32 * k, py = p / P;
-    tpx[k] = (float)(p - py * P - HALF); tpy[k] = (float)(py - HALF);
+    const int p = lane + 32 * k, py = p / P, px = p - py * P;
+    tpx[k] = (float)(px - HALF); tpy[k] = (float)(py - HALF);
+    toff[k] = py * RB + px;
   }
   // ---- lane j: item j
-  bool valid = false, tin = false;
+  bool valid = false, tin = false, uni = false;
   float ptx = 0.f, pty = 0.f;
-  int cols = 1, rows = 1, pitch = 4, wx0 = 0, wy0 = 0;
+  int cols = 1, rows = 1, pitch = 4, wx0 = 0, wy0 = 0, lv = 0, slot = 0;
   const unsigned char *img1 = images;
   unsigned char *rec = nullptr;
   {
@@ -235,64 +274,70 @@ __global__ void __launch_bounds__(256) pagk_lk_template_kernel(const unsigned ch
     const int per_pair = n_max * levels;
     if (idx < total) {
       const int pr = (int)(idx / per_pair), rem = (int)(idx - (long long)pr * per_pair);
-      const int i = rem / levels, lv = rem - i * levels;
+      const int i = rem / levels;
+      lv = rem - i * levels;
       if (i < pcs[pr].n_keys) {
         valid = true;
+        slot = pr * 2;
         const size_t o = (size_t)pr * max_keys + i;
         const float2 p1 = keys_un[o];
         const float scale = 1.0f / (float)(1 << lv);
         ptx = p1.x * scale; pty = p1.y * scale;  // pt = mvKeysRefUn[i].pt * mvScales[level] (:177)
         cols = g.lv[lv].cols; rows = g.lv[lv].rows; pitch = g.lv[lv].pitch;
-        img1 = images + (size_t)(pr * 2) * g.slot_bytes + g.lv[lv].offset;
+        img1 = images + (size_t)slot * g.slot_bytes + g.lv[lv].offset;
         rec = tmpl + (o * (size_t)levels + lv) * C::REC_BYTES;
         const float txlo = ptx + (-hf), txhi = ptx + hf, tylo = pty + (-hf), tyhi = pty + hf;
-        // no clamp of GetPixelValue fires anywhere in the template
-        tin = txlo >= 0.0f && txhi < (float)cols && tylo >= 0.0f && tyhi < (float)rows;
-        if (tin) { wx0 = (int)txlo & ~3; wy0 = (int)tylo; }  // pt - HALF is exact: floor(pt) - HALF
+        // no clamp of GetPixelValue fires anywhere in the template, and no tap lies in column `cols`: in a continuous
+        // level that column is the next row's first byte, which a tile of the (x, y, slot) tensor does not see
+        tin = txlo >= 0.0f && txhi < (float)(cols - 1) && tylo >= 0.0f && tyhi < (float)rows;
+        if (tin) {
+          wx0 = (int)txlo; wy0 = (int)tylo;  // pt - HALF is exact: floor(pt) - HALF (the box starts at wx0 & ~15)
+          // pt + HALF exact (the difference below is exact by Sterbenz: pt >= HALF) <=> every pt + x, |x| <= HALF, is
+          // exact: all pixels then share the fractions of pt and pixel (px, py) has its taps at (wx0 + px, wy0 + py)
+          uni = (txhi - ptx == hf) && (tyhi - pty == hf);
+        }
       }
     }
   }
-  auto stage = [&](int gi) {  // the tap blocks of items gi * G .. gi * G + G - 1 -> buffer gi & 1
-#pragma unroll 1
-    for (int jj = 0; jj < G; ++jj) {
-      const int j = gi * G + jj;
-      const int go = __shfl_sync(FULL, (int)(valid && tin), j);
-      const int sp = __shfl_sync(FULL, pitch, j), sx0 = __shfl_sync(FULL, wx0, j), sy0 = __shfl_sync(FULL, wy0, j);
-      const int rmax = __shfl_sync(FULL, rows, j) - sy0;  // rows past the guard row are never sampled: copy the guard row again
-      const unsigned char *src = reinterpret_cast<const unsigned char *>(__shfl_sync(FULL, (unsigned long long)img1, j)) + sy0 * sp + sx0;
-      if (!go) continue;
-      const unsigned int dst = smem_u32(&s_raw[warp][gi & 1][jj][0]);
-#pragma unroll
-      for (int k = 0; k < (TC::WORDS + 31) / 32; ++k) {
-        const int e = lane + 32 * k, r = e / TC::RWORDS, w = e - r * TC::RWORDS;
-        if (e < TC::WORDS) cp_async4(dst + 4u * (unsigned int)e, src + min(r, rmax) * sp + 4 * w);
-      }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
   float myc = 0.f, mylast = 0.f;
-  stage(0);
 #pragma unroll 1
-  for (int gi = 0; gi < 32 / G; ++gi) {
-    if (gi + 1 < 32 / G) {
-      stage(gi + 1);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
+  for (int g0 = 0; g0 < 32; g0 += G) {
+    // ---- the tap blocks of items g0 .. g0 + G - 1: every owner lane issues its own tile load
+    const bool mine = lane >= g0 && lane < g0 + G && valid && tin;
+    const unsigned int mm = __ballot_sync(FULL, mine);
+    if (mm) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the blocks were read through the generic proxy
+      if (lane == 0) mbar_expect_tx(mbar, (unsigned int)TC::BOX_BYTES * (unsigned int)__popc(mm));
+      __syncwarp();
+      if (mine) tma_load_3d(smem_u32(&s_raw[warp][lane - g0][0]), &maps.lv[lv], wx0 & ~15, wy0, slot, mbar);
+      mbar_wait(mbar, phase);
+      phase ^= 1u;
     }
     __syncwarp();
 #pragma unroll 1
     for (int jj = 0; jj < G; ++jj) {
-      const int j = gi * G + jj;
+      const int j = g0 + jj;
       if (!__shfl_sync(FULL, (int)valid, j)) continue;
-      const int stin = __shfl_sync(FULL, (int)tin, j);
+      const int kind = __shfl_sync(FULL, (int)tin + (int)uni, j);  // 0: clamps may fire, 1: per-pixel weights, 2: shared weights
       const float sptx = __shfl_sync(FULL, ptx, j), spty = __shfl_sync(FULL, pty, j);
       float *T = reinterpret_cast<float *>(__shfl_sync(FULL, (unsigned long long)rec, j));
+      // the tap of column x, row y sits at (y - wy0) * RB + (x - (wx0 & ~15))
+      const int sx0 = __shfl_sync(FULL, wx0, j), sy0 = __shfl_sync(FULL, wy0, j);
+      const unsigned char *raw = &s_raw[warp][jj][0] + (sx0 & 15);
       float tv[TK];
-      if (stin) {
-        // floor by a round-down add of 2^23 (exact for 0 <= x < 2^22), u8 -> float without the conversion pipe
-        const int sx0 = __shfl_sync(FULL, wx0, j), sy0 = __shfl_sync(FULL, wy0, j);
-        const unsigned char *raw = &s_raw[warp][gi & 1][jj][0];
+      if (kind == 2) {
+        // floor by a round-down add of 2^23 (exact for 0 <= x < 2^22)
+        const float xx = sptx - (__fadd_rd(sptx, 8388608.0f) - 8388608.0f), yy = spty - (__fadd_rd(spty, 8388608.0f) - 8388608.0f);
+        const float wa = 1.0f - xx, wb = 1.0f - yy;
+#pragma unroll
+        for (int k = 0; k < TK; ++k) {
+          tv[k] = 0.f;
+          if (lane + 32 * k < NP) {
+            const unsigned char *q = raw + toff[k];
+            tv[k] = wb * (wa * u8f(q[0]) + xx * u8f(q[1])) + yy * (wa * u8f(q[RB]) + xx * u8f(q[RB + 1]));
+          }
+        }
+      } else if (kind == 1) {
 #pragma unroll
         for (int k = 0; k < TK; ++k) {
           const float cx = sptx + tpx[k], cy = spty + tpy[k];
@@ -301,7 +346,7 @@ __global__ void __launch_bounds__(256) pagk_lk_template_kernel(const unsigned ch
           const int ix = __float_as_int(tx) - 0x4B000000, iy = __float_as_int(ty) - 0x4B000000;
           tv[k] = 0.f;
           if (lane + 32 * k < NP) {
-            CHECK_IDX((iy - sy0) * RB + (ix - sx0), 0, TC::WORDS * 4 - RB - 2);
+            CHECK_IDX((iy - sy0) * RB + (ix - sx0) + (sx0 & 15), 0, TC::BOX_BYTES - RB - 2);
             const unsigned char *q = raw + (iy - sy0) * RB + (ix - sx0);
             tv[k] = wb * (wa * u8f(q[0]) + xx * u8f(q[1])) + yy * (wa * u8f(q[RB]) + xx * u8f(q[RB + 1]));
           }
@@ -822,6 +867,12 @@ bool pagk_lk_lanes_supported(const PagkMode &mode) {
   return (mode.half == 5 || mode.half == 10) && mode.iterations >= 1;
 }
 
+// the box of the tensor maps the template kernel loads its tap blocks with
+void pagk_lk_lanes_tma_box(int half, int *box_w, int *box_h) {
+  *box_w = half == 5 ? TmplCfg<5>::ROW_BYTES : TmplCfg<10>::ROW_BYTES;
+  *box_h = half == 5 ? TmplCfg<5>::ROWS : TmplCfg<10>::ROWS;
+}
+
 size_t pagk_lk_lanes_record_bytes(int half) {
   return half == 5 ? (size_t)LanesCfg<5>::REC_BYTES : half == 10 ? (size_t)LanesCfg<10>::REC_BYTES : 0;
 }
@@ -854,13 +905,14 @@ template <int HALF, bool AFFINE>
 static int launch_lanes(const unsigned char *images, const PagkGeom &g, const PagkPairConst *pcs, const float2 *keys_un,
                         const PagkOutPtrs &out, const PagkMode &mode, int max_keys, int n_max, int n_pairs,
                         int *work_counter, int *next_counter, int *progress, int epoch, int n_sms, unsigned char *tmpl,
-                        cudaStream_t st, long long *prof) {
+                        const PagkTmaLevels *tmaps, cudaStream_t st, long long *prof) {
   using C = LanesCfg<HALF>;
   const long long total = (long long)n_max * n_pairs;
-  {  // K3a: 8 warps per CTA, 32 items per warp
+  {  // K3a: 32 items per warp
+    constexpr int W = TmplCfg<HALF>::WARPS;
     const long long items = total * mode.levels, groups = (items + 31) / 32;
-    pagk_lk_template_kernel<HALF><<<(unsigned)((groups + 7) / 8), 256, 0, st>>>(images, g, pcs, keys_un, mode.levels, max_keys, n_max,
-                                                                               n_pairs, tmpl);
+    pagk_lk_template_kernel<HALF><<<(unsigned)((groups + W - 1) / W), W * 32, 0, st>>>(images, g, *tmaps, pcs, keys_un, mode.levels, max_keys,
+                                                                                      n_max, n_pairs, tmpl);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
   }
@@ -886,17 +938,17 @@ static int launch_lanes(const unsigned char *images, const PagkGeom &g, const Pa
 int pagk_launch_lk_lanes(const unsigned char *images, const PagkGeom &g, const PagkPairConst *pcs, const float2 *keys_un,
                          const PagkOutPtrs &out, const PagkMode &mode, int max_keys, int n_max, int n_pairs,
                          int *work_counters, int parity, int *progress, int epoch, int n_sms, unsigned char *tmpl,
-                         cudaStream_t st, long long *launches, long long *prof) {
+                         const PagkTmaLevels *tmaps, cudaStream_t st, long long *launches, long long *prof) {
   if (n_max <= 0 || n_pairs <= 0) return 0;
   // work_counters[0..1]: both zero when the handle is created; launch n uses [n & 1] and zeroes the other one
   int *work_counter = work_counters + (parity & 1), *next_counter = work_counters + ((parity + 1) & 1);
   int rc;
   if (mode.half == 5) {
-    rc = mode.affine ? launch_lanes<5, true>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, next_counter, progress, epoch, n_sms, tmpl, st, prof)
-                     : launch_lanes<5, false>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, next_counter, progress, epoch, n_sms, tmpl, st, prof);
+    rc = mode.affine ? launch_lanes<5, true>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, next_counter, progress, epoch, n_sms, tmpl, tmaps, st, prof)
+                     : launch_lanes<5, false>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, next_counter, progress, epoch, n_sms, tmpl, tmaps, st, prof);
   } else {
-    rc = mode.affine ? launch_lanes<10, true>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, next_counter, progress, epoch, n_sms, tmpl, st, prof)
-                     : launch_lanes<10, false>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, next_counter, progress, epoch, n_sms, tmpl, st, prof);
+    rc = mode.affine ? launch_lanes<10, true>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, next_counter, progress, epoch, n_sms, tmpl, tmaps, st, prof)
+                     : launch_lanes<10, false>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, next_counter, progress, epoch, n_sms, tmpl, tmaps, st, prof);
   }
   *launches += 2;
   return rc;
