@@ -31,9 +31,17 @@ METRIC = "tracked features/sec at 752x480, 1024 feats, 4 levels; px error vs CPU
 # algorithmic work of one feature-iteration at an 11x11 patch
 FP32_FLOP_PER_FEATURE_ITER = {5: 8.5e3, 10: 30.9e3}
 HBM_BYTES_PER_FEATURE_ITER = 120.0
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the LK kernel on this workload, from the committed
-# `ncu --set full` capture (profiles/r01_ncu_summary.md): 48.91 MB + 2.80 MB
-LK_DRAM_TRAFFIC_BYTES_PER_LAUNCH = {("B", 64): 51.72e6}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the patch-alignment kernels on a workload: NOT measured in this
+# run; read from the committed summary of the `ncu --set full` capture (profiles/r02_k3_traffic.json), null when absent
+def profiled_traffic(cfg_name, n_pairs):
+    p = os.path.join(ROOT, "profiles", "r02_k3_traffic.json")
+    try:
+        with open(p) as f:
+            d = json.load(f)
+        e = d.get(f"{cfg_name}/{n_pairs}")
+        return (e["bytes_per_launch"], "profiles/r02_k3_traffic.json: " + e["note"]) if e else (None, None)
+    except Exception:
+        return None, None
 N_ROTATE = 3  # resident batches per GPU; 3 x 61 MB of pyramids > 126 MB L2
 E2E_DEPTH = 5  # handles (streams) the end-to-end leg rotates over: uploads, kernels and downloads of 5 batches in flight
 
@@ -186,8 +194,10 @@ def run_reference(args, rank, world):
         return
     oracle, kind, kind_note = cpu_arm()
     cores = os.cpu_count() or 1
-    sample_pairs = args.ref_pairs
-    batches, cfg = make_batches(args.config, sample_pairs, 1, 1000 * (ord(args.config) - 64), False)
+    sample_pairs = args.ref_pairs or args.pairs or min(synth.CONFIGS[args.config]["pairs"], 64)
+    distinct = min(sample_pairs, 16)   # generating synthetic pairs is the slow part: the batch repeats 16 distinct pairs
+    batches, cfg = make_batches(args.config, distinct, 1, 1000 * (ord(args.config) - 64), False)
+    batches[0]["pairs"] = [batches[0]["pairs"][i % distinct] for i in range(sample_pairs)]
     pairs = batches[0]["pairs"]
     prm = capi.default_params(pyramids=cfg["pyramids"], half_patch=cfg["half_patch"])
     for _ in range(max(1, args.warmup // 3)):
@@ -203,7 +213,7 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "features/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
-            "config": {"workload": workload_name(args.config, cfg, sample_pairs), "sample": True},
+            "config": {"workload": workload_name(args.config, cfg, sample_pairs)},
             "feature_iterations_per_sec": iters / dt,
             "cpu_baseline": {"value": v, "unit": "features/s", "cores": cores, "kind": kind, "kind_note": kind_note,
                              "sample": f"{sample_pairs} frame pairs per step x {args.steps} steps, {cores} std::threads over features"},
@@ -281,6 +291,104 @@ def stream_leg(args, cfg, prm, n_streams, new_ctx, barrier, world):
     return res
 
 
+def bind_to_gpu_numa_node(index: int):
+    """run this process (its pinned allocations are first-touched by it) on the CPUs NVML names as local to the GPU"""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
+def run_threads(args):
+    """--threads: one process, one host thread per GPU, every thread with its own handles on its own device (include/pagk.h:
+    "one handle per device; handles on different devices are independent").  Resident and end-to-end legs, reduced line."""
+    import torch
+    from pixel_aware_gyro_aided_klt_feature_tracker_b200 import tracker
+    n_dev = args.gpus
+    if torch.cuda.device_count() < n_dev:
+        raise SystemExit(f"bench.py --threads: {n_dev} GPUs asked for, {torch.cuda.device_count()} visible")
+    cfgd = synth.CONFIGS[args.config]
+    n_pairs = args.pairs or min(cfgd["pairs"], 64)
+    batches, cfg = make_batches(args.config, n_pairs, N_ROTATE, 1000 * (ord(args.config) - 64), True)
+    N, half = cfg["n_keys"], cfg["half_patch"]
+    prm = capi.default_params(pyramids=cfg["pyramids"], half_patch=half)
+    e2e_steps = args.e2e_steps or max(3, min(args.steps, 30))
+    gate = threading.Barrier(n_dev)
+    res = [None] * n_dev
+
+    def worker(d):
+        mk = lambda: tracker.Context(device=d, max_width=cfg["width"], max_height=cfg["height"], max_keys=N, max_pairs=n_pairs,
+                                     max_levels=cfg["pyramids"], max_half_patch=half)
+        pctx = [mk() for _ in range(N_ROTATE)]
+        for c, b in zip(pctx, batches):
+            c.upload(b["pairs"], prm)
+            c.set_stage_timing(False)
+        for k in range(max(3, args.warmup) + N_ROTATE):
+            pctx[k % N_ROTATE].run()
+        for c in pctx:
+            c.synchronize()
+        gate.wait()
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            pctx[k % N_ROTATE].run()
+        for c in pctx:
+            c.synchronize()
+        dt = time.perf_counter() - t0
+        ectx = [mk() for _ in range(E2E_DEPTH)]
+        for c in ectx:
+            c.set_stage_timing(False)
+        oblocks = [OutBlock(n_pairs, N) for _ in range(E2E_DEPTH)]
+        ins = [capi.make_in_array(batches[j % N_ROTATE]["pairs"]) for j in range(E2E_DEPTH)]
+        oarrs = [capi.make_out_array(ob.outs) for ob in oblocks]
+
+        def loop(steps):
+            inflight = [False] * E2E_DEPTH
+            for k in range(steps):
+                j = k % E2E_DEPTH
+                if inflight[j]:
+                    ectx[j].wait()
+                ectx[j].submit_prepared(prm, ins[j], oarrs[j], n_pairs)
+                inflight[j] = True
+            for j in range(E2E_DEPTH):
+                if inflight[j]:
+                    ectx[j].wait()
+        loop(E2E_DEPTH + 2)
+        gate.wait()
+        t0 = time.perf_counter()
+        loop(e2e_steps)
+        dte = time.perf_counter() - t0
+        res[d] = (dt, dte, int(oarrs[0][0].n_predict))
+        for c in pctx + ectx:
+            c.close()
+    ths = [threading.Thread(target=worker, args=(d,)) for d in range(n_dev)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    if any(r is None for r in res):
+        raise SystemExit("bench.py --threads: a device thread failed")
+    dt, dte = max(r[0] for r in res), max(r[1] for r in res)
+    feats = n_pairs * N
+    b0 = batches[0]
+    emit({"metric": METRIC, "value": n_dev * args.steps * feats / dt, "unit": "features/s", "n_gpus": n_dev, "steps": args.steps,
+          "warmup": max(3, args.warmup), "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+          "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic", "config": {"workload": workload_name(args.config, cfg, n_pairs)},
+          "mode": "one process, one host thread and one set of handles per GPU (--threads)",
+          "e2e": {"value": n_dev * e2e_steps * feats / dte, "unit": "features/s",
+                  "h2d_bytes_per_step": int(b0["imgs"].nbytes + b0["keys"].nbytes + n_pairs * 96), "steps": e2e_steps,
+                  "tracked_in_first_pair": [r[2] for r in res]}})
+
+
 def workload_name(name, cfg, n_pairs):
     return (f"config {name}: {cfg['width']}x{cfg['height']}, {cfg['n_keys']} features/pair, {cfg['pyramids']} levels, "
             f"{2 * cfg['half_patch'] + 1}x{2 * cfg['half_patch'] + 1} patch, eType 4, {n_pairs} frame pairs/step")
@@ -294,12 +402,16 @@ def main():
     ap.add_argument("--impl", default="pagk", choices=["pagk", "reference"])
     ap.add_argument("--config", default="B", choices=list(synth.CONFIGS))
     ap.add_argument("--pairs", type=int, default=None, help="frame pairs per step (default: the config's batch, 64 for B)")
-    ap.add_argument("--ref-pairs", type=int, default=8, help="frame pairs per step of the CPU reference arm")
+    ap.add_argument("--ref-pairs", type=int, default=None,
+                    help="frame pairs per step of the CPU reference arm (default: the same batch as the CUDA arm, 64 for config B)")
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity leg")
-    ap.add_argument("--stream", action="store_true",
-                    help="extra leg `e2e_stream`: the same end-to-end pipeline over camera streams (BASELINE config D's unit): each "
-                         "step tracks frame t against frame t-1 of every stream, whose pyramid stayed on the device")
+    ap.add_argument("--no-stream", action="store_true",
+                    help="skip the leg `e2e_stream` (the end-to-end pipeline over camera streams, BASELINE config D's unit: each step "
+                         "tracks frame t against frame t-1 of every stream, whose pyramid stayed on the device)")
+    ap.add_argument("--threads", action="store_true",
+                    help="ONE process, one host thread and one set of handles per GPU (the in-process form of include/pagk.h) "
+                         "instead of one process per GPU: prints a reduced line (value, e2e, e2e_stream)")
     args = ap.parse_args()
 
     claim_stdout()
@@ -309,6 +421,9 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+    if args.threads:
+        run_threads(args)
+        return
 
     import torch
     import torch.distributed as dist
@@ -316,6 +431,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the pagk hot path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    numa_cpus = bind_to_gpu_numa_node(local_rank) if world > 1 else None   # pinned buffers on the GPU's own NUMA node
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -449,7 +565,7 @@ def main():
     h2d = int(b0["imgs"].nbytes + b0["keys"].nbytes + n_pairs * 96)
     d2h = int(oblocks[0].nbytes + n_pairs * 24)
 
-    e2e_stream = stream_leg(args, cfg, prm, n_pairs, new_ctx, barrier, world) if args.stream else None
+    e2e_stream = None if args.no_stream else stream_leg(args, cfg, prm, n_pairs, new_ctx, barrier, world)
 
     if world > 1:
         dist.barrier()
@@ -465,10 +581,10 @@ def main():
     fp32_peak = 148 * 128 * 2 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12  # TFLOP/s with FMA, nominal lanes x clock
     ach = it_launch * FP32_FLOP_PER_FEATURE_ITER.get(half, 70.0 * (2 * half + 1) ** 2) / (lk_avg_ms * 1e-3) / 1e12
     hbm_ach = it_launch * HBM_BYTES_PER_FEATURE_ITER / (lk_avg_ms * 1e-3) / 1e9
-    roofline = {"bound": "fp32", "kernel": "pagk_lk_lanes_kernel", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
+    roofline = {"bound": "fp32", "kernel": "pagk_lk_template_kernel + pagk_lk_lanes_kernel (K3a + K3b, one event pair around both)", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
                 "frac": ach / fp32_peak, "frac_of_non_fma_peak": ach / (fp32_peak / 2),
-                "traffic": LK_DRAM_TRAFFIC_BYTES_PER_LAUNCH.get((args.config, n_pairs)),
-                "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                "traffic": profiled_traffic(args.config, n_pairs)[0], "traffic_from_profile": profiled_traffic(args.config, n_pairs)[1],
+                "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum; not measured in this run)",
                 "algorithmic_flop_per_feature_iteration": FP32_FLOP_PER_FEATURE_ITER.get(half, 70.0 * (2 * half + 1) ** 2),
                 "peak_source": f"148 SM x 128 lanes x 2 x {peaks.get('sm_max_mhz', 1965.0):.0f} MHz ({peaks_kind} sm_max_mhz); "
                                "FMA contraction is forbidden by bit-parity, so half of it is the reachable ceiling",
@@ -518,16 +634,16 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": "features/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": 1e3 * dt_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
-            "config": {"workload": workload_name(args.config, cfg, n_pairs),
-                       "l2": f"{N_ROTATE} rotating resident batches per GPU ({(N_ROTATE * 2 * n_pairs * cfg['width'] * cfg['height'] * 4 // 3) >> 20} MiB of pyramids) > 126 MB L2",
+            "config": {"workload": workload_name(args.config, cfg, n_pairs)},
+            "method": {"l2": f"{N_ROTATE} rotating resident batches per GPU ({(N_ROTATE * 2 * n_pairs * cfg['width'] * cfg['height'] * 4 // 3) >> 20} MiB of pyramids) > 126 MB L2",
                        "timing": f"wall clock around K back-to-back steps over {N_ROTATE} resident batches, each on its own handle and stream (consecutive steps overlap on the device), barrier + device synchronize on both sides, max over ranks; `serial` repeats the K steps on one in-order stream, and the kernel ms of `roofline` are CUDA events around every LK launch of that serial leg; stage_ms from one untimed run with per-stage events on"},
             "feature_iterations_per_sec": fi_per_s,
             "serial": {"ms_per_step": 1e3 * dt_serial / args.steps, "value": world * args.steps * feats_per_step / dt_serial,
                        "unit": "features/s", "clocks": clocks_serial,
                        "note": "the same steps on ONE in-order stream (no overlap between steps): the leg the kernel events of `roofline` and `stage_ms` come from"},
-            "stage_ms": stage_ms, "clocks": clocks,
+            "stage_ms": stage_ms, "clocks": clocks, "host_cpus_bound_to_gpu_numa_node": numa_cpus,
             "e2e": {"value": e2e_value, "unit": "features/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "results_ok": bool(e2e_ok),
+                    "steps": e2e_steps, "results_ok": bool(e2e_ok), "d2h_fields": [f[0] for f in OutBlock.FIELDS] + ["n_predict", "n_iterations", "Rcl"],
                     "api": f"pagk_submit_batch/pagk_wait_batch over {E2E_DEPTH} handles (pinned host buffers in and out, pagk_set_stage_timing off)"},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity}
     if e2e_stream is not None:

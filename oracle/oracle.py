@@ -40,6 +40,8 @@ def load():
         lib.pagk_oracle_get_pixel_value.restype = C.c_float
         lib.pagk_oracle_llt_solve.argtypes = [_f64p, _f64p, _f64p]
         lib.pagk_oracle_llt_solve.restype = None
+        lib.pagk_oracle_set_llt_variant.argtypes = [C.c_int]
+        lib.pagk_oracle_set_llt_variant.restype = None
         lib.pagk_oracle_affine_from_corners.argtypes = [_f32p, C.c_int, _f32p]
         lib.pagk_oracle_affine_from_corners.restype = None
         lib.pagk_oracle_integrate_gyro.argtypes = [C.POINTER(capi.PagkPairIn), _f32p, _f32p]
@@ -89,6 +91,11 @@ def get_pixel_value(img: np.ndarray, x: float, y: float) -> float:
     img = np.ascontiguousarray(img, np.uint8)
     h, w = img.shape
     return float(load().pagk_oracle_get_pixel_value(img.ctypes.data_as(_u8p), w, h, img.strides[0], x, y))
+
+
+def set_llt_variant(v: int) -> None:
+    """sensitivity study only (tools/eigen_variants.py): 0 = the oracle proper, 1..6 = one other plausible association"""
+    load().pagk_oracle_set_llt_variant(int(v))
 
 
 def llt_solve(H: np.ndarray, b: np.ndarray) -> np.ndarray:

@@ -402,25 +402,51 @@ int gyro_predict_features(const Cam &c, const float Rcl[9], const float M[9], in
 // m[r][c]; only the lower triangle is read.  The factorisation stops at the first pivot <= 0 and
 // leaves the rest untouched; solve() still runs on the partial factor, exactly as Eigen does.
 // ---------------------------------------------------------------------------------------------
+// Sensitivity study only (tools/eigen_variants.py): Eigen is not in the container, so the operation
+// order above is a restatement of Eigen 3.3.4 from memory.  g_llt_variant != 0 switches ONE association to the other
+// plausible reading so that the effect of a misreading can be measured; 0 is the order every parity claim refers to.
+//   1  pivot:    (m_kk - m_k0^2) - m_k1^2 ...  instead of  m_kk - (m_k0^2 + m_k1^2 + ...)
+//   2  column update:  m_ik - (m_i0 m_k0 + m_i1 m_k1 ...)  (dot product first) instead of column by column
+//   3  forward substitution sums left to right instead of the scalar tree a0 + (a1 + a2)
+//   4  backward substitution sums as a0 + (a1 + a2) instead of the packet order (a0 + a1) + a2
+//   5  norm(): ((u0^2 + u1^2) + u2^2) + u3^2 instead of the packet order (u0^2 + u2^2) + (u1^2 + u3^2)
+//   6  all of 1..5 together
+static int g_llt_variant = 0;
+
 void llt_solve4(const double Hin[4][4], const double bin[4], double x[4]) {
+  const int V = g_llt_variant;
+  const bool v1 = V == 1 || V == 6, v2 = V == 2 || V == 6, v3 = V == 3 || V == 6, v4 = V == 4 || V == 6;
   double m[4][4];
   memcpy(m, Hin, sizeof(m));
   for (int k = 0; k < 4; ++k) {
     const int rs = 3 - k;
     double piv = m[k][k];
     if (k > 0) {
-      double s = m[k][0] * m[k][0];
-      for (int j = 1; j < k; ++j) s = s + m[k][j] * m[k][j];
-      piv -= s;
+      if (v1) {
+        for (int j = 0; j < k; ++j) piv -= m[k][j] * m[k][j];
+      } else {
+        double s = m[k][0] * m[k][0];
+        for (int j = 1; j < k; ++j) s = s + m[k][j] * m[k][j];
+        piv -= s;
+      }
     }
     if (piv <= 0.0) break;
     piv = std::sqrt(piv);
     m[k][k] = piv;
-    if (k > 0 && rs > 0)
-      for (int j = 0; j < k; ++j) {
-        const double t = -1.0 * m[k][j];
-        for (int i = k + 1; i < 4; ++i) m[i][k] += m[i][j] * t;
+    if (k > 0 && rs > 0) {
+      if (v2) {
+        for (int i = k + 1; i < 4; ++i) {
+          double d = m[i][0] * m[k][0];
+          for (int j = 1; j < k; ++j) d = d + m[i][j] * m[k][j];
+          m[i][k] -= d;
+        }
+      } else {
+        for (int j = 0; j < k; ++j) {
+          const double t = -1.0 * m[k][j];
+          for (int i = k + 1; i < 4; ++i) m[i][k] += m[i][j] * t;
+        }
       }
+    }
     for (int i = k + 1; i < 4; ++i) m[i][k] /= piv;
   }
   double r[4] = {bin[0], bin[1], bin[2], bin[3]};
@@ -430,7 +456,8 @@ void llt_solve4(const double Hin[4][4], const double bin[4], double x[4]) {
   r[1] /= m[1][1];
   r[2] -= (m[2][0] * r[0] + m[2][1] * r[1]);
   r[2] /= m[2][2];
-  r[3] -= (m[3][0] * r[0] + (m[3][1] * r[1] + m[3][2] * r[2]));
+  if (v3) r[3] -= ((m[3][0] * r[0] + m[3][1] * r[1]) + m[3][2] * r[2]);
+  else r[3] -= (m[3][0] * r[0] + (m[3][1] * r[1] + m[3][2] * r[2]));
   r[3] /= m[3][3];
   // L^T x = y
   r[3] /= m[3][3];
@@ -438,7 +465,8 @@ void llt_solve4(const double Hin[4][4], const double bin[4], double x[4]) {
   r[2] /= m[2][2];
   r[1] -= (m[2][1] * r[2] + m[3][1] * r[3]);
   r[1] /= m[1][1];
-  r[0] -= ((m[1][0] * r[1] + m[2][0] * r[2]) + m[3][0] * r[3]);
+  if (v4) r[0] -= (m[1][0] * r[1] + (m[2][0] * r[2] + m[3][0] * r[3]));
+  else r[0] -= ((m[1][0] * r[1] + m[2][0] * r[2]) + m[3][0] * r[3]);
   r[0] /= m[0][0];
   x[0] = r[0]; x[1] = r[1]; x[2] = r[2]; x[3] = r[3];
 }
@@ -577,7 +605,9 @@ void one_pixel(PM &pm, int level, int i) {
     if (pm.illum) { dg += up[2]; db += up[3]; }
     lastCost = cost;
     succ = true;
-    const double nrm = std::sqrt((up[0] * up[0] + up[2] * up[2]) + (up[1] * up[1] + up[3] * up[3]));
+    const double nrm = (g_llt_variant == 5 || g_llt_variant == 6)
+                           ? std::sqrt(((up[0] * up[0] + up[1] * up[1]) + up[2] * up[2]) + up[3] * up[3])
+                           : std::sqrt((up[0] * up[0] + up[2] * up[2]) + (up[1] * up[1] + up[3] * up[3]));
     if (nrm < 1e-2) break;
   }
   pm.pt2[i].x = pt.x + dx;
@@ -980,6 +1010,9 @@ float pagk_oracle_get_pixel_value(const uint8_t *img, int cols, int rows, int pi
   level_from_image(img, cols, rows, pitch, L);
   return get_pixel_value(L, x, y);
 }
+
+// sensitivity study switch (see llt_solve4); not thread-safe against running track calls, 0 restores the oracle proper
+void pagk_oracle_set_llt_variant(int v) { g_llt_variant = v; }
 
 void pagk_oracle_llt_solve(const double *H16, const double *b4, double *x4) {
   double H[4][4];

@@ -282,7 +282,8 @@ def test_reference_shaped_classes(gpu_ctx, oracle):
 
 
 def test_large_patch_generic_kernel(gpu_ctx, oracle):
-    """21 x 21 patches (BASELINE config C's patch size) run on the any-patch-size kernel"""
+    """21 x 21 patches (BASELINE config C's patch size): pagk_lk_lanes_kernel<10, *>, 28 slots per warp (the full-size config C
+    and a 2048-feature case with level-granular items are in tests/test_baseline_configs.py)"""
     p = synth.make_pair(7800, width=480, height=360, n_keys=150, half_patch=10, pyramids=3, border=40,
                         K=synth.scaled_euroc_K(480))
     prm = capi.default_params(pyramids=3, half_patch=10)
