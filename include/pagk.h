@@ -299,12 +299,27 @@ int pagk_fast_detect(pagk_handle *h, const uint8_t *img, int width, int height, 
  * ComputeKeyPointsOctTree :789-876), as Frame::DetectKeyPoints uses it to top keypoints up (src/frame.cpp:155-219): the
  * image inside a 16-pixel border is cut into cells of about 30 pixels, every cell runs cv::FAST with non-maximum suppression
  * at ini_th and, if that yields nothing, at min_th; keypoints on a zero mask byte are dropped (:1200-1203).  Keypoints come
- * back cell by cell (cells row-major, row-major inside a cell).  NOT included: DistributeOctTree, which thins the set to
- * nfeatures -- its node order is sorted with pointer values as tie-break (src/ORBextractor.cc:706-707), so its selection is
- * not reproducible even between two runs of the reference; with nfeatures above the candidate count it keeps every keypoint,
+ * back cell by cell (cells row-major, row-major inside a cell).  The thinning to nfeatures (DistributeOctTree) is
+ * pagk_distribute_octtree / pagk_orb_detect_features below; with nfeatures above the candidate count it keeps every keypoint,
  * which is how the tests compare this call with the reference's own DetectFeatures. */
 int pagk_orb_cell_detect(pagk_handle *h, const uint8_t *img, int width, int height, int pitch, int ini_th, int min_th,
                          const uint8_t *mask, int max_out, float *xy, float *response, int *n_out);
+
+/* == ORBextractor::DistributeOctTree (src/ORBextractor.cc:563-787): thins candidates to about n_features keypoints, one per
+ * leaf of a quadtree over [min_x, max_x) x [min_y, max_y), the strongest corner of each leaf.  xy are RELATIVE to (min_x,
+ * min_y) as ComputeKeyPointsOctTree hands them over (:846-851).  Host code (a serial walk over a linked list of nodes; needs
+ * no device and no handle).  Same splitting rule, list order and early exit as the reference; nodes of EQUAL size are split
+ * in the order of their upper-left corner where the reference compares node addresses (:706-707).  out_index receives the
+ * indices of the kept candidates in the reference's output order; *n_out their number (at most n). */
+int pagk_distribute_octtree(int n, const float *xy, const float *response, int min_x, int max_x, int min_y, int max_y,
+                            int n_features, int *out_index, int *n_out);
+
+/* == ORBextractor(n_features, 1.2, 1, ini_th, min_th).DetectFeatures(img, mask) (src/ORBextractor.cc:1148-1205): the keypoint
+ * top-up of Frame::DetectKeyPoints (src/frame.cpp:155-219) for one pyramid level: per-cell FAST on the device
+ * (pagk_orb_cell_detect without a mask), DistributeOctTree down to n_features (pagk_distribute_octtree), then the mask filter
+ * of :1200-1203, in that order as in the reference. */
+int pagk_orb_detect_features(pagk_handle *h, const uint8_t *img, int width, int height, int pitch, int n_features, int ini_th,
+                             int min_th, const uint8_t *mask, int max_out, float *xy, float *response, int *n_out);
 
 /* == cv::remap(src, dst, map_x, map_y, cv::INTER_LINEAR) on CV_8UC1 with CV_32FC1 maps and the default constant (0) border:
  * the rectification both drivers run on every frame before tracking (Examples/Demo/RealSenseD435i.cpp:202,

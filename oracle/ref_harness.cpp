@@ -415,6 +415,32 @@ int pagk_ref_orb_detect(const uint8_t *img, int width, int height, int pitch, co
   return PAGK_OK;
 }
 
+// ORBextractor::DistributeOctTree itself (src/ORBextractor.cc:563-787; protected, reached through a derived class) on
+// caller-given candidates relative to (min_x, min_y): indices of the kept candidates in its output order.  The index travels
+// in cv::KeyPoint::class_id, which the function copies along with the keypoint.
+namespace {
+struct OctTreeAccess : public ORB_SLAM2::ORBextractor {
+  OctTreeAccess(int n) : ORB_SLAM2::ORBextractor(n, 1.2f, 1, 20, 7) {}
+  std::vector<cv::KeyPoint> run(const std::vector<cv::KeyPoint> &k, int minX, int maxX, int minY, int maxY, int N) {
+    return DistributeOctTree(k, minX, maxX, minY, maxY, N, 0);
+  }
+};
+}  // namespace
+int pagk_ref_distribute_octtree(int n, const float *xy, const float *response, int min_x, int max_x, int min_y, int max_y,
+                                int n_features, int *out_index, int *n_out) {
+  std::vector<cv::KeyPoint> keys((size_t)n);
+  for (int k = 0; k < n; ++k) {
+    keys[(size_t)k].pt = cv::Point2f(xy[2 * k], xy[2 * k + 1]);
+    keys[(size_t)k].response = response[k];
+    keys[(size_t)k].class_id = k;
+  }
+  OctTreeAccess ex(n_features);
+  const std::vector<cv::KeyPoint> out = ex.run(keys, min_x, max_x, min_y, max_y, n_features);
+  *n_out = (int)out.size();
+  for (size_t k = 0; k < out.size(); ++k) out_index[k] = out[k].class_id;
+  return PAGK_OK;
+}
+
 // PatchMatch(&tracker, ...).OpticalFlowMultiLevel() on caller-given predictions, status and deformation matrices
 int pagk_ref_patch_match(const pagk_patch_match_in *in, pagk_pair_out *out, int n_threads) {
   cv::shim_num_threads() = n_threads > 0 ? n_threads : 1;

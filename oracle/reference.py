@@ -87,8 +87,20 @@ def load():
         lib.pagk_ref_set_predict_keypoints_and_mask.argtypes = [C.c_int, C.POINTER(capi.PagkCarryIn), C.POINTER(capi.PagkCarryOut)]
         lib.pagk_ref_orb_detect.argtypes = [C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int,
                                             C.c_int, _f32p, _f32p, C.POINTER(C.c_int)]
+        lib.pagk_ref_distribute_octtree.argtypes = [C.c_int, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int),
+                                                    C.POINTER(C.c_int)]
         _lib = lib
     return _lib
+
+
+def distribute_octtree(xy, response, min_x, max_x, min_y, max_y, n_features):
+    """ORBextractor::DistributeOctTree (src/ORBextractor.cc:563-787) on candidates relative to (min_x, min_y): kept indices"""
+    xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+    rs = np.ascontiguousarray(response, np.float32).reshape(-1)
+    idx, n = np.zeros(max(1, len(rs)), np.int32), C.c_int(0)
+    load().pagk_ref_distribute_octtree(len(rs), xy.ctypes.data_as(_f32p), rs.ctypes.data_as(_f32p), int(min_x), int(max_x), int(min_y),
+                                       int(max_y), int(n_features), idx.ctypes.data_as(C.POINTER(C.c_int)), C.byref(n))
+    return idx[:n.value].copy()
 
 
 def last_path() -> int:

@@ -192,6 +192,10 @@ SYMBOLS = {
                                    C.POINTER(C.c_int)]),
     "pagk_orb_cell_detect": (C.c_int, [_H, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u8p, C.c_int, _f32p, _f32p,
                                        C.POINTER(C.c_int)]),
+    "pagk_distribute_octtree": (C.c_int, [C.c_int, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int),
+                                          C.POINTER(C.c_int)]),
+    "pagk_orb_detect_features": (C.c_int, [_H, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u8p, C.c_int, _f32p, _f32p,
+                                           C.POINTER(C.c_int)]),
     "pagk_set_rectify_maps": (C.c_int, [_H, _f32p, _f32p, C.c_int, C.c_int]),
     "pagk_remap_linear": (C.c_int, [_H, _u8p, C.c_int, C.c_int, C.c_int, _f32p, _f32p, C.c_int, C.c_int, _u8p]),
     "pagk_set_predict_keypoints_and_mask": (C.c_int, [_H, C.c_int, C.POINTER(PagkCarryIn), C.POINTER(PagkCarryOut)]),

@@ -13,6 +13,7 @@
 #include "../../include/pagk.h"
 #include "pagk_host_math.h"
 #include "pagk_kernels.h"
+#include "pagk_octree.h"
 
 #include <algorithm>
 #include <cstdio>
@@ -1055,6 +1056,44 @@ int pagk_orb_cell_detect(pagk_handle *h, const uint8_t *img, int width, int heig
     CU(cudaStreamSynchronize(st));
   }
   *n_out = total_found;
+  return PAGK_OK;
+}
+
+int pagk_distribute_octtree(int n, const float *xy, const float *response, int min_x, int max_x, int min_y, int max_y,
+                            int n_features, int *out_index, int *n_out) {
+  if (n < 0 || !n_out || (n > 0 && (!xy || !response || !out_index))) return fail(PAGK_ERR_INVALID, "null argument");
+  const std::vector<int> keep = pagk_octree::distribute(xy, response, n, min_x, max_x, min_y, max_y, n_features);
+  for (size_t k = 0; k < keep.size(); ++k) out_index[k] = keep[k];
+  *n_out = (int)keep.size();
+  return PAGK_OK;
+}
+
+int pagk_orb_detect_features(pagk_handle *h, const uint8_t *img, int width, int height, int pitch, int n_features, int ini_th,
+                             int min_th, const uint8_t *mask, int max_out, float *xy, float *response, int *n_out) {
+  if (!h || !img || !n_out || max_out < 0 || (max_out > 0 && (!xy || !response))) return fail(PAGK_ERR_INVALID, "null argument");
+  *n_out = 0;
+  // every candidate of the per-cell FAST (no mask: the reference filters AFTER the thinning, :1200-1203)
+  int cap = 1 << 16, found = 0;
+  std::vector<float> cxy, crs;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    cxy.assign((size_t)cap * 2, 0.f); crs.assign((size_t)cap, 0.f);
+    const int rc = pagk_orb_cell_detect(h, img, width, height, pitch, ini_th, min_th, nullptr, cap, cxy.data(), crs.data(), &found);
+    if (rc != PAGK_OK) return rc;
+    if (found <= cap) break;
+    cap = found;
+  }
+  const int EDGE_THRESHOLD = 19;  // src/ORBextractor.cc:65; ComputeKeyPointsOctTree :797-800
+  const int min_x = EDGE_THRESHOLD - 3, min_y = min_x, max_x = width - EDGE_THRESHOLD + 3, max_y = height - EDGE_THRESHOLD + 3;
+  for (int k = 0; k < found; ++k) { cxy[2 * (size_t)k] -= (float)min_x; cxy[2 * (size_t)k + 1] -= (float)min_y; }
+  const std::vector<int> keep = pagk_octree::distribute(cxy.data(), crs.data(), found, min_x, max_x, min_y, max_y, n_features);
+  int n = 0;
+  for (int k : keep) {
+    const float x = cxy[2 * (size_t)k] + (float)min_x, y = cxy[2 * (size_t)k + 1] + (float)min_y;  // :866-867
+    if (mask && !mask[(size_t)(int)y * width + (int)x]) continue;
+    if (n < max_out) { xy[2 * n] = x; xy[2 * n + 1] = y; response[n] = crs[(size_t)k]; }
+    ++n;
+  }
+  *n_out = n;
   return PAGK_OK;
 }
 

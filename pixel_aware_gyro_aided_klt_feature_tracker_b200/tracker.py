@@ -28,6 +28,18 @@ def _check(lib, rc: int):
         raise PagkError(rc, lib.pagk_last_error().decode("utf-8", "replace"))
 
 
+def distribute_octtree(xy, response, min_x, max_x, min_y, max_y, n_features, lib=None):
+    """ORBextractor::DistributeOctTree on candidates relative to (min_x, min_y): indices of the kept ones (host code, no device)"""
+    lib = lib or capi.load()
+    xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+    rs = np.ascontiguousarray(response, np.float32).reshape(-1)
+    idx, n = np.zeros(max(1, len(rs)), np.int32), C.c_int(0)
+    f32 = C.POINTER(C.c_float)
+    _check(lib, lib.pagk_distribute_octtree(len(rs), xy.ctypes.data_as(f32), rs.ctypes.data_as(f32), int(min_x), int(max_x), int(min_y),
+                                            int(max_y), int(n_features), idx.ctypes.data_as(C.POINTER(C.c_int)), C.byref(n)))
+    return idx[:n.value].copy()
+
+
 class Context:
     """One pagk_handle = the device workspace of one GPU (images, keypoints, results)."""
 
@@ -137,6 +149,20 @@ class Context:
         _check(self.lib, self.lib.pagk_orb_cell_detect(self.handle, img.ctypes.data_as(u8), w, h, img.strides[0], int(ini_th), int(min_th),
                                                        None if m is None else m.ctypes.data_as(u8), max_out, xy.ctypes.data_as(f32),
                                                        rs.ctypes.data_as(f32), C.byref(n)))
+        k = min(n.value, max_out)
+        return xy[:k].copy(), rs[:k].copy()
+
+    def orb_detect_features(self, img, n_features, ini_th=20, min_th=7, mask=None, max_out=100000):
+        """ORBextractor(n_features, 1.2, 1, ini_th, min_th).DetectFeatures(img, mask), one level (include/pagk.h)"""
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape
+        xy, rs, n = np.zeros((max_out, 2), np.float32), np.zeros(max_out, np.float32), C.c_int(0)
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        u8 = C.POINTER(C.c_uint8)
+        f32 = C.POINTER(C.c_float)
+        _check(self.lib, self.lib.pagk_orb_detect_features(self.handle, img.ctypes.data_as(u8), w, h, img.strides[0], int(n_features),
+                                                           int(ini_th), int(min_th), None if m is None else m.ctypes.data_as(u8), max_out,
+                                                           xy.ctypes.data_as(f32), rs.ctypes.data_as(f32), C.byref(n)))
         k = min(n.value, max_out)
         return xy[:k].copy(), rs[:k].copy()
 
