@@ -229,12 +229,17 @@ int pagk_gyro_predict(pagk_handle *h, const pagk_params *prm, const pagk_pair_in
  * inputs; fills pm_pt_un, pm_pt, pm_status, pixel_error, distance, ncc, iters of `out`. */
 int pagk_patch_match(pagk_handle *h, const pagk_patch_match_in *in, pagk_pair_out *out);
 
-/* == GyroAidedTracker::GeometryValidation() without its two RANSAC estimators (src/gyro_aided_tracker.cpp:429-508,
- * CheckHomography :589-678, CheckFundamental :680-768): the step both reference drivers run right after TrackFeatures().
- * The caller supplies H21 / F21 -- what cv::findHomography(vPts1, vPts2, RANSAC, 3) and
- * cv::findFundamentalMat(vPts1, vPts2, FM_RANSAC, 3., 0.99) returned for the status-1 correspondences -- and gets the
- * symmetric-transfer / epipolar chi-square scoring, the model choice RH = SH / (SH + SF) > 0.45 and the outlier marking.
- * (OpenCV's RANSAC draws from its own RNG; no from-scratch estimator can reproduce its models, so they stay with the caller.)
+/* == GyroAidedTracker::GeometryValidation() (src/gyro_aided_tracker.cpp:429-508, CheckHomography :589-678,
+ * CheckFundamental :680-768): the step both reference drivers run right after TrackFeatures(): two robust models of the
+ * status-1 correspondences, the symmetric-transfer / epipolar chi-square scoring, the model choice
+ * RH = SH / (SH + SF) > 0.45 and the outlier marking.
+ *   estimate == 0  the caller supplies H21 / F21 -- what cv::findHomography(vPts1, vPts2, RANSAC, 3) and
+ *                  cv::findFundamentalMat(vPts1, vPts2, FM_RANSAC, 3., 0.99) returned -- and everything after them is
+ *                  bit-exact against the reference's own functions.
+ *   estimate != 0  H21 / F21 are ignored: the device estimates both (csrc/pagk_ransac.h: RANSAC over 1024 hypotheses each
+ *                  from a counter-based generator seeded with `seed`, refit on the inliers, same 3 px tests as OpenCV) and
+ *                  the whole step stays on the device.  OpenCV's hypotheses come from OpenCV's own RNG, so these models
+ *                  are not OpenCV's bit for bit: they are accepted statistically (tests/test_ransac.py).
  * keys_ref_un / pt_predict_un / status NULL: use the vectors of the handle's last run, resident on the device. */
 typedef struct pagk_geometry_in {
   int n_keys;
@@ -244,6 +249,9 @@ typedef struct pagk_geometry_in {
   double H21[9];              /* row-major 3x3, CV_64F as cv::findHomography returns it */
   double F21[9];
   float sigma;                /* 1.0 in the reference (:447) */
+  int estimate;               /* 0: H21 / F21 given; 1: estimated on the device */
+  unsigned int seed;          /* of the hypothesis generator when estimate != 0 */
+  int reserved;
 } pagk_geometry_in;
 
 typedef struct pagk_geometry_out {
@@ -253,6 +261,8 @@ typedef struct pagk_geometry_out {
   int used_H;        /* 1: RH > 0.45, the homography's inliers were kept; 0: the fundamental matrix's */
   int n_candidates;  /* vPts1.size(): features with status 1 before the call */
   int n_inlier;      /* return value of GeometryValidation() (0 when n_candidates <= 8: nothing is validated) */
+  double H21[9];     /* the models that were scored (the caller's, or the device's estimates) */
+  double F21[9];
 } pagk_geometry_out;
 
 int pagk_geometry_validation(pagk_handle *h, int n_pairs, const pagk_geometry_in *in, pagk_geometry_out *out);

@@ -171,9 +171,11 @@ class GyroAidedTracker {
   }
 
   // int GeometryValidation(), reference :429-508.  The reference estimates H21 / F21 itself with cv::findHomography and
-  // cv::findFundamentalMat (OpenCV RANSAC); here the caller passes what those two calls returned for the status-1
-  // correspondences (mvKeysRefUn[i].pt -> mvPtPredictUn[i]) and the scoring, model choice and outlier marking run on the GPU.
-  int GeometryValidation(const double H21[9], const double F21[9], float sigma = 1.0f) {
+  // cv::findFundamentalMat (OpenCV RANSAC).  GeometryValidation() does the same on the device (pagk's own RANSAC: not
+  // OpenCV's models bit for bit); GeometryValidation(H21, F21) takes what those two OpenCV calls returned for the status-1
+  // correspondences (mvKeysRefUn[i].pt -> mvPtPredictUn[i]); scoring, model choice and outlier marking run on the GPU.
+  int GeometryValidation(unsigned int seed = 1, float sigma = 1.0f) { return GeometryValidation(nullptr, nullptr, sigma, seed); }
+  int GeometryValidation(const double H21[9], const double F21[9], float sigma = 1.0f, unsigned int seed = 1) {
     pagk_geometry_in gi;
     std::vector<float> k1((size_t)mN * 2), k2((size_t)mN * 2);
     for (int i = 0; i < mN; ++i) {
@@ -181,8 +183,8 @@ class GyroAidedTracker {
       k2[2 * (size_t)i] = mvPtPredictUn[(size_t)i].x; k2[2 * (size_t)i + 1] = mvPtPredictUn[(size_t)i].y;
     }
     gi.n_keys = mN; gi.keys_ref_un = k1.data(); gi.pt_predict_un = k2.data(); gi.status = mvStatus.data();
-    for (int i = 0; i < 9; ++i) { gi.H21[i] = H21[i]; gi.F21[i] = F21[i]; }
-    gi.sigma = sigma;
+    for (int i = 0; i < 9; ++i) { gi.H21[i] = H21 ? H21[i] : 0.0; gi.F21[i] = F21 ? F21[i] : 0.0; }
+    gi.sigma = sigma; gi.estimate = (H21 && F21) ? 0 : 1; gi.seed = seed; gi.reserved = 0;
     std::vector<uint8_t> st((size_t)mN);
     pagk_geometry_out go;
     go.status = st.data();

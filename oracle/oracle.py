@@ -19,9 +19,8 @@ _u8p, _f32p, _f64p = C.POINTER(C.c_uint8), C.POINTER(C.c_float), C.POINTER(C.c_d
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "pagk_oracle.cpp")
-    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src):
-        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    # make knows the dependencies (the source, its headers and include/pagk.h: a changed struct must rebuild the checker)
+    subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
     return LIB
 
 

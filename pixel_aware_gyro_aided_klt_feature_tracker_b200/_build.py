@@ -8,7 +8,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 SOURCES = ["pagk_kernels.cu", "pagk_lk_lanes.cu", "pagk_api.cu"]
-HEADERS = ["pagk_device.cuh", "pagk_kernels.h", "pagk_host_math.h", "pagk_octree.h", os.path.join("..", "..", "include", "pagk.h")]
+HEADERS = ["pagk_device.cuh", "pagk_kernels.h", "pagk_host_math.h", "pagk_octree.h", "pagk_ransac.h", os.path.join("..", "..", "include", "pagk.h")]
 OUT = os.path.join(CSRC, "libpagk_cuda.so")
 # the same library with the index traps of the LK lanes kernel compiled in (-DPAGK_LANES_CHECK): test infrastructure,
 # selected with PAGK_LIB=<this path>; compute-sanitizer is not available on the GPU pool

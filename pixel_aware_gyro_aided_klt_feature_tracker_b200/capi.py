@@ -80,18 +80,23 @@ class PagkPatchMatchIn(C.Structure):
 
 class PagkGeometryIn(C.Structure):
     _fields_ = [("n_keys", C.c_int), ("keys_ref_un", _f32p), ("pt_predict_un", _f32p), ("status", _u8p),
-                ("H21", C.c_double * 9), ("F21", C.c_double * 9), ("sigma", C.c_float)]
+                ("H21", C.c_double * 9), ("F21", C.c_double * 9), ("sigma", C.c_float), ("estimate", C.c_int),
+                ("seed", C.c_uint), ("reserved", C.c_int)]
 
 
 class PagkGeometryOut(C.Structure):
     _fields_ = [("status", _u8p), ("score_H", C.c_float), ("score_F", C.c_float), ("used_H", C.c_int),
-                ("n_candidates", C.c_int), ("n_inlier", C.c_int)]
+                ("n_candidates", C.c_int), ("n_inlier", C.c_int), ("H21", C.c_double * 9), ("F21", C.c_double * 9)]
 
 
 class GeometryCase:
     """One GeometryValidation() call in numpy form: correspondences, status, the two models; owns the output status."""
 
-    def __init__(self, keys_ref_un, pt_predict_un, status, H21, F21, sigma=1.0):
+    def __init__(self, keys_ref_un, pt_predict_un, status, H21=None, F21=None, sigma=1.0, estimate=False, seed=1):
+        # H21 / F21 None with estimate=True: the device estimates both models (include/pagk.h)
+        self.estimate, self.seed = bool(estimate), int(seed)
+        H21 = np.eye(3) if H21 is None else H21
+        F21 = np.zeros((3, 3)) if F21 is None else F21
         self.keys_ref_un = None if keys_ref_un is None else np.ascontiguousarray(keys_ref_un, np.float32).reshape(-1, 2)
         self.pt_predict_un = None if pt_predict_un is None else np.ascontiguousarray(pt_predict_un, np.float32).reshape(-1, 2)
         self.status = None if status is None else np.ascontiguousarray(status, np.uint8).reshape(-1)
@@ -111,6 +116,7 @@ class GeometryCase:
         i.H21[:] = self.H21.reshape(-1).tolist()
         i.F21[:] = self.F21.reshape(-1).tolist()
         i.sigma = self.sigma
+        i.estimate, i.seed, i.reserved = int(self.estimate), self.seed, 0
         o.status = _ptr(self.out_status, _u8p)
         return i, o
 

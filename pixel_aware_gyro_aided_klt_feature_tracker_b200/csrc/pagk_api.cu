@@ -119,6 +119,7 @@ struct pagk_handle {
   int fast_out_cap = 0;
   PagkGeoModel *d_geo = nullptr;    // pagk_geometry_validation: models in, results out (allocated on first use)
   PagkGeoResult *d_geo_res = nullptr;
+  unsigned char *d_ransac = nullptr;  // its estimators: per pair and model an index list and inlier flags, then the estimate flags
   int *d_progress = nullptr;  // lanes kernel, level-granular work items: per feature, epoch * 8 + levels finished
   int lk_epoch = 0;           // launch number of the lanes kernel on this handle (values of earlier launches never match)
   int n_sms = 0;
@@ -479,7 +480,7 @@ void pagk_destroy(pagk_handle *h) {
   if (h->stream && h->own_stream) cudaStreamSynchronize(h->stream);
   else cudaDeviceSynchronize();
   cudaFree(h->d_images); cudaFree(h->d_keys_un); cudaFree(h->d_keys); cudaFree(h->d_pc); cudaFree(h->d_res);
-  cudaFree(h->d_out); cudaFree(h->d_ntab); cudaFree(h->d_work); cudaFree(h->d_tmpl); cudaFree(h->d_progress); cudaFree(h->d_geo); cudaFree(h->d_geo_res); cudaFree(h->d_carry); cudaFree(h->d_mask); cudaFreeHost(h->h_aux); cudaFree(h->d_fast); cudaFree(h->d_fast_out); cudaFree(h->d_remap); cudaFree(h->d_maps); cudaFree(h->d_raw); cudaFree(h->d_dbg);
+  cudaFree(h->d_out); cudaFree(h->d_ntab); cudaFree(h->d_work); cudaFree(h->d_tmpl); cudaFree(h->d_progress); cudaFree(h->d_geo); cudaFree(h->d_geo_res); cudaFree(h->d_ransac); cudaFree(h->d_carry); cudaFree(h->d_mask); cudaFreeHost(h->h_aux); cudaFree(h->d_fast); cudaFree(h->d_fast_out); cudaFree(h->d_remap); cudaFree(h->d_maps); cudaFree(h->d_raw); cudaFree(h->d_dbg);
   cudaFreeHost(h->h_in); cudaFreeHost(h->h_out); cudaFreeHost(h->h_res);
   for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
@@ -897,10 +898,24 @@ int pagk_geometry_validation(pagk_handle *h, int n_pairs, const pagk_geometry_in
     }
   }
   CU(cudaMemcpyAsync(h->d_geo, models.data(), models.size() * sizeof(PagkGeoModel), cudaMemcpyHostToDevice, st));
+  bool any_est = false;
+  for (int p = 0; p < n_pairs; ++p) any_est |= in[p].estimate != 0;
+  if (any_est) {  // the two robust estimators on the device: H21 / H12 / F21 of those pairs are overwritten in d_geo
+    const size_t NK2 = (size_t)2 * h->cfg.max_pairs * h->cfg.max_keys;
+    const size_t off_in = align_up(NK2 * sizeof(int), 256), off_est = off_in + align_up(NK2, 256);
+    if (!h->d_ransac) CU(cudaMalloc(&h->d_ransac, off_est + align_up((size_t)h->cfg.max_pairs, 256)));
+    std::vector<unsigned char> est((size_t)n_pairs);
+    for (int p = 0; p < n_pairs; ++p) est[(size_t)p] = in[p].estimate != 0 ? 1 : 0;
+    CU(cudaMemcpyAsync(h->d_ransac + off_est, est.data(), est.size(), cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));  // `est` and `models` are host temporaries
+    CU((cudaError_t)pagk_launch_ransac(h->d_keys_un, o.pt_predict_un, o.status, h->cfg.max_keys, n_pairs, in[0].seed, (int *)h->d_ransac,
+                                       h->d_ransac + off_in, h->d_geo, h->d_ransac + off_est, st, &h->launches));
+  }
   CU((cudaError_t)pagk_launch_geometry(h->d_geo, h->d_keys_un, o.pt_predict_un, o.status, h->cfg.max_keys, n_pairs, h->d_geo_res,
                                        st, &h->launches));
   std::vector<PagkGeoResult> res((size_t)n_pairs);
   CU(cudaMemcpyAsync(res.data(), h->d_geo_res, res.size() * sizeof(PagkGeoResult), cudaMemcpyDeviceToHost, st));
+  if (any_est) CU(cudaMemcpyAsync(models.data(), h->d_geo, models.size() * sizeof(PagkGeoModel), cudaMemcpyDeviceToHost, st));
   // one copy of the status rows into pinned memory, then per pair on the host
   const size_t st_bytes = (size_t)n_pairs * h->cfg.max_keys;
   if (aux_staging(h, st_bytes) != PAGK_OK) return PAGK_ERR_CUDA;
@@ -911,6 +926,7 @@ int pagk_geometry_validation(pagk_handle *h, int n_pairs, const pagk_geometry_in
   for (int p = 0; p < n_pairs; ++p) {
     out[p].score_H = res[(size_t)p].score_H; out[p].score_F = res[(size_t)p].score_F; out[p].used_H = res[(size_t)p].used_H;
     out[p].n_candidates = res[(size_t)p].n_candidates; out[p].n_inlier = res[(size_t)p].n_inlier;
+    std::memcpy(out[p].H21, models[(size_t)p].H21, sizeof(out[p].H21)); std::memcpy(out[p].F21, models[(size_t)p].F21, sizeof(out[p].F21));
   }
   return PAGK_OK;
 }

@@ -14,6 +14,7 @@
 // Compiled with --fmad=false (see pagk_device.cuh for the arithmetic contract).
 #include "pagk_device.cuh"
 #include "pagk_kernels.h"
+#include "pagk_ransac.h"
 
 #include <math_constants.h>
 
@@ -1158,6 +1159,236 @@ __global__ void __launch_bounds__(256) pagk_remap_slots_kernel(const unsigned ch
 }
 
 // =================================================================================================
+// The two robust estimators of GeometryValidation (reference src/gyro_aided_tracker.cpp:597, :691; pagk_ransac.h says what
+// is and is not shared with OpenCV).  One CTA per (pair, model): model 0 the homography, model 1 the fundamental matrix.
+//   1  the status-1 correspondences in index order -> a compact index list (vPts1 / vPts2, :432-440)
+//   2  kHypotheses hypotheses, one thread each (four per thread): minimal sample from the counter-based generator, model,
+//      inlier count over the whole list; the best one (most inliers, then the lowest hypothesis number) by a block reduction
+//   3  refit on the inliers of the best hypothesis: every entry of the 9 x 9 normal matrix is owned by one thread that walks
+//      the list in order (deterministic sums), thread 0 takes the null vector (Jacobi) and finishes the model
+//   4  homography only: five Gauss-Newton steps on the forward reprojection error of those inliers, same ownership scheme
+// A pair with at most eight candidates is left alone (the reference does not validate it, :446).
+// =================================================================================================
+#define RANSAC_THREADS 256
+
+__device__ __forceinline__ void pagk_ransac_point(const float2 *__restrict__ keys_un, const float2 *__restrict__ pred_un, size_t o,
+                                                  double &x, double &y, double &u, double &v) {
+  const float2 a = keys_un[o], b = pred_un[o];
+  x = (double)a.x; y = (double)a.y; u = (double)b.x; v = (double)b.y;
+}
+
+__global__ void __launch_bounds__(RANSAC_THREADS) pagk_ransac_kernel(const float2 *__restrict__ keys_un, const float2 *__restrict__ pred_un,
+                                                                   const unsigned char *__restrict__ status, int max_keys, unsigned int seed,
+                                                                   int *__restrict__ scratch_idx, unsigned char *__restrict__ scratch_in,
+                                                                   PagkGeoModel *__restrict__ models, const unsigned char *__restrict__ estimate) {
+  using namespace pagk_ransac;
+  const int pair = blockIdx.x, model = blockIdx.y, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if (!estimate[pair]) return;
+  PagkGeoModel &G = models[pair];
+  const int N = G.n_keys;
+  const size_t o0 = (size_t)pair * max_keys;
+  int *list = scratch_idx + ((size_t)pair * 2 + model) * max_keys;
+  unsigned char *inl = scratch_in + ((size_t)pair * 2 + model) * max_keys;
+  __shared__ int s_warp[RANSAC_THREADS / 32];
+  __shared__ int s_base, s_M, s_best_cnt, s_best_hyp, s_nin;
+  __shared__ double s_model[9], s_mat[81], s_vec[16], s_sim[6];
+  __shared__ int s_cnt[RANSAC_THREADS / 32], s_hyp[RANSAC_THREADS / 32];
+  // ---- 1: compact list, order preserved
+  if (t == 0) s_base = 0;
+  __syncthreads();
+  for (int c0 = 0; c0 < N; c0 += RANSAC_THREADS) {
+    const int i = c0 + t;
+    const bool f = i < N && status[o0 + i] != 0;
+    const unsigned int bal = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    int off = s_base;
+    for (int w = 0; w < warp; ++w) off += s_warp[w];
+    if (f) list[off + __popc(bal & ((1u << lane) - 1u))] = i;
+    __syncthreads();
+    if (t == 0) { int tot = 0; for (int w = 0; w < RANSAC_THREADS / 32; ++w) tot += s_warp[w]; s_base += tot; }
+    __syncthreads();
+  }
+  const int M = s_base;
+  double *out = model == 0 ? G.H21 : G.F21;
+  if (M <= 8) {  // nothing is validated: a neutral model
+    if (t < 9) out[t] = (model == 0 && (t == 0 || t == 4 || t == 8)) ? 1.0 : 0.0;
+    if (model == 0 && t < 9) G.H12[t] = (t == 0 || t == 4 || t == 8) ? 1.0 : 0.0;
+    return;
+  }
+  __threadfence_block();
+  __syncthreads();
+  // ---- 2: hypotheses
+  int best_cnt = -1, best_hyp = 0x7fffffff;
+  for (int hyp = t; hyp < kHypotheses; hyp += RANSAC_THREADS) {
+    double Mdl[9];
+    bool ok;
+    if (model == 0) {
+      int id[4];
+      sample<4>(seed, (unsigned int)pair, (unsigned int)hyp, M, id);
+      double x[4], y[4], u[4], v[4];
+      for (int k = 0; k < 4; ++k) pagk_ransac_point(keys_un, pred_un, o0 + list[id[k]], x[k], y[k], u[k], v[k]);
+      ok = h_from_4(x, y, u, v, Mdl);
+    } else {
+      int id[8];
+      sample<8>(seed, (unsigned int)pair, (unsigned int)hyp + kHypotheses, M, id);
+      double x[8], y[8], u[8], v[8];
+      for (int k = 0; k < 8; ++k) pagk_ransac_point(keys_un, pred_un, o0 + list[id[k]], x[k], y[k], u[k], v[k]);
+      ok = f_from_8(x, y, u, v, Mdl);
+    }
+    if (!ok) continue;
+    int cnt = 0;
+    for (int k = 0; k < M; ++k) {
+      double x, y, u, v;
+      pagk_ransac_point(keys_un, pred_un, o0 + list[k], x, y, u, v);
+      const double e = model == 0 ? h_error(Mdl, x, y, u, v) : f_error(Mdl, x, y, u, v);
+      cnt += (e <= kThreshold2) ? 1 : 0;
+    }
+    if (cnt > best_cnt) { best_cnt = cnt; best_hyp = hyp; }  // hypotheses of a thread come in increasing order
+  }
+  for (int d = 16; d >= 1; d >>= 1) {
+    const int oc = __shfl_xor_sync(0xffffffffu, best_cnt, d), oh = __shfl_xor_sync(0xffffffffu, best_hyp, d);
+    if (oc > best_cnt || (oc == best_cnt && oh < best_hyp)) { best_cnt = oc; best_hyp = oh; }
+  }
+  if (lane == 0) { s_cnt[warp] = best_cnt; s_hyp[warp] = best_hyp; }
+  __syncthreads();
+  if (t == 0) {
+    int bc = s_cnt[0], bh = s_hyp[0];
+    for (int w = 1; w < RANSAC_THREADS / 32; ++w)
+      if (s_cnt[w] > bc || (s_cnt[w] == bc && s_hyp[w] < bh)) { bc = s_cnt[w]; bh = s_hyp[w]; }
+    s_best_cnt = bc; s_best_hyp = bh;
+    // recompute the winning model (cheaper than keeping four models per thread)
+    double Mdl[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    if (bc >= 0) {
+      if (model == 0) {
+        int id[4];
+        sample<4>(seed, (unsigned int)pair, (unsigned int)bh, M, id);
+        double x[4], y[4], u[4], v[4];
+        for (int k = 0; k < 4; ++k) pagk_ransac_point(keys_un, pred_un, o0 + list[id[k]], x[k], y[k], u[k], v[k]);
+        h_from_4(x, y, u, v, Mdl);
+      } else {
+        int id[8];
+        sample<8>(seed, (unsigned int)pair, (unsigned int)bh + kHypotheses, M, id);
+        double x[8], y[8], u[8], v[8];
+        for (int k = 0; k < 8; ++k) pagk_ransac_point(keys_un, pred_un, o0 + list[id[k]], x[k], y[k], u[k], v[k]);
+        f_from_8(x, y, u, v, Mdl);
+      }
+    } else if (model == 1) {
+      for (int i = 0; i < 9; ++i) Mdl[i] = 0.0;
+    }
+    for (int i = 0; i < 9; ++i) s_model[i] = Mdl[i];
+  }
+  __syncthreads();
+  // ---- 3: inliers of the best hypothesis, refit on them
+  const int need = model == 0 ? 4 : 8;
+  if (s_best_cnt >= need) {
+    for (int k = t; k < M; k += RANSAC_THREADS) {
+      double x, y, u, v;
+      pagk_ransac_point(keys_un, pred_un, o0 + list[k], x, y, u, v);
+      const double e = model == 0 ? h_error(s_model, x, y, u, v) : f_error(s_model, x, y, u, v);
+      inl[k] = (e <= kThreshold2) ? 1 : 0;
+    }
+    __threadfence_block();
+    __syncthreads();
+    // Hartley similarities of the inliers: four ordered sums, then two
+    if (t < 4) {
+      double sum = 0.0;
+      int n = 0;
+      for (int k = 0; k < M; ++k)
+        if (inl[k]) {
+          double x, y, u, v;
+          pagk_ransac_point(keys_un, pred_un, o0 + list[k], x, y, u, v);
+          sum += t == 0 ? x : t == 1 ? y : t == 2 ? u : v;
+          ++n;
+        }
+      s_sim[t] = sum / n;
+      if (t == 0) s_nin = n;
+    }
+    __syncthreads();
+    if (t < 2) {
+      double sum = 0.0;
+      const double cx = s_sim[2 * t], cy = s_sim[2 * t + 1];
+      for (int k = 0; k < M; ++k)
+        if (inl[k]) {
+          double x, y, u, v;
+          pagk_ransac_point(keys_un, pred_un, o0 + list[k], x, y, u, v);
+          const double px = t == 0 ? x : u, py = t == 0 ? y : v;
+          sum += sqrt((px - cx) * (px - cx) + (py - cy) * (py - cy));
+        }
+      const double d = sum / s_nin;
+      s_sim[4 + t] = d > 1e-12 ? 1.4142135623730951 / d : 1.0;
+    }
+    __syncthreads();
+    const Sim t1 = {s_sim[4], s_sim[0], s_sim[1]}, t2 = {s_sim[5], s_sim[2], s_sim[3]};
+    if (t < 81) {
+      const int r = t / 9, c = t - 9 * r;
+      double acc = 0.0;
+      if (c >= r) {  // the upper triangle; mirrored below
+        for (int k = 0; k < M; ++k)
+          if (inl[k]) {
+            double x, y, u, v;
+            pagk_ransac_point(keys_un, pred_un, o0 + list[k], x, y, u, v);
+            const double xn = t1.s * (x - t1.cx), yn = t1.s * (y - t1.cy), un = t2.s * (u - t2.cx), vn = t2.s * (v - t2.cy);
+            if (model == 0) {
+              double r0[9], r1[9];
+              h_rows(xn, yn, un, vn, r0, r1);
+              acc += r0[r] * r0[c] + r1[r] * r1[c];
+            } else {
+              double rr[9];
+              f_row(xn, yn, un, vn, rr);
+              acc += rr[r] * rr[c];
+            }
+          }
+      }
+      s_mat[t] = acc;
+    }
+    __syncthreads();
+    if (t < 81) { const int r = t / 9, c = t - 9 * r; if (c < r) s_mat[t] = s_mat[c * 9 + r]; }
+    __syncthreads();
+    if (t == 0) {
+      double A[81], V[81], vec[9], Mdl[9];
+      for (int i = 0; i < 81; ++i) A[i] = s_mat[i];
+      const int k = jacobi_smallest<9>(A, V);
+      for (int i = 0; i < 9; ++i) vec[i] = V[i * 9 + k];
+      const bool ok = model == 0 ? h_denormalise(vec, t1, t2, Mdl) : f_finish(vec, t1, t2, Mdl);
+      if (ok) for (int i = 0; i < 9; ++i) s_model[i] = Mdl[i];
+    }
+    __syncthreads();
+    // ---- 4: Gauss-Newton polish of the homography on the same inliers
+    if (model == 0) {
+      for (int it = 0; it < 5; ++it) {
+        if (t < 72) {  // 64 entries of J^T J, 8 of J^T r
+          const int r = t < 64 ? t / 8 : t - 64, c = t < 64 ? t - 8 * (t / 8) : -1;
+          double acc = 0.0;
+          if (c < 0 || c >= r) {
+            for (int k = 0; k < M; ++k)
+              if (inl[k]) {
+                double x, y, u, v, ju[8], jv[8], ru, rv;
+                pagk_ransac_point(keys_un, pred_un, o0 + list[k], x, y, u, v);
+                h_jacobian(s_model, x, y, u, v, ju, jv, &ru, &rv);
+                acc += c < 0 ? (ju[r] * ru + jv[r] * rv) : (ju[r] * ju[c] + jv[r] * jv[c]);
+              }
+          }
+          if (t < 64) s_mat[t] = acc; else s_vec[t - 64] = acc;
+        }
+        __syncthreads();
+        if (t < 64) { const int r = t / 8, c = t - 8 * r; if (c < r) s_mat[t] = s_mat[c * 8 + r]; }
+        __syncthreads();
+        if (t == 0) {
+          double A[64], b[8], d[8];
+          for (int i = 0; i < 64; ++i) A[i] = s_mat[i];
+          for (int i = 0; i < 8; ++i) b[i] = s_vec[i];
+          if (solve8(A, b, d)) for (int i = 0; i < 8; ++i) s_model[i] -= d[i];
+        }
+        __syncthreads();
+      }
+    }
+  }
+  if (t < 9) out[t] = s_model[t];
+  if (model == 0 && t == 0) inv3(s_model, G.H12);  // cv::Mat H12 = H21.inv(), src/gyro_aided_tracker.cpp:597
+}
+
+// =================================================================================================
 // launch wrappers (host)
 // =================================================================================================
 int pagk_pyramid_fused_max_level() {
@@ -1243,6 +1474,16 @@ int pagk_launch_geometry(const PagkGeoModel *models, const float2 *keys_un, cons
                          int max_keys, int n_pairs, PagkGeoResult *res, cudaStream_t st, long long *launches) {
   if (n_pairs <= 0) return 0;
   pagk_geometry_kernel<<<n_pairs, GEO_THREADS, 0, st>>>(models, keys_un, pred_un, status, max_keys, res);
+  ++*launches;
+  return (int)cudaGetLastError();
+}
+
+int pagk_launch_ransac(const float2 *keys_un, const float2 *pred_un, const unsigned char *status, int max_keys, int n_pairs,
+                       unsigned int seed, int *scratch_idx, unsigned char *scratch_in, PagkGeoModel *models,
+                       const unsigned char *estimate, cudaStream_t st, long long *launches) {
+  if (n_pairs <= 0) return 0;
+  pagk_ransac_kernel<<<dim3(n_pairs, 2), RANSAC_THREADS, 0, st>>>(keys_un, pred_un, status, max_keys, seed, scratch_idx, scratch_in, models,
+                                                                 estimate);
   ++*launches;
   return (int)cudaGetLastError();
 }

@@ -29,6 +29,10 @@ int pagk_launch_epilogue(const PagkPairConst *pcs, const PagkOutPtrs &out, const
 // GeometryValidation minus its RANSAC estimators (reference src/gyro_aided_tracker.cpp:429-508, 589-768)
 int pagk_launch_geometry(const PagkGeoModel *models, const float2 *keys_un, const float2 *pred_un, unsigned char *status,
                          int max_keys, int n_pairs, PagkGeoResult *res, cudaStream_t st, long long *launches);
+// the two RANSAC estimators of GeometryValidation on the device (pagk_ransac.h): fills H21 / H12 / F21 of models[p] where estimate[p]
+int pagk_launch_ransac(const float2 *keys_un, const float2 *pred_un, const unsigned char *status, int max_keys, int n_pairs,
+                       unsigned int seed, int *scratch_idx, unsigned char *scratch_in, PagkGeoModel *models,
+                       const unsigned char *estimate, cudaStream_t st, long long *launches);
 // Frame::SetPredictKeyPointsAndMask (reference src/frame.cpp:115-153); mask may be null
 int pagk_launch_carry(const PagkCarryConst *cc, const float2 *pt_predict, const float2 *pt_predict_un, const unsigned char *status,
                       const float2 *normal_last, int max_keys, int n_pairs, float2 *keys, float2 *keys_un, float2 *keys_normal,

@@ -28,6 +28,7 @@ def test_struct_layout_matches_ctypes(tmp_path):
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "pagk.h"\nint main(void){\n'
                    'printf("%zu %zu %zu %zu %zu\\n", sizeof(pagk_config), sizeof(pagk_params), sizeof(pagk_pair_in), sizeof(pagk_pair_out), sizeof(pagk_patch_match_in));\n'
                    'printf("%zu %zu %zu %zu\\n", offsetof(pagk_pair_in, K), offsetof(pagk_pair_in, Rcl_override), offsetof(pagk_pair_out, Rcl), offsetof(pagk_pair_out, n_iterations));\n'
+                   'printf("%zu %zu %zu %zu\\n", sizeof(pagk_geometry_in), sizeof(pagk_geometry_out), offsetof(pagk_geometry_in, estimate), offsetof(pagk_geometry_out, H21));\n'
                    'return 0;}\n')
     exe = tmp_path / "layout"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
@@ -35,7 +36,8 @@ def test_struct_layout_matches_ctypes(tmp_path):
     sizes = [C.sizeof(x) for x in (capi.PagkConfig, capi.PagkParams, capi.PagkPairIn, capi.PagkPairOut, capi.PagkPatchMatchIn)]
     offs = [capi.PagkPairIn.K.offset, capi.PagkPairIn.Rcl_override.offset, capi.PagkPairOut.Rcl.offset,
             capi.PagkPairOut.n_iterations.offset]
-    assert [int(x) for x in out] == sizes + offs
+    geo = [C.sizeof(capi.PagkGeometryIn), C.sizeof(capi.PagkGeometryOut), capi.PagkGeometryIn.estimate.offset, capi.PagkGeometryOut.H21.offset]
+    assert [int(x) for x in out] == sizes + offs + geo
 
 
 def test_default_params_are_the_reference_constants(cuda_lib):
