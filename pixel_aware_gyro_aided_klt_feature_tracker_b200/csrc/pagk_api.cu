@@ -334,7 +334,7 @@ int launch_lk_kernel(pagk_handle *h, const PagkOutPtrs &o, const PagkMode &m, in
   if (h->lk_kernel == 0 && pagk_lk_lanes_supported(m) && h->d_tmpl && pagk_lk_lanes_record_bytes(m.half) <= h->tmpl_rec) {
     if (build_tmaps(h, m.half) != PAGK_OK) return (int)cudaErrorUnknown;
     // PAGK_LK_TIMELINE=<file> with a -DPAGK_LANES_PROF build: per-warp phase cycles (developer aid)
-    if (h->d_dbg) CU(cudaMemsetAsync(h->d_dbg, 0, 2048 * 8 * sizeof(long long), h->stream));
+    if (h->d_dbg) CU(cudaMemsetAsync(h->d_dbg, 0, 2048 * 16 * sizeof(long long), h->stream));
     if (++h->lk_epoch >= 0x0fffffff) {  // the epoch is about to repeat: forget every progress word written so far
       CU(cudaMemsetAsync(h->d_progress, 0, (size_t)h->cfg.max_pairs * h->cfg.max_keys * sizeof(int), h->stream));
       h->lk_epoch = 1;
@@ -344,13 +344,13 @@ int launch_lk_kernel(pagk_handle *h, const PagkOutPtrs &o, const PagkMode &m, in
                                         h->stream, &h->launches, h->d_dbg);
     if (rc == 0 && n_max > 0 && n_pairs > 0) h->lk_parity ^= 1;
     if (h->d_dbg && rc == 0) {
-      std::vector<long long> tl(2048 * 8);
+      std::vector<long long> tl(2048 * 16);
       CU(cudaMemcpyAsync(tl.data(), h->d_dbg, tl.size() * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
       CU(cudaStreamSynchronize(h->stream));
       if (FILE *f = fopen(h->dbg_path, "w")) {
-        for (size_t w = 0; w < tl.size() / 8; ++w) {
-          if (!tl[w * 8 + 6]) continue;
-          for (int k = 0; k < 8; ++k) fprintf(f, "%lld%c", tl[w * 8 + k], k == 7 ? '\n' : ' ');
+        for (size_t w = 0; w < tl.size() / 16; ++w) {
+          if (!tl[w * 16 + 6]) continue;
+          for (int k = 0; k < 16; ++k) fprintf(f, "%lld%c", tl[w * 16 + k], k == 15 ? '\n' : ' ');
         }
         fclose(f);
       }
@@ -456,7 +456,7 @@ int pagk_create(const pagk_config *cfg, pagk_handle **out) {
     const char *k = getenv("PAGK_LK_KERNEL");
     h->lk_kernel = (k && std::strcmp(k, "generic") == 0) ? 2 : 0;
     h->dbg_path = getenv("PAGK_LK_TIMELINE");
-    if (h->dbg_path) { ok(cudaMalloc(&h->d_dbg, 2048 * 8 * sizeof(long long))); }
+    if (h->dbg_path) { ok(cudaMalloc(&h->d_dbg, 2048 * 16 * sizeof(long long))); }
   }
   ok(cudaMallocHost(&h->h_in, h->h_in_bytes));
   ok(cudaMallocHost(&h->h_out, h->out_bytes));

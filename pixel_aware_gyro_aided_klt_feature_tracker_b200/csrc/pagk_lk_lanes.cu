@@ -27,8 +27,17 @@
 // the warp waits for them once; no tap is staged through registers and no lane-serial setup code is left in the
 // alignment kernel (it was 31 % of a warp's time and a third of the kernel's code).
 //
-// Shared memory per slot: T_BULK bytes of template + the window (u8).  u8 -> float is (0x4B000000 | b) - 2^23
-// (LOP3 + FADD): exact, and off the 4-lane conversion pipe that the three float -> double conversions per pixel need.
+// Shared memory holds the windows only (u8), laid out ONE BANK PER LANE: word w of lane l's window sits at
+// (w * 32 + l) * 4 inside the warp's block, so whatever the lanes' sample offsets are, a tap load is one wavefront.
+// (Slot-contiguous windows cost 2.65 wavefronts per load at production offsets: the pass was bound by the
+// shared-memory pipe as soon as its arithmetic got cheaper, tools/ubench_pass2.cu.)
+//
+// The pass arithmetic (argued bit-exact above the loop):
+//   * two pixels per step, every FP32 operation packed across the pair (FADD2 / FMUL2 / FFMA2, sm_100): 35 packed
+//     operations per pixel instead of 75 scalar ones;
+//   * no u8 -> float conversion at all: a tap enters the arithmetic as the raw byte read as a SUBNORMAL float
+//     (b * 2^-149), and the sample coordinates carry a factor 2^100, so that every product weight * tap is the
+//     reference's product times 2^-49 exactly; the factor leaves the sums after the loop.
 //
 // Per round a warp does, with warp-uniform control flow:
 //   refill   idle lanes take the next items from the global counter
@@ -42,74 +51,94 @@
 //
 // Bit-exactness of the window path is argued above the pass loop.
 #include <cstdlib>
-#include <type_traits>
 #include "pagk_device.cuh"
 #include "pagk_kernels.h"
 
 namespace {
 
-// a warp with at most this many live lanes runs them one by one through the cooperative pass (lanes = pixels,
-// then lanes = accumulators: about 2.2 k warp instructions per slot) instead of a lockstep pass (15 k)
+// a warp with at most this many live lanes runs them through the pixel-parallel pass (lanes = pixels, then lanes =
+// accumulators: about 5 k cycles per slot, two slots at a time) instead of a lockstep pass (20 k to 28 k cycles whatever
+// the number of live lanes).  Measured on config B: 2 beats 5, 8 and 12.
 #ifndef PAGK_LANES_SPARSE
-#define PAGK_LANES_SPARSE 5
+#define PAGK_LANES_SPARSE 2
 #endif
-// pixels per trip of the pass loop = floats per vector load of T (4: LDG.128, 2: LDG.64)
-#ifndef PAGK_LANES_UNROLL
-#define PAGK_LANES_UNROLL 4
-#endif
-// warps per SM for 11 x 11 patches.  Twelve (three per scheduler, what the register file allows) win on batches of 128
-// pairs and more (lane occupancy 0.92, 14 % faster per pair than eight); on config B's 64 pairs a launch is only 16
-// rounds deep for 56 k lanes, the tail and the level hand-overs leave 28 % of the lanes idle, and eight warps are faster.
-// Eight warps also leave a third of the registers to the small kernels of the neighbouring steps (other streams).
-#ifndef PAGK_WIN16
-#define PAGK_WIN16 0
-#endif
+// warps per SM for 11 x 11 patches, chosen per launch: twelve (three per scheduler, 170 registers per thread: the low-ILP
+// phases of one warp -- claim, window copies, solve -- are covered by the passes of two others) are 9 % faster per pair on
+// batches of 128 pairs and more; on config B's 64 pairs a launch is only 4.6 items per lane deep for 56 k lanes, a
+// fifth of them idle in the tail or waiting for a level hand-over, and eight warps (6.9 items per lane) win by 12 %.
 #ifndef PAGK_LANES_WARPS5
 #define PAGK_LANES_WARPS5 8
 #endif
+#ifndef PAGK_LANES_WARPS5_BIG
+#define PAGK_LANES_WARPS5_BIG 12
+#endif
+// features per launch from which the larger number of warps is used
+#ifndef PAGK_LANES_BIG_FEATURES
+#define PAGK_LANES_BIG_FEATURES 110000
+#endif
+// template vectors (four pixels = two packed pairs) per trip of the pass loop: the independent chains a lone warp has
+// in flight
+#ifndef PAGK_LANES_TRIP
+#define PAGK_LANES_TRIP 2
+#endif
 // warps per CTA: the warps of an SM as several small CTAs leave the SM one by one when the work runs out, and the
 // CTAs of the next launch (another stream) move in
+// measured and left off (config B, 8 warps): the first template vectors loaded before the window copies (0.708 against
+// 0.698 ms), the pair offsets from shared memory instead of the constant bank (0.784 ms)
+#ifndef PAGK_LANES_TPRE
+#define PAGK_LANES_TPRE 0
+#endif
+#ifndef PAGK_LANES_LDSPAIRS
+#define PAGK_LANES_LDSPAIRS 0
+#endif
+// register cap of the alignment kernel as CTAs per SM in its launch bounds (0: what the warps per SM imply)
+#ifndef PAGK_LANES_REGCTAS
+#define PAGK_LANES_REGCTAS 0
+#endif
 #ifndef PAGK_LANES_CTA_WARPS
 #define PAGK_LANES_CTA_WARPS 4
 #endif
 
-template <int HALF>
+template <int HALF, int WSM = (HALF <= 5 ? PAGK_LANES_WARPS5 : 7)>
 struct LanesCfg {
   static constexpr int P = 2 * HALF + 1;
   static constexpr int NP = P * P;
-  // window of the current level: WIN_W x WIN_H elements, copied as 4-byte words from a 4-byte aligned origin: the
-  // origin is a multiple of ALIGN elements and the usable width for any box is WIN_W - (ALIGN - 1).  The elements are
-  // the level's bytes.  -DPAGK_WIN16=1 (11 x 11 patches): the bfloat16 pixels of a 16-bit plane that the pyramid kernel
-  // then writes beside every current image; a tap is one load and one shift instead of a load, an OR and a subtraction
-  // (115 instead of 126 instructions per pixel).  Measured on config B: the passes get 4 % shorter, the pyramid kernel
-  // 14 us longer and the windows twice as large (no room left for the neighbouring steps' kernels): not the default.
-  static constexpr bool W16 = PAGK_WIN16 != 0 && HALF <= 5;
-  static constexpr int ELT = W16 ? 2 : 1;
-  static constexpr int ALIGN = 4 / ELT;
-  static constexpr int WIN_W = HALF > 5 ? 36 : W16 ? 22 : 24;
+  // window of the current level: WIN_W x WIN_H bytes, copied as 4-byte words from a 4-byte aligned origin: the
+  // origin is a multiple of ALIGN columns and the usable width for any box is WIN_W - (ALIGN - 1).
+  static constexpr int ALIGN = 4;
+  static constexpr int WIN_W = HALF > 5 ? 32 : 24;
   static constexpr int WIN_H = P + 6;
-  static constexpr int WPR = WIN_W * ELT / 4;  // words per window row
+  static constexpr int WPR = WIN_W / 4;  // words per window row
   static constexpr int WIN_WORDS = WPR * WIN_H;
-  // bytes from one slot's window to the next: an ODD number of words, lane-private windows start in distinct banks
-  static constexpr int WIN_STRIDE = (WIN_WORDS | 1) * 4;
+  // one bank per lane: byte i of lane l's window sits at (i >> 2) * 128 + (i & 3) + 4 * l of the warp's block
+  static constexpr int ROW_BYTES = WPR * 128;  // from a byte to the byte below it
   // a template record in global memory: T[0 .. NP-2] (T_BULK bytes, a multiple of 16: the pass reads it with 16-byte
   // loads), then T[NP-1], c = -T[NP/2], and h22 = the ordered double sum of c*c over the patch
   static constexpr int T_BULK = (NP * 4) & ~15;
   static constexpr int REC_BYTES = T_BULK + 16;
   static_assert(NP * 4 - T_BULK == 4, "exactly the last template value sits in the record's tail");
-  // Shared memory holds the windows only (the template is streamed from its record), so the warps per SM are bound
-  // by the register file: 12 warps of 32 slots for 11 x 11; a 21 x 21 window is 972 bytes: 8 warps of 28 slots
-  static constexpr int SLOTS = HALF <= 5 ? 32 : 28;
-  static constexpr int WARPS_SM = HALF <= 5 ? PAGK_LANES_WARPS5 : 8;
+  // Shared memory holds the windows (the template is streamed from its record) and the buffers of the pixel-parallel
+  // pass: 12.8 + 3.9 KB per warp for 11 x 11, 27 + 1.7 KB for 21 x 21 (seven warps: 201 KB)
+  static constexpr int SLOTS = 32;
+  static constexpr int WARPS_SM = WSM;
   static constexpr int WARPS = WARPS_SM % PAGK_LANES_CTA_WARPS == 0 ? PAGK_LANES_CTA_WARPS : WARPS_SM;  // per CTA
   static constexpr int CTAS_SM = WARPS_SM / WARPS;
-  // per-warp scratch of the cooperative pass: 32 records (Ix, Iy, -e) -- one chunk of the patch -- and the two
-  // constants c and 1
-  static constexpr int SCRATCH_FLOATS = 32 * 3 + 4;
-  static constexpr int WARP_BYTES = SLOTS * WIN_STRIDE + SCRATCH_FLOATS * 4;
+  // per-warp scratch of the pixel-parallel pass: COOP_BUFS buffers (one slot each), a buffer = COOP_CH records
+  // (Ix, Iy, -e) -- the whole 11 x 11 patch, a chunk of a 21 x 21 one --, the two constants c and 1, the twelve sums and
+  // the cost the accumulator lanes hand back, and a row-major copy of the slot's window
+  static constexpr int COOP_CH = HALF <= 5 ? 128 : 64;
+  static constexpr int COOP_BUFS = HALF <= 5 ? 2 : 1;
+  static constexpr int COOP_RES = COOP_CH * 3 + 4;              // float index of the results (8-byte aligned)
+  static constexpr int COOP_LIN = COOP_RES + 28;                // float index of the row-major window copy
+  static constexpr int BUF_FLOATS = (COOP_LIN + WIN_WORDS + 3) & ~3;
+  static constexpr int SCRATCH_FLOATS = COOP_BUFS * BUF_FLOATS;
+  static constexpr int WARP_BYTES = WIN_WORDS * 128 + SCRATCH_FLOATS * 4;
   static constexpr int SMEM_BYTES = WARPS * WARP_BYTES;
-  static_assert((WIN_W * ELT) % 4 == 0 && WIN_W - (ALIGN - 1) >= P + 4, "window narrower than a sample box");
-  static_assert(CTAS_SM * (SMEM_BYTES + 1024 + 256) <= 228 * 1024, "windows do not fit the SM");
+  static_assert(WIN_W % 4 == 0 && WIN_W - (ALIGN - 1) >= P + 4, "window narrower than a sample box");
+  // static shared memory of the kernel: level geometry and the table of pixel-pair offsets
+  static constexpr int STATIC_BYTES = 256 + (PAGK_LANES_LDSPAIRS ? ((NP + 1) / 2) * 16 : 0);
+  static_assert(SMEM_BYTES + STATIC_BYTES <= 227 * 1024, "a CTA's windows exceed the shared memory of a block");
+  static_assert(CTAS_SM * (SMEM_BYTES + STATIC_BYTES + 1024) <= 228 * 1024, "windows do not fit the SM");
 };
 
 // floor(x) as float for 0 <= x < 2^22 without the conversion pipe: x + 2^23 rounds to an integer,
@@ -161,14 +190,10 @@ __device__ __forceinline__ void tma_load_3d(unsigned int dst, const CUtensorMap 
                "l"(reinterpret_cast<unsigned long long>(map)), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
 }
 
-// PatchMatch::GetPixelValue (reference src/patch_match.cpp:391-406) with the four taps taken from a staged
-// window with origin (wx0, wy0): the same clamps, the same expression tree.
-// a window element as float: a byte through the 2^23 trick, a bfloat16 by moving it to the upper half
-__device__ __forceinline__ float elt_f(unsigned char b) { return u8f(b); }
-__device__ __forceinline__ float elt_f(unsigned short h) { return __uint_as_float((unsigned int)h << 16); }
-
-template <int WIN_W, int WIN_H, class E>
-__device__ __forceinline__ float window_sample(const E *__restrict__ win, int wx0, int wy0, float fcols,
+// PatchMatch::GetPixelValue (reference src/patch_match.cpp:391-406) with the four taps taken from a row-major copy
+// `lin` (WIN_W bytes per row) of a staged window with origin (wx0, wy0): the same clamps, the same expression tree.
+template <int WIN_W, int WIN_H>
+__device__ __forceinline__ float window_sample(const unsigned char *__restrict__ lin, int wx0, int wy0, float fcols,
                                                float fcm1, float frows, float frm1, float x, float y) {
   if (x < 0.f) x = 0.f;
   if (y < 0.f) y = 0.f;
@@ -177,28 +202,66 @@ __device__ __forceinline__ float window_sample(const E *__restrict__ win, int wx
   int ix, iy;
   const float fx = floor_nn(x, ix), fy = floor_nn(y, iy);
   const float xx = x - fx, yy = y - fy, wa = 1.0f - xx, wb = 1.0f - yy;
-  CHECK_IDX((iy - wy0) * WIN_W + (ix - wx0), 0, WIN_W * WIN_H - WIN_W - 2);
-  const E *q = win + (iy - wy0) * WIN_W + (ix - wx0);
-  return wb * (wa * elt_f(q[0]) + xx * elt_f(q[1])) + yy * (wa * elt_f(q[WIN_W]) + xx * elt_f(q[WIN_W + 1]));
+  const int i = (iy - wy0) * WIN_W + (ix - wx0);
+  CHECK_IDX(i, 0, WIN_W * WIN_H - WIN_W - 2);
+  const unsigned char *q = lin + i;
+  return wb * (wa * u8f(q[0]) + xx * u8f(q[1])) + yy * (wa * u8f(q[WIN_W]) + xx * u8f(q[WIN_W + 1]));
 }
 
-// developer aid (-DPAGK_LANES_PROF): per-warp cycles of every phase, rounds and active lane-rounds -> prof[warp_global][8]
+// ---- packed FP32 (sm_100: add / mul / fma .f32x2 -> FADD2 / FMUL2 / FFMA2, IEEE round-to-nearest per element).
+// ptxas contracts mul.f32x2 + add.f32x2 into FFMA2 even under -fmad=false (measured, CUDA 12.9), so a sum with a
+// product among its operands is written fma2(product, ONE, other) with ONE = (1, 1) from a kernel argument:
+// rn(a * 1 + b) == rn(a + b), and a product that feeds the MULTIPLICAND of an FMA cannot be contracted into it.
+// tests/test_sass.py counts the FFMA2 of the built kernel against the number written here.
+struct f2 { float x, y; };
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {
+  f2 r;
+  asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; add.rn.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc; }"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) { return add2(a, f2{-b.x, -b.y}); }
+__device__ __forceinline__ f2 addrd2(f2 a, f2 b) {  // rounded towards minus infinity
+  f2 r;
+  asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; add.rm.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc; }"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+  f2 r;
+  asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mul.rn.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc; }"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+  f2 r;
+  asm("{ .reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mov.b64 rc, {%6, %7}; fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0, %1}, rd; }"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return r;
+}
+
+// developer aid (-DPAGK_LANES_PROF): per-warp cycles of every phase, rounds and active lane-rounds, wall-clock marks
+// (start, queue exhausted, end) and what the warp had done when the queue ran out -> prof[warp_global][16]
 #ifdef PAGK_LANES_PROF
-#define PROF_DECL long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long pt = clock64();
+__device__ __forceinline__ long long prof_ns() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define PROF_DECL long long pf[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long pt = clock64(); pf[8] = prof_ns();
 #define PROF(i) do { const long long now_ = clock64(); pf[i] += now_ - pt; pt = now_; } while (0)
 #define PROF_ADD(i, v) pf[i] += (v)
-#define PROF_FLUSH() do { if (prof && lane == 0) for (int i_ = 0; i_ < 8; ++i_) prof[(size_t)(blockIdx.x * (blockDim.x >> 5) + warp) * 8 + i_] = pf[i_]; } while (0)
+#define PROF_SET(i, v) pf[i] = (v)
+#define PROF_FLUSH() do { pf[10] = prof_ns(); if (prof && lane == 0) for (int i_ = 0; i_ < 16; ++i_) prof[(size_t)(blockIdx.x * (blockDim.x >> 5) + warp) * 16 + i_] = pf[i_]; } while (0)
 #else
 #define PROF_DECL
 #define PROF(i)
 #define PROF_ADD(i, v)
+#define PROF_SET(i, v)
 #define PROF_FLUSH()
 #endif
 
-// patch offsets (x, y) of pixel p in the reference's order (y outer, x inner, src/patch_match.cpp:233-246), read with
-// a warp-uniform index in the pass: one constant load instead of the compare/select that walks (x, y)
-__constant__ float2 c_pix5[121];
-__constant__ float2 c_pix10[441];
+// patch offsets of the pixel pair (p, q) = (2k, 2k + 1) in the reference's order (y outer, x inner,
+// src/patch_match.cpp:233-246) as (x_p, x_q, y_p, y_q), read with a warp-uniform index in the pass; the last pair of
+// an odd patch repeats its pixel
+__constant__ float4 c_pair5[61];
+__constant__ float4 c_pair10[221];
 
 struct Sums {
   double h00, h10, h11, h20, h21, h30, h31, b0, b1, b2, b3;
@@ -387,23 +450,20 @@ __global__ void __launch_bounds__(TmplCfg<HALF>::WARPS * 32) pagk_lk_template_ke
 // =================================================================================================
 // K3b: the alignment kernel
 // =================================================================================================
-template <int HALF, bool AFFINE>
-__global__ void __launch_bounds__(LanesCfg<HALF>::WARPS * 32, LanesCfg<HALF>::CTAS_SM)
+template <int HALF, bool AFFINE, int WSM>
+__global__ void __launch_bounds__(LanesCfg<HALF, WSM>::WARPS * 32, PAGK_LANES_REGCTAS && HALF <= 5 ? PAGK_LANES_REGCTAS : LanesCfg<HALF, WSM>::CTAS_SM)
 pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const PagkPairConst *__restrict__ pcs,
                      const float2 *__restrict__ keys_un, PagkOutPtrs out, PagkMode mode, int max_keys, int n_max,
                      int n_pairs, int *__restrict__ work_counter, int *__restrict__ next_counter, int lane_cap,
-                     int split, int *progress, int epoch_base, const unsigned char *__restrict__ tmpl,
+                     int split, int *progress, int epoch_base, const unsigned char *__restrict__ tmpl, float unit,
                      long long *__restrict__ prof) {
-  using C = LanesCfg<HALF>;
+  using C = LanesCfg<HALF, WSM>;
   constexpr int P = C::P, NP = C::NP, WIN_W = C::WIN_W, WIN_H = C::WIN_H;
-  using E = typename std::conditional<C::W16, unsigned short, unsigned char>::type;  // window element
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned char *wwin = smem_raw + (size_t)warp * C::WARP_BYTES;                          // [SLOTS] windows, stride WIN_STRIDE
-  float *scratch = reinterpret_cast<float *>(wwin + C::SLOTS * C::WIN_STRIDE);            // [32][3] records, c, 1
-  // lanes beyond SLOTS never own a feature; in the lockstep pass they read (harmlessly) the last slot's memory
-  const int myslot = lane < C::SLOTS ? lane : C::SLOTS - 1;
-  const E *mywin = reinterpret_cast<const E *>(wwin + myslot * C::WIN_STRIDE);
+  unsigned char *wwin = smem_raw + (size_t)warp * C::WARP_BYTES;                          // [WIN_WORDS][32 lanes] words
+  float *scratch = reinterpret_cast<float *>(wwin + C::WIN_WORDS * 128);                  // COOP_BUFS buffers of the pixel-parallel pass
+  const unsigned char *mywin = wwin + lane * 4;                                            // byte 0 of this lane's window
   const int total_work = n_pairs * n_max;
   const int top = mode.levels - 1;
   // Work items.  split == 0: an item is a feature (all levels in one lane).  split != 0: an item is one LEVEL of a
@@ -418,23 +478,31 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
   // level geometry, indexed by each lane's own level
   __shared__ int s_cols[PAGK_MAX_LEVELS], s_rows[PAGK_MAX_LEVELS], s_pitch[PAGK_MAX_LEVELS];
   __shared__ unsigned int s_off[PAGK_MAX_LEVELS], s_offw[PAGK_MAX_LEVELS];  // u8 level, level the windows come from
+  // -DPAGK_LANES_LDSPAIRS: patch offsets of the pixel pairs from shared memory (one broadcast LDS.128 per pair)
+#if PAGK_LANES_LDSPAIRS
+  __shared__ float4 s_pairs[(NP + 1) / 2];
+  for (int k = threadIdx.x; k < (NP + 1) / 2; k += blockDim.x) s_pairs[k] = (HALF == 5 ? c_pair5 : c_pair10)[k];
+#endif
   // the two work counters of a handle alternate between launches: this launch zeroes the one the next launch uses
   if (blockIdx.x == 0 && threadIdx.x == 0) *next_counter = 0;
   if (threadIdx.x < PAGK_MAX_LEVELS) {
     s_cols[threadIdx.x] = g.lv[threadIdx.x].cols; s_rows[threadIdx.x] = g.lv[threadIdx.x].rows;
     s_pitch[threadIdx.x] = g.lv[threadIdx.x].pitch; s_off[threadIdx.x] = g.lv[threadIdx.x].offset;
-    s_offw[threadIdx.x] = C::W16 ? g.lv[threadIdx.x].offset16 : g.lv[threadIdx.x].offset;
+    s_offw[threadIdx.x] = g.lv[threadIdx.x].offset;
   }
   __syncthreads();
 
-  // accumulator role of this lane in the cooperative pass: acc += A * B with A in {Ix, Iy, c, 1} and B in
-  // {Ix, Iy, -e, c}; lanes 0..11 = h00 h10 h11 h20 h21 h22 h30 h31 b0 b1 b2 b3.  An operand is a float in the
-  // scratch: a record field (stride 3) or one of the two constants behind the records (stride 0).
-  const int role = lane < 12 ? lane : 0;
+  // accumulator role of this lane in the pixel-parallel pass: acc += A * B with A in {Ix, Iy, c, 1} and B in
+  // {Ix, Iy, -e, c}; roles 0..11 = h00 h10 h11 h20 h21 h22 h30 h31 b0 b1 b2 b3.  An operand is a float in the lane's
+  // buffer: a record field (stride 3) or one of the two constants behind the records (stride 0).  With two buffers
+  // lanes 0..15 serve the first one, lanes 16..31 the second.
+  const int cbuf = C::COOP_BUFS == 2 ? lane >> 4 : 0;
+  const int role16 = C::COOP_BUFS == 2 ? lane & 15 : lane;
+  const int role = role16 < 12 ? role16 : 0;
   const int selA = (int)((0x431044333110ull >> (4 * role)) & 0xfull);  // 0 Ix, 1 Iy, 3 c, 4 one
   const int selB = (int)((0x222210310100ull >> (4 * role)) & 0xfull);  // 0 Ix, 1 Iy, 2 -e, 3 c
-  const int offA = selA < 3 ? selA : 32 * 3 + (selA - 3), strideA = selA < 3 ? 3 : 0;
-  const int offB = selB < 3 ? selB : 32 * 3 + (selB - 3), strideB = selB < 3 ? 3 : 0;
+  const int offA = selA < 3 ? selA : C::COOP_CH * 3 + (selA - 3), strideA = selA < 3 ? 3 : 0;
+  const int offB = selB < 3 ? selB : C::COOP_CH * 3 + (selB - 3), strideB = selB < 3 ? 3 : 0;
 
   // ---- slot state (registers of the owning lane) ----
   int feat = -1, pair = 0, level = 0, iter = 0, n_iter = 0, succ = 1;
@@ -461,7 +529,7 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
       int base = 0;
       if (lane == 0) base = atomicAdd(work_counter, cnt);
       base = __shfl_sync(FULL, base, 0);
-      if (base + cnt >= total_items) exhausted = true;
+      if (base + cnt >= total_items) { exhausted = true; PROF_SET(9, prof_ns()); PROF_SET(11, pf[6]); PROF_SET(12, pf[7]); }
       if (want) {
         const int wi = base + __popc(m & ((1u << lane) - 1u));
         if (wi < total_items) {
@@ -587,22 +655,28 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
       }
     }
 
-    // ------------------------------------------------------------------ window of the current level: LDGSTS, lanes = words
-    {
-      unsigned m = __ballot_sync(FULL, restage);
-      while (m) {
-        const int s = __ffs(m) - 1;
-        m &= m - 1;
-        const int x0 = __shfl_sync(FULL, nx0, s), y0 = __shfl_sync(FULL, ny0, s), sp = __shfl_sync(FULL, pitch, s);
-        const unsigned char *src = reinterpret_cast<const unsigned char *>(__shfl_sync(FULL, (unsigned long long)I2w, s)) + (y0 * sp + x0) * C::ELT;
-        const unsigned int dst = smem_u32(wwin + s * C::WIN_STRIDE);
+    // the first template vectors of the pass: in flight across the window copies below
+#if PAGK_LANES_TPRE
+    float4 t4[PAGK_LANES_TRIP];
 #pragma unroll
-        for (int k = 0; k < (C::WIN_WORDS + 31) / 32; ++k) {
-          const int e = lane + 32 * k, r = e / C::WPR, w = e - r * C::WPR;
-          if (e < C::WIN_WORDS) cp_async4(dst + 4u * (unsigned int)e, src + r * (sp * C::ELT) + 4 * w);
+    for (int u = 0; u < PAGK_LANES_TRIP; ++u) t4[u] = __ldg(Tg + u);
+#endif
+
+    // ------------------------------------------------------------------ window of the current level: LDGSTS, lane = slot
+    // Every lane that (re)stages copies its own window word by word: the destinations of one instruction are the
+    // lanes' own banks (no conflict), the sources WIN_H short row segments per lane.
+    if (__ballot_sync(FULL, restage) != 0u) {
+      if (restage) {
+        const unsigned char *src = I2w + (size_t)ny0 * (size_t)pitch + (size_t)nx0;
+        const unsigned int dst = smem_u32(mywin);
+#pragma unroll 1
+        for (int r = 0; r < WIN_H; ++r) {
+#pragma unroll
+          for (int w = 0; w < C::WPR; ++w) cp_async4(dst + (unsigned int)((r * C::WPR + w) * 128), src + 4 * w);
+          src += pitch;
         }
+        win_x0 = nx0; win_y0 = ny0; win_valid = true;
       }
-      if (restage) { win_x0 = nx0; win_y0 = ny0; win_valid = true; }
     }
     // one wait for every copy of the round
     cp_async_wait_all();
@@ -616,6 +690,7 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
     const float gain = 1.0f + dg;
     const bool sparse = __popc(m_active) <= PAGK_LANES_SPARSE;
     bool coop = active && (sparse || !fast);
+    bool lockbad = false;  // the lockstep pass met the rounding case its shared weights exclude
 
     // ------------------------------------------------------------------ the pass: lane = slot
     // Bit-exactness of the window path.  The reference samples at (sx, sy), (sx+-1, sy), (sx, sy+-1), each
@@ -626,148 +701,275 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
     //   pass through the cooperative path, which evaluates every sample on its own.
     // Horizontal interpolations are shared between samples only where the reference would evaluate the
     // identical expression.
+    // Scaling.  The coordinate chain (pbx, the affine matrix, 1, 2^23) carries the factor SC = 2^100.  Every operation
+    // on it is an addition, a subtraction or a product with a small integer, 0 <= coordinates < 2^22, so every
+    // intermediate of the scaled chain is 2^100 times the reference's (scaling by a power of two commutes with
+    // rounding while nothing overflows or goes subnormal: the largest value is 2^123 + 2^122, the smallest non-zero
+    // one a weight of 2^-23 * 2^100).  A tap is the byte b read as the float b * 2^-149 (subnormal operands are full
+    // speed).  A horizontal interpolation is then rn(w * b) * 2^-49 + ..., exactly the reference's times 2^-49 (smallest
+    // non-zero value 2^-72), a sample -- one more scaled weight -- the reference's times 2^51 (smallest non-zero
+    // product 2^-95, differences are multiples of 2^-118: all normal).  The residual takes the sample through
+    // fma(v, 2^-51, db) = rn(v0 + db) (the product is exact), the gradient differences keep the factor into the double
+    // sums, where it is a power of two again and leaves after the loop together with the 0.5 of the central difference.
     if (!sparse) {
+      constexpr float SC = 1.2676506002282294e30f;  // 2^100
+      constexpr float BIGS = 8388608.0f * SC;       // 2^123: a coordinate added to it (rounding down) loses its fraction
+      constexpr float UNS = 4.440892098500626e-16f; // 2^-51
       float badv = 0.0f;
       // lanes without a fast slot walk a harmless patch in the middle of their window
-      const float pbx = fast ? bx : (float)(HALF + 5) + 0.5f, pby = fast ? by : (float)(HALF + 3) + 0.5f;
-      const float q00 = fast ? a00 : 1.0f, q01 = fast ? a01 : 0.0f, q10 = fast ? a10 : 0.0f, q11 = fast ? a11 : 1.0f;
-      // window element index from the mantissas of ty = 2^23 + floor(sy) and tx = 2^23 + floor(sx):
-      // bits(ty) * WIN_W + bits(tx) - kk, with kk = (WIN_W + 1) * bits(2^23) + origin (mod 2^32)
-      const unsigned int kk = (unsigned int)(WIN_W + 1) * 0x4B000000u + (unsigned int)(fast ? win_y0 * WIN_W + win_x0 : 0);
-      // one flat walk over the P * P pixels (row-major, the reference's order), PAGK_LANES_UNROLL pixels per trip with
-      // their template values in one vector load; the last pixel's template value is a register
-      const float2 *pix = HALF == 5 ? c_pix5 : c_pix10;
-      auto pixel = [&](const int p, const float tval) {
-        const float2 xy = pix[p];
-        const float xf = xy.x, yf = xy.y;
-        float wx = xf, wy = yf;
-        if (AFFINE) { wx = q00 * xf + q01 * yf; wy = q10 * xf + q11 * yf; }
-        const float sx = pbx + wx, sy = pby + wy;
+      const float pbx = (fast ? bx : (float)(HALF + 5) + 0.5f) * SC, pby = (fast ? by : (float)(HALF + 3) + 0.5f) * SC;
+      const f2 PBX = {pbx, pbx}, PBY = {pby, pby};
+      const float q00 = (fast ? a00 : 1.0f) * SC, q01 = (fast ? a01 : 0.0f) * SC, q10 = (fast ? a10 : 0.0f) * SC, q11 = (fast ? a11 : 1.0f) * SC;
+      const f2 Q00 = {q00, q00}, Q01 = {q01, q01}, Q10 = {q10, q10}, Q11 = {q11, q11};
+      const f2 ONE = {unit, unit}, BIG = {BIGS, BIGS}, NBIG = {-BIGS, -BIGS}, P1 = {SC, SC}, UN = {UNS, UNS};
+      const f2 DB = {db, db}, GAIN = {gain, gain};
+      // window byte index of the tap left of (floor(sx), floor(sy)) from the mantissas of ty = 2^123 + floor(sy) * 2^100
+      // and tx: bits(ty) * WIN_W + bits(tx) - kk, kk = (WIN_W + 1) * bits(2^123) + origin + 1 (mod 2^32)
+      const unsigned int kk = (unsigned int)(WIN_W + 1) * 0x7D000000u + (unsigned int)(fast ? win_y0 * WIN_W + win_x0 : 0) + 1u;
+#if PAGK_LANES_LDSPAIRS
+      const float4 *pix = s_pairs;
+#else
+      const float4 *pix = HALF == 5 ? c_pair5 : c_pair10;
+#endif
+      // the four taps of a window row start at byte i1 of the lane's window; tap j sits at
+      // A0 + j + 124 * ((s + j) >> 2), A0 = (i1 >> 2) * 128 + (i1 & 3), s = i1 & 3 (a word of the lane is 128 bytes from the
+      // next one); rows are ROW_BYTES apart
+      auto bases = [&](const unsigned int i1, const unsigned char *&b0, const unsigned char *&b1, const unsigned char *&b2, const unsigned char *&b3) {
+        CHECK_IDX((int)i1, WIN_W, WIN_W * WIN_H - 2 * WIN_W - 4);
+        const unsigned int s = i1 & 3u;
+        b0 = mywin + ((i1 >> 2) * 124u + i1);
+        b1 = b0 + ((s + 1u) & 4u) * 31u; b2 = b0 + ((s + 2u) & 4u) * 31u; b3 = b0 + ((s + 3u) & 4u) * 31u;
+      };
+      // pixels p = 2 * k2 (.x) and p + 1 (.y); `both` false: only .x enters the sums (the last pixel of an odd patch)
+      auto pixels = [&](const int k2, const f2 tv, const bool both) {
+        const float4 xy = pix[k2];
+        const f2 XF = {xy.x, xy.y}, YF = {xy.z, xy.w};
+        f2 SX, SY;
+        if (AFFINE) {
+          const f2 WX = fma2(mul2(Q00, XF), ONE, mul2(Q01, YF)), WY = fma2(mul2(Q10, XF), ONE, mul2(Q11, YF));
+          SX = add2(PBX, WX); SY = add2(PBY, WY);
+        } else {  // the scaled offset x * 2^100 is exact: the fused form rounds once, like the sum it stands for
+          SX = fma2(XF, P1, PBX); SY = fma2(YF, P1, PBY);
+        }
         // floor for 0 <= x < 2^22: x + 2^23 rounded DOWN is 2^23 + floor(x) exactly; taking 2^23 off is exact
-        const float tx = __fadd_rd(sx, 8388608.0f), ty = __fadd_rd(sy, 8388608.0f);
-        const float fx = tx - 8388608.0f, fy = ty - 8388608.0f;
-        const float xx = sx - fx, yy = sy - fy;
-        const float wa = 1.0f - xx, wb = 1.0f - yy;
-        const float X1 = sx + 1.0f, Y1 = sy + 1.0f;
-        const float xx1 = X1 - (fx + 1.0f), yy1 = Y1 - (fy + 1.0f);
-        const float wa1 = 1.0f - xx1, wb1 = 1.0f - yy1;
-        badv = fmaxf(badv, fmaxf(xx1, yy1));
-        const int widx = (int)((unsigned int)__float_as_int(ty) * (unsigned int)WIN_W + (unsigned int)__float_as_int(tx) - kk);
-        CHECK_IDX(widx, WIN_W + 1, WIN_W * WIN_H - 2 * WIN_W - 3);
-        const E *w = mywin + widx;
-        const float m0 = elt_f(w[-WIN_W]), m1 = elt_f(w[-WIN_W + 1]);
-        const float c_1 = elt_f(w[-1]), c0 = elt_f(w[0]), c1 = elt_f(w[1]), c2 = elt_f(w[2]);
-        const float d_1 = elt_f(w[WIN_W - 1]), d0 = elt_f(w[WIN_W]), d1 = elt_f(w[WIN_W + 1]), d2 = elt_f(w[WIN_W + 2]);
-        const float n0 = elt_f(w[2 * WIN_W]), n1 = elt_f(w[2 * WIN_W + 1]);
-        const float Hm = wa * m0 + xx * m1;
-        const float H0 = wa * c0 + xx * c1, H0p = wa1 * c1 + xx1 * c2, H0m = wa * c_1 + xx * c0;
-        const float H1 = wa * d0 + xx * d1, H1p = wa1 * d1 + xx1 * d2, H1m = wa * d_1 + xx * d0;
-        const float H2 = wa * n0 + xx * n1;
-        const float v0 = wb * H0 + yy * H1;
-        const float vx1 = wb * H0p + yy * H1p, vx2 = wb * H0m + yy * H1m;
-        const float vy1 = wb1 * H1 + yy1 * H2, vy2 = wb * Hm + yy * H0;
-        const float e = (v0 + db) - gain * tval;
-        // twice the gradient: Ix = 0.5 * gxf is an exact halving, and every sum below that contains Ix or Iy is the
-        // reference's sum times a power of two at every step (scaling by 2^k commutes with rounding; nothing here is
-        // near the subnormals), so the factors 0.5 and 0.25 are applied once, after the loop
-        const float gxf = vx1 - vx2, gyf = vy1 - vy2, mf = -e;
+        const f2 TX = addrd2(SX, BIG), TY = addrd2(SY, BIG);
+        const f2 FX = add2(TX, NBIG), FY = add2(TY, NBIG);
+        const f2 XX = sub2(SX, FX), YY = sub2(SY, FY);
+        const f2 WA = sub2(P1, XX), WB = sub2(P1, YY);
+        const f2 X1 = add2(SX, P1), Y1 = add2(SY, P1);
+        const f2 XX1 = sub2(X1, add2(FX, P1)), YY1 = sub2(Y1, add2(FY, P1));
+        const f2 WA1 = sub2(P1, XX1), WB1 = sub2(P1, YY1);
+        badv = fmaxf(badv, fmaxf(XX1.x, YY1.x));
+        if (both) badv = fmaxf(badv, fmaxf(XX1.y, YY1.y));
+        const unsigned int ip = (unsigned int)__float_as_int(TY.x) * (unsigned int)WIN_W + (unsigned int)__float_as_int(TX.x) - kk;
+        const unsigned int iq = (unsigned int)__float_as_int(TY.y) * (unsigned int)WIN_W + (unsigned int)__float_as_int(TX.y) - kk;
+        const unsigned char *p0, *p1, *p2, *p3, *q0, *q1, *q2, *q3;
+        bases(ip, p0, p1, p2, p3); bases(iq, q0, q1, q2, q3);
+        constexpr int R = C::ROW_BYTES;
+#define PAGK_TAP(pb, qb, o) f2{__uint_as_float((unsigned int)pb[o]), __uint_as_float((unsigned int)qb[o])}
+        const f2 m0 = PAGK_TAP(p1, q1, 1 - R), m1 = PAGK_TAP(p2, q2, 2 - R);
+        const f2 c_1 = PAGK_TAP(p0, q0, 0), c0 = PAGK_TAP(p1, q1, 1), c1 = PAGK_TAP(p2, q2, 2), c2 = PAGK_TAP(p3, q3, 3);
+        const f2 d_1 = PAGK_TAP(p0, q0, R), d0 = PAGK_TAP(p1, q1, 1 + R), d1 = PAGK_TAP(p2, q2, 2 + R), d2 = PAGK_TAP(p3, q3, 3 + R);
+        const f2 n0 = PAGK_TAP(p1, q1, 1 + 2 * R), n1 = PAGK_TAP(p2, q2, 2 + 2 * R);
+#undef PAGK_TAP
+        // rn(rn(w * a) + rn(u * b)): two products and a sum that ptxas cannot contract
+#define PAGK_LERP(w, a, u, b) fma2(mul2(w, a), ONE, mul2(u, b))
+        const f2 Hm = PAGK_LERP(WA, m0, XX, m1);
+        const f2 H0 = PAGK_LERP(WA, c0, XX, c1), H0p = PAGK_LERP(WA1, c1, XX1, c2), H0m = PAGK_LERP(WA, c_1, XX, c0);
+        const f2 H1 = PAGK_LERP(WA, d0, XX, d1), H1p = PAGK_LERP(WA1, d1, XX1, d2), H1m = PAGK_LERP(WA, d_1, XX, d0);
+        const f2 H2 = PAGK_LERP(WA, n0, XX, n1);
+        const f2 v0 = PAGK_LERP(WB, H0, YY, H1);
+        const f2 vx1 = PAGK_LERP(WB, H0p, YY, H1p), vx2 = PAGK_LERP(WB, H0m, YY, H1m);
+        const f2 vy1 = PAGK_LERP(WB1, H1, YY1, H2), vy2 = PAGK_LERP(WB, Hm, YY, H0);
+#undef PAGK_LERP
+        // -e = gain * T - (v0 + db) (the reference's e = (v0 + db) - gain * T negated: exact)
+        const f2 U = fma2(v0, UN, DB);
+        const f2 MF = fma2(mul2(GAIN, tv), ONE, f2{-U.x, -U.y});
+        // 2^52 times the gradient: Ix = 0.5 * (vx1 - vx2) is an exact halving, and every sum below that contains Ix or Iy is
+        // the reference's sum times a power of two at every step, so the factors are applied once, after the loop
+        const f2 GX = sub2(vx1, vx2), GY = sub2(vy1, vy2);
+        const f2 M2 = mul2(MF, MF);
         // J = (Ix, Iy, c, 1) as double; b += -J * e; H += J * J^T; cost += e * e (float), reference :264-299.
         // Each product of two float-valued doubles is exact, so DFMA rounds like the separate mul + add.
         // (H[2][2] = sum of c*c does not depend on the samples: it comes with the template record.)
-        const double x = (double)gxf, y = (double)gyf, mm = (double)mf;
-        S.h00 = fma(x, x, S.h00); S.h10 = fma(y, x, S.h10); S.h11 = fma(y, y, S.h11);
-        S.h20 = fma(c, x, S.h20); S.h21 = fma(c, y, S.h21);
-        S.h30 = S.h30 + x; S.h31 = S.h31 + y;
-        S.b0 = fma(x, mm, S.b0); S.b1 = fma(y, mm, S.b1); S.b2 = fma(c, mm, S.b2); S.b3 = S.b3 + mm;
-        S.cost = S.cost + mf * mf;
+        {
+          const double x = (double)GX.x, y = (double)GY.x, mm = (double)MF.x;
+          S.h00 = fma(x, x, S.h00); S.h10 = fma(y, x, S.h10); S.h11 = fma(y, y, S.h11);
+          S.h20 = fma(c, x, S.h20); S.h21 = fma(c, y, S.h21);
+          S.h30 = S.h30 + x; S.h31 = S.h31 + y;
+          S.b0 = fma(x, mm, S.b0); S.b1 = fma(y, mm, S.b1); S.b2 = fma(c, mm, S.b2); S.b3 = S.b3 + mm;
+          S.cost = S.cost + M2.x;
+        }
+        if (both) {
+          const double x = (double)GX.y, y = (double)GY.y, mm = (double)MF.y;
+          S.h00 = fma(x, x, S.h00); S.h10 = fma(y, x, S.h10); S.h11 = fma(y, y, S.h11);
+          S.h20 = fma(c, x, S.h20); S.h21 = fma(c, y, S.h21);
+          S.h30 = S.h30 + x; S.h31 = S.h31 + y;
+          S.b0 = fma(x, mm, S.b0); S.b1 = fma(y, mm, S.b1); S.b2 = fma(c, mm, S.b2); S.b3 = S.b3 + mm;
+          S.cost = S.cost + M2.y;
+        }
       };
-      constexpr int V = PAGK_LANES_UNROLL;
-      static_assert((NP - 1) % V == 0 && (V == 4 || V == 2), "vector width of the template loads");
-      // T streams from the record (L1 / L2): the next trip's vector is loaded before this trip's pixels are computed
-      if (V == 4) {
-        float4 t4 = __ldg(Tg);
+      // one flat walk over the P * P pixels (row-major, the reference's order), two pairs per trip with their template
+      // values in one vector load (L1 / L2; the next trip's vector is loaded before this trip's pixels are computed);
+      // the last pixel's template value is a register
+      static_assert((NP - 1) % (4 * PAGK_LANES_TRIP) == 0, "vector loads of the template per trip");
+      constexpr int NV = (NP - 1) / 4;  // vectors of four template values
+#if !PAGK_LANES_TPRE
+      float4 t4[PAGK_LANES_TRIP];
+#pragma unroll
+      for (int u = 0; u < PAGK_LANES_TRIP; ++u) t4[u] = __ldg(Tg + u);
+#endif
 #pragma unroll 1
-        for (int j = 0; j < (NP - 1) / 4; ++j) {
-          const float4 nx = __ldg(Tg + min(j + 1, (NP - 1) / 4 - 1));
-          pixel(4 * j, t4.x); pixel(4 * j + 1, t4.y); pixel(4 * j + 2, t4.z); pixel(4 * j + 3, t4.w);
-          t4 = nx;
+      for (int j = 0; j < NV; j += PAGK_LANES_TRIP) {
+        float4 nx[PAGK_LANES_TRIP];
+#pragma unroll
+        for (int u = 0; u < PAGK_LANES_TRIP; ++u) nx[u] = __ldg(Tg + min(j + PAGK_LANES_TRIP + u, NV - 1));
+#pragma unroll
+        for (int u = 0; u < PAGK_LANES_TRIP; ++u) {
+          pixels(2 * (j + u), f2{t4[u].x, t4[u].y}, true); pixels(2 * (j + u) + 1, f2{t4[u].z, t4[u].w}, true);
         }
-      } else {
-        const float2 *Tg2 = reinterpret_cast<const float2 *>(Tg);
-        float2 t2 = __ldg(Tg2);
-#pragma unroll 1
-        for (int j = 0; j < (NP - 1) / 2; ++j) {
-          const float2 nx = __ldg(Tg2 + min(j + 1, (NP - 1) / 2 - 1));
-          pixel(2 * j, t2.x); pixel(2 * j + 1, t2.y);
-          t2 = nx;
-        }
+#pragma unroll
+        for (int u = 0; u < PAGK_LANES_TRIP; ++u) t4[u] = nx[u];
       }
-      pixel(NP - 1, tlast);
-      S.h00 *= 0.25; S.h10 *= 0.25; S.h11 *= 0.25;
-      S.h20 *= 0.5; S.h21 *= 0.5; S.h30 *= 0.5; S.h31 *= 0.5; S.b0 *= 0.5; S.b1 *= 0.5;
-      coop |= active && fast && (badv >= 1.0f);
+      pixels((NP - 1) / 2, f2{tlast, tlast}, false);
+      constexpr double G1 = 2.220446049250313e-16;  // 2^-52: the samples' 2^51 and the central difference's 2
+      S.h00 *= G1 * G1; S.h10 *= G1 * G1; S.h11 *= G1 * G1;
+      S.h20 *= G1; S.h21 *= G1; S.h30 *= G1; S.h31 *= G1; S.b0 *= G1; S.b1 *= G1;
+      lockbad = active && fast && (badv >= SC);
+      coop |= lockbad;
     }
     PROF(3);
 
-    // ------------------------------------------------------------------ the cooperative pass, one slot at a time
+    // ------------------------------------------------------------------ the pixel-parallel pass, COOP_BUFS slots at a time
     // For slots whose samples may clamp at the image border, slots that hit the rounding case above, slots whose
-    // box does not fit the window (sampled straight from the level) and every live slot of a sparse warp.
-    // Lanes = pixels: each of the five samples through GetPixelValue on its own -> records; then lanes =
-    // accumulators: the twelve double sums and the float cost walk the records in pixel order.
+    // box does not fit the window (sampled straight from the level) and every live slot of a sparse warp (the tail of a
+    // launch, small batches: a pass then takes about a microsecond per slot instead of ten for the lockstep pass).
+    // Lanes = pixels: samples -> records (Ix, Iy, -e) in the slot's buffer; then lanes = accumulators: the twelve double
+    // sums and the float cost walk the records in pixel order (lanes 0..15 the first buffer, 16..31 the second).
+    // The window of a slot lives in ONE bank (its lane's), which lanes = pixels would hit 32 ways, so the slot's window
+    // is first copied row-major into the buffer.  A slot without clamps (`fast`) uses the shared interpolations of the
+    // lockstep pass (same argument); a pixel that meets the excluded rounding case evaluates its five samples one by
+    // one like every pixel of the other slots (PatchMatch::GetPixelValue semantics).
     {
       unsigned m = __ballot_sync(FULL, coop);
+      PROF_ADD(13, __popc(m)); PROF_ADD(14, sparse ? 1 : 0); PROF_ADD(15, __popc(__ballot_sync(FULL, restage)));
+      constexpr int NB = C::COOP_BUFS, CH = C::COOP_CH;
       while (m) {
-        const int s = __ffs(m) - 1;
-        m &= m - 1;
-        const float sbx = __shfl_sync(FULL, bx, s), sby = __shfl_sync(FULL, by, s);
-        const float s00 = __shfl_sync(FULL, a00, s), s01 = __shfl_sync(FULL, a01, s), s10 = __shfl_sync(FULL, a10, s), s11 = __shfl_sync(FULL, a11, s);
-        const float sdb = __shfl_sync(FULL, db, s), sgain = __shfl_sync(FULL, gain, s), scv = __shfl_sync(FULL, cval, s);
-        const float stl = __shfl_sync(FULL, tlast, s);
-        const int scols = __shfl_sync(FULL, cols, s), srows = __shfl_sync(FULL, rows, s), sp = __shfl_sync(FULL, pitch, s);
-        const int swx0 = __shfl_sync(FULL, win_x0, s), swy0 = __shfl_sync(FULL, win_y0, s);
-        const int swin = __shfl_sync(FULL, (int)windowable, s);
-        const int spair = __shfl_sync(FULL, pair, s), slevel = __shfl_sync(FULL, level, s);
-        const unsigned char *img2 = images + (size_t)(spair * 2 + 1) * slot_bytes + s_off[slevel];  // the u8 level
-        const E *win = reinterpret_cast<const E *>(wwin + s * C::WIN_STRIDE);
-        const float *T = reinterpret_cast<const float *>(__shfl_sync(FULL, (unsigned long long)Tg, s));
-        const float gc = (float)scols, gr = (float)srows, gc1 = (float)(scols - 1), gr1 = (float)(srows - 1);
+        int sl[NB];
+        float sbx[NB], sby[NB], s00[NB], s01[NB], s10[NB], s11[NB], sdb[NB], sgain[NB], stl[NB];
+        int scols[NB], srows[NB], sp[NB], swx0[NB], swy0[NB], skind[NB];
+        const unsigned char *img2[NB];
+        const float *Tp[NB];
+        __syncwarp();
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          sl[b] = m ? __ffs(m) - 1 : -1;
+          m &= m - 1;
+          const int s = sl[b] < 0 ? 0 : sl[b];
+          sbx[b] = __shfl_sync(FULL, bx, s); sby[b] = __shfl_sync(FULL, by, s);
+          s00[b] = __shfl_sync(FULL, a00, s); s01[b] = __shfl_sync(FULL, a01, s); s10[b] = __shfl_sync(FULL, a10, s); s11[b] = __shfl_sync(FULL, a11, s);
+          sdb[b] = __shfl_sync(FULL, db, s); sgain[b] = __shfl_sync(FULL, gain, s); stl[b] = __shfl_sync(FULL, tlast, s);
+          const float scv = __shfl_sync(FULL, cval, s);
+          scols[b] = __shfl_sync(FULL, cols, s); srows[b] = __shfl_sync(FULL, rows, s); sp[b] = __shfl_sync(FULL, pitch, s);
+          swx0[b] = __shfl_sync(FULL, win_x0, s); swy0[b] = __shfl_sync(FULL, win_y0, s);
+          // 0: no clamp can fire (shared interpolations), 1: per-sample from the window, 2: per-sample from the level
+          skind[b] = __shfl_sync(FULL, windowable ? (fast && !lockbad ? 0 : 1) : 2, s);
+          const int spair = __shfl_sync(FULL, pair, s), slevel = __shfl_sync(FULL, level, s);
+          img2[b] = images + (size_t)(spair * 2 + 1) * slot_bytes + s_off[slevel];  // the u8 level
+          Tp[b] = reinterpret_cast<const float *>(__shfl_sync(FULL, (unsigned long long)Tg, s));
+          if (sl[b] >= 0) {
+            float *buf = scratch + b * C::BUF_FLOATS;
+            if (lane == 0) { buf[CH * 3] = scv; buf[CH * 3 + 1] = 1.0f; }
+            if (skind[b] != 2) {  // the slot's window, row-major
+              const unsigned int *src = reinterpret_cast<const unsigned int *>(wwin) + s;
+              unsigned int *lin = reinterpret_cast<unsigned int *>(buf + C::COOP_LIN);
+#pragma unroll
+              for (int k = 0; k < (C::WIN_WORDS + 31) / 32; ++k) {
+                const int w = lane + 32 * k;
+                if (w < C::WIN_WORDS) lin[w] = src[w * 32];
+              }
+            }
+          }
+        }
         double acc = 0.0;
         float cacc = 0.f;
-        __syncwarp();
-        if (lane == 0) { scratch[32 * 3] = scv; scratch[32 * 3 + 1] = 1.0f; }
-        // the patch in chunks of 32 pixels: records into the scratch, then every accumulator walks the chunk in order
 #pragma unroll 1
-        for (int p0 = 0; p0 < NP; p0 += 32) {
-          const int p = p0 + lane;
-          if (p < NP) {
-            const int py = p / P, px = p - py * P;
-            const float xf = (float)(px - HALF), yf = (float)(py - HALF);
-            float wx = xf, wy = yf;
-            if (AFFINE) { wx = s00 * xf + s01 * yf; wy = s10 * xf + s11 * yf; }
-            const float sx = sbx + wx, sy = sby + wy;
-            float v0, vx1, vx2, vy1, vy2;
-            if (swin) {
-              v0 = window_sample<WIN_W, WIN_H>(win, swx0, swy0, gc, gc1, gr, gr1, sx, sy);
-              vx1 = window_sample<WIN_W, WIN_H>(win, swx0, swy0, gc, gc1, gr, gr1, sx + 1.0f, sy);
-              vx2 = window_sample<WIN_W, WIN_H>(win, swx0, swy0, gc, gc1, gr, gr1, sx - 1.0f, sy);
-              vy1 = window_sample<WIN_W, WIN_H>(win, swx0, swy0, gc, gc1, gr, gr1, sx, sy + 1.0f);
-              vy2 = window_sample<WIN_W, WIN_H>(win, swx0, swy0, gc, gc1, gr, gr1, sx, sy - 1.0f);
-            } else {
-              v0 = pagk_sample_call(img2, sp, scols, srows, sx, sy);
-              vx1 = pagk_sample_call(img2, sp, scols, srows, sx + 1.0f, sy);
-              vx2 = pagk_sample_call(img2, sp, scols, srows, sx - 1.0f, sy);
-              vy1 = pagk_sample_call(img2, sp, scols, srows, sx, sy + 1.0f);
-              vy2 = pagk_sample_call(img2, sp, scols, srows, sx, sy - 1.0f);
+        for (int p0 = 0; p0 < NP; p0 += CH) {
+          __syncwarp();
+#pragma unroll
+          for (int b = 0; b < NB; ++b) {
+            if (sl[b] < 0) continue;
+            float *buf = scratch + b * C::BUF_FLOATS;
+            const unsigned char *lin = reinterpret_cast<const unsigned char *>(buf + C::COOP_LIN);
+            const float gc = (float)scols[b], gr = (float)srows[b], gc1 = (float)(scols[b] - 1), gr1 = (float)(srows[b] - 1);
+            const int kind = skind[b];
+            float tv[CH / 32];
+#pragma unroll
+            for (int k = 0; k < CH / 32; ++k) {
+              const int p = p0 + lane + 32 * k;
+              tv[k] = p < NP - 1 ? __ldg(Tp[b] + p) : stl[b];
             }
-            const float tval = p < NP - 1 ? __ldg(T + p) : stl;
-            const float e = (v0 + sdb) - sgain * tval;
-            scratch[3 * lane] = 0.5f * (vx1 - vx2);
-            scratch[3 * lane + 1] = 0.5f * (vy1 - vy2);
-            scratch[3 * lane + 2] = -e;
+#pragma unroll 2
+            for (int k = 0; k < CH / 32; ++k) {
+              const int q = lane + 32 * k, p = p0 + q;
+              if (p >= NP) continue;
+              const int py = p / P, px = p - py * P;
+              const float xf = (float)(px - HALF), yf = (float)(py - HALF);
+              float wx = xf, wy = yf;
+              if (AFFINE) { wx = s00[b] * xf + s01[b] * yf; wy = s10[b] * xf + s11[b] * yf; }
+              const float sx = sbx[b] + wx, sy = sby[b] + wy;
+              float v0, vx1, vx2, vy1, vy2;
+              bool each = kind != 0;
+              if (kind == 0) {
+                // floor for 0 <= x < 2^22: x + 2^23 rounded DOWN is 2^23 + floor(x) exactly; taking 2^23 off is exact
+                const float tx = __fadd_rd(sx, 8388608.0f), ty = __fadd_rd(sy, 8388608.0f);
+                const float fx = tx - 8388608.0f, fy = ty - 8388608.0f;
+                const float xx = sx - fx, yy = sy - fy;
+                const float wa = 1.0f - xx, wb = 1.0f - yy;
+                const float X1 = sx + 1.0f, Y1 = sy + 1.0f;
+                const float xx1 = X1 - (fx + 1.0f), yy1 = Y1 - (fy + 1.0f);
+                const float wa1 = 1.0f - xx1, wb1 = 1.0f - yy1;
+                each = fmaxf(xx1, yy1) >= 1.0f;
+                const int widx = (__float_as_int(ty) - 0x4B000000 - swy0[b]) * WIN_W + (__float_as_int(tx) - 0x4B000000 - swx0[b]);
+                CHECK_IDX(widx, WIN_W + 1, WIN_W * WIN_H - 2 * WIN_W - 3);
+                const unsigned char *w = lin + widx;
+                const float m0 = u8f(w[-WIN_W]), m1 = u8f(w[-WIN_W + 1]);
+                const float c_1 = u8f(w[-1]), c0 = u8f(w[0]), c1 = u8f(w[1]), c2 = u8f(w[2]);
+                const float d_1 = u8f(w[WIN_W - 1]), d0 = u8f(w[WIN_W]), d1 = u8f(w[WIN_W + 1]), d2 = u8f(w[WIN_W + 2]);
+                const float n0 = u8f(w[2 * WIN_W]), n1 = u8f(w[2 * WIN_W + 1]);
+                const float Hm = wa * m0 + xx * m1;
+                const float H0 = wa * c0 + xx * c1, H0p = wa1 * c1 + xx1 * c2, H0m = wa * c_1 + xx * c0;
+                const float H1 = wa * d0 + xx * d1, H1p = wa1 * d1 + xx1 * d2, H1m = wa * d_1 + xx * d0;
+                const float H2 = wa * n0 + xx * n1;
+                v0 = wb * H0 + yy * H1;
+                vx1 = wb * H0p + yy * H1p; vx2 = wb * H0m + yy * H1m;
+                vy1 = wb1 * H1 + yy1 * H2; vy2 = wb * Hm + yy * H0;
+              }
+              if (each) {
+                if (kind != 2) {
+                  v0 = window_sample<WIN_W, WIN_H>(lin, swx0[b], swy0[b], gc, gc1, gr, gr1, sx, sy);
+                  vx1 = window_sample<WIN_W, WIN_H>(lin, swx0[b], swy0[b], gc, gc1, gr, gr1, sx + 1.0f, sy);
+                  vx2 = window_sample<WIN_W, WIN_H>(lin, swx0[b], swy0[b], gc, gc1, gr, gr1, sx - 1.0f, sy);
+                  vy1 = window_sample<WIN_W, WIN_H>(lin, swx0[b], swy0[b], gc, gc1, gr, gr1, sx, sy + 1.0f);
+                  vy2 = window_sample<WIN_W, WIN_H>(lin, swx0[b], swy0[b], gc, gc1, gr, gr1, sx, sy - 1.0f);
+                } else {
+                  v0 = pagk_sample_call(img2[b], sp[b], scols[b], srows[b], sx, sy);
+                  vx1 = pagk_sample_call(img2[b], sp[b], scols[b], srows[b], sx + 1.0f, sy);
+                  vx2 = pagk_sample_call(img2[b], sp[b], scols[b], srows[b], sx - 1.0f, sy);
+                  vy1 = pagk_sample_call(img2[b], sp[b], scols[b], srows[b], sx, sy + 1.0f);
+                  vy2 = pagk_sample_call(img2[b], sp[b], scols[b], srows[b], sx, sy - 1.0f);
+                }
+              }
+              const float e = (v0 + sdb[b]) - sgain[b] * tv[k];
+              buf[3 * q] = 0.5f * (vx1 - vx2);
+              buf[3 * q + 1] = 0.5f * (vy1 - vy2);
+              buf[3 * q + 2] = -e;
+            }
           }
           __syncwarp();
-          const int n = min(32, NP - p0);
-          const float *pa = scratch + offA, *pb = scratch + offB, *pm = scratch + 2;
+          const int n = min(CH, NP - p0);
+          const float *base = scratch + cbuf * C::BUF_FLOATS;
+          const float *pa = base + offA, *pb = base + offB, *pm = base + 2;
 #pragma unroll 4
           for (int q = 0; q < n; ++q) {
             const float fa = *pa, fb = *pb, fm = *pm;
@@ -775,15 +977,23 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
             acc = fma((double)fa, (double)fb, acc);
             cacc = cacc + fm * fm;
           }
-          __syncwarp();
         }
-        const double t0 = __shfl_sync(FULL, acc, 0), t1 = __shfl_sync(FULL, acc, 1), t2 = __shfl_sync(FULL, acc, 2),
-                     t3 = __shfl_sync(FULL, acc, 3), t4 = __shfl_sync(FULL, acc, 4), t6 = __shfl_sync(FULL, acc, 6),
-                     t7 = __shfl_sync(FULL, acc, 7), t8 = __shfl_sync(FULL, acc, 8), t9 = __shfl_sync(FULL, acc, 9),
-                     t10 = __shfl_sync(FULL, acc, 10), t11 = __shfl_sync(FULL, acc, 11);
-        if (lane == s) {
-          S.h00 = t0; S.h10 = t1; S.h11 = t2; S.h20 = t3; S.h21 = t4; S.h30 = t6; S.h31 = t7;
-          S.b0 = t8; S.b1 = t9; S.b2 = t10; S.b3 = t11; S.cost = cacc;
+        // the sums back to the slots' lanes through the buffers
+        {
+          float *base = scratch + cbuf * C::BUF_FLOATS;
+          double *res = reinterpret_cast<double *>(base + C::COOP_RES);
+          if (role16 < 12) res[role16] = acc;
+          if (role16 == 0) base[C::COOP_RES + 24] = cacc;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          if (lane == sl[b]) {
+            const float *base = scratch + b * C::BUF_FLOATS;
+            const double *res = reinterpret_cast<const double *>(base + C::COOP_RES);
+            S.h00 = res[0]; S.h10 = res[1]; S.h11 = res[2]; S.h20 = res[3]; S.h21 = res[4]; S.h30 = res[6]; S.h31 = res[7];
+            S.b0 = res[8]; S.b1 = res[9]; S.b2 = res[10]; S.b3 = res[11]; S.cost = base[C::COOP_RES + 24];
+          }
         }
       }
       __syncwarp();
@@ -861,7 +1071,7 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
 
 // -------------------------------------------------------------------------------------------------
 // whether the alignment kernel stages its windows from the 16-bit plane of the current images (build option)
-bool pagk_lk_lanes_win16() { return PAGK_WIN16 != 0; }
+bool pagk_lk_lanes_win16() { return false; }  // the bfloat16 window plane of an earlier build is gone
 
 bool pagk_lk_lanes_supported(const PagkMode &mode) {
   return (mode.half == 5 || mode.half == 10) && mode.iterations >= 1;
@@ -877,48 +1087,45 @@ size_t pagk_lk_lanes_record_bytes(int half) {
   return half == 5 ? (size_t)LanesCfg<5>::REC_BYTES : half == 10 ? (size_t)LanesCfg<10>::REC_BYTES : 0;
 }
 
-template <int HALF, bool AFFINE>
+template <int HALF, bool AFFINE, int WSM>
 static cudaError_t configure_lanes() {
-  return cudaFuncSetAttribute(pagk_lk_lanes_kernel<HALF, AFFINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, LanesCfg<HALF>::SMEM_BYTES);
+  return cudaFuncSetAttribute(pagk_lk_lanes_kernel<HALF, AFFINE, WSM>, cudaFuncAttributeMaxDynamicSharedMemorySize, LanesCfg<HALF, WSM>::SMEM_BYTES);
 }
 
 template <int HALF>
-static cudaError_t upload_pix(const float2 *sym) {
-  constexpr int P = 2 * HALF + 1;
-  float2 h[P * P];
-  for (int p = 0; p < P * P; ++p) h[p] = make_float2((float)(p % P - HALF), (float)(p / P - HALF));
-  return cudaMemcpyToSymbol(*reinterpret_cast<const float2(*)[P * P]>(sym), h, sizeof(h));
+static cudaError_t upload_pairs(const float4 *sym) {
+  constexpr int P = 2 * HALF + 1, NP = P * P, N2 = (NP + 1) / 2;
+  float4 h[N2];
+  for (int k = 0; k < N2; ++k) {
+    const int p = 2 * k, q = p + 1 < NP ? p + 1 : p;
+    h[k] = make_float4((float)(p % P - HALF), (float)(q % P - HALF), (float)(p / P - HALF), (float)(q / P - HALF));
+  }
+  return cudaMemcpyToSymbol(*reinterpret_cast<const float4(*)[N2]>(sym), h, sizeof(h));
 }
 
 // per device, from pagk_create after cudaSetDevice (function attributes and __constant__ data belong to the device)
 int pagk_lk_lanes_configure() {
-  cudaError_t e = upload_pix<5>(c_pix5);
-  if (e == cudaSuccess) e = upload_pix<10>(c_pix10);
-  if (e == cudaSuccess) e = configure_lanes<5, true>();
-  if (e == cudaSuccess) e = configure_lanes<5, false>();
-  if (e == cudaSuccess) e = configure_lanes<10, true>();
-  if (e == cudaSuccess) e = configure_lanes<10, false>();
+  cudaError_t e = upload_pairs<5>(c_pair5);
+  if (e == cudaSuccess) e = upload_pairs<10>(c_pair10);
+  if (e == cudaSuccess) e = configure_lanes<5, true, PAGK_LANES_WARPS5>();
+  if (e == cudaSuccess) e = configure_lanes<5, false, PAGK_LANES_WARPS5>();
+  if (e == cudaSuccess) e = configure_lanes<5, true, PAGK_LANES_WARPS5_BIG>();
+  if (e == cudaSuccess) e = configure_lanes<5, false, PAGK_LANES_WARPS5_BIG>();
+  if (e == cudaSuccess) e = configure_lanes<10, true, 7>();
+  if (e == cudaSuccess) e = configure_lanes<10, false, 7>();
   return (int)e;
 }
 
-template <int HALF, bool AFFINE>
-static int launch_lanes(const unsigned char *images, const PagkGeom &g, const PagkPairConst *pcs, const float2 *keys_un,
-                        const PagkOutPtrs &out, const PagkMode &mode, int max_keys, int n_max, int n_pairs,
-                        int *work_counter, int *next_counter, int *progress, int epoch, int n_sms, unsigned char *tmpl,
-                        const PagkTmaLevels *tmaps, cudaStream_t st, long long *prof) {
-  using C = LanesCfg<HALF>;
+template <int HALF, bool AFFINE, int WSM>
+static int launch_lanes_w(const unsigned char *images, const PagkGeom &g, const PagkPairConst *pcs, const float2 *keys_un,
+                          const PagkOutPtrs &out, const PagkMode &mode, int max_keys, int n_max, int n_pairs,
+                          int *work_counter, int *next_counter, int *progress, int epoch, int n_sms, unsigned char *tmpl,
+                          cudaStream_t st, long long *prof) {
+  using C = LanesCfg<HALF, WSM>;
   const long long total = (long long)n_max * n_pairs;
-  {  // K3a: 32 items per warp
-    constexpr int W = TmplCfg<HALF>::WARPS;
-    const long long items = total * mode.levels, groups = (items + 31) / 32;
-    pagk_lk_template_kernel<HALF><<<(unsigned)((groups + W - 1) / W), W * 32, 0, st>>>(images, g, *tmaps, pcs, keys_un, mode.levels, max_keys,
-                                                                                      n_max, n_pairs, tmpl);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return (int)e;
-  }
   long long ctas = (long long)n_sms * C::CTAS_SM;  // persistent: the SMs are filled once
   // A small batch is spread over all warps (lane_cap features per warp at a time) instead of filling a few: a warp
-  // with a handful of live lanes runs them through the cooperative pass, several times faster per iteration
+  // with a handful of live lanes runs them through the pixel-parallel pass, several times faster per iteration
   // than a lockstep pass, which is what the latency of a single frame pair is made of.
   const long long warps = ctas * C::WARPS;
   int lane_cap = (int)((total + warps - 1) / warps);
@@ -929,10 +1136,38 @@ static int launch_lanes(const unsigned char *images, const PagkGeom &g, const Pa
   static const int forced = [] { const char *e = getenv("PAGK_LK_SPLIT"); return e ? atoi(e) : -1; }();
   int split = (progress != nullptr && mode.levels > 1 && total > warps * C::SLOTS) ? 1 : 0;
   if (forced >= 0 && progress != nullptr && mode.levels > 1) split = forced ? 1 : 0;
-  pagk_lk_lanes_kernel<HALF, AFFINE><<<(unsigned)ctas, C::WARPS * 32, C::SMEM_BYTES, st>>>(
+  pagk_lk_lanes_kernel<HALF, AFFINE, WSM><<<(unsigned)ctas, C::WARPS * 32, C::SMEM_BYTES, st>>>(
       images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, next_counter, lane_cap, split, progress, epoch * 8,
-      tmpl, prof);
+      tmpl, 1.0f, prof);
   return (int)cudaGetLastError();
+}
+
+template <int HALF, bool AFFINE>
+static int launch_lanes(const unsigned char *images, const PagkGeom &g, const PagkPairConst *pcs, const float2 *keys_un,
+                        const PagkOutPtrs &out, const PagkMode &mode, int max_keys, int n_max, int n_pairs,
+                        int *work_counter, int *next_counter, int *progress, int epoch, int n_sms, unsigned char *tmpl,
+                        const PagkTmaLevels *tmaps, cudaStream_t st, long long *prof) {
+  const long long total = (long long)n_max * n_pairs;
+  {  // K3a: 32 items per warp
+    constexpr int W = TmplCfg<HALF>::WARPS;
+    const long long items = total * mode.levels, groups = (items + 31) / 32;
+    pagk_lk_template_kernel<HALF><<<(unsigned)((groups + W - 1) / W), W * 32, 0, st>>>(images, g, *tmaps, pcs, keys_un, mode.levels, max_keys,
+                                                                                      n_max, n_pairs, tmpl);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+  }
+  if constexpr (HALF <= 5) {
+    // PAGK_LK_WARPS=<n> forces the small (n < 12) or the large number of warps per SM
+    static const int forced_w = [] { const char *e = getenv("PAGK_LK_WARPS"); return e ? atoi(e) : 0; }();
+    const bool big = forced_w ? forced_w >= PAGK_LANES_WARPS5_BIG : total >= PAGK_LANES_BIG_FEATURES;
+    if (big)
+      return launch_lanes_w<HALF, AFFINE, PAGK_LANES_WARPS5_BIG>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter,
+                                                                  next_counter, progress, epoch, n_sms, tmpl, st, prof);
+    return launch_lanes_w<HALF, AFFINE, PAGK_LANES_WARPS5>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter,
+                                                            next_counter, progress, epoch, n_sms, tmpl, st, prof);
+  } else
+    return launch_lanes_w<HALF, AFFINE, 7>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, next_counter, progress, epoch,
+                                         n_sms, tmpl, st, prof);
 }
 
 int pagk_launch_lk_lanes(const unsigned char *images, const PagkGeom &g, const PagkPairConst *pcs, const float2 *keys_un,

@@ -29,3 +29,16 @@ for i, n in enumerate(names):
     print(f"{n:12s} mean {t[:, i].mean():10.0f}  min {t[:, i].min():10.0f} max {t[:, i].max():10.0f}" + (f"  share {100 * t[:, i].sum() / tot.sum():5.1f}%" if i in (0, 1, 3, 4, 5) else ""))
 print("slots per warp-round: active %.2f waiting %.2f" % (t[:, 7].sum() / t[:, 6].sum(), t[:, 2].sum() / t[:, 6].sum()))
 print("lane occupancy %.3f ; cycles per round %.0f ; pass cycles per round %.0f" % (t[:, 7].sum() / (32 * t[:, 6].sum()), tot.sum() / t[:, 6].sum(), t[:, 3].sum() / t[:, 6].sum()))
+
+if t.shape[1] >= 16:
+    t0 = t[:, 8].min()
+    st, ex, en = (t[:, 8] - t0) / 1e3, (t[:, 9] - t0) / 1e3, (t[:, 10] - t0) / 1e3
+    print("wall clock (us from the first warp's start): start max %.1f | queue exhausted min %.1f mean %.1f max %.1f | end min %.1f mean %.1f max %.1f" %
+          (st.max(), ex.min(), ex.mean(), ex.max(), en.min(), en.mean(), en.max()))
+    rb, lb = t[:, 11], t[:, 12]
+    ra, la = t[:, 6] - rb, t[:, 7] - lb
+    print("before the queue ran out: rounds/warp %.1f, lane occupancy %.3f ; after: rounds/warp %.1f, lane occupancy %.3f" %
+          (rb.mean(), lb.sum() / (32 * rb.sum()), ra.mean(), la.sum() / (32 * max(ra.sum(), 1))))
+    print("coop slot-passes/warp %.1f (%.1f %% of lane-rounds) ; sparse rounds/warp %.1f ; window stagings/warp %.1f" %
+          (t[:, 13].mean(), 100 * t[:, 13].sum() / t[:, 7].sum(), t[:, 14].mean(), t[:, 15].mean()))
+    print("end-time percentiles (us):", " ".join("%.0f" % np.percentile(en, q) for q in (1, 10, 25, 50, 75, 90, 99, 100)))
