@@ -54,14 +54,7 @@ bool make_geom(int width, int height, int levels, PagkGeom *g) {
     off += align_up((size_t)std::max(r + 1, 32) * pitch + 64, 256);
     c = (int)(c * 0.5); r = (int)(r * 0.5);  // cv::Size(cols * 0.5, rows * 0.5), reference src/patch_match.cpp:69
   }
-  g->u8_bytes = off;
-  for (int l = 0; l < levels; ++l) {  // the same levels with 16-bit elements (bfloat16 pixels of the current images)
-    g->lv[l].offset16 = 0;
-    if (!pagk_lk_lanes_win16()) continue;  // only builds whose alignment kernel reads that plane have it
-    g->lv[l].offset16 = (unsigned int)off;
-    off += align_up(2 * ((size_t)std::max(g->lv[l].rows + 1, 32) * g->lv[l].pitch + 64), 256);
-  }
-  for (int l = levels; l < PAGK_MAX_LEVELS; ++l) g->lv[l] = PagkLevelGeom{0, 0, 0, 0, 0};
+  for (int l = levels; l < PAGK_MAX_LEVELS; ++l) g->lv[l] = PagkLevelGeom{0, 0, 0, 0};
   g->slot_bytes = off;
   return true;
 }
@@ -255,8 +248,7 @@ int upload_images(pagk_handle *h, int n_pairs, const uint8_t *const *refs, const
 int upload_images_continue(pagk_handle *h, int n_pairs, const uint8_t *const *curs, int width, int height, const int *pitches) {
   const PagkGeom &g = h->geom;
   const size_t img_bytes = (size_t)width * height;
-  // (the u8 levels only: a reference image's bfloat16 plane is not read)
-  CU(cudaMemcpy2DAsync(h->d_images, 2 * g.slot_bytes, h->d_images + g.slot_bytes, 2 * g.slot_bytes, g.u8_bytes, (size_t)n_pairs,
+  CU(cudaMemcpy2DAsync(h->d_images, 2 * g.slot_bytes, h->d_images + g.slot_bytes, 2 * g.slot_bytes, g.slot_bytes, (size_t)n_pairs,
                        cudaMemcpyDeviceToDevice, h->stream));
   if (h->d_maps) return upload_images_rectify(h, n_pairs, nullptr, curs, width, height, pitches);
   const size_t dp = (size_t)g.lv[0].pitch;
@@ -595,8 +587,8 @@ int pagk_run_resident(pagk_handle *h) {
                                         h->geom.width, h->geom.height, h->d_ntab, h->ntab_stride, h->aux, &h->launches));
     CU(cudaEventRecord(h->ev_aux, h->aux));
     // a stream continuation already has the reference pyramids (copied from the previous current ones at upload)
-    if (h->cont) CU((cudaError_t)pagk_launch_pyramids(h->d_images + h->geom.slot_bytes, h->geom, h->n_pairs, 2, 1, st, &h->launches));
-    else CU((cudaError_t)pagk_launch_pyramids(h->d_images, h->geom, 2 * h->n_pairs, 1, 0, st, &h->launches));
+    if (h->cont) CU((cudaError_t)pagk_launch_pyramids(h->d_images + h->geom.slot_bytes, h->geom, h->n_pairs, 2, st, &h->launches));
+    else CU((cudaError_t)pagk_launch_pyramids(h->d_images, h->geom, 2 * h->n_pairs, 1, st, &h->launches));
     h->cur_pairs = h->n_pairs;
     if (stages) CU(cudaEventRecord(h->ev[1], st));
     CU(cudaStreamWaitEvent(st, h->ev_aux, 0));
@@ -826,7 +818,7 @@ int pagk_build_pyramids(pagk_handle *h, int n_images, const uint8_t *const *imgs
   for (int i = 0; i < n_images; ++i)
     CU(cudaMemcpy2DAsync(h->d_images + (size_t)i * h->geom.slot_bytes + h->geom.lv[0].offset, (size_t)h->geom.lv[0].pitch, imgs[i], pitch,
                          width, height, cudaMemcpyHostToDevice, h->stream));
-  CU((cudaError_t)pagk_launch_pyramids(h->d_images, h->geom, n_images, 1, 0, h->stream, &h->launches));
+  CU((cudaError_t)pagk_launch_pyramids(h->d_images, h->geom, n_images, 1, h->stream, &h->launches));
   CU(cudaStreamSynchronize(h->stream));
   return PAGK_OK;
 }
@@ -1229,7 +1221,7 @@ int pagk_patch_match(pagk_handle *h, const pagk_patch_match_in *in, pagk_pair_ou
   h->ran_stages = true;
   CU(cudaEventRecord(h->ev[0], st));
   h->cur_pairs = 0;
-  CU((cudaError_t)pagk_launch_pyramids(h->d_images, h->geom, 2, 1, 0, st, &h->launches));
+  CU((cudaError_t)pagk_launch_pyramids(h->d_images, h->geom, 2, 1, st, &h->launches));
   CU(cudaEventRecord(h->ev[1], st));
   CU(cudaEventRecord(h->ev[2], st));
   CU((cudaError_t)launch_lk(h, o, m, in->n_keys, 1));

@@ -21,38 +21,18 @@
 // and in both cases row `rows` is a guard row (a copy of row rows - 1, with its own wrap byte).  So the byte at
 // (x, y) for 0 <= x <= cols, 0 <= y <= rows is what a continuous cv::Mat followed by a copy of its last row yields.
 // Past that the allocation continues (at least 32 rows and 64 bytes of slack) so that a staged window may overhang.
-//
-// Behind the u8 levels a slot holds the same levels once more with 16-bit elements: the pixel as a bfloat16 (exact for
-// 0..255), same pitch in ELEMENTS, same wrap column and guard row.  The pyramid kernel writes them for CURRENT images
-// (odd slots); the alignment kernel stages its windows from this plane, because a bfloat16 becomes the float the
-// bilinear samples need with one shift, where a byte needs an OR and a subtraction (12 taps per pixel and iteration).
 struct PagkLevelGeom {
   int cols, rows;
   int pitch;              // row pitch in elements, a multiple of 4, >= cols (+1 when it is not cols)
-  unsigned int offset;    // u8 level: bytes from the start of the image slot, 256-byte aligned
-  unsigned int offset16;  // bf16 level: bytes from the start of the image slot, 256-byte aligned
+  unsigned int offset;    // bytes from the start of the image slot, 256-byte aligned
 };
 
 struct PagkGeom {
   int levels;
   int width, height;
-  unsigned long long slot_bytes;  // bytes per image slot (all levels, both planes), 256-byte aligned
-  unsigned long long u8_bytes;    // bytes of the u8 levels at the start of the slot
+  unsigned long long slot_bytes;  // bytes per image slot (all levels), 256-byte aligned
   PagkLevelGeom lv[PAGK_MAX_LEVELS];
 };
-
-// the pixel value b (0..255) as a bfloat16: the upper half of the float b, itself (2^23 + b) - 2^23
-__device__ __forceinline__ unsigned int pagk_f32bits_of_u8(unsigned int b) {
-  return __float_as_uint(__uint_as_float(0x4B000000u | b) - 8388608.0f);
-}
-__device__ __forceinline__ unsigned short pagk_bf16_of_u8(unsigned int b) { return (unsigned short)(pagk_f32bits_of_u8(b) >> 16); }
-// four pixels of a word -> four bfloat16 in two words
-__device__ __forceinline__ uint2 pagk_bf16x4_of_u8x4(unsigned int w) {
-  uint2 r;
-  r.x = __byte_perm(pagk_f32bits_of_u8(w & 0xffu), pagk_f32bits_of_u8((w >> 8) & 0xffu), 0x7632);
-  r.y = __byte_perm(pagk_f32bits_of_u8((w >> 16) & 0xffu), pagk_f32bits_of_u8(w >> 24), 0x7632);
-  return r;
-}
 
 // What GyroAidedTracker::Initialize / SetRcl cache per tracker (src/gyro_aided_tracker.cpp:64-70, 511-519)
 struct PagkPairConst {

@@ -21,212 +21,177 @@
 // =================================================================================================
 // K1: image pyramid.  cv::resize(INTER_LINEAR) to exactly half size is OpenCV's 2x2 INTER_AREA fast
 // path: dst = (a + b + c + d + 2) >> 2 (verified against cv2).  One CTA owns a
-// 128 x 64 tile of level 0 and produces that tile of every further level of the exact-2x chain from
-// shared memory, so level 0 is read from HBM once and nothing is re-read.  16-byte loads, 8-byte
-// stores.  The CTA that owns the last row of a level also writes that level's guard row.
+// 128 x 128 tile of level 0 and produces that tile of every further level of the exact-2x chain from
+// shared memory, so level 0 is read from HBM once and nothing is re-read.  A thread has its four 16-byte
+// loads (two row pairs) in flight together -- 64 KB per SM with four CTAs resident, what the HBM latency
+// needs --, stores are 8 bytes.  The CTA that owns the last row of a level also writes that level's guard row.
 // =================================================================================================
 #define PYR_TW 128
-#define PYR_TH 64
+#define PYR_TH 128
 
 // Pixel (0, gy) = v has just been produced: write the wrap bytes that mirror it (pagk_device.cuh, PagkLevelGeom):
 // column `cols` of the row above when the level is padded, and for the last row its own wrap byte and the guard row's.
-// l16: the level's bfloat16 plane (null: not written).
-__device__ __forceinline__ void pagk_write_wrap(unsigned char *ll, unsigned short *l16, int pitch, int cols, int rows, int gy,
-                                                unsigned char v) {
-  const unsigned short v16 = pagk_bf16_of_u8(v);
-  if (gy >= 1 && pitch > cols) {
-    ll[(size_t)(gy - 1) * pitch + cols] = v;
-    if (l16) l16[(size_t)(gy - 1) * pitch + cols] = v16;
-  }
+__device__ __forceinline__ void pagk_write_wrap(unsigned char *ll, int pitch, int cols, int rows, int gy, unsigned char v) {
+  if (gy >= 1 && pitch > cols) ll[(size_t)(gy - 1) * pitch + cols] = v;
   if (gy == rows - 1) {
-    if (pitch > cols) {
-      ll[(size_t)gy * pitch + cols] = v;
-      if (l16) l16[(size_t)gy * pitch + cols] = v16;
-    }
+    if (pitch > cols) ll[(size_t)gy * pitch + cols] = v;
     ll[(size_t)rows * pitch + cols] = v;
-    if (l16) l16[(size_t)rows * pitch + cols] = v16;
   }
 }
 
+// r0, r1: four horizontally adjacent pixels of two rows -> (a + b + c + d + 2) >> 2 of the two 2 x 2 blocks, in bytes
+// 0 and 2 of the result.  The even and the odd bytes of a word go to 16-bit lanes with one PRMT each (byte 4 of the
+// selector is the zero register), the four partial sums are two three-input adds.
+__device__ __forceinline__ unsigned int pagk_avg2x2_lanes(unsigned int r0, unsigned int r1) {
+  const unsigned int e0 = __byte_perm(r0, 0u, 0x4240), o0 = __byte_perm(r0, 0u, 0x4341);
+  const unsigned int e1 = __byte_perm(r1, 0u, 0x4240), o1 = __byte_perm(r1, 0u, 0x4341);
+  return (((e0 + o0 + e1) + (o1 + 0x00020002u)) >> 2) & 0x00ff00ffu;
+}
+// eight pixels of two rows (two words each) -> four output pixels in one word
+__device__ __forceinline__ unsigned int pagk_avg8x8(unsigned int a0, unsigned int a1, unsigned int b0, unsigned int b1) {
+  return __byte_perm(pagk_avg2x2_lanes(a0, b0), pagk_avg2x2_lanes(a1, b1), 0x6420);
+}
 __device__ __forceinline__ unsigned int pagk_avg4x8(unsigned int r0, unsigned int r1) {
   // r0, r1: four horizontally adjacent pixels of two rows -> two output pixels in the low 16 bits
-  const unsigned int a = (r0 & 0xffu) + ((r0 >> 8) & 0xffu) + (r1 & 0xffu) + ((r1 >> 8) & 0xffu) + 2u;
-  const unsigned int b = ((r0 >> 16) & 0xffu) + (r0 >> 24) + ((r1 >> 16) & 0xffu) + (r1 >> 24) + 2u;
-  return (a >> 2) | ((b >> 2) << 8);
+  return __byte_perm(pagk_avg2x2_lanes(r0, r1), 0u, 0x4420);
 }
 
 // One more level of a tile: the TW x TH tile of level l-1 in shared memory `s` -> its (TW/2) x (TH/2) tile of level l,
-// to shared memory `d` and to the image; then recurses to level l+1.  All index arithmetic is shifts and masks.
+// to shared memory `d` and to the image; then recurses to level l+1.  A thread produces four adjacent pixels of a row
+// (two 8-byte shared-memory loads, one 4-byte store to each side); tile origins and pitches are multiples of four at
+// every fused level, so only a level's ragged right edge falls back to bytes.
 template <int TW, int TH>
 __device__ __forceinline__ void pagk_pyramid_tile_level(const unsigned char *s, unsigned char *d, unsigned char *img,
-                                                        const PagkGeom &g, int l, int n_fused, int tx0, int ty0, int t, bool w16) {
+                                                        const PagkGeom &g, int l, int n_fused, int tx0, int ty0, int t) {
   constexpr int OW = TW / 2, OH = TH / 2;
-  if constexpr (OW >= 1 && OH >= 1) {
+  if constexpr (OW >= 4 && OH >= 1) {
     __syncthreads();
     const int colsl = g.lv[l].cols, rowsl = g.lv[l].rows, pl = g.lv[l].pitch;
     unsigned char *ll = img + g.lv[l].offset;
-    unsigned short *l16 = w16 ? reinterpret_cast<unsigned short *>(img + g.lv[l].offset16) : nullptr;
     const int ox0 = tx0 >> l, oy0 = ty0 >> l;
+    constexpr int QW = OW / 4;  // groups of four pixels per row
 #pragma unroll
-    for (int p = t; p < OW * OH; p += 256) {
-      const int ox = p % OW, oy = p / OW;  // OW is a power of two: a mask and a shift
-      const unsigned char *q = s + (2 * oy) * TW + 2 * ox;
-      const unsigned int r0 = *reinterpret_cast<const unsigned short *>(q), r1 = *reinterpret_cast<const unsigned short *>(q + TW);
-      const unsigned char v = (unsigned char)(((r0 & 0xffu) + (r0 >> 8) + (r1 & 0xffu) + (r1 >> 8) + 2u) >> 2);
-      d[oy * OW + ox] = v;
+    for (int p = t; p < QW * OH; p += 256) {
+      const int oq = p % QW, oy = p / QW, ox = oq * 4;  // QW is a power of two: a mask and a shift
+      const uint2 r0 = *reinterpret_cast<const uint2 *>(s + (2 * oy) * TW + 2 * ox);
+      const uint2 r1 = *reinterpret_cast<const uint2 *>(s + (2 * oy + 1) * TW + 2 * ox);
+      const unsigned int v4 = pagk_avg8x8(r0.x, r0.y, r1.x, r1.y);
+      *reinterpret_cast<unsigned int *>(d + oy * OW + ox) = v4;
       const int gx = ox0 + ox, gy = oy0 + oy;
       if (gx < colsl && gy < rowsl) {
-        ll[(size_t)gy * pl + gx] = v;
-        if (gy == rowsl - 1) ll[(size_t)rowsl * pl + gx] = v;  // guard row
-        if (l16) {
-          const unsigned short v16 = pagk_bf16_of_u8(v);
-          l16[(size_t)gy * pl + gx] = v16;
-          if (gy == rowsl - 1) l16[(size_t)rowsl * pl + gx] = v16;
+        unsigned char *dst = ll + (unsigned int)(gy * pl + gx);
+        if (gx + 4 <= colsl) {
+          *reinterpret_cast<unsigned int *>(dst) = v4;
+          if (gy == rowsl - 1) *reinterpret_cast<unsigned int *>(dst + pl) = v4;  // guard row
+        } else {
+          for (int k = 0; k < 4 && gx + k < colsl; ++k) {
+            dst[k] = (unsigned char)(v4 >> (8 * k));
+            if (gy == rowsl - 1) dst[pl + k] = (unsigned char)(v4 >> (8 * k));
+          }
         }
-        if (gx == 0) pagk_write_wrap(ll, l16, pl, colsl, rowsl, gy, v);
+        if (gx == 0) pagk_write_wrap(ll, pl, colsl, rowsl, gy, (unsigned char)(v4 & 0xffu));
       }
     }
-    if (l < n_fused) pagk_pyramid_tile_level<OW, OH>(d, const_cast<unsigned char *>(s), img, g, l + 1, n_fused, tx0, ty0, t, w16);
+    if (l < n_fused) pagk_pyramid_tile_level<OW, OH>(d, const_cast<unsigned char *>(s), img, g, l + 1, n_fused, tx0, ty0, t);
   }
 }
 
 #ifndef PAGK_PYR_MIN_BLOCKS
-#define PAGK_PYR_MIN_BLOCKS 4
+#define PAGK_PYR_MIN_BLOCKS 5
 #endif
+// VEC: the width of level 0 is a multiple of 16 (then its pitch is its width and the fused levels are continuous too)
+template <bool VEC>
 __global__ void __launch_bounds__(256, PAGK_PYR_MIN_BLOCKS) pagk_pyramid_fused_kernel(unsigned char *__restrict__ images, PagkGeom g,
                                                                int n_fused /* last level produced here */,
-                                                               int z_stride /* image z lives in slot z * z_stride */,
-                                                               int cur_parity /* (z * z_stride + cur_parity) odd: a current image */) {
+                                                               int z_stride /* image z lives in slot z * z_stride */) {
   __shared__ __align__(16) unsigned char sbuf[2][(PYR_TW / 2) * (PYR_TH / 2)];
   unsigned char *img = images + (size_t)blockIdx.z * z_stride * g.slot_bytes;
-  const bool w16 = g.lv[0].offset16 != 0 && ((blockIdx.z * z_stride + cur_parity) & 1) != 0;  // current images get their bfloat16 plane
   const int t = threadIdx.x;
   const int cols0 = g.lv[0].cols, rows0 = g.lv[0].rows, p0 = g.lv[0].pitch;
   unsigned char *l0 = img + g.lv[0].offset;
-  unsigned short *l0h = reinterpret_cast<unsigned short *>(img + g.lv[0].offset16);
   const int tx0 = blockIdx.x * PYR_TW, ty0 = blockIdx.y * PYR_TH;
 
   // ---- level 0 -> level 1 (or only the guard row of level 0 when there is a single level)
-  {
-    const int tx = t & 7, ty = t >> 3;  // 8 threads x 16 px per row pair, 32 row pairs
-    const int x0 = tx0 + tx * 16, y0 = ty0 + ty * 2;
-    const bool vec = ((cols0 & 15) == 0);  // then p0 == cols0 and every further fused level is continuous as well
-    unsigned int a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
-    const bool in0 = (x0 < cols0) && (y0 < rows0), in1 = (x0 < cols0) && (y0 + 1 < rows0);
-    if (vec) {
-      if (in0) { const uint4 v = *reinterpret_cast<const uint4 *>(l0 + (size_t)y0 * p0 + x0); a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w; }
-      if (in1) { const uint4 v = *reinterpret_cast<const uint4 *>(l0 + (size_t)(y0 + 1) * p0 + x0); b[0] = v.x; b[1] = v.y; b[2] = v.z; b[3] = v.w; }
+  const int tx = t & 7, ty = t >> 3;  // 8 threads x 16 px per row pair, 32 row pairs, two of them per thread
+  const int x0 = tx0 + tx * 16;
+  constexpr int NR = PYR_TH / 64;
+  unsigned int a[NR][4], b[NR][4];
+  bool in0[NR], in1[NR];
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    const int y0 = ty0 + r * 64 + ty * 2;
+    in0[r] = (x0 < cols0) && (y0 < rows0); in1[r] = (x0 < cols0) && (y0 + 1 < rows0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { a[r][k] = 0; b[r][k] = 0; }
+    const unsigned char *src = l0 + (unsigned int)(y0 * p0 + x0);
+    if (VEC) {
+      if (in0[r]) { const uint4 v = *reinterpret_cast<const uint4 *>(src); a[r][0] = v.x; a[r][1] = v.y; a[r][2] = v.z; a[r][3] = v.w; }
+      if (in1[r]) { const uint4 v = *reinterpret_cast<const uint4 *>(src + p0); b[r][0] = v.x; b[r][1] = v.y; b[r][2] = v.z; b[r][3] = v.w; }
     } else {
       for (int k = 0; k < 16; ++k) {
-        if (in0 && x0 + k < cols0) a[k >> 2] |= (unsigned int)l0[(size_t)y0 * p0 + x0 + k] << (8 * (k & 3));
-        if (in1 && x0 + k < cols0) b[k >> 2] |= (unsigned int)l0[(size_t)(y0 + 1) * p0 + x0 + k] << (8 * (k & 3));
+        if (in0[r] && x0 + k < cols0) a[r][k >> 2] |= (unsigned int)src[k] << (8 * (k & 3));
+        if (in1[r] && x0 + k < cols0) b[r][k >> 2] |= (unsigned int)src[p0 + k] << (8 * (k & 3));
       }
     }
-    // explicit wrap bytes of a padded level 0 (the caller's image has a width that is not a multiple of 4)
-    if (p0 > cols0 && x0 == 0) {
-      if (in0 && y0 >= 1) l0[(size_t)(y0 - 1) * p0 + cols0] = (unsigned char)(a[0] & 0xffu);
-      if (in1) l0[(size_t)y0 * p0 + cols0] = (unsigned char)(b[0] & 0xffu);
-      if (in0 && y0 == rows0 - 1) l0[(size_t)y0 * p0 + cols0] = (unsigned char)(a[0] & 0xffu);
-      if (in1 && y0 + 1 == rows0 - 1) l0[(size_t)(y0 + 1) * p0 + cols0] = (unsigned char)(b[0] & 0xffu);
-      if (w16) {
-        if (in0 && y0 >= 1) l0h[(size_t)(y0 - 1) * p0 + cols0] = pagk_bf16_of_u8(a[0] & 0xffu);
-        if (in1) l0h[(size_t)y0 * p0 + cols0] = pagk_bf16_of_u8(b[0] & 0xffu);
-        if (in0 && y0 == rows0 - 1) l0h[(size_t)y0 * p0 + cols0] = pagk_bf16_of_u8(a[0] & 0xffu);
-        if (in1 && y0 + 1 == rows0 - 1) l0h[(size_t)(y0 + 1) * p0 + cols0] = pagk_bf16_of_u8(b[0] & 0xffu);
-      }
-    }
-    // the bfloat16 plane of level 0 itself
-    if (w16) {
+  }
+  const int cols1 = g.lv[1].cols, rows1 = g.lv[1].rows, p1 = g.lv[1].pitch;
+  unsigned char *l1 = img + g.lv[1].offset;
 #pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const unsigned int *src = r ? b : a;
-        if (!(r ? in1 : in0)) continue;
-        unsigned short *dst = l0h + (size_t)(y0 + r) * p0 + x0;
-        if (vec) {
-          const uint2 q0 = pagk_bf16x4_of_u8x4(src[0]), q1 = pagk_bf16x4_of_u8x4(src[1]), q2 = pagk_bf16x4_of_u8x4(src[2]),
-                      q3 = pagk_bf16x4_of_u8x4(src[3]);
-          reinterpret_cast<uint4 *>(dst)[0] = make_uint4(q0.x, q0.y, q1.x, q1.y);
-          reinterpret_cast<uint4 *>(dst)[1] = make_uint4(q2.x, q2.y, q3.x, q3.y);
-        } else {
-          for (int k = 0; k < 16 && x0 + k < cols0; ++k) dst[k] = pagk_bf16_of_u8((src[k >> 2] >> (8 * (k & 3))) & 0xffu);
-        }
-      }
+  for (int r = 0; r < NR; ++r) {
+    const int y0 = ty0 + r * 64 + ty * 2;
+    // explicit wrap bytes of a padded level 0 (the caller's image has a width that is not a multiple of 4)
+    if (!VEC && p0 > cols0 && x0 == 0) {
+      if (in0[r] && y0 >= 1) l0[(size_t)(y0 - 1) * p0 + cols0] = (unsigned char)(a[r][0] & 0xffu);
+      if (in1[r]) l0[(size_t)y0 * p0 + cols0] = (unsigned char)(b[r][0] & 0xffu);
+      if (in0[r] && y0 == rows0 - 1) l0[(size_t)y0 * p0 + cols0] = (unsigned char)(a[r][0] & 0xffu);
+      if (in1[r] && y0 + 1 == rows0 - 1) l0[(size_t)(y0 + 1) * p0 + cols0] = (unsigned char)(b[r][0] & 0xffu);
     }
     // guard row of level 0 = copy of row rows0-1 (+ one byte)
-    if (in0 && (y0 == rows0 - 1 || y0 + 1 == rows0 - 1)) {
-      const unsigned int *src = (y0 == rows0 - 1) ? a : b;
+    if (in0[r] && (y0 == rows0 - 1 || y0 + 1 == rows0 - 1)) {
+      const unsigned int *src = (y0 == rows0 - 1) ? a[r] : b[r];
       unsigned char *gr = l0 + (size_t)rows0 * p0 + x0;
-      unsigned short *grh = l0h + (size_t)rows0 * p0 + x0;
-      if (vec) {
+      if (VEC) {
         *reinterpret_cast<uint4 *>(gr) = make_uint4(src[0], src[1], src[2], src[3]);
-        if (w16) {
-          const uint2 q0 = pagk_bf16x4_of_u8x4(src[0]), q1 = pagk_bf16x4_of_u8x4(src[1]), q2 = pagk_bf16x4_of_u8x4(src[2]),
-                      q3 = pagk_bf16x4_of_u8x4(src[3]);
-          reinterpret_cast<uint4 *>(grh)[0] = make_uint4(q0.x, q0.y, q1.x, q1.y);
-          reinterpret_cast<uint4 *>(grh)[1] = make_uint4(q2.x, q2.y, q3.x, q3.y);
-        }
       } else {
-        for (int k = 0; k < 16 && x0 + k < cols0; ++k) {
-          gr[k] = (unsigned char)(src[k >> 2] >> (8 * (k & 3)));
-          if (w16) grh[k] = pagk_bf16_of_u8((src[k >> 2] >> (8 * (k & 3))) & 0xffu);
-        }
+        for (int k = 0; k < 16 && x0 + k < cols0; ++k) gr[k] = (unsigned char)(src[k >> 2] >> (8 * (k & 3)));
       }
-      if (x0 == 0) {
-        l0[(size_t)rows0 * p0 + cols0] = (unsigned char)(src[0] & 0xffu);
-        if (w16) l0h[(size_t)rows0 * p0 + cols0] = pagk_bf16_of_u8(src[0] & 0xffu);
-      }
+      if (x0 == 0) l0[(size_t)rows0 * p0 + cols0] = (unsigned char)(src[0] & 0xffu);
     }
     if (n_fused >= 1) {
-      const int cols1 = g.lv[1].cols, rows1 = g.lv[1].rows, p1 = g.lv[1].pitch;
-      unsigned char *l1 = img + g.lv[1].offset;
-      unsigned short *l1h = w16 ? reinterpret_cast<unsigned short *>(img + g.lv[1].offset16) : nullptr;
       uint2 o;
-      o.x = pagk_avg4x8(a[0], b[0]) | (pagk_avg4x8(a[1], b[1]) << 16);
-      o.y = pagk_avg4x8(a[2], b[2]) | (pagk_avg4x8(a[3], b[3]) << 16);
-      *reinterpret_cast<uint2 *>(&sbuf[0][ty * (PYR_TW / 2) + tx * 8]) = o;
+      o.x = pagk_avg8x8(a[r][0], a[r][1], b[r][0], b[r][1]);
+      o.y = pagk_avg8x8(a[r][2], a[r][3], b[r][2], b[r][3]);
+      *reinterpret_cast<uint2 *>(&sbuf[0][(r * 32 + ty) * (PYR_TW / 2) + tx * 8]) = o;
       const int x1 = x0 >> 1, y1 = y0 >> 1;
       if (y1 < rows1 && x1 < cols1) {
-        unsigned char *dst = l1 + (size_t)y1 * p1 + x1;
-        if (vec && x1 + 8 <= cols1) {
+        unsigned char *dst = l1 + (unsigned int)(y1 * p1 + x1);
+        if (VEC && x1 + 8 <= cols1) {
           *reinterpret_cast<uint2 *>(dst) = o;
           if (y1 == rows1 - 1) *reinterpret_cast<uint2 *>(dst + p1) = o;
-          if (l1h) {
-            const uint2 q0 = pagk_bf16x4_of_u8x4(o.x), q1 = pagk_bf16x4_of_u8x4(o.y);
-            const uint4 q = make_uint4(q0.x, q0.y, q1.x, q1.y);
-            *reinterpret_cast<uint4 *>(l1h + (size_t)y1 * p1 + x1) = q;
-            if (y1 == rows1 - 1) *reinterpret_cast<uint4 *>(l1h + (size_t)rows1 * p1 + x1) = q;
-          }
         } else {
           for (int k = 0; k < 8 && x1 + k < cols1; ++k) {
             const unsigned char v = (unsigned char)((k < 4 ? o.x : o.y) >> (8 * (k & 3)));
             dst[k] = v;
             if (y1 == rows1 - 1) dst[p1 + k] = v;
-            if (l1h) {
-              const unsigned short v16 = pagk_bf16_of_u8(v);
-              l1h[(size_t)y1 * p1 + x1 + k] = v16;
-              if (y1 == rows1 - 1) l1h[(size_t)rows1 * p1 + x1 + k] = v16;
-            }
           }
         }
-        if (x1 == 0) pagk_write_wrap(l1, l1h, p1, cols1, rows1, y1, (unsigned char)(o.x & 0xffu));
+        if (x1 == 0) pagk_write_wrap(l1, p1, cols1, rows1, y1, (unsigned char)(o.x & 0xffu));
       }
     }
   }
   // ---- level l-1 (shared memory) -> level l, l = 2 .. n_fused: tile sizes are compile-time constants
-  if (n_fused >= 2) pagk_pyramid_tile_level<PYR_TW / 2, PYR_TH / 2>(sbuf[0], sbuf[1], img, g, 2, n_fused, tx0, ty0, t, w16);
+  if (n_fused >= 2) pagk_pyramid_tile_level<PYR_TW / 2, PYR_TH / 2>(sbuf[0], sbuf[1], img, g, 2, n_fused, tx0, ty0, t);
 }
 
 // General half-size cv::resize(INTER_LINEAR) for levels whose source has an odd dimension: the
 // 11-bit fixed-point bilinear of OpenCV.  One thread per output pixel.
 __global__ void __launch_bounds__(256) pagk_pyramid_general_kernel(unsigned char *__restrict__ images, PagkGeom g,
-                                                                 int level, int z_stride, int cur_parity) {
+                                                                 int level, int z_stride) {
   unsigned char *img = images + (size_t)blockIdx.z * z_stride * g.slot_bytes;
-  const bool w16 = g.lv[0].offset16 != 0 && ((blockIdx.z * z_stride + cur_parity) & 1) != 0;
   const int scols = g.lv[level - 1].cols, srows = g.lv[level - 1].rows, sp = g.lv[level - 1].pitch;
   const int dcols = g.lv[level].cols, drows = g.lv[level].rows, dp = g.lv[level].pitch;
   const unsigned char *src = img + g.lv[level - 1].offset;
   unsigned char *dst = img + g.lv[level].offset;
-  unsigned short *d16 = w16 ? reinterpret_cast<unsigned short *>(img + g.lv[level].offset16) : nullptr;
   const int dx = blockIdx.x * blockDim.x + threadIdx.x;
   const int dy = blockIdx.y;
   if (dx >= dcols || dy >= drows) return;
@@ -256,12 +221,7 @@ __global__ void __launch_bounds__(256) pagk_pyramid_general_kernel(unsigned char
   }
   dst[(size_t)dy * dp + dx] = v;
   if (dy == drows - 1) dst[(size_t)drows * dp + dx] = v;
-  if (d16) {
-    const unsigned short v16 = pagk_bf16_of_u8(v);
-    d16[(size_t)dy * dp + dx] = v16;
-    if (dy == drows - 1) d16[(size_t)drows * dp + dx] = v16;
-  }
-  if (dx == 0) pagk_write_wrap(dst, d16, dp, dcols, drows, dy, v);
+  if (dx == 0) pagk_write_wrap(dst, dp, dcols, drows, dy, v);
 }
 
 // =================================================================================================
@@ -1391,13 +1351,13 @@ __global__ void __launch_bounds__(RANSAC_THREADS) pagk_ransac_kernel(const float
 // =================================================================================================
 // launch wrappers (host)
 // =================================================================================================
-int pagk_pyramid_fused_max_level() {
+int pagk_pyramid_fused_max_level() {  // a level's tile has to be at least four pixels wide
   int l = 1, tw = PYR_TW / 2, th = PYR_TH / 2;
-  while ((tw >> 1) > 0 && (th >> 1) > 0) { tw >>= 1; th >>= 1; ++l; }
+  while ((tw >> 1) >= 4 && (th >> 1) > 0) { tw >>= 1; th >>= 1; ++l; }
   return l;
 }
 
-int pagk_launch_pyramids(unsigned char *images, const PagkGeom &g, int n_images, int z_stride, int cur_parity, cudaStream_t st,
+int pagk_launch_pyramids(unsigned char *images, const PagkGeom &g, int n_images, int z_stride, cudaStream_t st,
                          long long *launches) {
   // levels 1..n_fused form the exact-2x chain and come out of the fused kernel
   int n_fused = 0;
@@ -1406,11 +1366,12 @@ int pagk_launch_pyramids(unsigned char *images, const PagkGeom &g, int n_images,
     else break;
   }
   dim3 grid((g.lv[0].cols + PYR_TW - 1) / PYR_TW, (g.lv[0].rows + PYR_TH - 1) / PYR_TH, n_images);
-  pagk_pyramid_fused_kernel<<<grid, 256, 0, st>>>(images, g, n_fused, z_stride, cur_parity);
+  if ((g.lv[0].cols & 15) == 0) pagk_pyramid_fused_kernel<true><<<grid, 256, 0, st>>>(images, g, n_fused, z_stride);
+  else pagk_pyramid_fused_kernel<false><<<grid, 256, 0, st>>>(images, g, n_fused, z_stride);
   ++*launches;
   for (int l = n_fused + 1; l < g.levels; ++l) {
     dim3 gg((g.lv[l].cols + 255) / 256, g.lv[l].rows, n_images);
-    pagk_pyramid_general_kernel<<<gg, 256, 0, st>>>(images, g, l, z_stride, cur_parity);
+    pagk_pyramid_general_kernel<<<gg, 256, 0, st>>>(images, g, l, z_stride);
     ++*launches;
   }
   return (int)cudaGetLastError();

@@ -9,10 +9,8 @@ struct PagkTmaLevels {
 };
 
 int pagk_pyramid_fused_max_level();
-// image z of the launch lives in slot z * z_stride (1: every slot, 2: every other one, i.e. only the current images);
-// slots with (z * z_stride + cur_parity) odd hold current images and get their bfloat16 plane as well when the
-// geometry has one (PagkLevelGeom::offset16 != 0)
-int pagk_launch_pyramids(unsigned char *images, const PagkGeom &g, int n_images, int z_stride, int cur_parity, cudaStream_t st,
+// image z of the launch lives in slot z * z_stride (1: every slot, 2: every other one, i.e. only the current images)
+int pagk_launch_pyramids(unsigned char *images, const PagkGeom &g, int n_images, int z_stride, cudaStream_t st,
                          long long *launches);
 int pagk_launch_predict(const PagkPairConst *pcs, const float2 *keys_un, const float2 *keys, const PagkOutPtrs &out,
                         const PagkMode &mode, int max_keys, int n_max, int n_pairs, int width, int height,
@@ -64,7 +62,6 @@ int pagk_lk_lanes_configure();
 // production patch-alignment kernels (pagk_lk_lanes.cu): template staging pass + persistent CTAs, one lane per feature.
 // tmpl: [max_pairs * max_keys][levels] template records of pagk_lk_lanes_record_bytes(half) bytes each.
 bool pagk_lk_lanes_supported(const PagkMode &mode);
-bool pagk_lk_lanes_win16();
 size_t pagk_lk_lanes_record_bytes(int half);
 void pagk_lk_lanes_tma_box(int half, int *box_w, int *box_h);
 int pagk_launch_lk_lanes(const unsigned char *images, const PagkGeom &g, const PagkPairConst *pcs, const float2 *keys_un,

@@ -290,7 +290,7 @@ struct TmplCfg {
   static constexpr int ROW_BYTES = (15 + P + 2 + 15) & ~15;
   static constexpr int BOX_BYTES = ROWS * ROW_BYTES;
   static constexpr int ITEM_BYTES = (BOX_BYTES + 127) & ~127;  // TMA destinations are 128-byte aligned
-  static constexpr int G = HALF <= 5 ? 16 : 8;                 // items fetched together: 8 / 9 KB per warp
+  static constexpr int G = HALF <= 5 ? 8 : 4;                  // items per group; two groups in flight: 10 / 9 KB per warp
   static constexpr int WARPS = 4;
 };
 
@@ -299,24 +299,23 @@ __global__ void __launch_bounds__(TmplCfg<HALF>::WARPS * 32) pagk_lk_template_ke
                                                              const __grid_constant__ PagkTmaLevels maps,
                                                              const PagkPairConst *__restrict__ pcs,
                                                              const float2 *__restrict__ keys_un, int levels, int max_keys,
-                                                             int n_max, int n_pairs, unsigned char *__restrict__ tmpl) {
+                                                             int n_max, int n_pairs, unsigned char *__restrict__ tmpl, float unit) {
   using C = LanesCfg<HALF>;
   using TC = TmplCfg<HALF>;
   constexpr int P = C::P, NP = C::NP, TK = (NP + 31) / 32, G = TC::G, RB = TC::ROW_BYTES;
   constexpr unsigned FULL = 0xffffffffu;
-  __shared__ __align__(128) unsigned char s_raw[TC::WARPS][G][TC::ITEM_BYTES];
-  __shared__ __align__(8) unsigned long long s_bar[TC::WARPS];
+  __shared__ __align__(128) unsigned char s_raw[TC::WARPS][2][G][TC::ITEM_BYTES];
+  __shared__ __align__(8) unsigned long long s_bar[TC::WARPS][2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long wg = (long long)blockIdx.x * TC::WARPS + warp;
   const long long total = (long long)n_pairs * n_max * levels, base = wg * 32;
   if (base >= total) return;
-  const unsigned int mbar = smem_u32(&s_bar[warp]);
+  const unsigned int mbar = smem_u32(&s_bar[warp][0]);  // the barrier of buffer b is mbar + 8 * b
   if (lane == 0) {
-    mbar_init(mbar, 1);
+    mbar_init(mbar, 1); mbar_init(mbar + 8u, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
-  unsigned int phase = 0;
   const float hf = (float)HALF;
   float tpx[TK], tpy[TK];
   int toff[TK];  // tap offset of pixel p inside the staged block when nothing is rounded: py * RB + px
@@ -325,6 +324,15 @@ __global__ void __launch_bounds__(TmplCfg<HALF>::WARPS * 32) pagk_lk_template_ke
     const int p = lane + 32 * k, py = p / P, px = p - py * P;
     tpx[k] = (float)(px - HALF); tpy[k] = (float)(py - HALF);
     toff[k] = py * RB + px;
+  }
+  // pixel pairs (2k, 2k + 1), k = lane + 32 * kk, of the shared-weight path: tap offsets of both pixels
+  constexpr int NPAIR = (NP + 1) / 2, TK2 = (NPAIR + 31) / 32;
+  int toffp[TK2], toffq[TK2];
+#pragma unroll
+  for (int kk = 0; kk < TK2; ++kk) {
+    const int p = 2 * (lane + 32 * kk), q = p + 1 < NP ? p + 1 : p;
+    toffp[kk] = (p / P) * RB + p % P;
+    toffq[kk] = (q / P) * RB + q % P;
   }
   // ---- lane j: item j
   bool valid = false, tin = false, uni = false;
@@ -363,18 +371,30 @@ __global__ void __launch_bounds__(TmplCfg<HALF>::WARPS * 32) pagk_lk_template_ke
     }
   }
   float myc = 0.f, mylast = 0.f;
-#pragma unroll 1
-  for (int g0 = 0; g0 < 32; g0 += G) {
-    // ---- the tap blocks of items g0 .. g0 + G - 1: every owner lane issues its own tile load
-    const bool mine = lane >= g0 && lane < g0 + G && valid && tin;
-    const unsigned int mm = __ballot_sync(FULL, mine);
+  // ---- the tap blocks of a group of G items: every owner lane issues its own tile load.  Two groups are in flight: the
+  // loads of group n + 1 are issued before the pixels of group n are computed.
+  const unsigned int tin_mask = __ballot_sync(FULL, valid && tin);
+  auto issue = [&](const int grp) {
+    const int g0 = grp * G, b = grp & 1;
+    const unsigned int mm = (tin_mask >> g0) & ((1u << G) - 1u);
     if (mm) {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the blocks were read through the generic proxy
-      if (lane == 0) mbar_expect_tx(mbar, (unsigned int)TC::BOX_BYTES * (unsigned int)__popc(mm));
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the buffer was read through the generic proxy
+      if (lane == 0) mbar_expect_tx(mbar + 8u * b, (unsigned int)TC::BOX_BYTES * (unsigned int)__popc(mm));
       __syncwarp();
-      if (mine) tma_load_3d(smem_u32(&s_raw[warp][lane - g0][0]), &maps.lv[lv], wx0 & ~15, wy0, slot, mbar);
-      mbar_wait(mbar, phase);
-      phase ^= 1u;
+      if (lane >= g0 && lane < g0 + G && valid && tin)
+        tma_load_3d(smem_u32(&s_raw[warp][b][lane - g0][0]), &maps.lv[lv], wx0 & ~15, wy0, slot, mbar + 8u * b);
+    }
+  };
+  issue(0);
+  unsigned int phases = 0;  // bit b: parity of the phase buffer b's next wait is for
+#pragma unroll 1
+  for (int grp = 0; grp < 32 / G; ++grp) {
+    const int g0 = grp * G, buf = grp & 1;
+    if (grp + 1 < 32 / G) issue(grp + 1);
+    // a buffer's barrier advances one phase per group that loaded anything into it
+    if ((tin_mask >> g0) & ((1u << G) - 1u)) {
+      mbar_wait(mbar + 8u * buf, (phases >> buf) & 1u);
+      phases ^= 1u << buf;
     }
     __syncwarp();
 #pragma unroll 1
@@ -386,20 +406,41 @@ __global__ void __launch_bounds__(TmplCfg<HALF>::WARPS * 32) pagk_lk_template_ke
       float *T = reinterpret_cast<float *>(__shfl_sync(FULL, (unsigned long long)rec, j));
       // the tap of column x, row y sits at (y - wy0) * RB + (x - (wx0 & ~15))
       const int sx0 = __shfl_sync(FULL, wx0, j), sy0 = __shfl_sync(FULL, wy0, j);
-      const unsigned char *raw = &s_raw[warp][jj][0] + (sx0 & 15);
+      const unsigned char *raw = &s_raw[warp][buf][jj][0] + (sx0 & 15);
       float tv[TK];
       if (kind == 2) {
+        // Every pixel has the weights of pt.  Lanes = pixel PAIRS, the arithmetic packed across the pair, the taps taken as
+        // raw bytes read as subnormal floats (b * 2^-149) against weights scaled by 2^100: the same scaling argument as in
+        // the pass of the alignment kernel (a weight is 0 or at least 2^-21 here: pt >= HALF), every intermediate is the
+        // reference's times a power of two, and the last product with 2^-51 is exact.
         // floor by a round-down add of 2^23 (exact for 0 <= x < 2^22)
         const float xx = sptx - (__fadd_rd(sptx, 8388608.0f) - 8388608.0f), yy = spty - (__fadd_rd(spty, 8388608.0f) - 8388608.0f);
         const float wa = 1.0f - xx, wb = 1.0f - yy;
+        constexpr float SC = 1.2676506002282294e30f, UNS = 4.440892098500626e-16f;  // 2^100, 2^-51
+        const f2 WA = {wa * SC, wa * SC}, XX = {xx * SC, xx * SC}, WB = {wb * SC, wb * SC}, YY = {yy * SC, yy * SC};
+        const f2 ONE = {unit, unit}, UN = {UNS, UNS};
+        float tcv = 0.f, tlv = 0.f;
 #pragma unroll
-        for (int k = 0; k < TK; ++k) {
-          tv[k] = 0.f;
-          if (lane + 32 * k < NP) {
-            const unsigned char *q = raw + toff[k];
-            tv[k] = wb * (wa * u8f(q[0]) + xx * u8f(q[1])) + yy * (wa * u8f(q[RB]) + xx * u8f(q[RB + 1]));
+        for (int kk = 0; kk < TK2; ++kk) {
+          const int k = lane + 32 * kk;
+          if (k < NPAIR) {
+            const unsigned char *a = raw + toffp[kk], *b = raw + toffq[kk];
+#define PAGK_TAP2(o) f2{__uint_as_float((unsigned int)a[o]), __uint_as_float((unsigned int)b[o])}
+            const f2 t00 = PAGK_TAP2(0), t01 = PAGK_TAP2(1), t10 = PAGK_TAP2(RB), t11 = PAGK_TAP2(RB + 1);
+#undef PAGK_TAP2
+            const f2 top = fma2(mul2(WA, t00), ONE, mul2(XX, t01)), bot = fma2(mul2(WA, t10), ONE, mul2(XX, t11));
+            const f2 v = mul2(fma2(mul2(WB, top), ONE, mul2(YY, bot)), UN);
+            const int p = 2 * k;
+            if (p + 1 < NP - 1) *reinterpret_cast<float2 *>(T + p) = make_float2(v.x, v.y);
+            else if (p < NP - 1) T[p] = v.x;
+            if (k == (NP / 2) / 2) tcv = (NP / 2) % 2 ? v.y : v.x;
+            if (k == (NP - 1) / 2) tlv = v.x;
           }
         }
+        const float tc = __shfl_sync(FULL, tcv, ((NP / 2) / 2) % 32);
+        const float tl = __shfl_sync(FULL, tlv, ((NP - 1) / 2) % 32);
+        if (lane == j) { myc = -tc; mylast = tl; }
+        continue;
       } else if (kind == 1) {
 #pragma unroll
         for (int k = 0; k < TK; ++k) {
@@ -477,7 +518,7 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
   constexpr unsigned FULL = 0xffffffffu;
   // level geometry, indexed by each lane's own level
   __shared__ int s_cols[PAGK_MAX_LEVELS], s_rows[PAGK_MAX_LEVELS], s_pitch[PAGK_MAX_LEVELS];
-  __shared__ unsigned int s_off[PAGK_MAX_LEVELS], s_offw[PAGK_MAX_LEVELS];  // u8 level, level the windows come from
+  __shared__ unsigned int s_off[PAGK_MAX_LEVELS];
   // -DPAGK_LANES_LDSPAIRS: patch offsets of the pixel pairs from shared memory (one broadcast LDS.128 per pair)
 #if PAGK_LANES_LDSPAIRS
   __shared__ float4 s_pairs[(NP + 1) / 2];
@@ -488,7 +529,6 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
   if (threadIdx.x < PAGK_MAX_LEVELS) {
     s_cols[threadIdx.x] = g.lv[threadIdx.x].cols; s_rows[threadIdx.x] = g.lv[threadIdx.x].rows;
     s_pitch[threadIdx.x] = g.lv[threadIdx.x].pitch; s_off[threadIdx.x] = g.lv[threadIdx.x].offset;
-    s_offw[threadIdx.x] = g.lv[threadIdx.x].offset;
   }
   __syncthreads();
 
@@ -620,7 +660,7 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
     PROF(0); PROF_ADD(6, 1); PROF_ADD(7, __popc(m_active)); PROF_ADD(2, __popc(__ballot_sync(FULL, waiting)));
 
     const int cols = s_cols[level], rows = s_rows[level], pitch = s_pitch[level];
-    const unsigned char *I2w = images + (size_t)(pair * 2 + 1) * slot_bytes + s_offw[level];  // the plane the windows come from
+    const unsigned char *I2w = images + (size_t)(pair * 2 + 1) * slot_bytes + s_off[level];  // the plane the windows come from
     const float fcols = (float)cols, frows = (float)rows, fcm1 = (float)(cols - 1), frm1 = (float)(rows - 1);
 
     // ------------------------------------------------------------------ sample box of this pass (lane = slot)
@@ -1070,9 +1110,6 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
 }
 
 // -------------------------------------------------------------------------------------------------
-// whether the alignment kernel stages its windows from the 16-bit plane of the current images (build option)
-bool pagk_lk_lanes_win16() { return false; }  // the bfloat16 window plane of an earlier build is gone
-
 bool pagk_lk_lanes_supported(const PagkMode &mode) {
   return (mode.half == 5 || mode.half == 10) && mode.iterations >= 1;
 }
@@ -1152,7 +1189,7 @@ static int launch_lanes(const unsigned char *images, const PagkGeom &g, const Pa
     constexpr int W = TmplCfg<HALF>::WARPS;
     const long long items = total * mode.levels, groups = (items + 31) / 32;
     pagk_lk_template_kernel<HALF><<<(unsigned)((groups + W - 1) / W), W * 32, 0, st>>>(images, g, *tmaps, pcs, keys_un, mode.levels, max_keys,
-                                                                                      n_max, n_pairs, tmpl);
+                                                                                      n_max, n_pairs, tmpl, 1.0f);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
   }
