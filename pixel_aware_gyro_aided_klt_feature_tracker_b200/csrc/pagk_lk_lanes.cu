@@ -91,6 +91,10 @@ namespace {
 #ifndef PAGK_LANES_LDSPAIRS
 #define PAGK_LANES_LDSPAIRS 0
 #endif
+// the pass software-pipelined by hand: a pair's front half (coordinates, weights, taps) ahead of the previous pair's back half
+#ifndef PAGK_LANES_PIPE
+#define PAGK_LANES_PIPE 1
+#endif
 // register cap of the alignment kernel as CTAs per SM in its launch bounds (0: what the warps per SM imply)
 #ifndef PAGK_LANES_REGCTAS
 #define PAGK_LANES_REGCTAS 0
@@ -123,13 +127,16 @@ struct LanesCfg {
   static constexpr int WARPS_SM = WSM;
   static constexpr int WARPS = WARPS_SM % PAGK_LANES_CTA_WARPS == 0 ? PAGK_LANES_CTA_WARPS : WARPS_SM;  // per CTA
   static constexpr int CTAS_SM = WARPS_SM / WARPS;
-  // per-warp scratch of the pixel-parallel pass: COOP_BUFS buffers (one slot each), a buffer = COOP_CH records
-  // (Ix, Iy, -e) -- the whole 11 x 11 patch, a chunk of a 21 x 21 one --, the two constants c and 1, the twelve sums and
-  // the cost the accumulator lanes hand back, and a row-major copy of the slot's window
+  // per-warp scratch of the pixel-parallel pass: COOP_BUFS buffers (one slot each).  A buffer = COOP_CH records of
+  // 32 bytes (Ix, Iy, -e as doubles, e * e as float: converted by the lanes that sample, so that the serial
+  // accumulation loop has no conversion in it) -- the whole 11 x 11 patch, a chunk of a 21 x 21 one --, the two constants
+  // c and 1 (doubles), the twelve sums and the cost the accumulator lanes hand back, and a row-major copy of the slot's
+  // window.  Indices in floats.
   static constexpr int COOP_CH = HALF <= 5 ? 128 : 64;
-  static constexpr int COOP_BUFS = HALF <= 5 ? 2 : 1;
-  static constexpr int COOP_RES = COOP_CH * 3 + 4;              // float index of the results (8-byte aligned)
-  static constexpr int COOP_LIN = COOP_RES + 28;                // float index of the row-major window copy
+  static constexpr int COOP_BUFS = (HALF <= 5 && WSM <= 8) ? 2 : 1;
+  static constexpr int COOP_CONST = COOP_CH * 8;                // c, 1
+  static constexpr int COOP_RES = COOP_CONST + 4;               // twelve doubles, then the cost
+  static constexpr int COOP_LIN = COOP_RES + 28;                // the row-major window copy
   static constexpr int BUF_FLOATS = (COOP_LIN + WIN_WORDS + 3) & ~3;
   static constexpr int SCRATCH_FLOATS = COOP_BUFS * BUF_FLOATS;
   static constexpr int WARP_BYTES = WIN_WORDS * 128 + SCRATCH_FLOATS * 4;
@@ -541,8 +548,9 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
   const int role = role16 < 12 ? role16 : 0;
   const int selA = (int)((0x431044333110ull >> (4 * role)) & 0xfull);  // 0 Ix, 1 Iy, 3 c, 4 one
   const int selB = (int)((0x222210310100ull >> (4 * role)) & 0xfull);  // 0 Ix, 1 Iy, 2 -e, 3 c
-  const int offA = selA < 3 ? selA : C::COOP_CH * 3 + (selA - 3), strideA = selA < 3 ? 3 : 0;
-  const int offB = selB < 3 ? selB : C::COOP_CH * 3 + (selB - 3), strideB = selB < 3 ? 3 : 0;
+  // offsets and strides in doubles: a record is four doubles wide
+  const int offA = selA < 3 ? selA : C::COOP_CONST / 2 + (selA - 3), strideA = selA < 3 ? 4 : 0;
+  const int offB = selB < 3 ? selB : C::COOP_CONST / 2 + (selB - 3), strideB = selB < 3 ? 4 : 0;
 
   // ---- slot state (registers of the owning lane) ----
   int feat = -1, pair = 0, level = 0, iter = 0, n_iter = 0, succ = 1;
@@ -780,8 +788,14 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
         b0 = mywin + ((i1 >> 2) * 124u + i1);
         b1 = b0 + ((s + 1u) & 4u) * 31u; b2 = b0 + ((s + 2u) & 4u) * 31u; b3 = b0 + ((s + 3u) & 4u) * 31u;
       };
-      // pixels p = 2 * k2 (.x) and p + 1 (.y); `both` false: only .x enters the sums (the last pixel of an odd patch)
-      auto pixels = [&](const int k2, const f2 tv, const bool both) {
+      // A pixel pair p = 2 * k2 (.x), p + 1 (.y) in two halves.  front: sample coordinates, weights, tap loads (a pair's
+      // 20 weights and 24 taps); back: the interpolations, residual, gradient and the ordered sums (`both` false: only .x
+      // enters the sums -- the last pixel of an odd patch, whose pair repeats it).  The loop issues the front half of
+      // pair k + 1 before the back half of pair k, so that a warp alone on its scheduler has a pair's loads and address
+      // arithmetic in flight under the previous pair's arithmetic (tools/ubench_pass2.cu V5: 10 % fewer cycles per pass
+      // for a lone warp, 9 % with three warps per scheduler).
+      struct Front { f2 WA, XX, WB, YY, WA1, XX1, WB1, YY1, m0, m1, c_1, c0, c1, c2, d_1, d0, d1, d2, n0, n1; };
+      auto front = [&](const int k2, Front &F) {
         const float4 xy = pix[k2];
         const f2 XF = {xy.x, xy.y}, YF = {xy.z, xy.w};
         f2 SX, SY;
@@ -794,33 +808,34 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
         // floor for 0 <= x < 2^22: x + 2^23 rounded DOWN is 2^23 + floor(x) exactly; taking 2^23 off is exact
         const f2 TX = addrd2(SX, BIG), TY = addrd2(SY, BIG);
         const f2 FX = add2(TX, NBIG), FY = add2(TY, NBIG);
-        const f2 XX = sub2(SX, FX), YY = sub2(SY, FY);
-        const f2 WA = sub2(P1, XX), WB = sub2(P1, YY);
+        F.XX = sub2(SX, FX); F.YY = sub2(SY, FY);
+        F.WA = sub2(P1, F.XX); F.WB = sub2(P1, F.YY);
         const f2 X1 = add2(SX, P1), Y1 = add2(SY, P1);
-        const f2 XX1 = sub2(X1, add2(FX, P1)), YY1 = sub2(Y1, add2(FY, P1));
-        const f2 WA1 = sub2(P1, XX1), WB1 = sub2(P1, YY1);
-        badv = fmaxf(badv, fmaxf(XX1.x, YY1.x));
-        if (both) badv = fmaxf(badv, fmaxf(XX1.y, YY1.y));
+        F.XX1 = sub2(X1, add2(FX, P1)); F.YY1 = sub2(Y1, add2(FY, P1));
+        F.WA1 = sub2(P1, F.XX1); F.WB1 = sub2(P1, F.YY1);
+        badv = fmaxf(badv, fmaxf(fmaxf(F.XX1.x, F.YY1.x), fmaxf(F.XX1.y, F.YY1.y)));
         const unsigned int ip = (unsigned int)__float_as_int(TY.x) * (unsigned int)WIN_W + (unsigned int)__float_as_int(TX.x) - kk;
         const unsigned int iq = (unsigned int)__float_as_int(TY.y) * (unsigned int)WIN_W + (unsigned int)__float_as_int(TX.y) - kk;
         const unsigned char *p0, *p1, *p2, *p3, *q0, *q1, *q2, *q3;
         bases(ip, p0, p1, p2, p3); bases(iq, q0, q1, q2, q3);
         constexpr int R = C::ROW_BYTES;
 #define PAGK_TAP(pb, qb, o) f2{__uint_as_float((unsigned int)pb[o]), __uint_as_float((unsigned int)qb[o])}
-        const f2 m0 = PAGK_TAP(p1, q1, 1 - R), m1 = PAGK_TAP(p2, q2, 2 - R);
-        const f2 c_1 = PAGK_TAP(p0, q0, 0), c0 = PAGK_TAP(p1, q1, 1), c1 = PAGK_TAP(p2, q2, 2), c2 = PAGK_TAP(p3, q3, 3);
-        const f2 d_1 = PAGK_TAP(p0, q0, R), d0 = PAGK_TAP(p1, q1, 1 + R), d1 = PAGK_TAP(p2, q2, 2 + R), d2 = PAGK_TAP(p3, q3, 3 + R);
-        const f2 n0 = PAGK_TAP(p1, q1, 1 + 2 * R), n1 = PAGK_TAP(p2, q2, 2 + 2 * R);
+        F.m0 = PAGK_TAP(p1, q1, 1 - R); F.m1 = PAGK_TAP(p2, q2, 2 - R);
+        F.c_1 = PAGK_TAP(p0, q0, 0); F.c0 = PAGK_TAP(p1, q1, 1); F.c1 = PAGK_TAP(p2, q2, 2); F.c2 = PAGK_TAP(p3, q3, 3);
+        F.d_1 = PAGK_TAP(p0, q0, R); F.d0 = PAGK_TAP(p1, q1, 1 + R); F.d1 = PAGK_TAP(p2, q2, 2 + R); F.d2 = PAGK_TAP(p3, q3, 3 + R);
+        F.n0 = PAGK_TAP(p1, q1, 1 + 2 * R); F.n1 = PAGK_TAP(p2, q2, 2 + 2 * R);
 #undef PAGK_TAP
+      };
+      auto back = [&](const Front &F, const f2 tv, const bool both) {
         // rn(rn(w * a) + rn(u * b)): two products and a sum that ptxas cannot contract
 #define PAGK_LERP(w, a, u, b) fma2(mul2(w, a), ONE, mul2(u, b))
-        const f2 Hm = PAGK_LERP(WA, m0, XX, m1);
-        const f2 H0 = PAGK_LERP(WA, c0, XX, c1), H0p = PAGK_LERP(WA1, c1, XX1, c2), H0m = PAGK_LERP(WA, c_1, XX, c0);
-        const f2 H1 = PAGK_LERP(WA, d0, XX, d1), H1p = PAGK_LERP(WA1, d1, XX1, d2), H1m = PAGK_LERP(WA, d_1, XX, d0);
-        const f2 H2 = PAGK_LERP(WA, n0, XX, n1);
-        const f2 v0 = PAGK_LERP(WB, H0, YY, H1);
-        const f2 vx1 = PAGK_LERP(WB, H0p, YY, H1p), vx2 = PAGK_LERP(WB, H0m, YY, H1m);
-        const f2 vy1 = PAGK_LERP(WB1, H1, YY1, H2), vy2 = PAGK_LERP(WB, Hm, YY, H0);
+        const f2 Hm = PAGK_LERP(F.WA, F.m0, F.XX, F.m1);
+        const f2 H0 = PAGK_LERP(F.WA, F.c0, F.XX, F.c1), H0p = PAGK_LERP(F.WA1, F.c1, F.XX1, F.c2), H0m = PAGK_LERP(F.WA, F.c_1, F.XX, F.c0);
+        const f2 H1 = PAGK_LERP(F.WA, F.d0, F.XX, F.d1), H1p = PAGK_LERP(F.WA1, F.d1, F.XX1, F.d2), H1m = PAGK_LERP(F.WA, F.d_1, F.XX, F.d0);
+        const f2 H2 = PAGK_LERP(F.WA, F.n0, F.XX, F.n1);
+        const f2 v0 = PAGK_LERP(F.WB, H0, F.YY, H1);
+        const f2 vx1 = PAGK_LERP(F.WB, H0p, F.YY, H1p), vx2 = PAGK_LERP(F.WB, H0m, F.YY, H1m);
+        const f2 vy1 = PAGK_LERP(F.WB1, H1, F.YY1, H2), vy2 = PAGK_LERP(F.WB, Hm, F.YY, H0);
 #undef PAGK_LERP
         // -e = gain * T - (v0 + db) (the reference's e = (v0 + db) - gain * T negated: exact)
         const f2 U = fma2(v0, UN, DB);
@@ -849,9 +864,8 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
           S.cost = S.cost + M2.y;
         }
       };
-      // one flat walk over the P * P pixels (row-major, the reference's order), two pairs per trip with their template
-      // values in one vector load (L1 / L2; the next trip's vector is loaded before this trip's pixels are computed);
-      // the last pixel's template value is a register
+      // one flat walk over the P * P pixels (row-major, the reference's order), two pairs per template vector (L1 / L2; the
+      // next trip's vectors are loaded before this trip's pixels are computed); the last pixel's template value is a register
       static_assert((NP - 1) % (4 * PAGK_LANES_TRIP) == 0, "vector loads of the template per trip");
       constexpr int NV = (NP - 1) / 4;  // vectors of four template values
 #if !PAGK_LANES_TPRE
@@ -859,6 +873,27 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
 #pragma unroll
       for (int u = 0; u < PAGK_LANES_TRIP; ++u) t4[u] = __ldg(Tg + u);
 #endif
+#if PAGK_LANES_PIPE
+      Front F0, F1;
+      front(0, F0);
+#pragma unroll 1
+      for (int j = 0; j < NV; j += PAGK_LANES_TRIP) {
+        float4 nx[PAGK_LANES_TRIP];
+#pragma unroll
+        for (int u = 0; u < PAGK_LANES_TRIP; ++u) nx[u] = __ldg(Tg + min(j + PAGK_LANES_TRIP + u, NV - 1));
+#pragma unroll
+        for (int u = 0; u < PAGK_LANES_TRIP; ++u) {
+          front(2 * (j + u) + 1, F1);
+          back(F0, f2{t4[u].x, t4[u].y}, true);
+          front(2 * (j + u) + 2, F0);
+          back(F1, f2{t4[u].z, t4[u].w}, true);
+        }
+#pragma unroll
+        for (int u = 0; u < PAGK_LANES_TRIP; ++u) t4[u] = nx[u];
+      }
+      back(F0, f2{tlast, tlast}, false);
+#else
+      auto pixels = [&](const int k2, const f2 tv, const bool both) { Front F; front(k2, F); back(F, tv, both); };
 #pragma unroll 1
       for (int j = 0; j < NV; j += PAGK_LANES_TRIP) {
         float4 nx[PAGK_LANES_TRIP];
@@ -872,6 +907,7 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
         for (int u = 0; u < PAGK_LANES_TRIP; ++u) t4[u] = nx[u];
       }
       pixels((NP - 1) / 2, f2{tlast, tlast}, false);
+#endif
       constexpr double G1 = 2.220446049250313e-16;  // 2^-52: the samples' 2^51 and the central difference's 2
       S.h00 *= G1 * G1; S.h10 *= G1 * G1; S.h11 *= G1 * G1;
       S.h20 *= G1; S.h21 *= G1; S.h30 *= G1; S.h31 *= G1; S.b0 *= G1; S.b1 *= G1;
@@ -919,7 +955,7 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
           Tp[b] = reinterpret_cast<const float *>(__shfl_sync(FULL, (unsigned long long)Tg, s));
           if (sl[b] >= 0) {
             float *buf = scratch + b * C::BUF_FLOATS;
-            if (lane == 0) { buf[CH * 3] = scv; buf[CH * 3 + 1] = 1.0f; }
+            if (lane == 0) { reinterpret_cast<double *>(buf + C::COOP_CONST)[0] = (double)scv; reinterpret_cast<double *>(buf + C::COOP_CONST)[1] = 1.0; }
             if (skind[b] != 2) {  // the slot's window, row-major
               const unsigned int *src = reinterpret_cast<const unsigned int *>(wwin) + s;
               unsigned int *lin = reinterpret_cast<unsigned int *>(buf + C::COOP_LIN);
@@ -1000,22 +1036,24 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
                   vy2 = pagk_sample_call(img2[b], sp[b], scols[b], srows[b], sx, sy - 1.0f);
                 }
               }
-              const float e = (v0 + sdb[b]) - sgain[b] * tv[k];
-              buf[3 * q] = 0.5f * (vx1 - vx2);
-              buf[3 * q + 1] = 0.5f * (vy1 - vy2);
-              buf[3 * q + 2] = -e;
+              const float e = (v0 + sdb[b]) - sgain[b] * tv[k], me = -e;
+              double2 *rec = reinterpret_cast<double2 *>(buf + 8 * q);
+              rec[0] = make_double2((double)(0.5f * (vx1 - vx2)), (double)(0.5f * (vy1 - vy2)));
+              rec[1] = make_double2((double)me, __hiloint2double(0, __float_as_int(me * me)));
             }
           }
           __syncwarp();
           const int n = min(CH, NP - p0);
-          const float *base = scratch + cbuf * C::BUF_FLOATS;
-          const float *pa = base + offA, *pb = base + offB, *pm = base + 2;
-#pragma unroll 4
+          const double *base = reinterpret_cast<const double *>(scratch + cbuf * C::BUF_FLOATS);
+          const double *pa = base + offA, *pb = base + offB;
+          const float *pm = reinterpret_cast<const float *>(base) + 6;  // e * e: the low word of a record's fourth double
+#pragma unroll 8
           for (int q = 0; q < n; ++q) {
-            const float fa = *pa, fb = *pb, fm = *pm;
-            pa += strideA; pb += strideB; pm += 3;
-            acc = fma((double)fa, (double)fb, acc);
-            cacc = cacc + fm * fm;
+            const double da = *pa, db2 = *pb;
+            const float m2 = *pm;
+            pa += strideA; pb += strideB; pm += 8;
+            acc = fma(da, db2, acc);
+            cacc = cacc + m2;
           }
         }
         // the sums back to the slots' lanes through the buffers

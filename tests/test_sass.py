@@ -66,13 +66,16 @@ def test_fused_operations_of_the_pass_are_the_written_ones(kernels, affine):
         assert body is not None, n
         c = opcodes(body)
         pairs = c["DFMA"] // 16        # a pixel pair has 2 x 8 DFMA
-        assert pairs in (2, 4) and c["DADD"] == 6 * pairs and c["F2F"] == 6 * pairs
+        # three conversions per pixel (a register-starved instantiation may rematerialise the loop-invariant c or gain)
+        assert pairs in (2, 4) and c["DADD"] == 6 * pairs and 6 * pairs <= c["F2F"] <= 6 * pairs + 2, (n, c)
         # per pair: 13 interpolations + the residual's two + the two sample coordinates (affine: the warp offsets), each ONE
         # fma2 in the source -- fma2(x, 1, y), fma(v, 2^-51, db), fma(offset, 2^100, base) --; every other packed
         # operation must still be a separate FMUL2 / FADD2
         assert c["FFMA2"] == 17 * pairs, (n, c)
         assert c["FMUL2"] == (32 if affine else 28) * pairs, (n, c)
-        assert c["FADD2"] == (20 if affine else 18) * pairs, (n, c)
+        # (a contraction would move one FMUL2 and one FADD2 into an FFMA2: the two counts above exclude it; an instantiation at
+        # its register cap may recompute a loop-invariant packed constant inside the loop, which adds FADD2 only)
+        assert (20 if affine else 18) * pairs <= c["FADD2"] <= (20 if affine else 18) * pairs + 2, (n, c)
         assert c["FFMA"] == 0 and c["FMUL"] == 0, (n, c)    # no scalar FP32 product left in the loop, fused or not
         assert c["LDS"] == 24 * pairs, (n, c)               # twelve byte taps per pixel, nothing spilled
 
