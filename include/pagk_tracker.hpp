@@ -269,9 +269,12 @@ class GyroAidedTracker {
       pts(t.mvPtPredictUn, p_un, n); pts(t.mvPtPredict, p, n); pts(t.mvPtGyroPredictUn, g_un, n); pts(t.mvPtGyroPredict, g, n);
       pts(t.mvFlowsPredictUn, fl, n);
       t.mvStatus = st;
-      // the corner vectors and A exist only for features that passed the gyro border test (:131-168)
+      // the corner vectors and A exist only for features that passed the gyro border test (:131-168); without a gyro
+      // prediction (IMAGE_ONLY_..., :264-270) the reference leaves the corner vectors empty and the kernels write A = identity
       std::vector<uint8_t> gyro_ok(n);
-      for (size_t i = 0; i < n; ++i) gyro_ok[i] = (aff[4 * i] != 0.f || aff[4 * i + 1] != 0.f || aff[4 * i + 2] != 0.f || aff[4 * i + 3] != 0.f);
+      const bool predicted = t.mType != GyroAidedTracker::IMAGE_ONLY_OPTICAL_FLOW_CONSIDER_ILLUMINATION;
+      for (size_t i = 0; i < n; ++i)
+        gyro_ok[i] = predicted && (aff[4 * i] != 0.f || aff[4 * i + 1] != 0.f || aff[4 * i + 2] != 0.f || aff[4 * i + 3] != 0.f);
       corners(t.mvvFlowsPredictCorners, cfl, gyro_ok, n); corners(t.mvvPtPredictCornersUn, c_un, gyro_ok, n);
       corners(t.mvvPtPredictCorners, c, gyro_ok, n);
       t.mvAffineDeformationMatrix.resize(n);
