@@ -294,10 +294,13 @@ struct TmplCfg {
   // coordinate is not a multiple of 16 bytes faults: measured, tools/probes/tma_probe2.cu), so the box is the aligned
   // ROW_BYTES around those columns x ROWS.
   static constexpr int ROWS = P + 2;
-  static constexpr int ROW_BYTES = (15 + P + 2 + 15) & ~15;
+  // (32 bytes would do for 11 x 11; with 48 the rows that one tap load of the pixel-pair lanes touches fall into distinct
+  // shared-memory banks: 65 -> 61 us)
+  static constexpr int ROW_BYTES = HALF <= 5 ? 48 : (15 + P + 2 + 15) & ~15;
   static constexpr int BOX_BYTES = ROWS * ROW_BYTES;
   static constexpr int ITEM_BYTES = (BOX_BYTES + 127) & ~127;  // TMA destinations are 128-byte aligned
-  static constexpr int G = HALF <= 5 ? 8 : 4;                  // items per group; two groups in flight: 10 / 9 KB per warp
+  // items per group; two groups in flight: 10 / 9 KB per warp (groups of four with twice the CTAs per SM: 70 us against 61)
+  static constexpr int G = HALF <= 5 ? 8 : 4;
   static constexpr int WARPS = 4;
 };
 
@@ -380,7 +383,7 @@ __global__ void __launch_bounds__(TmplCfg<HALF>::WARPS * 32) pagk_lk_template_ke
   float myc = 0.f, mylast = 0.f;
   // ---- the tap blocks of a group of G items: every owner lane issues its own tile load.  Two groups are in flight: the
   // loads of group n + 1 are issued before the pixels of group n are computed.
-  const unsigned int tin_mask = __ballot_sync(FULL, valid && tin);
+  const unsigned int tin_mask = __ballot_sync(FULL, valid && tin), uni_mask = __ballot_sync(FULL, valid && tin && uni);
   auto issue = [&](const int grp) {
     const int g0 = grp * G, b = grp & 1;
     const unsigned int mm = (tin_mask >> g0) & ((1u << G) - 1u);
@@ -404,51 +407,79 @@ __global__ void __launch_bounds__(TmplCfg<HALF>::WARPS * 32) pagk_lk_template_ke
       phases ^= 1u << buf;
     }
     __syncwarp();
+    // ---- items whose pixels all have the weights of pt (the usual case), TWO items at a time so that a warp has two
+    // independent chains of loads and arithmetic in flight.  Lanes = pixel PAIRS, the arithmetic packed across the pair, the
+    // taps taken as raw bytes read as subnormal floats (b * 2^-149) against weights scaled by 2^100: the same scaling
+    // argument as in the pass of the alignment kernel (a weight is 0 or at least 2^-21 here: pt >= HALF), every intermediate
+    // is the reference's times a power of two, and the last product with 2^-51 is exact.
+    {
+      struct Item { f2 WA, XX, WB, YY; const unsigned char *raw; float *T; };
+      auto prep = [&](const int j, const int jj) {
+        const float sptx = __shfl_sync(FULL, ptx, j), spty = __shfl_sync(FULL, pty, j);
+        const int sx0 = __shfl_sync(FULL, wx0, j);
+        Item it;
+        it.T = reinterpret_cast<float *>(__shfl_sync(FULL, (unsigned long long)rec, j));
+        it.raw = &s_raw[warp][buf][jj][0] + (sx0 & 15);  // the tap of column x, row y sits at (y - wy0) * RB + (x - (wx0 & ~15))
+        // floor by a round-down add of 2^23 (exact for 0 <= x < 2^22)
+        const float xx = sptx - (__fadd_rd(sptx, 8388608.0f) - 8388608.0f), yy = spty - (__fadd_rd(spty, 8388608.0f) - 8388608.0f);
+        const float wa = 1.0f - xx, wb = 1.0f - yy;
+        constexpr float SC = 1.2676506002282294e30f;  // 2^100
+        it.WA = f2{wa * SC, wa * SC}; it.XX = f2{xx * SC, xx * SC}; it.WB = f2{wb * SC, wb * SC}; it.YY = f2{yy * SC, yy * SC};
+        return it;
+      };
+      const f2 ONE = {unit, unit}, UN = {4.440892098500626e-16f, 4.440892098500626e-16f};  // 1, 2^-51
+      auto pair_of = [&](const Item &it, const int kk) {
+        const unsigned char *a = it.raw + toffp[kk], *b = it.raw + toffq[kk];
+#define PAGK_TAP2(o) f2{__uint_as_float((unsigned int)a[o]), __uint_as_float((unsigned int)b[o])}
+        const f2 t00 = PAGK_TAP2(0), t01 = PAGK_TAP2(1), t10 = PAGK_TAP2(RB), t11 = PAGK_TAP2(RB + 1);
+#undef PAGK_TAP2
+        const f2 top = fma2(mul2(it.WA, t00), ONE, mul2(it.XX, t01)), bot = fma2(mul2(it.WA, t10), ONE, mul2(it.XX, t11));
+        return mul2(fma2(mul2(it.WB, top), ONE, mul2(it.YY, bot)), UN);
+      };
+      auto put = [&](const Item &it, const int k, const f2 v, float &tcv, float &tlv) {
+        const int p = 2 * k;
+        if (p + 1 < NP - 1) *reinterpret_cast<float2 *>(it.T + p) = make_float2(v.x, v.y);
+        else if (p < NP - 1) it.T[p] = v.x;
+        if (k == (NP / 2) / 2) tcv = (NP / 2) % 2 ? v.y : v.x;
+        if (k == (NP - 1) / 2) tlv = v.x;
+      };
+      unsigned int m2 = (uni_mask >> g0) & ((1u << G) - 1u);
+      while (m2) {
+        const int ja = __ffs(m2) - 1;
+        m2 &= m2 - 1;
+        const bool two = m2 != 0u;
+        const int jb = two ? __ffs(m2) - 1 : ja;
+        m2 &= m2 - 1;
+        const Item A = prep(g0 + ja, ja), B = prep(g0 + jb, jb);
+        float tca = 0.f, tla = 0.f, tcb = 0.f, tlb = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < TK2; ++kk) {
+          const int k = lane + 32 * kk;
+          if (k < NPAIR) {
+            const f2 va = pair_of(A, kk), vb = pair_of(B, kk);
+            put(A, k, va, tca, tla);
+            if (two) put(B, k, vb, tcb, tlb);
+          }
+        }
+        const float ca = __shfl_sync(FULL, tca, ((NP / 2) / 2) % 32), la = __shfl_sync(FULL, tla, ((NP - 1) / 2) % 32);
+        const float cb = __shfl_sync(FULL, tcb, ((NP / 2) / 2) % 32), lb = __shfl_sync(FULL, tlb, ((NP - 1) / 2) % 32);
+        if (lane == g0 + ja) { myc = -ca; mylast = la; }
+        if (two && lane == g0 + jb) { myc = -cb; mylast = lb; }
+      }
+    }
+    // ---- the other items, one at a time
 #pragma unroll 1
     for (int jj = 0; jj < G; ++jj) {
       const int j = g0 + jj;
-      if (!__shfl_sync(FULL, (int)valid, j)) continue;
-      const int kind = __shfl_sync(FULL, (int)tin + (int)uni, j);  // 0: clamps may fire, 1: per-pixel weights, 2: shared weights
+      if (!__shfl_sync(FULL, (int)(valid && !(tin && uni)), j)) continue;
+      const int kind = __shfl_sync(FULL, (int)tin + (int)uni, j);  // 0: clamps may fire, 1: per-pixel weights
       const float sptx = __shfl_sync(FULL, ptx, j), spty = __shfl_sync(FULL, pty, j);
       float *T = reinterpret_cast<float *>(__shfl_sync(FULL, (unsigned long long)rec, j));
       // the tap of column x, row y sits at (y - wy0) * RB + (x - (wx0 & ~15))
       const int sx0 = __shfl_sync(FULL, wx0, j), sy0 = __shfl_sync(FULL, wy0, j);
       const unsigned char *raw = &s_raw[warp][buf][jj][0] + (sx0 & 15);
       float tv[TK];
-      if (kind == 2) {
-        // Every pixel has the weights of pt.  Lanes = pixel PAIRS, the arithmetic packed across the pair, the taps taken as
-        // raw bytes read as subnormal floats (b * 2^-149) against weights scaled by 2^100: the same scaling argument as in
-        // the pass of the alignment kernel (a weight is 0 or at least 2^-21 here: pt >= HALF), every intermediate is the
-        // reference's times a power of two, and the last product with 2^-51 is exact.
-        // floor by a round-down add of 2^23 (exact for 0 <= x < 2^22)
-        const float xx = sptx - (__fadd_rd(sptx, 8388608.0f) - 8388608.0f), yy = spty - (__fadd_rd(spty, 8388608.0f) - 8388608.0f);
-        const float wa = 1.0f - xx, wb = 1.0f - yy;
-        constexpr float SC = 1.2676506002282294e30f, UNS = 4.440892098500626e-16f;  // 2^100, 2^-51
-        const f2 WA = {wa * SC, wa * SC}, XX = {xx * SC, xx * SC}, WB = {wb * SC, wb * SC}, YY = {yy * SC, yy * SC};
-        const f2 ONE = {unit, unit}, UN = {UNS, UNS};
-        float tcv = 0.f, tlv = 0.f;
-#pragma unroll
-        for (int kk = 0; kk < TK2; ++kk) {
-          const int k = lane + 32 * kk;
-          if (k < NPAIR) {
-            const unsigned char *a = raw + toffp[kk], *b = raw + toffq[kk];
-#define PAGK_TAP2(o) f2{__uint_as_float((unsigned int)a[o]), __uint_as_float((unsigned int)b[o])}
-            const f2 t00 = PAGK_TAP2(0), t01 = PAGK_TAP2(1), t10 = PAGK_TAP2(RB), t11 = PAGK_TAP2(RB + 1);
-#undef PAGK_TAP2
-            const f2 top = fma2(mul2(WA, t00), ONE, mul2(XX, t01)), bot = fma2(mul2(WA, t10), ONE, mul2(XX, t11));
-            const f2 v = mul2(fma2(mul2(WB, top), ONE, mul2(YY, bot)), UN);
-            const int p = 2 * k;
-            if (p + 1 < NP - 1) *reinterpret_cast<float2 *>(T + p) = make_float2(v.x, v.y);
-            else if (p < NP - 1) T[p] = v.x;
-            if (k == (NP / 2) / 2) tcv = (NP / 2) % 2 ? v.y : v.x;
-            if (k == (NP - 1) / 2) tlv = v.x;
-          }
-        }
-        const float tc = __shfl_sync(FULL, tcv, ((NP / 2) / 2) % 32);
-        const float tl = __shfl_sync(FULL, tlv, ((NP - 1) / 2) % 32);
-        if (lane == j) { myc = -tc; mylast = tl; }
-        continue;
-      } else if (kind == 1) {
+      if (kind == 1) {
 #pragma unroll
         for (int k = 0; k < TK; ++k) {
           const float cx = sptx + tpx[k], cy = spty + tpy[k];
