@@ -42,7 +42,7 @@ def profiled_traffic(cfg_name, n_pairs):
         return (e["bytes_per_launch"], "profiles/r02_k3_traffic.json: " + e["note"]) if e else (None, None)
     except Exception:
         return None, None
-N_ROTATE = 3  # resident batches per GPU; 3 x 61 MB of pyramids > 126 MB L2
+N_ROTATE = int(os.environ.get("PAGK_BENCH_ROTATE", "3"))  # resident batches per GPU; 3 x 61 MB of pyramids > 126 MB L2
 E2E_DEPTH = 5  # handles (streams) the end-to-end leg rotates over: uploads, kernels and downloads of 5 batches in flight
 
 

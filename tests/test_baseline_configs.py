@@ -128,6 +128,40 @@ def test_21x21_patches_level_granular_items_two_thousand_features():
         assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout[-2000:] + r.stderr[-2000:]
 
 
+def test_11x11_both_launch_shapes_and_item_modes():
+    """pagk_lk_lanes_kernel<5, *, 8> and <5, *, 12> (the launcher picks by the number of features; PAGK_LK_WARPS forces
+    either) with feature-granular and level-granular items, on a batch small enough for every combination to be unusual:
+    3 pairs x 700 features with border features, eType 4 and eType 3 (no affine matrix).  Child processes because the
+    switches are read once."""
+    code = (
+        "import os, numpy as np\n"
+        "from pixel_aware_gyro_aided_klt_feature_tracker_b200 import capi, synth, tracker\n"
+        "from oracle import oracle\n"
+        "from tests import helpers\n"
+        "pairs = [synth.make_pair(5200 + i, width=640, height=400, n_keys=700, pyramids=4, border=6) for i in range(3)]\n"
+        "oracle.build(); oracle.load()\n"
+        "tot = 0\n"
+        "for et in (4, 3):\n"
+        "    prm = capi.default_params(pyramids=4, e_type=et)\n"
+        "    with tracker.Context(max_width=640, max_height=400, max_keys=700, max_pairs=3, max_levels=4) as ctx:\n"
+        "        gpu = ctx.track_batch(pairs, prm)\n"
+        "    rc, cpu = oracle.track_batch(pairs, prm, os.cpu_count() or 4)\n"
+        "    assert rc == 0\n"
+        "    for g, c in zip(gpu, cpu):\n"
+        "        helpers.assert_north_star(g, c); helpers.assert_bit_exact(g, c)\n"
+        "    tot += sum(g.n_iterations for g in gpu)\n"
+        "print('ok', tot)\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    seen = set()
+    for warps in ("8", "12"):
+        for split in ("1", "0"):
+            r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, PAGK_LK_WARPS=warps, PAGK_LK_SPLIT=split),
+                               capture_output=True, text=True, timeout=900, cwd=root)
+            assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout[-2000:] + r.stderr[-2000:]
+            seen.add(r.stdout.split()[1])
+    assert len(seen) == 1, seen   # the same number of feature-iterations whatever the shape of the launch
+
+
 def test_two_devices_one_process_two_host_threads(cuda_lib):
     """include/pagk.h: "one handle per device; handles on different devices are independent".  Function attributes (the
     dynamic shared memory opt-in of the alignment kernel) and __constant__ tables belong to a device: pagk_create sets them
