@@ -1,5 +1,5 @@
-// pagk_lk_lanes.cu -- K3, the production patch-alignment kernels: a template staging pass (K3a) and the alignment
-// kernel proper (K3b, one LANE per feature) fed by the copy engines.
+// pagk_lk_lanes.cu -- K3, the production patch-alignment kernels: a template pass (K3a, fed by TMA tile loads) and the
+// alignment kernel proper (K3b, one LANE per feature, windows by asynchronous copies).
 //
 // Reference: PatchMatch::OpticalFlowMultiLevel + OpticalFlowConsideringIlluminationChange_onePixel,
 // src/patch_match.cpp:79-142 and :167-367 (forward-additive Gauss-Newton on (dx, dy, dg, db)).
@@ -7,49 +7,52 @@
 // Why this shape.  The 4x4 normal matrix of the reference is structurally singular, so the
 // 14 sums of one Gauss-Newton pass must be taken in double, in the reference's pixel order: a serial chain
 // of P*P steps per feature.  Independent features are the only parallelism that keeps that order, so a
-// lane owns a feature ("slot") for a whole pyramid level -- all its iterations -- and walks the patch pixel by
-// pixel: five bilinear samples of the current image (FP32, no FMA contraction), residual and gradient, then
-// straight into the lane's eleven FP64 accumulators and the float cost.  Nothing is handed over between threads
-// inside a level, there is no block barrier and no role: every warp of the CTA is an independent worker with 32
-// slots, and a lane refills itself from the global work counter when its level is finished.
+// lane owns a feature ("slot") for a whole pyramid level -- all its iterations -- and walks the patch two pixels
+// at a time: five bilinear samples per pixel of the current image (packed FP32, no FMA contraction), residual and
+// gradient, then straight into the lane's eleven FP64 accumulators and the float cost.  Nothing is handed over between
+// threads inside a level, there is no block barrier and no role: every warp of the CTA is an independent worker with
+// 32 slots, and a lane refills itself from the global work counter when its level is finished.
 //
 // What a level needs before its first pass, and where it comes from:
 //   T[p] = I1(pt + (x, y)), the P*P template values, c = -I1(pt) and h22 = sum of c*c.  They depend on the
 //        reference keypoint and the level only -- not on the tracking result of the level above -- so K3a computes
-//        them for every (feature, level) of the batch up front, pixel-parallel at full occupancy, into one record
-//        per item in global memory.  K3b moves a record's T into the lane's slot with ONE bulk asynchronous copy
-//        (cp.async.bulk -> UBLKCP, completion on a per-warp mbarrier) issued by the lane itself, and the record's
-//        16-byte tail (last T value, c, h22) with one vector load.
+//        them for every (feature, level) of the batch up front, pixel-parallel, into one record per item in global
+//        memory: an item's (P+2) x (P+2) tap block arrives by ONE TMA tile load (cp.async.bulk.tensor -> UTMALDG.3D,
+//        completion on the warp's mbarrier).  K3b streams T from the record during the pass (LDG.128, the next
+//        vectors prefetched) and takes the record's 16-byte tail (last T value, c, h22) with one vector load.
 //   the WIN_W x WIN_H u8 window of the current image around the lane's sample box: 4-byte asynchronous copies
-//        (cp.async -> LDGSTS, lanes = window words) straight from the pyramid level, which is why a level's rows
-//        are 4-byte aligned (PagkLevelGeom::pitch).
-// All copies of a round -- every lane that starts a level, every window that moved -- are in flight together and
-// the warp waits for them once; no tap is staged through registers and no lane-serial setup code is left in the
-// alignment kernel (it was 31 % of a warp's time and a third of the kernel's code).
+//        (cp.async -> LDGSTS, each lane copies its own window) straight from the pyramid level, which is why a
+//        level's rows are aligned (PagkLevelGeom::pitch).
+// All copies of a round -- every window that starts a level or moved -- are in flight together and the warp waits for
+// them once; no tap is staged through registers and no lane-serial setup code is left in the alignment kernel (it was
+// 31 % of a warp's time and a third of the kernel's code in round 1).
 //
-// Shared memory holds the windows only (u8), laid out ONE BANK PER LANE: word w of lane l's window sits at
+// Shared memory holds the windows (u8), laid out ONE BANK PER LANE: word w of lane l's window sits at
 // (w * 32 + l) * 4 inside the warp's block, so whatever the lanes' sample offsets are, a tap load is one wavefront.
 // (Slot-contiguous windows cost 2.65 wavefronts per load at production offsets: the pass was bound by the
-// shared-memory pipe as soon as its arithmetic got cheaper, tools/ubench_pass2.cu.)
+// shared-memory pipe as soon as its arithmetic got cheaper, tools/ubench_pass2.cu.)  Behind the windows: the buffers
+// of the pixel-parallel pass.
 //
-// The pass arithmetic (argued bit-exact above the loop):
-//   * two pixels per step, every FP32 operation packed across the pair (FADD2 / FMUL2 / FFMA2, sm_100): 35 packed
-//     operations per pixel instead of 75 scalar ones;
+// The pass arithmetic (argued bit-exact above the loop; tests/test_sass.py counts its fused operations):
+//   * two pixels per step, every FP32 operation packed across the pair (FADD2 / FMUL2 / FFMA2, sm_100): 34.5 packed
+//     operations per pixel instead of 69 scalar ones;
 //   * no u8 -> float conversion at all: a tap enters the arithmetic as the raw byte read as a SUBNORMAL float
 //     (b * 2^-149), and the sample coordinates carry a factor 2^100, so that every product weight * tap is the
-//     reference's product times 2^-49 exactly; the factor leaves the sums after the loop.
+//     reference's product times 2^-49 exactly; the factor leaves the sums after the loop;
+//   * software-pipelined by hand: a pair's coordinates, weights and tap loads ahead of the previous pair's sums.
 //
 // Per round a warp does, with warp-uniform control flow:
 //   refill   idle lanes take the next items from the global counter
-//   issue    lanes that start a level: bulk copy of T + tail load; lanes whose sample box left the window (or that
+//   issue    lanes that start a level: tail of the template record; lanes whose sample box left the window (or that
 //            start a level): window copy; one wait for everything
 //   pass     lane = slot: P*P pixels, samples + ordered sums            <- the hot loop
-//   slow     lanes whose samples may clamp at the border, whose box does not fit the window, or that hit
-//            the one rounding case the shared-weight sampling does not cover, redo the pass sample by
-//            sample (PatchMatch::GetPixelValue semantics, any coordinates), lanes = pixels then lanes = accumulators
+//   pixel-parallel pass
+//            lanes whose samples may clamp at the border, whose box does not fit the window, that hit the one
+//            rounding case the shared-weight sampling does not cover, and every live lane of a nearly empty warp:
+//            lanes = pixels (each sample with PatchMatch::GetPixelValue semantics where needed), then lanes =
+//            accumulators, two slots at a time
 //   solve    lane = slot: 4x4 LLT in Eigen's operation order, update, exits, next level / next item
 //
-// Bit-exactness of the window path is argued above the pass loop.
 #include <cstdlib>
 #include "pagk_device.cuh"
 #include "pagk_kernels.h"
@@ -777,7 +780,7 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
     //   sx - 1 is exact (same or finer binade), so that sample has floor(sx) - 1 and the weights of sx;
     //   X1 = fl(sx + 1) lies in [fx + 1, fx + 2]; X1 - (fx + 1) is exact (Sterbenz) and equals the reference's
     //   X1 - floor(X1) unless X1 == fx + 2, where it is exactly 1 -- flagged `bad`, the slot then redoes the
-    //   pass through the cooperative path, which evaluates every sample on its own.
+    //   pass through the pixel-parallel pass, which evaluates every sample on its own.
     // Horizontal interpolations are shared between samples only where the reference would evaluate the
     // identical expression.
     // Scaling.  The coordinate chain (pbx, the affine matrix, 1, 2^23) carries the factor SC = 2^100.  Every operation
