@@ -49,6 +49,8 @@
 #include "pagk_cv_fast.h"
 
 #include <cmath>
+#include <cstdlib>
+#include <cstdio>
 #include <cstdint>
 #include <cstring>
 #include <thread>
@@ -645,10 +647,16 @@ int patch_match_run(const pagk_patch_match_in &in, Work &w, int n_threads) {
     pm.pt2[i] = pm.gyro_init ? P2{in.pt_predict_un[2 * i], in.pt_predict_un[2 * i + 1]} : pm.pt1[i];
   }
   pm.success.assign(pm.N, 0); pm.pix_err.assign(pm.N, 0.0); pm.ncc.assign(pm.N, 0.f); pm.iters.assign(pm.N, 0);
-  for (int level = pm.pyramids - 1; level >= 0; --level)
+  // developer aid: PAGK_ORACLE_LEVEL_ITERS=<file> appends the running pass counts after every level ([level][N] int32 per pair)
+  const char *dump_path = std::getenv("PAGK_ORACLE_LEVEL_ITERS");
+  for (int level = pm.pyramids - 1; level >= 0; --level) {
     parallel_for(pm.N, n_threads, [&](int i0, int i1) {
       for (int i = i0; i < i1; ++i) one_pixel(pm, level, i);
     });
+    if (dump_path) {
+      if (FILE *f = std::fopen(dump_path, "ab")) { std::fwrite(pm.iters.data(), sizeof(int32_t), (size_t)pm.N, f); std::fclose(f); }
+    }
+  }
   // DistortPoints (:409-416) + SetMatcher (:370-388)
   const Cam c = make_cam(in.K, in.dist, in.n_dist, in.width, in.height);
   for (int i = 0; i < pm.N; ++i) {

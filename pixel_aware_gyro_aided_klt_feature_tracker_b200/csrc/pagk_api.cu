@@ -113,7 +113,7 @@ struct pagk_handle {
   PagkGeoModel *d_geo = nullptr;    // pagk_geometry_validation: models in, results out (allocated on first use)
   PagkGeoResult *d_geo_res = nullptr;
   unsigned char *d_ransac = nullptr;  // its estimators: per pair and model an index list and inlier flags, then the estimate flags
-  int *d_progress = nullptr;  // lanes kernel, level-granular work items: per feature, epoch * 8 + levels finished
+  int *d_progress = nullptr;  // lanes kernel, level-granular work items: per feature a 32-byte hand-over record (tag = epoch * 8 + levels finished)
   int lk_epoch = 0;           // launch number of the lanes kernel on this handle (values of earlier launches never match)
   int n_sms = 0;
   long long *d_dbg = nullptr;  // PAGK_LK_TIMELINE=<file>: clock64 timeline of CTA 0 of the LK kernel (developer aid)
@@ -328,7 +328,7 @@ int launch_lk_kernel(pagk_handle *h, const PagkOutPtrs &o, const PagkMode &m, in
     // PAGK_LK_TIMELINE=<file> with a -DPAGK_LANES_PROF build: per-warp phase cycles (developer aid)
     if (h->d_dbg) CU(cudaMemsetAsync(h->d_dbg, 0, 2048 * 16 * sizeof(long long), h->stream));
     if (++h->lk_epoch >= 0x0fffffff) {  // the epoch is about to repeat: forget every progress word written so far
-      CU(cudaMemsetAsync(h->d_progress, 0, (size_t)h->cfg.max_pairs * h->cfg.max_keys * sizeof(int), h->stream));
+      CU(cudaMemsetAsync(h->d_progress, 0, (size_t)h->cfg.max_pairs * h->cfg.max_keys * 8 * sizeof(int), h->stream));
       h->lk_epoch = 1;
     }
     const int rc = pagk_launch_lk_lanes(h->d_images, h->geom, h->d_pc, h->d_keys_un, o, m, h->cfg.max_keys, n_max, n_pairs,
@@ -435,8 +435,8 @@ int pagk_create(const pagk_config *cfg, pagk_handle **out) {
   ok(cudaMalloc(&h->d_out, h->out_bytes));
   ok(cudaMalloc(&h->d_work, 256));
   if (e == cudaSuccess) ok(cudaMemset(h->d_work, 0, 256));
-  ok(cudaMalloc(&h->d_progress, NK * sizeof(int)));
-  if (e == cudaSuccess) ok(cudaMemset(h->d_progress, 0, NK * sizeof(int)));
+  ok(cudaMalloc(&h->d_progress, NK * 8 * sizeof(int)));
+  if (e == cudaSuccess) ok(cudaMemset(h->d_progress, 0, NK * 8 * sizeof(int)));
   ok(cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, cfg->device));
   // function attributes belong to the device: set them for this handle's device (no process-wide "done" flag)
   ok((cudaError_t)pagk_configure_kernels());

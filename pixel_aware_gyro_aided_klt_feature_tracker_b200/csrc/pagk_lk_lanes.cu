@@ -63,7 +63,7 @@ namespace {
 // accumulators: about 5 k cycles per slot, two slots at a time) instead of a lockstep pass (20 k to 28 k cycles whatever
 // the number of live lanes).  Measured on config B: 2 beats 5, 8 and 12.
 #ifndef PAGK_LANES_SPARSE
-#define PAGK_LANES_SPARSE 2
+#define PAGK_LANES_SPARSE 3
 #endif
 // warps per SM for 11 x 11 patches, chosen per launch: twelve (three per scheduler, 170 registers per thread: the low-ILP
 // phases of one warp -- claim, window copies, solve -- are covered by the passes of two others) are 9 % faster per pair on
@@ -532,6 +532,27 @@ __global__ void __launch_bounds__(TmplCfg<HALF>::WARPS * 32) pagk_lk_template_ke
 // =================================================================================================
 // K3b: the alignment kernel
 // =================================================================================================
+// The hand-over of a feature from one level to the next (level-granular work items): a 32-byte record per feature of
+// three 8-byte words, each carrying the tag epoch * 8 + levels finished in its upper half:
+//   (tag, pm.x) (tag, pm.y) (tag, passes so far)
+// An aligned 8-byte access is single-copy atomic, so a reader that finds the expected tag in all three words has the
+// three values of that publication whatever order the words were written or read in: no acquire load in front of the
+// data, and the record is fetched together with everything else a claim needs (one global round trip).
+__device__ __forceinline__ void handover_store(unsigned long long *rec, int tag, float x, float y, int n) {
+  const unsigned long long t = (unsigned long long)(unsigned int)tag << 32;
+  const unsigned long long q0 = t | (unsigned long long)__float_as_uint(x), q1 = t | (unsigned long long)__float_as_uint(y);
+  const unsigned long long q2 = t | (unsigned long long)(unsigned int)n;
+  asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" ::"l"(rec), "l"(q0), "l"(q1) : "memory");
+  asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(rec + 2), "l"(q2) : "memory");
+}
+__device__ __forceinline__ void handover_load(const unsigned long long *rec, unsigned long long &q0, unsigned long long &q1, unsigned long long &q2) {
+  asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(q0), "=l"(q1) : "l"(rec) : "memory");
+  asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(q2) : "l"(rec + 2) : "memory");
+}
+__device__ __forceinline__ bool handover_valid(int tag, unsigned long long q0, unsigned long long q1, unsigned long long q2) {
+  return (unsigned int)(q0 >> 32) == (unsigned int)tag && (unsigned int)(q1 >> 32) == (unsigned int)tag && (unsigned int)(q2 >> 32) == (unsigned int)tag;
+}
+
 template <int HALF, bool AFFINE, int WSM>
 __global__ void __launch_bounds__(LanesCfg<HALF, WSM>::WARPS * 32, PAGK_LANES_REGCTAS && HALF <= 5 ? PAGK_LANES_REGCTAS : LanesCfg<HALF, WSM>::CTAS_SM)
 pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const PagkPairConst *__restrict__ pcs,
@@ -548,10 +569,11 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
   const unsigned char *mywin = wwin + lane * 4;                                            // byte 0 of this lane's window
   const int total_work = n_pairs * n_max;
   const int top = mode.levels - 1;
+  unsigned long long *handover = reinterpret_cast<unsigned long long *>(progress);
   // Work items.  split == 0: an item is a feature (all levels in one lane).  split != 0: an item is one LEVEL of a
   // feature, queued level-major (every feature's coarsest level first).  All a level hands to the next one is
-  // mvPtPyr2Un[i] (src/patch_match.cpp:348; dg, db, cost restart per level), so the hand-over is out.pm_un[o] and the
-  // running pass count out.iters[o] through global memory plus progress[o] = epoch_base + levels finished.  The tail of
+  // mvPtPyr2Un[i] (src/patch_match.cpp:348; dg, db, cost restart per level), so the hand-over is that point and the
+  // running pass count in the feature's tagged hand-over record (above; tag = epoch_base + levels finished).  The tail of
   // a launch -- lanes idling while the last items finish -- is then one level long instead of one feature life long.
   const int total_items = split ? total_work * mode.levels : total_work;
   const unsigned long long slot_bytes = g.slot_bytes;
@@ -626,12 +648,15 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
           const float2 p1 = keys_un[o];
           const float4 A = out.affine[o];
           float2 pp = p1;
-          int pv = 0;
+          unsigned long long q0 = 0ull, q1 = 0ull, q2 = 0ull;
           if (lv == top) {
             if (mode.gyro_init) pp = out.pt_predict_un[o];
           } else {
-            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(pv) : "l"(progress + o) : "memory");
+            handover_load(handover + 4 * o, q0, q1, q2);
           }
+          // the tail of the level's template record as well: its address depends on the item only
+          const unsigned char *rec = tmpl + (o * (size_t)mode.levels + (size_t)lv) * C::REC_BYTES;
+          const float4 tl = __ldg(reinterpret_cast<const float4 *>(rec + C::T_BULK));
           if (i < nk) {
             if (!st) {  // the reference skips these (src/patch_match.cpp:173): default outputs
               if (lv == top) {
@@ -640,16 +665,18 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
               }
             } else {
               const float scale = 1.0f / (float)(1 << lv);
-              feat = (int)o; pair = pr; level = lv; item_lo = lo; needs_setup = true; win_valid = false;
+              feat = (int)o; pair = pr; level = lv; item_lo = lo; needs_setup = false; win_valid = false;
+              Tg = reinterpret_cast<const float4 *>(rec);
+              tlast = tl.x; cval = tl.y;
+              h22v = __hiloint2double(__float_as_int(tl.w), __float_as_int(tl.z));
               pt1x = p1.x; pt1y = p1.y;
               ptx = p1.x * scale; pty = p1.y * scale;
               if (lv == top) {
                 dx = pp.x * scale - ptx; dy = pp.y * scale - pty;
                 n_iter = 0; waiting = false;
-              } else if (pv == epoch_base + (top - lv)) {  // the level above is already published (the usual case)
-                const float2 p2 = __ldcg(&out.pm_un[o]);
-                n_iter = __ldcg(&out.iters[o]);
-                dx = p2.x * 2.0f - ptx; dy = p2.y * 2.0f - pty;  // nextPt = mvPtPyr2Un[i] * 1.0f / mPyramidScale (:182)
+              } else if (handover_valid(epoch_base + (top - lv), q0, q1, q2)) {  // the level above is already published (the usual case)
+                n_iter = (int)(unsigned int)q2;
+                dx = __uint_as_float((unsigned int)q0) * 2.0f - ptx; dy = __uint_as_float((unsigned int)q1) * 2.0f - pty;  // nextPt = mvPtPyr2Un[i] * 1.0f / mPyramidScale (:182)
                 waiting = false;
               } else {
                 waiting = true;  // polled once per round below
@@ -683,12 +710,11 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
       // a claimed level starts once the level above it has published its result.  The owner of that level is a
       // running lane of this launch (items are claimed in queue order), so polling once per round cannot deadlock.
       if (waiting) {
-        int v;
-        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(progress + feat) : "memory");
-        if (v == epoch_base + (top - level)) {
-          const float2 p2 = __ldcg(&out.pm_un[feat]);
-          n_iter = __ldcg(&out.iters[feat]);
-          dx = p2.x * 2.0f - ptx; dy = p2.y * 2.0f - pty;  // nextPt = mvPtPyr2Un[i] * 1.0f / mPyramidScale (:182)
+        unsigned long long q0, q1, q2;
+        handover_load(handover + 4 * (size_t)feat, q0, q1, q2);
+        if (handover_valid(epoch_base + (top - level), q0, q1, q2)) {
+          n_iter = (int)(unsigned int)q2;
+          dx = __uint_as_float((unsigned int)q0) * 2.0f - ptx; dy = __uint_as_float((unsigned int)q1) * 2.0f - pty;  // nextPt = mvPtPyr2Un[i] * 1.0f / mPyramidScale (:182)
           waiting = false;
         }
       }
@@ -1159,11 +1185,7 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
           out.iters[o] = n_iter;
           feat = -1;
         } else if (level == item_lo) {  // split mode: publish this level's result, the lane is free
-          const size_t o = (size_t)feat;
-          __stcg(&out.pm_un[o], make_float2(p2x, p2y));
-          __stcg(&out.iters[o], n_iter);
-          // release at gpu scope: the two stores above are visible to whoever acquires this word
-          asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(progress + o), "r"(epoch_base + (top - level + 1)) : "memory");
+          handover_store(handover + 4 * (size_t)feat, epoch_base + (top - level + 1), p2x, p2y, n_iter);
           feat = -1;
         } else {
           --level;

@@ -7,12 +7,13 @@ import numpy as np
 from pixel_aware_gyro_aided_klt_feature_tracker_b200 import capi, synth, tracker
 if len(sys.argv) > 1:
     capi._lib = capi.load(sys.argv[1])
-cfg = {k: v for k, v in synth.CONFIGS["B"].items() if k != "pairs"}
-pairs = [synth.make_pair(2000 + i, **cfg) for i in range(64)]
-prm = capi.default_params(pyramids=4)
+CFG = os.environ.get("PROF_CONFIG", "B")  # PROF_CONFIG=A PROF_PAIRS=1: the sparse rounds of a single frame pair
+cfg = {k: v for k, v in synth.CONFIGS[CFG].items() if k != "pairs"}
 NP = int(os.environ.get("PROF_PAIRS", "64"))
+pairs = [synth.make_pair(2000 + i, **cfg) for i in range(min(NP, 64))]
+prm = capi.default_params(pyramids=cfg["pyramids"])
 pairs = (pairs * ((NP + 63) // 64))[:NP]
-with tracker.Context(max_keys=1024, max_pairs=NP, max_levels=4) as ctx:
+with tracker.Context(max_width=cfg["width"], max_height=cfg["height"], max_keys=cfg["n_keys"], max_pairs=NP, max_levels=cfg["pyramids"]) as ctx:
     ctx.upload(pairs, prm)
     for _ in range(3):
         ctx.run(); ctx.synchronize()
