@@ -1091,29 +1091,63 @@ __device__ __forceinline__ unsigned int pagk_remap_px(const unsigned char *__res
   return (unsigned int)min(max(v, 0), 255);
 }
 
-// four output pixels per thread when the row length allows it: 16-byte map loads, one 4-byte store
-__global__ void __launch_bounds__(256) pagk_remap_slots_kernel(const unsigned char *__restrict__ raw, unsigned char *__restrict__ images,
+// The maps are the same for every image of a batch, so a thread prepares its four output pixels once -- source offset,
+// 1/32-pixel fractions and which of the four taps lie inside the source -- and then walks REMAP_ZB images with them: per
+// image and pixel four byte loads, the 15-bit weighted sum and a shift (the map loads, the rounding and the border tests
+// are paid once per REMAP_ZB images; 16-byte map loads, one 4-byte store per image).
+#define REMAP_ZB 8
+struct PagkRemapTap { int off; unsigned int fxy; };  // fxy: fx | fy << 8 | inside mask (p00 p01 p10 p11) << 16
+__device__ __forceinline__ PagkRemapTap pagk_remap_prepare(int cols, int rows, float mx, float my) {
+  const int sx = __float2int_rn(mx * 32.0f), sy = __float2int_rn(my * 32.0f);
+  const int ix = min(max(sx >> 5, -32768), 32767), iy = min(max(sy >> 5, -32768), 32767), fx = sx & 31, fy = sy & 31;
+  const bool x0 = ix >= 0 && ix < cols, x1 = ix + 1 >= 0 && ix + 1 < cols, y0 = iy >= 0 && iy < rows, y1 = iy + 1 >= 0 && iy + 1 < rows;
+  PagkRemapTap t;
+  t.off = iy * cols + ix;
+  t.fxy = (unsigned int)fx | ((unsigned int)fy << 8) | ((unsigned int)(x0 && y0) << 16) | ((unsigned int)(x1 && y0) << 17) |
+          ((unsigned int)(x0 && y1) << 18) | ((unsigned int)(x1 && y1) << 19);
+  return t;
+}
+__device__ __forceinline__ unsigned int pagk_remap_apply(const unsigned char *__restrict__ src, int cols, const PagkRemapTap t) {
+  const int fx = (int)(t.fxy & 31u), fy = (int)((t.fxy >> 8) & 31u);
+  const unsigned char *p = src + t.off;
+  const int p00 = (t.fxy & (1u << 16)) ? __ldg(p) : 0, p01 = (t.fxy & (1u << 17)) ? __ldg(p + 1) : 0;
+  const int p10 = (t.fxy & (1u << 18)) ? __ldg(p + cols) : 0, p11 = (t.fxy & (1u << 19)) ? __ldg(p + cols + 1) : 0;
+  const int v = (p00 * ((32 - fy) * (32 - fx) * 32) + p01 * ((32 - fy) * fx * 32) + p10 * (fy * (32 - fx) * 32) + p11 * (fy * fx * 32) + (1 << 14)) >> 15;
+  return (unsigned int)min(max(v, 0), 255);
+}
+
+__global__ void __launch_bounds__(256, 4) pagk_remap_slots_kernel(const unsigned char *__restrict__ raw, unsigned char *__restrict__ images,
                                                              PagkGeom g, const float *__restrict__ map_x, const float *__restrict__ map_y,
-                                                             int z_stride, int z_offset) {
+                                                             int n_images, int z_stride, int z_offset) {
   const int cols = g.lv[0].cols, rows = g.lv[0].rows, pitch = g.lv[0].pitch;  // the raw images and the maps are dense
   const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
   if (y >= rows) return;
-  const unsigned char *src = raw + (size_t)blockIdx.z * cols * rows;
-  unsigned char *dst = images + (size_t)(blockIdx.z * z_stride + z_offset) * g.slot_bytes + g.lv[0].offset;
+  const int z0 = blockIdx.z * REMAP_ZB, z1 = min(z0 + REMAP_ZB, n_images);
+  const size_t img_bytes = (size_t)cols * rows;
   if ((cols & 3) == 0) {
     const int x = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4;
     if (x >= cols) return;
     const size_t o = (size_t)y * cols + x;
     const float4 mx = *reinterpret_cast<const float4 *>(map_x + o), my = *reinterpret_cast<const float4 *>(map_y + o);
-    const unsigned int v = pagk_remap_px(src, cols, rows, mx.x, my.x) | (pagk_remap_px(src, cols, rows, mx.y, my.y) << 8) |
-                           (pagk_remap_px(src, cols, rows, mx.z, my.z) << 16) | (pagk_remap_px(src, cols, rows, mx.w, my.w) << 24);
-    *reinterpret_cast<unsigned int *>(dst + (size_t)y * pitch + x) = v;
+    const PagkRemapTap t0 = pagk_remap_prepare(cols, rows, mx.x, my.x), t1 = pagk_remap_prepare(cols, rows, mx.y, my.y);
+    const PagkRemapTap t2 = pagk_remap_prepare(cols, rows, mx.z, my.z), t3 = pagk_remap_prepare(cols, rows, mx.w, my.w);
+#pragma unroll 1
+    for (int z = z0; z < z1; ++z) {
+      const unsigned char *src = raw + (size_t)z * img_bytes;
+      unsigned char *dst = images + (size_t)(z * z_stride + z_offset) * g.slot_bytes + g.lv[0].offset;
+      const unsigned int v = pagk_remap_apply(src, cols, t0) | (pagk_remap_apply(src, cols, t1) << 8) |
+                             (pagk_remap_apply(src, cols, t2) << 16) | (pagk_remap_apply(src, cols, t3) << 24);
+      *reinterpret_cast<unsigned int *>(dst + (size_t)y * pitch + x) = v;
+    }
   } else {
     for (int k = 0; k < 4; ++k) {
       const int x = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4 + k;
       if (x >= cols) return;
       const size_t o = (size_t)y * cols + x;
-      dst[(size_t)y * pitch + x] = (unsigned char)pagk_remap_px(src, cols, rows, map_x[o], map_y[o]);
+      const PagkRemapTap t = pagk_remap_prepare(cols, rows, map_x[o], map_y[o]);
+      for (int z = z0; z < z1; ++z)
+        images[(size_t)(z * z_stride + z_offset) * g.slot_bytes + g.lv[0].offset + (size_t)y * pitch + x] =
+            (unsigned char)pagk_remap_apply(raw + (size_t)z * img_bytes, cols, t);
     }
   }
 }
@@ -1501,8 +1535,8 @@ int pagk_launch_remap(const unsigned char *src, int cols, int rows, const float 
 int pagk_launch_remap_slots(const unsigned char *raw, unsigned char *images, const PagkGeom &g, const float *map_x, const float *map_y,
                             int n_images, int z_stride, int z_offset, cudaStream_t st, long long *launches) {
   if (n_images <= 0) return 0;
-  dim3 grid((g.lv[0].cols + 127) / 128, (g.lv[0].rows + 7) / 8, n_images);
-  pagk_remap_slots_kernel<<<grid, 256, 0, st>>>(raw, images, g, map_x, map_y, z_stride, z_offset);
+  dim3 grid((g.lv[0].cols + 127) / 128, (g.lv[0].rows + 7) / 8, (n_images + REMAP_ZB - 1) / REMAP_ZB);
+  pagk_remap_slots_kernel<<<grid, 256, 0, st>>>(raw, images, g, map_x, map_y, n_images, z_stride, z_offset);
   ++*launches;
   return (int)cudaGetLastError();
 }
