@@ -7,7 +7,7 @@
 //   K3  pagk_lk_kernel (generic, any patch size)
 //         PatchMatch::OpticalFlowMultiLevel + OpticalFlowConsideringIlluminationChange_onePixel
 //                                                  reference src/patch_match.cpp:79-142, 167-367
-//   K4  pagk_epilogue_kernel
+//   K4  pagk_epilogue1_kernel / pagk_epilogue_points, _mean, _filter_kernel
 //         DistortPoints / SetMatcher               reference src/patch_match.cpp:370-388, 409-416
 //         threshold filter                         reference src/gyro_aided_tracker.cpp:289-336
 //
@@ -494,80 +494,102 @@ __global__ void __launch_bounds__(128) pagk_ncc_kernel(const unsigned char *__re
 // error is a double sum in feature-index order (src/gyro_aided_tracker.cpp:294-305): thread 0 adds
 // chunk after chunk from shared memory so that the rounding sequence is the reference's.
 // =================================================================================================
-#define EPI_THREADS 256
-#define EPI_CHUNK 2048
-
-__global__ void __launch_bounds__(EPI_THREADS) pagk_epilogue_kernel(const PagkPairConst *__restrict__ pcs,
-                                                                  PagkOutPtrs out, PagkMode mode, int max_keys,
-                                                                  PagkPairResult *__restrict__ res, int do_filter) {
-  __shared__ double s_err[EPI_CHUNK];
-  __shared__ unsigned char s_ok[EPI_CHUNK];
-  __shared__ double s_th[2];
-  __shared__ int s_cnt;
-  __shared__ unsigned long long s_it;
-  const int pair = blockIdx.x, t = threadIdx.x;
+// Pairs with many features (BASELINE configs C and E: 8192 and 32768) as three launches, because one CTA per pair walking its
+// features in strides leaves the machine to a handful of CTAs (config E, four pairs: 0.65 ms): the two elementwise phases over a
+// grid of features, and between them the only serial part -- the mean pixel error, an ordered double sum per pair -- by
+// one thread that adds from shared memory while the other warps of its CTA fetch the next chunk.
+#define EPIW_THREADS 256
+__global__ void __launch_bounds__(EPIW_THREADS) pagk_epilogue_points_kernel(const PagkPairConst *__restrict__ pcs, PagkOutPtrs out, int max_keys) {
+  const int pair = blockIdx.y, i = blockIdx.x * EPIW_THREADS + threadIdx.x;
   const PagkPairConst &c = pcs[pair];
-  const int N = c.n_keys;
-  const size_t o0 = (size_t)pair * max_keys;
-  if (t == 0) { s_cnt = 0; s_it = 0ull; }
+  if (i >= c.n_keys) return;
+  const size_t o = (size_t)pair * max_keys + i;
   // distort + drift distance (src/patch_match.cpp:378-387, 409-416)
-  for (int i = t; i < N; i += EPI_THREADS) {
-    const float2 p = out.pm_un[o0 + i];
-    out.pm[o0 + i] = (c.k1 == 0.0f) ? p : pagk_distort(c, p);
-    const float2 base = out.pt_predict_un[o0 + i];  // still the gyro prediction here (mvPtPredictUn, :384)
-    const float ddx = base.x - p.x, ddy = base.y - p.y;
-    out.dist[o0 + i] = (double)sqrtf(ddx * ddx + ddy * ddy);
-  }
+  const float2 p = out.pm_un[o];
+  out.pm[o] = (c.k1 == 0.0f) ? p : pagk_distort(c, p);
+  const float2 base = out.pt_predict_un[o];  // still the gyro prediction here (mvPtPredictUn, :384)
+  const float ddx = base.x - p.x, ddy = base.y - p.y;
+  out.dist[o] = (double)sqrtf(ddx * ddx + ddy * ddy);
+}
+
+#define EPIS_THREADS 1024
+#define EPIS_CHUNK 2048
+__global__ void __launch_bounds__(EPIS_THREADS) pagk_epilogue_mean_kernel(const PagkPairConst *__restrict__ pcs, PagkOutPtrs out, int max_keys,
+                                                                      PagkPairResult *__restrict__ res) {
+  __shared__ double s_err[2][EPIS_CHUNK];
+  const int pair = blockIdx.x, t = threadIdx.x;
+  const int N = pcs[pair].n_keys;
+  const size_t o0 = (size_t)pair * max_keys;
+  // a feature that is not ok contributes +0.0, which leaves a sum >= +0 unchanged
+  auto fetch = [&](int c0, int b, int first, int stride) {
+    int n = 0;
+    for (int i = first; i < EPIS_CHUNK; i += stride) {
+      const bool ok = c0 + i < N && out.pm_status[o0 + c0 + i] != 0;
+      s_err[b][i] = ok ? out.pix_err[o0 + c0 + i] : 0.0;
+      n += ok ? 1 : 0;
+    }
+    return n;
+  };
+  int my_ok = fetch(0, 0, t, EPIS_THREADS);
   double sum = 0.0;
-  int cnt = 0;
-  for (int c0 = 0; c0 < N; c0 += EPI_CHUNK) {
-    __syncthreads();
-    for (int i = t; i < EPI_CHUNK && c0 + i < N; i += EPI_THREADS) {
-      s_err[i] = out.pix_err[o0 + c0 + i];
-      s_ok[i] = out.pm_status[o0 + c0 + i];
-    }
-    __syncthreads();
-    if (t == 0) {
-      // one thread, index order (the rounding sequence is the reference's).  Branch-free so that the loads run
-      // ahead of the dependent adds: a feature that is not ok contributes +0.0, which leaves a sum >= +0 unchanged
-      const int m = min(EPI_CHUNK, N - c0);
-#pragma unroll 8
-      for (int i = 0; i < m; ++i) {
-        const bool ok = s_ok[i] != 0;
-        sum += ok ? s_err[i] : 0.0;
-        cnt += ok ? 1 : 0;
-      }
+  for (int c0 = 0, b = 0; c0 < N; c0 += EPIS_CHUNK, b ^= 1) {
+    __syncthreads();  // chunk c0 is in buffer b; the other buffer has been summed
+    if (t >= 32) {    // warps 1..31 fetch the next chunk
+      if (c0 + EPIS_CHUNK < N) my_ok += fetch(c0 + EPIS_CHUNK, b ^ 1, t - 32, EPIS_THREADS - 32);
+    } else if (t == 0) {
+      // one thread, index order: the rounding sequence is the reference's (src/gyro_aided_tracker.cpp:294-305)
+      const int m = min(EPIS_CHUNK, N - c0);
+      const double *e = s_err[b];
+#pragma unroll 16
+      for (int i = 0; i < m; ++i) sum += e[i];
     }
   }
+  __shared__ int s_cnt;
+  if (t == 0) s_cnt = 0;
+  __syncthreads();
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) my_ok += __shfl_xor_sync(0xffffffffu, my_ok, d);
+  if ((t & 31) == 0) atomicAdd(&s_cnt, my_ok);
+  __syncthreads();
   if (t == 0) {
-    const double avg = sum / (double)cnt;  // cnt == 0 -> NaN -> threshold falls back to half (:305-308)
-    const double hp = (double)mode.half;
-    s_th[0] = (4.0 * avg > hp) ? 4.0 * avg : hp;
-    s_th[1] = hp * 4.0;
-    res[pair].avg_pixel_error = avg;
+    const int cnt = s_cnt;
+    res[pair].avg_pixel_error = sum / (double)cnt;  // cnt == 0 -> NaN -> threshold falls back to half (:305-308)
     res[pair].cnt_pm_ok = cnt;
+    res[pair].n_predict = 0;
+    res[pair].n_iterations = 0;  // the filter kernel adds to both
   }
-  __syncthreads();
-  const double thPix = s_th[0], thDist = s_th[1];
-  int my_cnt = 0;
-  unsigned long long my_it = 0;
-  for (int i = t; i < N; i += EPI_THREADS) {
-    my_it += (unsigned long long)out.iters[o0 + i];
-    if (!do_filter) continue;
-    const bool keep = out.pm_status[o0 + i] && out.pix_err[o0 + i] < thPix && out.dist[o0 + i] < thDist;
-    if (keep) {
-      out.pt_predict[o0 + i] = out.pm[o0 + i];
-      out.pt_predict_un[o0 + i] = out.pm_un[o0 + i];
-      out.status[o0 + i] = 1;
-      ++my_cnt;
-    } else {
-      out.status[o0 + i] = 0;
+}
+
+__global__ void __launch_bounds__(EPIW_THREADS) pagk_epilogue_filter_kernel(const PagkPairConst *__restrict__ pcs, PagkOutPtrs out, PagkMode mode,
+                                                                        int max_keys, PagkPairResult *__restrict__ res, int do_filter) {
+  const int pair = blockIdx.y, i = blockIdx.x * EPIW_THREADS + threadIdx.x;
+  const int N = pcs[pair].n_keys;
+  const size_t o = (size_t)pair * max_keys + i;
+  const double avg = res[pair].avg_pixel_error, hp = (double)mode.half;
+  const double thPix = (4.0 * avg > hp) ? 4.0 * avg : hp, thDist = hp * 4.0;
+  int kc = 0;
+  unsigned long long its = 0ull;
+  if (i < N) {
+    its = (unsigned long long)out.iters[o];
+    if (do_filter) {
+      const bool keep = out.pm_status[o] && out.pix_err[o] < thPix && out.dist[o] < thDist;
+      if (keep) {
+        out.pt_predict[o] = out.pm[o];
+        out.pt_predict_un[o] = out.pm_un[o];
+      }
+      out.status[o] = keep ? 1 : 0;
+      kc = keep ? 1 : 0;
     }
   }
-  atomicAdd(&s_cnt, my_cnt);
-  atomicAdd(&s_it, my_it);
-  __syncthreads();
-  if (t == 0) { res[pair].n_predict = s_cnt; res[pair].n_iterations = (long long)s_it; }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    kc += __shfl_xor_sync(0xffffffffu, kc, d);
+    its += __shfl_xor_sync(0xffffffffu, its, d);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (kc) atomicAdd(&res[pair].n_predict, kc);
+    if (its) atomicAdd(reinterpret_cast<unsigned long long *>(&res[pair].n_iterations), its);
+  }
 }
 
 // The same for pairs of at most EPI1_THREADS features (the usual case: BASELINE config B has 1024): one feature per
@@ -1459,9 +1481,16 @@ int pagk_launch_ncc(const unsigned char *images, const PagkGeom &g, const PagkPa
 int pagk_launch_epilogue(const PagkPairConst *pcs, const PagkOutPtrs &out, const PagkMode &mode, int max_keys, int n_max,
                          int n_pairs, PagkPairResult *res, int do_filter, cudaStream_t st, long long *launches) {
   if (n_pairs <= 0) return 0;
-  if (n_max <= EPI1_THREADS) pagk_epilogue1_kernel<<<n_pairs, EPI1_THREADS, 0, st>>>(pcs, out, mode, max_keys, res, do_filter);
-  else pagk_epilogue_kernel<<<n_pairs, EPI_THREADS, 0, st>>>(pcs, out, mode, max_keys, res, do_filter);
-  ++*launches;
+  if (n_max <= EPI1_THREADS) {
+    pagk_epilogue1_kernel<<<n_pairs, EPI1_THREADS, 0, st>>>(pcs, out, mode, max_keys, res, do_filter);
+    ++*launches;
+  } else {
+    const dim3 grid((n_max + EPIW_THREADS - 1) / EPIW_THREADS, n_pairs);
+    pagk_epilogue_points_kernel<<<grid, EPIW_THREADS, 0, st>>>(pcs, out, max_keys);
+    pagk_epilogue_mean_kernel<<<n_pairs, EPIS_THREADS, 0, st>>>(pcs, out, max_keys, res);
+    pagk_epilogue_filter_kernel<<<grid, EPIW_THREADS, 0, st>>>(pcs, out, mode, max_keys, res, do_filter);
+    *launches += 3;
+  }
   return (int)cudaGetLastError();
 }
 

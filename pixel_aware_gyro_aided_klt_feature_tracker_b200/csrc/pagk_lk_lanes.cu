@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(TmplCfg<HALF>::WARPS * 32) pagk_lk_template_ke
         ptx = p1.x * scale; pty = p1.y * scale;  // pt = mvKeysRefUn[i].pt * mvScales[level] (:177)
         cols = g.lv[lv].cols; rows = g.lv[lv].rows; pitch = g.lv[lv].pitch;
         img1 = images + (size_t)slot * g.slot_bytes + g.lv[lv].offset;
-        rec = tmpl + (o * (size_t)levels + lv) * C::REC_BYTES;
+        rec = tmpl + ((size_t)lv * ((size_t)n_pairs * max_keys) + o) * C::REC_BYTES;  // level-major: a level's records lie together
         const float txlo = ptx + (-hf), txhi = ptx + hf, tylo = pty + (-hf), tyhi = pty + hf;
         // no clamp of GetPixelValue fires anywhere in the template, and no tap lies in column `cols`: in a continuous
         // level that column is the next row's first byte, which a tile of the (x, y, slot) tensor does not see
@@ -570,6 +570,9 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
   const int total_work = n_pairs * n_max;
   const int top = mode.levels - 1;
   unsigned long long *handover = reinterpret_cast<unsigned long long *>(progress);
+  // template records are level-major ([level][pair * max_keys + feature]): the lanes work on one level at a time (the
+  // queue is level-major too), so the records in use lie together and stay in L2 between a level's passes
+  const size_t lv_stride = (size_t)n_pairs * (size_t)max_keys;
   // Work items.  split == 0: an item is a feature (all levels in one lane).  split != 0: an item is one LEVEL of a
   // feature, queued level-major (every feature's coarsest level first).  All a level hands to the next one is
   // mvPtPyr2Un[i] (src/patch_match.cpp:348; dg, db, cost restart per level), so the hand-over is that point and the
@@ -655,7 +658,7 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
             handover_load(handover + 4 * o, q0, q1, q2);
           }
           // the tail of the level's template record as well: its address depends on the item only
-          const unsigned char *rec = tmpl + (o * (size_t)mode.levels + (size_t)lv) * C::REC_BYTES;
+          const unsigned char *rec = tmpl + ((size_t)lv * lv_stride + o) * C::REC_BYTES;
           const float4 tl = __ldg(reinterpret_cast<const float4 *>(rec + C::T_BULK));
           if (i < nk) {
             if (!st) {  // the reference skips these (src/patch_match.cpp:173): default outputs
@@ -699,7 +702,7 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
     // (the pass streams T from it; c, h22 and the last T value come from the record's tail).  The template does not depend
     // on the level above, so a lane that still waits for its hand-over does this as well.
     if (feat >= 0 && needs_setup) {
-      const unsigned char *rec = tmpl + ((size_t)feat * (size_t)mode.levels + (size_t)level) * C::REC_BYTES;
+      const unsigned char *rec = tmpl + ((size_t)level * lv_stride + (size_t)feat) * C::REC_BYTES;
       Tg = reinterpret_cast<const float4 *>(rec);
       const float4 tl = __ldg(reinterpret_cast<const float4 *>(rec + C::T_BULK));
       tlast = tl.x; cval = tl.y;
