@@ -136,6 +136,15 @@ def test_batch_shapes_around_the_lane_cap(gpu_ctx, oracle, n_pairs, n_keys):
     _check(gpu_ctx, oracle, pairs, capi.default_params(pyramids=3), threads=8)
 
 
+def test_ragged_pairs_with_more_than_1024_features(gpu_ctx, oracle):
+    """pairs above 1024 features go through the three-launch epilogue (elementwise phases over a grid of features, the
+    ordered mean pixel error between them): counts that are no multiple of its block or chunk sizes, several chunks,
+    and a pair below the limit in the same batch"""
+    ns = [2500, 1025, 4100, 300]
+    pairs = [synth.make_pair(8300 + i, width=640, height=480, n_keys=n, pyramids=3, border=16) for i, n in enumerate(ns)]
+    _check(gpu_ctx, oracle, pairs, capi.default_params(pyramids=3), threads=8)
+
+
 @pytest.mark.parametrize("half", [3, 7])
 def test_patch_sizes_served_by_the_generic_kernel(gpu_ctx, oracle, half):
     """7 x 7 and 15 x 15 patches: no lane-kernel instantiation, the any-size kernel runs"""
