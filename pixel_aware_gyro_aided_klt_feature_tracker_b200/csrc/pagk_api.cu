@@ -82,6 +82,7 @@ struct pagk_handle {
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t slot_capacity = 0;
   unsigned char *d_images = nullptr;
+  unsigned char *d_in = nullptr;  // [constants][undistorted keypoints][raw keypoints], laid out like the pinned h_in
   float2 *d_keys_un = nullptr, *d_keys = nullptr;
   PagkPairConst *d_pc = nullptr;
   PagkPairResult *d_res = nullptr;
@@ -417,10 +418,12 @@ int pagk_create(const pagk_config *cfg, pagk_handle **out) {
   size_t off = 0;
   for (int k = 0; k < O_COUNT; ++k) { h->out_off[k] = off; off += align_up(NK * kOutElt[k], 256); }
   h->out_bytes = off;
-  h->h_in_keys_un = 0;
-  h->h_in_keys = align_up(NK * sizeof(float2), 256);
-  h->h_in_pc = h->h_in_keys + align_up(NK * sizeof(float2), 256);
-  h->h_in_bytes = h->h_in_pc + align_up((size_t)cfg->max_pairs * sizeof(PagkPairConst), 256);
+  // per-pair constants, undistorted keypoints, raw keypoints: one block on the host and the same block on the device, so that
+  // a batch's constants and keypoints go up in one copy (the raw keypoints, last, only in the mode that reads them)
+  h->h_in_pc = 0;
+  h->h_in_keys_un = align_up((size_t)cfg->max_pairs * sizeof(PagkPairConst), 256);
+  h->h_in_keys = h->h_in_keys_un + align_up(NK * sizeof(float2), 256);
+  h->h_in_bytes = h->h_in_keys + align_up(NK * sizeof(float2), 256);
   cudaError_t e = cudaSuccess;
   auto ok = [&](cudaError_t r) { if (e == cudaSuccess && r != cudaSuccess) e = r; return r == cudaSuccess; };
   ok(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -428,9 +431,12 @@ int pagk_create(const pagk_config *cfg, pagk_handle **out) {
   ok(cudaEventCreateWithFlags(&h->ev_aux, cudaEventDisableTiming));
   for (int i = 0; i < 6; ++i) ok(cudaEventCreate(&h->ev[i]));
   ok(cudaMalloc(&h->d_images, h->slot_capacity * 2 * (size_t)cfg->max_pairs));
-  ok(cudaMalloc(&h->d_keys_un, NK * sizeof(float2)));
-  ok(cudaMalloc(&h->d_keys, NK * sizeof(float2)));
-  ok(cudaMalloc(&h->d_pc, (size_t)cfg->max_pairs * sizeof(PagkPairConst)));
+  ok(cudaMalloc(&h->d_in, h->h_in_bytes));
+  if (e == cudaSuccess) {
+    h->d_pc = reinterpret_cast<PagkPairConst *>(h->d_in + h->h_in_pc);
+    h->d_keys_un = reinterpret_cast<float2 *>(h->d_in + h->h_in_keys_un);
+    h->d_keys = reinterpret_cast<float2 *>(h->d_in + h->h_in_keys);
+  }
   ok(cudaMalloc(&h->d_res, (size_t)cfg->max_pairs * sizeof(PagkPairResult)));
   ok(cudaMalloc(&h->d_out, h->out_bytes));
   ok(cudaMalloc(&h->d_work, 256));
@@ -471,7 +477,7 @@ void pagk_destroy(pagk_handle *h) {
   // a borrowed stream (pagk_share_stream) may already be gone with its owner: synchronise the device instead
   if (h->stream && h->own_stream) cudaStreamSynchronize(h->stream);
   else cudaDeviceSynchronize();
-  cudaFree(h->d_images); cudaFree(h->d_keys_un); cudaFree(h->d_keys); cudaFree(h->d_pc); cudaFree(h->d_res);
+  cudaFree(h->d_images); cudaFree(h->d_in); cudaFree(h->d_res);
   cudaFree(h->d_out); cudaFree(h->d_ntab); cudaFree(h->d_work); cudaFree(h->d_tmpl); cudaFree(h->d_progress); cudaFree(h->d_geo); cudaFree(h->d_geo_res); cudaFree(h->d_ransac); cudaFree(h->d_carry); cudaFree(h->d_mask); cudaFreeHost(h->h_aux); cudaFree(h->d_fast); cudaFree(h->d_fast_out); cudaFree(h->d_remap); cudaFree(h->d_maps); cudaFree(h->d_raw); cudaFree(h->d_dbg);
   cudaFreeHost(h->h_in); cudaFreeHost(h->h_out); cudaFreeHost(h->h_res);
   for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -538,9 +544,16 @@ int pagk_upload_batch(pagk_handle *h, const pagk_params *prm, int n_pairs, const
   }
   std::memcpy(h->h_in + h->h_in_pc, h->pcs.data(), (size_t)n_pairs * sizeof(PagkPairConst));
   const size_t key_bytes = (size_t)n_pairs * h->cfg.max_keys * sizeof(float2);
-  CU(cudaMemcpyAsync(h->d_keys_un, s_un, key_bytes, cudaMemcpyHostToDevice, h->stream));
+  // constants and undistorted keypoints in one copy (the gap between them is the constants of the pairs not in this batch:
+  // at most 256 bytes per unused pair)
+  const size_t pc_bytes = (size_t)n_pairs * sizeof(PagkPairConst);
+  if (h->h_in_keys_un - pc_bytes <= 65536) {
+    CU(cudaMemcpyAsync(h->d_in, h->h_in, h->h_in_keys_un + key_bytes, cudaMemcpyHostToDevice, h->stream));
+  } else {  // a handle sized for far more pairs than this batch has
+    CU(cudaMemcpyAsync(h->d_pc, h->h_in + h->h_in_pc, pc_bytes, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_keys_un, s_un, key_bytes, cudaMemcpyHostToDevice, h->stream));
+  }
   if (!m.gyro_init) CU(cudaMemcpyAsync(h->d_keys, s_k, key_bytes, cudaMemcpyHostToDevice, h->stream));
-  CU(cudaMemcpyAsync(h->d_pc, h->h_in + h->h_in_pc, (size_t)n_pairs * sizeof(PagkPairConst), cudaMemcpyHostToDevice, h->stream));
   if (any_table) {
     const size_t per = (size_t)W * H * 2;
     if (!h->d_ntab || h->ntab_stride < per) {
@@ -582,16 +595,23 @@ int pagk_run_resident(pagk_handle *h) {
     // K2 (prediction) and K1 (pyramids) are independent: K2 runs on the handle's second stream beside K1 and joins
     // before K3.  Stage clocks: ev[0]..ev[1] = the pyramid build with the prediction beside it, ev[1]..ev[2] = what
     // is left of the prediction after the pyramids are done.
-    CU(cudaStreamWaitEvent(h->aux, h->ev[0], 0));
-    CU((cudaError_t)pagk_launch_predict(h->d_pc, h->d_keys_un, h->d_keys, o, h->mode, h->cfg.max_keys, h->n_max, h->n_pairs,
-                                        h->geom.width, h->geom.height, h->d_ntab, h->ntab_stride, h->aux, &h->launches));
-    CU(cudaEventRecord(h->ev_aux, h->aux));
+    // (a small batch is bound by the host's launch rate, not by the device: there the fork and the join -- four runtime calls
+    // for three microseconds of kernel -- cost more than they hide, and K2 simply follows K1 on the handle's stream)
+    const bool beside = (long long)h->n_pairs * h->n_max >= 16384;
+    if (beside) {
+      CU(cudaStreamWaitEvent(h->aux, h->ev[0], 0));
+      CU((cudaError_t)pagk_launch_predict(h->d_pc, h->d_keys_un, h->d_keys, o, h->mode, h->cfg.max_keys, h->n_max, h->n_pairs,
+                                          h->geom.width, h->geom.height, h->d_ntab, h->ntab_stride, h->aux, &h->launches));
+      CU(cudaEventRecord(h->ev_aux, h->aux));
+    }
     // a stream continuation already has the reference pyramids (copied from the previous current ones at upload)
     if (h->cont) CU((cudaError_t)pagk_launch_pyramids(h->d_images + h->geom.slot_bytes, h->geom, h->n_pairs, 2, st, &h->launches));
     else CU((cudaError_t)pagk_launch_pyramids(h->d_images, h->geom, 2 * h->n_pairs, 1, st, &h->launches));
     h->cur_pairs = h->n_pairs;
     if (stages) CU(cudaEventRecord(h->ev[1], st));
-    CU(cudaStreamWaitEvent(st, h->ev_aux, 0));
+    if (beside) CU(cudaStreamWaitEvent(st, h->ev_aux, 0));
+    else CU((cudaError_t)pagk_launch_predict(h->d_pc, h->d_keys_un, h->d_keys, o, h->mode, h->cfg.max_keys, h->n_max, h->n_pairs,
+                                             h->geom.width, h->geom.height, h->d_ntab, h->ntab_stride, st, &h->launches));
   } else {
     if (stages) CU(cudaEventRecord(h->ev[1], st));
     CU((cudaError_t)pagk_launch_predict(h->d_pc, h->d_keys_un, h->d_keys, o, h->mode, h->cfg.max_keys, h->n_max, h->n_pairs,
@@ -709,6 +729,25 @@ int download_enqueue(pagk_handle *h, int n_pairs, pagk_pair_out *out) {
   h->pending_staged.assign(kNumWants, 0);
   if (n_pairs == 0) return PAGK_OK;
   CU(cudaSetDevice(h->cfg.device));
+  // A small batch is bound by the number of runtime calls, not by bytes: when the requested vectors span at most 1 MB of the
+  // result block they come down in ONE copy into the pinned mirror and are scattered from there.
+  {
+    size_t lo = (size_t)-1, hi = 0;
+    for (int w = 0; w < kNumWants; ++w) {
+      bool any = false;
+      for (int p = 0; p < n_pairs && !any; ++p) any = out_field(out, p, kWants[w].field_off) != nullptr;
+      if (!any) continue;
+      const size_t a = h->out_off[kWants[w].k], b = a + (size_t)n_pairs * h->cfg.max_keys * kOutElt[kWants[w].k];
+      lo = a < lo ? a : lo; hi = b > hi ? b : hi;
+      h->pending_staged[w] = 1;
+    }
+    if (hi > lo && hi - lo <= (size_t)1 << 20) {
+      CU(cudaMemcpyAsync(h->h_out + lo, h->d_out + lo, hi - lo, cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaMemcpyAsync(h->h_res, h->d_res, (size_t)n_pairs * sizeof(PagkPairResult), cudaMemcpyDeviceToHost, h->stream));
+      return PAGK_OK;
+    }
+    h->pending_staged.assign(kNumWants, 0);
+  }
   for (int w = 0; w < kNumWants; ++w) {
     const size_t elt = kOutElt[kWants[w].k];
     bool any = false, direct = true;
