@@ -608,8 +608,12 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
   const int selA = (int)((0x431044333110ull >> (4 * role)) & 0xfull);  // 0 Ix, 1 Iy, 3 c, 4 one
   const int selB = (int)((0x222210310100ull >> (4 * role)) & 0xfull);  // 0 Ix, 1 Iy, 2 -e, 3 c
   // offsets and strides in doubles: a record is four doubles wide
-  const int offA = selA < 3 ? selA : C::COOP_CONST / 2 + (selA - 3), strideA = selA < 3 ? 4 : 0;
-  const int offB = selB < 3 ? selB : C::COOP_CONST / 2 + (selB - 3), strideB = selB < 3 ? 4 : 0;
+  const int offA = selA < 3 ? selA : C::COOP_CONST / 2 + (selA - 3);
+  const int offB = selB < 3 ? selB : C::COOP_CONST / 2 + (selB - 3);
+  // (opaque to the compiler: as plain registers the strides cost one add per operand in the serial walk; known to be 0 or 4
+  // they become a predicated pair of instructions per operand -- 3.5 % of a single pair's patch alignment)
+  int strideA = selA < 3 ? 4 : 0, strideB = selB < 3 ? 4 : 0;
+  asm("" : "+r"(strideA), "+r"(strideB));
 
   // ---- slot state (registers of the owning lane) ----
   int feat = -1, pair = 0, level = 0, iter = 0, n_iter = 0, succ = 1;
