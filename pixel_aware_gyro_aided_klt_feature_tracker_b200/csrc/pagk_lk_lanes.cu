@@ -1052,8 +1052,15 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
               const int p = p0 + lane + 32 * k;
               tv[k] = p < NP - 1 ? __ldg(Tp[b] + p) : stl[b];
             }
-#pragma unroll 2
-            for (int k = 0; k < CH / 32; ++k) {
+            // (two pixels per trip; the template value of pixel k picked from registers: indexing tv[] with the trip
+            // counter would put it on the stack, and the store would wait for the loads before the first pixel starts)
+            static_assert(CH / 32 == 2 || CH / 32 == 4, "template values of a chunk: two or four per lane");
+#pragma unroll 1
+            for (int kk = 0; kk < CH / 32; kk += 2)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const int k = kk + j;
+              const float tvk = (CH / 32 == 4 && kk != 0) ? tv[2 + j] : tv[j];
               const int q = lane + 32 * k, p = p0 + q;
               if (p >= NP) continue;
               const int py = p / P, px = p - py * P;
@@ -1103,7 +1110,7 @@ pagk_lk_lanes_kernel(const unsigned char *__restrict__ images, PagkGeom g, const
                   vy2 = pagk_sample_call(img2[b], sp[b], scols[b], srows[b], sx, sy - 1.0f);
                 }
               }
-              const float e = (v0 + sdb[b]) - sgain[b] * tv[k], me = -e;
+              const float e = (v0 + sdb[b]) - sgain[b] * tvk, me = -e;
               double2 *rec = reinterpret_cast<double2 *>(buf + 8 * q);
               rec[0] = make_double2((double)(0.5f * (vx1 - vx2)), (double)(0.5f * (vy1 - vy2)));
               rec[1] = make_double2((double)me, __hiloint2double(0, __float_as_int(me * me)));
