@@ -443,6 +443,8 @@ int pagk_create(const pagk_config *cfg, pagk_handle **out) {
   if (e == cudaSuccess) ok(cudaMemset(h->d_work, 0, 256));
   ok(cudaMalloc(&h->d_progress, NK * 8 * sizeof(int)));
   if (e == cudaSuccess) ok(cudaMemset(h->d_progress, 0, NK * 8 * sizeof(int)));
+  // test hook: start the launch counter of the lanes kernel near its wrap (the hand-over tags are epoch * 8 + levels finished)
+  if (const char *ep = getenv("PAGK_DEBUG_LK_EPOCH")) h->lk_epoch = atoi(ep);
   ok(cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, cfg->device));
   // function attributes belong to the device: set them for this handle's device (no process-wide "done" flag)
   ok((cudaError_t)pagk_configure_kernels());

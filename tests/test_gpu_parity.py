@@ -360,6 +360,35 @@ def test_level_granular_work_items_forced_on_small_batches():
     assert " passed" in r.stdout and "failed" not in r.stdout
 
 
+def test_hand_over_tags_across_the_wrap_of_the_launch_counter():
+    """the hand-over records of the lanes kernel are tagged launch number * 8 + levels finished; when the launch number is
+    about to repeat (2^28 launches) the records are cleared and it restarts at 1.  A child process starts the counter 20
+    launches below the wrap (PAGK_DEBUG_LK_EPOCH) with level-granular items forced and reruns one batch 48 times: every run
+    bit-identical to the oracle."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import numpy as np\n"
+        "from pixel_aware_gyro_aided_klt_feature_tracker_b200 import capi, synth, tracker\n"
+        "from oracle import oracle\n"
+        "from tests import helpers\n"
+        "pairs = [synth.make_pair(8700 + i, width=320, height=240, n_keys=300, pyramids=3, border=16) for i in range(3)]\n"
+        "prm = capi.default_params(pyramids=3)\n"
+        "rc, cpu = oracle.track_batch(pairs, prm, 4)\n"
+        "assert rc == 0\n"
+        "with tracker.Context(max_width=320, max_height=240, max_keys=300, max_pairs=3, max_levels=3) as ctx:\n"
+        "    for it in range(48):\n"
+        "        gpu = ctx.track_batch(pairs, prm)\n"
+        "        for g, c in zip(gpu, cpu):\n"
+        "            helpers.assert_bit_exact(g, c)\n"
+        "print('wrap ok')\n")
+    env = dict(os.environ, PAGK_LK_SPLIT="1", PAGK_DEBUG_LK_EPOCH=str(0x0fffffff - 20))
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0 and "wrap ok" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
 def test_stage_timing_off_changes_only_the_clocks(gpu_ctx):
     """pagk_set_stage_timing(h, 0): no CUDA event between the kernels of a run; results identical, the whole device time is
     booked on the patch alignment"""
