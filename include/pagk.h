@@ -196,6 +196,12 @@ int pagk_synchronize(pagk_handle *h);
  * a throughput pipeline over several handles runs about 3 % faster without them -- and books the whole device time of
  * the batch on the patch alignment (t_opt_flow); the other two read 0. */
 int pagk_set_stage_timing(pagk_handle *h, int on);
+/* Throughput pipelines over several handles on one device (one handle per stream, all kept busy): n_handles > 1 makes a
+ * launch of the patch-alignment kernel take 1/n_handles of every SM's CTA slots, so that the launches of the other handles
+ * run beside it instead of behind it -- two batches interleaved on an SM halve the share of a launch's tail (config B over
+ * three rotating handles: 5 % more features/s).  It is the caller's statement about its own pipeline: a launch that turns
+ * out to be alone on the device runs on 1/n_handles of it.  Default 1 (a launch fills the device); results do not depend on it. */
+int pagk_set_device_share(pagk_handle *h, int n_handles);
 /* device time of the last pagk_run_resident, milliseconds (CUDA events on the handle's stream) */
 int pagk_last_run_ms(pagk_handle *h, float *total_ms, float *pyramid_ms, float *predict_ms,
                      float *lk_ms, float *filter_ms);

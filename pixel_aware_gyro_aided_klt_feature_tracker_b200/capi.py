@@ -182,6 +182,7 @@ SYMBOLS = {
     "pagk_synchronize": (C.c_int, [_H]),
     "pagk_last_run_ms": (C.c_int, [_H] + [_f32p] * 5),
     "pagk_set_stage_timing": (C.c_int, [_H, C.c_int]),
+    "pagk_set_device_share": (C.c_int, [_H, C.c_int]),
     "pagk_stream": (C.c_void_p, [_H]),
     "pagk_share_stream": (C.c_int, [_H, _H]),
     "pagk_timing_reset": (C.c_int, [_H]),

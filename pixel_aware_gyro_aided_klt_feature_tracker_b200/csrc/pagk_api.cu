@@ -75,6 +75,7 @@ struct pagk_handle {
   int cur_pairs = 0;           // pairs whose CURRENT-image slot holds a finished pyramid (of geometry `geom`) from the last run
   bool cont = false;           // the uploaded batch continues streams: its reference images are the previous current ones
   int stage_timing = 1;        // CUDA events between the kernels of a run (pagk_set_stage_timing)
+  int device_share = 1;        // handles that keep launches in flight on this device (pagk_set_device_share)
   cudaStream_t aux = nullptr;  // the gyro prediction runs here, beside the pyramid build (independent kernels)
   cudaEvent_t ev_aux = nullptr;
   std::vector<cudaEvent_t> tev;  // start/end event pairs around the LK kernel, pagk_timing_*
@@ -334,7 +335,7 @@ int launch_lk_kernel(pagk_handle *h, const PagkOutPtrs &o, const PagkMode &m, in
     }
     const int rc = pagk_launch_lk_lanes(h->d_images, h->geom, h->d_pc, h->d_keys_un, o, m, h->cfg.max_keys, n_max, n_pairs,
                                         h->d_work + 16, h->lk_parity, h->d_progress, h->lk_epoch, h->n_sms, h->d_tmpl, &h->tmaps,
-                                        h->stream, &h->launches, h->d_dbg);
+                                        h->stream, &h->launches, h->d_dbg, h->device_share);
     if (rc == 0 && n_max > 0 && n_pairs > 0) h->lk_parity ^= 1;
     if (h->d_dbg && rc == 0) {
       std::vector<long long> tl(2048 * 16);
@@ -644,6 +645,13 @@ int pagk_run_resident(pagk_handle *h) {
 int pagk_set_stage_timing(pagk_handle *h, int on) {
   if (!h) return fail(PAGK_ERR_INVALID, "null handle");
   h->stage_timing = on ? 1 : 0;
+  return PAGK_OK;
+}
+
+int pagk_set_device_share(pagk_handle *h, int n_handles) {
+  if (!h) return fail(PAGK_ERR_INVALID, "null handle");
+  if (n_handles < 1 || n_handles > 8) return fail(PAGK_ERR_INVALID, "pagk_set_device_share: 1 <= n_handles <= 8");
+  h->device_share = n_handles;
   return PAGK_OK;
 }
 

@@ -67,4 +67,4 @@ void pagk_lk_lanes_tma_box(int half, int *box_w, int *box_h);
 int pagk_launch_lk_lanes(const unsigned char *images, const PagkGeom &g, const PagkPairConst *pcs, const float2 *keys_un,
                          const PagkOutPtrs &out, const PagkMode &mode, int max_keys, int n_max, int n_pairs,
                          int *work_counters, int parity, int *progress, int epoch, int n_sms, unsigned char *tmpl,
-                         const PagkTmaLevels *tmaps, cudaStream_t st, long long *launches, long long *prof);
+                         const PagkTmaLevels *tmaps, cudaStream_t st, long long *launches, long long *prof, int share);

@@ -1265,10 +1265,19 @@ template <int HALF, bool AFFINE, int WSM>
 static int launch_lanes_w(const unsigned char *images, const PagkGeom &g, const PagkPairConst *pcs, const float2 *keys_un,
                           const PagkOutPtrs &out, const PagkMode &mode, int max_keys, int n_max, int n_pairs,
                           int *work_counter, int *next_counter, int *progress, int epoch, int n_sms, unsigned char *tmpl,
-                          cudaStream_t st, long long *prof) {
+                          cudaStream_t st, long long *prof, int share) {
   using C = LanesCfg<HALF, WSM>;
   const long long total = (long long)n_max * n_pairs;
   long long ctas = (long long)n_sms * C::CTAS_SM;  // persistent: the SMs are filled once
+  // pagk_set_device_share(h, n): the caller keeps the launches of n handles in flight on this device, so this one takes
+  // 1/n of an SM's CTA slots and the other handles' launches run BESIDE it instead of behind it.  Two batches interleaved on
+  // every SM are twice the independent work per lane: the tail of a launch (lanes idling while the last long items finish,
+  // 20 % of a launch that has the device to itself at 64 pairs) is half as large a share, and it lies under the body of
+  // the neighbour.  Config B over three rotating handles: 0.678 -> 0.645 ms per step.  (A launch that turns out to be alone
+  // runs on 1/n of the device: the setting is the caller's statement about its own pipeline, not a heuristic.)
+  // (only where the CTA slots divide evenly: the 12-warp shape of large batches has three, and a batch that large has the
+  // independent work to fill the device by itself)
+  if (share > 1 && total >= 16384 && C::CTAS_SM % share == 0) ctas = (long long)n_sms * (C::CTAS_SM / share);
   // A small batch is spread over all warps (lane_cap features per warp at a time) instead of filling a few: a warp
   // with a handful of live lanes runs them through the pixel-parallel pass, several times faster per iteration
   // than a lockstep pass, which is what the latency of a single frame pair is made of.
@@ -1291,7 +1300,7 @@ template <int HALF, bool AFFINE>
 static int launch_lanes(const unsigned char *images, const PagkGeom &g, const PagkPairConst *pcs, const float2 *keys_un,
                         const PagkOutPtrs &out, const PagkMode &mode, int max_keys, int n_max, int n_pairs,
                         int *work_counter, int *next_counter, int *progress, int epoch, int n_sms, unsigned char *tmpl,
-                        const PagkTmaLevels *tmaps, cudaStream_t st, long long *prof) {
+                        const PagkTmaLevels *tmaps, cudaStream_t st, long long *prof, int share) {
   const long long total = (long long)n_max * n_pairs;
   {  // K3a: 32 items per warp
     constexpr int W = TmplCfg<HALF>::WARPS;
@@ -1307,28 +1316,28 @@ static int launch_lanes(const unsigned char *images, const PagkGeom &g, const Pa
     const bool big = forced_w ? forced_w >= PAGK_LANES_WARPS5_BIG : total >= PAGK_LANES_BIG_FEATURES;
     if (big)
       return launch_lanes_w<HALF, AFFINE, PAGK_LANES_WARPS5_BIG>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter,
-                                                                  next_counter, progress, epoch, n_sms, tmpl, st, prof);
+                                                                  next_counter, progress, epoch, n_sms, tmpl, st, prof, share);
     return launch_lanes_w<HALF, AFFINE, PAGK_LANES_WARPS5>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter,
-                                                            next_counter, progress, epoch, n_sms, tmpl, st, prof);
+                                                            next_counter, progress, epoch, n_sms, tmpl, st, prof, share);
   } else
     return launch_lanes_w<HALF, AFFINE, 7>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, next_counter, progress, epoch,
-                                         n_sms, tmpl, st, prof);
+                                         n_sms, tmpl, st, prof, share);
 }
 
 int pagk_launch_lk_lanes(const unsigned char *images, const PagkGeom &g, const PagkPairConst *pcs, const float2 *keys_un,
                          const PagkOutPtrs &out, const PagkMode &mode, int max_keys, int n_max, int n_pairs,
                          int *work_counters, int parity, int *progress, int epoch, int n_sms, unsigned char *tmpl,
-                         const PagkTmaLevels *tmaps, cudaStream_t st, long long *launches, long long *prof) {
+                         const PagkTmaLevels *tmaps, cudaStream_t st, long long *launches, long long *prof, int share) {
   if (n_max <= 0 || n_pairs <= 0) return 0;
   // work_counters[0..1]: both zero when the handle is created; launch n uses [n & 1] and zeroes the other one
   int *work_counter = work_counters + (parity & 1), *next_counter = work_counters + ((parity + 1) & 1);
   int rc;
   if (mode.half == 5) {
-    rc = mode.affine ? launch_lanes<5, true>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, next_counter, progress, epoch, n_sms, tmpl, tmaps, st, prof)
-                     : launch_lanes<5, false>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, next_counter, progress, epoch, n_sms, tmpl, tmaps, st, prof);
+    rc = mode.affine ? launch_lanes<5, true>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, next_counter, progress, epoch, n_sms, tmpl, tmaps, st, prof, share)
+                     : launch_lanes<5, false>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, next_counter, progress, epoch, n_sms, tmpl, tmaps, st, prof, share);
   } else {
-    rc = mode.affine ? launch_lanes<10, true>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, next_counter, progress, epoch, n_sms, tmpl, tmaps, st, prof)
-                     : launch_lanes<10, false>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, next_counter, progress, epoch, n_sms, tmpl, tmaps, st, prof);
+    rc = mode.affine ? launch_lanes<10, true>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, next_counter, progress, epoch, n_sms, tmpl, tmaps, st, prof, share)
+                     : launch_lanes<10, false>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter, next_counter, progress, epoch, n_sms, tmpl, tmaps, st, prof, share);
   }
   *launches += 2;
   return rc;

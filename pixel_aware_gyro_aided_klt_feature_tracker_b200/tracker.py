@@ -191,6 +191,11 @@ class Context:
         """CUDA events between the kernels of a run (per-stage clocks); off for throughput pipelines"""
         _check(self.lib, self.lib.pagk_set_stage_timing(self.handle, 1 if on else 0))
 
+    def set_device_share(self, n_handles: int):
+        """this handle is one of n_handles that keep launches in flight on the device: a launch of the patch-alignment kernel
+        takes 1/n_handles of every SM's CTA slots and the other handles' launches run beside it (pagk_set_device_share)"""
+        _check(self.lib, self.lib.pagk_set_device_share(self.handle, int(n_handles)))
+
     def share_stream(self, other: "Context"):
         _check(self.lib, self.lib.pagk_share_stream(self.handle, other.handle))
 

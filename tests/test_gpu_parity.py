@@ -360,6 +360,36 @@ def test_level_granular_work_items_forced_on_small_batches():
     assert " passed" in r.stdout and "failed" not in r.stdout
 
 
+@pytest.mark.parametrize("share", [2, 3])
+def test_device_share_changes_only_the_launch_shape(cuda_lib, oracle, share):
+    """pagk_set_device_share(h, n): a launch of the alignment kernel takes 1/n of every SM's CTA slots (the other handles of
+    a pipeline run beside it); the results are the same bit for bit, also with two handles in flight at once"""
+    from pixel_aware_gyro_aided_klt_feature_tracker_b200 import tracker
+    pairs = [synth.make_pair(8800 + i, width=320, height=240, n_keys=1024, pyramids=3, border=16) for i in range(17)]  # 17 408 features
+    prm = capi.default_params(pyramids=3)
+    rc, cpu = oracle.track_batch(pairs, prm, 8)
+    assert rc == 0
+    mk = lambda: tracker.Context(max_width=320, max_height=240, max_keys=1024, max_pairs=17, max_levels=3)
+    with mk() as a, mk() as b:
+        for c in (a, b):
+            c.set_device_share(share)
+            c.upload(pairs, prm)
+        for _ in range(3):
+            a.run(); b.run()
+        outs = []
+        for c in (a, b):
+            c.synchronize()
+            o = [capi.PairOutputs(p.n_keys) for p in pairs]
+            c.download(o)
+            outs.append(o)
+    for o in outs:
+        for g, c in zip(o, cpu):
+            helpers.assert_bit_exact(g, c)
+    with mk() as c:
+        with pytest.raises(Exception):
+            c.set_device_share(0)
+
+
 def test_hand_over_tags_across_the_wrap_of_the_launch_counter():
     """the hand-over records of the lanes kernel are tagged launch number * 8 + levels finished; when the launch number is
     about to repeat (2^28 launches) the records are cleared and it restarts at 1.  A child process starts the counter 20
