@@ -42,8 +42,11 @@ def profiled_traffic(cfg_name, n_pairs):
         return (e["bytes_per_launch"], "profiles/r02_k3_traffic.json: " + e["note"]) if e else (None, None)
     except Exception:
         return None, None
-DEVICE_SHARE = int(os.environ.get("PAGK_BENCH_SHARE", "2"))  # pagk_set_device_share of the handles of a pipelined leg
-N_ROTATE = int(os.environ.get("PAGK_BENCH_ROTATE", "3"))  # resident batches per GPU; 3 x 61 MB of pyramids > 126 MB L2
+DEVICE_SHARE = int(os.environ.get("PAGK_BENCH_SHARE", "3"))  # pagk_set_device_share of the handles of the resident pipelined leg
+# ... and of the end-to-end legs, whose handles wait for their downloads: fewer launches are in flight at once (measured:
+# 98-101 M features/s over camera streams with 2, 95.5 M with 3)
+E2E_SHARE = int(os.environ.get("PAGK_BENCH_E2E_SHARE", "2"))
+N_ROTATE = int(os.environ.get("PAGK_BENCH_ROTATE", "4"))  # resident batches per GPU; 4 x 61 MB of pyramids > 126 MB L2
 E2E_DEPTH = 5  # handles (streams) the end-to-end leg rotates over: uploads, kernels and downloads of 5 batches in flight
 
 
@@ -253,7 +256,7 @@ def stream_leg(args, cfg, prm, n_streams, new_ctx, barrier, world):
     oarrs = [capi.make_out_array(ob.outs) for ob in oblocks]
     for c in ctxs:
         c.set_stage_timing(False)
-        c.set_device_share(DEVICE_SHARE)
+        c.set_device_share(E2E_SHARE)
     keep = [batch(0, False)] + [batch(t, True) for t in range(1, T - 1)]
     ins = [capi.make_in_array(b) for b in keep]
     pos = [0] * E2E_DEPTH                                        # next frame pair of each handle's streams
@@ -350,7 +353,7 @@ def run_threads(args):
         ectx = [mk() for _ in range(E2E_DEPTH)]
         for c in ectx:
             c.set_stage_timing(False)
-            c.set_device_share(DEVICE_SHARE)
+            c.set_device_share(E2E_SHARE)
         oblocks = [OutBlock(n_pairs, N) for _ in range(E2E_DEPTH)]
         ins = [capi.make_in_array(batches[j % N_ROTATE]["pairs"]) for j in range(E2E_DEPTH)]
         oarrs = [capi.make_out_array(ob.outs) for ob in oblocks]
@@ -539,7 +542,7 @@ def main():
     ectx = [new_ctx() for _ in range(E2E_DEPTH)]
     for c in ectx:
         c.set_stage_timing(False)   # a throughput pipeline does not read per-stage clocks (no event between kernels)
-        c.set_device_share(DEVICE_SHARE)
+        c.set_device_share(E2E_SHARE)
     oblocks = [OutBlock(n_pairs, N) for _ in range(E2E_DEPTH)]
     ins = [capi.make_in_array(batches[j % N_ROTATE]["pairs"]) for j in range(E2E_DEPTH)]
     oarrs = [capi.make_out_array(ob.outs) for ob in oblocks]
@@ -642,7 +645,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
             "config": {"workload": workload_name(args.config, cfg, n_pairs)},
             "method": {"l2": f"{N_ROTATE} rotating resident batches per GPU ({(N_ROTATE * 2 * n_pairs * cfg['width'] * cfg['height'] * 4 // 3) >> 20} MiB of pyramids) > 126 MB L2",
-                       "timing": f"wall clock around K back-to-back steps over {N_ROTATE} resident batches, each on its own handle and stream with pagk_set_device_share({DEVICE_SHARE}) (consecutive steps run beside each other on the device; the end-to-end legs likewise), barrier + device synchronize on both sides, max over ranks; `serial` repeats the K steps on one in-order stream with the device to each launch (share 1), and the kernel ms of `roofline` are CUDA events around every LK launch of that serial leg; stage_ms from one untimed run with per-stage events on"},
+                       "timing": f"wall clock around K back-to-back steps over {N_ROTATE} resident batches, each on its own handle and stream with pagk_set_device_share({DEVICE_SHARE}) (consecutive steps run beside each other on the device; the end-to-end legs with share {E2E_SHARE}), barrier + device synchronize on both sides, max over ranks; `serial` repeats the K steps on one in-order stream with the device to each launch (share 1), and the kernel ms of `roofline` are CUDA events around every LK launch of that serial leg; stage_ms from one untimed run with per-stage events on"},
             "feature_iterations_per_sec": fi_per_s,
             "serial": {"ms_per_step": 1e3 * dt_serial / args.steps, "value": world * args.steps * feats_per_step / dt_serial,
                        "unit": "features/s", "clocks": clocks_serial,

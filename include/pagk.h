@@ -198,8 +198,8 @@ int pagk_synchronize(pagk_handle *h);
 int pagk_set_stage_timing(pagk_handle *h, int on);
 /* Throughput pipelines over several handles on one device (one handle per stream, all kept busy): n_handles > 1 makes a
  * launch of the patch-alignment kernel take 1/n_handles of every SM's CTA slots, so that the launches of the other handles
- * run beside it instead of behind it -- two batches interleaved on an SM halve the share of a launch's tail (config B over
- * three rotating handles: 5 % more features/s).  It is the caller's statement about its own pipeline: a launch that turns
+ * run beside it instead of behind it -- two batches interleaved on an SM halve the share of a launch's tail (config B: 7 % more
+ * features/s over three rotating handles with n_handles = 2, 12 % over four with 3).  It is the caller's statement about its own pipeline: a launch that turns
  * out to be alone on the device runs on 1/n_handles of it.  Default 1 (a launch fills the device); results do not depend on it. */
 int pagk_set_device_share(pagk_handle *h, int n_handles);
 /* device time of the last pagk_run_resident, milliseconds (CUDA events on the handle's stream) */

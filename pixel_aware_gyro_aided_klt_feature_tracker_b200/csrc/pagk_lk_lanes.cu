@@ -1313,7 +1313,10 @@ static int launch_lanes(const unsigned char *images, const PagkGeom &g, const Pa
   if constexpr (HALF <= 5) {
     // PAGK_LK_WARPS=<n> forces the small (n < 12) or the large number of warps per SM
     static const int forced_w = [] { const char *e = getenv("PAGK_LK_WARPS"); return e ? atoi(e) : 0; }();
-    const bool big = forced_w ? forced_w >= PAGK_LANES_WARPS5_BIG : total >= PAGK_LANES_BIG_FEATURES;
+    // (a pipeline of three or more handles, pagk_set_device_share: the 12-warp shape, one of its three CTA slots per launch --
+    // three batches side by side are the independent work that shape needs: 0.611 ms per config-B step over four handles
+    // against 0.635 with two 8-warp launches side by side)
+    const bool big = forced_w ? forced_w >= PAGK_LANES_WARPS5_BIG : (total >= PAGK_LANES_BIG_FEATURES || (share >= 3 && total >= 16384));
     if (big)
       return launch_lanes_w<HALF, AFFINE, PAGK_LANES_WARPS5_BIG>(images, g, pcs, keys_un, out, mode, max_keys, n_max, n_pairs, work_counter,
                                                                   next_counter, progress, epoch, n_sms, tmpl, st, prof, share);
