@@ -601,6 +601,14 @@ def main():
                 "kernel_feature_iterations_per_sec": it_launch / (lk_avg_ms * 1e-3),
                 "hbm": {"achieved": hbm_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / peaks["hbm_gbs"],
                         "peak_source": peaks_kind}}
+    # the same accounting over the pipelined leg as a whole: launches of several handles run beside each other there, so a
+    # launch has no duration of its own -- algorithmic flops of the timed region / its wall time, per GPU, K1, K2, K3a and K4
+    # included in the time (a lower bound of what the alignment kernels reach in that configuration)
+    pipe_ach = (fi_per_s / world) * FP32_FLOP_PER_FEATURE_ITER.get(half, 70.0 * (2 * half + 1) ** 2) / 1e12
+    roofline["pipelined_whole_step"] = {"achieved": pipe_ach, "unit": "TFLOP/s", "frac": pipe_ach / fp32_peak,
+                                        "frac_of_non_fma_peak": pipe_ach / (fp32_peak / 2),
+                                        "note": f"feature-iterations of the timed region of `value` x flop per unit / wall time, per GPU; "
+                                                f"{N_ROTATE} handles with pagk_set_device_share({DEVICE_SHARE})"}
 
     # ---- CPU baseline + parity on the first batch (rank 0, bounded sample) ------------------------------
     cpu_baseline, parity = None, None
