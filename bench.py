@@ -598,6 +598,9 @@ def main():
                 "peak_source": f"148 SM x 128 lanes x 2 x {peaks.get('sm_max_mhz', 1965.0):.0f} MHz ({peaks_kind} sm_max_mhz); "
                                "FMA contraction is forbidden by bit-parity, so half of it is the reachable ceiling",
                 "kernel_ms": lk_avg_ms, "kernel_launches_timed": lk_n, "feature_iterations_per_launch": it_launch,
+                "kernel_ms_leg": "serial: one launch at a time with the device to itself (compare with serial.ms_per_step, not with "
+                                 "ms_per_step: in the pipelined leg the launches of different handles run beside each other, so a step "
+                                 "takes less wall time than one launch lasts)",
                 "kernel_feature_iterations_per_sec": it_launch / (lk_avg_ms * 1e-3),
                 "hbm": {"achieved": hbm_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / peaks["hbm_gbs"],
                         "peak_source": peaks_kind}}
