@@ -4,9 +4,10 @@
 //   images   [2 * max_pairs] slots; a slot holds every pyramid level of one image, each level with a
 //            4-byte aligned row pitch, its wrap column and guard row (PagkLevelGeom), level bases
 //            256-byte aligned.  Slot 2p is the reference image of pair p, slot 2p+1 the current image.
-//   tmpl     [max_pairs * max_keys][levels] template records of the alignment kernel (pagk_lk_lanes.cu)
-//   keys     float2 [max_pairs][max_keys] x 2 (undistorted, raw)
-//   consts   PagkPairConst [max_pairs]   (KRK^-1, r31..r33, intrinsics, distortion, n_keys)
+//   tmpl     [levels][pairs * max_keys] template records of the alignment kernel, level-major (pagk_lk_lanes.cu)
+//   handover [max_pairs * max_keys] 32-byte records: a feature's position and pass count from one level to the next
+//   in       one block like the pinned staging block: PagkPairConst [max_pairs] (KRK^-1, r31..r33, intrinsics,
+//            distortion, n_keys), then float2 [max_pairs][max_keys] x 2 (undistorted keypoints, raw keypoints)
 //   results  structure of arrays [max_pairs][max_keys] (PagkOutPtrs), PagkPairResult [max_pairs]
 // Host side: one pinned staging block mirrors keys+consts (upload) and one mirrors the results
 // (download) so that a batch moves with a handful of large copies.
