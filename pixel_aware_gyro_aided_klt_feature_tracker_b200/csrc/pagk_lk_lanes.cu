@@ -1277,7 +1277,8 @@ static int launch_lanes_w(const unsigned char *images, const PagkGeom &g, const 
   // runs on 1/n of the device: the setting is the caller's statement about its own pipeline, not a heuristic.)
   // (only where the CTA slots divide evenly: the 12-warp shape of large batches has three, and a batch that large has the
   // independent work to fill the device by itself)
-  if (share > 1 && total >= 16384 && C::CTAS_SM % share == 0) ctas = (long long)n_sms * (C::CTAS_SM / share);
+  const int eff_share = share > C::CTAS_SM ? C::CTAS_SM : share;  // more handles than CTA slots: one slot each
+  if (eff_share > 1 && total >= 16384 && C::CTAS_SM % eff_share == 0) ctas = (long long)n_sms * (C::CTAS_SM / eff_share);
   // A small batch is spread over all warps (lane_cap features per warp at a time) instead of filling a few: a warp
   // with a handful of live lanes runs them through the pixel-parallel pass, several times faster per iteration
   // than a lockstep pass, which is what the latency of a single frame pair is made of.

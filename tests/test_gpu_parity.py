@@ -360,7 +360,7 @@ def test_level_granular_work_items_forced_on_small_batches():
     assert " passed" in r.stdout and "failed" not in r.stdout
 
 
-@pytest.mark.parametrize("share", [2, 3])
+@pytest.mark.parametrize("share", [2, 3, 5])
 def test_device_share_changes_only_the_launch_shape(cuda_lib, oracle, share):
     """pagk_set_device_share(h, n): a launch of the alignment kernel takes 1/n of every SM's CTA slots (the other handles of
     a pipeline run beside it); the results are the same bit for bit, also with two handles in flight at once"""
